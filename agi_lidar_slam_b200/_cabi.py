@@ -1,0 +1,368 @@
+"""ctypes binding of liblio_b200.so (include/lio_b200.h).
+
+This is the ONLY way Python reaches the hot path: there is no NumPy/torch fallback.  Importing this module
+without the built library raises; creating a context without a B200-class GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "liblio_b200.so"
+
+LIO_OK = 0
+LIO_E_INVALID, LIO_E_NO_DEVICE, LIO_E_CUDA, LIO_E_CAPACITY, LIO_E_EMPTY_MAP, LIO_E_VOXEL_RANGE = -1, -2, -3, -4, -5, -6
+_ERR_NAMES = {
+    -1: "LIO_E_INVALID",
+    -2: "LIO_E_NO_DEVICE",
+    -3: "LIO_E_CUDA",
+    -4: "LIO_E_CAPACITY",
+    -5: "LIO_E_EMPTY_MAP",
+    -6: "LIO_E_VOXEL_RANGE",
+}
+
+STATE_DOUBLES = 26  # lio_state
+POSE_DOUBLES = 22  # lio_pose6d
+BLOB = 92
+
+
+class LioError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{_ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Caps(C.Structure):
+    _fields_ = [
+        ("max_scan_points", C.c_int64),
+        ("max_down_points", C.c_int64),
+        ("max_map_points", C.c_int64),
+        ("map_cell", C.c_float),
+        ("knn_max_d2", C.c_float),
+        ("plane_thr", C.c_float),
+        ("map_downsample", C.c_float),
+    ]
+
+
+# every symbol include/lio_b200.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = [
+    "lio_abi_version", "lio_default_caps", "lio_create", "lio_destroy", "lio_set_stream", "lio_synchronize",
+    "lio_last_error", "lio_launch_count", "lio_map_build", "lio_map_add", "lio_map_delete_boxes", "lio_map_size",
+    "lio_map_dump", "lio_knn5", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
+    "lio_update_pass", "lio_update_scan", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
+    "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
+    "lio_blob_download",
+    "lio_get_neighbors", "lio_map_incremental", "lio_predict", "lio_boxplus", "lio_boxminus",
+]  # fmt: skip
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load liblio_b200.so; fail loudly when it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C agi_lidar_slam_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+    P = C.POINTER
+    sig = {
+        "lio_abi_version": (C.c_int, []),
+        "lio_default_caps": (None, [P(Caps)]),
+        "lio_create": (C.c_int, [C.c_int, P(Caps), P(vp)]),
+        "lio_destroy": (None, [vp]),
+        "lio_set_stream": (C.c_int, [vp, vp]),
+        "lio_synchronize": (C.c_int, [vp]),
+        "lio_last_error": (C.c_char_p, [vp]),
+        "lio_launch_count": (i64, [vp]),
+        "lio_map_build": (C.c_int, [vp, vp, i64, C.c_int]),
+        "lio_map_add": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, P(i32)]),
+        "lio_map_delete_boxes": (C.c_int, [vp, vp, C.c_int, P(i32)]),
+        "lio_map_size": (C.c_int, [vp, P(i64), P(i64)]),
+        "lio_map_dump": (C.c_int, [vp, vp, vp, i64, P(i64)]),
+        "lio_knn5": (C.c_int, [vp, vp, i64, vp, vp, vp]),
+        "lio_scan_preprocess": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, f32, vp, P(i64), vp, vp]),
+        "lio_scan_preprocess_resident": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, f32, P(i64)]),
+        "lio_scan_upload": (C.c_int, [vp, vp, i64, C.c_int]),
+        "lio_update_pass": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, P(i32)]),
+        "lio_update_scan": (C.c_int, [vp, vp, vp, f64, C.c_int, C.c_int, P(i32), P(i32)]),
+        "lio_state_upload": (C.c_int, [vp, vp, vp]),
+        "lio_state_download": (C.c_int, [vp, vp, vp, P(i32), P(i32)]),
+        "lio_update_enqueue": (C.c_int, [vp, f64, C.c_int, C.c_int, C.c_int]),
+        "lio_update_begin": (C.c_int, [vp, C.c_int]),
+        "lio_update_pass_enqueue": (C.c_int, [vp, C.c_int, f32, f32]),
+        "lio_update_step_enqueue": (C.c_int, [vp, f64, C.c_int]),
+        "lio_blob_device_ptr": (vp, [vp]),
+        "lio_blob_download": (C.c_int, [vp, vp]),
+        "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+        "lio_map_incremental": (C.c_int, [vp, vp, f32, C.c_int, vp]),
+        "lio_predict": (C.c_int, [vp, vp, f64, vp, vp, vp]),
+        "lio_boxplus": (C.c_int, [vp, vp, vp]),
+        "lio_boxminus": (C.c_int, [vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library drift
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def default_caps() -> Caps:
+    caps = Caps()
+    load_library().lio_default_caps(C.byref(caps))
+    return caps
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape_last=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape_last is not None and (a.ndim != 2 or a.shape[1] != shape_last):
+        raise ValueError(f"expected an (n, {shape_last}) float32 array, got {a.shape}")
+    return a
+
+
+def _state(x):
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    if x.size != STATE_DOUBLES:
+        raise ValueError("state must hold 26 doubles (pos3, rot4 wxyz, R_LI4 wxyz, t_LI3, vel3, bg3, ba3, grav3)")
+    return x
+
+
+def _points(pts):
+    """(n,4) float32 -> stride 16; (n,12) float32 -> stride 48 (pcl::PointXYZINormal)."""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    if pts.ndim != 2 or pts.shape[1] not in (4, 12):
+        raise ValueError("points must be (n,4) [x,y,z,w] or (n,12) [PointXYZINormal] float32")
+    return pts, pts.shape[1] * 4
+
+
+class Context:
+    """One lio_ctx (one GPU).  Not re-entrant, like the reference's single application thread."""
+
+    def __init__(self, device: int = 0, caps: Caps | None = None, **cap_overrides):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        caps = caps or default_caps()
+        for k, v in cap_overrides.items():
+            if not hasattr(caps, k):
+                raise TypeError(f"unknown lio_caps field {k}")
+            setattr(caps, k, v)
+        self.caps = caps
+        rc = self._lib.lio_create(device, C.byref(caps), C.byref(self._h))
+        if rc != LIO_OK or not self._h:
+            self._h = C.c_void_p()
+            raise LioError(rc, "lio_create failed (needs a visible sm_100 GPU; there is no CPU fallback)")
+
+    # -- plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lio_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != LIO_OK:
+            raise LioError(rc, (self._lib.lio_last_error(self._h) or b"").decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.lio_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._lib.lio_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.lio_launch_count(self._h))
+
+    # -- map
+    def map_build(self, pts):
+        pts, stride = _points(pts)
+        self._check(self._lib.lio_map_build(self._h, _ptr(pts), pts.shape[0], stride))
+
+    def map_add(self, pts, downsample_on: bool) -> int:
+        pts, stride = _points(pts)
+        n = C.c_int32(0)
+        self._check(self._lib.lio_map_add(self._h, _ptr(pts), pts.shape[0], stride, int(downsample_on), C.byref(n)))
+        return n.value
+
+    def map_delete_boxes(self, boxes6) -> int:
+        b = _f32(boxes6).reshape(-1, 6)
+        n = C.c_int32(0)
+        self._check(self._lib.lio_map_delete_boxes(self._h, _ptr(b), b.shape[0], C.byref(n)))
+        return n.value
+
+    def map_size(self):
+        t, v = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.lio_map_size(self._h, C.byref(t), C.byref(v)))
+        return t.value, v.value
+
+    def map_dump(self):
+        n = C.c_int64(0)
+        self._check(self._lib.lio_map_dump(self._h, None, None, 0, C.byref(n)))
+        xyz = np.zeros((n.value, 3), np.float32)
+        ids = np.zeros(n.value, np.int32)
+        if n.value:
+            self._check(self._lib.lio_map_dump(self._h, _ptr(xyz), _ptr(ids), n.value, C.byref(n)))
+        return xyz, ids
+
+    def knn5(self, q_xyz, want_xyz=True):
+        q = _f32(q_xyz, 3)
+        m = q.shape[0]
+        idx = np.full((m, 5), -1, np.int32)
+        d2 = np.full((m, 5), np.inf, np.float32)
+        nbr = np.zeros((m, 5, 3), np.float32) if want_xyz else None
+        self._check(self._lib.lio_knn5(self._h, _ptr(q), m, _ptr(idx), _ptr(d2), _ptr(nbr)))
+        return idx, d2, nbr
+
+    # -- scan
+    def scan_preprocess(self, raw_pts, poses=None, end_state=None, leaf=0.5, want_undistorted=False, want_keys=False,
+                        resident=False):
+        raw, stride = _points(raw_pts)
+        n = raw.shape[0]
+        if poses is not None:
+            poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, POSE_DOUBLES)
+            n_poses = poses.shape[0]
+            end = _state(end_state)
+        else:
+            n_poses, end = 0, None
+        m = C.c_int64(0)
+        if resident:
+            self._check(self._lib.lio_scan_preprocess_resident(self._h, _ptr(raw), n, stride, _ptr(poses), n_poses,
+                                                               _ptr(end), leaf, C.byref(m)))
+            return m.value
+        out = np.zeros((int(self.caps.max_down_points), raw.shape[1]), np.float32)
+        und = np.zeros((n, 4), np.float32) if want_undistorted else None
+        keys = np.zeros((n, 3), np.int32) if want_keys else None
+        self._check(self._lib.lio_scan_preprocess(self._h, _ptr(raw), n, stride, _ptr(poses), n_poses, _ptr(end), leaf,
+                                                  _ptr(out), C.byref(m), _ptr(und), _ptr(keys)))
+        return out[: m.value].copy(), und, keys
+
+    def scan_upload(self, down_pts):
+        pts, stride = _points(down_pts)
+        self._check(self._lib.lio_scan_upload(self._h, _ptr(pts), pts.shape[0], stride))
+
+    # -- update
+    def update_pass(self, x, do_search: bool, extrinsic_est: bool):
+        x = _state(x)
+        blob = np.zeros(90, np.float64)
+        nv = C.c_int32(0)
+        self._check(self._lib.lio_update_pass(self._h, _ptr(x), int(do_search), int(extrinsic_est), _ptr(blob),
+                                              C.byref(nv)))
+        return blob, nv.value
+
+    def update_scan(self, x, P, R=0.001, max_iter=4, extrinsic_est=False):
+        x = _state(x).copy()
+        P = np.ascontiguousarray(P, dtype=np.float64).reshape(24, 24).copy()
+        nv, npass = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.lio_update_scan(self._h, _ptr(x), _ptr(P), R, max_iter, int(extrinsic_est),
+                                              C.byref(nv), C.byref(npass)))
+        return x, P, nv.value, npass.value
+
+    def state_upload(self, x, P):
+        x = _state(x)
+        P = np.ascontiguousarray(P, dtype=np.float64).reshape(576)
+        self._check(self._lib.lio_state_upload(self._h, _ptr(x), _ptr(P)))
+
+    def state_download(self):
+        x = np.zeros(STATE_DOUBLES, np.float64)
+        P = np.zeros((24, 24), np.float64)
+        nv, npass = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.lio_state_download(self._h, _ptr(x), _ptr(P), C.byref(nv), C.byref(npass)))
+        return x, P, nv.value, npass.value
+
+    def update_enqueue(self, R=0.001, max_iter=4, extrinsic_est=False, from_snapshot=False):
+        self._check(self._lib.lio_update_enqueue(self._h, R, max_iter, int(extrinsic_est), int(from_snapshot)))
+
+    def update_begin(self, from_snapshot=False):
+        self._check(self._lib.lio_update_begin(self._h, int(from_snapshot)))
+
+    def update_pass_enqueue(self, extrinsic_est=False, x_own_min=-np.inf, x_own_max=np.inf):
+        self._check(self._lib.lio_update_pass_enqueue(self._h, int(extrinsic_est), x_own_min, x_own_max))
+
+    def update_step_enqueue(self, R=0.001, max_iter=4):
+        self._check(self._lib.lio_update_step_enqueue(self._h, R, max_iter))
+
+    @property
+    def blob_device_ptr(self) -> int:
+        return int(self._lib.lio_blob_device_ptr(self._h) or 0)
+
+    def blob_download(self):
+        b = np.zeros(BLOB, np.float64)
+        self._check(self._lib.lio_blob_download(self._h, _ptr(b)))
+        return b
+
+    def get_neighbors(self, m: int):
+        idx = np.full((m, 5), -1, np.int32)
+        d2 = np.full((m, 5), np.inf, np.float32)
+        nbr = np.zeros((m, 5, 3), np.float32)
+        world = np.zeros((m, 3), np.float32)
+        sel = np.zeros(m, np.uint8)
+        nv = np.zeros((m, 4), np.float32)
+        self._check(self._lib.lio_get_neighbors(self._h, _ptr(idx), _ptr(d2), _ptr(nbr), _ptr(world), _ptr(sel),
+                                                _ptr(nv)))
+        return dict(idx=idx, d2=d2, nbr=nbr, world=world, selected=sel, normvec=nv)
+
+    def map_incremental(self, x, filter_size_map=0.5, ekf_inited=True):
+        x = _state(x)
+        counts = np.zeros(3, np.int32)
+        self._check(self._lib.lio_map_incremental(self._h, _ptr(x), filter_size_map, int(ekf_inited), _ptr(counts)))
+        return counts
+
+
+# -- host-side sequential pieces (no context needed)
+def predict(x, P, dt, Q, acc, gyro):
+    lib = load_library()
+    x = _state(x).copy()
+    P = np.ascontiguousarray(P, dtype=np.float64).reshape(24, 24).copy()
+    Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(144)
+    acc = np.ascontiguousarray(acc, dtype=np.float64)
+    gyro = np.ascontiguousarray(gyro, dtype=np.float64)
+    rc = lib.lio_predict(_ptr(x), _ptr(P), float(dt), _ptr(Q), _ptr(acc), _ptr(gyro))
+    if rc:
+        raise LioError(rc, "lio_predict")
+    return x, P
+
+
+def boxplus(x, f):
+    lib = load_library()
+    x = _state(x)
+    f = np.ascontiguousarray(f, dtype=np.float64).reshape(24)
+    out = np.zeros(STATE_DOUBLES)
+    rc = lib.lio_boxplus(_ptr(x), _ptr(f), _ptr(out))
+    if rc:
+        raise LioError(rc, "lio_boxplus")
+    return out
+
+
+def boxminus(x1, x2):
+    lib = load_library()
+    x1, x2 = _state(x1), _state(x2)
+    out = np.zeros(24)
+    rc = lib.lio_boxminus(_ptr(x1), _ptr(x2), _ptr(out))
+    if rc:
+        raise LioError(rc, "lio_boxminus")
+    return out

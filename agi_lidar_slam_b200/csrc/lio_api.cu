@@ -1,0 +1,745 @@
+// extern "C" surface of liblio_b200.so (include/lio_b200.h): context, staging copies, graph capture of the whole
+// update, and the small host-side sequential pieces (predict / boxplus / boxminus).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "lio_ctx.cuh"
+
+namespace lio {
+size_t preprocess_sort_bytes(int64_t n);
+int preprocess_init_tables(lio_ctx* c);
+int launch_reduce_blob_mode(lio_ctx* c, int host_search);
+int ensure_tables(lio_ctx* c);
+
+__global__ void set_w_kernel(float4* dst, const float* w, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i].w = w[i];
+}
+__global__ void set_scan_m_kernel(int* d, int m) { *d = m; }
+__global__ void xyz_to_float4_kernel(const float* xyz, float4* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
+}
+
+static uint32_t pow2_at_least(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return (uint32_t)p;
+}
+
+// Copy n point records from host memory into a device float4 array: x,y,z and w = the float at byte offset w_off
+// of each record (stride 16: w_off is 12).  aux (optional) receives the float at aux_off.
+static int stage_points(lio_ctx* c, const void* src, int64_t n, int stride, int w_off, float4* dst, int aux_off,
+                        float* aux, float* tmp_w) {
+  if (n <= 0) return LIO_OK;
+  const char* s = static_cast<const char*>(src);
+  if (stride == 16) {
+    LIO_CHECK(c, cudaMemcpyAsync(dst, s, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    return LIO_OK;
+  }
+  LIO_CHECK(c, cudaMemcpy2DAsync(dst, 16, s, stride, 16, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  LIO_CHECK(c, cudaMemcpy2DAsync(tmp_w, 4, s + w_off, stride, 4, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  set_w_kernel<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(dst, tmp_w, (int)n);
+  c->launches++;
+  if (aux) LIO_CHECK(c, cudaMemcpy2DAsync(aux, 4, s + aux_off, stride, 4, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  return LIO_OK;
+}
+
+static int refresh_scan_m(lio_ctx* c) {
+  if (c->scan_m >= 0) return LIO_OK;
+  int m = 0;
+  LIO_CHECK(c, cudaMemcpyAsync(&m, c->d_scan_m, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  c->scan_m = m;
+  return LIO_OK;
+}
+
+static int enqueue_update_body(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot) {
+  int rc = launch_begin(c, max_iter, from_snapshot);
+  if (rc) return rc;
+  for (int it = -1; it < max_iter; ++it) {
+    rc = launch_pass(c, -1, ext, -INFINITY, INFINITY);
+    if (rc) return rc;
+    rc = launch_solve(c, R, 0);
+    if (rc) return rc;
+  }
+  return LIO_OK;
+}
+
+}  // namespace lio
+
+using namespace lio;
+
+extern "C" {
+
+int lio_abi_version(void) { return LIO_ABI_VERSION; }
+
+void lio_default_caps(lio_caps* caps) {
+  caps->max_scan_points = 262144;
+  caps->max_down_points = 100000;  // esekfom.hpp:23-29
+  caps->max_map_points = 4194304;
+  caps->map_cell = 1.0f;
+  caps->knn_max_d2 = 5.0f;      // esekfom.hpp:147
+  caps->plane_thr = 0.1f;       // esekfom.hpp:157
+  caps->map_downsample = 0.5f;  // filter_size_map (launch files)
+}
+
+const char* lio_last_error(lio_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t lio_launch_count(lio_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+#define ALLOC(ptr, bytes) LIO_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes)))
+
+static int create_impl(lio_ctx* c) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= c->device) {
+    c->err = "no usable CUDA device (this library has no CPU fallback)";
+    return LIO_E_NO_DEVICE;
+  }
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  LIO_CHECK(c, cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10) {
+    c->err = "device is not sm_100-class (kernels are built for sm_100a only)";
+    return LIO_E_NO_DEVICE;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  LIO_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  const lio_caps& k = c->caps;
+  const char* env = getenv("LIO_QPW_SEARCH");
+  if (env) {
+    const int v = atoi(env);
+    if (v == 4 || v == 8 || v == 16 || v == 32) c->qpw_search = v;
+  }
+  env = getenv("LIO_NO_GRAPH");
+  if (env && atoi(env)) c->use_graph = false;
+
+  // map
+  c->hash_cap = pow2_at_least((uint64_t)k.max_map_points * 2);
+  c->map.hash_mask = c->hash_cap - 1;
+  c->map.pool_cap = (uint32_t)std::min<uint64_t>((uint64_t)k.max_map_points * 4, 0xFFFFFFF0ull);
+  c->map.cell = k.map_cell;
+  c->map.inv_cell = 1.0f / k.map_cell;
+  c->knn_rings = (int)ceil(sqrt((double)k.knn_max_d2) / (double)k.map_cell);
+  if (c->knn_rings < 1) c->knn_rings = 1;
+  ALLOC(c->map.table, sizeof(CellEntry) * (size_t)c->hash_cap);
+  ALLOC(c->map.cell_cap, 4 * (size_t)c->hash_cap);
+  ALLOC(c->map.cell_pend, 4 * (size_t)c->hash_cap);
+  ALLOC(c->map.cell_base, 4 * (size_t)c->hash_cap);
+  ALLOC(c->map.pool, sizeof(float4) * (size_t)c->map.pool_cap);
+  ALLOC(c->map.counters, 4 * 8);
+  c->batch_cap = std::max<int64_t>(k.max_map_points, k.max_down_points);
+  ALLOC(c->d_batch_pts, sizeof(float4) * (size_t)c->batch_cap);
+  ALLOC(c->d_batch_slot, 4 * (size_t)c->batch_cap);
+  ALLOC(c->d_batch_rank, 4 * (size_t)c->batch_cap);
+  ALLOC(c->d_batch_flag, (size_t)c->batch_cap);
+  c->vox_cap = pow2_at_least((uint64_t)std::max<int64_t>(k.max_down_points, 131072) * 2);
+  ALLOC(c->d_vox_best, 8 * (size_t)c->vox_cap);
+  ALLOC(c->d_vox_key, 8 * (size_t)c->vox_cap);
+
+  // scan
+  const size_t M = (size_t)k.max_down_points;
+  ALLOC(c->d_scan_m, 4);
+  ALLOC(c->d_body, sizeof(float4) * M);
+  ALLOC(c->d_world, sizeof(float4) * M);
+  ALLOC(c->d_near, sizeof(float4) * M * LIO_K);
+  ALLOC(c->d_near_d2, 4 * M * LIO_K);
+  ALLOC(c->d_near_cnt, 4 * M);
+  ALLOC(c->d_selected, M);
+  ALLOC(c->d_normvec, sizeof(float4) * M);
+  c->max_tiles = (int)((M + 15) / 16);
+  ALLOC(c->d_partials, 8 * (size_t)LIO_BLOB * c->max_tiles);
+  ALLOC(c->d_blob, 8 * LIO_BLOB);
+  ALLOC(c->d_cls, M);
+  ALLOC(c->d_add_a, sizeof(float4) * M);
+  ALLOC(c->d_add_b, sizeof(float4) * M);
+  LIO_CHECK(c, cudaMemset(c->d_scan_m, 0, 4));
+  LIO_CHECK(c, cudaMemset(c->d_selected, 0, M));
+  LIO_CHECK(c, cudaMemset(c->d_near_cnt, 0, 4 * M));
+  LIO_CHECK(c, cudaMemset(c->d_blob, 0, 8 * LIO_BLOB));
+
+  // filter state
+  ALLOC(c->d_x, sizeof(StateD));
+  ALLOC(c->d_xprop, sizeof(StateD));
+  ALLOC(c->d_x0, sizeof(StateD));
+  ALLOC(c->d_P, 8 * 576);
+  ALLOC(c->d_P0, 8 * 576);
+  ALLOC(c->d_ctrl, sizeof(Ctrl));
+  ALLOC(c->d_dx, 8 * 24);
+  LIO_CHECK(c, cudaMemset(c->d_ctrl, 0, sizeof(Ctrl)));
+  c->h_pinned_bytes = 8 * (26 + 576 + LIO_BLOB + 64);
+  LIO_CHECK(c, cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
+
+  // preprocess
+  const size_t N = (size_t)k.max_scan_points;
+  ALLOC(c->d_raw, sizeof(float4) * N);
+  ALLOC(c->d_raw_aux, 4 * N);
+  ALLOC(c->d_undist, sizeof(float4) * N);
+  ALLOC(c->d_vkeys, 12 * N);
+  ALLOC(c->d_poses, sizeof(lio_pose6d) * 128);
+  c->svox_cap = pow2_at_least((uint64_t)N * 2);
+  ALLOC(c->d_svox_key, 8 * (size_t)c->svox_cap);
+  ALLOC(c->d_svox_acc, 8 * 5 * (size_t)c->svox_cap);
+  ALLOC(c->d_svox_cnt, 4 * (size_t)c->svox_cap);
+  ALLOC(c->d_sort_keys_in, 8 * N);
+  ALLOC(c->d_sort_keys_out, 8 * N);
+  ALLOC(c->d_sort_vals_in, 4 * N);
+  ALLOC(c->d_sort_vals_out, 4 * N);
+  c->cub_tmp_bytes = preprocess_sort_bytes((int64_t)N);
+  ALLOC(c->d_cub_tmp, c->cub_tmp_bytes + 16);
+  ALLOC(c->d_prep_counters, 4 * 16);
+  LIO_CHECK(c, cudaMemset(c->d_prep_counters, 0, 4 * 16));
+
+  int rc = ensure_tables(c);
+  if (rc) return rc;
+  rc = map_reset(c);
+  if (rc) return rc;
+  rc = preprocess_init_tables(c);
+  if (rc) return rc;
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  return LIO_OK;
+}
+
+int lio_create(int device, const lio_caps* caps, lio_ctx** out) {
+  if (!out) return LIO_E_INVALID;
+  *out = nullptr;
+  lio_ctx* c = new lio_ctx();
+  c->device = device;
+  if (caps)
+    c->caps = *caps;
+  else
+    lio_default_caps(&c->caps);
+  if (c->caps.max_scan_points <= 0 || c->caps.max_down_points <= 0 || c->caps.max_map_points <= 0 ||
+      !(c->caps.map_cell > 0.f) || !(c->caps.knn_max_d2 > 0.f) || !(c->caps.map_downsample > 0.f)) {
+    delete c;
+    return LIO_E_INVALID;
+  }
+  const int rc = create_impl(c);
+  if (rc != LIO_OK) {
+    fprintf(stderr, "lio_create failed: %s\n", c->err.c_str());
+    lio_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return LIO_OK;
+}
+
+void lio_destroy(lio_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& g : c->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  void* ptrs[] = {c->map.table,   c->map.cell_cap,  c->map.cell_pend, c->map.cell_base, c->map.pool,
+                  c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
+                  c->d_vox_best,  c->d_vox_key,     c->d_scan_m,      c->d_body,        c->d_world,
+                  c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,
+                  c->d_partials,  c->d_blob,        c->d_cls,         c->d_add_a,       c->d_add_b,
+                  c->d_x,         c->d_xprop,       c->d_x0,          c->d_P,           c->d_P0,
+                  c->d_ctrl,      c->d_dx,          c->d_raw,         c->d_raw_aux,     c->d_undist,
+                  c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
+                  c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
+                  c->d_prep_counters};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int lio_set_stream(lio_ctx* c, void* cuda_stream) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = static_cast<cudaStream_t>(cuda_stream);
+  c->own_stream = false;
+  for (auto& g : c->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = lio_ctx::GraphSlot();
+  }
+  return LIO_OK;
+}
+
+int lio_synchronize(lio_ctx* c) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  return LIO_OK;
+}
+
+// ---------------------------------------------------------------- map
+int lio_map_build(lio_ctx* c, const void* pts, int64_t n, int stride) {
+  if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !pts)) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (n > c->caps.max_map_points) {
+    c->err = "Build: more points than lio_caps.max_map_points";
+    return LIO_E_CAPACITY;
+  }
+  int rc = map_reset(c);
+  if (rc) return rc;
+  if (n == 0) return LIO_OK;  // KD_TREE::Build returns before creating a root (ikd_Tree.cpp:359)
+  rc = stage_points(c, pts, n, stride, 32, c->d_batch_pts, 0, nullptr, reinterpret_cast<float*>(c->d_batch_slot));
+  if (rc) return rc;
+  rc = map_append_batch(c, c->d_batch_pts, n, 0, nullptr);
+  if (rc) return rc;
+  c->next_id = (int32_t)n;
+  c->map_built = true;
+  return LIO_OK;
+}
+
+int lio_map_add(lio_ctx* c, const void* pts, int64_t n, int stride, int downsample_on, int32_t* n_added) {
+  if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !pts)) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (n_added) *n_added = 0;
+  if (!c->map_built) {
+    c->err = "Add_Points on an empty map (the reference dereferences Root_Node here)";
+    return LIO_E_EMPTY_MAP;
+  }
+  if (n == 0) return LIO_OK;
+  if (n > c->batch_cap) {
+    c->err = "Add_Points batch too large";
+    return LIO_E_CAPACITY;
+  }
+  int rc = stage_points(c, pts, n, stride, 32, c->d_batch_pts, 0, nullptr, reinterpret_cast<float*>(c->d_batch_slot));
+  if (rc) return rc;
+  if (downsample_on) {
+    rc = map_add_downsample(c, c->d_batch_pts, n, c->next_id, n_added);
+  } else {
+    rc = map_append_batch(c, c->d_batch_pts, n, c->next_id, nullptr);
+    if (n_added) *n_added = (int32_t)n;
+  }
+  if (rc) return rc;
+  c->next_id += (int32_t)n;
+  return LIO_OK;
+}
+
+int lio_map_delete_boxes(lio_ctx* c, const float* boxes6, int nb, int32_t* n_deleted) {
+  if (!c || nb < 0 || (nb > 0 && !boxes6)) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  return map_delete_boxes(c, boxes6, nb, n_deleted);
+}
+
+int lio_map_size(lio_ctx* c, int64_t* total, int64_t* valid) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  uint32_t h[8];
+  LIO_CHECK(c, cudaMemcpyAsync(h, c->map.counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (total) *total = c->next_id;
+  if (valid) *valid = h[2];
+  return LIO_OK;
+}
+
+int lio_map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  return map_dump(c, xyz, ids, cap, n);
+}
+
+static int download_neighbors(lio_ctx* c, int64_t m, int32_t* idx5, float* d2_5, float* nbr_xyz) {
+  if (m <= 0) return LIO_OK;
+  if (idx5 || nbr_xyz) {
+    std::vector<float4> h((size_t)m * LIO_K);
+    LIO_CHECK(c, cudaMemcpyAsync(h.data(), c->d_near, sizeof(float4) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+    LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (size_t j = 0; j < h.size(); ++j) {
+      if (idx5) memcpy(&idx5[j], &h[j].w, 4);
+      if (nbr_xyz) {
+        nbr_xyz[3 * j] = h[j].x;
+        nbr_xyz[3 * j + 1] = h[j].y;
+        nbr_xyz[3 * j + 2] = h[j].z;
+      }
+    }
+  }
+  if (d2_5) {
+    LIO_CHECK(c, cudaMemcpyAsync(d2_5, c->d_near_d2, 4 * (size_t)m * LIO_K, cudaMemcpyDeviceToHost, c->stream));
+    LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  return LIO_OK;
+}
+
+int lio_knn5(lio_ctx* c, const float* q_xyz, int64_t m, int32_t* idx5, float* d2_5, float* nbr_xyz) {
+  if (!c || m < 0 || (m > 0 && !q_xyz)) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  // processed in chunks of max_down_points through the scan-sized buffers (this invalidates cached neighbours)
+  const int64_t chunk = c->caps.max_down_points;
+  for (int64_t off = 0; off < m; off += chunk) {
+    const int64_t cm = std::min(chunk, m - off);
+    float* d_tmp = reinterpret_cast<float*>(c->d_add_a);  // 16 B/pt scratch >= 12 B/pt needed
+    LIO_CHECK(c, cudaMemcpyAsync(d_tmp, q_xyz + 3 * off, 12 * (size_t)cm, cudaMemcpyHostToDevice, c->stream));
+    xyz_to_float4_kernel<<<(int)((cm + 255) / 256), 256, 0, c->stream>>>(d_tmp, c->d_world, (int)cm);
+    c->launches++;
+    int rc = launch_knn_batch(c, c->d_world, cm);
+    if (rc) return rc;
+    rc = download_neighbors(c, cm, idx5 ? idx5 + off * LIO_K : nullptr, d2_5 ? d2_5 + off * LIO_K : nullptr,
+                            nbr_xyz ? nbr_xyz + off * LIO_K * 3 : nullptr);
+    if (rc) return rc;
+  }
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  return LIO_OK;
+}
+
+// ---------------------------------------------------------------- scan
+static int preprocess_common(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses,
+                             int n_poses, const lio_state* end_state, float leaf) {
+  if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !raw_pts) || !(leaf > 0.f)) return LIO_E_INVALID;
+  if (n_poses >= 2 && (!poses || !end_state)) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (n > c->caps.max_scan_points) {
+    c->err = "scan larger than lio_caps.max_scan_points";
+    return LIO_E_CAPACITY;
+  }
+  if (n_poses > 128) {
+    c->err = "more than 128 IMU poses";
+    return LIO_E_CAPACITY;
+  }
+  // stride 48: time = curvature (offset 36), intensity (offset 32) rides along as aux
+  int rc = stage_points(c, raw_pts, n, stride, 36, c->d_raw, 32, c->d_raw_aux, reinterpret_cast<float*>(c->d_vkeys));
+  if (rc) return rc;
+  if (n_poses >= 2)
+    LIO_CHECK(c, cudaMemcpyAsync(c->d_poses, poses, sizeof(lio_pose6d) * n_poses, cudaMemcpyHostToDevice, c->stream));
+  return preprocess(c, n, n_poses >= 2 ? n_poses : 0, end_state, leaf, stride == 48);
+}
+
+static int preprocess_status(lio_ctx* c, int64_t* m) {
+  int h[8];
+  LIO_CHECK(c, cudaMemcpyAsync(h, c->d_prep_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (h[7] == 1) {
+    c->err = "scan voxel hash full";
+    return LIO_E_CAPACITY;
+  }
+  if (h[7] == 2) {
+    c->err = "more occupied voxels than lio_caps.max_down_points";
+    return LIO_E_CAPACITY;
+  }
+  c->scan_m = std::min<int64_t>(h[0], c->caps.max_down_points);
+  if (m) *m = c->scan_m;
+  if (h[0] > 0) {
+    const int64_t dx = (int64_t)h[4] - h[1] + 1, dy = (int64_t)h[5] - h[2] + 1, dz = (int64_t)h[6] - h[3] + 1;
+    if (dx * dy * dz > (int64_t)INT32_MAX) {
+      c->err = "VoxelGrid: leaf size too small for the scan extent (index would overflow)";
+      return LIO_E_VOXEL_RANGE;
+    }
+  }
+  return LIO_OK;
+}
+
+int lio_scan_preprocess(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses, int n_poses,
+                        const lio_state* end_state, float leaf, void* out_pts, int64_t* m, float* undistorted,
+                        int32_t* voxel_key_xyz) {
+  int rc = preprocess_common(c, raw_pts, n, stride, poses, n_poses, end_state, leaf);
+  if (rc) return rc;
+  int64_t mm = 0;
+  rc = preprocess_status(c, &mm);
+  if (m) *m = mm;
+  if (rc) return rc;
+  if (undistorted && n > 0)
+    LIO_CHECK(c, cudaMemcpyAsync(undistorted, c->d_undist, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (voxel_key_xyz && n > 0)
+    LIO_CHECK(c, cudaMemcpyAsync(voxel_key_xyz, c->d_vkeys, 12 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (out_pts && mm > 0) {
+    if (stride == 16) {
+      LIO_CHECK(c, cudaMemcpyAsync(out_pts, c->d_body, 16 * (size_t)mm, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      std::vector<float4> hb((size_t)mm);
+      std::vector<float> ht((size_t)mm);
+      LIO_CHECK(c, cudaMemcpyAsync(hb.data(), c->d_body, 16 * (size_t)mm, cudaMemcpyDeviceToHost, c->stream));
+      LIO_CHECK(c, cudaMemcpyAsync(ht.data(), c->d_normvec, 4 * (size_t)mm, cudaMemcpyDeviceToHost, c->stream));
+      LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+      char* o = static_cast<char*>(out_pts);
+      for (int64_t j = 0; j < mm; ++j) {
+        float rec[12] = {hb[j].x, hb[j].y, hb[j].z, 1.0f, 0, 0, 0, 0, hb[j].w, ht[j], 0, 0};
+        memcpy(o + 48 * j, rec, 48);
+      }
+    }
+  }
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  return LIO_OK;
+}
+
+int lio_scan_preprocess_resident(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses,
+                                 int n_poses, const lio_state* end_state, float leaf, int64_t* m) {
+  int rc = preprocess_common(c, raw_pts, n, stride, poses, n_poses, end_state, leaf);
+  if (rc) return rc;
+  if (m) return preprocess_status(c, m);
+  return LIO_OK;
+}
+
+int lio_scan_upload(lio_ctx* c, const void* down_pts, int64_t m, int stride) {
+  if (!c || m < 0 || (stride != 16 && stride != 48) || (m > 0 && !down_pts)) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (m > c->caps.max_down_points) {
+    c->err = "scan larger than lio_caps.max_down_points (the reference's arrays hold 100000, esekfom.hpp:23-29)";
+    return LIO_E_CAPACITY;
+  }
+  int rc = stage_points(c, down_pts, m, stride, 32, c->d_body, 0, nullptr, reinterpret_cast<float*>(c->d_near_cnt));
+  if (rc) return rc;
+  set_scan_m_kernel<<<1, 1, 0, c->stream>>>(c->d_scan_m, (int)m);
+  c->launches++;
+  c->scan_m = m;
+  return LIO_OK;
+}
+
+// ---------------------------------------------------------------- update
+int lio_update_pass(lio_ctx* c, const lio_state* x, int do_search, int extrinsic_est, double blob90[90],
+                    int32_t* n_valid) {
+  if (!c || !x) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (do_search && !c->map_built) {
+    c->err = "update on an empty map";
+    return LIO_E_EMPTY_MAP;
+  }
+  double* hp = static_cast<double*>(c->h_pinned);
+  memcpy(hp, x, sizeof(lio_state));
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_x, hp, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
+  int rc = launch_pass(c, do_search ? 1 : 0, extrinsic_est, -INFINITY, INFINITY);
+  if (rc) return rc;
+  rc = launch_reduce_blob_mode(c, do_search ? 1 : 0);
+  if (rc) return rc;
+  double* hb = hp + 26 + 576;
+  LIO_CHECK(c, cudaMemcpyAsync(hb, c->d_blob, 8 * LIO_BLOB, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (blob90) memcpy(blob90, hb, 8 * 90);
+  if (n_valid) *n_valid = (int32_t)hb[90];
+  return LIO_OK;
+}
+
+int lio_state_upload(lio_ctx* c, const lio_state* x, const double P[576]) {
+  if (!c || !x || !P) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  double* hp = static_cast<double*>(c->h_pinned);
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));  // staging buffer reuse
+  memcpy(hp, x, sizeof(lio_state));
+  memcpy(hp + 26, P, 8 * 576);
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_x, hp, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_P, hp + 26, 8 * 576, cudaMemcpyHostToDevice, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_x0, c->d_x, sizeof(lio_state), cudaMemcpyDeviceToDevice, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_P0, c->d_P, 8 * 576, cudaMemcpyDeviceToDevice, c->stream));
+  return LIO_OK;
+}
+
+int lio_state_download(lio_ctx* c, lio_state* x, double P[576], int32_t* n_valid_last, int32_t* n_passes) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  double* hp = static_cast<double*>(c->h_pinned);
+  Ctrl* hc = reinterpret_cast<Ctrl*>(hp + 26 + 576 + LIO_BLOB);
+  LIO_CHECK(c, cudaMemcpyAsync(hp, c->d_x, sizeof(lio_state), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(hp + 26, c->d_P, 8 * 576, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(hc, c->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (x) memcpy(x, hp, sizeof(lio_state));
+  if (P) memcpy(P, hp + 26, 8 * 576);
+  if (n_valid_last) *n_valid_last = hc->n_valid_last;
+  if (n_passes) *n_passes = hc->n_passes;
+  return LIO_OK;
+}
+
+int lio_update_enqueue(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot) {
+  if (!c || max_iter < 0 || max_iter > 32) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (!c->map_built) {
+    c->err = "update on an empty map";
+    return LIO_E_EMPTY_MAP;
+  }
+  extrinsic_est = extrinsic_est ? 1 : 0;
+  from_snapshot = from_snapshot ? 1 : 0;
+  if (!c->use_graph) return enqueue_update_body(c, R, max_iter, extrinsic_est, from_snapshot);
+  lio_ctx::GraphSlot* slot = nullptr;
+  for (auto& g : c->graphs)
+    if (g.exec && g.max_iter == max_iter && g.ext == extrinsic_est && g.snap == from_snapshot && g.R == R) slot = &g;
+  if (!slot) {
+    for (auto& g : c->graphs)
+      if (!g.exec) {
+        slot = &g;
+        break;
+      }
+    if (!slot) {
+      slot = &c->graphs[0];
+      cudaGraphExecDestroy(slot->exec);
+      slot->exec = nullptr;
+    }
+    // make sure module-level one-time initialisation (constant tables) happens outside the capture
+    int rc0 = launch_begin(c, max_iter, 0);
+    if (rc0) return rc0;
+    LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+    const int64_t launches_before = c->launches;
+    cudaGraph_t graph = nullptr;
+    LIO_CHECK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_update_body(c, R, max_iter, extrinsic_est, from_snapshot);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    c->launches = launches_before;
+    if (rc) return rc;
+    LIO_CHECK(c, e);
+    LIO_CHECK(c, cudaGraphInstantiate(&slot->exec, graph, 0));
+    cudaGraphDestroy(graph);
+    slot->max_iter = max_iter;
+    slot->ext = extrinsic_est;
+    slot->snap = from_snapshot;
+    slot->R = R;
+  }
+  LIO_CHECK(c, cudaGraphLaunch(slot->exec, c->stream));
+  c->launches += 1 + 3 * (int64_t)(max_iter + 1);
+  return LIO_OK;
+}
+
+int lio_update_scan(lio_ctx* c, lio_state* x_io, double P_io[576], double R, int max_iter, int extrinsic_est,
+                    int32_t* n_valid_last, int32_t* n_passes) {
+  if (!c || !x_io || !P_io) return LIO_E_INVALID;
+  int rc = lio_state_upload(c, x_io, P_io);
+  if (rc) return rc;
+  rc = lio_update_enqueue(c, R, max_iter, extrinsic_est, 0);
+  if (rc) return rc;
+  return lio_state_download(c, x_io, P_io, n_valid_last, n_passes);
+}
+
+int lio_update_begin(lio_ctx* c, int from_snapshot) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  return launch_begin(c, -1 /* set by step_enqueue */, from_snapshot ? 1 : 0);
+}
+
+int lio_update_pass_enqueue(lio_ctx* c, int extrinsic_est, float x_own_min, float x_own_max) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  int rc = launch_pass(c, -1, extrinsic_est ? 1 : 0, x_own_min, x_own_max);
+  if (rc) return rc;
+  return launch_reduce_blob(c);
+}
+
+__global__ void set_max_iter_kernel(Ctrl* ctrl, int max_iter) { ctrl->max_iter = max_iter; }
+
+int lio_update_step_enqueue(lio_ctx* c, double R, int max_iter) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  set_max_iter_kernel<<<1, 1, 0, c->stream>>>(c->d_ctrl, max_iter);
+  c->launches++;
+  return launch_solve(c, R, 1);
+}
+
+void* lio_blob_device_ptr(lio_ctx* c) { return c ? c->d_blob : nullptr; }
+
+int lio_blob_download(lio_ctx* c, double blob92[92]) {
+  if (!c || !blob92) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  LIO_CHECK(c, cudaMemcpyAsync(blob92, c->d_blob, 8 * LIO_BLOB, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  return LIO_OK;
+}
+
+int lio_get_neighbors(lio_ctx* c, int32_t* idx5, float* d2_5, float* nbr_xyz, float* world_xyz, uint8_t* selected,
+                      float* normvec) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  int rc = refresh_scan_m(c);
+  if (rc) return rc;
+  const int64_t m = c->scan_m;
+  if (m <= 0) return LIO_OK;
+  rc = download_neighbors(c, m, idx5, d2_5, nbr_xyz);
+  if (rc) return rc;
+  std::vector<float4> h;
+  if (world_xyz) {
+    h.resize((size_t)m);
+    LIO_CHECK(c, cudaMemcpyAsync(h.data(), c->d_world, 16 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+    LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < m; ++i) {
+      world_xyz[3 * i] = h[i].x;
+      world_xyz[3 * i + 1] = h[i].y;
+      world_xyz[3 * i + 2] = h[i].z;
+    }
+  }
+  if (selected) LIO_CHECK(c, cudaMemcpyAsync(selected, c->d_selected, (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  if (normvec) LIO_CHECK(c, cudaMemcpyAsync(normvec, c->d_normvec, 16 * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  return LIO_OK;
+}
+
+int lio_map_incremental(lio_ctx* c, const lio_state* x, float filter_size_map, int ekf_inited, int32_t counts[3]) {
+  if (!c || !x || !counts) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  int rc = refresh_scan_m(c);
+  if (rc) return rc;
+  return map_incremental(c, x, filter_size_map, ekf_inited, counts);
+}
+
+// ---------------------------------------------------------------- host-side sequential pieces
+int lio_boxplus(const lio_state* x, const double f[24], lio_state* out) {
+  if (!x || !f || !out) return LIO_E_INVALID;
+  StateD r;
+  boxplus(*reinterpret_cast<const StateD*>(x), f, r);
+  memcpy(out, &r, sizeof(r));
+  return LIO_OK;
+}
+int lio_boxminus(const lio_state* x1, const lio_state* x2, double out[24]) {
+  if (!x1 || !x2 || !out) return LIO_E_INVALID;
+  boxminus(*reinterpret_cast<const StateD*>(x1), *reinterpret_cast<const StateD*>(x2), out);
+  return LIO_OK;
+}
+
+// esekf::predict (esekfom.hpp:82-95) with get_f / df_dx / df_dw of use-ikfom.hpp:57-123.  The Jacobians are sparse;
+// the products are formed block-wise instead of as dense 24x24x24 loops.
+int lio_predict(lio_state* xs, double P[576], double dt, const double Q[144], const double acc[3],
+                const double gyro[3]) {
+  if (!xs || !P || !Q || !acc || !gyro) return LIO_E_INVALID;
+  StateD& x = *reinterpret_cast<StateD*>(xs);
+  double R[9];
+  quat_to_mat(x.rot, R);
+  const double am[3] = {acc[0] - x.ba[0], acc[1] - x.ba[1], acc[2] - x.ba[2]};
+  double a_in[3];
+  mat3_vec(R, am, a_in);
+  double f[24] = {0};
+  for (int i = 0; i < 3; ++i) {
+    f[i] = x.vel[i] * dt;
+    f[3 + i] = (gyro[i] - x.bg[i]) * dt;
+    f[12 + i] = (a_in[i] + x.grav[i]) * dt;
+  }
+  // F = I + dt * df_dx ; W = dt * df_dw
+  std::vector<double> F(576, 0.0), W(24 * 12, 0.0);
+  for (int i = 0; i < 24; ++i) F[i * 24 + i] = 1.0;
+  const double hat[9] = {0, -am[2], am[1], am[2], 0, -am[0], -am[1], am[0], 0};
+  double Rh[9];
+  mat3_mul(R, hat, Rh);
+  for (int i = 0; i < 3; ++i) {
+    F[i * 24 + 12 + i] += dt;
+    F[(3 + i) * 24 + 15 + i] += -dt;
+    F[(12 + i) * 24 + 21 + i] += dt;
+    W[(3 + i) * 12 + i] = -dt;
+    W[(15 + i) * 12 + 6 + i] = dt;
+    W[(18 + i) * 12 + 9 + i] = dt;
+    for (int j = 0; j < 3; ++j) {
+      F[(12 + i) * 24 + 3 + j] += -Rh[3 * i + j] * dt;
+      F[(12 + i) * 24 + 18 + j] += -R[3 * i + j] * dt;
+      W[(12 + i) * 12 + 3 + j] = -R[3 * i + j] * dt;
+    }
+  }
+  StateD xn;
+  boxplus(x, f, xn);
+  x = xn;
+  std::vector<double> T(576), Pn(576), WQ(24 * 12);
+  for (int i = 0; i < 24; ++i)
+    for (int j = 0; j < 24; ++j) {
+      double s = 0;
+      for (int k = 0; k < 24; ++k) s += F[i * 24 + k] * P[k * 24 + j];
+      T[i * 24 + j] = s;
+    }
+  for (int i = 0; i < 24; ++i)
+    for (int j = 0; j < 12; ++j) {
+      double s = 0;
+      for (int k = 0; k < 12; ++k) s += W[i * 12 + k] * Q[k * 12 + j];
+      WQ[i * 12 + j] = s;
+    }
+  for (int i = 0; i < 24; ++i)
+    for (int j = 0; j < 24; ++j) {
+      double s = 0, s2 = 0;
+      for (int k = 0; k < 24; ++k) s += T[i * 24 + k] * F[j * 24 + k];
+      for (int k = 0; k < 12; ++k) s2 += WQ[i * 12 + k] * W[j * 12 + k];
+      Pn[i * 24 + j] = s + s2;
+    }
+  memcpy(P, Pn.data(), 8 * 576);
+  return LIO_OK;
+}
+
+}  // extern "C"

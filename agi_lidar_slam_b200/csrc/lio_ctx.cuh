@@ -1,0 +1,113 @@
+// Context layout shared by the translation units of liblio_b200.so.
+#pragma once
+#include <string>
+
+#include "lio_common.cuh"
+
+struct lio_ctx {
+  int device = 0;
+  int sm_count = 148;
+  lio_caps caps{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int64_t launches = 0;
+
+  // ---- map
+  lio::MapView map{};
+  uint32_t hash_cap = 0;
+  int32_t next_id = 0;     // id given to the next inserted point (host mirror)
+  bool map_built = false;  // ≙ ikdtree.Root_Node != nullptr
+  int knn_rings = 3;
+  // batch scratch (sized for max(max_down_points, build chunk))
+  int64_t batch_cap = 0;
+  float4* d_batch_pts = nullptr;    // staged points of the current insert batch
+  uint32_t* d_batch_slot = nullptr; // hash slot per point
+  uint32_t* d_batch_rank = nullptr; // rank within its cell for this batch
+  unsigned long long* d_vox_best = nullptr;  // downsample-add: per batch-voxel best (dist bits << 32 | ~idx)
+  unsigned long long* d_vox_key = nullptr;   //                  per batch-voxel key (bmin bit patterns hashed)
+  uint32_t vox_cap = 0;
+  uint8_t* d_batch_flag = nullptr;  // 1 = append this point
+
+  // ---- current scan (feats_down_body) and per-point persistent state
+  int64_t scan_m = 0;               // host mirror (-1: unknown, device-resident only)
+  int* d_scan_m = nullptr;          // device copy read by the kernels
+  float4* d_body = nullptr;         // M x (x,y,z,intensity)
+  float4* d_world = nullptr;        // M x FP32 p_world of the last pass
+  float4* d_near = nullptr;         // M x 5 cached Nearest_Points (x,y,z,id bits)
+  float* d_near_d2 = nullptr;       // M x 5
+  int* d_near_cnt = nullptr;        // M
+  uint8_t* d_selected = nullptr;    // M point_selected_surf
+  float4* d_normvec = nullptr;      // M x (a,b,c,pd2)
+  double* d_partials = nullptr;     // max_tiles x LIO_BLOB
+  int max_tiles = 0;
+  double* d_blob = nullptr;         // LIO_BLOB
+  uint8_t* d_cls = nullptr;         // map_incremental class per point
+  float4* d_add_a = nullptr;        // compacted PointToAdd
+  float4* d_add_b = nullptr;        // compacted PointNoNeedDownsample
+
+  // ---- filter state
+  lio::StateD* d_x = nullptr;       // current state
+  lio::StateD* d_xprop = nullptr;   // x_propagated
+  double* d_P = nullptr;            // 24x24
+  lio::StateD* d_x0 = nullptr;      // prior snapshot (lio_state_upload)
+  double* d_P0 = nullptr;
+  lio::Ctrl* d_ctrl = nullptr;
+  double* d_dx = nullptr;           // last dx (24)
+  void* h_pinned = nullptr;         // pinned staging (state + P + ctrl + blob)
+  size_t h_pinned_bytes = 0;
+
+  // ---- preprocess
+  float4* d_raw = nullptr;          // N raw points (x,y,z,t_ms)
+  float* d_raw_aux = nullptr;       // N intensity (stride-48 input)
+  float4* d_undist = nullptr;       // N undistorted
+  int* d_vkeys = nullptr;           // N x 3
+  lio_pose6d* d_poses = nullptr;    // up to 256
+  uint32_t svox_cap = 0;            // scan-voxel hash capacity
+  unsigned long long* d_svox_key = nullptr;
+  long long* d_svox_acc = nullptr;  // cap x 5 fixed-point sums (x,y,z,intensity,time)
+  uint32_t* d_svox_cnt = nullptr;
+  unsigned long long* d_sort_keys_in = nullptr;
+  unsigned long long* d_sort_keys_out = nullptr;
+  uint32_t* d_sort_vals_in = nullptr;
+  uint32_t* d_sort_vals_out = nullptr;
+  void* d_cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  int* d_prep_counters = nullptr;   // [0] M, [1..6] key min/max, [7] error
+
+  // ---- whole-update CUDA graphs, keyed by (max_iter, extrinsic_est, from_snapshot)
+  struct GraphSlot {
+    int max_iter = -1, ext = -1, snap = -1;
+    double R = 0;
+    cudaGraphExec_t exec = nullptr;
+  } graphs[8];
+  bool use_graph = true;
+  int qpw_search = 8;   // queries per warp in search passes (tunable: LIO_QPW_SEARCH)
+};
+
+#define LIO_CHECK(ctx, call)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                         \
+      return LIO_E_CUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+namespace lio {
+// launchers implemented in lio_pass.cu / lio_map.cu / lio_preprocess.cu
+int launch_pass(lio_ctx* c, int force_search, int extrinsic_est, float own_min, float own_max);
+int launch_reduce_blob(lio_ctx* c);
+int launch_solve(lio_ctx* c, double R, int external_blob);
+int launch_begin(lio_ctx* c, int max_iter, int from_snapshot);
+int launch_knn_batch(lio_ctx* c, const float4* d_q, int64_t m);
+
+int map_reset(lio_ctx* c);
+int map_append_batch(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, const uint8_t* d_flag);
+int map_add_downsample(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, int32_t* n_added);
+int map_delete_boxes(lio_ctx* c, const float* h_boxes6, int nb, int32_t* n_deleted);
+int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
+int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]);
+
+int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux);
+}  // namespace lio

@@ -1,0 +1,284 @@
+// Warp-cooperative bounded 5-nearest-neighbour search on the voxel-hash map, and the FP32 plane fit.
+// Replaces KD_TREE::Nearest_Search (ikd_Tree.cpp:370-402, 960-1101) and esti_plane (common_lib.h:102-134).
+#pragma once
+#include <float.h>
+
+#include "lio_common.cuh"
+
+namespace lio {
+
+// Lane-local candidate list, ascending by key = (d2 bits << 32 | id).  d2 >= 0 so its IEEE bit pattern orders
+// like the value; ids are unique, so the key order is the canonical (d2, id) order of the parity contract.
+struct TopK {
+  unsigned long long k0, k1, k2, k3, k4;
+  uint32_t s0, s1, s2, s3, s4;  // pool slots
+  __device__ __forceinline__ void init() {
+    k0 = k1 = k2 = k3 = k4 = ~0ull;
+    s0 = s1 = s2 = s3 = s4 = 0;
+  }
+  __device__ __forceinline__ void insert(unsigned long long k, uint32_t s) {
+    if (k < k4) {
+      k4 = k;
+      s4 = s;
+      if (k4 < k3) {
+        unsigned long long tk = k3; k3 = k4; k4 = tk;
+        uint32_t ts = s3; s3 = s4; s4 = ts;
+        if (k3 < k2) {
+          tk = k2; k2 = k3; k3 = tk;
+          ts = s2; s2 = s3; s3 = ts;
+          if (k2 < k1) {
+            tk = k1; k1 = k2; k2 = tk;
+            ts = s1; s1 = s2; s2 = ts;
+            if (k1 < k0) {
+              tk = k0; k0 = k1; k1 = tk;
+              ts = s0; s0 = s1; s1 = ts;
+            }
+          }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void pop() {
+    k0 = k1; k1 = k2; k2 = k3; k3 = k4; k4 = ~0ull;
+    s0 = s1; s1 = s2; s2 = s3; s3 = s4;
+  }
+};
+
+// All 32 lanes call this with the SAME query.  Stage 1: lane l < 27 owns neighbour cell
+// (l%3-1, (l/3)%3-1, l/9-1) of the query's cell, walks that cell's float4 bucket and keeps a private top-5.
+// The 3x3x3 block holds every map point closer than `cell` to the query, so if the warp has seen >= 5 points
+// with d2 < cell^2 the result is already exact (the common case at one map point per 0.5 m voxel).  Otherwise
+// stage 2 visits the remaining cells of the (2*rings+1)^3 block whose box distance is within the bound.
+// The warp then extracts the global top-5 with five rounds of redux.min on (d2 bits, id).
+// Outputs are warp-uniform: out_key[r] (d2 bits << 32 | id; ~0 when fewer than r+1 found), out_slot[r].
+__device__ __forceinline__ void warp_scan_cell(const MapView& map, float qx, float qy, float qz, uint32_t max_bits,
+                                               uint32_t start, uint32_t count, TopK& top) {
+  const uint32_t maxc = __reduce_max_sync(0xffffffffu, count);
+  for (uint32_t t = 0; t < maxc; ++t) {
+    if (t < count) {
+      const float4 p = __ldg(map.pool + start + t);
+      const int id = __float_as_int(p.w);
+      if (id >= 0) {
+        const uint32_t db = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
+        if (db <= max_bits) top.insert(((unsigned long long)db << 32) | (uint32_t)id, start + t);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int warp_knn5(const MapView& map, float qx, float qy, float qz, float max_d2, int rings,
+                                         unsigned long long out_key[LIO_K], uint32_t out_slot[LIO_K]) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int cx = cell_coord(qx, map.inv_cell), cy = cell_coord(qy, map.inv_cell), cz = cell_coord(qz, map.inv_cell);
+  TopK top;
+  top.init();
+  const uint32_t max_bits = __float_as_uint(max_d2);
+  {
+    uint32_t start = 0, count = 0;
+    if (lane < 27) map_find(map, pack_cell(cx + lane % 3 - 1, cy + (lane / 3) % 3 - 1, cz + lane / 9 - 1), start, count);
+    warp_scan_cell(map, qx, qy, qz, max_bits, start, count, top);
+  }
+  if (rings > 1) {
+    // exact already?  (0.999: any unseen point has true distance > cell, so its rounded d2 exceeds this bound)
+    const uint32_t near_bits = __float_as_uint(fminf(map.cell * map.cell * 0.999f, max_d2));
+    const int mine = (int)((uint32_t)(top.k0 >> 32) <= near_bits) + (int)((uint32_t)(top.k1 >> 32) <= near_bits) +
+                     (int)((uint32_t)(top.k2 >> 32) <= near_bits) + (int)((uint32_t)(top.k3 >> 32) <= near_bits) +
+                     (int)((uint32_t)(top.k4 >> 32) <= near_bits);
+    const int seen = __reduce_add_sync(FULL, mine);
+    if (seen < LIO_K) {
+      const int side = 2 * rings + 1;
+      const int ncell = side * side * side;
+      for (int base = 0; base < ncell; base += 32) {
+        const int c = base + lane;
+        uint32_t start = 0, count = 0;
+        if (c < ncell) {
+          const int dx = c % side - rings, dy = (c / side) % side - rings, dz = c / (side * side) - rings;
+          const bool inner = (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1);
+          if (!inner) {
+            const float lx = (float)(cx + dx) * map.cell, ly = (float)(cy + dy) * map.cell,
+                        lz = (float)(cz + dz) * map.cell;
+            const float ex = fmaxf(fmaxf(lx - qx, qx - (lx + map.cell)), 0.f);
+            const float ey = fmaxf(fmaxf(ly - qy, qy - (ly + map.cell)), 0.f);
+            const float ez = fmaxf(fmaxf(lz - qz, qz - (lz + map.cell)), 0.f);
+            // conservative (shrunk by 1e-3 relative) so rounding can never skip a cell that matters
+            if ((ex * ex + ey * ey + ez * ez) * 0.999f <= max_d2)
+              map_find(map, pack_cell(cx + dx, cy + dy, cz + dz), start, count);
+          }
+        }
+        warp_scan_cell(map, qx, qy, qz, max_bits, start, count, top);
+      }
+    }
+  }
+  int found = 0;
+#pragma unroll
+  for (int r = 0; r < LIO_K; ++r) {
+    const uint32_t hi = (uint32_t)(top.k0 >> 32);
+    const uint32_t mhi = __reduce_min_sync(FULL, hi);
+    const uint32_t lo = (hi == mhi) ? (uint32_t)top.k0 : 0xffffffffu;
+    const uint32_t mlo = __reduce_min_sync(FULL, lo);
+    const bool win = (hi == mhi) && ((uint32_t)top.k0 == mlo) && (top.k0 != ~0ull);
+    const unsigned wmask = __ballot_sync(FULL, win);
+    if (wmask == 0) {
+      out_key[r] = ~0ull;
+      out_slot[r] = 0;
+    } else {
+      const int wl = __ffs(wmask) - 1;
+      out_key[r] = ((unsigned long long)mhi << 32) | mlo;
+      out_slot[r] = __shfl_sync(FULL, top.s0, wl);
+      if (lane == wl) top.pop();
+      ++found;
+    }
+  }
+  return found;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// esti_plane<float> (common_lib.h:102-134): 5x3 FP32 column-pivoted Householder QR solve of A n = -1 in the
+// operation order of SURVEY.md App. B.1 (Eigen ColPivHouseholderQR recipe), one IEEE rounding per operation.
+// P[j] = neighbour j (x,y,z).  Returns true when all 5 neighbours lie within `thr` of the fitted plane.
+// ---------------------------------------------------------------------------------------------------------
+#define LIO_SWAPF(a, b) \
+  {                     \
+    float _t = (a);     \
+    (a) = (b);          \
+    (b) = _t;           \
+  }
+
+__device__ __forceinline__ bool esti_plane(const float4 P[5], float thr, float pabcd[4]) {
+  float A[5][3];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    A[i][0] = P[i].x;
+    A[i][1] = P[i].y;
+    A[i][2] = P[i].z;
+  }
+  float c[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
+  float nd[3], nu[3], tau[3];
+  int trans[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) s = s + A[i][j] * A[i][j];
+    nd[j] = nu[j] = sqrtf(s);
+  }
+  const float maxn = fmaxf(nu[0], fmaxf(nu[1], nu[2]));
+  const float eps = FLT_EPSILON;
+  const float thr_helper = ((maxn * eps) * (maxn * eps)) / 5.0f;
+  const float downdate_thr = sqrtf(eps);
+  int nonzero = 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int jb = k;
+    float best = nu[k];
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j)
+      if (nu[j] > best) {
+        best = nu[j];
+        jb = j;
+      }
+    if (nonzero == 3 && best * best < thr_helper * (float)(5 - k)) nonzero = k;
+    trans[k] = jb;
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j)
+      if (jb == j) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) LIO_SWAPF(A[i][k], A[i][j]);
+        LIO_SWAPF(nu[k], nu[j]);
+        LIO_SWAPF(nd[k], nd[j]);
+      }
+    float tailsq = 0.f;
+#pragma unroll
+    for (int i = k + 1; i < 5; ++i) tailsq = tailsq + A[i][k] * A[i][k];
+    const float c0 = A[k][k];
+    float beta, t;
+    float ess[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (tailsq <= FLT_MIN) {
+      t = 0.f;
+      beta = c0;
+    } else {
+      beta = sqrtf(c0 * c0 + tailsq);
+      if (c0 >= 0.f) beta = -beta;
+      const float den = c0 - beta;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) ess[i] = A[i][k] / den;
+      t = (beta - c0) / beta;
+    }
+    tau[k] = t;
+    A[k][k] = beta;
+#pragma unroll
+    for (int i = k + 1; i < 5; ++i) A[i][k] = ess[i];
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j) {
+      float tmp = 0.f;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) tmp = tmp + ess[i] * A[i][j];
+      tmp = tmp + A[k][j];
+      A[k][j] = A[k][j] - t * tmp;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) A[i][j] = A[i][j] - (t * tmp) * ess[i];
+    }
+#pragma unroll
+    for (int j = k + 1; j < 3; ++j) {
+      if (nu[j] != 0.f) {
+        float tt = fabsf(A[k][j]) / nu[j];
+        tt = (1.f + tt) * (1.f - tt);
+        if (tt < 0.f) tt = 0.f;
+        const float ratio = nu[j] / nd[j];
+        const float t2 = tt * (ratio * ratio);
+        if (t2 <= downdate_thr) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = k + 1; i < 5; ++i) s = s + A[i][j] * A[i][j];
+          nd[j] = sqrtf(s);
+          nu[j] = nd[j];
+        } else {
+          nu[j] = nu[j] * sqrtf(tt);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k < nonzero) {
+      float tmp = 0.f;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) tmp = tmp + A[i][k] * c[i];
+      tmp = tmp + c[k];
+      c[k] = c[k] - tau[k] * tmp;
+#pragma unroll
+      for (int i = k + 1; i < 5; ++i) c[i] = c[i] - (tau[k] * tmp) * A[i][k];
+    }
+  }
+  float y[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 2; i >= 0; --i) {
+    if (i < nonzero) {
+      float s = c[i];
+#pragma unroll
+      for (int j = i + 1; j < 3; ++j)
+        if (j < nonzero) s = s - A[i][j] * y[j];
+      y[i] = s / A[i][i];
+    }
+  }
+  // un-permute (column transpositions in reverse)
+  if (trans[2] != 2) { /* trans[2] can only be 2 */ }
+  if (trans[1] == 2) LIO_SWAPF(y[1], y[2]);
+  if (trans[0] == 1) LIO_SWAPF(y[0], y[1]);
+  if (trans[0] == 2) LIO_SWAPF(y[0], y[2]);
+  const float n = sqrtf((y[0] * y[0] + y[1] * y[1]) + y[2] * y[2]);
+  pabcd[0] = y[0] / n;
+  pabcd[1] = y[1] / n;
+  pabcd[2] = y[2] / n;
+  pabcd[3] = (float)(1.0 / (double)n);
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const float d = ((pabcd[0] * P[j].x + pabcd[1] * P[j].y) + pabcd[2] * P[j].z) + pabcd[3];
+    if (fabsf(d) > thr) ok = false;
+  }
+  return ok;
+}
+
+}  // namespace lio

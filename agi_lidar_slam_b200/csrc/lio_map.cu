@@ -1,0 +1,513 @@
+// GPU voxel-hash map: the observable semantics of the reference ikd-Tree calls on the hot path
+//   Build (ikd_Tree.cpp:355-367) / Add_Points (:419-512) / Delete_Point_Boxes (:559-579) / flatten (:1490-1516)
+// on a hash of kNN cells, each owning one contiguous float4 bucket in a point pool (x,y,z,id bits; id < 0 = dead).
+// Inserts are batched in three phases (reserve -> grow -> fill) so no thread ever waits on another.
+// map_incremental (laserMapping.cpp:382-433) is classified and applied on the device as well.
+#include "lio_ctx.cuh"
+
+namespace lio {
+
+#define BASE_SENTINEL 0xFFFFFFFFu
+
+__global__ void map_init_kernel(MapView m, uint32_t hash_cap) {
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < hash_cap; h += gridDim.x * blockDim.x) {
+    m.table[h].key = LIO_EMPTY_KEY;
+    m.table[h].start = 0;
+    m.table[h].count = 0;
+    m.cell_cap[h] = 0;
+    m.cell_pend[h] = 0;
+    m.cell_base[h] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 8) m.counters[threadIdx.x] = 0;
+}
+
+// phase 1: find-or-create the cell of every point, take a rank inside this batch
+__global__ void map_reserve_kernel(MapView m, const float4* pts, int n, const uint8_t* flag, uint32_t* slot,
+                                   uint32_t* rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flag && !flag[i]) return;
+  const float4 p = pts[i];
+  const unsigned long long key =
+      pack_cell(cell_coord(p.x, m.inv_cell), cell_coord(p.y, m.inv_cell), cell_coord(p.z, m.inv_cell));
+  uint32_t h = hash64(key) & m.hash_mask;
+  uint32_t probes = 0;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(&m.table[h].key, LIO_EMPTY_KEY, key);
+    if (prev == LIO_EMPTY_KEY) {
+      atomicAdd(&m.counters[1], 1u);
+      break;
+    }
+    if (prev == key) break;
+    h = (h + 1) & m.hash_mask;
+    if (++probes > m.hash_mask) {
+      atomicExch(&m.counters[3], 1u);
+      slot[i] = BASE_SENTINEL;
+      return;
+    }
+  }
+  slot[i] = h;
+  rank[i] = atomicAdd(&m.cell_pend[h], 1u);
+}
+
+// phase 2: one thread per touched cell makes room (amortised doubling; the live points move, the old run is retired)
+__global__ void map_grow_kernel(MapView m, int n, const uint8_t* flag, const uint32_t* slot, const uint32_t* rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flag && !flag[i]) return;
+  const uint32_t h = slot[i];
+  if (h == BASE_SENTINEL || rank[i] != 0) return;
+  uint32_t cnt = m.table[h].count;
+  const uint32_t need = cnt + m.cell_pend[h];
+  if (need > m.cell_cap[h]) {
+    uint32_t newcap = 8;
+    while (newcap < need) newcap <<= 1;
+    const uint32_t newstart = atomicAdd(&m.counters[0], newcap);
+    if ((unsigned long long)newstart + newcap > m.pool_cap) {
+      atomicExch(&m.counters[3], 2u);
+      m.cell_base[h] = BASE_SENTINEL;
+      return;
+    }
+    const uint32_t old = m.table[h].start;
+    uint32_t live = 0;
+    for (uint32_t t = 0; t < cnt; ++t) {
+      float4 p = m.pool[old + t];
+      if (__float_as_int(p.w) >= 0) {
+        m.pool[newstart + live++] = p;
+        p.w = __int_as_float(-1);
+        m.pool[old + t] = p;  // retire the old slot so pool sweeps see each live point once
+      }
+    }
+    m.table[h].start = newstart;
+    m.table[h].count = live;
+    m.cell_cap[h] = newcap;
+    cnt = live;
+  }
+  m.cell_base[h] = cnt;
+}
+
+// phase 3: write the points
+__global__ void map_fill_kernel(MapView m, const float4* pts, int n, const uint8_t* flag, const uint32_t* slot,
+                                const uint32_t* rank, int id_base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool wrote = false;
+  if (i < n && (!flag || flag[i])) {
+    const uint32_t h = slot[i];
+    if (h != BASE_SENTINEL) {
+      const uint32_t base = m.cell_base[h];
+      if (base != BASE_SENTINEL) {
+        float4 p = pts[i];
+        p.w = __int_as_float(id_base + i);
+        m.pool[m.table[h].start + base + rank[i]] = p;
+        wrote = true;
+        if (rank[i] == 0) {
+          m.table[h].count = base + m.cell_pend[h];
+          m.cell_pend[h] = 0;
+        }
+      }
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, wrote);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&m.counters[2], (uint32_t)__popc(b));
+}
+
+// ---- Add_Points with downsample --------------------------------------------------------------------------------
+struct VoxGeom {
+  float bmin[3], bmax[3], mid[3];
+  int k[3];
+};
+__device__ __forceinline__ VoxGeom vox_geom(const float4 p, float ds) {
+  VoxGeom g;
+  const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float f = floorf(v[a] / ds);
+    g.k[a] = (int)f;
+    g.bmin[a] = f * ds + 0.0f;  // ikd_Tree.cpp:431-439 (FP32); +0 folds -0 into +0
+    g.bmax[a] = g.bmin[a] + ds;
+    g.mid[a] = (float)((double)g.bmin[a] + (double)(g.bmax[a] - g.bmin[a]) / 2.0);  // :440-448
+  }
+  return g;
+}
+
+__global__ void vox_init_kernel(unsigned long long* vkey, unsigned long long* vbest, uint32_t cap) {
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += gridDim.x * blockDim.x) {
+    vkey[h] = LIO_EMPTY_KEY;
+    vbest[h] = ~0ull;
+  }
+}
+
+// per batch voxel: nearest-to-centre new point; ties go to the LATER point (a new point wins ties, :456-462)
+__global__ void vox_best_kernel(const float4* pts, int n, float ds, unsigned long long* vkey, unsigned long long* vbest,
+                                uint32_t vmask, uint32_t* vslot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  const VoxGeom g = vox_geom(p, ds);
+  const float d = dist2(p.x, p.y, p.z, g.mid[0], g.mid[1], g.mid[2]);
+  const unsigned long long key = pack_cell(g.k[0], g.k[1], g.k[2]);
+  uint32_t h = hash64(key) & vmask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(&vkey[h], LIO_EMPTY_KEY, key);
+    if (prev == LIO_EMPTY_KEY || prev == key) break;
+    h = (h + 1) & vmask;
+  }
+  vslot[i] = h;
+  atomicMin(&vbest[h], ((unsigned long long)__float_as_uint(d) << 32) | (0xFFFFFFFFu - (uint32_t)i));
+}
+
+// the winner of each batch voxel settles it against the points already in the map
+__global__ void vox_apply_kernel(MapView m, const float4* pts, int n, float ds, const unsigned long long* vbest,
+                                 const uint32_t* vslot, int id_base, uint8_t* append_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  append_flag[i] = 0;
+  const unsigned long long best = vbest[vslot[i]];
+  if ((uint32_t)best != 0xFFFFFFFFu - (uint32_t)i) return;
+  const float4 p = pts[i];
+  const VoxGeom g = vox_geom(p, ds);
+  const float dnew = __uint_as_float((uint32_t)(best >> 32));
+  int c0[3], c1[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    c0[a] = cell_coord(g.bmin[a], m.inv_cell);
+    c1[a] = cell_coord(g.bmax[a], m.inv_cell);
+  }
+  // pass 1: existing points inside the half-open box
+  int E = 0;
+  float best_d = dnew;
+  int best_id = -1;
+  uint32_t best_slot = 0, first_slot = 0;
+  for (int cz = c0[2]; cz <= c1[2]; ++cz)
+    for (int cy = c0[1]; cy <= c1[1]; ++cy)
+      for (int cx = c0[0]; cx <= c1[0]; ++cx) {
+        uint32_t start, count;
+        if (map_find(m, pack_cell(cx, cy, cz), start, count) < 0) continue;
+        for (uint32_t t = 0; t < count; ++t) {
+          const float4 q = m.pool[start + t];
+          const int id = __float_as_int(q.w);
+          if (id < 0) continue;
+          if (g.bmin[0] <= q.x && g.bmax[0] > q.x && g.bmin[1] <= q.y && g.bmax[1] > q.y && g.bmin[2] <= q.z &&
+              g.bmax[2] > q.z) {
+            if (E == 0) first_slot = start + t;
+            ++E;
+            const float d = dist2(q.x, q.y, q.z, g.mid[0], g.mid[1], g.mid[2]);
+            if (d < best_d || (best_id >= 0 && d == best_d && id < best_id)) {
+              best_d = d;
+              best_id = id;
+              best_slot = start + t;
+            }
+          }
+        }
+      }
+  if (best_id >= 0 && E <= 1) return;  // the single existing point stays (:463-465)
+  if (E == 0) {
+    append_flag[i] = 1;  // new voxel: plain insert
+    atomicAdd(&m.counters[4], 1u);
+    return;
+  }
+  // collapse the voxel to the winner
+  const uint32_t keep_slot = best_id >= 0 ? best_slot : first_slot;
+  for (int cz = c0[2]; cz <= c1[2]; ++cz)
+    for (int cy = c0[1]; cy <= c1[1]; ++cy)
+      for (int cx = c0[0]; cx <= c1[0]; ++cx) {
+        uint32_t start, count;
+        if (map_find(m, pack_cell(cx, cy, cz), start, count) < 0) continue;
+        for (uint32_t t = 0; t < count; ++t) {
+          float4 q = m.pool[start + t];
+          if (__float_as_int(q.w) < 0) continue;
+          if (g.bmin[0] <= q.x && g.bmax[0] > q.x && g.bmin[1] <= q.y && g.bmax[1] > q.y && g.bmin[2] <= q.z &&
+              g.bmax[2] > q.z && start + t != keep_slot) {
+            q.w = __int_as_float(-1);
+            m.pool[start + t] = q;
+          }
+        }
+      }
+  if (best_id < 0) {
+    // the new point wins and reuses the first slot of its voxel
+    m.pool[keep_slot] = make_float4(p.x, p.y, p.z, __int_as_float(id_base + i));
+    atomicAdd(&m.counters[4], 1u);
+  }
+  if (E > 1) atomicSub(&m.counters[2], (uint32_t)(E - 1));
+}
+
+// ---- Delete_Point_Boxes / flatten: pool sweeps --------------------------------------------------------------------
+__global__ void map_delete_kernel(MapView m, const float* boxes6, int nb, uint32_t* n_deleted) {
+  const uint32_t top = m.counters[0];
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < top; s += gridDim.x * blockDim.x) {
+    float4 q = m.pool[s];
+    if (__float_as_int(q.w) < 0) continue;
+    bool hit = false;
+    for (int b = 0; b < nb && !hit; ++b) {
+      const float* mn = boxes6 + 6 * b;
+      hit = mn[0] <= q.x && mn[3] > q.x && mn[1] <= q.y && mn[4] > q.y && mn[2] <= q.z && mn[5] > q.z;
+    }
+    if (hit) {
+      q.w = __int_as_float(-1);
+      m.pool[s] = q;
+      atomicAdd(n_deleted, 1u);
+      atomicSub(&m.counters[2], 1u);
+    }
+  }
+}
+
+__global__ void map_dump_kernel(MapView m, float4* out, uint32_t cap, uint32_t* n_out) {
+  const uint32_t top = m.counters[0];
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < top; s += gridDim.x * blockDim.x) {
+    const float4 q = m.pool[s];
+    if (__float_as_int(q.w) < 0) continue;
+    const uint32_t j = atomicAdd(n_out, 1u);
+    if (j < cap) out[j] = q;
+  }
+}
+
+// ---- map_incremental (laserMapping.cpp:382-433) -------------------------------------------------------------------
+// class 0 = skip, 1 = PointToAdd (Add_Points with downsample), 2 = PointNoNeedDownsample
+__global__ void map_incr_classify_kernel(const float4* body, const int* scan_m, const StateD* xs, const float4* near_pts,
+                                         const int* near_cnt, int ekf_inited, float fsm, float4* world,
+                                         uint8_t* cls) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *scan_m) return;
+  // pointBodyToWorld (laserMapping.cpp:277-288): rotation MATRICES here, FP64 -> FP32
+  double R[9], Rli[9];
+  quat_to_mat(xs->rot, R);
+  quat_to_mat(xs->rli, Rli);
+  const float4 b = body[i];
+  const double p[3] = {b.x, b.y, b.z};
+  double a[3], w[3];
+  mat3_vec(Rli, p, a);
+  a[0] += xs->tli[0];
+  a[1] += xs->tli[1];
+  a[2] += xs->tli[2];
+  mat3_vec(R, a, w);
+  const float pw[3] = {(float)(w[0] + xs->pos[0]), (float)(w[1] + xs->pos[1]), (float)(w[2] + xs->pos[2])};
+  world[i] = make_float4(pw[0], pw[1], pw[2], b.w);
+  uint8_t c = 1;
+  const int cnt = near_cnt[i];
+  if (cnt > 0 && ekf_inited) {
+    const double fs = (double)fsm;
+    float mid[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mid[k] = (float)(floor((double)pw[k] / fs) * fs + 0.5 * fs);
+    const float dist = dist2(pw[0], pw[1], pw[2], mid[0], mid[1], mid[2]);
+    const float4 n0 = near_pts[(size_t)i * LIO_K];
+    if (fabs((double)(n0.x - mid[0])) > 0.5 * fs && fabs((double)(n0.y - mid[1])) > 0.5 * fs &&
+        fabs((double)(n0.z - mid[2])) > 0.5 * fs) {
+      c = 2;
+    } else {
+      bool need_add = true;
+      for (int j = 0; j < LIO_K; ++j) {
+        if (cnt < LIO_K) break;
+        const float4 q = near_pts[(size_t)i * LIO_K + j];
+        if (dist2(q.x, q.y, q.z, mid[0], mid[1], mid[2]) < dist) {
+          need_add = false;
+          break;
+        }
+      }
+      c = need_add ? 1 : 0;
+    }
+  }
+  cls[i] = c;
+}
+
+// order-preserving compaction of the two classes by a single block (M <= ~1e5; not a hot kernel)
+__global__ void __launch_bounds__(1024) map_incr_compact_kernel(const float4* world, const uint8_t* cls,
+                                                                const int* scan_m, float4* out_a, float4* out_b,
+                                                                int* counts /*[2]*/) {
+  __shared__ int sa[1024], sb[1024];
+  const int M = *scan_m;
+  const int chunk = (M + 1023) / 1024;
+  const int lo = threadIdx.x * chunk, hi = min(M, lo + chunk);
+  int na = 0, nb = 0;
+  for (int i = lo; i < hi; ++i) {
+    na += cls[i] == 1;
+    nb += cls[i] == 2;
+  }
+  sa[threadIdx.x] = na;
+  sb[threadIdx.x] = nb;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int va = 0, vb = 0;
+    if (threadIdx.x >= off) {
+      va = sa[threadIdx.x - off];
+      vb = sb[threadIdx.x - off];
+    }
+    __syncthreads();
+    sa[threadIdx.x] += va;
+    sb[threadIdx.x] += vb;
+    __syncthreads();
+  }
+  int oa = sa[threadIdx.x] - na, ob = sb[threadIdx.x] - nb;
+  for (int i = lo; i < hi; ++i) {
+    if (cls[i] == 1) out_a[oa++] = world[i];
+    if (cls[i] == 2) out_b[ob++] = world[i];
+  }
+  if (threadIdx.x == 1023) {
+    counts[0] = sa[1023];
+    counts[1] = sb[1023];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static int check_map_error(lio_ctx* c) {
+  uint32_t h[8];
+  LIO_CHECK(c, cudaMemcpyAsync(h, c->map.counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (h[3] != 0) {
+    c->err = h[3] == 1 ? "map hash table full (raise lio_caps.max_map_points)"
+                       : "map point pool full (raise lio_caps.max_map_points)";
+    return LIO_E_CAPACITY;
+  }
+  return LIO_OK;
+}
+
+int map_reset(lio_ctx* c) {
+  map_init_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->map, c->hash_cap);
+  c->launches++;
+  LIO_CHECK(c, cudaGetLastError());
+  c->next_id = 0;
+  c->map_built = false;
+  return LIO_OK;
+}
+
+int map_append_batch(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, const uint8_t* d_flag) {
+  if (n <= 0) return LIO_OK;
+  if (n > c->batch_cap) {
+    c->err = "insert batch larger than the context's batch capacity";
+    return LIO_E_CAPACITY;
+  }
+  const int grid = (int)((n + 255) / 256);
+  map_reserve_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, d_flag, c->d_batch_slot, c->d_batch_rank);
+  map_grow_kernel<<<grid, 256, 0, c->stream>>>(c->map, (int)n, d_flag, c->d_batch_slot, c->d_batch_rank);
+  map_fill_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, d_flag, c->d_batch_slot, c->d_batch_rank,
+                                               id_base);
+  c->launches += 3;
+  LIO_CHECK(c, cudaGetLastError());
+  return check_map_error(c);
+}
+
+int map_add_downsample(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, int32_t* n_added) {
+  if (n_added) *n_added = 0;
+  if (n <= 0) return LIO_OK;
+  if (n > c->batch_cap || (uint64_t)n * 2 > c->vox_cap) {
+    c->err = "Add_Points batch larger than the context's batch capacity";
+    return LIO_E_CAPACITY;
+  }
+  const int grid = (int)((n + 255) / 256);
+  LIO_CHECK(c, cudaMemsetAsync(c->map.counters + 4, 0, sizeof(uint32_t), c->stream));
+  vox_init_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(c->d_vox_key, c->d_vox_best, c->vox_cap);
+  vox_best_kernel<<<grid, 256, 0, c->stream>>>(d_pts, (int)n, c->caps.map_downsample, c->d_vox_key, c->d_vox_best,
+                                               c->vox_cap - 1, c->d_batch_rank /*reused as vslot*/);
+  vox_apply_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, c->caps.map_downsample, c->d_vox_best,
+                                                c->d_batch_rank, id_base, c->d_batch_flag);
+  c->launches += 3;
+  LIO_CHECK(c, cudaGetLastError());
+  int rc = map_append_batch(c, d_pts, n, id_base, c->d_batch_flag);
+  if (rc) return rc;
+  if (n_added) {
+    uint32_t v = 0;
+    LIO_CHECK(c, cudaMemcpyAsync(&v, c->map.counters + 4, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+    *n_added = (int32_t)v;
+  }
+  return LIO_OK;
+}
+
+int map_delete_boxes(lio_ctx* c, const float* h_boxes6, int nb, int32_t* n_deleted) {
+  if (n_deleted) *n_deleted = 0;
+  if (nb <= 0) return LIO_OK;
+  float* d_boxes = nullptr;
+  uint32_t* d_n = nullptr;
+  LIO_CHECK(c, cudaMallocAsync(&d_boxes, sizeof(float) * 6 * nb, c->stream));
+  LIO_CHECK(c, cudaMallocAsync(&d_n, sizeof(uint32_t), c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(d_boxes, h_boxes6, sizeof(float) * 6 * nb, cudaMemcpyHostToDevice, c->stream));
+  LIO_CHECK(c, cudaMemsetAsync(d_n, 0, sizeof(uint32_t), c->stream));
+  map_delete_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->map, d_boxes, nb, d_n);
+  c->launches++;
+  uint32_t v = 0;
+  LIO_CHECK(c, cudaMemcpyAsync(&v, d_n, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  cudaFreeAsync(d_boxes, c->stream);
+  cudaFreeAsync(d_n, c->stream);
+  if (n_deleted) *n_deleted = (int32_t)v;
+  return LIO_OK;
+}
+
+}  // namespace lio
+
+#include <algorithm>
+#include <vector>
+
+namespace lio {
+
+int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n) {
+  uint32_t h[8];
+  LIO_CHECK(c, cudaMemcpyAsync(h, c->map.counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  const uint32_t live = h[2];
+  if (n) *n = live;
+  if ((!xyz && !ids) || live == 0) return LIO_OK;
+  float4* d_out = nullptr;
+  uint32_t* d_n = nullptr;
+  LIO_CHECK(c, cudaMallocAsync(&d_out, sizeof(float4) * (size_t)live, c->stream));
+  LIO_CHECK(c, cudaMallocAsync(&d_n, sizeof(uint32_t), c->stream));
+  LIO_CHECK(c, cudaMemsetAsync(d_n, 0, sizeof(uint32_t), c->stream));
+  map_dump_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->map, d_out, live, d_n);
+  c->launches++;
+  std::vector<float4> host((size_t)live);
+  LIO_CHECK(c, cudaMemcpyAsync(host.data(), d_out, sizeof(float4) * (size_t)live, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  cudaFreeAsync(d_out, c->stream);
+  cudaFreeAsync(d_n, c->stream);
+  std::sort(host.begin(), host.end(), [](const float4& a, const float4& b) {
+    int ia, ib;
+    memcpy(&ia, &a.w, 4);
+    memcpy(&ib, &b.w, 4);
+    return ia < ib;
+  });
+  for (int64_t i = 0; i < (int64_t)live && i < cap; ++i) {
+    if (xyz) {
+      xyz[3 * i] = host[i].x;
+      xyz[3 * i + 1] = host[i].y;
+      xyz[3 * i + 2] = host[i].z;
+    }
+    if (ids) memcpy(&ids[i], &host[i].w, 4);
+  }
+  return LIO_OK;
+}
+
+int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]) {
+  if (!c->map_built) {
+    c->err = "map_incremental needs a built map";
+    return LIO_E_EMPTY_MAP;
+  }
+  if (c->scan_m <= 0) {
+    counts[0] = counts[1] = counts[2] = 0;
+    return LIO_OK;
+  }
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_x, x, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
+  const int grid = (int)((c->scan_m + 255) / 256);
+  map_incr_classify_kernel<<<grid, 256, 0, c->stream>>>(c->d_body, c->d_scan_m, c->d_x, c->d_near, c->d_near_cnt,
+                                                        ekf_inited, fsm, c->d_world, c->d_cls);
+  int* d_counts = c->d_prep_counters + 8;
+  map_incr_compact_kernel<<<1, 1024, 0, c->stream>>>(c->d_world, c->d_cls, c->d_scan_m, c->d_add_a, c->d_add_b,
+                                                     d_counts);
+  c->launches += 2;
+  int hc[2] = {0, 0};
+  LIO_CHECK(c, cudaMemcpyAsync(hc, d_counts, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  counts[0] = hc[0];
+  counts[1] = hc[1];
+  counts[2] = 0;
+  int rc = map_add_downsample(c, c->d_add_a, hc[0], c->next_id, &counts[2]);
+  if (rc) return rc;
+  c->next_id += hc[0];
+  rc = map_append_batch(c, c->d_add_b, hc[1], c->next_id, nullptr);
+  if (rc) return rc;
+  c->next_id += hc[1];
+  return LIO_OK;
+}
+
+}  // namespace lio

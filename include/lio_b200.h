@@ -1,0 +1,184 @@
+/*
+ * lio_b200.h — C-ABI of the B200-native S-FAST_LIO hot path (liblio_b200.so).
+ *
+ * The reference (zhan994/agi_lidar_slam, src/S-FAST_LIO) has NO plugin/FFI boundary for this path:
+ * everything is C++ templates compiled into one ROS node.  The boundary kept here is
+ * the reference's C++ CALL SURFACE; each entry point below names the reference call it stands under
+ * (paths relative to src/S-FAST_LIO/).  include/lio_facade.hpp re-creates that C++ surface
+ * (KD_TREE<PointType>, esekfom::esekf, ImuProcess, VoxelGrid) on top of these functions, and
+ * INTEGRATION.md shows the lines a maintainer changes in laserMapping.cpp.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; int return = 0 (LIO_OK) or a negative LIO_E_*;
+ * no exceptions cross the boundary; caller owns every host buffer; the library owns all device memory;
+ * one context per GPU; a context is NOT re-entrant (the reference drives the path from one thread).
+ * There is no CPU fallback: lio_create fails with LIO_E_NO_DEVICE when no sm_100 device is usable.
+ *
+ * Point buffers are arrays of records `stride_bytes` apart whose first three floats are x,y,z:
+ *   stride 16 : {x,y,z,w}           w = per-point time [ms] for raw scans, intensity otherwise
+ *   stride 48 : pcl::PointXYZINormal {x,y,z,_}{nx,ny,nz,_}{intensity,curvature,_,_}  (common_lib.h:26);
+ *               curvature = per-point time offset in ms (preprocess.cpp:165-168)
+ */
+#ifndef LIO_B200_H
+#define LIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIO_ABI_VERSION 1
+#define LIO_NUM_MATCH_POINTS 5 /* common_lib.h:18 */
+
+enum {
+  LIO_OK = 0,
+  LIO_E_INVALID = -1,     /* bad argument */
+  LIO_E_NO_DEVICE = -2,   /* no usable CUDA device (product never falls back to CPU) */
+  LIO_E_CUDA = -3,        /* CUDA runtime error; see lio_last_error() */
+  LIO_E_CAPACITY = -4,    /* scan / map / hash capacity given in lio_caps exceeded */
+  LIO_E_EMPTY_MAP = -5,   /* operation needs a built map (ikdtree.Root_Node == nullptr) */
+  LIO_E_VOXEL_RANGE = -6  /* pcl::VoxelGrid "leaf size too small" overflow: output == input */
+};
+
+/* state_ikfom (include/use-ikfom.hpp:18-27).  Rotations are unit quaternions (w,x,y,z), as the old
+ * Sophus::SO3 the reference links stores them.  Error-state order (24): pos, rot, R_LI, t_LI, vel, bg, ba, grav. */
+typedef struct lio_state {
+  double pos[3];
+  double rot[4];
+  double offset_R_L_I[4];
+  double offset_T_L_I[3];
+  double vel[3];
+  double bg[3];
+  double ba[3];
+  double grav[3];
+} lio_state; /* 26 doubles */
+
+/* sfast_lio::Pose6D (msg/Pose6D.msg), element of ImuProcess::IMUpose (src/IMU_Processing.hpp:127). */
+typedef struct lio_pose6d {
+  double offset_time;
+  double acc[3];
+  double gyr[3];
+  double vel[3];
+  double pos[3];
+  double rot[9]; /* row-major */
+} lio_pose6d; /* 22 doubles */
+
+/* One IMU sample (sensor_msgs::Imu fields the path reads): stamp [s], linear_acceleration, angular_velocity. */
+typedef struct lio_imu_sample {
+  double stamp;
+  double acc[3];
+  double gyr[3];
+} lio_imu_sample; /* 7 doubles */
+
+typedef struct lio_caps {
+  int64_t max_scan_points; /* N cap of a raw scan                                   (default 262144)  */
+  int64_t max_down_points; /* M cap after the surf voxel filter; reference: 100000  (esekfom.hpp:23-29) */
+  int64_t max_map_points;  /* live + garbage slots of the map point pool            (default 4194304) */
+  float map_cell;          /* edge of a kNN hash cell [m]; does not change results  (default 1.0)     */
+  float knn_max_d2;        /* search bound on squared distance; the path needs 5    (esekfom.hpp:147) */
+  float plane_thr;         /* esti_plane inlier threshold                           (esekfom.hpp:157: 0.1f) */
+  float map_downsample;    /* ikdtree.set_downsample_param(filter_size_map_min)     (laserMapping.cpp:748: 0.5) */
+} lio_caps;
+
+typedef struct lio_ctx lio_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int lio_abi_version(void);
+void lio_default_caps(lio_caps* caps);
+/* Creates a context on CUDA device `device`; *out = NULL on failure. */
+int lio_create(int device, const lio_caps* caps, lio_ctx** out);
+void lio_destroy(lio_ctx* ctx);
+/* Work is enqueued on this cudaStream_t (pass torch.cuda.current_stream().cuda_stream); default: own stream. */
+int lio_set_stream(lio_ctx* ctx, void* cuda_stream);
+int lio_synchronize(lio_ctx* ctx);
+const char* lio_last_error(lio_ctx* ctx);
+/* Kernels launched by this context since creation (bench.py's "gpu_launches"). */
+int64_t lio_launch_count(lio_ctx* ctx);
+
+/* ---- map: KD_TREE<PointType> surface (include/ikd-Tree/ikd_Tree.h:264-299) ----------------------- */
+/* ≙ KD_TREE::Build (ikd_Tree.cpp:355-367; laserMapping.cpp:756).  Replaces any existing map. ids = 0..n-1. */
+int lio_map_build(lio_ctx* ctx, const void* pts, int64_t n, int stride_bytes);
+/* ≙ KD_TREE::Add_Points (ikd_Tree.cpp:419-512; laserMapping.cpp:430-431).  With downsample_on the per-voxel
+ * "keep the point nearest the voxel centre, new point wins ties" rule is applied per batch.
+ * *n_added = new points that ended up in the map.  New point i gets id = next_id + i. */
+int lio_map_add(lio_ctx* ctx, const void* pts, int64_t n, int stride_bytes, int downsample_on, int32_t* n_added);
+/* ≙ KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:559-579; laserMapping.cpp:361-364). boxes6 = nb x {min xyz, max xyz}, half-open. */
+int lio_map_delete_boxes(lio_ctx* ctx, const float* boxes6, int nb, int32_t* n_deleted);
+/* ≙ KD_TREE::size() / validnum() (ikd_Tree.cpp:66-128): total = slots ever used, valid = live points. */
+int lio_map_size(lio_ctx* ctx, int64_t* total, int64_t* valid);
+/* ≙ KD_TREE::flatten(Root_Node, PCL_Storage, NOT_RECORD) (ikd_Tree.cpp:1490-1516): live points, ascending id.
+ * xyz (cap x 3) and ids (cap) may be NULL; *n = live count. */
+int lio_map_dump(lio_ctx* ctx, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
+/* ≙ a batch of KD_TREE::Nearest_Search(point, 5, ...) (ikd_Tree.cpp:370-402; esekfom.hpp:140) bounded at
+ * d2 <= caps.knn_max_d2.  q_xyz: m x 3 world-frame points.  Outputs (each may be NULL), per query ascending by
+ * (d2 FP32, id): idx5 m x 5 point ids (-1 pad), d2_5 m x 5 (+inf pad), nbr_xyz m x 5 x 3. */
+int lio_knn5(lio_ctx* ctx, const float* q_xyz, int64_t m, int32_t* idx5, float* d2_5, float* nbr_xyz);
+
+/* ---- scan preprocessing: ImuProcess::UndistortPcl back half + pcl::VoxelGrid ------------------------ */
+/* ≙ IMU_Processing.hpp:361-401 followed by laserMapping.cpp:737-738 (leaf from :683), fused in one pass.
+ * raw_pts: n records (time in w / curvature, ms).  imu_poses/n_poses = ImuProcess::IMUpose; end_state = state
+ * after forward propagation (imu_state at :355).  n_poses < 2 => no motion compensation (voxel filter only).
+ * Outputs: out_pts (max_down_points records of `stride_bytes`; centroids ascending by (kz,ky,kx)), *m = count;
+ * optional undistorted (n x 4 floats, INPUT order) and voxel_key_xyz (n x 3 absolute voxel indices).
+ * The downsampled cloud stays resident on the device as the current scan (feats_down_body). */
+int lio_scan_preprocess(lio_ctx* ctx, const void* raw_pts, int64_t n, int stride_bytes, const lio_pose6d* imu_poses,
+                        int n_poses, const lio_state* end_state, float leaf, void* out_pts, int64_t* m,
+                        float* undistorted, int32_t* voxel_key_xyz);
+/* Same work without host output copies (device-resident result only); *m may be NULL (no sync). */
+int lio_scan_preprocess_resident(lio_ctx* ctx, const void* raw_pts, int64_t n, int stride_bytes,
+                                 const lio_pose6d* imu_poses, int n_poses, const lio_state* end_state, float leaf,
+                                 int64_t* m);
+/* Sets the current scan (feats_down_body, laserMapping.cpp:738) from host memory: m records. */
+int lio_scan_upload(lio_ctx* ctx, const void* down_pts, int64_t m, int stride_bytes);
+
+/* ---- IESKF update: esekfom::esekf surface (include/esekfom.hpp) --------------------------------------- */
+/* ≙ one esekf::h_share_model call (esekfom.hpp:106-227) + the H^T H / H^T h products of :306-319 for the
+ * current scan at state x.  do_search ≙ dyn_share.converge.  blob90 = upper triangle of H^T H (12x12, row-major,
+ * 78) followed by H^T h (12); *n_valid = effct_feat_num. */
+int lio_update_pass(lio_ctx* ctx, const lio_state* x, int do_search, int extrinsic_est, double blob90[90],
+                    int32_t* n_valid);
+/* ≙ esekf::update_iterated_dyn_share_modified(R, feats_down_body, ikdtree, Nearest_Points, maximum_iter,
+ * extrinsic_est) (esekfom.hpp:270-346), whole loop on the device.  x_io / P_io (24x24 row-major) are the
+ * propagated prior in, the posterior out.  *n_valid_last = effct_feat_num of the last pass, *n_passes = number of
+ * h_share_model calls made. */
+int lio_update_scan(lio_ctx* ctx, lio_state* x_io, double P_io[576], double R, int max_iter, int extrinsic_est,
+                    int32_t* n_valid_last, int32_t* n_passes);
+/* Device-resident pieces of the above (used by bench.py and by the multi-GPU sharded-map driver):        */
+int lio_state_upload(lio_ctx* ctx, const lio_state* x, const double P[576]); /* also stored as the prior snapshot */
+int lio_state_download(lio_ctx* ctx, lio_state* x, double P[576], int32_t* n_valid_last, int32_t* n_passes);
+/* Enqueue the whole update on the context stream; no host sync.  from_snapshot != 0 first restores the state
+ * uploaded by lio_state_upload (so a benchmark can repeat the same update). */
+int lio_update_enqueue(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, int from_snapshot);
+/* Sharded-map driver: begin, then per pass {pass_enqueue -> all-reduce 92 doubles at
+ * lio_blob_device_ptr -> step_enqueue}.  x_own_min/max restrict the queries this rank owns to
+ * x_own_min <= p_world.x < x_own_max (use -inf/+inf for a single GPU). */
+int lio_update_begin(lio_ctx* ctx, int from_snapshot);
+int lio_update_pass_enqueue(lio_ctx* ctx, int extrinsic_est, float x_own_min, float x_own_max);
+int lio_update_step_enqueue(lio_ctx* ctx, double R, int max_iter);
+/* Device pointer of the 92-double reduction blob {HtH 78, Hth 12, n_valid, n_searched} written by pass_enqueue. */
+void* lio_blob_device_ptr(lio_ctx* ctx);
+/* Synchronises and copies that blob to the host (tests, single-rank drivers). */
+int lio_blob_download(lio_ctx* ctx, double blob92[92]);
+
+/* ≙ the global Nearest_Points the update fills (esekfom.hpp:136; laserMapping.cpp:62,771) plus the per-point
+ * intermediates of the last pass.  All outputs optional (NULL): idx5 m x 5, d2_5 m x 5, nbr_xyz m x 5 x 3,
+ * world_xyz m x 3 (FP32 p_world), selected m (point_selected_surf), normvec m x 4 (a,b,c,pd2). */
+int lio_get_neighbors(lio_ctx* ctx, int32_t* idx5, float* d2_5, float* nbr_xyz, float* world_xyz, uint8_t* selected,
+                      float* normvec);
+
+/* ---- map maintenance: map_incremental (src/laserMapping.cpp:382-433) ----------------------------------- */
+/* Classifies the current scan with the cached neighbours at state x and performs both Add_Points calls
+ * (:430-431).  counts[0] = |PointToAdd|, counts[1] = |PointNoNeedDownsample|, counts[2] = added by the first call. */
+int lio_map_incremental(lio_ctx* ctx, const lio_state* x, float filter_size_map, int ekf_inited, int32_t counts[3]);
+
+/* ---- host-side, sequential (<= 50 steps / scan): ImuProcess forward half ------------------------------- */
+/* ≙ esekf::predict (esekfom.hpp:82-95; use-ikfom.hpp:57-123).  Q is 12x12 row-major. */
+int lio_predict(lio_state* x, double P[576], double dt, const double Q[144], const double acc[3], const double gyro[3]);
+/* ≙ esekf::boxplus / boxminus (esekfom.hpp:59-73, 236-258). */
+int lio_boxplus(const lio_state* x, const double f[24], lio_state* out);
+int lio_boxminus(const lio_state* x1, const lio_state* x2, double out[24]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIO_B200_H */

@@ -1,0 +1,114 @@
+"""Map maintenance parity: Build / Add_Points (with and without downsample) / Delete_Point_Boxes / flatten and the
+map_incremental policy, against the oracle map (itself pinned to the reference ikd-Tree in test_oracle_map.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _p4(xyz):
+    return np.concatenate([xyz, np.zeros((len(xyz), 1), np.float32)], 1)
+
+
+def _same_map(ctx, om):
+    gx, gi = ctx.map_dump()
+    ox, oi = om.dump()
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(gx.view(np.uint32), ox.view(np.uint32))
+
+
+def test_build_and_dump(ctx, orc, small_cfg):
+    mp = small_cfg["map"]
+    ctx.map_build(_p4(mp))
+    om = orc.Map(1.0)
+    om.build(mp)
+    _same_map(ctx, om)
+    assert ctx.map_size() == (len(mp), len(mp))
+
+
+def test_add_points_sequences(ctx, orc):
+    rng = np.random.default_rng(2)
+    base = rng.uniform(-6, 6, (3000, 3)).astype(np.float32) * np.array([1, 1, 0.1], np.float32)
+    ctx.map_build(_p4(base))
+    om = orc.Map(1.0)
+    om.build(base)
+    for it in range(6):
+        new = rng.uniform(-7, 7, (2500, 3)).astype(np.float32) * np.array([1, 1, 0.1], np.float32)
+        if it == 2:
+            new[::3] = new[1::3][: len(new[::3])]  # duplicates inside one batch
+        ds = it % 3 != 2
+        a = ctx.map_add(_p4(new), ds)
+        b = om.add(new, ds, 0.5)
+        assert a == b
+        _same_map(ctx, om)
+        q = rng.uniform(-7, 7, (2000, 3)).astype(np.float32) * np.array([1, 1, 0.1], np.float32)
+        gi, gd, _ = ctx.knn5(q)
+        oi, od, _ = om.knn(q)
+        assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    t, v = ctx.map_size()
+    assert v == om.size()
+
+
+def test_bucket_growth_dense_cell(ctx, orc):
+    """Hundreds of un-thinned points in one cell force repeated bucket doubling."""
+    rng = np.random.default_rng(3)
+    base = rng.uniform(0, 1, (40, 3)).astype(np.float32)
+    ctx.map_build(_p4(base))
+    om = orc.Map(1.0)
+    om.build(base)
+    for _ in range(5):
+        new = rng.uniform(0, 1, (300, 3)).astype(np.float32)
+        ctx.map_add(_p4(new), False)
+        om.add(new, False)
+    _same_map(ctx, om)
+    q = rng.uniform(0, 1, (500, 3)).astype(np.float32)
+    gi, gd, _ = ctx.knn5(q)
+    oi, od, _ = om.knn(q)
+    assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
+
+def test_delete_boxes(ctx, orc, small_cfg):
+    mp = small_cfg["map"]
+    ctx.map_build(_p4(mp))
+    om = orc.Map(1.0)
+    om.build(mp)
+    boxes = np.array([[-5, -5, -1, 5, 5, 3], [10, -30, -1, 30, 0, 10]], np.float32)
+    assert ctx.map_delete_boxes(boxes) == om.delete_boxes(boxes) > 0
+    _same_map(ctx, om)
+
+
+def test_errors(ctx):
+    from agi_lidar_slam_b200 import _cabi
+
+    with pytest.raises(_cabi.LioError) as e:
+        ctx.map_add(np.zeros((3, 4), np.float32), True)
+    assert e.value.code == _cabi.LIO_E_EMPTY_MAP
+    ctx.map_build(np.zeros((0, 4), np.float32))  # Build([]) leaves the map empty (ikd_Tree.cpp:359)
+    with pytest.raises(_cabi.LioError):
+        ctx.update_scan(np.zeros(26), np.eye(24))
+    with pytest.raises(_cabi.LioError) as e:
+        ctx.map_build(np.zeros((int(ctx.caps.max_map_points) + 1, 4), np.float32))
+    assert e.value.code == _cabi.LIO_E_CAPACITY
+
+
+def test_map_incremental_matches_oracle(ctx, orc, small_cfg):
+    cfg = small_cfg
+    mp = cfg["map"][::2]  # thinner map so that some scan voxels are new
+    ctx.map_build(_p4(mp))
+    om = orc.Map(1.0)
+    om.build(mp)
+    s = cfg["scan"]
+    pts5 = np.concatenate([s[:, :3], np.zeros((len(s), 1), np.float32), s[:, 3:4]], 1)
+    body = np.ascontiguousarray(orc.voxel_grid(pts5, 0.5)[0][:, :4])
+    ctx.scan_upload(body)
+    x, P, nv, npass = ctx.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, False)
+    sc = orc.Scan(body[:, :3])
+    xr, Pr, trace, _ = sc.update(cfg["x_prior"], cfg["P"], om.knn_backend(), 0.001, 4, False, threads=8)
+    ref = sc.get()
+    world = orc.body_to_world(xr, body[:, :3])
+    cls = orc.map_incremental_classify(world, ref["near_raw"], ref["cnt"], True, 0.5)
+    na = om.add(world[cls == 1], True, 0.5)
+    om.add(world[cls == 2], False)
+    counts = ctx.map_incremental(xr, 0.5, True)  # same state on both sides: stage-wise comparison
+    assert counts.tolist() == [int((cls == 1).sum()), int((cls == 2).sum()), na]
+    _same_map(ctx, om)

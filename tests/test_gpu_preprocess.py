@@ -1,0 +1,115 @@
+"""Undistort + voxel downsample parity: voxel assignment bit-exact, centroids and
+undistorted coordinates within 1e-5 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _motion(orc, seed=3):
+    """A plausible IMUpose list + end state from the oracle's own forward propagation."""
+    from agi_lidar_slam_b200 import synth
+
+    traj = synth.Trajectory()
+    t0, t1 = 5.0, 5.1
+    imu = synth.imu_stream(traj, t0 - 0.005, t1, 200.0, seed)
+    x = synth.make_state(pos=traj.pos(t0), R=traj.rot(t0), vel=traj.vel(t0), bg=(0.002,) * 3, ba=(0.02,) * 3)
+    carry = orc.new_carry()
+    carry[20:27] = imu[0]  # last_imu_
+    carry[19] = t0  # last_lidar_end_time_
+    poses, x_end, P_end = orc.imu_forward(imu[1:], t0, t1, x, orc.imu_init_P(), carry)
+    return poses, x_end
+
+
+def test_voxel_assignment_exact_and_centroids(ctx, orc, avia_cfg):
+    raw = avia_cfg["scan"]  # (n,4) x,y,z,t_ms
+    out, und, keys = ctx.scan_preprocess(raw, None, None, 0.5, want_undistorted=True, want_keys=True)
+    pts5 = np.concatenate([raw[:, :3], np.zeros((len(raw), 1), np.float32), raw[:, 3:4]], 1)
+    cen, ckeys, pkeys = orc.voxel_grid(pts5, 0.5)
+    assert np.array_equal(und, raw)  # no poses => untouched
+    assert np.array_equal(keys, pkeys)  # per-point voxel index, bit-exact
+    assert out.shape[0] == cen.shape[0]  # M
+    # same voxel set in the same (kz,ky,kx) order
+    gk = np.floor(out[:, :3] / 0.5)
+    assert np.abs(out[:, :3] - cen[:, :3]).max() <= 1e-5 * np.abs(cen[:, :3]).max()
+    assert np.abs(out[:, :3] - cen[:, :3]).max() < 2e-6  # FP32 sums (oracle) vs exact fixed point (GPU)
+    lin = lambda k: (k[:, 2].astype(np.int64) << 42) + (k[:, 1].astype(np.int64) << 21) + k[:, 0]
+    assert np.all(np.diff(lin(ckeys)) > 0)
+
+
+def test_stride48_fields(ctx, orc, small_cfg):
+    raw4 = small_cfg["scan"]
+    n = len(raw4)
+    rng = np.random.default_rng(0)
+    rec = np.zeros((n, 12), np.float32)
+    rec[:, :3] = raw4[:, :3]
+    rec[:, 3] = 1.0
+    rec[:, 8] = rng.uniform(0, 200, n).astype(np.float32)  # intensity
+    rec[:, 9] = raw4[:, 3]  # curvature = time ms
+    out, _, keys = ctx.scan_preprocess(rec, None, None, 0.5, want_keys=True)
+    pts5 = np.concatenate([rec[:, :3], rec[:, 8:10]], 1)
+    cen, ckeys, pkeys = orc.voxel_grid(pts5, 0.5)
+    assert np.array_equal(keys, pkeys) and out.shape == (cen.shape[0], 12)
+    assert np.abs(out[:, :3] - cen[:, :3]).max() < 2e-6
+    assert np.abs(out[:, 8] - cen[:, 3]).max() < 1e-3  # mean intensity
+    assert np.abs(out[:, 9] - cen[:, 4]).max() < 1e-4  # mean time
+
+
+def test_undistort_matches_oracle(ctx, orc, small_cfg):
+    poses, x_end = _motion(orc)
+    raw = small_cfg["scan"].copy()
+    raw[:, 3] = np.linspace(0, 99.9, len(raw)).astype(np.float32)  # ascending, first point at t = 0
+    ref_sorted, order = orc.undistort(raw, poses, x_end)
+    ref = np.zeros_like(ref_sorted)
+    ref[order] = ref_sorted
+    out, und, keys = ctx.scan_preprocess(raw, poses, x_end, 0.5, want_undistorted=True, want_keys=True)
+    moved = np.abs(ref[:, :3] - raw[:, :3]).max()
+    assert moved > 0.05  # the compensation is not a no-op on this motion
+    err = np.abs(und[:, :3] - ref[:, :3]).max()
+    assert err <= 1e-5 * np.abs(ref[:, :3]).max()
+    assert np.array_equal(und[0], raw[0])  # t <= IMUpose[0].offset_time is never compensated (A.4)
+    # downstream voxel filter on the oracle's undistorted cloud: same M, centroids within tolerance
+    pts5 = np.concatenate([ref[:, :3], np.zeros((len(ref), 1), np.float32), ref[:, 3:4]], 1)
+    cen, ckeys, pkeys = orc.voxel_grid(pts5, 0.5)
+    same = (keys == pkeys).all(1).mean()
+    assert same > 0.999  # a 1-ulp coordinate difference may move a point across a voxel face; never seen here
+    if same == 1.0:
+        assert out.shape[0] == cen.shape[0]
+        assert np.abs(out[:, :3] - cen[:, :3]).max() < 1e-5 * np.abs(cen[:, :3]).max()
+
+
+def test_preprocess_edge_cases(ctx):
+    from agi_lidar_slam_b200 import _cabi
+
+    out, _, _ = ctx.scan_preprocess(np.zeros((0, 4), np.float32), None, None, 0.5)
+    assert out.shape[0] == 0
+    one = np.array([[1.2, -3.4, 0.7, 0.0]], np.float32)
+    out, _, keys = ctx.scan_preprocess(one, None, None, 0.5, want_keys=True)
+    assert out.shape[0] == 1 and np.allclose(out[0, :3], one[0, :3], atol=1e-6)
+    assert keys.tolist() == [[2, -7, 1]]
+    # negative coordinates / exact voxel faces
+    p = np.array([[-0.5, 0.0, 0.5, 0], [-0.5000001, -0.0, 0.4999999, 0], [0.25, 0.25, 0.25, 0]], np.float32)
+    out, _, keys = ctx.scan_preprocess(p, None, None, 0.5, want_keys=True)
+    assert keys.tolist() == [[-1, 0, 1], [-2, 0, 0], [0, 0, 0]]
+    # PCL's "leaf size too small" guard
+    far = np.array([[0, 0, 0, 0], [3e4, 3e4, 3e4, 0]], np.float32)
+    with pytest.raises(_cabi.LioError) as e:
+        ctx.scan_preprocess(far, None, None, 0.01)
+    assert e.value.code == _cabi.LIO_E_VOXEL_RANGE
+    # the context is still usable afterwards
+    out, _, _ = ctx.scan_preprocess(one, None, None, 0.5)
+    assert out.shape[0] == 1
+
+
+def test_preprocess_then_update_resident(ctx, orc, small_cfg):
+    """The downsampled cloud stays on the device and feeds the update without a host round trip."""
+    cfg = small_cfg
+    mp = cfg["map"]
+    ctx.map_build(np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1))
+    m = ctx.scan_preprocess(cfg["scan"], None, None, 0.5, resident=True)
+    x1, P1, nv1, np1 = ctx.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, False)
+    out, _, _ = ctx.scan_preprocess(cfg["scan"], None, None, 0.5)
+    assert out.shape[0] == m
+    ctx.scan_upload(out)
+    x2, P2, nv2, np2 = ctx.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, False)
+    assert np.array_equal(x1, x2) and nv1 == nv2 and np1 == np2
