@@ -323,10 +323,10 @@ def init_P() -> np.ndarray:
 
 def config1_avia(seed=1001, n_map=200_000, n_rays=24_000):
     """Config 1: 24k-ray Avia-style scan vs a 200k-point hall map."""
-    scene = hall_scene(half=80.0, height=10.0)
+    scene = hall_scene(half=110.0, height=10.0)
     mp = sample_map(scene, n_map, seed)
-    R = rot_zyx(0.3, 0.02, -0.01)
-    pos = np.array([3.0, -2.0, 1.5])
+    R = rot_zyx(0.3, 0.45, -0.01)  # nose down: the 70 x 77 deg window looks at the floor and the far wall
+    pos = np.array([3.0, -2.0, 3.0])
     d = avia_dirs(n_rays, seed + 1)
     tms = (np.arange(n_rays) / 240000.0 * 1000.0)
     scan = static_scan(scene, d, tms, pos, R, 100.0, seed + 2)

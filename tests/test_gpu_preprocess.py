@@ -31,8 +31,9 @@ def test_voxel_assignment_exact_and_centroids(ctx, orc, avia_cfg):
     assert out.shape[0] == cen.shape[0]  # M
     # same voxel set in the same (kz,ky,kx) order
     gk = np.floor(out[:, :3] / 0.5)
-    assert np.abs(out[:, :3] - cen[:, :3]).max() <= 1e-5 * np.abs(cen[:, :3]).max()
-    assert np.abs(out[:, :3] - cen[:, :3]).max() < 2e-6  # FP32 sums (oracle) vs exact fixed point (GPU)
+    # 1e-5 relative (north_star); FP32 running sums (oracle, as PCL) vs exact fixed point (GPU)
+    assert np.all(np.abs(out[:, :3] - cen[:, :3]) <= 1e-5 * np.maximum(1.0, np.abs(cen[:, :3])))
+    assert np.abs(out[:, :3] - cen[:, :3]).max() < 2e-5
     lin = lambda k: (k[:, 2].astype(np.int64) << 42) + (k[:, 1].astype(np.int64) << 21) + k[:, 0]
     assert np.all(np.diff(lin(ckeys)) > 0)
 
@@ -50,7 +51,7 @@ def test_stride48_fields(ctx, orc, small_cfg):
     pts5 = np.concatenate([rec[:, :3], rec[:, 8:10]], 1)
     cen, ckeys, pkeys = orc.voxel_grid(pts5, 0.5)
     assert np.array_equal(keys, pkeys) and out.shape == (cen.shape[0], 12)
-    assert np.abs(out[:, :3] - cen[:, :3]).max() < 2e-6
+    assert np.all(np.abs(out[:, :3] - cen[:, :3]) <= 1e-5 * np.maximum(1.0, np.abs(cen[:, :3])))
     assert np.abs(out[:, 8] - cen[:, 3]).max() < 1e-3  # mean intensity
     assert np.abs(out[:, 9] - cen[:, 4]).max() < 1e-4  # mean time
 
