@@ -55,7 +55,7 @@ EXPORTS = [
     "lio_map_dump", "lio_knn5", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
-    "lio_blob_download",
+    "lio_blob_download", "lio_pass_only_enqueue",
     "lio_get_neighbors", "lio_map_incremental", "lio_predict", "lio_boxplus", "lio_boxminus",
 ]  # fmt: skip
 
@@ -103,6 +103,7 @@ def load_library() -> C.CDLL:
         "lio_update_step_enqueue": (C.c_int, [vp, f64, C.c_int]),
         "lio_blob_device_ptr": (vp, [vp]),
         "lio_blob_download": (C.c_int, [vp, vp]),
+        "lio_pass_only_enqueue": (C.c_int, [vp, C.c_int, C.c_int]),
         "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "lio_map_incremental": (C.c_int, [vp, vp, f32, C.c_int, vp]),
         "lio_predict": (C.c_int, [vp, vp, f64, vp, vp, vp]),
@@ -309,6 +310,9 @@ class Context:
     @property
     def blob_device_ptr(self) -> int:
         return int(self._lib.lio_blob_device_ptr(self._h) or 0)
+
+    def pass_only_enqueue(self, do_search: bool, extrinsic_est=False):
+        self._check(self._lib.lio_pass_only_enqueue(self._h, int(do_search), int(extrinsic_est)))
 
     def blob_download(self):
         b = np.zeros(BLOB, np.float64)

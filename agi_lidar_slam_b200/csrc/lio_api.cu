@@ -620,6 +620,13 @@ int lio_update_step_enqueue(lio_ctx* c, double R, int max_iter) {
   return launch_solve(c, R, 1);
 }
 
+int lio_pass_only_enqueue(lio_ctx* c, int do_search, int extrinsic_est) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (do_search && !c->map_built) return LIO_E_EMPTY_MAP;
+  return launch_pass(c, do_search ? 1 : 0, extrinsic_est ? 1 : 0, -INFINITY, INFINITY);
+}
+
 void* lio_blob_device_ptr(lio_ctx* c) { return c ? c->d_blob : nullptr; }
 
 int lio_blob_download(lio_ctx* c, double blob92[92]) {

@@ -60,7 +60,7 @@ __global__ void map_grow_kernel(MapView m, int n, const uint8_t* flag, const uin
   uint32_t cnt = m.table[h].count;
   const uint32_t need = cnt + m.cell_pend[h];
   if (need > m.cell_cap[h]) {
-    uint32_t newcap = 8;
+    uint32_t newcap = 4;
     while (newcap < need) newcap <<= 1;
     const uint32_t newstart = atomicAdd(&m.counters[0], newcap);
     if ((unsigned long long)newstart + newcap > m.pool_cap) {
@@ -364,6 +364,8 @@ static int check_map_error(lio_ctx* c) {
 }
 
 int map_reset(lio_ctx* c) {
+  // every pool slot starts dead (id bits 0xFFFFFFFF < 0) so that pool sweeps (dump / delete) never see garbage
+  LIO_CHECK(c, cudaMemsetAsync(c->map.pool, 0xFF, sizeof(float4) * (size_t)c->map.pool_cap, c->stream));
   map_init_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->map, c->hash_cap);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());

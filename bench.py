@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py — scans/s of the S-FAST_LIO IESKF update on synthetic OS1-128 scans against a 2M-point map.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2]): Ouster OS1-128 scan (128 x 1024 rays, ~1.3e5 points)
+against a 2,000,000-point "city" map, 0.5 m surf voxel, up to 4 IESKF iterations, 5 cm / 1 deg perturbed prior.
+A "step" is one whole update_iterated_dyn_share_modified of one scan (all passes: kNN + plane fit + Jacobian +
+HtH/Hth reduction + 24x24 Kalman step).
+
+`value`   scans/s with the downsampled scan, the map and the prior already resident in HBM; L2 is flushed before
+          every timed step (the 2M-point map is 32 MB and would otherwise sit in the 126 MB L2).
+`e2e`     the same metric through the C-ABI call a host program makes (lio_scan_upload + lio_update_scan) with
+          pinned HOST buffers: scan + prior go host->device and the posterior comes back inside the timed region.
+`roofline`the dominant kernel (fused search pass), algorithmic bytes 116 B x M per launch over its
+          CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline` the CPU path on this box's host cores: the reference's ikd-Tree (compiled in place, oracle/_ref) under
+          the oracle's restated h_share_model / update loop, on a bounded sample of the same workload.
+With N > 1 (torchrun) every rank replays its own scan sequence against its own replica of the map (independent
+sequences, no collective in the data path; SURVEY.md §8e case 1): weak scaling, value = total scans / max-rank time.
+`--workload sharded` runs the spatially sharded-map variant instead (x-slabs + NCCL all-reduce of the 92-double blob).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "scans/sec for IESKF update (kNN+plane+HtH) on OS1-128 scans"
+UNIT = "scans/s"
+R_COV = 0.001  # LASER_POINT_COV (laserMapping.cpp:29)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="os1_128_2m", choices=["os1_128_2m"])
+    ap.add_argument("--map-points", type=int, default=2_000_000)
+    ap.add_argument("--rings", type=int, default=128)
+    ap.add_argument("--cols", type=int, default=1024)
+    ap.add_argument("--poses", type=int, default=4, help="distinct scan poses cycled through the steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------ workload
+def make_workload(args, rank):
+    from agi_lidar_slam_b200 import synth
+
+    scene, mp = synth.city_map(args.map_points, 3003)
+    scans = []
+    d, col = synth.spinning_dirs(args.rings, args.cols, -22.5, 22.5)
+    tms = col / args.cols * 100.0
+    for k in range(args.poses):
+        rng = np.random.default_rng(3003 + 1000 * rank + 17 * k + 1)
+        pos = np.array([rng.uniform(-30, 30), rng.uniform(-30, 30), 2.0])
+        R = synth.rot_zyx(rng.uniform(-np.pi, np.pi), rng.normal(0, 0.02), rng.normal(0, 0.02))
+        scan = synth.static_scan(scene, d, tms, pos, R, 120.0, 3003 + 1000 * rank + k)
+        x_true = synth.make_state(pos=pos, R=R)
+        scans.append(dict(scan=scan, x_true=x_true, x_prior=synth.perturbed_prior(x_true, 3003 + 1000 * rank + 31 * k)))
+    return dict(scene=scene, map=mp, scans=scans, P=synth.init_P(), leaf=0.5, max_iter=4, ext=False)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(wl, steps, warmup, seconds_budget, threads=None):
+    """The reference CPU path: reference ikd-Tree (oracle/_ref) + restated update loop.  Returns a dict with scans/s."""
+    from oracle import pyoracle as orc
+
+    threads = threads or (os.cpu_count() or 1)
+    orc.build()
+    use_ikd = orc.ikd_available()
+    t0 = time.perf_counter()
+    if use_ikd:
+        tree = orc.IkdTree()
+        tree.build(wl["map"])
+    else:
+        tree = orc.Map(1.0)
+        tree.build(wl["map"])
+    build_s = time.perf_counter() - t0
+    backend = tree.knn_backend()
+    bodies = []
+    for s in wl["scans"]:
+        raw = s["scan"]
+        pts5 = np.concatenate([raw[:, :3], np.zeros((len(raw), 1), np.float32), raw[:, 3:4]], 1)
+        bodies.append(np.ascontiguousarray(orc.voxel_grid(pts5, wl["leaf"])[0][:, :3]))
+    times, nvalid, npass = [], [], []
+    k = 0
+    t_start = time.perf_counter()
+    while True:
+        s = wl["scans"][k % len(bodies)]
+        sc = orc.Scan(bodies[k % len(bodies)])
+        t0 = time.perf_counter()
+        x, P, trace, nv = sc.update(s["x_prior"], wl["P"], backend, R_COV, wl["max_iter"], wl["ext"], threads=threads)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+            nvalid.append(nv)
+            npass.append(len(trace))
+        k += 1
+        if len(times) >= steps or (len(times) >= 3 and time.perf_counter() - t_start > seconds_budget):
+            break
+    tot = float(np.sum(times))
+    return dict(value=len(times) / tot, ms_per_step=1000 * tot / len(times), steps=len(times), cores=threads,
+                kind="reference" if use_ikd else "port",
+                kind_detail=("reference ikd-Tree (oracle/_ref, compiled in place) for Build/Nearest_Search + restated "
+                             "h_share_model/update loop (Eigen/PCL/Sophus absent)") if use_ikd else
+                "oracle port (hashed-grid kNN + restated update loop)", build_s=build_s,
+                matched_pts_per_s=float(np.sum(nvalid)) / tot, m=int(np.mean([len(b) for b in bodies])),
+                passes=float(np.mean(npass)))
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    rank, world, local = dist_env()
+    n_gpus = args.gpus
+    if world > 1:
+        n_gpus = world
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = make_workload(args, 0)
+        r = cpu_arm(wl, args.steps, args.warmup, seconds_budget=150.0)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n_gpus,
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 filter", "data": "synthetic",
+            "config": {"workload": "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4" %
+                       (args.rings, args.cols, args.map_points), "M": r["m"], "passes_per_scan": r["passes"]},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                             "kind_detail": r["kind_detail"],
+                             "sample": "%d whole updates of the bench scans (tree build %.1f s untimed)" %
+                             (r["steps"], r["build_s"])},
+            "matched_pts_per_s": r["matched_pts_per_s"],
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    from agi_lidar_slam_b200 import _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    wl = make_workload(args, rank)
+    n_map = len(wl["map"])
+    ctx = _cabi.Context(local, max_scan_points=max(1 << 18, args.rings * args.cols), max_down_points=100000,
+                        max_map_points=max(1 << 21, int(n_map * 1.05)))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    map4 = np.concatenate([wl["map"], np.zeros((n_map, 1), np.float32)], 1)
+    t0 = time.perf_counter()
+    ctx.map_build(map4)
+    ctx.synchronize()
+    map_build_s = time.perf_counter() - t0
+
+    # downsample every scan on the device once (lio_scan_preprocess) and keep host copies for the e2e leg
+    bodies, raws = [], []
+    for s in wl["scans"]:
+        body, _, _ = ctx.scan_preprocess(s["scan"], None, None, wl["leaf"])
+        bodies.append(torch.from_numpy(np.ascontiguousarray(body)).pin_memory())
+        raws.append(torch.from_numpy(np.ascontiguousarray(s["scan"])).pin_memory())
+    M = int(np.mean([b.shape[0] for b in bodies]))
+    P0 = wl["P"]
+
+    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def l2_flush():
+        flush.fill_(1)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- value: device-resident update, cold L2
+    def resident_run(steps, warmup, cold):
+        total_ms, nvalid, npass = 0.0, 0, 0
+        evs = []
+        for k in range(warmup + steps):
+            j = k % len(bodies)
+            ctx.scan_upload(bodies[j].numpy())
+            ctx.state_upload(wl["scans"][j]["x_prior"], P0)
+            if cold:
+                l2_flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.update_enqueue(R_COV, wl["max_iter"], wl["ext"], from_snapshot=True)
+            e1.record(stream)
+            if k >= warmup:
+                evs.append((e0, e1))
+                x, P, nv, npz = ctx.state_download()
+                nvalid += nv
+                npass += npz
+        torch.cuda.synchronize(dev)
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        return total_ms, nvalid, npass
+
+    resident_run(0, max(3, args.warmup), True)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ms_cold, nvalid, npass = resident_run(args.steps, 0, True)
+    launches = ctx.launch_count - launches0
+    barrier()
+    ms_cold = max_over_ranks(ms_cold)
+    ms_warm, _, _ = resident_run(args.steps, 0, False)
+    barrier()
+    ms_warm = max_over_ranks(ms_warm)
+    clocks = sampler.stop()
+    value = n_gpus * args.steps / (ms_cold / 1000.0)
+    value_warm = n_gpus * args.steps / (ms_warm / 1000.0)
+    matched = sum_over_ranks(float(nvalid)) / (ms_cold / 1000.0)
+    passes_per_scan = npass / args.steps
+
+    # ---------------------------------------------------------------- e2e: host buffers through the C-ABI
+    def e2e_run(steps, warmup):
+        t_ms = 0.0
+        for k in range(warmup + steps):
+            j = k % len(bodies)
+            l2_flush()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            ctx.scan_upload(bodies[j].numpy())  # H2D M x 16 B from pinned memory
+            x, P, nv, npz = ctx.update_scan(wl["scans"][j]["x_prior"], P0, R_COV, wl["max_iter"], wl["ext"])
+            dt = time.perf_counter() - t0  # update_scan returns after the D2H of the posterior (host sync)
+            if k >= warmup:
+                t_ms += dt * 1000.0
+        return t_ms
+
+    e2e_run(0, 3)
+    barrier()
+    e2e_ms = max_over_ranks(e2e_run(args.steps, 0))
+    barrier()
+    e2e_value = n_gpus * args.steps / (e2e_ms / 1000.0)
+    h2d = M * 16 + (26 + 576) * 8
+    d2h = (26 + 576) * 8 + 32
+
+    # full scan (undistort-free preprocess + update), raw scan from pinned host memory: second line of SURVEY §8d
+    def full_run(steps, warmup):
+        t_ms = 0.0
+        for k in range(warmup + steps):
+            j = k % len(raws)
+            l2_flush()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            ctx.scan_preprocess(raws[j].numpy(), None, None, wl["leaf"], resident=True)
+            ctx.update_scan(wl["scans"][j]["x_prior"], P0, R_COV, wl["max_iter"], wl["ext"])
+            dt = time.perf_counter() - t0
+            if k >= warmup:
+                t_ms += dt * 1000.0
+        return t_ms
+
+    full_run(0, 2)
+    full_ms = max_over_ranks(full_run(max(5, args.steps // 2), 0))
+    full_value = n_gpus * max(5, args.steps // 2) / (full_ms / 1000.0)
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (search pass)
+    peak, peak_src = measured_peak()
+    ctx.scan_upload(bodies[0].numpy())
+    ctx.state_upload(wl["scans"][0]["x_prior"], P0)
+    m0 = bodies[0].shape[0]
+
+    def time_pass(search, cold, reps=20):
+        ts = []
+        for _ in range(reps + 3):
+            if cold:
+                l2_flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.pass_only_enqueue(search, wl["ext"])
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        return float(np.mean(ts[3:]))
+
+    t_search_cold = time_pass(True, True)
+    t_search_warm = time_pass(True, False)
+    t_cached_warm = time_pass(False, False)
+    alg_bytes = 116.0 * m0
+    achieved = alg_bytes / (t_search_cold * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "pass_kernel<search> (kNN + plane + Jacobian + block reduce)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "launch_ms_cold_l2": t_search_cold, "launch_ms_warm_l2": t_search_warm,
+                "cached_pass_launch_ms_warm_l2": t_cached_warm,
+                "achieved_warm_l2": alg_bytes / (t_search_warm * 1e-3) / 1e9}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_cold / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 geometry / f64 filter", "data": "synthetic",
+        "config": {"workload": "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4, 1 sequence per GPU" %
+                   (args.rings, args.cols, n_map), "N_raw": int(np.mean([len(r) for r in raws])), "M": M,
+                   "passes_per_scan": passes_per_scan, "l2": "flushed (384 MiB write) before every timed step",
+                   "map_build_s": map_build_s},
+        "value_l2_warm": value_warm, "matched_pts_per_s": matched,
+        "full_scan": {"value": full_value, "unit": UNIT,
+                      "what": "raw scan H2D + voxel downsample + update + posterior D2H, host-timed"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+    }
+
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(wl, steps=1000, warmup=1, seconds_budget=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                "kind_detail": r["kind_detail"],
+                                "sample": "%d whole updates of the same scans in %.1f s (tree build %.1f s untimed)" %
+                                (r["steps"], r["steps"] / r["value"], r["build_s"]),
+                                "matched_pts_per_s": r["matched_pts_per_s"]}
+        r3 = cpu_arm(wl, steps=1000, warmup=1, seconds_budget=min(8.0, args.cpu_seconds), threads=3)
+        line["cpu_baseline_3_threads"] = {"value": r3["value"], "unit": UNIT, "cores": 3,
+                                          "note": "MP_PROC_NUM=3, the reference's own setting (CMakeLists.txt:23-26)"}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

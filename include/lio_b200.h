@@ -155,6 +155,9 @@ int lio_update_enqueue(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, 
 int lio_update_begin(lio_ctx* ctx, int from_snapshot);
 int lio_update_pass_enqueue(lio_ctx* ctx, int extrinsic_est, float x_own_min, float x_own_max);
 int lio_update_step_enqueue(lio_ctx* ctx, double R, int max_iter);
+/* Instrumentation: enqueue ONLY the fused pass kernel (search or cached variant) at the device-resident state, with
+ * no reduction / solve behind it, so that bench.py can bracket exactly that kernel with CUDA events. */
+int lio_pass_only_enqueue(lio_ctx* ctx, int do_search, int extrinsic_est);
 /* Device pointer of the 92-double reduction blob {HtH 78, Hth 12, n_valid, n_searched} written by pass_enqueue. */
 void* lio_blob_device_ptr(lio_ctx* ctx);
 /* Synchronises and copies that blob to the host (tests, single-rank drivers). */
