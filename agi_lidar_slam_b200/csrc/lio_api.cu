@@ -247,6 +247,7 @@ void lio_destroy(lio_ctx* c) {
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
   delete c;
 }
 
@@ -568,9 +569,18 @@ int lio_update_enqueue(lio_ctx* c, double R, int max_iter, int extrinsic_est, in
     LIO_CHECK(c, cudaStreamSynchronize(c->stream));
     const int64_t launches_before = c->launches;
     cudaGraph_t graph = nullptr;
-    LIO_CHECK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_update_body(c, R, max_iter, extrinsic_est, from_snapshot);
-    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    // capture on a private stream (the caller's stream may be the legacy default stream, which cannot be captured);
+    // the instantiated graph is launched on the caller's stream
+    if (!c->capture_stream) LIO_CHECK(c, cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t user_stream = c->stream;
+    c->stream = c->capture_stream;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = LIO_OK;
+    if (e == cudaSuccess) {
+      rc = enqueue_update_body(c, R, max_iter, extrinsic_est, from_snapshot);
+      e = cudaStreamEndCapture(c->stream, &graph);
+    }
+    c->stream = user_stream;
     c->launches = launches_before;
     if (rc) return rc;
     LIO_CHECK(c, e);

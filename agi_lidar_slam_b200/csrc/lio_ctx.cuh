@@ -10,6 +10,7 @@ struct lio_ctx {
   lio_caps caps{};
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t capture_stream = nullptr;  // graphs are captured here, launched on `stream`
   std::string err;
   int64_t launches = 0;
 

@@ -35,7 +35,8 @@ def test_add_points_sequences(ctx, orc):
     for it in range(6):
         new = rng.uniform(-7, 7, (2500, 3)).astype(np.float32) * np.array([1, 1, 0.1], np.float32)
         if it == 2:
-            new[::3] = new[1::3][: len(new[::3])]  # duplicates inside one batch
+            k = len(new[1::3])
+            new[::3][:k] = new[1::3]  # duplicates inside one batch
         ds = it % 3 != 2
         a = ctx.map_add(_p4(new), ds)
         b = om.add(new, ds, 0.5)
