@@ -98,7 +98,7 @@ def load_library() -> C.CDLL:
         "lio_state_upload": (C.c_int, [vp, vp, vp]),
         "lio_state_download": (C.c_int, [vp, vp, vp, P(i32), P(i32)]),
         "lio_update_enqueue": (C.c_int, [vp, f64, C.c_int, C.c_int, C.c_int]),
-        "lio_update_begin": (C.c_int, [vp, C.c_int]),
+        "lio_update_begin": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "lio_update_pass_enqueue": (C.c_int, [vp, C.c_int, f32, f32]),
         "lio_update_step_enqueue": (C.c_int, [vp, f64, C.c_int]),
         "lio_blob_device_ptr": (vp, [vp]),
@@ -298,14 +298,14 @@ class Context:
     def update_enqueue(self, R=0.001, max_iter=4, extrinsic_est=False, from_snapshot=False):
         self._check(self._lib.lio_update_enqueue(self._h, R, max_iter, int(extrinsic_est), int(from_snapshot)))
 
-    def update_begin(self, from_snapshot=False):
-        self._check(self._lib.lio_update_begin(self._h, int(from_snapshot)))
+    def update_begin(self, max_iter=4, extrinsic_est=False, from_snapshot=False):
+        self._check(self._lib.lio_update_begin(self._h, max_iter, int(extrinsic_est), int(from_snapshot)))
 
     def update_pass_enqueue(self, extrinsic_est=False, x_own_min=-np.inf, x_own_max=np.inf):
         self._check(self._lib.lio_update_pass_enqueue(self._h, int(extrinsic_est), x_own_min, x_own_max))
 
-    def update_step_enqueue(self, R=0.001, max_iter=4):
-        self._check(self._lib.lio_update_step_enqueue(self._h, R, max_iter))
+    def update_step_enqueue(self, R=0.001, extrinsic_est=False):
+        self._check(self._lib.lio_update_step_enqueue(self._h, R, int(extrinsic_est)))
 
     @property
     def blob_device_ptr(self) -> int:

@@ -11,8 +11,6 @@
 namespace lio {
 size_t preprocess_sort_bytes(int64_t n);
 int preprocess_init_tables(lio_ctx* c);
-int launch_reduce_blob_mode(lio_ctx* c, int host_search);
-int ensure_tables(lio_ctx* c);
 
 __global__ void set_w_kernel(float4* dst, const float* w, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,18 +55,6 @@ static int refresh_scan_m(lio_ctx* c) {
   return LIO_OK;
 }
 
-static int enqueue_update_body(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot) {
-  int rc = launch_begin(c, max_iter, from_snapshot);
-  if (rc) return rc;
-  for (int it = -1; it < max_iter; ++it) {
-    rc = launch_pass(c, -1, ext, -INFINITY, INFINITY);
-    if (rc) return rc;
-    rc = launch_solve(c, R, 0);
-    if (rc) return rc;
-  }
-  return LIO_OK;
-}
-
 }  // namespace lio
 
 using namespace lio;
@@ -109,14 +95,6 @@ static int create_impl(lio_ctx* c) {
   LIO_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
   const lio_caps& k = c->caps;
-  const char* env = getenv("LIO_QPW_SEARCH");
-  if (env) {
-    const int v = atoi(env);
-    if (v == 4 || v == 8 || v == 16 || v == 32) c->qpw_search = v;
-  }
-  env = getenv("LIO_NO_GRAPH");
-  if (env && atoi(env)) c->use_graph = false;
-
   // map
   c->hash_cap = pow2_at_least((uint64_t)k.max_map_points * 2);
   c->map.hash_mask = c->hash_cap - 1;
@@ -150,9 +128,12 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_near_cnt, 4 * M);
   ALLOC(c->d_selected, M);
   ALLOC(c->d_normvec, sizeof(float4) * M);
-  c->max_tiles = (int)((M + 15) / 16);
-  ALLOC(c->d_partials, 8 * (size_t)LIO_BLOB * c->max_tiles);
+  ALLOC(c->d_partials, 8 * (size_t)LIO_BLOB * pass_grid_blocks(c));
+  LIO_CHECK(c, cudaMemset(c->d_partials, 0, 8 * (size_t)LIO_BLOB * pass_grid_blocks(c)));
   ALLOC(c->d_blob, 8 * LIO_BLOB);
+  ALLOC(c->d_prior, 8 * 288);
+  ALLOC(c->d_sync, 2 * sizeof(unsigned));
+  LIO_CHECK(c, cudaMemset(c->d_sync, 0, 2 * sizeof(unsigned)));
   ALLOC(c->d_cls, M);
   ALLOC(c->d_add_a, sizeof(float4) * M);
   ALLOC(c->d_add_b, sizeof(float4) * M);
@@ -161,17 +142,23 @@ static int create_impl(lio_ctx* c) {
   LIO_CHECK(c, cudaMemset(c->d_near_cnt, 0, 4 * M));
   LIO_CHECK(c, cudaMemset(c->d_blob, 0, 8 * LIO_BLOB));
 
-  // filter state
-  ALLOC(c->d_x, sizeof(StateD));
-  ALLOC(c->d_xprop, sizeof(StateD));
-  ALLOC(c->d_x0, sizeof(StateD));
-  ALLOC(c->d_P, 8 * 576);
-  ALLOC(c->d_P0, 8 * 576);
-  ALLOC(c->d_ctrl, sizeof(Ctrl));
-  ALLOC(c->d_dx, 8 * 24);
-  LIO_CHECK(c, cudaMemset(c->d_ctrl, 0, sizeof(Ctrl)));
-  c->h_pinned_bytes = 8 * (26 + 576 + LIO_BLOB + 64);
+  // filter state: one block so that the prior goes up and the posterior comes down in one copy each
+  {
+    const size_t nd = 606 + 602 + 26 + 24 + 6;
+    ALLOC(c->d_state_blk, 8 * nd);
+    LIO_CHECK(c, cudaMemset(c->d_state_blk, 0, 8 * nd));
+    double* b = c->d_state_blk;
+    c->d_x = reinterpret_cast<StateD*>(b);
+    c->d_P = b + 26;
+    c->d_ctrl = reinterpret_cast<Ctrl*>(b + 602);
+    c->d_x0 = reinterpret_cast<StateD*>(b + 606);
+    c->d_P0 = b + 606 + 26;
+    c->d_xprop = reinterpret_cast<StateD*>(b + 1208);
+    c->d_dx = b + 1234;
+  }
+  c->h_pinned_bytes = 8 * (1280 + LIO_BLOB + 4);
   LIO_CHECK(c, cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
+  LIO_CHECK(c, cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
 
   // preprocess
   const size_t N = (size_t)k.max_scan_points;
@@ -231,15 +218,13 @@ void lio_destroy(lio_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (auto& g : c->graphs)
-    if (g.exec) cudaGraphExecDestroy(g.exec);
   void* ptrs[] = {c->map.table,   c->map.cell_cap,  c->map.cell_pend, c->map.cell_base, c->map.pool,
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
                   c->d_vox_best,  c->d_vox_key,     c->d_scan_m,      c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,
                   c->d_partials,  c->d_blob,        c->d_cls,         c->d_add_a,       c->d_add_b,
-                  c->d_x,         c->d_xprop,       c->d_x0,          c->d_P,           c->d_P0,
-                  c->d_ctrl,      c->d_dx,          c->d_raw,         c->d_raw_aux,     c->d_undist,
+                  c->d_state_blk, c->d_prior,       c->d_sync,
+                  c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
                   c->d_prep_counters};
@@ -247,7 +232,7 @@ void lio_destroy(lio_ctx* c) {
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-  if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
+  if (c->upload_done) cudaEventDestroy(c->upload_done);
   delete c;
 }
 
@@ -258,10 +243,6 @@ int lio_set_stream(lio_ctx* c, void* cuda_stream) {
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   c->own_stream = false;
-  for (auto& g : c->graphs) {
-    if (g.exec) cudaGraphExecDestroy(g.exec);
-    g = lio_ctx::GraphSlot();
-  }
   return LIO_OK;
 }
 
@@ -486,6 +467,13 @@ int lio_scan_upload(lio_ctx* c, const void* down_pts, int64_t m, int stride) {
 }
 
 // ---------------------------------------------------------------- update
+// upload staging area: wait until the previous asynchronous upload has left it
+static int upload_area(lio_ctx* c, double** area) {
+  LIO_CHECK(c, cudaEventSynchronize(c->upload_done));
+  *area = static_cast<double*>(c->h_pinned) + 640;
+  return LIO_OK;
+}
+
 int lio_update_pass(lio_ctx* c, const lio_state* x, int do_search, int extrinsic_est, double blob90[90],
                     int32_t* n_valid) {
   if (!c || !x) return LIO_E_INVALID;
@@ -494,14 +482,15 @@ int lio_update_pass(lio_ctx* c, const lio_state* x, int do_search, int extrinsic
     c->err = "update on an empty map";
     return LIO_E_EMPTY_MAP;
   }
-  double* hp = static_cast<double*>(c->h_pinned);
-  memcpy(hp, x, sizeof(lio_state));
-  LIO_CHECK(c, cudaMemcpyAsync(c->d_x, hp, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
-  int rc = launch_pass(c, do_search ? 1 : 0, extrinsic_est, -INFINITY, INFINITY);
+  double* up = nullptr;
+  int rc = upload_area(c, &up);
   if (rc) return rc;
-  rc = launch_reduce_blob_mode(c, do_search ? 1 : 0);
+  memcpy(up, x, sizeof(lio_state));
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_x, up, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
+  LIO_CHECK(c, cudaEventRecord(c->upload_done, c->stream));
+  rc = launch_pass(c, do_search ? 1 : 0, extrinsic_est ? 1 : 0, -INFINITY, INFINITY);
   if (rc) return rc;
-  double* hb = hp + 26 + 576;
+  double* hb = static_cast<double*>(c->h_pinned) + 1280;
   LIO_CHECK(c, cudaMemcpyAsync(hb, c->d_blob, 8 * LIO_BLOB, cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
   if (blob90) memcpy(blob90, hb, 8 * 90);
@@ -509,29 +498,32 @@ int lio_update_pass(lio_ctx* c, const lio_state* x, int do_search, int extrinsic
   return LIO_OK;
 }
 
+// One H2D copy into the snapshot {x0, P0}; to_current also makes it the current state {x, P}.
+static int state_upload_impl(lio_ctx* c, const lio_state* x, const double P[576], bool to_current) {
+  double* up = nullptr;
+  int rc = upload_area(c, &up);
+  if (rc) return rc;
+  memcpy(up, x, sizeof(lio_state));
+  memcpy(up + 26, P, 8 * 576);
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_x0, up, 8 * 602, cudaMemcpyHostToDevice, c->stream));
+  LIO_CHECK(c, cudaEventRecord(c->upload_done, c->stream));
+  if (to_current) LIO_CHECK(c, cudaMemcpyAsync(c->d_x, c->d_x0, 8 * 602, cudaMemcpyDeviceToDevice, c->stream));
+  return LIO_OK;
+}
+
 int lio_state_upload(lio_ctx* c, const lio_state* x, const double P[576]) {
   if (!c || !x || !P) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
-  double* hp = static_cast<double*>(c->h_pinned);
-  LIO_CHECK(c, cudaStreamSynchronize(c->stream));  // staging buffer reuse
-  memcpy(hp, x, sizeof(lio_state));
-  memcpy(hp + 26, P, 8 * 576);
-  LIO_CHECK(c, cudaMemcpyAsync(c->d_x, hp, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(c->d_P, hp + 26, 8 * 576, cudaMemcpyHostToDevice, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(c->d_x0, c->d_x, sizeof(lio_state), cudaMemcpyDeviceToDevice, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(c->d_P0, c->d_P, 8 * 576, cudaMemcpyDeviceToDevice, c->stream));
-  return LIO_OK;
+  return state_upload_impl(c, x, P, true);
 }
 
 int lio_state_download(lio_ctx* c, lio_state* x, double P[576], int32_t* n_valid_last, int32_t* n_passes) {
   if (!c) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
   double* hp = static_cast<double*>(c->h_pinned);
-  Ctrl* hc = reinterpret_cast<Ctrl*>(hp + 26 + 576 + LIO_BLOB);
-  LIO_CHECK(c, cudaMemcpyAsync(hp, c->d_x, sizeof(lio_state), cudaMemcpyDeviceToHost, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(hp + 26, c->d_P, 8 * 576, cudaMemcpyDeviceToHost, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(hc, c->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(hp, c->d_x, 8 * 606, cudaMemcpyDeviceToHost, c->stream));  // {x, P, ctrl} in one copy
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  const Ctrl* hc = reinterpret_cast<const Ctrl*>(hp + 602);
   if (x) memcpy(x, hp, sizeof(lio_state));
   if (P) memcpy(P, hp + 26, 8 * 576);
   if (n_valid_last) *n_valid_last = hc->n_valid_last;
@@ -546,88 +538,41 @@ int lio_update_enqueue(lio_ctx* c, double R, int max_iter, int extrinsic_est, in
     c->err = "update on an empty map";
     return LIO_E_EMPTY_MAP;
   }
-  extrinsic_est = extrinsic_est ? 1 : 0;
-  from_snapshot = from_snapshot ? 1 : 0;
-  if (!c->use_graph) return enqueue_update_body(c, R, max_iter, extrinsic_est, from_snapshot);
-  lio_ctx::GraphSlot* slot = nullptr;
-  for (auto& g : c->graphs)
-    if (g.exec && g.max_iter == max_iter && g.ext == extrinsic_est && g.snap == from_snapshot && g.R == R) slot = &g;
-  if (!slot) {
-    for (auto& g : c->graphs)
-      if (!g.exec) {
-        slot = &g;
-        break;
-      }
-    if (!slot) {
-      slot = &c->graphs[0];
-      cudaGraphExecDestroy(slot->exec);
-      slot->exec = nullptr;
-    }
-    // make sure module-level one-time initialisation (constant tables) happens outside the capture
-    int rc0 = launch_begin(c, max_iter, 0);
-    if (rc0) return rc0;
-    LIO_CHECK(c, cudaStreamSynchronize(c->stream));
-    const int64_t launches_before = c->launches;
-    cudaGraph_t graph = nullptr;
-    // capture on a private stream (the caller's stream may be the legacy default stream, which cannot be captured);
-    // the instantiated graph is launched on the caller's stream
-    if (!c->capture_stream) LIO_CHECK(c, cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
-    cudaStream_t user_stream = c->stream;
-    c->stream = c->capture_stream;
-    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-    int rc = LIO_OK;
-    if (e == cudaSuccess) {
-      rc = enqueue_update_body(c, R, max_iter, extrinsic_est, from_snapshot);
-      e = cudaStreamEndCapture(c->stream, &graph);
-    }
-    c->stream = user_stream;
-    c->launches = launches_before;
-    if (rc) return rc;
-    LIO_CHECK(c, e);
-    LIO_CHECK(c, cudaGraphInstantiate(&slot->exec, graph, 0));
-    cudaGraphDestroy(graph);
-    slot->max_iter = max_iter;
-    slot->ext = extrinsic_est;
-    slot->snap = from_snapshot;
-    slot->R = R;
-  }
-  LIO_CHECK(c, cudaGraphLaunch(slot->exec, c->stream));
-  c->launches += 1 + 3 * (int64_t)(max_iter + 1);
-  return LIO_OK;
+  return launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, from_snapshot ? 1 : 0);
 }
 
 int lio_update_scan(lio_ctx* c, lio_state* x_io, double P_io[576], double R, int max_iter, int extrinsic_est,
                     int32_t* n_valid_last, int32_t* n_passes) {
-  if (!c || !x_io || !P_io) return LIO_E_INVALID;
-  int rc = lio_state_upload(c, x_io, P_io);
+  if (!c || !x_io || !P_io || max_iter < 0 || max_iter > 32) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (!c->map_built) {
+    c->err = "update on an empty map";
+    return LIO_E_EMPTY_MAP;
+  }
+  // prior up in one copy, one kernel (which starts from the snapshot), posterior down in one copy
+  int rc = state_upload_impl(c, x_io, P_io, false);
   if (rc) return rc;
-  rc = lio_update_enqueue(c, R, max_iter, extrinsic_est, 0);
+  rc = launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, 1);
   if (rc) return rc;
   return lio_state_download(c, x_io, P_io, n_valid_last, n_passes);
 }
 
-int lio_update_begin(lio_ctx* c, int from_snapshot) {
-  if (!c) return LIO_E_INVALID;
+int lio_update_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot) {
+  if (!c || max_iter < 0 || max_iter > 32) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
-  return launch_begin(c, -1 /* set by step_enqueue */, from_snapshot ? 1 : 0);
+  return launch_begin(c, max_iter, extrinsic_est ? 1 : 0, from_snapshot ? 1 : 0);
 }
 
 int lio_update_pass_enqueue(lio_ctx* c, int extrinsic_est, float x_own_min, float x_own_max) {
   if (!c) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
-  int rc = launch_pass(c, -1, extrinsic_est ? 1 : 0, x_own_min, x_own_max);
-  if (rc) return rc;
-  return launch_reduce_blob(c);
+  return launch_pass(c, -1, extrinsic_est ? 1 : 0, x_own_min, x_own_max);
 }
 
-__global__ void set_max_iter_kernel(Ctrl* ctrl, int max_iter) { ctrl->max_iter = max_iter; }
-
-int lio_update_step_enqueue(lio_ctx* c, double R, int max_iter) {
+int lio_update_step_enqueue(lio_ctx* c, double R, int extrinsic_est) {
   if (!c) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
-  set_max_iter_kernel<<<1, 1, 0, c->stream>>>(c->d_ctrl, max_iter);
-  c->launches++;
-  return launch_solve(c, R, 1);
+  return launch_solve(c, R, extrinsic_est ? 1 : 0);
 }
 
 int lio_pass_only_enqueue(lio_ctx* c, int do_search, int extrinsic_est) {

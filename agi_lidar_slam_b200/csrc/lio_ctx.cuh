@@ -40,14 +40,17 @@ struct lio_ctx {
   int* d_near_cnt = nullptr;        // M
   uint8_t* d_selected = nullptr;    // M point_selected_surf
   float4* d_normvec = nullptr;      // M x (a,b,c,pd2)
-  double* d_partials = nullptr;     // max_tiles x LIO_BLOB
-  int max_tiles = 0;
+  double* d_partials = nullptr;     // pass_grid x LIO_BLOB: per-block partial sums of one pass
+  int pass_grid = 0;                // blocks of the persistent update grid (all co-resident)
   double* d_blob = nullptr;         // LIO_BLOB
+  double* d_prior = nullptr;        // 288: P11^-1 and P21 P11^-1 of the current update
+  unsigned* d_sync = nullptr;       // grid barrier words {arrivals, release}
   uint8_t* d_cls = nullptr;         // map_incremental class per point
   float4* d_add_a = nullptr;        // compacted PointToAdd
   float4* d_add_b = nullptr;        // compacted PointNoNeedDownsample
 
   // ---- filter state
+  double* d_state_blk = nullptr;    // one allocation: {x 26, P 576, ctrl 4} {x0 26, P0 576} {xprop 26} {dx 24}
   lio::StateD* d_x = nullptr;       // current state
   lio::StateD* d_xprop = nullptr;   // x_propagated
   double* d_P = nullptr;            // 24x24
@@ -55,8 +58,9 @@ struct lio_ctx {
   double* d_P0 = nullptr;
   lio::Ctrl* d_ctrl = nullptr;
   double* d_dx = nullptr;           // last dx (24)
-  void* h_pinned = nullptr;         // pinned staging (state + P + ctrl + blob)
+  void* h_pinned = nullptr;         // pinned staging: [0,606) download area, [640, 1242) upload area, [1280, ..) blob
   size_t h_pinned_bytes = 0;
+  cudaEvent_t upload_done = nullptr;  // guards reuse of the upload staging area
 
   // ---- preprocess
   float4* d_raw = nullptr;          // N raw points (x,y,z,t_ms)
@@ -76,14 +80,6 @@ struct lio_ctx {
   size_t cub_tmp_bytes = 0;
   int* d_prep_counters = nullptr;   // [0] M, [1..6] key min/max, [7] error
 
-  // ---- whole-update CUDA graphs, keyed by (max_iter, extrinsic_est, from_snapshot)
-  struct GraphSlot {
-    int max_iter = -1, ext = -1, snap = -1;
-    double R = 0;
-    cudaGraphExec_t exec = nullptr;
-  } graphs[8];
-  bool use_graph = true;
-  int qpw_search = 8;   // queries per warp in search passes (tunable: LIO_QPW_SEARCH)
 };
 
 #define LIO_CHECK(ctx, call)                                                                   \
@@ -97,10 +93,12 @@ struct lio_ctx {
 
 namespace lio {
 // launchers implemented in lio_pass.cu / lio_map.cu / lio_preprocess.cu
-int launch_pass(lio_ctx* c, int force_search, int extrinsic_est, float own_min, float own_max);
-int launch_reduce_blob(lio_ctx* c);
-int launch_solve(lio_ctx* c, double R, int external_blob);
-int launch_begin(lio_ctx* c, int max_iter, int from_snapshot);
+int ensure_tables(lio_ctx* c);
+int pass_grid_blocks(lio_ctx* c);
+int launch_update(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot);
+int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float own_max);
+int launch_solve(lio_ctx* c, double R, int extrinsic_est);
+int launch_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot);
 int launch_knn_batch(lio_ctx* c, const float4* d_q, int64_t m);
 
 int map_reset(lio_ctx* c);

@@ -1,4 +1,4 @@
-// Warp-cooperative bounded 5-nearest-neighbour search on the voxel-hash map, and the FP32 plane fit.
+// Group-cooperative bounded 5-nearest-neighbour search on the voxel-hash map, and the FP32 plane fit.
 // Replaces KD_TREE::Nearest_Search (ikd_Tree.cpp:370-402, 960-1101) and esti_plane (common_lib.h:102-134).
 #pragma once
 #include <float.h>
@@ -44,40 +44,72 @@ struct TopK {
   }
 };
 
-// All 32 lanes call this with the SAME query.  Stage 1: lane l < 27 owns neighbour cell
-// (l%3-1, (l/3)%3-1, l/9-1) of the query's cell, walks that cell's float4 bucket and keeps a private top-5.
-// The 3x3x3 block holds every map point closer than `cell` to the query, so if the warp has seen >= 5 points
-// with d2 < cell^2 the result is already exact (the common case at one map point per 0.5 m voxel).  Otherwise
-// stage 2 visits the remaining cells of the (2*rings+1)^3 block whose box distance is within the bound.
-// The warp then extracts the global top-5 with five rounds of redux.min on (d2 bits, id).
-// Outputs are warp-uniform: out_key[r] (d2 bits << 32 | id; ~0 when fewer than r+1 found), out_slot[r].
-__device__ __forceinline__ void warp_scan_cell(const MapView& map, float qx, float qy, float qz, uint32_t max_bits,
-                                               uint32_t start, uint32_t count, TopK& top) {
-  const uint32_t maxc = __reduce_max_sync(0xffffffffu, count);
-  for (uint32_t t = 0; t < maxc; ++t) {
-    if (t < count) {
-      const float4 p = __ldg(map.pool + start + t);
-      const int id = __float_as_int(p.w);
-      if (id >= 0) {
-        const uint32_t db = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
-        if (db <= max_bits) top.insert(((unsigned long long)db << 32) | (uint32_t)id, start + t);
+// One bucket: the cell's float4 slots are contiguous, so a lane streams them with four loads in flight.
+__device__ __forceinline__ void scan_bucket(const MapView& map, float qx, float qy, float qz, uint32_t max_bits,
+                                            uint32_t start, uint32_t count, TopK& top) {
+  for (uint32_t t = 0; t < count; t += 4) {
+    float4 p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (t + j < count) p[j] = __ldg(map.pool + start + t + j);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (t + j < count) {
+        const int id = __float_as_int(p[j].w);
+        if (id >= 0) {
+          const uint32_t db = __float_as_uint(dist2(qx, qy, qz, p[j].x, p[j].y, p[j].z));
+          if (db <= max_bits) top.insert(((unsigned long long)db << 32) | (uint32_t)id, start + t + j);
+        }
       }
-    }
   }
 }
 
-__device__ __forceinline__ int warp_knn5(const MapView& map, float qx, float qy, float qz, float max_d2, int rings,
-                                         unsigned long long out_key[LIO_K], uint32_t out_slot[LIO_K]) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+// A group of G lanes (G = 8, 16 or 32, aligned inside a warp) calls this with the SAME query; `gmask` names the
+// group's lanes, `gl` is the lane's index inside the group.
+// Stage 1: the 27 cells of the 3x3x3 block around the query's cell are dealt round-robin to the lanes; a lane
+// first issues the hash probes of all its cells (independent loads), then walks each cell's float4 bucket keeping
+// a private top-5.  The block holds every map point closer than `cell` to the query, so if the group has seen >= 5
+// points with d2 < cell^2 the result is already exact (the common case at one map point per 0.5 m voxel).
+// Otherwise stage 2 visits the remaining cells of the (2*rings+1)^3 block whose box distance is within the bound.
+// The group then extracts the global top-5 with five rounds of redux.min on (d2 bits, id).
+// Outputs are group-uniform: out_key[r] (d2 bits << 32 | id; ~0 when fewer than r+1 found), out_slot[r].
+template <int G>
+__device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy, float qz, float max_d2, int rings,
+                                          unsigned gmask, int gl, unsigned long long out_key[LIO_K],
+                                          uint32_t out_slot[LIO_K]) {
+  constexpr int CPL = (27 + G - 1) / G;  // cells per lane in stage 1
   const int cx = cell_coord(qx, map.inv_cell), cy = cell_coord(qy, map.inv_cell), cz = cell_coord(qz, map.inv_cell);
   TopK top;
   top.init();
   const uint32_t max_bits = __float_as_uint(max_d2);
   {
-    uint32_t start = 0, count = 0;
-    if (lane < 27) map_find(map, pack_cell(cx + lane % 3 - 1, cy + (lane / 3) % 3 - 1, cz + lane / 9 - 1), start, count);
-    warp_scan_cell(map, qx, qy, qz, max_bits, start, count, top);
+    unsigned long long key[CPL];
+    uint32_t h[CPL];
+    uint4 e[CPL];
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+      const int c = gl + u * G;
+      key[u] = LIO_EMPTY_KEY;
+      if (c < 27) {
+        key[u] = pack_cell(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1);
+        h[u] = hash64(key[u]) & map.hash_mask;
+        e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+      if (key[u] == LIO_EMPTY_KEY) continue;
+      for (;;) {
+        const unsigned long long k = ((unsigned long long)e[u].y << 32) | e[u].x;
+        if (k == key[u]) {
+          scan_bucket(map, qx, qy, qz, max_bits, e[u].z, e[u].w, top);
+          break;
+        }
+        if (k == LIO_EMPTY_KEY) break;
+        h[u] = (h[u] + 1) & map.hash_mask;
+        e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
+      }
+    }
   }
   if (rings > 1) {
     // exact already?  (0.999: any unseen point has true distance > cell, so its rounded d2 exceeds this bound)
@@ -85,13 +117,12 @@ __device__ __forceinline__ int warp_knn5(const MapView& map, float qx, float qy,
     const int mine = (int)((uint32_t)(top.k0 >> 32) <= near_bits) + (int)((uint32_t)(top.k1 >> 32) <= near_bits) +
                      (int)((uint32_t)(top.k2 >> 32) <= near_bits) + (int)((uint32_t)(top.k3 >> 32) <= near_bits) +
                      (int)((uint32_t)(top.k4 >> 32) <= near_bits);
-    const int seen = __reduce_add_sync(FULL, mine);
+    const int seen = __reduce_add_sync(gmask, mine);
     if (seen < LIO_K) {
       const int side = 2 * rings + 1;
       const int ncell = side * side * side;
-      for (int base = 0; base < ncell; base += 32) {
-        const int c = base + lane;
-        uint32_t start = 0, count = 0;
+      for (int base = 0; base < ncell; base += G) {
+        const int c = base + gl;
         if (c < ncell) {
           const int dx = c % side - rings, dy = (c / side) % side - rings, dz = c / (side * side) - rings;
           const bool inner = (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1);
@@ -102,11 +133,13 @@ __device__ __forceinline__ int warp_knn5(const MapView& map, float qx, float qy,
             const float ey = fmaxf(fmaxf(ly - qy, qy - (ly + map.cell)), 0.f);
             const float ez = fmaxf(fmaxf(lz - qz, qz - (lz + map.cell)), 0.f);
             // conservative (shrunk by 1e-3 relative) so rounding can never skip a cell that matters
-            if ((ex * ex + ey * ey + ez * ez) * 0.999f <= max_d2)
-              map_find(map, pack_cell(cx + dx, cy + dy, cz + dz), start, count);
+            if ((ex * ex + ey * ey + ez * ez) * 0.999f <= max_d2) {
+              uint32_t start, count;
+              if (map_find(map, pack_cell(cx + dx, cy + dy, cz + dz), start, count) >= 0)
+                scan_bucket(map, qx, qy, qz, max_bits, start, count, top);
+            }
           }
         }
-        warp_scan_cell(map, qx, qy, qz, max_bits, start, count, top);
       }
     }
   }
@@ -114,23 +147,30 @@ __device__ __forceinline__ int warp_knn5(const MapView& map, float qx, float qy,
 #pragma unroll
   for (int r = 0; r < LIO_K; ++r) {
     const uint32_t hi = (uint32_t)(top.k0 >> 32);
-    const uint32_t mhi = __reduce_min_sync(FULL, hi);
+    const uint32_t mhi = __reduce_min_sync(gmask, hi);
     const uint32_t lo = (hi == mhi) ? (uint32_t)top.k0 : 0xffffffffu;
-    const uint32_t mlo = __reduce_min_sync(FULL, lo);
+    const uint32_t mlo = __reduce_min_sync(gmask, lo);
     const bool win = (hi == mhi) && ((uint32_t)top.k0 == mlo) && (top.k0 != ~0ull);
-    const unsigned wmask = __ballot_sync(FULL, win);
+    const unsigned wmask = __ballot_sync(gmask, win) & gmask;
     if (wmask == 0) {
       out_key[r] = ~0ull;
       out_slot[r] = 0;
     } else {
       const int wl = __ffs(wmask) - 1;
       out_key[r] = ((unsigned long long)mhi << 32) | mlo;
-      out_slot[r] = __shfl_sync(FULL, top.s0, wl);
-      if (lane == wl) top.pop();
+      out_slot[r] = __shfl_sync(gmask, top.s0, wl);
+      if ((int)(threadIdx.x & 31) == wl) top.pop();
       ++found;
     }
   }
   return found;
+}
+
+// Lanes of the aligned G-lane group that contains `lane`.
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  constexpr unsigned ones = (G >= 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  return ones << (lane & ~(G - 1) & 31);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -262,8 +302,7 @@ __device__ __forceinline__ bool esti_plane(const float4 P[5], float thr, float p
       y[i] = s / A[i][i];
     }
   }
-  // un-permute (column transpositions in reverse)
-  if (trans[2] != 2) { /* trans[2] can only be 2 */ }
+  // un-permute (column transpositions in reverse; trans[2] can only be 2)
   if (trans[1] == 2) LIO_SWAPF(y[1], y[2]);
   if (trans[0] == 1) LIO_SWAPF(y[0], y[1]);
   if (trans[0] == 2) LIO_SWAPF(y[0], y[2]);

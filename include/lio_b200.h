@@ -146,17 +146,18 @@ int lio_update_scan(lio_ctx* ctx, lio_state* x_io, double P_io[576], double R, i
 /* Device-resident pieces of the above (used by bench.py and by the multi-GPU sharded-map driver):        */
 int lio_state_upload(lio_ctx* ctx, const lio_state* x, const double P[576]); /* also stored as the prior snapshot */
 int lio_state_download(lio_ctx* ctx, lio_state* x, double P[576], int32_t* n_valid_last, int32_t* n_passes);
-/* Enqueue the whole update on the context stream; no host sync.  from_snapshot != 0 first restores the state
+/* Enqueue the whole update (one persistent cooperative kernel) on the context stream; no host sync.  from_snapshot != 0 first restores the state
  * uploaded by lio_state_upload (so a benchmark can repeat the same update). */
 int lio_update_enqueue(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, int from_snapshot);
 /* Sharded-map driver: begin, then per pass {pass_enqueue -> all-reduce 92 doubles at
  * lio_blob_device_ptr -> step_enqueue}.  x_own_min/max restrict the queries this rank owns to
- * x_own_min <= p_world.x < x_own_max (use -inf/+inf for a single GPU). */
-int lio_update_begin(lio_ctx* ctx, int from_snapshot);
+ * x_own_min <= p_world.x < x_own_max (use -inf/+inf for a single GPU).  begin resets the loop state
+ * (x_propagated = x, converge = true, ...) and forms the per-update constants of the Kalman step. */
+int lio_update_begin(lio_ctx* ctx, int max_iter, int extrinsic_est, int from_snapshot);
 int lio_update_pass_enqueue(lio_ctx* ctx, int extrinsic_est, float x_own_min, float x_own_max);
-int lio_update_step_enqueue(lio_ctx* ctx, double R, int max_iter);
-/* Instrumentation: enqueue ONLY the fused pass kernel (search or cached variant) at the device-resident state, with
- * no reduction / solve behind it, so that bench.py can bracket exactly that kernel with CUDA events. */
+int lio_update_step_enqueue(lio_ctx* ctx, double R, int extrinsic_est);
+/* Instrumentation: enqueue ONE h_share_model pass (search or cached) at the device-resident state with no Kalman
+ * step behind it, so that bench.py can bracket exactly that kernel with CUDA events. */
 int lio_pass_only_enqueue(lio_ctx* ctx, int do_search, int extrinsic_est);
 /* Device pointer of the 92-double reduction blob {HtH 78, Hth 12, n_valid, n_searched} written by pass_enqueue. */
 void* lio_blob_device_ptr(lio_ctx* ctx);

@@ -122,3 +122,20 @@ def test_sharded_ownership_sums_to_whole(ctx, orc, small_cfg):
     tot = parts[0] + parts[1]
     assert int(tot[90]) == nv and 0 < int(parts[0][90]) < nv
     assert rel_err(tot[:90], full) < 1e-12
+
+
+@pytest.mark.parametrize("ext", [False, True])
+def test_stepwise_driver_equals_persistent_kernel(ctx, orc, small_cfg, ext):
+    """begin -> {pass_enqueue, step_enqueue} x (max_iter + 1) (the sharded-map driver's sequence, where an all-reduce
+    sits between the two) runs the same device code as the single persistent launch: bit-identical posterior."""
+    cfg = small_cfg
+    _setup(ctx, cfg, orc)
+    a = ctx.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, ext)
+    ctx.state_upload(cfg["x_prior"], cfg["P"])
+    ctx.update_begin(4, ext, True)
+    for _ in range(5):
+        ctx.update_pass_enqueue(ext)
+        ctx.update_step_enqueue(0.001, ext)
+    c = ctx.state_download()
+    assert a[2:] == c[2:]
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
