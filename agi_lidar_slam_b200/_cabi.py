@@ -55,7 +55,7 @@ EXPORTS = [
     "lio_map_dump", "lio_knn5", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
-    "lio_blob_download", "lio_pass_only_enqueue",
+    "lio_blob_download", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_predict", "lio_boxplus", "lio_boxminus",
 ]  # fmt: skip
 
@@ -104,6 +104,7 @@ def load_library() -> C.CDLL:
         "lio_blob_device_ptr": (vp, [vp]),
         "lio_blob_download": (C.c_int, [vp, vp]),
         "lio_pass_only_enqueue": (C.c_int, [vp, C.c_int, C.c_int]),
+        "lio_debug_timeline": (C.c_int, [vp, vp]),
         "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "lio_map_incremental": (C.c_int, [vp, vp, f32, C.c_int, vp]),
         "lio_predict": (C.c_int, [vp, vp, f64, vp, vp, vp]),
@@ -313,6 +314,14 @@ class Context:
 
     def pass_only_enqueue(self, do_search: bool, extrinsic_est=False):
         self._check(self._lib.lio_pass_only_enqueue(self._h, int(do_search), int(extrinsic_est)))
+
+    def debug_timeline(self):
+        """[(tag, ns)] of block 0 and of the solving block (needs LIO_TIMELINE=1 at context creation)."""
+        t = np.zeros(256, np.int64)
+        self._check(self._lib.lio_debug_timeline(self._h, _ptr(t)))
+        a = [(int(t[1 + 2 * k]), int(t[2 + 2 * k])) for k in range(int(t[0]))]
+        b = [(int(t[129 + 2 * k]), int(t[130 + 2 * k])) for k in range(int(t[128]))]
+        return a, b
 
     def blob_download(self):
         b = np.zeros(BLOB, np.float64)

@@ -67,7 +67,7 @@ void lio_default_caps(lio_caps* caps) {
   caps->max_scan_points = 262144;
   caps->max_down_points = 100000;  // esekfom.hpp:23-29
   caps->max_map_points = 4194304;
-  caps->map_cell = 1.0f;
+  caps->map_cell = 1.5f;  // 3x3x3 block covers 1.5 m: the 5th neighbour is almost always inside
   caps->knn_max_d2 = 5.0f;      // esekfom.hpp:147
   caps->plane_thr = 0.1f;       // esekfom.hpp:157
   caps->map_downsample = 0.5f;  // filter_size_map (launch files)
@@ -134,6 +134,13 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_prior, 8 * 288);
   ALLOC(c->d_sync, 2 * sizeof(unsigned));
   LIO_CHECK(c, cudaMemset(c->d_sync, 0, 2 * sizeof(unsigned)));
+  {
+    const char* env = getenv("LIO_TIMELINE");
+    if (env && atoi(env)) {
+      ALLOC(c->d_dbg, 256 * sizeof(long long));
+      LIO_CHECK(c, cudaMemset(c->d_dbg, 0, 256 * sizeof(long long)));
+    }
+  }
   ALLOC(c->d_cls, M);
   ALLOC(c->d_add_a, sizeof(float4) * M);
   ALLOC(c->d_add_b, sizeof(float4) * M);
@@ -223,7 +230,7 @@ void lio_destroy(lio_ctx* c) {
                   c->d_vox_best,  c->d_vox_key,     c->d_scan_m,      c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,
                   c->d_partials,  c->d_blob,        c->d_cls,         c->d_add_a,       c->d_add_b,
-                  c->d_state_blk, c->d_prior,       c->d_sync,
+                  c->d_state_blk, c->d_prior,       c->d_sync,        c->d_dbg,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
@@ -580,6 +587,18 @@ int lio_pass_only_enqueue(lio_ctx* c, int do_search, int extrinsic_est) {
   LIO_CHECK(c, cudaSetDevice(c->device));
   if (do_search && !c->map_built) return LIO_E_EMPTY_MAP;
   return launch_pass(c, do_search ? 1 : 0, extrinsic_est ? 1 : 0, -INFINITY, INFINITY);
+}
+
+int lio_debug_timeline(lio_ctx* c, int64_t out[256]) {
+  if (!c || !out) return LIO_E_INVALID;
+  if (!c->d_dbg) {
+    c->err = "timeline not enabled (set LIO_TIMELINE=1 before lio_create)";
+    return LIO_E_INVALID;
+  }
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  LIO_CHECK(c, cudaMemcpy(out, c->d_dbg, 256 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return LIO_OK;
 }
 
 void* lio_blob_device_ptr(lio_ctx* c) { return c ? c->d_blob : nullptr; }

@@ -134,7 +134,7 @@ __host__ __device__ __forceinline__ Quatd quat_normalized(Quatd q) {
   const double n = sqrt(((q.w * q.w + q.x * q.x) + q.y * q.y) + q.z * q.z);
   return Quatd{q.w / n, q.x / n, q.y / n, q.z / n};
 }
-__host__ __device__ __forceinline__ Quatd quat_mul(const Quatd& a, const Quatd& b) {
+__host__ __device__ __noinline__ inline Quatd quat_mul(const Quatd& a, const Quatd& b) {
   Quatd r;
   r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
   r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
@@ -142,7 +142,7 @@ __host__ __device__ __forceinline__ Quatd quat_mul(const Quatd& a, const Quatd& 
   r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
   return quat_normalized(r);
 }
-__host__ __device__ __forceinline__ Quatd mat_to_quat(const double m[9]) {
+__host__ __device__ __noinline__ inline Quatd mat_to_quat(const double m[9]) {
   Quatd q;
   double t = m[0] + m[4] + m[8];
   if (t > 0.0) {
@@ -171,7 +171,7 @@ __host__ __device__ __forceinline__ Quatd mat_to_quat(const double m[9]) {
   return quat_normalized(q);
 }
 // Sophus::SO3::exp / log (old, quaternion-backed)
-__host__ __device__ __forceinline__ Quatd so3_exp(const double w[3]) {
+__host__ __device__ __noinline__ inline Quatd so3_exp(const double w[3]) {
   const double theta = sqrt((w[0] * w[0] + w[1] * w[1]) + w[2] * w[2]);
   const double half = 0.5 * theta;
   double imag, real;
@@ -185,7 +185,7 @@ __host__ __device__ __forceinline__ Quatd so3_exp(const double w[3]) {
   }
   return quat_normalized(Quatd{real, imag * w[0], imag * w[1], imag * w[2]});
 }
-__host__ __device__ __forceinline__ void so3_log(const Quatd& q, double o[3]) {
+__host__ __device__ __noinline__ inline void so3_log(const Quatd& q, double o[3]) {
   const double n = sqrt((q.x * q.x + q.y * q.y) + q.z * q.z);
   const double w = q.w;
   double f;
@@ -214,7 +214,7 @@ struct StateD {
 };
 static_assert(sizeof(StateD) == sizeof(lio_state), "state layout");
 
-__host__ __device__ inline void boxplus(const StateD& x, const double f[24], StateD& r) {
+__host__ __device__ __noinline__ inline void boxplus(const StateD& x, const double f[24], StateD& r) {
   r = x;
   for (int i = 0; i < 3; ++i) r.pos[i] = x.pos[i] + f[i];
   r.rot = quat_mul(x.rot, so3_exp(f + 3));
@@ -227,7 +227,7 @@ __host__ __device__ inline void boxplus(const StateD& x, const double f[24], Sta
     r.grav[i] = x.grav[i] + f[21 + i];
   }
 }
-__host__ __device__ inline void boxminus(const StateD& x1, const StateD& x2, double o[24]) {
+__host__ __device__ __noinline__ inline void boxminus(const StateD& x1, const StateD& x2, double o[24]) {
   double R1[9], R2[9], D[9];
   for (int i = 0; i < 3; ++i) o[i] = x1.pos[i] - x2.pos[i];
   quat_to_mat(x1.rot, R1);

@@ -45,6 +45,7 @@ struct lio_ctx {
   double* d_blob = nullptr;         // LIO_BLOB
   double* d_prior = nullptr;        // 288: P11^-1 and P21 P11^-1 of the current update
   unsigned* d_sync = nullptr;       // grid barrier words {arrivals, release}
+  long long* d_dbg = nullptr;       // in-kernel timeline (only with LIO_TIMELINE=1)
   uint8_t* d_cls = nullptr;         // map_incremental class per point
   float4* d_add_a = nullptr;        // compacted PointToAdd
   float4* d_add_b = nullptr;        // compacted PointNoNeedDownsample

@@ -45,22 +45,26 @@ struct TopK {
 };
 
 // One bucket: the cell's float4 slots are contiguous, so a lane streams them with four loads in flight.
+// Code size matters more than instruction count here (the pass has to stay inside the 32 KB L1.5 instruction cache),
+// so the loop over buckets is NOT unrolled around this.
 __device__ __forceinline__ void scan_bucket(const MapView& map, float qx, float qy, float qz, uint32_t max_bits,
                                             uint32_t start, uint32_t count, TopK& top) {
+#pragma unroll 1
   for (uint32_t t = 0; t < count; t += 4) {
     float4 p[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (t + j < count) p[j] = __ldg(map.pool + start + t + j);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (t + j < count) {
-        const int id = __float_as_int(p[j].w);
-        if (id >= 0) {
-          const uint32_t db = __float_as_uint(dist2(qx, qy, qz, p[j].x, p[j].y, p[j].z));
-          if (db <= max_bits) top.insert(((unsigned long long)db << 32) | (uint32_t)id, start + t + j);
-        }
-      }
+    for (int j = 0; j < 4; ++j) p[j] = __ldg(map.pool + start + min(t + j, count - 1));
+    const uint32_t nj = min(4u, count - t);
+#pragma unroll 1
+    for (uint32_t j = 0; j < nj; ++j) {
+      float4 q = p[0];  // static selects keep p[] in registers; ONE copy of the insertion code
+      if (j == 1) q = p[1];
+      if (j == 2) q = p[2];
+      if (j == 3) q = p[3];
+      const int id = __float_as_int(q.w);
+      const uint32_t db = __float_as_uint(dist2(qx, qy, qz, q.x, q.y, q.z));
+      if (id >= 0 && db <= max_bits) top.insert(((unsigned long long)db << 32) | (uint32_t)id, start + t + j);
+    }
   }
 }
 
@@ -90,24 +94,37 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
     for (int u = 0; u < CPL; ++u) {
       const int c = gl + u * G;
       key[u] = LIO_EMPTY_KEY;
+      h[u] = 0;
+      e[u] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
       if (c < 27) {
         key[u] = pack_cell(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1);
         h[u] = hash64(key[u]) & map.hash_mask;
         e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
       }
     }
-#pragma unroll
+#pragma unroll 1
     for (int u = 0; u < CPL; ++u) {
-      if (key[u] == LIO_EMPTY_KEY) continue;
+      // static selects instead of dynamic indexing (keeps the arrays in registers)
+      unsigned long long ku = key[0];
+      uint32_t hu = h[0];
+      uint4 eu = e[0];
+#pragma unroll
+      for (int v = 1; v < CPL; ++v)
+        if (u == v) {
+          ku = key[v];
+          hu = h[v];
+          eu = e[v];
+        }
+      if (ku == LIO_EMPTY_KEY) continue;
       for (;;) {
-        const unsigned long long k = ((unsigned long long)e[u].y << 32) | e[u].x;
-        if (k == key[u]) {
-          scan_bucket(map, qx, qy, qz, max_bits, e[u].z, e[u].w, top);
+        const unsigned long long k = ((unsigned long long)eu.y << 32) | eu.x;
+        if (k == ku) {
+          scan_bucket(map, qx, qy, qz, max_bits, eu.z, eu.w, top);
           break;
         }
         if (k == LIO_EMPTY_KEY) break;
-        h[u] = (h[u] + 1) & map.hash_mask;
-        e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
+        hu = (hu + 1) & map.hash_mask;
+        eu = __ldg(reinterpret_cast<const uint4*>(map.table + hu));
       }
     }
   }
@@ -121,6 +138,7 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
     if (seen < LIO_K) {
       const int side = 2 * rings + 1;
       const int ncell = side * side * side;
+#pragma unroll 1
       for (int base = 0; base < ncell; base += G) {
         const int c = base + gl;
         if (c < ncell) {
@@ -185,7 +203,7 @@ __device__ __forceinline__ unsigned group_mask(int lane) {
     (b) = _t;           \
   }
 
-__device__ __forceinline__ bool esti_plane(const float4 P[5], float thr, float pabcd[4]) {
+__device__ __noinline__ bool esti_plane(const float4 P[5], float thr, float pabcd[4]) {
   float A[5][3];
 #pragma unroll
   for (int i = 0; i < 5; ++i) {

@@ -48,8 +48,26 @@ struct PassArgs {
   float max_d2, plane_thr;
   int rings;
   float own_min, own_max;
-  double* partials;  // [gridDim][LIO_BLOB]
+  double* partials;  // [LIO_BLOB][gridDim]: element e of block b at e * gridDim + b (coalesced grid reduction)
+  long long* dbg;    // optional timeline (LIO_TIMELINE=1): [0] = entries used by block 0, [1..] = (tag, globaltimer ns)
 };
+
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// block 0 / thread 0 appends (tag, time) pairs from slot 1; the solving block's thread 0 appends from slot 129
+__device__ __forceinline__ void stamp(long long* dbg, int base, int tag) {
+  if (dbg == nullptr || threadIdx.x != 0) return;
+  if (base == 0 && blockIdx.x != 0) return;
+  const long long n = dbg[base];
+  if (n < 62) {
+    dbg[base + 1 + 2 * n] = tag;
+    dbg[base + 2 + 2 * n] = global_ns();
+    dbg[base] = n + 1;
+  }
+}
 
 struct SolveArgs {
   StateD* x;
@@ -65,6 +83,7 @@ struct SolveArgs {
   double R;
   int max_iter;
   int from_snapshot;
+  long long* dbg;
 };
 
 // per-pass constants shared by the block
@@ -100,63 +119,6 @@ __device__ __forceinline__ void load_pass_const(const StateD* x, PassConst& pc) 
   quat_to_mat(pc.rli, pc.Rli);
 }
 
-// steps 1.4-3 of h_share_model for one point whose neighbours are known (esekfom.hpp:144-226)
-__device__ __forceinline__ void finish_point(const PassArgs& a, const PassConst& pc, int i, const double pb[3], float pwx,
-                                             float pwy, float pwz, const float4 nb[LIO_K], bool sel, double* row,
-                                             unsigned char* valid_out) {
-  float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
-  float pd2 = 0.f;
-  if (sel) {
-    sel = false;
-    if (esti_plane(nb, a.plane_thr, pabcd)) {
-      pd2 = ((pabcd[0] * pwx + pabcd[1] * pwy) + pabcd[2] * pwz) + pabcd[3];
-      const double nrm = sqrt((pb[0] * pb[0] + pb[1] * pb[1]) + pb[2] * pb[2]);
-      const float sc = (float)(1.0 - 0.9 * fabs((double)pd2) / sqrt(nrm));
-      if ((double)sc > 0.9) sel = true;
-    }
-  }
-  a.selected[i] = sel ? 1 : 0;
-  if (sel) a.normvec[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
-  const bool valid = sel && (pwx >= a.own_min) && (pwx < a.own_max);
-  *valid_out = valid ? 1 : 0;
-  if (valid) {
-    double pI[3], C[3], A[3];
-    quat_rotate(pc.rli, pb, pI);
-    pI[0] += pc.tli[0];
-    pI[1] += pc.tli[1];
-    pI[2] += pc.tli[2];
-    const double nv[3] = {(double)pabcd[0], (double)pabcd[1], (double)pabcd[2]};
-    mat3T_vec(pc.Rt, nv, C);
-    const double pIx[9] = {0.0, -pI[2], pI[1], pI[2], 0.0, -pI[0], -pI[1], pI[0], 0.0};
-    mat3_vec(pIx, C, A);
-    row[0] = nv[0];
-    row[1] = nv[1];
-    row[2] = nv[2];
-    row[3] = A[0];
-    row[4] = A[1];
-    row[5] = A[2];
-    if (a.extrinsic_est) {
-      double M1[9], B[3];
-      const double px[9] = {0.0, -pb[2], pb[1], pb[2], 0.0, -pb[0], -pb[1], pb[0], 0.0};
-      for (int r = 0; r < 3; ++r)
-        for (int c2 = 0; c2 < 3; ++c2)
-          M1[3 * r + c2] =
-              (px[3 * r] * pc.Rli[3 * c2] + px[3 * r + 1] * pc.Rli[3 * c2 + 1]) + px[3 * r + 2] * pc.Rli[3 * c2 + 2];
-      mat3_vec(M1, C, B);
-      row[6] = B[0];
-      row[7] = B[1];
-      row[8] = B[2];
-      row[9] = C[0];
-      row[10] = C[1];
-      row[11] = C[2];
-    } else {
-      row[6] = row[7] = row[8] = row[9] = row[10] = row[11] = 0.0;
-    }
-    row[12] = -(double)pd2;  // esekfom.hpp:225
-    row[13] = 1.0;
-  }
-}
-
 // step 1.1-1.2 (esekfom.hpp:123-133): p_world = rot * (R_LI * p + t_LI) + pos, FP64 -> FP32
 __device__ __forceinline__ void body_to_world(const PassConst& pc, const double pb[3], float& pwx, float& pwy,
                                               float& pwz) {
@@ -171,55 +133,61 @@ __device__ __forceinline__ void body_to_world(const PassConst& pc, const double 
   pwz = (float)(pg[2] + pc.pos[2]);
 }
 
-// One tile of a search pass: THREADS / G queries, one per G-lane group.
+constexpr int SROWS_MAX = THREADS / 8;  // rows of a search tile at the smallest group size
+
+// Search phase of one tile: THREADS / G queries, one per G-lane group (esekfom.hpp:140).  The 5 neighbours go to
+// the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.
 template <int G>
-__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int M, int tile, double* s_rows,
-                                            unsigned char* s_valid) {
+__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int M, int tile, float4* s_nb,
+                                         int* s_cnt) {
   constexpr int ROWS = THREADS / G;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const unsigned gmask = group_mask<G>(lane);
   const int row = threadIdx.x / G;
   const int i = tile * ROWS + row;
-  if (i >= M) {  // group-uniform
-    if (gl == 0) s_valid[row] = 0;
-    return;
-  }
+  if (i >= M) return;  // group-uniform
   const float4 b = __ldg(a.body + i);
   const double pb[3] = {b.x, b.y, b.z};
   float pwx, pwy, pwz;
   body_to_world(pc, pb, pwx, pwy, pwz);
   unsigned long long key[LIO_K];
   uint32_t slot[LIO_K];
-  const int cnt = group_knn5<G>(a.map, pwx, pwy, pwz, a.max_d2, a.rings, gmask, gl, key, slot);  // esekfom.hpp:140
-  if (gl != 0) return;
-  a.world[i] = make_float4(pwx, pwy, pwz, b.w);
-  float4 nb[LIO_K];
-  float d2[LIO_K];
+  const int cnt = group_knn5<G>(a.map, pwx, pwy, pwz, a.max_d2, a.rings, gmask, gl, key, slot);
+  // lanes 0..4 of the group fetch and publish one neighbour each
+  if (gl < LIO_K) {
+    unsigned long long k = key[0];
+    uint32_t sl = slot[0];
 #pragma unroll
-  for (int r = 0; r < LIO_K; ++r) {
-    if (r < cnt) {
-      nb[r] = __ldg(a.map.pool + slot[r]);
-      d2[r] = __uint_as_float((uint32_t)(key[r] >> 32));
-    } else {
-      nb[r] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-      d2[r] = CUDART_INF_F;
+    for (int r = 1; r < LIO_K; ++r)
+      if (gl == r) {
+        k = key[r];
+        sl = slot[r];
+      }
+    float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    float d = CUDART_INF_F;
+    if (gl < cnt) {
+      v = __ldg(a.map.pool + sl);
+      d = __uint_as_float((uint32_t)(k >> 32));
     }
+    s_nb[row * LIO_K + gl] = v;
+    a.near_pts[(size_t)i * LIO_K + gl] = v;
+    a.near_d2[(size_t)i * LIO_K + gl] = d;
   }
-#pragma unroll
-  for (int r = 0; r < LIO_K; ++r) {
-    a.near_pts[(size_t)i * LIO_K + r] = nb[r];
-    a.near_d2[(size_t)i * LIO_K + r] = d2[r];
+  if (gl == 0) {
+    // step 1.4 (esekfom.hpp:144-147): gate on the count and on the 5th squared distance
+    const float d4 = __uint_as_float((uint32_t)(key[LIO_K - 1] >> 32));
+    const bool sel = (cnt < LIO_K) ? false : (d4 > 5.0f ? false : true);
+    s_cnt[row] = sel ? 1 : 0;
+    a.near_cnt[i] = cnt;
   }
-  a.near_cnt[i] = cnt;
-  // step 1.4 (esekfom.hpp:144-147)
-  const bool sel = (cnt < LIO_K) ? false : (d2[LIO_K - 1] > 5.0f ? false : true);
-  finish_point(a, pc, i, pb, pwx, pwy, pwz, nb, sel, s_rows + row * RS, s_valid + row);
 }
 
-// One tile of a non-search pass: `rows` points, one per thread, neighbours and the sticky mask from the last search.
-__device__ __noinline__ void cached_tile(const PassArgs& a, const PassConst& pc, int M, int tile, int rows,
-                                            double* s_rows, unsigned char* s_valid) {
+// Finish phase of one tile, one thread per point: steps 1.1-1.2 and 1.5-3 of h_share_model (esekfom.hpp:123-133,
+// 153-226) from the point's 5 neighbours (just found: shared memory; cached: a.near_pts with the sticky mask).
+__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int M, int tile, int rows, bool search,
+                                         const float4* s_nb, const int* s_cnt, double* s_rows,
+                                         unsigned char* s_valid) {
   const int row = threadIdx.x;
   if (row >= rows) return;
   const int i = tile * rows + row;
@@ -233,162 +201,146 @@ __device__ __noinline__ void cached_tile(const PassArgs& a, const PassConst& pc,
   body_to_world(pc, pb, pwx, pwy, pwz);
   a.world[i] = make_float4(pwx, pwy, pwz, b.w);
   float4 nb[LIO_K];
+  bool sel;
+  if (search) {
 #pragma unroll
-  for (int r = 0; r < LIO_K; ++r) nb[r] = __ldcg(a.near_pts + (size_t)i * LIO_K + r);
-  const bool sel = __ldcg(a.selected + i) != 0;  // sticky between search passes (esekfom.hpp:150)
-  finish_point(a, pc, i, pb, pwx, pwy, pwz, nb, sel, s_rows + row * RS, s_valid + row);
+    for (int r = 0; r < LIO_K; ++r) nb[r] = s_nb[row * LIO_K + r];
+    sel = s_cnt[row] != 0;
+  } else {
+#pragma unroll
+    for (int r = 0; r < LIO_K; ++r) nb[r] = __ldcg(a.near_pts + (size_t)i * LIO_K + r);
+    sel = __ldcg(a.selected + i) != 0;  // sticky between search passes (esekfom.hpp:150)
+  }
+  float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
+  float pd2 = 0.f;
+  if (sel) {
+    sel = false;
+    if (esti_plane(nb, a.plane_thr, pabcd)) {
+      pd2 = ((pabcd[0] * pwx + pabcd[1] * pwy) + pabcd[2] * pwz) + pabcd[3];
+      const double nrm = sqrt((pb[0] * pb[0] + pb[1] * pb[1]) + pb[2] * pb[2]);
+      const float sc = (float)(1.0 - 0.9 * fabs((double)pd2) / sqrt(nrm));
+      if ((double)sc > 0.9) sel = true;
+    }
+  }
+  a.selected[i] = sel ? 1 : 0;
+  if (sel) a.normvec[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
+  const bool valid = sel && (pwx >= a.own_min) && (pwx < a.own_max);
+  s_valid[row] = valid ? 1 : 0;
+  if (valid) {
+    // step 3 (esekfom.hpp:197-226): Jacobian row and residual
+    double* rowp = s_rows + row * RS;
+    double pI[3], C[3], A[3];
+    quat_rotate(pc.rli, pb, pI);
+    pI[0] += pc.tli[0];
+    pI[1] += pc.tli[1];
+    pI[2] += pc.tli[2];
+    const double nv[3] = {(double)pabcd[0], (double)pabcd[1], (double)pabcd[2]};
+    mat3T_vec(pc.Rt, nv, C);
+    const double pIx[9] = {0.0, -pI[2], pI[1], pI[2], 0.0, -pI[0], -pI[1], pI[0], 0.0};
+    mat3_vec(pIx, C, A);
+    rowp[0] = nv[0];
+    rowp[1] = nv[1];
+    rowp[2] = nv[2];
+    rowp[3] = A[0];
+    rowp[4] = A[1];
+    rowp[5] = A[2];
+    if (a.extrinsic_est) {
+      double M1[9], B[3];
+      const double px[9] = {0.0, -pb[2], pb[1], pb[2], 0.0, -pb[0], -pb[1], pb[0], 0.0};
+      for (int r = 0; r < 3; ++r)
+        for (int c2 = 0; c2 < 3; ++c2)
+          M1[3 * r + c2] =
+              (px[3 * r] * pc.Rli[3 * c2] + px[3 * r + 1] * pc.Rli[3 * c2 + 1]) + px[3 * r + 2] * pc.Rli[3 * c2 + 2];
+      mat3_vec(M1, C, B);
+      rowp[6] = B[0];
+      rowp[7] = B[1];
+      rowp[8] = B[2];
+      rowp[9] = C[0];
+      rowp[10] = C[1];
+      rowp[11] = C[2];
+    } else {
+      rowp[6] = rowp[7] = rowp[8] = rowp[9] = rowp[10] = rowp[11] = 0.0;
+    }
+    rowp[12] = -(double)pd2;  // esekfom.hpp:225
+    rowp[13] = 1.0;
+  }
 }
 
 // One h_share_model pass of this block: its tiles (tile = blockIdx.x, += gridDim.x), Jacobian rows staged in shared
 // memory, products accumulated by thread (output o, segment seg) over rows seg, seg + nseg, ... of every tile, then
 // the segments are combined in order and the block's partial blob is written to a.partials[blockIdx.x].
-__device__ void block_pass(const PassArgs& a, const StateD* x, bool search, double* s_rows, unsigned char* s_valid,
-                           PassConst* s_pc, double* s_acc) {
-  const int tid = threadIdx.x;
-  const int M = *a.scan_m;
-  if (tid == 0) load_pass_const(x, *s_pc);
-  __syncthreads();
-  const PassConst& pc = *s_pc;
-  const int G = pick_group(M, gridDim.x);
-  const int rows = search ? THREADS / G : pick_rows_cached(M, gridDim.x);
-  const int ntiles = tiles_of(M, rows);
-  const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
-  const int nseg = THREADS / nout;
-  const int o = tid % nout, seg = tid / nout;
-  int ca = 0, cb = 0;
-  if (seg < nseg) {
-    ca = a.extrinsic_est ? c_oa_ext[o] : c_oa_no[o];
-    cb = a.extrinsic_est ? c_ob_ext[o] : c_ob_no[o];
-  }
-  double acc = 0.0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    if (search) {
-      if (G == 32)
-        search_tile<32>(a, pc, M, tile, s_rows, s_valid);
-      else if (G == 16)
-        search_tile<16>(a, pc, M, tile, s_rows, s_valid);
-      else
-        search_tile<8>(a, pc, M, tile, s_rows, s_valid);
-    } else {
-      cached_tile(a, pc, M, tile, rows, s_rows, s_valid);
-    }
-    __syncthreads();
-    if (seg < nseg) {
-      for (int r = seg; r < rows; r += nseg)
-        if (s_valid[r]) acc = fma(s_rows[r * RS + ca], s_rows[r * RS + cb], acc);
-    }
-    __syncthreads();
-  }
-  if (blockIdx.x < ntiles) {
-    if (seg < nseg) s_acc[seg * nout + o] = acc;
-    __syncthreads();
-    double* out = a.partials + (size_t)blockIdx.x * LIO_BLOB;
-    if (tid < nout) {
-      double s = 0.0;
-      for (int g = 0; g < nseg; ++g) s += s_acc[g * nout + tid];
-      out[a.extrinsic_est ? c_oe_ext[tid] : c_oe_no[tid]] = s;
-    }
-  }
-}
+struct PassSmem;
+__device__ void block_pass(const PassArgs& a, const StateD* x, bool search, PassSmem* ps);
 
-// Sum of the per-block partials in block order into s_blob[LIO_BLOB] (all threads of the block take part).
-__device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool search, double* s_blob, double* s_acc) {
-  const int tid = threadIdx.x;
+// Sum of the per-block partials into s_blob[LIO_BLOB] in a fixed order: warp w takes outputs w, w + nwarps, ...;
+// lane l adds the partials of blocks l, l + 32, ... (coalesced rows of the transposed partial array; the loads of a
+// row are issued together, two rows at a time), then a fixed shuffle tree combines the lanes.
+constexpr int RED_K = 10;  // 32 * RED_K blocks per batch of loads
+__device__ __forceinline__ double row_sum(const double* src, int nb, int lane) {
+  double acc = 0.0;
+#pragma unroll 1
+  for (int base = 0; base < nb; base += 32 * RED_K) {
+    double v[RED_K];
+#pragma unroll
+    for (int k = 0; k < RED_K; ++k) {
+      const int b = base + lane + 32 * k;
+      v[k] = b < nb ? __ldcg(src + b) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < RED_K; ++k) acc += v[k];
+  }
+  return acc;
+}
+__device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool search, double* s_blob) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = *a.scan_m;
   const int G = pick_group(M, gridDim.x);
   const int rows = search ? THREADS / G : pick_rows_cached(M, gridDim.x);
   const int ntiles = tiles_of(M, rows);
   const int nb = ntiles < (int)gridDim.x ? ntiles : (int)gridDim.x;
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
-  const int nsub = THREADS / nout;
-  const int o = tid % nout, sub = tid / nout;
   if (tid < LIO_BLOB) s_blob[tid] = 0.0;
-  if (sub < nsub) {
-    const int e = a.extrinsic_est ? c_oe_ext[o] : c_oe_no[o];
-    double acc = 0.0;
-    for (int b = sub; b < nb; b += nsub) acc += __ldcg(a.partials + (size_t)b * LIO_BLOB + e);
-    s_acc[sub * nout + o] = acc;
-  }
   __syncthreads();
-  if (tid < nout) {
-    double s = 0.0;
-    for (int g = 0; g < nsub; ++g) s += s_acc[g * nout + tid];
-    s_blob[a.extrinsic_est ? c_oe_ext[tid] : c_oe_no[tid]] = s;
+  constexpr int NW = THREADS / 32;
+#pragma unroll 1
+  for (int o = warp; o < nout; o += 2 * NW) {
+    const int o2 = o + NW;
+    const int e1 = a.extrinsic_est ? c_oe_ext[o] : c_oe_no[o];
+    const int e2 = o2 < nout ? (a.extrinsic_est ? c_oe_ext[o2] : c_oe_no[o2]) : e1;
+    double acc1 = row_sum(a.partials + (size_t)e1 * gridDim.x, nb, lane);
+    double acc2 = row_sum(a.partials + (size_t)e2 * gridDim.x, o2 < nout ? nb : 0, lane);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      acc1 += __shfl_down_sync(0xffffffffu, acc1, off);
+      acc2 += __shfl_down_sync(0xffffffffu, acc2, off);
+    }
+    if (lane == 0) {
+      s_blob[e1] = acc1;
+      if (o2 < nout) s_blob[e2] = acc2;
+    }
   }
   if (tid == 0) s_blob[91] = search ? 1.0 : 0.0;
   __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// N x N FP64 inverse in one warp: lane r holds row r of [A | I] in registers; Gauss-Jordan with partial pivoting
-// (first maximum of |a_rk|, r >= k), elimination of all other rows per step, one division per row at the end.
-// A, Ainv: shared memory, row-major N x N.  Called by all 32 lanes of one warp.
+// n x n FP64 inverse (n <= 12) in one warp: [A | I] in shared memory (W: n rows of WS doubles), lane r owns row r;
+// Gauss-Jordan with partial pivoting (first maximum of |a_rk|, r >= k), elimination of all other rows per step, one
+// division per row at the end.  A LOOP on purpose: the solve runs once per pass in one block, from a cold
+// instruction cache, so its cost is its code size.
 // ---------------------------------------------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ void warp_inverse(const double* A, double* Ainv) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  double a[N], b[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    a[j] = lane < N ? A[lane * N + j] : 0.0;
-    b[j] = (lane == j) ? 1.0 : 0.0;
-  }
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    const bool cand0 = lane >= k && lane < N;
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(a[k]));
-    const uint32_t hi = cand0 ? (uint32_t)(bits >> 32) : 0u, lo32 = (uint32_t)bits;
-    const uint32_t mhi = __reduce_max_sync(FULL, hi);
-    const bool cand = cand0 && hi == mhi;
-    const uint32_t mlo = __reduce_max_sync(FULL, cand ? lo32 : 0u);
-    const unsigned wm = __ballot_sync(FULL, cand && lo32 == mlo);
-    const int piv = wm ? __ffs(wm) - 1 : k;
-    if (piv != k) {  // warp-uniform
-      const int src = lane == k ? piv : (lane == piv ? k : lane);
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        a[j] = __shfl_sync(FULL, a[j], src);
-        b[j] = __shfl_sync(FULL, b[j], src);
-      }
-    }
-    const double pivot = __shfl_sync(FULL, a[k], k);
-    const double f = a[k] / pivot;
-    const bool upd = lane != k && lane < N;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      if (j > k) {
-        const double pk = __shfl_sync(FULL, a[j], k);
-        if (upd) a[j] = fma(-f, pk, a[j]);
-      }
-      const double pbj = __shfl_sync(FULL, b[j], k);
-      if (upd) b[j] = fma(-f, pbj, b[j]);
-    }
-    if (upd) a[k] = 0.0;
-  }
-  double diag = 1.0;
-#pragma unroll
-  for (int j = 0; j < N; ++j)
-    if (lane == j) diag = a[j];
-  if (lane < N) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) Ainv[lane * N + j] = b[j] / diag;
-  }
-  __syncwarp();
-}
-
-// The same algorithm for a run-time n <= 12 with [A | I] in shared memory (W: n rows of WS doubles); used for
-// n = 12, where the unrolled register version would not fit the 128-register budget of the persistent kernel.
 constexpr int WS = 25;  // odd row stride: lanes (= rows) hit distinct banks
 __device__ __noinline__ void warp_inverse_smem(const double* A, double* Ainv, int n, double* W) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int w = 2 * n;
+#pragma unroll 1
   for (int idx = lane; idx < n * w; idx += 32) {
     const int r = idx / w, c = idx % w;
     W[r * WS + c] = c < n ? A[r * n + c] : (c - n == r ? 1.0 : 0.0);
   }
   __syncwarp();
+#pragma unroll 1
   for (int k = 0; k < n; ++k) {
     const bool cand0 = lane >= k && lane < n;
     const unsigned long long bits = cand0 ? (unsigned long long)__double_as_longlong(fabs(W[lane * WS + k])) : 0ull;
@@ -408,6 +360,7 @@ __device__ __noinline__ void warp_inverse_smem(const double* A, double* Ainv, in
     }
     if (lane < n && lane != k) {
       const double f = W[lane * WS + k] / W[k * WS + k];
+#pragma unroll 4
       for (int c = k + 1; c < w; ++c) W[lane * WS + c] = fma(-f, W[k * WS + c], W[lane * WS + c]);
       W[lane * WS + k] = 0.0;
     }
@@ -415,29 +368,92 @@ __device__ __noinline__ void warp_inverse_smem(const double* A, double* Ainv, in
   }
   if (lane < n) {
     const double d = W[lane * WS + lane];
+#pragma unroll 1
     for (int c = 0; c < n; ++c) Ainv[lane * n + c] = W[lane * WS + n + c] / d;
   }
   __syncwarp();
 }
 
-// shared scratch of the solve step (doubles)
+// ---------------------------------------------------------------------------------------------------------
+// SO(3) pieces of boxplus / boxminus (esekfom.hpp:59-73, 236-258) in quaternion form, one rotation per thread so the
+// two rotations of the state (rot, offset_R_L_I) run side by side.  Same formulas as Sophus::SO3::exp / log
+// (lio_common.cuh); the relative rotation of boxminus is formed as conj(q2) * q1 instead of through 3x3 matrices,
+// and unit norm is restored with the series of 1/sqrt(1+e) (e ~ 1e-16) instead of sqrt + 4 divisions.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Quatd qmul_raw(const Quatd& a, const Quatd& b) {
+  Quatd r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  return r;
+}
+__device__ __forceinline__ Quatd renorm(const Quatd& q) {
+  const double n2 = ((q.w * q.w + q.x * q.x) + q.y * q.y) + q.z * q.z;
+  const double e = n2 - 1.0;
+  const double sc = fabs(e) < 1e-6 ? (1.0 - 0.5 * e) + 0.375 * (e * e) : 1.0 / sqrt(n2);
+  return Quatd{q.w * sc, q.x * sc, q.y * sc, q.z * sc};
+}
+// q * Exp(w)
+__device__ __noinline__ void rot_plus(const Quatd* q, const double* w, Quatd* out) {
+  const double theta = sqrt((w[0] * w[0] + w[1] * w[1]) + w[2] * w[2]);
+  double imag, real;
+  if (theta < 1e-10) {
+    const double t2 = theta * theta, t4 = t2 * t2;
+    imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
+    real = 1.0 - 0.125 * t2 + 0.00260417 * t4;
+  } else {
+    double sn, cs;
+    sincos(0.5 * theta, &sn, &cs);
+    imag = sn / theta;
+    real = cs;
+  }
+  *out = renorm(qmul_raw(*q, Quatd{real, imag * w[0], imag * w[1], imag * w[2]}));
+}
+// Log(q2^-1 * q1)
+__device__ __noinline__ void rot_minus(const Quatd* q1, const Quatd* q2, double* o) {
+  const Quatd r = qmul_raw(Quatd{q2->w, -q2->x, -q2->y, -q2->z}, *q1);
+  const double n = sqrt((r.x * r.x + r.y * r.y) + r.z * r.z);
+  double f;
+  if (n < 1e-10) {
+    f = 2.0 / r.w - 2.0 * (n * n) / (r.w * (r.w * r.w));
+  } else if (fabs(r.w) < 1e-10) {
+    f = (r.w > 0 ? 3.14159265358979323846 : -3.14159265358979323846) / n;
+  } else {
+    f = 2.0 * atan(n / r.w) / n;
+  }
+  o[0] = f * r.x;
+  o[1] = f * r.y;
+  o[2] = f * r.z;
+}
+
+// shared scratch of the solve step; aliases the Jacobian-row staging area of the pass (the solving block is done
+// with its rows by then)
 struct SolveSmem {
   double blob[LIO_BLOB];
   double S[144], Sinv[144], Kf[288], KH[288], Kh[24], dxn[24], dx[24];
-  double W[12 * WS];  // [A | I] of warp_inverse_smem
-  int fin, skip;
+  double W[12 * WS];   // [A | I] of warp_inverse_smem
+  double prior[288];   // P11^-1 (n x n) and P21 P11^-1 ((24-n) x n) of this update
+  double P[576];
+  double xa[26], xb[26], xn[26];  // x, x_propagated, x [+] dx
+  int fin;
 };
 
 // Once per update: restore the prior (from_snapshot), x_propagated = x, loop state, P11^-1 and P21 P11^-1.
 __device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* sm) {
   const int tid = threadIdx.x;
-  if (s.from_snapshot) {
-    if (tid < 26) reinterpret_cast<double*>(s.x)[tid] = reinterpret_cast<const double*>(s.x0)[tid];
-    for (int k = tid; k < 576; k += THREADS) s.P[k] = s.P0[k];
-  }
   const double* Psrc = s.from_snapshot ? s.P0 : s.P;
   const double* xsrc = reinterpret_cast<const double*>(s.from_snapshot ? s.x0 : s.x);
-  if (tid < 26) reinterpret_cast<double*>(s.xprop)[tid] = xsrc[tid];  // esekfom.hpp:287
+#pragma unroll 1
+  for (int k = tid; k < 576; k += THREADS) sm->P[k] = Psrc[k];
+  if (tid < 26) sm->xa[tid] = xsrc[tid];
+  __syncthreads();
+  if (s.from_snapshot) {
+    if (tid < 26) reinterpret_cast<double*>(s.x)[tid] = sm->xa[tid];
+#pragma unroll 1
+    for (int k = tid; k < 576; k += THREADS) s.P[k] = sm->P[k];
+  }
+  if (tid < 26) reinterpret_cast<double*>(s.xprop)[tid] = sm->xa[tid];  // esekfom.hpp:287
   if (tid == 0) {
     s.ctrl->iter = -1;
     s.ctrl->converge = 1;
@@ -447,20 +463,19 @@ __device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* s
     s.ctrl->n_valid_last = 0;
     s.ctrl->max_iter = s.max_iter;
   }
-  for (int k = tid; k < n * n; k += THREADS) sm->S[k] = Psrc[(k / n) * 24 + (k % n)];
+#pragma unroll 1
+  for (int k = tid; k < n * n; k += THREADS) sm->S[k] = sm->P[(k / n) * 24 + (k % n)];
   __syncthreads();
-  if (tid < 32) {
-    if (n == 6)
-      warp_inverse<6>(sm->S, sm->Sinv);
-    else
-      warp_inverse_smem(sm->S, sm->Sinv, n, sm->W);
-  }
+  if (tid < 32) warp_inverse_smem(sm->S, sm->Sinv, n, sm->W);
   __syncthreads();
+#pragma unroll 1
   for (int k = tid; k < n * n; k += THREADS) s.prior[k] = sm->Sinv[k];
+#pragma unroll 1
   for (int k = tid; k < (24 - n) * n; k += THREADS) {
     const int r = k / n, c = k % n;
     double acc = 0.0;
-    for (int j = 0; j < n; ++j) acc = fma(Psrc[(n + r) * 24 + j], sm->Sinv[j * n + c], acc);
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) acc = fma(sm->P[(n + r) * 24 + j], sm->Sinv[j * n + c], acc);
     s.prior[144 + k] = acc;
   }
   __syncthreads();
@@ -470,44 +485,67 @@ __device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* s
 __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* sm) {
   const int tid = threadIdx.x;
   Ctrl* ctrl = s.ctrl;
-  const int iter = __ldcg(&ctrl->iter), max_iter = __ldcg(&ctrl->max_iter);
+  // everything the step reads comes in with ONE round of loads (all issued before the first use)
+  {
+    double vp[3], vq[2], va = 0.0, vb = 0.0;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) vp[u] = (tid + u * THREADS < 576) ? __ldcg(s.P + tid + u * THREADS) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) vq[u] = (tid + u * THREADS < 288) ? __ldcg(s.prior + tid + u * THREADS) : 0.0;
+    if (tid < 26) {
+      va = __ldcg(reinterpret_cast<const double*>(s.x) + tid);
+      vb = __ldcg(reinterpret_cast<const double*>(s.xprop) + tid);
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (tid + u * THREADS < 576) sm->P[tid + u * THREADS] = vp[u];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (tid + u * THREADS < 288) sm->prior[tid + u * THREADS] = vq[u];
+    if (tid < 26) {
+      sm->xa[tid] = va;
+      sm->xb[tid] = vb;
+    }
+  }
+  const int iter = __ldcg(&ctrl->iter), max_iter = __ldcg(&ctrl->max_iter), t_old = __ldcg(&ctrl->t),
+            np_old = __ldcg(&ctrl->n_passes);
   if (tid < LIO_BLOB) s.blob[tid] = sm->blob[tid];
   const int n_valid = (int)sm->blob[90];
   if (n_valid < 1) {
     // `if (!dyn_share.valid) continue;` (esekfom.hpp:297-299): nothing changes, the loop counter advances
     if (tid == 0) {
       ctrl->n_valid_last = 0;
-      ctrl->n_passes = __ldcg(&ctrl->n_passes) + 1;
+      ctrl->n_passes = np_old + 1;
       ctrl->iter = iter + 1;
       if (iter + 1 >= max_iter) ctrl->done = 1;
     }
     __syncthreads();
     return;
   }
-  // S = HtH[:n,:n] / R + P11^-1 ; dx_new = x [-] x_propagated (esekfom.hpp:303), in another warp
+  __syncthreads();
+  stamp(s.dbg, 128, 20);
+  const double inv_R = 1.0 / s.R;
+  // S = HtH[:n,:n] / R + P11^-1
+#pragma unroll 1
   for (int k = tid; k < n * n; k += THREADS) {
     const int r = k / n, c = k % n;
     const int lo = r < c ? r : c, hi = r < c ? c : r;
-    sm->S[k] = sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)] / s.R + __ldcg(s.prior + k);
+    sm->S[k] = sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)] * inv_R + sm->prior[k];
   }
-  if (tid == 32) {
-    StateD xa, xb;
-#pragma unroll
-    for (int k = 0; k < 26; ++k) {
-      reinterpret_cast<double*>(&xa)[k] = __ldcg(reinterpret_cast<const double*>(s.x) + k);
-      reinterpret_cast<double*>(&xb)[k] = __ldcg(reinterpret_cast<const double*>(s.xprop) + k);
-    }
-    boxminus(xa, xb, sm->dxn);
-  }
-  __syncthreads();
-  if (tid < 32) {
-    if (n == 6)
-      warp_inverse<6>(sm->S, sm->Sinv);
-    else
-      warp_inverse_smem(sm->S, sm->Sinv, n, sm->W);
+  // dx_new = x [-] x_propagated (esekfom.hpp:303): warp 1 (two rotations) and warp 2 (vector parts)
+  if (tid == 32) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 3), reinterpret_cast<const Quatd*>(sm->xb + 3), sm->dxn + 3);
+  if (tid == 33) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 7), reinterpret_cast<const Quatd*>(sm->xb + 7), sm->dxn + 6);
+  if (tid >= 64 && tid < 64 + 24) {
+    const int j = tid - 64;  // error-state index; state index: pos 0-2 | t_LI 11-13 | vel.. 14-25
+    if (j < 3) sm->dxn[j] = sm->xa[j] - sm->xb[j];
+    if (j >= 9) sm->dxn[j] = sm->xa[j + 2] - sm->xb[j + 2];
   }
   __syncthreads();
+  if (tid < 32) warp_inverse_smem(sm->S, sm->Sinv, n, sm->W);
+  __syncthreads();
+  stamp(s.dbg, 128, 21);
   // K_front[:, :n] = [Sinv ; (P21 P11^-1) Sinv]
+#pragma unroll 1
   for (int k = tid; k < 24 * n; k += THREADS) {
     const int r = k / n, c = k % n;
     double acc;
@@ -515,32 +553,37 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
       acc = sm->Sinv[r * n + c];
     } else {
       acc = 0.0;
-      for (int j = 0; j < n; ++j) acc = fma(__ldcg(s.prior + 144 + (r - n) * n + j), sm->Sinv[j * n + c], acc);
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) acc = fma(sm->prior[144 + (r - n) * n + j], sm->Sinv[j * n + c], acc);
     }
     sm->Kf[k] = acc;
   }
   __syncthreads();
   // KH[:, :n] = K_front[:, :n] HtH / R ;  K h = K_front[:, :n] Hth / R   (esekfom.hpp:314-319, regrouped)
+#pragma unroll 1
   for (int k = tid; k < 24 * n + 24; k += THREADS) {
     if (k < 24 * n) {
       const int r = k / n, c = k % n;
       double acc = 0.0;
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         const int lo = j < c ? j : c, hi = j < c ? c : j;
         acc = fma(sm->Kf[r * n + j], sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)], acc);
       }
-      sm->KH[k] = acc / s.R;
+      sm->KH[k] = acc * inv_R;
     } else {
       const int r = k - 24 * n;
       double acc = 0.0;
+#pragma unroll 1
       for (int j = 0; j < n; ++j) acc = fma(sm->Kf[r * n + j], sm->blob[78 + j], acc);
-      sm->Kh[r] = acc / s.R;
+      sm->Kh[r] = acc * inv_R;
     }
   }
   __syncthreads();
   if (tid < 24) {
     // dx = K h + (K H - I) dx_new   (esekfom.hpp:319)
     double acc = 0.0;
+#pragma unroll 1
     for (int c = 0; c < 24; ++c) {
       const double khc = (c < n) ? sm->KH[tid * n + c] : 0.0;
       acc = fma(khc - (tid == c ? 1.0 : 0.0), sm->dxn[c], acc);
@@ -548,46 +591,49 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
     sm->dx[tid] = sm->Kh[tid] + acc;
   }
   __syncthreads();
-  if (tid == 0) {
-    StateD xa, xn;
-#pragma unroll
-    for (int k = 0; k < 26; ++k)
-      reinterpret_cast<double*>(&xa)[k] = __ldcg(reinterpret_cast<const double*>(s.x) + k);
-    boxplus(xa, sm->dx, xn);  // esekfom.hpp:321
-    *s.x = xn;
+  stamp(s.dbg, 128, 22);
+  // x = x [+] dx (esekfom.hpp:321): warp 0 the two rotations, warp 1 the vector parts, warp 2 the loop state
+  if (tid == 0) rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 3), sm->dx + 3, reinterpret_cast<Quatd*>(sm->xn + 3));
+  if (tid == 1) rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 7), sm->dx + 6, reinterpret_cast<Quatd*>(sm->xn + 7));
+  if (tid >= 32 && tid < 32 + 24) {
+    const int j = tid - 32;
+    if (j < 3) sm->xn[j] = sm->xa[j] + sm->dx[j];
+    if (j >= 9) sm->xn[j + 2] = sm->xa[j + 2] + sm->dx[j];
+  }
+  if (tid == 64) {
     bool converge = true;
+#pragma unroll 1
     for (int jj = 0; jj < 24; ++jj)
       if (fabs(sm->dx[jj]) > 0.001) {
         converge = false;
         break;
       }
-    int t = __ldcg(&ctrl->t);
+    int t = t_old;
     if (converge) t++;
     if (!t && iter == max_iter - 2) converge = true;
     const int fin = (t > 1 || iter == max_iter - 1) ? 1 : 0;
     ctrl->converge = converge ? 1 : 0;
     ctrl->t = t;
     ctrl->n_valid_last = n_valid;
-    ctrl->n_passes = __ldcg(&ctrl->n_passes) + 1;
+    ctrl->n_passes = np_old + 1;
     ctrl->iter = iter + 1;
     if (fin) ctrl->done = 1;
     sm->fin = fin;
   }
   if (tid < 24 && s.dx_out) s.dx_out[tid] = sm->dx[tid];
   __syncthreads();
+  stamp(s.dbg, 128, 23);
+  if (tid < 26) reinterpret_cast<double*>(s.x)[tid] = sm->xn[tid];
   if (sm->fin) {
-    // P = (I - K H) P   (esekfom.hpp:342); K H has n non-zero columns.  Rows are independent: read all, then write.
-    double out[3];
-    int cnt = 0;
+    // P = (I - K H) P   (esekfom.hpp:342); K H has n non-zero columns
+#pragma unroll 1
     for (int k = tid; k < 576; k += THREADS) {
       const int r = k / 24, c = k % 24;
-      double acc = __ldcg(s.P + r * 24 + c);
-      for (int j = 0; j < n; ++j) acc = fma(-sm->KH[r * n + j], __ldcg(s.P + j * 24 + c), acc);
-      out[cnt++] = acc;
+      double acc = sm->P[k];
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) acc = fma(-sm->KH[r * n + j], sm->P[j * 24 + c], acc);
+      s.P[k] = acc;
     }
-    __syncthreads();
-    cnt = 0;
-    for (int k = tid; k < 576; k += THREADS) s.P[k] = out[cnt++];
   }
   __syncthreads();
 }
@@ -595,10 +641,66 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
 struct __align__(16) PassSmem {
   double rows[ROWS_MAX * RS];
   double acc[THREADS];
+  float4 nb[SROWS_MAX * LIO_K];  // neighbours found by the search phase of the current tile
   PassConst pc;
+  int cnt[SROWS_MAX];            // gate 1 of the search phase
   unsigned char valid[ROWS_MAX];
   int flag;
 };
+
+__device__ void block_pass(const PassArgs& a, const StateD* x, bool search, PassSmem* ps) {
+  const int tid = threadIdx.x;
+  const int M = *a.scan_m;
+  stamp(a.dbg, 0, 1);
+  if (tid == 0) load_pass_const(x, ps->pc);
+  __syncthreads();
+  stamp(a.dbg, 0, 2);
+  const int G = pick_group(M, gridDim.x);
+  const int rows = search ? THREADS / G : pick_rows_cached(M, gridDim.x);
+  const int ntiles = tiles_of(M, rows);
+  const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
+  const int nseg = THREADS / nout;
+  const int o = tid % nout, seg = tid / nout;
+  int ca = 0, cb = 0;
+  if (seg < nseg) {
+    ca = a.extrinsic_est ? c_oa_ext[o] : c_oa_no[o];
+    cb = a.extrinsic_est ? c_ob_ext[o] : c_ob_no[o];
+  }
+  double acc = 0.0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (search) {
+      if (G == 32)
+        search_tile<32>(a, ps->pc, M, tile, ps->nb, ps->cnt);
+      else if (G == 16)
+        search_tile<16>(a, ps->pc, M, tile, ps->nb, ps->cnt);
+      else
+        search_tile<8>(a, ps->pc, M, tile, ps->nb, ps->cnt);
+      __syncthreads();
+      stamp(a.dbg, 0, 3);
+    }
+    finish_tile(a, ps->pc, M, tile, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid);
+    __syncthreads();
+    stamp(a.dbg, 0, 4);
+    if (seg < nseg) {
+#pragma unroll 1
+      for (int r = seg; r < rows; r += nseg)
+        if (ps->valid[r]) acc = fma(ps->rows[r * RS + ca], ps->rows[r * RS + cb], acc);
+    }
+    __syncthreads();
+    stamp(a.dbg, 0, 5);
+  }
+  if (blockIdx.x < ntiles) {
+    if (seg < nseg) ps->acc[seg * nout + o] = acc;
+    __syncthreads();
+    if (tid < nout) {
+      double s = 0.0;
+      for (int g = 0; g < nseg; ++g) s += ps->acc[g * nout + tid];
+      a.partials[(size_t)(a.extrinsic_est ? c_oe_ext[tid] : c_oe_no[tid]) * gridDim.x + blockIdx.x] = s;
+    }
+  }
+  stamp(a.dbg, 0, 6);
+}
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -612,7 +714,8 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 // The whole update_iterated_dyn_share_modified loop (esekfom.hpp:270-346).  Cooperative launch: all blocks resident.
 __global__ void __launch_bounds__(THREADS, 2) update_kernel(const PassArgs a, const SolveArgs s) {
   __shared__ PassSmem ps;
-  __shared__ SolveSmem ss;
+  static_assert(sizeof(SolveSmem) <= sizeof(double) * ROWS_MAX * RS, "solve scratch must fit the row staging area");
+  SolveSmem& ss = *reinterpret_cast<SolveSmem*>(ps.rows);
   const int tid = threadIdx.x;
   const int n = a.extrinsic_est ? 12 : 6;
   const unsigned nblk = gridDim.x;
@@ -622,7 +725,7 @@ __global__ void __launch_bounds__(THREADS, 2) update_kernel(const PassArgs a, co
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
     bool search = true;
     if (pass_no > 0) search = __ldcg(&s.ctrl->converge) != 0;
-    block_pass(a, pass_no == 0 ? x_first : s.x, search, ps.rows, ps.valid, &ps.pc, ps.acc);
+    block_pass(a, pass_no == 0 ? x_first : s.x, search, &ps);
     // grid barrier; the last block to arrive reduces and solves
     __threadfence();
     __syncthreads();
@@ -631,10 +734,14 @@ __global__ void __launch_bounds__(THREADS, 2) update_kernel(const PassArgs a, co
       ps.flag = (ticket == (unsigned)(pass_no + 1) * nblk - 1u) ? 1 : 0;
     }
     __syncthreads();
+    stamp(a.dbg, 0, 7);
     if (ps.flag) {
       __threadfence();
-      block_reduce_partials(a, search, ss.blob, ps.acc);
+      stamp(a.dbg, 128, 10);
+      block_reduce_partials(a, search, ss.blob);
+      stamp(a.dbg, 128, 11);
       block_solve(s, n, &ss);
+      stamp(a.dbg, 128, 12);
       __threadfence();
       if (tid == 0) st_release(&s.sync[1], (unsigned)(pass_no + 1));
     } else if (tid == 0) {
@@ -642,6 +749,7 @@ __global__ void __launch_bounds__(THREADS, 2) update_kernel(const PassArgs a, co
       }
     }
     __syncthreads();
+    stamp(a.dbg, 0, 8);
     if (__ldcg(&s.ctrl->done)) break;
   }
 }
@@ -654,7 +762,7 @@ __global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassArgs a, cons
   const int tid = threadIdx.x;
   if (mode < 0 && s.ctrl->done) return;
   const bool search = mode < 0 ? (s.ctrl->converge != 0) : (mode != 0);
-  block_pass(a, s.x, search, ps.rows, ps.valid, &ps.pc, ps.acc);
+  block_pass(a, s.x, search, &ps);
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -662,9 +770,12 @@ __global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassArgs a, cons
     ps.flag = (ticket == gridDim.x - 1u) ? 1 : 0;
   }
   __syncthreads();
+  stamp(a.dbg, 0, 7);
   if (ps.flag) {
     __threadfence();
-    block_reduce_partials(a, search, s_blob, ps.acc);
+    stamp(a.dbg, 128, 10);
+    block_reduce_partials(a, search, s_blob);
+    stamp(a.dbg, 128, 11);
     if (tid < LIO_BLOB) s.blob[tid] = s_blob[tid];
     if (tid == 0) s.sync[0] = 0;  // ready for the next pass launch
   }
@@ -800,6 +911,8 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.own_min = own_min;
   a.own_max = own_max;
   a.partials = c->d_partials;
+  a.dbg = c->d_dbg;
+  if (c->d_dbg) cudaMemsetAsync(c->d_dbg, 0, 256 * sizeof(long long), c->stream);
   return a;
 }
 
@@ -818,6 +931,7 @@ static SolveArgs make_solve_args(lio_ctx* c, double R, int max_iter, int from_sn
   s.R = R;
   s.max_iter = max_iter;
   s.from_snapshot = from_snapshot;
+  s.dbg = c->d_dbg;
   return s;
 }
 

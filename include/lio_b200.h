@@ -74,7 +74,7 @@ typedef struct lio_caps {
   int64_t max_scan_points; /* N cap of a raw scan                                   (default 262144)  */
   int64_t max_down_points; /* M cap after the surf voxel filter; reference: 100000  (esekfom.hpp:23-29) */
   int64_t max_map_points;  /* live + garbage slots of the map point pool            (default 4194304) */
-  float map_cell;          /* edge of a kNN hash cell [m]; does not change results  (default 1.0)     */
+  float map_cell;          /* edge of a kNN hash cell [m]; does not change results  (default 1.5)     */
   float knn_max_d2;        /* search bound on squared distance; the path needs 5    (esekfom.hpp:147) */
   float plane_thr;         /* esti_plane inlier threshold                           (esekfom.hpp:157: 0.1f) */
   float map_downsample;    /* ikdtree.set_downsample_param(filter_size_map_min)     (laserMapping.cpp:748: 0.5) */
@@ -159,6 +159,10 @@ int lio_update_step_enqueue(lio_ctx* ctx, double R, int extrinsic_est);
 /* Instrumentation: enqueue ONE h_share_model pass (search or cached) at the device-resident state with no Kalman
  * step behind it, so that bench.py can bracket exactly that kernel with CUDA events. */
 int lio_pass_only_enqueue(lio_ctx* ctx, int do_search, int extrinsic_est);
+/* Instrumentation: with LIO_TIMELINE=1 in the environment at lio_create, the update kernels record %globaltimer at
+ * their phase boundaries; out[0] = pairs written by block 0 from out[1] on as (tag, ns), out[128] = pairs written by
+ * the block that ran the Kalman step from out[129] on.  Tags are listed in csrc/lio_pass.cu. */
+int lio_debug_timeline(lio_ctx* ctx, int64_t out[256]);
 /* Device pointer of the 92-double reduction blob {HtH 78, Hth 12, n_valid, n_searched} written by pass_enqueue. */
 void* lio_blob_device_ptr(lio_ctx* ctx);
 /* Synchronises and copies that blob to the host (tests, single-rank drivers). */

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""In-kernel phase timeline of the update kernels (LIO_TIMELINE=1): python tools/timeline.py [--poses K]"""
+import argparse
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+os.environ["LIO_TIMELINE"] = "1"
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+from agi_lidar_slam_b200 import _cabi  # noqa: E402
+
+TAGS = {1: "pass entry", 2: "pass const ready", 3: "search done", 4: "finish done", 5: "tile reduced", 6: "partial written",
+        7: "ticket taken", 8: "released", 10: "solver: start", 11: "solver: partials reduced", 12: "solver: solved", 20: "solve: inputs in smem", 21: "solve: inverse+boxminus done", 22: "solve: K, KH, dx done", 23: "solve: boxplus+ctrl done"}
+
+
+def show(name, tl):
+    a, b = tl
+    ev = sorted([(t, "blk0  " + TAGS.get(k, str(k))) for k, t in a] + [(t, "SOLVER " + TAGS.get(k, str(k))) for k, t in b])
+    if not ev:
+        print(name, ": no events")
+        return
+    t0 = ev[0][0]
+    print(f"--- {name}: total {(ev[-1][0] - t0) / 1000.0:.2f} us")
+    prev = t0
+    for t, n in ev:
+        print(f"   {(t - t0) / 1000.0:8.2f} us  (+{(t - prev) / 1000.0:6.2f})  {n}")
+        prev = t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--map-points", type=int, default=2_000_000)
+    ap.add_argument("--rings", type=int, default=128)
+    ap.add_argument("--cols", type=int, default=1024)
+    ap.add_argument("--poses", type=int, default=4)
+    ap.add_argument("--map-cell", type=float, default=1.0)
+    a = ap.parse_args()
+    wl = bench.make_workload(a, 0)
+    mp = wl["map"]
+    ctx = _cabi.Context(0, max_scan_points=max(1 << 18, a.rings * a.cols), max_down_points=100000,
+                        max_map_points=max(1 << 21, int(len(mp) * 1.05)), map_cell=a.map_cell)
+    ctx.map_build(np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1))
+    s = wl["scans"][0]
+    body, _, _ = ctx.scan_preprocess(s["scan"], None, None, wl["leaf"])
+    print("M =", len(body))
+    ctx.scan_upload(body)
+    ctx.state_upload(s["x_prior"], wl["P"])
+    for rep in range(3):
+        ctx.pass_only_enqueue(True, False)
+        tl = ctx.debug_timeline()
+        if rep == 2:
+            show("single search pass (warm)", tl)
+        ctx.pass_only_enqueue(False, False)
+        tl = ctx.debug_timeline()
+        if rep == 2:
+            show("single cached pass (warm)", tl)
+    for rep in range(3):
+        ctx.update_enqueue(0.001, 4, False, from_snapshot=True)
+        tl = ctx.debug_timeline()
+        if rep == 2:
+            show("whole update (warm)", tl)
+    print(ctx.state_download()[2:])
+
+
+if __name__ == "__main__":
+    main()
