@@ -321,6 +321,7 @@ class Context:
         self._check(self._lib.lio_debug_timeline(self._h, _ptr(t)))
         a = [(int(t[1 + 2 * k]), int(t[2 + 2 * k])) for k in range(int(t[0]))]
         b = [(int(t[129 + 2 * k]), int(t[130 + 2 * k])) for k in range(int(t[128]))]
+        self.timeline_raw = t
         return a, b
 
     def blob_download(self):

@@ -128,10 +128,12 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_near_cnt, 4 * M);
   ALLOC(c->d_selected, M);
   ALLOC(c->d_normvec, sizeof(float4) * M);
+  ALLOC(c->d_plane, sizeof(float4) * M);
   ALLOC(c->d_partials, 8 * (size_t)LIO_BLOB * pass_grid_blocks(c));
   LIO_CHECK(c, cudaMemset(c->d_partials, 0, 8 * (size_t)LIO_BLOB * pass_grid_blocks(c)));
   ALLOC(c->d_blob, 8 * LIO_BLOB);
   ALLOC(c->d_prior, 8 * 288);
+  ALLOC(c->d_pub, 8 * 40);
   ALLOC(c->d_sync, 2 * sizeof(unsigned));
   LIO_CHECK(c, cudaMemset(c->d_sync, 0, 2 * sizeof(unsigned)));
   {
@@ -228,9 +230,9 @@ void lio_destroy(lio_ctx* c) {
   void* ptrs[] = {c->map.table,   c->map.cell_cap,  c->map.cell_pend, c->map.cell_base, c->map.pool,
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
                   c->d_vox_best,  c->d_vox_key,     c->d_scan_m,      c->d_body,        c->d_world,
-                  c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,
+                  c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
                   c->d_partials,  c->d_blob,        c->d_cls,         c->d_add_a,       c->d_add_b,
-                  c->d_state_blk, c->d_prior,       c->d_sync,        c->d_dbg,
+                  c->d_state_blk, c->d_prior,       c->d_sync,        c->d_dbg,  c->d_pub,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,

@@ -40,11 +40,13 @@ struct lio_ctx {
   int* d_near_cnt = nullptr;        // M
   uint8_t* d_selected = nullptr;    // M point_selected_surf
   float4* d_normvec = nullptr;      // M x (a,b,c,pd2)
+  float4* d_plane = nullptr;        // M x pabcd fitted by the last search pass
   double* d_partials = nullptr;     // pass_grid x LIO_BLOB: per-block partial sums of one pass
   int pass_grid = 0;                // blocks of the persistent update grid (all co-resident)
   double* d_blob = nullptr;         // LIO_BLOB
   double* d_prior = nullptr;        // 288: P11^-1 and P21 P11^-1 of the current update
   unsigned* d_sync = nullptr;       // grid barrier words {arrivals, release}
+  double* d_pub = nullptr;          // 34 doubles published by the solving block after every Kalman step
   long long* d_dbg = nullptr;       // in-kernel timeline (only with LIO_TIMELINE=1)
   uint8_t* d_cls = nullptr;         // map_incremental class per point
   float4* d_add_a = nullptr;        // compacted PointToAdd

@@ -102,30 +102,62 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
         e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
       }
     }
-#pragma unroll 1
-    for (int u = 0; u < CPL; ++u) {
-      // static selects instead of dynamic indexing (keeps the arrays in registers)
-      unsigned long long ku = key[0];
-      uint32_t hu = h[0];
-      uint4 eu = e[0];
+    // resolve the probes; the lane's buckets then form ONE virtual list [0, total): list index idx lives in pool slot
+    // base[u] + idx for the first u with idx < end[u]
+    uint32_t base[CPL], end[CPL];
+    uint32_t total = 0;
 #pragma unroll
-      for (int v = 1; v < CPL; ++v)
-        if (u == v) {
-          ku = key[v];
-          hu = h[v];
-          eu = e[v];
+    for (int u = 0; u < CPL; ++u) {
+      uint32_t st = 0, cn = 0;
+      if (key[u] != LIO_EMPTY_KEY) {
+        for (;;) {
+          const unsigned long long k = ((unsigned long long)e[u].y << 32) | e[u].x;
+          if (k == key[u]) {
+            st = e[u].z;
+            cn = e[u].w;
+            break;
+          }
+          if (k == LIO_EMPTY_KEY) break;
+          h[u] = (h[u] + 1) & map.hash_mask;
+          e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
         }
-      if (ku == LIO_EMPTY_KEY) continue;
-      for (;;) {
-        const unsigned long long k = ((unsigned long long)eu.y << 32) | eu.x;
-        if (k == ku) {
-          scan_bucket(map, qx, qy, qz, max_bits, eu.z, eu.w, top);
-          break;
-        }
-        if (k == LIO_EMPTY_KEY) break;
-        hu = (hu + 1) & map.hash_mask;
-        eu = __ldg(reinterpret_cast<const uint4*>(map.table + hu));
       }
+      base[u] = st - total;
+      total += cn;
+      end[u] = total;
+    }
+    // stream the list four points at a time, the next four already in flight while the current four are inserted
+    float4 cur[4], nxt[4];
+    auto slot_of = [&](uint32_t idx) -> uint32_t {
+      uint32_t b = base[CPL - 1];
+#pragma unroll
+      for (int u = CPL - 2; u >= 0; --u)
+        if (idx < end[u]) b = base[u];
+      return b + idx;
+    };
+    if (total > 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = __ldg(map.pool + slot_of(min((uint32_t)j, total - 1)));
+    }
+#pragma unroll 1
+    for (uint32_t t = 0; t < total; t += 4) {
+      if (t + 4 < total) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nxt[j] = __ldg(map.pool + slot_of(min(t + 4 + j, total - 1)));
+      }
+      const uint32_t nj = min(4u, total - t);
+#pragma unroll 1
+      for (uint32_t j = 0; j < nj; ++j) {
+        float4 q = cur[0];  // static selects keep cur[] in registers; ONE copy of the insertion code
+        if (j == 1) q = cur[1];
+        if (j == 2) q = cur[2];
+        if (j == 3) q = cur[3];
+        const int id = __float_as_int(q.w);
+        const uint32_t db = __float_as_uint(dist2(qx, qy, qz, q.x, q.y, q.z));
+        if (id >= 0 && db <= max_bits) top.insert(((unsigned long long)db << 32) | (uint32_t)id, slot_of(t + j));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
   }
   if (rings > 1) {

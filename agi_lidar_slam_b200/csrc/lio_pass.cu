@@ -43,6 +43,7 @@ struct PassArgs {
   int* near_cnt;
   uint8_t* selected;
   float4* normvec;
+  float4* plane;     // pabcd of the last search pass (the fit depends on the neighbours only)
   float4* world;
   int extrinsic_est;
   float max_d2, plane_thr;
@@ -80,6 +81,7 @@ struct SolveArgs {
   double* blob;      // LIO_BLOB: reduced blob of the last pass (also the all-reduce buffer of the sharded driver)
   double* prior;     // 144 (P11^-1) + 144 (P21 P11^-1, (24-n) x n)
   unsigned* sync;    // [0] arrival counter, [1] release flag
+  double* pub;       // 34: PassConst of the new state, converge, done -- what every block needs for the next pass
   double R;
   int max_iter;
   int from_snapshot;
@@ -200,27 +202,37 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
   float pwx, pwy, pwz;
   body_to_world(pc, pb, pwx, pwy, pwz);
   a.world[i] = make_float4(pwx, pwy, pwz, b.w);
-  float4 nb[LIO_K];
+  // esti_plane (common_lib.h:102-134) depends on the 5 neighbours only, and they change only in search passes: a
+  // cached pass re-reads the plane fitted by the last search pass instead of repeating the QR (same bits).  A point
+  // still selected at that time necessarily passed the fit (esekfom.hpp:150-173).
+  float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
+  float pd2 = 0.f;
   bool sel;
   if (search) {
+    float4 nb[LIO_K];
 #pragma unroll
     for (int r = 0; r < LIO_K; ++r) nb[r] = s_nb[row * LIO_K + r];
     sel = s_cnt[row] != 0;
+    if (sel) {
+      sel = esti_plane(nb, a.plane_thr, pabcd);
+      a.plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
+    }
   } else {
-#pragma unroll
-    for (int r = 0; r < LIO_K; ++r) nb[r] = __ldcg(a.near_pts + (size_t)i * LIO_K + r);
     sel = __ldcg(a.selected + i) != 0;  // sticky between search passes (esekfom.hpp:150)
+    if (sel) {
+      const float4 pl = __ldcg(a.plane + i);
+      pabcd[0] = pl.x;
+      pabcd[1] = pl.y;
+      pabcd[2] = pl.z;
+      pabcd[3] = pl.w;
+    }
   }
-  float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
-  float pd2 = 0.f;
   if (sel) {
     sel = false;
-    if (esti_plane(nb, a.plane_thr, pabcd)) {
-      pd2 = ((pabcd[0] * pwx + pabcd[1] * pwy) + pabcd[2] * pwz) + pabcd[3];
-      const double nrm = sqrt((pb[0] * pb[0] + pb[1] * pb[1]) + pb[2] * pb[2]);
-      const float sc = (float)(1.0 - 0.9 * fabs((double)pd2) / sqrt(nrm));
-      if ((double)sc > 0.9) sel = true;
-    }
+    pd2 = ((pabcd[0] * pwx + pabcd[1] * pwy) + pabcd[2] * pwz) + pabcd[3];
+    const double nrm = sqrt((pb[0] * pb[0] + pb[1] * pb[1]) + pb[2] * pb[2]);
+    const float sc = (float)(1.0 - 0.9 * fabs((double)pd2) / sqrt(nrm));
+    if ((double)sc > 0.9) sel = true;
   }
   a.selected[i] = sel ? 1 : 0;
   if (sel) a.normvec[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
@@ -270,7 +282,7 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
 // memory, products accumulated by thread (output o, segment seg) over rows seg, seg + nseg, ... of every tile, then
 // the segments are combined in order and the block's partial blob is written to a.partials[blockIdx.x].
 struct PassSmem;
-__device__ void block_pass(const PassArgs& a, const StateD* x, bool search, PassSmem* ps);
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps);
 
 // Sum of the per-block partials into s_blob[LIO_BLOB] in a fixed order: warp w takes outputs w, w + nwarps, ...;
 // lane l adds the partials of blocks l, l + 32, ... (coalesced rows of the transposed partial array; the loads of a
@@ -324,52 +336,40 @@ __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool searc
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// n x n FP64 inverse (n <= 12) in one warp: [A | I] in shared memory (W: n rows of WS doubles), lane r owns row r;
-// Gauss-Jordan with partial pivoting (first maximum of |a_rk|, r >= k), elimination of all other rows per step, one
-// division per row at the end.  A LOOP on purpose: the solve runs once per pass in one block, from a cold
-// instruction cache, so its cost is its code size.
+// n x n FP64 inverse (n <= 12) of a symmetric positive definite matrix in one warp: Gauss-Jordan on [A | I] held in
+// shared memory (W: n rows of WS doubles).  Both matrices inverted here are SPD by construction (P11 is a covariance
+// block, S = HtH / R + P11^-1), so no pivot search is needed: step k eliminates column k from every other row with
+// one division per row.  Lane = (row, column group): 32 / n lanes share a row and split its columns, so a step is
+// one division plus a handful of FMAs deep.  A LOOP on purpose: the solve runs once per pass in one block, from a
+// cold instruction cache, so its cost is its code size.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int WS = 25;  // odd row stride: lanes (= rows) hit distinct banks
+constexpr int WS = 25;  // odd row stride: the rows of one column land in distinct banks
 __device__ __noinline__ void warp_inverse_smem(const double* A, double* Ainv, int n, double* W) {
-  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int w = 2 * n;
+  const int g = 32 / n;           // lanes per row
+  const int i = lane / g, cg = lane - i * g;
+  const bool act = i < n;
 #pragma unroll 1
   for (int idx = lane; idx < n * w; idx += 32) {
-    const int r = idx / w, c = idx % w;
+    const int r = idx / w, c = idx - r * w;
     W[r * WS + c] = c < n ? A[r * n + c] : (c - n == r ? 1.0 : 0.0);
   }
   __syncwarp();
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
-    const bool cand0 = lane >= k && lane < n;
-    const unsigned long long bits = cand0 ? (unsigned long long)__double_as_longlong(fabs(W[lane * WS + k])) : 0ull;
-    const uint32_t hi = (uint32_t)(bits >> 32), lo32 = (uint32_t)bits;
-    const uint32_t mhi = __reduce_max_sync(FULL, hi);
-    const bool cand = cand0 && hi == mhi;
-    const uint32_t mlo = __reduce_max_sync(FULL, cand ? lo32 : 0u);
-    const unsigned wm = __ballot_sync(FULL, cand && lo32 == mlo);
-    const int piv = wm ? __ffs(wm) - 1 : k;
-    if (piv != k) {
-      if (lane < w) {
-        const double t = W[k * WS + lane];
-        W[k * WS + lane] = W[piv * WS + lane];
-        W[piv * WS + lane] = t;
-      }
-      __syncwarp();
-    }
-    if (lane < n && lane != k) {
-      const double f = W[lane * WS + k] / W[k * WS + k];
-#pragma unroll 4
-      for (int c = k + 1; c < w; ++c) W[lane * WS + c] = fma(-f, W[k * WS + c], W[lane * WS + c]);
-      W[lane * WS + k] = 0.0;
+    double f = 0.0;
+    if (act && i != k) {
+      f = W[i * WS + k] / W[k * WS + k];  // column k is not written in step k
+#pragma unroll 2
+      for (int c = k + 1 + cg; c < w; c += g) W[i * WS + c] = fma(-f, W[k * WS + c], W[i * WS + c]);
     }
     __syncwarp();
   }
-  if (lane < n) {
-    const double d = W[lane * WS + lane];
+  if (act) {
+    const double d = W[i * WS + i];
 #pragma unroll 1
-    for (int c = 0; c < n; ++c) Ainv[lane * n + c] = W[lane * WS + n + c] / d;
+    for (int c = n + cg; c < w; c += g) Ainv[i * n + (c - n)] = W[i * WS + c] / d;
   }
   __syncwarp();
 }
@@ -436,6 +436,7 @@ struct SolveSmem {
   double prior[288];   // P11^-1 (n x n) and P21 P11^-1 ((24-n) x n) of this update
   double P[576];
   double xa[26], xb[26], xn[26];  // x, x_propagated, x [+] dx
+  double pubrec[34];              // staging of SolveArgs::pub
   int fin;
 };
 
@@ -513,12 +514,16 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
   const int n_valid = (int)sm->blob[90];
   if (n_valid < 1) {
     // `if (!dyn_share.valid) continue;` (esekfom.hpp:297-299): nothing changes, the loop counter advances
+    const int conv_old = __ldcg(&ctrl->converge);
     if (tid == 0) {
       ctrl->n_valid_last = 0;
       ctrl->n_passes = np_old + 1;
       ctrl->iter = iter + 1;
       if (iter + 1 >= max_iter) ctrl->done = 1;
+      sm->pubrec[32] = (double)conv_old;
+      sm->pubrec[33] = (iter + 1 >= max_iter) ? 1.0 : 0.0;
     }
+    if (tid < 26) sm->xn[tid] = sm->xa[tid];
     __syncthreads();
     return;
   }
@@ -532,7 +537,10 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
     const int lo = r < c ? r : c, hi = r < c ? c : r;
     sm->S[k] = sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)] * inv_R + sm->prior[k];
   }
-  // dx_new = x [-] x_propagated (esekfom.hpp:303): warp 1 (two rotations) and warp 2 (vector parts)
+  __syncthreads();
+  // warp 0 inverts S while warp 1 (two rotations) and warp 2 (vector parts) form dx_new = x [-] x_propagated
+  // (esekfom.hpp:303)
+  if (tid < 32) warp_inverse_smem(sm->S, sm->Sinv, n, sm->W);
   if (tid == 32) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 3), reinterpret_cast<const Quatd*>(sm->xb + 3), sm->dxn + 3);
   if (tid == 33) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 7), reinterpret_cast<const Quatd*>(sm->xb + 7), sm->dxn + 6);
   if (tid >= 64 && tid < 64 + 24) {
@@ -540,8 +548,6 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
     if (j < 3) sm->dxn[j] = sm->xa[j] - sm->xb[j];
     if (j >= 9) sm->dxn[j] = sm->xa[j + 2] - sm->xb[j + 2];
   }
-  __syncthreads();
-  if (tid < 32) warp_inverse_smem(sm->S, sm->Sinv, n, sm->W);
   __syncthreads();
   stamp(s.dbg, 128, 21);
   // K_front[:, :n] = [Sinv ; (P21 P11^-1) Sinv]
@@ -619,6 +625,8 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
     ctrl->iter = iter + 1;
     if (fin) ctrl->done = 1;
     sm->fin = fin;
+    sm->pubrec[32] = converge ? 1.0 : 0.0;
+    sm->pubrec[33] = fin ? 1.0 : 0.0;
   }
   if (tid < 24 && s.dx_out) s.dx_out[tid] = sm->dx[tid];
   __syncthreads();
@@ -638,6 +646,25 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
   __syncthreads();
 }
 
+// After a step: the per-pass constants of the new state (sm->xn) and the loop flags go out as one 34-double record,
+// so that every other block starts its next pass after a single round of loads.
+__device__ __forceinline__ void block_publish(const SolveArgs& s, SolveSmem* sm) {
+  const int tid = threadIdx.x;
+  PassConst* pc = reinterpret_cast<PassConst*>(sm->pubrec);
+  if (tid == 0) {
+    pc->pos[0] = sm->xn[0]; pc->pos[1] = sm->xn[1]; pc->pos[2] = sm->xn[2];
+    pc->rot = Quatd{sm->xn[3], sm->xn[4], sm->xn[5], sm->xn[6]};
+    quat_to_mat(pc->rot, pc->Rt);
+  }
+  if (tid == 32) {
+    pc->rli = Quatd{sm->xn[7], sm->xn[8], sm->xn[9], sm->xn[10]};
+    pc->tli[0] = sm->xn[11]; pc->tli[1] = sm->xn[12]; pc->tli[2] = sm->xn[13];
+    quat_to_mat(pc->rli, pc->Rli);
+  }
+  __syncthreads();
+  if (tid < 34) s.pub[tid] = sm->pubrec[tid];
+}
+
 struct __align__(16) PassSmem {
   double rows[ROWS_MAX * RS];
   double acc[THREADS];
@@ -648,12 +675,10 @@ struct __align__(16) PassSmem {
   int flag;
 };
 
-__device__ void block_pass(const PassArgs& a, const StateD* x, bool search, PassSmem* ps) {
+// ps->pc holds the per-pass constants (the caller loads or computes them and synchronises the block).
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps) {
   const int tid = threadIdx.x;
   const int M = *a.scan_m;
-  stamp(a.dbg, 0, 1);
-  if (tid == 0) load_pass_const(x, ps->pc);
-  __syncthreads();
   stamp(a.dbg, 0, 2);
   const int G = pick_group(M, gridDim.x);
   const int rows = search ? THREADS / G : pick_rows_cached(M, gridDim.x);
@@ -722,10 +747,12 @@ __global__ void __launch_bounds__(THREADS, 2) update_kernel(const PassArgs a, co
   // the last block prepares the prior while the others already search (pass 0 always searches at the prior state)
   if (blockIdx.x == nblk - 1) block_prior(s, n, &ss);
   const StateD* x_first = s.from_snapshot ? s.x0 : s.x;
+  stamp(a.dbg, 0, 1);
+  if (tid == 0) load_pass_const(x_first, ps.pc);  // pass 0 searches at the prior
+  __syncthreads();
+  bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
-    bool search = true;
-    if (pass_no > 0) search = __ldcg(&s.ctrl->converge) != 0;
-    block_pass(a, pass_no == 0 ? x_first : s.x, search, &ps);
+    block_pass(a, search, &ps);
     // grid barrier; the last block to arrive reduces and solves
     __threadfence();
     __syncthreads();
@@ -741,16 +768,29 @@ __global__ void __launch_bounds__(THREADS, 2) update_kernel(const PassArgs a, co
       block_reduce_partials(a, search, ss.blob);
       stamp(a.dbg, 128, 11);
       block_solve(s, n, &ss);
+      block_publish(s, &ss);
       stamp(a.dbg, 128, 12);
       __threadfence();
+      __syncthreads();
       if (tid == 0) st_release(&s.sync[1], (unsigned)(pass_no + 1));
     } else if (tid == 0) {
       while (ld_acquire(&s.sync[1]) < (unsigned)(pass_no + 1)) {
       }
     }
     __syncthreads();
+    // one round of loads: constants of the new state + loop flags
+    double* pcd = reinterpret_cast<double*>(&ps.pc);
+    double v = 0.0;
+    if (tid < 34) v = __ldcg(s.pub + tid);
+    if (tid < 32) pcd[tid] = v;
+    if (tid == 32) ps.cnt[0] = (int)v;  // converge -> search next
+    if (tid == 33) ps.cnt[1] = (int)v;  // done
+    __syncthreads();
     stamp(a.dbg, 0, 8);
-    if (__ldcg(&s.ctrl->done)) break;
+    search = ps.cnt[0] != 0;
+    const bool done = ps.cnt[1] != 0;
+    __syncthreads();  // ps.cnt is reused by the next search tile
+    if (done) break;
   }
 }
 
@@ -762,7 +802,9 @@ __global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassArgs a, cons
   const int tid = threadIdx.x;
   if (mode < 0 && s.ctrl->done) return;
   const bool search = mode < 0 ? (s.ctrl->converge != 0) : (mode != 0);
-  block_pass(a, s.x, search, &ps);
+  if (tid == 0) load_pass_const(s.x, ps.pc);
+  __syncthreads();
+  block_pass(a, search, &ps);
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -903,6 +945,7 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.near_cnt = c->d_near_cnt;
   a.selected = c->d_selected;
   a.normvec = c->d_normvec;
+  a.plane = c->d_plane;
   a.world = c->d_world;
   a.extrinsic_est = ext;
   a.max_d2 = c->caps.knn_max_d2;
@@ -928,6 +971,7 @@ static SolveArgs make_solve_args(lio_ctx* c, double R, int max_iter, int from_sn
   s.blob = c->d_blob;
   s.prior = c->d_prior;
   s.sync = c->d_sync;
+  s.pub = c->d_pub;
   s.R = R;
   s.max_iter = max_iter;
   s.from_snapshot = from_snapshot;

@@ -37,7 +37,7 @@ def main():
     ap.add_argument("--rings", type=int, default=128)
     ap.add_argument("--cols", type=int, default=1024)
     ap.add_argument("--poses", type=int, default=4)
-    ap.add_argument("--map-cell", type=float, default=1.0)
+    ap.add_argument("--map-cell", type=float, default=1.5)
     a = ap.parse_args()
     wl = bench.make_workload(a, 0)
     mp = wl["map"]
