@@ -56,7 +56,8 @@ EXPORTS = [
     "lio_update_pass", "lio_update_scan", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_pass_only_enqueue", "lio_debug_timeline",
-    "lio_get_neighbors", "lio_map_incremental", "lio_predict", "lio_boxplus", "lio_boxminus",
+    "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
+    "lio_imu_proc_init", "lio_imu_set_param", "lio_imu_process",
 ]  # fmt: skip
 
 _lib = None
@@ -107,9 +108,13 @@ def load_library() -> C.CDLL:
         "lio_debug_timeline": (C.c_int, [vp, vp]),
         "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "lio_map_incremental": (C.c_int, [vp, vp, f32, C.c_int, vp]),
+        "lio_map_build_scan": (C.c_int, [vp, vp]),
         "lio_predict": (C.c_int, [vp, vp, f64, vp, vp, vp]),
         "lio_boxplus": (C.c_int, [vp, vp, vp]),
         "lio_boxminus": (C.c_int, [vp, vp, vp]),
+        "lio_imu_proc_init": (None, [vp]),
+        "lio_imu_set_param": (None, [vp, vp, vp, vp, vp, vp, vp]),
+        "lio_imu_process": (C.c_int, [vp, vp, C.c_int, f64, f64, vp, vp, vp, C.c_int, P(C.c_int), P(C.c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == header/library drift
@@ -340,6 +345,10 @@ class Context:
                                                 _ptr(nv)))
         return dict(idx=idx, d2=d2, nbr=nbr, world=world, selected=sel, normvec=nv)
 
+    def map_build_scan(self, x):
+        x = _state(x)
+        self._check(self._lib.lio_map_build_scan(self._h, _ptr(x)))
+
     def map_incremental(self, x, filter_size_map=0.5, ekf_inited=True):
         x = _state(x)
         counts = np.zeros(3, np.int32)
@@ -380,3 +389,40 @@ def boxminus(x1, x2):
     if rc:
         raise LioError(rc, "lio_boxminus")
     return out
+
+
+IMU_PROC_BYTES = 51 * 8 + 16  # lio_imu_proc: 51 doubles + 4 int32
+
+
+class ImuProc:
+    """Host-side ImuProcess mirror (lio_imu_proc): IMU_init + the forward half of UndistortPcl."""
+
+    def __init__(self):
+        self._lib = load_library()
+        self._buf = np.zeros(IMU_PROC_BYTES // 8, np.float64)
+        self._lib.lio_imu_proc_init(_ptr(self._buf))
+
+    def set_param(self, transl=(0, 0, 0), rot=None, gyr=(0.1,) * 3, acc=(0.1,) * 3, gyr_bias=(1e-4,) * 3,
+                  acc_bias=(1e-4,) * 3):
+        a = [np.ascontiguousarray(v, np.float64) for v in (transl, np.eye(3) if rot is None else rot, gyr, acc, gyr_bias,
+                                                            acc_bias)]
+        self._lib.lio_imu_set_param(_ptr(self._buf), *[_ptr(v) for v in a])
+
+    @property
+    def need_init(self) -> bool:
+        return bool(self._buf[51:].view(np.int32)[1])
+
+    def process(self, imu, lidar_beg_time, lidar_end_time, x, P):
+        """imu: (n,7) [stamp, acc3, gyr3].  Returns (x, P, poses (n_poses,22), initialising)."""
+        imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 7)
+        x = _state(x).copy()
+        P = np.ascontiguousarray(P, np.float64).reshape(24, 24).copy()
+        cap = imu.shape[0] + 2
+        poses = np.zeros((cap, POSE_DOUBLES))
+        npos, ini = C.c_int(0), C.c_int(0)
+        rc = self._lib.lio_imu_process(_ptr(self._buf), _ptr(imu), imu.shape[0], float(lidar_beg_time),
+                                       float(lidar_end_time), _ptr(x), _ptr(P), _ptr(poses), cap, C.byref(npos),
+                                       C.byref(ini))
+        if rc:
+            raise LioError(rc, "lio_imu_process")
+        return x, P, poses[: npos.value].copy(), bool(ini.value)

@@ -648,6 +648,14 @@ int lio_map_incremental(lio_ctx* c, const lio_state* x, float filter_size_map, i
   return map_incremental(c, x, filter_size_map, ekf_inited, counts);
 }
 
+int lio_map_build_scan(lio_ctx* c, const lio_state* x) {
+  if (!c || !x) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  int rc = refresh_scan_m(c);
+  if (rc) return rc;
+  return map_build_scan(c, x);
+}
+
 // ---------------------------------------------------------------- host-side sequential pieces
 int lio_boxplus(const lio_state* x, const double f[24], lio_state* out) {
   if (!x || !f || !out) return LIO_E_INVALID;

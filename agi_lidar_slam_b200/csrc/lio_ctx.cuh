@@ -110,6 +110,7 @@ int map_add_downsample(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_ba
 int map_delete_boxes(lio_ctx* c, const float* h_boxes6, int nb, int32_t* n_deleted);
 int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
 int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]);
+int map_build_scan(lio_ctx* c, const lio_state* x);
 
 int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux);
 }  // namespace lio

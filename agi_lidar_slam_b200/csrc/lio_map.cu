@@ -310,6 +310,24 @@ __global__ void map_incr_classify_kernel(const float4* body, const int* scan_m, 
   cls[i] = c;
 }
 
+// pointBodyToWorld (laserMapping.cpp:277-288) for the whole current scan: the first-scan map build (:747-758)
+__global__ void scan_to_world_kernel(const float4* body, const int* scan_m, const StateD* xs, float4* world) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *scan_m) return;
+  double R[9], Rli[9];
+  quat_to_mat(xs->rot, R);
+  quat_to_mat(xs->rli, Rli);
+  const float4 b = body[i];
+  const double p[3] = {b.x, b.y, b.z};
+  double a[3], w[3];
+  mat3_vec(Rli, p, a);
+  a[0] += xs->tli[0];
+  a[1] += xs->tli[1];
+  a[2] += xs->tli[2];
+  mat3_vec(R, a, w);
+  world[i] = make_float4((float)(w[0] + xs->pos[0]), (float)(w[1] + xs->pos[1]), (float)(w[2] + xs->pos[2]), b.w);
+}
+
 // order-preserving compaction of the two classes by a single block (M <= ~1e5; not a hot kernel)
 __global__ void __launch_bounds__(1024) map_incr_compact_kernel(const float4* world, const uint8_t* cls,
                                                                 const int* scan_m, float4* out_a, float4* out_b,
@@ -477,6 +495,26 @@ int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n) {
     }
     if (ids) memcpy(&ids[i], &host[i].w, 4);
   }
+  return LIO_OK;
+}
+
+int map_build_scan(lio_ctx* c, const lio_state* x) {
+  int rc = map_reset(c);
+  if (rc) return rc;
+  if (c->scan_m <= 0) return LIO_OK;
+  if (c->scan_m > c->caps.max_map_points) {
+    c->err = "Build: more points than lio_caps.max_map_points";
+    return LIO_E_CAPACITY;
+  }
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_x, x, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
+  scan_to_world_kernel<<<(int)((c->scan_m + 255) / 256), 256, 0, c->stream>>>(c->d_body, c->d_scan_m, c->d_x,
+                                                                               c->d_batch_pts);
+  c->launches++;
+  LIO_CHECK(c, cudaGetLastError());
+  rc = map_append_batch(c, c->d_batch_pts, c->scan_m, 0, nullptr);
+  if (rc) return rc;
+  c->next_id = (int32_t)c->scan_m;
+  c->map_built = true;
   return LIO_OK;
 }
 

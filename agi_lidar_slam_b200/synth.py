@@ -292,6 +292,76 @@ def moving_scan(scene: Scene, traj: Trajectory, t_beg: float, period: float, rin
     return np.concatenate([p, tms[:, None]], 1).astype(np.float32)
 
 
+@dataclass
+class RampedTrajectory:
+    """`base` replayed on a warped clock that stands still until t_start and reaches unit rate T seconds later (rate =
+    smoothstep): the platform is at rest while the filter initialises from the first IMU samples, then moves off."""
+
+    base: Trajectory
+    t_start: float = 0.45
+    T: float = 1.5
+
+    def _tau(self, t):
+        u = np.clip((np.asarray(t, float) - self.t_start) / self.T, 0.0, None)
+        uc = np.minimum(u, 1.0)
+        tau = self.T * (uc ** 3 - 0.5 * uc ** 4) + self.T * np.maximum(u - 1.0, 0.0)
+        d1 = np.where(u < 1.0, 3 * uc ** 2 - 2 * uc ** 3, 1.0)
+        d2 = np.where(u < 1.0, (6 * uc - 6 * uc ** 2) / self.T, 0.0)
+        return tau, d1, d2
+
+    def pos(self, t):
+        return self.base.pos(self._tau(t)[0])
+
+    def vel(self, t):
+        tau, d1, _ = self._tau(t)
+        return self.base.vel(tau) * np.asarray(d1)[..., None]
+
+    def acc(self, t):
+        tau, d1, d2 = self._tau(t)
+        return self.base.acc(tau) * np.asarray(d1 ** 2)[..., None] + self.base.vel(tau) * np.asarray(d2)[..., None]
+
+    def rot(self, t):
+        return self.base.rot(float(self._tau(t)[0]))
+
+    def omega_body(self, t, h=1e-5):
+        Rm, Rp = self.rot(t - h), self.rot(t + h)
+        dR = Rm.T @ Rp
+        w = np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]]) / 2.0
+        return w / (2 * h)
+
+
+def sequence(n_scans: int, seed: int, rings=16, cols=1800, fov=(-15.0, 15.0), max_range=100.0, scan_hz=10.0,
+             imu_hz=200.0, scene: Scene | None = None, traj=None):
+    """Config 2 / 4 shape: `n_scans` contiguous motion-distorted revolutions with their IMU samples, packaged the way
+    sync_packages (src/laserMapping.cpp:218-275) hands them to the main loop: list of dicts
+    {lidar (n,4) [x,y,z,t_ms], imu (k,7) [stamp, acc3, gyr3], lidar_beg_time, lidar_end_time} plus ground truth."""
+    scene = scene or block_scene()
+    traj = traj or RampedTrajectory(Trajectory())
+    period = 1.0 / scan_hz
+    t_first = 0.05
+    imu = imu_stream(traj, 0.0, t_first + n_scans * period + 0.05, imu_hz, seed + 1)
+    out = []
+    k_imu = 0
+    mean_scantime, scan_num = 0.0, 0
+    for k in range(n_scans):
+        t_beg = t_first + k * period
+        pts = moving_scan(scene, traj, t_beg, period, rings, cols, fov[0], fov[1], max_range, seed + 10 + k)
+        last = float(pts[-1, 3]) / 1000.0 if len(pts) else 0.0
+        if len(pts) <= 5 or last < 0.5 * mean_scantime:
+            t_end = t_beg + mean_scantime
+        else:
+            scan_num += 1
+            t_end = t_beg + last
+            mean_scantime += (last - mean_scantime) / scan_num
+        j = k_imu
+        while j < len(imu) and imu[j, 0] <= t_end:
+            j += 1
+        out.append(dict(lidar=pts, imu=imu[k_imu:j].copy(), lidar_beg_time=t_beg, lidar_end_time=t_end,
+                        truth_pos=traj.pos(t_end), truth_R=traj.rot(t_end)))
+        k_imu = j
+    return out
+
+
 # ------------------------------------------------------------------------------------------- named configs
 def perturbed_prior(x_true: np.ndarray, seed: int, dpos=0.05, drot_deg=1.0) -> np.ndarray:
     """Truth pose + (5 cm, 1 deg) perturbation: the propagated prior of a single-scan update."""

@@ -179,7 +179,33 @@ int lio_get_neighbors(lio_ctx* ctx, int32_t* idx5, float* d2_5, float* nbr_xyz, 
  * (:430-431).  counts[0] = |PointToAdd|, counts[1] = |PointNoNeedDownsample|, counts[2] = added by the first call. */
 int lio_map_incremental(lio_ctx* ctx, const lio_state* x, float filter_size_map, int ekf_inited, int32_t counts[3]);
 
+/* ≙ the first-scan branch of the main loop (laserMapping.cpp:747-758): every point of the current scan goes through
+ * pointBodyToWorld (:277-288) at state x and the result is KD_TREE::Build'ed (ids 0..M-1, scan order). */
+int lio_map_build_scan(lio_ctx* ctx, const lio_state* x);
+
 /* ---- host-side, sequential (<= 50 steps / scan): ImuProcess forward half ------------------------------- */
+/* ImuProcess members that persist between scans (src/IMU_Processing.hpp:95-136). */
+typedef struct lio_imu_proc {
+  double cov_gyr[3], cov_acc[3], cov_bias_gyr[3], cov_bias_acc[3];
+  double cov_gyr_scale[3], cov_acc_scale[3];
+  double mean_acc[3], mean_gyr[3];
+  double acc_s_last[3], angvel_last[3];
+  double lidar_T_wrt_imu[3], lidar_R_wrt_imu[9]; /* row-major */
+  double last_lidar_end_time, first_lidar_time;
+  lio_imu_sample last_imu;
+  int32_t init_iter_num, imu_need_init, b_first_frame, pad_;
+} lio_imu_proc; /* 51 doubles + 4 int32 */
+/* ≙ ImuProcess::ImuProcess() (IMU_Processing.hpp:139-153). */
+void lio_imu_proc_init(lio_imu_proc* ip);
+/* ≙ ImuProcess::set_param (IMU_Processing.hpp:169-178; laserMapping.cpp:692-695). */
+void lio_imu_set_param(lio_imu_proc* ip, const double transl[3], const double rot[9], const double gyr[3],
+                       const double acc[3], const double gyr_bias[3], const double acc_bias[3]);
+/* ≙ ImuProcess::Process (IMU_Processing.hpp:405-441) without the per-point loop: while the filter is initialising
+ * (IMU_init, :180-244) it updates x / P from the IMU statistics and returns *initialising = 1, *n_poses = 0;
+ * afterwards it runs the forward half of UndistortPcl (:258-358): x, P propagated to the scan end, IMUpose list
+ * (n_imu + 1 entries) for lio_scan_preprocess.  imu = meas.imu of this scan. */
+int lio_imu_process(lio_imu_proc* ip, const lio_imu_sample* imu, int n_imu, double lidar_beg_time, double lidar_end_time,
+                    lio_state* x, double P[576], lio_pose6d* poses, int cap, int* n_poses, int* initialising);
 /* ≙ esekf::predict (esekfom.hpp:82-95; use-ikfom.hpp:57-123).  Q is 12x12 row-major. */
 int lio_predict(lio_state* x, double P[576], double dt, const double Q[144], const double acc[3], const double gyro[3]);
 /* ≙ esekf::boxplus / boxminus (esekfom.hpp:59-73, 236-258). */
