@@ -399,10 +399,6 @@ static int preprocess_status(lio_ctx* c, int64_t* m) {
   int h[8];
   LIO_CHECK(c, cudaMemcpyAsync(h, c->d_prep_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
-  if (h[7] == 1) {
-    c->err = "scan voxel hash full";
-    return LIO_E_CAPACITY;
-  }
   if (h[7] == 2) {
     c->err = "more occupied voxels than lio_caps.max_down_points";
     return LIO_E_CAPACITY;

@@ -1,39 +1,39 @@
-// Scan preprocessing in one pass over the raw scan:
+// Scan preprocessing:
 //   ImuProcess::UndistortPcl back half (src/IMU_Processing.hpp:361-401): per-point motion compensation, FP64
 //   pcl::VoxelGrid<PointType>::filter (src/laserMapping.cpp:737-738, leaf :683): centroid per occupied leaf
-// fused: each raw point is compensated in registers and binned straight into a scan-voxel hash.  Centroids are
-// accumulated as fixed-point int64 offsets from the voxel origin, so the sums are exact and independent of the
-// order in which the atomics land (no run-to-run jitter in downstream neighbour sets).  Output order is PCL's:
-// ascending (kz, ky, kx).  The only library call is cub::DeviceRadixSort for that final ordering of the M voxels.
+// The raw scan is read once: each point is compensated in registers, its voxel index is taken on the compensated
+// coordinates and the index bounds are reduced on the fly (one kernel).  The voxel filter then follows PCL's own
+// algorithm: linear leaf index relative to the cloud minimum, STABLE sort of (index, point)
+// pairs, one centroid per run of equal indices — with the FP32 sums taken in ascending point order, the order the
+// oracle defines (PCL's std::sort is unstable, so PCL itself leaves it open).  Sequential FP32 sums in a defined
+// order make the centroids BIT-EXACT against the oracle, and run-to-run deterministic, which the downstream
+// neighbour sets and validity gates need (the filter loop amplifies 1e-9 input differences to millimetres within
+// ten scans).  The only library calls are cub::DeviceRadixSort / cub::DeviceSelect.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#include <algorithm>
 
 #include "lio_ctx.cuh"
 
 namespace lio {
 
 #define MAX_POSES 128
-constexpr double FX_POS = 68719476736.0;    // 2^36 per metre (offset inside the leaf)
-constexpr double FX_INT = 1048576.0;        // 2^20 per intensity unit
-constexpr double FX_TIME = 4294967296.0;    // 2^32 per millisecond
 
 struct PrepArgs {
   const float4* raw;      // x,y,z,t_ms
-  const float* aux;       // intensity or nullptr
   int n;
   const lio_pose6d* poses;
   int n_poses;
   StateD end;
-  float leaf, inv_leaf;
+  float inv_leaf;
   float4* undist;         // n (x,y,z,t_ms)
-  int* vkeys;             // n x 3 or nullptr
-  unsigned long long* svox_key;
-  long long* svox_acc;
-  uint32_t* svox_cnt;
-  uint32_t smask;
+  int* vkeys;             // n x 3 absolute voxel indices
   int* counters;          // [0] M  [1..3] key min  [4..6] key max  [7] error
 };
 
-__global__ void __launch_bounds__(256) undistort_voxel_kernel(const PrepArgs a) {
+__global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
   __shared__ lio_pose6d s_pose[MAX_POSES];
   for (int k = threadIdx.x; k < a.n_poses * 22; k += blockDim.x)
     reinterpret_cast<double*>(s_pose)[k] = reinterpret_cast<const double*>(a.poses)[k];
@@ -91,44 +91,16 @@ __global__ void __launch_bounds__(256) undistort_voxel_kernel(const PrepArgs a) 
         oz = (float)v4[2];
       }
     }
-    if (a.undist) a.undist[i] = make_float4(ox, oy, oz, r.w);
+    a.undist[i] = make_float4(ox, oy, oz, r.w);
     // voxel index: floor(p * inverse_leaf_size) in FP32, as PCL computes it
     kx = (int)floorf(ox * a.inv_leaf);
     ky = (int)floorf(oy * a.inv_leaf);
     kz = (int)floorf(oz * a.inv_leaf);
-    if (a.vkeys) {
-      a.vkeys[3 * i] = kx;
-      a.vkeys[3 * i + 1] = ky;
-      a.vkeys[3 * i + 2] = kz;
-    }
-    const unsigned long long key = pack_cell(kx, ky, kz);
-    uint32_t h = hash64(key) & a.smask;
-    uint32_t probes = 0;
-    bool ok = true;
-    for (;;) {
-      const unsigned long long prev = atomicCAS(&a.svox_key[h], LIO_EMPTY_KEY, key);
-      if (prev == LIO_EMPTY_KEY || prev == key) break;
-      h = (h + 1) & a.smask;
-      if (++probes > a.smask) {
-        ok = false;
-        atomicExch(&a.counters[7], 1);
-        break;
-      }
-    }
-    if (ok) {
-      const double offx = (double)ox - (double)kx * (double)a.leaf;
-      const double offy = (double)oy - (double)ky * (double)a.leaf;
-      const double offz = (double)oz - (double)kz * (double)a.leaf;
-      unsigned long long* acc = reinterpret_cast<unsigned long long*>(a.svox_acc + (size_t)h * 5);
-      atomicAdd(acc + 0, (unsigned long long)__double2ll_rn(offx * FX_POS));
-      atomicAdd(acc + 1, (unsigned long long)__double2ll_rn(offy * FX_POS));
-      atomicAdd(acc + 2, (unsigned long long)__double2ll_rn(offz * FX_POS));
-      if (a.aux) atomicAdd(acc + 3, (unsigned long long)__double2ll_rn((double)__ldg(a.aux + i) * FX_INT));
-      atomicAdd(acc + 4, (unsigned long long)__double2ll_rn((double)r.w * FX_TIME));
-      atomicAdd(&a.svox_cnt[h], 1u);
-    }
+    a.vkeys[3 * i] = kx;
+    a.vkeys[3 * i + 1] = ky;
+    a.vkeys[3 * i + 2] = kz;
   }
-  // voxel index bounds for PCL's "leaf size too small" check: warp-reduce, then 6 atomics per warp
+  // voxel index bounds (PCL: min_b / max_b from getMinMax3D): warp-reduce, then 6 atomics per warp
   const unsigned FULL = 0xffffffffu;
   const int big = 0x7fffffff;
   int mnx = act ? kx : big, mny = act ? ky : big, mnz = act ? kz : big;
@@ -149,87 +121,76 @@ __global__ void __launch_bounds__(256) undistort_voxel_kernel(const PrepArgs a) 
   }
 }
 
-__global__ void svox_init_kernel(unsigned long long* key, long long* acc, uint32_t* cnt, uint32_t cap) {
-  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += gridDim.x * blockDim.x) {
-    key[h] = LIO_EMPTY_KEY;
-    cnt[h] = 0;
-#pragma unroll
-    for (int f = 0; f < 5; ++f) acc[(size_t)h * 5 + f] = 0;
-  }
+__global__ void prep_reset_kernel(int* counters) {
+  counters[0] = 0;
+  counters[1] = counters[2] = counters[3] = 0x7fffffff;
+  counters[4] = counters[5] = counters[6] = -0x7fffffff;
+  counters[7] = 0;
 }
 
-__global__ void prep_reset_kernel(int* counters, unsigned long long* sort_keys, int n) {
+// PCL's linear leaf index ijk . (1, div_x, div_x div_y) relative to min_b; values = point index
+__global__ void linear_index_kernel(const int* vkeys, int n, int* counters, uint32_t* keys, uint32_t* vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) sort_keys[i] = ~0ull;
-  if (i == 0) {
-    counters[0] = 0;
-    counters[1] = counters[2] = counters[3] = 0x7fffffff;
-    counters[4] = counters[5] = counters[6] = -0x7fffffff;
-    counters[7] = 0;
+  if (i >= n) return;
+  const long long dx = (long long)counters[4] - counters[1] + 1, dy = (long long)counters[5] - counters[2] + 1,
+                  dz = (long long)counters[6] - counters[3] + 1;
+  if (dx * dy * dz > 0x7fffffffLL) {  // "leaf size too small": PCL returns the input unchanged
+    if (i == 0) counters[7] = 3;
+    keys[i] = 0;
+    vals[i] = i;
+    return;
   }
+  const long long lin = (long long)(vkeys[3 * i] - counters[1]) +
+                        dx * ((long long)(vkeys[3 * i + 1] - counters[2]) + dy * (long long)(vkeys[3 * i + 2] - counters[3]));
+  keys[i] = (uint32_t)lin;
+  vals[i] = (uint32_t)i;
 }
 
-// occupied slots -> (key, slot) list (unordered; sorted next)
-__global__ void svox_compact_kernel(const unsigned long long* key, uint32_t cap, unsigned long long* out_key,
-                                    uint32_t* out_slot, int* counters, int max_out) {
-  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += gridDim.x * blockDim.x) {
-    const unsigned long long k = key[h];
-    if (k != LIO_EMPTY_KEY) {
-      const int j = atomicAdd(&counters[0], 1);
-      if (j < max_out) {
-        out_key[j] = k;
-        out_slot[j] = h;
-      }
-    }
-  }
-}
+struct HeadFlag {
+  const uint32_t* keys;
+  __device__ __forceinline__ bool operator()(const int& j) const { return j == 0 || keys[j] != keys[j - 1]; }
+};
 
-// centroid per voxel in sorted order; the consumed hash slots are cleared for the next scan
-__global__ void svox_finalize_kernel(const unsigned long long* sorted_key, const uint32_t* sorted_slot, int* counters,
-                                     int max_m, float leaf, unsigned long long* key, long long* acc, uint32_t* cnt,
-                                     float4* body, float* body_time, int* scan_m) {
-  const int Mtot = counters[0];
+// one thread per run of equal leaf indices: FP32 sums in sorted (= ascending point) order, then / count
+__global__ void centroid_kernel(const uint32_t* sorted_vals, const int* heads, const int* n_runs, int n, int max_m,
+                                const float4* undist, const float* aux, float4* body, float* body_time, int* scan_m,
+                                int* counters) {
+  const int Mtot = *n_runs;
   const int M = Mtot > max_m ? max_m : Mtot;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0) {
-    *scan_m = M;
-    if (Mtot > max_m) counters[7] = 2;  // more voxels than lio_caps.max_down_points
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m == 0) {
+    *scan_m = counters[7] == 3 ? 0 : M;
+    counters[0] = Mtot;
+    if (Mtot > max_m && counters[7] == 0) counters[7] = 2;  // more voxels than lio_caps.max_down_points
   }
-  if (j >= Mtot) return;
-  const unsigned long long k = sorted_key[j];
-  const uint32_t h = sorted_slot[j];
-  const int B = 1 << 20;
-  const int kx = (int)(k & 0x1FFFFF) - B, ky = (int)((k >> 21) & 0x1FFFFF) - B, kz = (int)((k >> 42) & 0x1FFFFF) - B;
-  const double n = (double)cnt[h];
-  const long long* s = acc + (size_t)h * 5;
-  const double cx = (double)kx * (double)leaf + ((double)s[0] / n) / FX_POS;
-  const double cy = (double)ky * (double)leaf + ((double)s[1] / n) / FX_POS;
-  const double cz = (double)kz * (double)leaf + ((double)s[2] / n) / FX_POS;
-  const double ci = ((double)s[3] / n) / FX_INT;
-  const double ct = ((double)s[4] / n) / FX_TIME;
-  if (j < M) {
-    body[j] = make_float4((float)cx, (float)cy, (float)cz, (float)ci);
-    if (body_time) body_time[j] = (float)ct;
+  if (m >= M) return;
+  const int beg = heads[m], end = (m + 1 < Mtot) ? heads[m + 1] : n;
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f, st = 0.f;
+  for (int j = beg; j < end; ++j) {
+    const uint32_t i = sorted_vals[j];
+    const float4 p = __ldg(undist + i);
+    sx = sx + p.x;
+    sy = sy + p.y;
+    sz = sz + p.z;
+    st = st + p.w;
+    if (aux) si = si + __ldg(aux + i);
   }
-  key[h] = LIO_EMPTY_KEY;
-  cnt[h] = 0;
-#pragma unroll
-  for (int f = 0; f < 5; ++f) acc[(size_t)h * 5 + f] = 0;
+  const float cnt = (float)(end - beg);
+  body[m] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+  if (body_time) body_time[m] = st / cnt;
 }
 
 size_t preprocess_sort_bytes(int64_t n) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 63);
-  return bytes;
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)n, 0, 31);
+  cub::CountingInputIterator<int> it(0);
+  HeadFlag hf{nullptr};
+  cub::DeviceSelect::If(nullptr, b, it, (int*)nullptr, (int*)nullptr, (int)n, hf);
+  return a > b ? a : b;
 }
 
-int preprocess_init_tables(lio_ctx* c) {
-  svox_init_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_svox_key, c->d_svox_acc, c->d_svox_cnt, c->svox_cap);
-  c->launches++;
-  LIO_CHECK(c, cudaGetLastError());
-  return LIO_OK;
-}
+int preprocess_init_tables(lio_ctx*) { return LIO_OK; }
 
 // raw points already staged in c->d_raw (and c->d_raw_aux when has_aux), poses in c->d_poses
 int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux) {
@@ -239,7 +200,6 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
   }
   PrepArgs a;
   a.raw = c->d_raw;
-  a.aux = has_aux ? c->d_raw_aux : nullptr;
   a.n = (int)n;
   a.poses = c->d_poses;
   a.n_poses = n_poses;
@@ -247,30 +207,37 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
     memcpy(&a.end, end_state, sizeof(lio_state));
   else
     memset(&a.end, 0, sizeof(a.end));
-  a.leaf = leaf;
   a.inv_leaf = 1.0f / leaf;
   a.undist = c->d_undist;
   a.vkeys = c->d_vkeys;
-  a.svox_key = c->d_svox_key;
-  a.svox_acc = c->d_svox_acc;
-  a.svox_cnt = c->d_svox_cnt;
-  a.smask = c->svox_cap - 1;
   a.counters = c->d_prep_counters;
   const int grid = (int)((n + 255) / 256);
-  prep_reset_kernel<<<grid > 0 ? grid : 1, 256, 0, c->stream>>>(c->d_prep_counters, c->d_sort_keys_in, (int)n);
-  if (n > 0) undistort_voxel_kernel<<<grid, 256, 0, c->stream>>>(a);
-  svox_compact_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_svox_key, c->svox_cap, c->d_sort_keys_in,
-                                                              c->d_sort_vals_in, c->d_prep_counters, (int)n);
-  c->launches += 3;
+  uint32_t* keys_in = reinterpret_cast<uint32_t*>(c->d_sort_keys_in);
+  uint32_t* keys_out = reinterpret_cast<uint32_t*>(c->d_sort_keys_out);
+  int* heads = reinterpret_cast<int*>(c->d_svox_cnt);
+  int* n_runs = c->d_prep_counters + 10;
+  prep_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_prep_counters);
+  c->launches++;
   if (n > 0) {
+    undistort_key_kernel<<<grid, 256, 0, c->stream>>>(a);
+    linear_index_kernel<<<grid, 256, 0, c->stream>>>(c->d_vkeys, (int)n, c->d_prep_counters, keys_in,
+                                                      c->d_sort_vals_in);
+    c->launches += 2;
     size_t bytes = c->cub_tmp_bytes;
-    LIO_CHECK(c, cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, bytes, c->d_sort_keys_in, c->d_sort_keys_out,
-                                                 c->d_sort_vals_in, c->d_sort_vals_out, (int)n, 0, 63, c->stream));
+    LIO_CHECK(c, cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, bytes, keys_in, keys_out, c->d_sort_vals_in,
+                                                 c->d_sort_vals_out, (int)n, 0, 31, c->stream));
+    bytes = c->cub_tmp_bytes;
+    cub::CountingInputIterator<int> it(0);
+    HeadFlag hf{keys_out};
+    LIO_CHECK(c, cub::DeviceSelect::If(c->d_cub_tmp, bytes, it, heads, n_runs, (int)n, hf, c->stream));
+  } else {
+    LIO_CHECK(c, cudaMemsetAsync(n_runs, 0, sizeof(int), c->stream));
   }
-  svox_finalize_kernel<<<grid > 0 ? grid : 1, 256, 0, c->stream>>>(
-      c->d_sort_keys_out, c->d_sort_vals_out, c->d_prep_counters, (int)c->caps.max_down_points, leaf, c->d_svox_key,
-      c->d_svox_acc, c->d_svox_cnt, c->d_body, reinterpret_cast<float*>(c->d_normvec) /*scratch: mean time*/,
-      c->d_scan_m);
+  const int max_m = (int)c->caps.max_down_points;
+  const int cgrid = (int)((std::min<int64_t>(n, max_m) + 127) / 128);
+  centroid_kernel<<<cgrid > 0 ? cgrid : 1, 128, 0, c->stream>>>(
+      c->d_sort_vals_out, heads, n_runs, (int)n, max_m, c->d_undist, has_aux ? c->d_raw_aux : nullptr, c->d_body,
+      reinterpret_cast<float*>(c->d_normvec) /*scratch: mean time*/, c->d_scan_m, c->d_prep_counters);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());
   c->scan_m = -1;  // known on the device only until someone asks

@@ -132,3 +132,20 @@ def test_map_incremental_policy(orc, small_cfg):
     nd = ((r["nbr"] - mid[:, None, :]) ** 2).sum(2)
     full = r["cnt"] >= 5
     assert np.all((nd[(cls == 0)] < dist[(cls == 0), None] + 1e-6).any(1))
+
+
+def test_reference_loop_is_chaotic(orc):
+    """Why the comparison above is per scan: the oracle against itself, one state perturbed by 1e-9 m after scan 3."""
+    from agi_lidar_slam_b200 import synth
+    from replay_oracle import OracleReplay
+
+    seq = synth.sequence(16, 2002)
+    a, b = OracleReplay(orc, max_iteration=3), OracleReplay(orc, max_iteration=3)
+    d = []
+    for k, m in enumerate(seq):
+        xa, xb = a.process(m), b.process(m)
+        if k == 3:
+            b.x[0] += 1e-9
+        if xa is not None:
+            d.append(float(np.abs(a.x - b.x).max()))
+    assert d[0] <= 1.1e-9 and max(d) > 1e-4  # five orders of magnitude in a dozen scans
