@@ -100,7 +100,9 @@ int64_t lio_launch_count(lio_ctx* ctx);
 int lio_map_build(lio_ctx* ctx, const void* pts, int64_t n, int stride_bytes);
 /* ≙ KD_TREE::Add_Points (ikd_Tree.cpp:419-512; laserMapping.cpp:430-431).  With downsample_on the per-voxel
  * "keep the point nearest the voxel centre, new point wins ties" rule is applied per batch.
- * *n_added = new points that ended up in the map.  New point i gets id = next_id + i. */
+ * *n_added = new points that ended up in the map (the reference's return value instead counts the insert operations
+ * of its sequential loop, re-insertions of surviving old points included; it is only printed).  New point i gets
+ * id = next_id + i. */
 int lio_map_add(lio_ctx* ctx, const void* pts, int64_t n, int stride_bytes, int downsample_on, int32_t* n_added);
 /* ≙ KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:559-579; laserMapping.cpp:361-364). boxes6 = nb x {min xyz, max xyz}, half-open. */
 int lio_map_delete_boxes(lio_ctx* ctx, const float* boxes6, int nb, int32_t* n_deleted);
