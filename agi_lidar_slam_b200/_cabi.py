@@ -55,7 +55,7 @@ EXPORTS = [
     "lio_map_dump", "lio_knn5", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
-    "lio_blob_download", "lio_pass_only_enqueue", "lio_debug_timeline",
+    "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
     "lio_imu_proc_init", "lio_imu_set_param", "lio_imu_process",
 ]  # fmt: skip
@@ -104,6 +104,8 @@ def load_library() -> C.CDLL:
         "lio_update_step_enqueue": (C.c_int, [vp, f64, C.c_int]),
         "lio_blob_device_ptr": (vp, [vp]),
         "lio_blob_download": (C.c_int, [vp, vp]),
+        "lio_blob_upload": (C.c_int, [vp, vp]),
+        "lio_blob_bind": (C.c_int, [vp, vp]),
         "lio_pass_only_enqueue": (C.c_int, [vp, C.c_int, C.c_int]),
         "lio_debug_timeline": (C.c_int, [vp, vp]),
         "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
@@ -319,6 +321,13 @@ class Context:
 
     def pass_only_enqueue(self, do_search: bool, extrinsic_est=False):
         self._check(self._lib.lio_pass_only_enqueue(self._h, int(do_search), int(extrinsic_est)))
+
+    def blob_upload(self, blob92):
+        b = np.ascontiguousarray(blob92, np.float64).reshape(BLOB)
+        self._check(self._lib.lio_blob_upload(self._h, _ptr(b)))
+
+    def blob_bind(self, device_ptr: int | None):
+        self._check(self._lib.lio_blob_bind(self._h, C.c_void_p(device_ptr or 0)))
 
     def debug_timeline(self):
         """[(tag, ns)] of block 0 and of the solving block (needs LIO_TIMELINE=1 at context creation)."""

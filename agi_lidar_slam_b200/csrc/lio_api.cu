@@ -131,7 +131,8 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_plane, sizeof(float4) * M);
   ALLOC(c->d_partials, 8 * (size_t)LIO_BLOB * pass_grid_blocks(c));
   LIO_CHECK(c, cudaMemset(c->d_partials, 0, 8 * (size_t)LIO_BLOB * pass_grid_blocks(c)));
-  ALLOC(c->d_blob, 8 * LIO_BLOB);
+  ALLOC(c->d_blob_own, 8 * LIO_BLOB);
+  c->d_blob = c->d_blob_own;
   ALLOC(c->d_prior, 8 * 288);
   ALLOC(c->d_pub, 8 * 40);
   ALLOC(c->d_sync, 2 * sizeof(unsigned));
@@ -231,7 +232,7 @@ void lio_destroy(lio_ctx* c) {
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
                   c->d_vox_best,  c->d_vox_key,     c->d_scan_m,      c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
-                  c->d_partials,  c->d_blob,        c->d_cls,         c->d_add_a,       c->d_add_b,
+                  c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,       c->d_add_b,
                   c->d_state_blk, c->d_prior,       c->d_sync,        c->d_dbg,  c->d_pub,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
@@ -600,6 +601,26 @@ int lio_debug_timeline(lio_ctx* c, int64_t out[256]) {
 }
 
 void* lio_blob_device_ptr(lio_ctx* c) { return c ? c->d_blob : nullptr; }
+
+int lio_blob_upload(lio_ctx* c, const double blob92[92]) {
+  if (!c || !blob92) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  double* up = nullptr;
+  int rc = upload_area(c, &up);
+  if (rc) return rc;
+  memcpy(up, blob92, 8 * LIO_BLOB);
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_blob, up, 8 * LIO_BLOB, cudaMemcpyHostToDevice, c->stream));
+  LIO_CHECK(c, cudaEventRecord(c->upload_done, c->stream));
+  return LIO_OK;
+}
+
+int lio_blob_bind(lio_ctx* c, void* device_buffer) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  c->d_blob = device_buffer ? static_cast<double*>(device_buffer) : c->d_blob_own;
+  return LIO_OK;
+}
 
 int lio_blob_download(lio_ctx* c, double blob92[92]) {
   if (!c || !blob92) return LIO_E_INVALID;

@@ -43,7 +43,8 @@ struct lio_ctx {
   float4* d_plane = nullptr;        // M x pabcd fitted by the last search pass
   double* d_partials = nullptr;     // pass_grid x LIO_BLOB: per-block partial sums of one pass
   int pass_grid = 0;                // blocks of the persistent update grid (all co-resident)
-  double* d_blob = nullptr;         // LIO_BLOB
+  double* d_blob = nullptr;         // LIO_BLOB (own buffer, or the one given to lio_blob_bind)
+  double* d_blob_own = nullptr;
   double* d_prior = nullptr;        // 288: P11^-1 and P21 P11^-1 of the current update
   unsigned* d_sync = nullptr;       // grid barrier words {arrivals, release}
   double* d_pub = nullptr;          // 34 doubles published by the solving block after every Kalman step

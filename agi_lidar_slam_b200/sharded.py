@@ -1,0 +1,78 @@
+"""Spatially sharded map (BASELINE.json config 5, SURVEY.md §8e case 2): host side.
+
+The map is cut into `world` equal-count slabs along x.  Rank r holds the points of its slab plus a halo of
+sqrt(knn_max_d2) + margin metres on both sides, so every neighbour set that can pass the validity gate
+(d2[4] <= 5, esekfom.hpp:147) of a query inside the slab is complete in the rank's local map.  During an update every
+rank runs the pass on the whole scan against its local map, but only the queries whose p_world.x falls inside its CORE
+slab contribute Jacobian rows (lio_update_pass_enqueue's ownership window); the 92-double blob {HtH 78, Hth 12, n_valid,
+searched} is summed over the ranks (NCCL all-reduce on the device buffer, or any `reduce` callable) and every rank
+performs the identical Kalman step, so the states stay bit-identical across ranks.  Nothing else crosses NVLink.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+HALO_MARGIN = 0.5  # metres on top of sqrt(5): the pose moves by centimetres between the passes of one update
+
+
+def slab_bounds(x_coords: np.ndarray, world: int) -> np.ndarray:
+    """Equal-count cut points along x: (world + 1,) float32 with -inf / +inf at the ends.  Deterministic on every rank
+    (computed from the same array)."""
+    xs = np.sort(np.asarray(x_coords, np.float32))
+    cuts = [np.float32(-np.inf)]
+    for r in range(1, world):
+        cuts.append(xs[(len(xs) * r) // world])
+    cuts.append(np.float32(np.inf))
+    return np.asarray(cuts, np.float32)
+
+
+def shard_indices(x_coords: np.ndarray, bounds: np.ndarray, rank: int, knn_max_d2: float = 5.0) -> np.ndarray:
+    """Indices of the map points rank `rank` keeps: core slab [bounds[r], bounds[r+1]) plus the halo."""
+    halo = np.float32(np.sqrt(knn_max_d2) + HALO_MARGIN)
+    x = np.asarray(x_coords, np.float32)
+    return np.nonzero((x >= bounds[rank] - halo) & (x < bounds[rank + 1] + halo))[0]
+
+
+class ShardedUpdate:
+    """update_iterated_dyn_share_modified (esekfom.hpp:270-346) over a sharded map.
+
+    ctx     : this rank's context, whose map was built from map_xyz[shard_indices(...)]
+    own     : (x_min, x_max) core slab of this rank
+    reduce  : callable that sums the 92-double blob over the ranks IN PLACE on the device (see `nccl_reduce`) -- or
+              None together with `host_reduce`, a callable blob92 -> summed blob92 on the host (tests, gloo).
+    """
+
+    def __init__(self, ctx, own, reduce=None, host_reduce=None):
+        self.ctx = ctx
+        self.own = (float(own[0]), float(own[1]))
+        self.reduce = reduce
+        self.host_reduce = host_reduce
+        assert (reduce is None) != (host_reduce is None)
+
+    def update(self, x, P, R=0.001, max_iter=4, extrinsic_est=False):
+        c = self.ctx
+        c.state_upload(x, P)
+        c.update_begin(max_iter, extrinsic_est, True)
+        for _ in range(max_iter + 1):  # the kernels exit at once when the loop has finished on the device
+            c.update_pass_enqueue(extrinsic_est, self.own[0], self.own[1])
+            if self.reduce is not None:
+                self.reduce()
+            else:
+                c.blob_upload(self.host_reduce(c.blob_download()))
+            c.update_step_enqueue(R, extrinsic_est)
+        return c.state_download()
+
+
+def nccl_reduce(ctx, device):
+    """Binds the context's blob to a torch tensor and returns (reduce_callable, tensor): an in-place NCCL all-reduce
+    (sum, 92 doubles = 736 bytes: pure latency over NVLink) on torch's current stream."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.zeros(92, dtype=torch.float64, device=device)
+    ctx.blob_bind(t.data_ptr())
+
+    def reduce():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    return reduce, t

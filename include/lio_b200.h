@@ -167,6 +167,11 @@ int lio_pass_only_enqueue(lio_ctx* ctx, int do_search, int extrinsic_est);
 int lio_debug_timeline(lio_ctx* ctx, int64_t out[256]);
 /* Device pointer of the 92-double reduction blob {HtH 78, Hth 12, n_valid, n_searched} written by pass_enqueue. */
 void* lio_blob_device_ptr(lio_ctx* ctx);
+/* Makes the context reduce into / solve from a caller-owned device buffer of 92 doubles (e.g. the storage of a tensor
+ * that an NCCL all-reduce works on in place); NULL restores the context's own buffer. */
+int lio_blob_bind(lio_ctx* ctx, void* device_buffer);
+/* Replaces the blob from host memory (a driver that sums the ranks' blobs on the host). */
+int lio_blob_upload(lio_ctx* ctx, const double blob92[92]);
 /* Synchronises and copies that blob to the host (tests, single-rank drivers). */
 int lio_blob_download(lio_ctx* ctx, double blob92[92]);
 
