@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "liblio_b200.so"
+LIB_PATH = Path(os.environ.get("LIO_LIB", str(_PKG / "liblio_b200.so")))  # LIO_LIB: kernel-variant experiments
 
 LIO_OK = 0
 LIO_E_INVALID, LIO_E_NO_DEVICE, LIO_E_CUDA, LIO_E_CAPACITY, LIO_E_EMPTY_MAP, LIO_E_VOXEL_RANGE = -1, -2, -3, -4, -5, -6
@@ -53,7 +53,7 @@ EXPORTS = [
     "lio_abi_version", "lio_default_caps", "lio_create", "lio_destroy", "lio_set_stream", "lio_synchronize",
     "lio_last_error", "lio_launch_count", "lio_map_build", "lio_map_add", "lio_map_delete_boxes", "lio_map_size",
     "lio_map_dump", "lio_knn5", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
-    "lio_update_pass", "lio_update_scan", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
+    "lio_update_pass", "lio_update_scan", "lio_update_scan_host", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
         "lio_scan_upload": (C.c_int, [vp, vp, i64, C.c_int]),
         "lio_update_pass": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, P(i32)]),
         "lio_update_scan": (C.c_int, [vp, vp, vp, f64, C.c_int, C.c_int, P(i32), P(i32)]),
+        "lio_update_scan_host": (C.c_int, [vp, vp, i64, C.c_int, vp, vp, f64, C.c_int, C.c_int, P(i32), P(i32)]),
         "lio_state_upload": (C.c_int, [vp, vp, vp]),
         "lio_state_download": (C.c_int, [vp, vp, vp, P(i32), P(i32)]),
         "lio_update_enqueue": (C.c_int, [vp, f64, C.c_int, C.c_int, C.c_int]),
@@ -290,6 +291,15 @@ class Context:
         self._check(self._lib.lio_update_scan(self._h, _ptr(x), _ptr(P), R, max_iter, int(extrinsic_est),
                                               C.byref(nv), C.byref(npass)))
         return x, P, nv.value, npass.value
+
+    def update_scan_host(self, down_pts4, x, P, R=0.001, max_iter=4, extrinsic_est=False):
+        """Per-scan call with the downsampled cloud (n,4) float32 in host memory.  x (26,) and P (24,24) float64 are
+        updated IN PLACE (no conversions on the hot call); returns (n_valid, n_passes)."""
+        nv, npass = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.lio_update_scan_host(self._h, down_pts4.ctypes.data, down_pts4.shape[0], 16, x.ctypes.data,
+                                                   P.ctypes.data, R, max_iter, int(extrinsic_est), C.byref(nv),
+                                                   C.byref(npass)))
+        return nv.value, npass.value
 
     def state_upload(self, x, P):
         x = _state(x)

@@ -120,7 +120,6 @@ static int create_impl(lio_ctx* c) {
 
   // scan
   const size_t M = (size_t)k.max_down_points;
-  ALLOC(c->d_scan_m, 4);
   ALLOC(c->d_body, sizeof(float4) * M);
   ALLOC(c->d_world, sizeof(float4) * M);
   ALLOC(c->d_near, sizeof(float4) * M * LIO_K);
@@ -135,8 +134,8 @@ static int create_impl(lio_ctx* c) {
   c->d_blob = c->d_blob_own;
   ALLOC(c->d_prior, 8 * 288);
   ALLOC(c->d_pub, 8 * 40);
-  ALLOC(c->d_sync, 2 * sizeof(unsigned));
-  LIO_CHECK(c, cudaMemset(c->d_sync, 0, 2 * sizeof(unsigned)));
+  ALLOC(c->d_arrive, sizeof(unsigned) * 1024);
+  LIO_CHECK(c, cudaMemset(c->d_arrive, 0, sizeof(unsigned) * 1024));
   {
     const char* env = getenv("LIO_TIMELINE");
     if (env && atoi(env)) {
@@ -147,14 +146,15 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_cls, M);
   ALLOC(c->d_add_a, sizeof(float4) * M);
   ALLOC(c->d_add_b, sizeof(float4) * M);
-  LIO_CHECK(c, cudaMemset(c->d_scan_m, 0, 4));
   LIO_CHECK(c, cudaMemset(c->d_selected, 0, M));
   LIO_CHECK(c, cudaMemset(c->d_near_cnt, 0, 4 * M));
   LIO_CHECK(c, cudaMemset(c->d_blob, 0, 8 * LIO_BLOB));
 
   // filter state: one block so that the prior goes up and the posterior comes down in one copy each
   {
-    const size_t nd = 606 + 602 + 26 + 24 + 6;
+    // {x 26, P 576, ctrl 4} {x0 26, P0 576, scan_m 1, sync 1} {xprop 26} {dx 24}: the second group is what one update
+    // needs from the host, so lio_update_scan_host sends it in ONE copy (prior + scan size + zeroed barrier words)
+    const size_t nd = 606 + 604 + 26 + 24 + 6;
     ALLOC(c->d_state_blk, 8 * nd);
     LIO_CHECK(c, cudaMemset(c->d_state_blk, 0, 8 * nd));
     double* b = c->d_state_blk;
@@ -163,8 +163,10 @@ static int create_impl(lio_ctx* c) {
     c->d_ctrl = reinterpret_cast<Ctrl*>(b + 602);
     c->d_x0 = reinterpret_cast<StateD*>(b + 606);
     c->d_P0 = b + 606 + 26;
-    c->d_xprop = reinterpret_cast<StateD*>(b + 1208);
-    c->d_dx = b + 1234;
+    c->d_scan_m = reinterpret_cast<int*>(b + 606 + 602);
+    c->d_sync = reinterpret_cast<unsigned*>(b + 606 + 603);
+    c->d_xprop = reinterpret_cast<StateD*>(b + 1210);
+    c->d_dx = b + 1236;
   }
   c->h_pinned_bytes = 8 * (1280 + LIO_BLOB + 4);
   LIO_CHECK(c, cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
@@ -230,10 +232,10 @@ void lio_destroy(lio_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->map.table,   c->map.cell_cap,  c->map.cell_pend, c->map.cell_base, c->map.pool,
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
-                  c->d_vox_best,  c->d_vox_key,     c->d_scan_m,      c->d_body,        c->d_world,
+                  c->d_vox_best,  c->d_vox_key,     c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
                   c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,       c->d_add_b,
-                  c->d_state_blk, c->d_prior,       c->d_sync,        c->d_dbg,  c->d_pub,
+                  c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
@@ -558,6 +560,38 @@ int lio_update_scan(lio_ctx* c, lio_state* x_io, double P_io[576], double R, int
   // prior up in one copy, one kernel (which starts from the snapshot), posterior down in one copy
   int rc = state_upload_impl(c, x_io, P_io, false);
   if (rc) return rc;
+  rc = launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, 1);
+  if (rc) return rc;
+  return lio_state_download(c, x_io, P_io, n_valid_last, n_passes);
+}
+
+// The call a host makes per scan when the downsampled cloud is in host memory: 2 copies up, 1 kernel, 1 copy down.
+int lio_update_scan_host(lio_ctx* c, const void* down_pts, int64_t m, int stride, lio_state* x_io, double P_io[576],
+                         double R, int max_iter, int extrinsic_est, int32_t* n_valid_last, int32_t* n_passes) {
+  if (!c || !x_io || !P_io || m < 0 || (m > 0 && !down_pts) || stride != 16 || max_iter < 0 || max_iter > 32)
+    return LIO_E_INVALID;  // stride 48 clouds go through lio_scan_upload + lio_update_scan
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (!c->map_built) {
+    c->err = "update on an empty map";
+    return LIO_E_EMPTY_MAP;
+  }
+  if (m > c->caps.max_down_points) {
+    c->err = "scan larger than lio_caps.max_down_points";
+    return LIO_E_CAPACITY;
+  }
+  if (m > 0) LIO_CHECK(c, cudaMemcpyAsync(c->d_body, down_pts, 16 * (size_t)m, cudaMemcpyHostToDevice, c->stream));
+  double* up = nullptr;
+  int rc = upload_area(c, &up);
+  if (rc) return rc;
+  memcpy(up, x_io, sizeof(lio_state));
+  memcpy(up + 26, P_io, 8 * 576);
+  up[602] = 0.0;
+  up[603] = 0.0;  // barrier words
+  const int mi = (int)m;
+  memcpy(up + 602, &mi, sizeof(int));
+  LIO_CHECK(c, cudaMemcpyAsync(c->d_x0, up, 8 * 604, cudaMemcpyHostToDevice, c->stream));
+  LIO_CHECK(c, cudaEventRecord(c->upload_done, c->stream));
+  c->scan_m = m;
   rc = launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, 1);
   if (rc) return rc;
   return lio_state_download(c, x_io, P_io, n_valid_last, n_passes);

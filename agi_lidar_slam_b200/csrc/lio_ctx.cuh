@@ -47,6 +47,8 @@ struct lio_ctx {
   double* d_blob_own = nullptr;
   double* d_prior = nullptr;        // 288: P11^-1 and P21 P11^-1 of the current update
   unsigned* d_sync = nullptr;       // grid barrier words {arrivals, release}
+  unsigned* d_arrive = nullptr;     // per-worker arrival stamps of update_kernel (1024 entries)
+  unsigned epoch = 0;               // stamp base of the next update_kernel launch
   double* d_pub = nullptr;          // 34 doubles published by the solving block after every Kalman step
   long long* d_dbg = nullptr;       // in-kernel timeline (only with LIO_TIMELINE=1)
   uint8_t* d_cls = nullptr;         // map_incremental class per point

@@ -24,7 +24,13 @@
 
 namespace lio {
 
-constexpr int THREADS = 256;     // threads per block of every kernel in this file
+#ifndef LIO_THREADS
+#define LIO_THREADS 256
+#endif
+constexpr int THREADS = LIO_THREADS;  // threads per block of every kernel in this file
+#ifndef LIO_BLOCKS_PER_SM
+#define LIO_BLOCKS_PER_SM 2
+#endif
 constexpr int ROWS_MAX = 256;    // Jacobian rows staged per tile (cached passes: one thread per point)
 constexpr int RS = 14;           // row stride: 12 Jacobian columns, residual, 1.0 (row counter)
 constexpr int NOUT_EXT = 91;     // 78 HtH + 12 Hth + count
@@ -33,6 +39,7 @@ constexpr int NOUT_NOEXT = 28;   // 21 HtH (6x6 upper) + 6 Hth + count
 // compact output o -> (row column a, row column b): the accumulated quantity is sum_rows row[a] * row[b]
 __constant__ unsigned char c_oa_ext[NOUT_EXT], c_ob_ext[NOUT_EXT], c_oe_ext[NOUT_EXT];
 __constant__ unsigned char c_oa_no[NOUT_NOEXT], c_ob_no[NOUT_NOEXT], c_oe_no[NOUT_NOEXT];
+__constant__ unsigned char c_is_no[78];  // 1 where the HtH entry is one of the 21 kept without extrinsic estimation
 
 struct PassArgs {
   const float4* body;
@@ -49,7 +56,8 @@ struct PassArgs {
   float max_d2, plane_thr;
   int rings;
   float own_min, own_max;
-  double* partials;  // [LIO_BLOB][gridDim]: element e of block b at e * gridDim + b (coalesced grid reduction)
+  double* partials;  // [workers][LIO_BLOB]: one 92-double row per worker block
+  unsigned* arrive;  // [workers]: epoch stamp a worker stores (release) once its partial of the current pass is written
   long long* dbg;    // optional timeline (LIO_TIMELINE=1): [0] = entries used by block 0, [1..] = (tag, globaltimer ns)
 };
 
@@ -282,96 +290,126 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
 // memory, products accumulated by thread (output o, segment seg) over rows seg, seg + nseg, ... of every tile, then
 // the segments are combined in order and the block's partial blob is written to a.partials[blockIdx.x].
 struct PassSmem;
-__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps);
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid);
 
-// Sum of the per-block partials into s_blob[LIO_BLOB] in a fixed order: warp w takes outputs w, w + nwarps, ...;
-// lane l adds the partials of blocks l, l + 32, ... (coalesced rows of the transposed partial array; the loads of a
-// row are issued together, two rows at a time), then a fixed shuffle tree combines the lanes.
-constexpr int RED_K = 10;  // 32 * RED_K blocks per batch of loads
-__device__ __forceinline__ double row_sum(const double* src, int nb, int lane) {
-  double acc = 0.0;
-#pragma unroll 1
-  for (int base = 0; base < nb; base += 32 * RED_K) {
-    double v[RED_K];
-#pragma unroll
-    for (int k = 0; k < RED_K; ++k) {
-      const int b = base + lane + 32 * k;
-      v[k] = b < nb ? __ldcg(src + b) : 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < RED_K; ++k) acc += v[k];
-  }
-  return acc;
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-__device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool search, double* s_blob) {
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Sum of the workers' partial rows into s_blob[LIO_BLOB] in a FIXED order: warp w adds the rows of workers
+// w, w + nwarps, ... in ascending order (lane = output, one coalesced row load per worker, CH rows in flight), then
+// the per-warp sums are added in warp order.  With target != 0 the warp first waits until the workers of the chunk
+// have stamped their arrival flag (the lanes poll the chunk's flags in parallel), so the reduction runs WHILE the
+// slower workers are still busy and only the last chunk is left when the last one arrives.  The waiting does not
+// change the order, hence not the bits.
+template <int KPL, int CH>
+__device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout, unsigned target, double* s_warp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int M = *a.scan_m;
-  const int G = pick_group(M, gridDim.x);
-  const int rows = search ? THREADS / G : pick_rows_cached(M, gridDim.x);
-  const int ntiles = tiles_of(M, rows);
-  const int nb = ntiles < (int)gridDim.x ? ntiles : (int)gridDim.x;
-  const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
-  if (tid < LIO_BLOB) s_blob[tid] = 0.0;
-  __syncthreads();
   constexpr int NW = THREADS / 32;
-#pragma unroll 1
-  for (int o = warp; o < nout; o += 2 * NW) {
-    const int o2 = o + NW;
-    const int e1 = a.extrinsic_est ? c_oe_ext[o] : c_oe_no[o];
-    const int e2 = o2 < nout ? (a.extrinsic_est ? c_oe_ext[o2] : c_oe_no[o2]) : e1;
-    double acc1 = row_sum(a.partials + (size_t)e1 * gridDim.x, nb, lane);
-    double acc2 = row_sum(a.partials + (size_t)e2 * gridDim.x, o2 < nout ? nb : 0, lane);
+  int e[KPL];
+  double acc[KPL];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      acc1 += __shfl_down_sync(0xffffffffu, acc1, off);
-      acc2 += __shfl_down_sync(0xffffffffu, acc2, off);
-    }
-    if (lane == 0) {
-      s_blob[e1] = acc1;
-      if (o2 < nout) s_blob[e2] = acc2;
-    }
+  for (int k = 0; k < KPL; ++k) {
+    const int o = lane + 32 * k;
+    e[k] = o < nout ? (a.extrinsic_est ? c_oe_ext[o] : c_oe_no[o]) : -1;
+    acc[k] = 0.0;
   }
-  if (tid == 0) s_blob[91] = search ? 1.0 : 0.0;
+#pragma unroll 1
+  for (int base = warp; base < nb; base += NW * CH) {
+    if (target != 0) {
+      const int b = base + NW * lane;
+      bool ready;
+      do {
+        ready = (lane >= CH || b >= nb) ? true : (ld_acquire(a.arrive + b) - target) < 0x40000000u;
+      } while (!__all_sync(0xffffffffu, ready));
+    }
+    double v[CH][KPL];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int b = base + NW * j;
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) v[j][k] = (b < nb && e[k] >= 0) ? __ldcg(a.partials + (size_t)b * LIO_BLOB + e[k]) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) acc[k] += v[j][k];
+  }
+#pragma unroll
+  for (int k = 0; k < KPL; ++k)
+    if (e[k] >= 0) s_warp[warp * LIO_BLOB + e[k]] = acc[k];
+}
+
+__device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool search, int nworkers, unsigned target,
+                                                   double* s_blob, double* s_warp) {
+  const int tid = threadIdx.x;
+  const int M = *a.scan_m;
+  const int G = pick_group(M, nworkers);
+  const int rows = search ? THREADS / G : pick_rows_cached(M, nworkers);
+  const int ntiles = tiles_of(M, rows);
+  const int nb = ntiles < nworkers ? ntiles : nworkers;
+  const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
+  if (a.extrinsic_est)
+    reduce_rows<3, 10>(a, nb, nout, target, s_warp);
+  else
+    reduce_rows<1, 32>(a, nb, nout, target, s_warp);
+  __syncthreads();
+  if (tid < LIO_BLOB) {
+    double sum = 0.0;
+    const int o_valid = a.extrinsic_est ? 1 : ((tid < 78 && c_is_no[tid]) || (tid >= 78 && tid < 84) || tid == 90);
+    if (tid < 91 && o_valid) {
+#pragma unroll 1
+      for (int w = 0; w < THREADS / 32; ++w) sum += s_warp[w * LIO_BLOB + tid];
+    }
+    if (tid == 91) sum = search ? 1.0 : 0.0;
+    s_blob[tid] = sum;
+  }
   __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// n x n FP64 inverse (n <= 12) of a symmetric positive definite matrix in one warp: Gauss-Jordan on [A | I] held in
-// shared memory (W: n rows of WS doubles).  Both matrices inverted here are SPD by construction (P11 is a covariance
-// block, S = HtH / R + P11^-1), so no pivot search is needed: step k eliminates column k from every other row with
-// one division per row.  Lane = (row, column group): 32 / n lanes share a row and split its columns, so a step is
-// one division plus a handful of FMAs deep.  A LOOP on purpose: the solve runs once per pass in one block, from a
-// cold instruction cache, so its cost is its code size.
+// n x n FP64 inverse (n <= 12) of a symmetric positive definite matrix: Gauss-Jordan on [A | I] held in shared
+// memory (W: n rows of WS doubles), ONE ELEMENT PER THREAD.  Both matrices inverted here are SPD by construction (P11
+// is a covariance block, S = HtH / R + P11^-1), so no pivot search is needed: step k subtracts
+// (a_ik / a_kk) * row k from every other row.  An element (i != k, c > k) reads a_ik, a_kk, a_kc -- none of which is
+// written in step k -- so a step is: four shared loads, one division, one FMA, one store, one barrier.  The first
+// `nthr` threads of the block call this (nthr = inv_threads(n), whole warps) and meet at named barrier 1; the other
+// warps are free to do something else meanwhile.  A LOOP on purpose: the solve runs from a cold instruction cache,
+// so its cost is its code size.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WS = 25;  // odd row stride: the rows of one column land in distinct banks
-__device__ __noinline__ void warp_inverse_smem(const double* A, double* Ainv, int n, double* W) {
-  const int lane = threadIdx.x & 31;
-  const int w = 2 * n;
-  const int g = 32 / n;           // lanes per row
-  const int i = lane / g, cg = lane - i * g;
-  const bool act = i < n;
+__device__ __forceinline__ int inv_threads(int n) { return n <= 6 ? 96 : 192; }
+__device__ __forceinline__ void inv_barrier(int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
+__device__ __noinline__ void block_inverse_spd(const double* A, double* Ainv, int n, double* W) {
+  const int tid = threadIdx.x;
+  const int nthr = inv_threads(n);
+  const int w = 2 * n, total = n * w;
 #pragma unroll 1
-  for (int idx = lane; idx < n * w; idx += 32) {
+  for (int idx = tid; idx < total; idx += nthr) {
     const int r = idx / w, c = idx - r * w;
     W[r * WS + c] = c < n ? A[r * n + c] : (c - n == r ? 1.0 : 0.0);
   }
-  __syncwarp();
+  // this thread's (at most two) elements
+  const int i0 = tid / w, c0 = tid - i0 * w;
+  const int idx1 = tid + nthr;
+  const int i1 = idx1 / w, c1 = idx1 - i1 * w;
+  const bool has0 = tid < total, has1 = idx1 < total;
+  inv_barrier(nthr);
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
-    double f = 0.0;
-    if (act && i != k) {
-      f = W[i * WS + k] / W[k * WS + k];  // column k is not written in step k
-#pragma unroll 2
-      for (int c = k + 1 + cg; c < w; c += g) W[i * WS + c] = fma(-f, W[k * WS + c], W[i * WS + c]);
-    }
-    __syncwarp();
+    const double pivot = W[k * WS + k];
+    if (has0 && i0 != k && c0 > k) W[i0 * WS + c0] = fma(-(W[i0 * WS + k] / pivot), W[k * WS + c0], W[i0 * WS + c0]);
+    if (has1 && i1 != k && c1 > k) W[i1 * WS + c1] = fma(-(W[i1 * WS + k] / pivot), W[k * WS + c1], W[i1 * WS + c1]);
+    inv_barrier(nthr);
   }
-  if (act) {
-    const double d = W[i * WS + i];
-#pragma unroll 1
-    for (int c = n + cg; c < w; c += g) Ainv[i * n + (c - n)] = W[i * WS + c] / d;
-  }
-  __syncwarp();
+  if (has0 && c0 >= n) Ainv[i0 * n + (c0 - n)] = W[i0 * WS + c0] / W[i0 * WS + i0];
+  if (has1 && c1 >= n) Ainv[i1 * n + (c1 - n)] = W[i1 * WS + c1] / W[i1 * WS + i1];
+  inv_barrier(nthr);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -427,12 +465,14 @@ __device__ __noinline__ void rot_minus(const Quatd* q1, const Quatd* q2, double*
   o[2] = f * r.z;
 }
 
-// shared scratch of the solve step; aliases the Jacobian-row staging area of the pass (the solving block is done
-// with its rows by then)
+// shared state of the solving block: the filter (x, x_propagated, P, loop state) and the per-update constants stay
+// here for the whole update; the rest is scratch of one step
 struct SolveSmem {
   double blob[LIO_BLOB];
+  double warp_part[(THREADS / 32) * LIO_BLOB];  // per-warp sums of the grid reduction
+  Ctrl sc;                                      // loop state (mirrored to SolveArgs::ctrl after every step)
   double S[144], Sinv[144], Kf[288], KH[288], Kh[24], dxn[24], dx[24];
-  double W[12 * WS];   // [A | I] of warp_inverse_smem
+  double W[12 * WS];   // [A | I] of block_inverse_spd
   double prior[288];   // P11^-1 (n x n) and P21 P11^-1 ((24-n) x n) of this update
   double P[576];
   double xa[26], xb[26], xn[26];  // x, x_propagated, x [+] dx
@@ -454,23 +494,33 @@ __device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* s
 #pragma unroll 1
     for (int k = tid; k < 576; k += THREADS) s.P[k] = sm->P[k];
   }
-  if (tid < 26) reinterpret_cast<double*>(s.xprop)[tid] = sm->xa[tid];  // esekfom.hpp:287
+  if (tid < 26) {
+    reinterpret_cast<double*>(s.xprop)[tid] = sm->xa[tid];  // esekfom.hpp:287
+    sm->xb[tid] = sm->xa[tid];
+  }
   if (tid == 0) {
-    s.ctrl->iter = -1;
-    s.ctrl->converge = 1;
-    s.ctrl->t = 0;
-    s.ctrl->done = 0;
-    s.ctrl->n_passes = 0;
-    s.ctrl->n_valid_last = 0;
-    s.ctrl->max_iter = s.max_iter;
+    Ctrl c0;
+    c0.iter = -1;
+    c0.converge = 1;
+    c0.t = 0;
+    c0.done = 0;
+    c0.n_passes = 0;
+    c0.n_valid_last = 0;
+    c0.max_iter = s.max_iter;
+    c0.pad = 0;
+    sm->sc = c0;
+    *s.ctrl = c0;
   }
 #pragma unroll 1
   for (int k = tid; k < n * n; k += THREADS) sm->S[k] = sm->P[(k / n) * 24 + (k % n)];
   __syncthreads();
-  if (tid < 32) warp_inverse_smem(sm->S, sm->Sinv, n, sm->W);
+  if (tid < inv_threads(n)) block_inverse_spd(sm->S, sm->Sinv, n, sm->W);
   __syncthreads();
 #pragma unroll 1
-  for (int k = tid; k < n * n; k += THREADS) s.prior[k] = sm->Sinv[k];
+  for (int k = tid; k < n * n; k += THREADS) {
+    s.prior[k] = sm->Sinv[k];
+    sm->prior[k] = sm->Sinv[k];
+  }
 #pragma unroll 1
   for (int k = tid; k < (24 - n) * n; k += THREADS) {
     const int r = k / n, c = k % n;
@@ -478,53 +528,68 @@ __device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* s
 #pragma unroll 1
     for (int j = 0; j < n; ++j) acc = fma(sm->P[(n + r) * 24 + j], sm->Sinv[j * n + c], acc);
     s.prior[144 + k] = acc;
+    sm->prior[144 + k] = acc;
   }
   __syncthreads();
 }
 
-// One Kalman step from the reduced blob in sm->blob (esekfom.hpp:297-345).
+// The stepwise driver keeps nothing in shared memory between its launches: filter state and constants come back from
+// global memory in ONE round of loads (all issued before the first use).
+__device__ __forceinline__ void solve_load_inputs(const SolveArgs& s, SolveSmem* sm) {
+  const int tid = threadIdx.x;
+  double vp[(576 + THREADS - 1) / THREADS], vq[(288 + THREADS - 1) / THREADS], va = 0.0, vb = 0.0;
+#pragma unroll
+  for (int u = 0; u < (576 + THREADS - 1) / THREADS; ++u)
+    vp[u] = (tid + u * THREADS < 576) ? __ldcg(s.P + tid + u * THREADS) : 0.0;
+#pragma unroll
+  for (int u = 0; u < (288 + THREADS - 1) / THREADS; ++u)
+    vq[u] = (tid + u * THREADS < 288) ? __ldcg(s.prior + tid + u * THREADS) : 0.0;
+  if (tid < 26) {
+    va = __ldcg(reinterpret_cast<const double*>(s.x) + tid);
+    vb = __ldcg(reinterpret_cast<const double*>(s.xprop) + tid);
+  }
+  int cv = 0;
+  if (tid < 8) cv = __ldcg(reinterpret_cast<const int*>(s.ctrl) + tid);
+#pragma unroll
+  for (int u = 0; u < (576 + THREADS - 1) / THREADS; ++u)
+    if (tid + u * THREADS < 576) sm->P[tid + u * THREADS] = vp[u];
+#pragma unroll
+  for (int u = 0; u < (288 + THREADS - 1) / THREADS; ++u)
+    if (tid + u * THREADS < 288) sm->prior[tid + u * THREADS] = vq[u];
+  if (tid < 26) {
+    sm->xa[tid] = va;
+    sm->xb[tid] = vb;
+  }
+  if (tid < 8) reinterpret_cast<int*>(&sm->sc)[tid] = cv;
+  __syncthreads();
+}
+
+struct SolveSmem;
+__device__ __forceinline__ void block_publish_unchanged(const SolveArgs& s, SolveSmem* sm);
+
+// One Kalman step from the reduced blob in sm->blob (esekfom.hpp:297-345) on the filter state held in shared memory
+// (sm->xa = x, sm->xb = x_propagated, sm->P, sm->sc); x, the loop state and -- at the end -- P are mirrored to global.
 __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* sm) {
   const int tid = threadIdx.x;
   Ctrl* ctrl = s.ctrl;
-  // everything the step reads comes in with ONE round of loads (all issued before the first use)
-  {
-    double vp[3], vq[2], va = 0.0, vb = 0.0;
-#pragma unroll
-    for (int u = 0; u < 3; ++u) vp[u] = (tid + u * THREADS < 576) ? __ldcg(s.P + tid + u * THREADS) : 0.0;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) vq[u] = (tid + u * THREADS < 288) ? __ldcg(s.prior + tid + u * THREADS) : 0.0;
-    if (tid < 26) {
-      va = __ldcg(reinterpret_cast<const double*>(s.x) + tid);
-      vb = __ldcg(reinterpret_cast<const double*>(s.xprop) + tid);
-    }
-#pragma unroll
-    for (int u = 0; u < 3; ++u)
-      if (tid + u * THREADS < 576) sm->P[tid + u * THREADS] = vp[u];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (tid + u * THREADS < 288) sm->prior[tid + u * THREADS] = vq[u];
-    if (tid < 26) {
-      sm->xa[tid] = va;
-      sm->xb[tid] = vb;
-    }
-  }
-  const int iter = __ldcg(&ctrl->iter), max_iter = __ldcg(&ctrl->max_iter), t_old = __ldcg(&ctrl->t),
-            np_old = __ldcg(&ctrl->n_passes);
+  const int iter = sm->sc.iter, max_iter = sm->sc.max_iter, t_old = sm->sc.t, np_old = sm->sc.n_passes;
   if (tid < LIO_BLOB) s.blob[tid] = sm->blob[tid];
   const int n_valid = (int)sm->blob[90];
+  __syncthreads();
   if (n_valid < 1) {
     // `if (!dyn_share.valid) continue;` (esekfom.hpp:297-299): nothing changes, the loop counter advances
-    const int conv_old = __ldcg(&ctrl->converge);
     if (tid == 0) {
-      ctrl->n_valid_last = 0;
-      ctrl->n_passes = np_old + 1;
-      ctrl->iter = iter + 1;
-      if (iter + 1 >= max_iter) ctrl->done = 1;
-      sm->pubrec[32] = (double)conv_old;
-      sm->pubrec[33] = (iter + 1 >= max_iter) ? 1.0 : 0.0;
+      sm->sc.n_valid_last = 0;
+      sm->sc.n_passes = np_old + 1;
+      sm->sc.iter = iter + 1;
+      if (iter + 1 >= max_iter) sm->sc.done = 1;
+      *ctrl = sm->sc;
+      sm->pubrec[32] = (double)sm->sc.converge;
+      sm->pubrec[33] = (double)sm->sc.done;
     }
     if (tid < 26) sm->xn[tid] = sm->xa[tid];
     __syncthreads();
+    block_publish_unchanged(s, sm);
     return;
   }
   __syncthreads();
@@ -538,75 +603,81 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
     sm->S[k] = sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)] * inv_R + sm->prior[k];
   }
   __syncthreads();
-  // warp 0 inverts S while warp 1 (two rotations) and warp 2 (vector parts) form dx_new = x [-] x_propagated
-  // (esekfom.hpp:303)
-  if (tid < 32) warp_inverse_smem(sm->S, sm->Sinv, n, sm->W);
-  if (tid == 32) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 3), reinterpret_cast<const Quatd*>(sm->xb + 3), sm->dxn + 3);
-  if (tid == 33) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 7), reinterpret_cast<const Quatd*>(sm->xb + 7), sm->dxn + 6);
-  if (tid >= 64 && tid < 64 + 24) {
-    const int j = tid - 64;  // error-state index; state index: pos 0-2 | t_LI 11-13 | vel.. 14-25
-    if (j < 3) sm->dxn[j] = sm->xa[j] - sm->xb[j];
-    if (j >= 9) sm->dxn[j] = sm->xa[j + 2] - sm->xb[j + 2];
+  // warps 0-2 (0-5 when n = 12) invert S while the last two warps form dx_new = x [-] x_propagated (esekfom.hpp:303):
+  // one rotation per thread, the vector parts next to them
+  {
+    const int nthr = inv_threads(n);
+    if (tid < nthr) block_inverse_spd(sm->S, sm->Sinv, n, sm->W);
+    if (tid == THREADS - 32) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 3), reinterpret_cast<const Quatd*>(sm->xb + 3), sm->dxn + 3);
+    if (tid == THREADS - 64) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 7), reinterpret_cast<const Quatd*>(sm->xb + 7), sm->dxn + 6);
+    if (tid >= THREADS - 31 && tid < THREADS - 31 + 24) {
+      const int j = tid - (THREADS - 31);  // error-state index; state index: pos 0-2 | t_LI 11-13 | vel.. 14-25
+      if (j < 3) sm->dxn[j] = sm->xa[j] - sm->xb[j];
+      if (j >= 9) sm->dxn[j] = sm->xa[j + 2] - sm->xb[j + 2];
+    }
   }
   __syncthreads();
   stamp(s.dbg, 128, 21);
-  // K_front[:, :n] = [Sinv ; (P21 P11^-1) Sinv]
-#pragma unroll 1
-  for (int k = tid; k < 24 * n; k += THREADS) {
-    const int r = k / n, c = k % n;
-    double acc;
-    if (r < n) {
-      acc = sm->Sinv[r * n + c];
-    } else {
-      acc = 0.0;
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) acc = fma(sm->prior[144 + (r - n) * n + j], sm->Sinv[j * n + c], acc);
-    }
-    sm->Kf[k] = acc;
-  }
-  __syncthreads();
-  // KH[:, :n] = K_front[:, :n] HtH / R ;  K h = K_front[:, :n] Hth / R   (esekfom.hpp:314-319, regrouped)
-#pragma unroll 1
-  for (int k = tid; k < 24 * n + 24; k += THREADS) {
-    if (k < 24 * n) {
-      const int r = k / n, c = k % n;
-      double acc = 0.0;
+  // dx = K h + (K H - I) dx_new (esekfom.hpp:319) with K_front[:, :n] = [I ; P21 P11^-1] Sinv, regrouped so that only
+  // three n-sized products are on the way:  v = Hth/R + (HtH/R) dx_new[:n] ;  u = Sinv v ;
+  // dx[:n] = u - dx_new[:n] ;  dx[n:] = (P21 P11^-1) u - dx_new[n:].   One warp, no block barrier.
+  if (tid < 32) {
+    double* v = sm->Kh;       // n
+    double* u = sm->Kh + 12;  // n
+    if (tid < n) {
+      double acc = sm->blob[78 + tid];
 #pragma unroll 1
       for (int j = 0; j < n; ++j) {
-        const int lo = j < c ? j : c, hi = j < c ? c : j;
-        acc = fma(sm->Kf[r * n + j], sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)], acc);
+        const int lo = j < tid ? j : tid, hi = j < tid ? tid : j;
+        acc = fma(sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)], sm->dxn[j], acc);
       }
-      sm->KH[k] = acc * inv_R;
-    } else {
-      const int r = k - 24 * n;
+      v[tid] = acc * inv_R;
+    }
+    __syncwarp();
+    if (tid < n) {
       double acc = 0.0;
 #pragma unroll 1
-      for (int j = 0; j < n; ++j) acc = fma(sm->Kf[r * n + j], sm->blob[78 + j], acc);
-      sm->Kh[r] = acc * inv_R;
+      for (int j = 0; j < n; ++j) acc = fma(sm->Sinv[tid * n + j], v[j], acc);
+      u[tid] = acc;
     }
-  }
-  __syncthreads();
-  if (tid < 24) {
-    // dx = K h + (K H - I) dx_new   (esekfom.hpp:319)
-    double acc = 0.0;
+    __syncwarp();
+    if (tid < 24) {
+      double acc;
+      if (tid < n) {
+        acc = u[tid];
+      } else {
+        acc = 0.0;
 #pragma unroll 1
-    for (int c = 0; c < 24; ++c) {
-      const double khc = (c < n) ? sm->KH[tid * n + c] : 0.0;
-      acc = fma(khc - (tid == c ? 1.0 : 0.0), sm->dxn[c], acc);
+        for (int j = 0; j < n; ++j) acc = fma(sm->prior[144 + (tid - n) * n + j], u[j], acc);
+      }
+      sm->dx[tid] = acc - sm->dxn[tid];
     }
-    sm->dx[tid] = sm->Kh[tid] + acc;
   }
   __syncthreads();
   stamp(s.dbg, 128, 22);
-  // x = x [+] dx (esekfom.hpp:321): warp 0 the two rotations, warp 1 the vector parts, warp 2 the loop state
-  if (tid == 0) rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 3), sm->dx + 3, reinterpret_cast<Quatd*>(sm->xn + 3));
-  if (tid == 1) rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 7), sm->dx + 6, reinterpret_cast<Quatd*>(sm->xn + 7));
-  if (tid >= 32 && tid < 32 + 24) {
-    const int j = tid - 32;
-    if (j < 3) sm->xn[j] = sm->xa[j] + sm->dx[j];
-    if (j >= 9) sm->xn[j + 2] = sm->xa[j + 2] + sm->dx[j];
+  // x = x [+] dx (esekfom.hpp:321): one rotation per thread (each goes straight on to the per-pass constants of the
+  // new state that every worker needs next: SolveArgs::pub), the vector parts and the loop state in other warps
+  PassConst* pc = reinterpret_cast<PassConst*>(sm->pubrec);
+  if (tid == 0) {
+    rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 3), sm->dx + 3, reinterpret_cast<Quatd*>(sm->xn + 3));
+    pc->rot = Quatd{sm->xn[3], sm->xn[4], sm->xn[5], sm->xn[6]};
+    quat_to_mat(pc->rot, pc->Rt);
   }
-  if (tid == 64) {
+  if (tid == 32) {
+    rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 7), sm->dx + 6, reinterpret_cast<Quatd*>(sm->xn + 7));
+    pc->rli = Quatd{sm->xn[7], sm->xn[8], sm->xn[9], sm->xn[10]};
+    quat_to_mat(pc->rli, pc->Rli);
+  }
+  if (tid >= 64 && tid < 64 + 24) {
+    const int j = tid - 64;
+    if (j < 3) {
+      sm->xn[j] = sm->xa[j] + sm->dx[j];
+      pc->pos[j] = sm->xn[j];
+    }
+    if (j >= 9) sm->xn[j + 2] = sm->xa[j + 2] + sm->dx[j];
+    if (j >= 9 && j < 12) pc->tli[j - 9] = sm->xn[j + 2];
+  }
+  if (tid == 96) {
     bool converge = true;
 #pragma unroll 1
     for (int jj = 0; jj < 24; ++jj)
@@ -618,12 +689,13 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
     if (converge) t++;
     if (!t && iter == max_iter - 2) converge = true;
     const int fin = (t > 1 || iter == max_iter - 1) ? 1 : 0;
-    ctrl->converge = converge ? 1 : 0;
-    ctrl->t = t;
-    ctrl->n_valid_last = n_valid;
-    ctrl->n_passes = np_old + 1;
-    ctrl->iter = iter + 1;
-    if (fin) ctrl->done = 1;
+    sm->sc.converge = converge ? 1 : 0;
+    sm->sc.t = t;
+    sm->sc.n_valid_last = n_valid;
+    sm->sc.n_passes = np_old + 1;
+    sm->sc.iter = iter + 1;
+    if (fin) sm->sc.done = 1;
+    *ctrl = sm->sc;
     sm->fin = fin;
     sm->pubrec[32] = converge ? 1.0 : 0.0;
     sm->pubrec[33] = fin ? 1.0 : 0.0;
@@ -631,9 +703,40 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
   if (tid < 24 && s.dx_out) s.dx_out[tid] = sm->dx[tid];
   __syncthreads();
   stamp(s.dbg, 128, 23);
-  if (tid < 26) reinterpret_cast<double*>(s.x)[tid] = sm->xn[tid];
+  if (tid < 34) s.pub[tid] = sm->pubrec[tid];
+  if (tid < 26) {
+    reinterpret_cast<double*>(s.x)[tid] = sm->xn[tid];
+    sm->xa[tid] = sm->xn[tid];  // the next step starts here
+  }
   if (sm->fin) {
-    // P = (I - K H) P   (esekfom.hpp:342); K H has n non-zero columns
+    // P = (I - K H) P (esekfom.hpp:342), K H = K_front[:, :n] HtH / R with K_front[:, :n] = [Sinv ; (P21 P11^-1) Sinv];
+    // only needed once, after the last step
+#pragma unroll 1
+    for (int k = tid; k < 24 * n; k += THREADS) {
+      const int r = k / n, c = k % n;
+      double acc;
+      if (r < n) {
+        acc = sm->Sinv[r * n + c];
+      } else {
+        acc = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) acc = fma(sm->prior[144 + (r - n) * n + j], sm->Sinv[j * n + c], acc);
+      }
+      sm->Kf[k] = acc;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int k = tid; k < 24 * n; k += THREADS) {
+      const int r = k / n, c = k % n;
+      double acc = 0.0;
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) {
+        const int lo = j < c ? j : c, hi = j < c ? c : j;
+        acc = fma(sm->Kf[r * n + j], sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)], acc);
+      }
+      sm->KH[k] = acc * inv_R;
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int k = tid; k < 576; k += THREADS) {
       const int r = k / 24, c = k % 24;
@@ -646,9 +749,8 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
   __syncthreads();
 }
 
-// After a step: the per-pass constants of the new state (sm->xn) and the loop flags go out as one 34-double record,
-// so that every other block starts its next pass after a single round of loads.
-__device__ __forceinline__ void block_publish(const SolveArgs& s, SolveSmem* sm) {
+// The skipped step (no valid point) leaves the state as it was: its per-pass constants still have to go out.
+__device__ __forceinline__ void block_publish_unchanged(const SolveArgs& s, SolveSmem* sm) {
   const int tid = threadIdx.x;
   PassConst* pc = reinterpret_cast<PassConst*>(sm->pubrec);
   if (tid == 0) {
@@ -676,12 +778,13 @@ struct __align__(16) PassSmem {
 };
 
 // ps->pc holds the per-pass constants (the caller loads or computes them and synchronises the block).
-__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps) {
+// Worker `wid` of `nworkers` takes tiles wid, wid + nworkers, ... and leaves its partial blob in a.partials[wid].
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid) {
   const int tid = threadIdx.x;
   const int M = *a.scan_m;
   stamp(a.dbg, 0, 2);
-  const int G = pick_group(M, gridDim.x);
-  const int rows = search ? THREADS / G : pick_rows_cached(M, gridDim.x);
+  const int G = pick_group(M, nworkers);
+  const int rows = search ? THREADS / G : pick_rows_cached(M, nworkers);
   const int ntiles = tiles_of(M, rows);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   const int nseg = THREADS / nout;
@@ -693,7 +796,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps) {
   }
   double acc = 0.0;
 #pragma unroll 1
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = wid; tile < ntiles; tile += nworkers) {
     if (search) {
       if (G == 32)
         search_tile<32>(a, ps->pc, M, tile, ps->nb, ps->cnt);
@@ -715,66 +818,68 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps) {
     __syncthreads();
     stamp(a.dbg, 0, 5);
   }
-  if (blockIdx.x < ntiles) {
+  if (wid < ntiles) {
     if (seg < nseg) ps->acc[seg * nout + o] = acc;
     __syncthreads();
     if (tid < nout) {
       double s = 0.0;
       for (int g = 0; g < nseg; ++g) s += ps->acc[g * nout + tid];
-      a.partials[(size_t)(a.extrinsic_est ? c_oe_ext[tid] : c_oe_no[tid]) * gridDim.x + blockIdx.x] = s;
+      a.partials[(size_t)wid * LIO_BLOB + (a.extrinsic_est ? c_oe_ext[tid] : c_oe_no[tid])] = s;
     }
   }
   stamp(a.dbg, 0, 6);
 }
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // The whole update_iterated_dyn_share_modified loop (esekfom.hpp:270-346).  Cooperative launch: all blocks resident.
-__global__ void __launch_bounds__(THREADS, 2) update_kernel(const PassArgs a, const SolveArgs s) {
-  __shared__ PassSmem ps;
-  static_assert(sizeof(SolveSmem) <= sizeof(double) * ROWS_MAX * RS, "solve scratch must fit the row staging area");
-  SolveSmem& ss = *reinterpret_cast<SolveSmem*>(ps.rows);
+// Blocks 0 .. gridDim-2 are WORKERS (h_share_model passes); the last block is the SOLVER: it keeps the filter state in
+// shared memory for the whole update, sums the workers' partial blobs as they arrive, performs the Kalman step and
+// publishes the constants of the next pass.  Flags are epoch stamps (target = epoch + pass + 1), so nothing has to be
+// zeroed between launches.
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const PassArgs a, const SolveArgs s,
+                                                                            const unsigned epoch) {
+  __shared__ __align__(16) unsigned char smem_raw[sizeof(PassSmem) > sizeof(SolveSmem) ? sizeof(PassSmem)
+                                                                                        : sizeof(SolveSmem)];
   const int tid = threadIdx.x;
   const int n = a.extrinsic_est ? 12 : 6;
-  const unsigned nblk = gridDim.x;
-  // the last block prepares the prior while the others already search (pass 0 always searches at the prior state)
-  if (blockIdx.x == nblk - 1) block_prior(s, n, &ss);
+  const int nworkers = (int)gridDim.x - 1;
+  if ((int)blockIdx.x == nworkers) {
+    // ---------------------------------------------------------------- solver
+    SolveSmem& ss = *reinterpret_cast<SolveSmem*>(smem_raw);
+    block_prior(s, n, &ss);
+    bool search = true;
+    for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
+      const unsigned target = epoch + (unsigned)pass_no + 1u;
+      stamp(a.dbg, 128, 10);
+      block_reduce_partials(a, search, nworkers, target, ss.blob, ss.warp_part);
+      stamp(a.dbg, 128, 11);
+      block_solve(s, n, &ss);
+      stamp(a.dbg, 128, 12);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release(&s.sync[1], target);
+      search = ss.sc.converge != 0;
+      if (ss.sc.done) break;
+      __syncthreads();
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ workers
+  PassSmem& ps = *reinterpret_cast<PassSmem*>(smem_raw);
+  const int wid = (int)blockIdx.x;
   const StateD* x_first = s.from_snapshot ? s.x0 : s.x;
   stamp(a.dbg, 0, 1);
   if (tid == 0) load_pass_const(x_first, ps.pc);  // pass 0 searches at the prior
   __syncthreads();
   bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
-    block_pass(a, search, &ps);
-    // grid barrier; the last block to arrive reduces and solves
+    const unsigned target = epoch + (unsigned)pass_no + 1u;
+    block_pass(a, search, &ps, nworkers, wid);
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-      const unsigned ticket = atomicAdd(&s.sync[0], 1u);
-      ps.flag = (ticket == (unsigned)(pass_no + 1) * nblk - 1u) ? 1 : 0;
-    }
-    __syncthreads();
-    stamp(a.dbg, 0, 7);
-    if (ps.flag) {
-      __threadfence();
-      stamp(a.dbg, 128, 10);
-      block_reduce_partials(a, search, ss.blob);
-      stamp(a.dbg, 128, 11);
-      block_solve(s, n, &ss);
-      block_publish(s, &ss);
-      stamp(a.dbg, 128, 12);
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release(&s.sync[1], (unsigned)(pass_no + 1));
-    } else if (tid == 0) {
-      while (ld_acquire(&s.sync[1]) < (unsigned)(pass_no + 1)) {
+      st_release(a.arrive + wid, target);
+      stamp(a.dbg, 0, 7);
+      while ((ld_acquire(&s.sync[1]) - target) >= 0x40000000u) {
       }
     }
     __syncthreads();
@@ -794,17 +899,22 @@ __global__ void __launch_bounds__(THREADS, 2) update_kernel(const PassArgs a, co
   }
 }
 
-// One pass at the state in s.x (or its snapshot); the last block to finish reduces the partials into s.blob.
+// One pass at the state in s.x; the last block to finish reduces the partials into s.blob (same worker split and
+// the same summation order as update_kernel, so the stepwise driver reproduces its bits).
 // mode: 0 cached, 1 search, -1 as the loop state says (sharded driver).
-__global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassArgs a, const SolveArgs s, int mode) {
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const PassArgs a, const SolveArgs s, int mode) {
   __shared__ PassSmem ps;
   __shared__ double s_blob[LIO_BLOB];
+  __shared__ double s_warp[(THREADS / 32) * LIO_BLOB];
   const int tid = threadIdx.x;
+  const int nworkers = (int)gridDim.x - 1;
   if (mode < 0 && s.ctrl->done) return;
   const bool search = mode < 0 ? (s.ctrl->converge != 0) : (mode != 0);
-  if (tid == 0) load_pass_const(s.x, ps.pc);
-  __syncthreads();
-  block_pass(a, search, &ps);
+  if ((int)blockIdx.x < nworkers) {
+    if (tid == 0) load_pass_const(s.x, ps.pc);
+    __syncthreads();
+    block_pass(a, search, &ps, nworkers, (int)blockIdx.x);
+  }
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -816,7 +926,7 @@ __global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassArgs a, cons
   if (ps.flag) {
     __threadfence();
     stamp(a.dbg, 128, 10);
-    block_reduce_partials(a, search, s_blob);
+    block_reduce_partials(a, search, nworkers, 0u, s_blob, s_warp);
     stamp(a.dbg, 128, 11);
     if (tid < LIO_BLOB) s.blob[tid] = s_blob[tid];
     if (tid == 0) s.sync[0] = 0;  // ready for the next pass launch
@@ -827,6 +937,7 @@ __global__ void __launch_bounds__(THREADS, 2) pass_kernel(const PassArgs a, cons
 __global__ void __launch_bounds__(THREADS) solve_kernel(const SolveArgs s, int extrinsic_est) {
   __shared__ SolveSmem ss;
   if (s.ctrl->done) return;
+  solve_load_inputs(s, &ss);
   if (threadIdx.x < LIO_BLOB) ss.blob[threadIdx.x] = s.blob[threadIdx.x];
   __syncthreads();
   block_solve(s, extrinsic_est ? 12 : 6, &ss);
@@ -920,6 +1031,12 @@ int ensure_tables(lio_ctx* c) {
   LIO_CHECK(c, cudaMemcpyToSymbol(c_oa_no, na, NOUT_NOEXT));
   LIO_CHECK(c, cudaMemcpyToSymbol(c_ob_no, nb, NOUT_NOEXT));
   LIO_CHECK(c, cudaMemcpyToSymbol(c_oe_no, ne, NOUT_NOEXT));
+  {
+    unsigned char is_no[78];
+    memset(is_no, 0, sizeof(is_no));
+    for (int i = 0; i < 21; ++i) is_no[ne[i]] = 1;
+    LIO_CHECK(c, cudaMemcpyToSymbol(c_is_no, is_no, 78));
+  }
   if (c->device < 64) g_tables_ready[c->device] = true;
   return LIO_OK;
 }
@@ -930,7 +1047,7 @@ int pass_grid_blocks(lio_ctx* c) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, update_kernel, THREADS, 0) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > LIO_BLOCKS_PER_SM) per_sm = LIO_BLOCKS_PER_SM;
   c->pass_grid = per_sm * c->sm_count;
   return c->pass_grid;
 }
@@ -954,6 +1071,7 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.own_min = own_min;
   a.own_max = own_max;
   a.partials = c->d_partials;
+  a.arrive = c->d_arrive;
   a.dbg = c->d_dbg;
   if (c->d_dbg) cudaMemsetAsync(c->d_dbg, 0, 256 * sizeof(long long), c->stream);
   return a;
@@ -985,8 +1103,15 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   if (rc) return rc;
   PassArgs a = make_pass_args(c, ext, -INFINITY, INFINITY);
   SolveArgs s = make_solve_args(c, R, max_iter, from_snapshot);
-  LIO_CHECK(c, cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
-  void* args[] = {&a, &s};
+  // arrival / release flags are epoch stamps: nothing to zero between launches (wrap-around once in ~10^8 updates)
+  if (c->epoch > 0xF0000000u) {
+    LIO_CHECK(c, cudaMemsetAsync(c->d_arrive, 0, sizeof(unsigned) * 1024, c->stream));
+    LIO_CHECK(c, cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
+    c->epoch = 0;
+  }
+  unsigned epoch = c->epoch;
+  c->epoch += 40;  // > max_iter + 2
+  void* args[] = {&a, &s, &epoch};
   LIO_CHECK(c, cudaLaunchCooperativeKernel((const void*)update_kernel, dim3(pass_grid_blocks(c)), dim3(THREADS), args,
                                            0, c->stream));
   c->launches++;

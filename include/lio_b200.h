@@ -145,6 +145,11 @@ int lio_update_pass(lio_ctx* ctx, const lio_state* x, int do_search, int extrins
  * h_share_model calls made. */
 int lio_update_scan(lio_ctx* ctx, lio_state* x_io, double P_io[576], double R, int max_iter, int extrinsic_est,
                     int32_t* n_valid_last, int32_t* n_passes);
+/* The same for a downsampled cloud in HOST memory (m records of stride 16: x,y,z,intensity): scan up, prior up (one
+ * copy each), one kernel, posterior down.  This is the per-scan call of a host that runs its own voxel filter. */
+int lio_update_scan_host(lio_ctx* ctx, const void* down_pts, int64_t m, int stride_bytes, lio_state* x_io,
+                         double P_io[576], double R, int max_iter, int extrinsic_est, int32_t* n_valid_last,
+                         int32_t* n_passes);
 /* Device-resident pieces of the above (used by bench.py and by the multi-GPU sharded-map driver):        */
 int lio_state_upload(lio_ctx* ctx, const lio_state* x, const double P[576]); /* also stored as the prior snapshot */
 int lio_state_download(lio_ctx* ctx, lio_state* x, double P[576], int32_t* n_valid_last, int32_t* n_passes);

@@ -139,3 +139,16 @@ def test_stepwise_driver_equals_persistent_kernel(ctx, orc, small_cfg, ext):
     c = ctx.state_download()
     assert a[2:] == c[2:]
     assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+
+
+def test_update_scan_host_equals_upload_plus_update(ctx, orc, small_cfg):
+    """The fused per-scan host call (scan + prior up in two copies, one kernel, posterior down) gives the bits of
+    lio_scan_upload + lio_update_scan."""
+    cfg = small_cfg
+    body, _ = _setup(ctx, cfg, orc)
+    a = ctx.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, False)
+    for _ in range(2):  # twice: the barrier words travel with the prior
+        x, P = cfg["x_prior"].copy(), np.ascontiguousarray(cfg["P"]).copy()
+        nv, npass = ctx.update_scan_host(np.ascontiguousarray(body[:, :4]), x, P, 0.001, 4, False)
+        assert (nv, npass) == a[2:]
+        assert np.array_equal(x, a[0]) and np.array_equal(P, a[1])
