@@ -151,10 +151,20 @@ struct HeadFlag {
   __device__ __forceinline__ bool operator()(const int& j) const { return j == 0 || keys[j] != keys[j - 1]; }
 };
 
-// one thread per run of equal leaf indices: FP32 sums in sorted (= ascending point) order, then / count
-__global__ void centroid_kernel(const uint32_t* sorted_vals, const int* heads, const int* n_runs, int n, int max_m,
-                                const float4* undist, const float* aux, float4* body, float* body_time, int* scan_m,
-                                int* counters) {
+// points (and intensities) in sorted order: the runs become contiguous, so the sequential sums below stream memory
+__global__ void gather_sorted_kernel(const uint32_t* sorted_vals, int n, const float4* undist, const float* aux,
+                                     float4* sorted_pts, float* sorted_aux) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t i = sorted_vals[j];
+  sorted_pts[j] = __ldg(undist + i);
+  if (aux) sorted_aux[j] = __ldg(aux + i);
+}
+
+// one thread per run of equal leaf indices: FP32 sums in sorted (= ascending point) order, then / count.  The order
+// is sequential by definition (bit parity with the oracle); the loads are independent and issued eight at a time.
+__global__ void centroid_kernel(const float4* sorted_pts, const float* sorted_aux, const int* heads, const int* n_runs,
+                                int n, int max_m, float4* body, float* body_time, int* scan_m, int* counters) {
   const int Mtot = *n_runs;
   const int M = Mtot > max_m ? max_m : Mtot;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,14 +176,31 @@ __global__ void centroid_kernel(const uint32_t* sorted_vals, const int* heads, c
   if (m >= M) return;
   const int beg = heads[m], end = (m + 1 < Mtot) ? heads[m + 1] : n;
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f, st = 0.f;
-  for (int j = beg; j < end; ++j) {
-    const uint32_t i = sorted_vals[j];
-    const float4 p = __ldg(undist + i);
+  int j = beg;
+  for (; j + 8 <= end; j += 8) {
+    float4 p[8];
+    float q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      p[u] = __ldg(sorted_pts + j + u);
+      q[u] = sorted_aux ? __ldg(sorted_aux + j + u) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      sx = sx + p[u].x;
+      sy = sy + p[u].y;
+      sz = sz + p[u].z;
+      st = st + p[u].w;
+      si = si + q[u];
+    }
+  }
+  for (; j < end; ++j) {
+    const float4 p = __ldg(sorted_pts + j);
     sx = sx + p.x;
     sy = sy + p.y;
     sz = sz + p.z;
     st = st + p.w;
-    if (aux) si = si + __ldg(aux + i);
+    if (sorted_aux) si = si + __ldg(sorted_aux + j);
   }
   const float cnt = (float)(end - beg);
   body[m] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
@@ -235,8 +262,15 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
   }
   const int max_m = (int)c->caps.max_down_points;
   const int cgrid = (int)((std::min<int64_t>(n, max_m) + 127) / 128);
+  float4* sorted_pts = c->d_raw;  // the raw scan has been consumed by now
+  float* sorted_aux = has_aux ? reinterpret_cast<float*>(c->d_svox_acc) : nullptr;
+  if (n > 0) {
+    gather_sorted_kernel<<<grid, 256, 0, c->stream>>>(c->d_sort_vals_out, (int)n, c->d_undist,
+                                                      has_aux ? c->d_raw_aux : nullptr, sorted_pts, sorted_aux);
+    c->launches++;
+  }
   centroid_kernel<<<cgrid > 0 ? cgrid : 1, 128, 0, c->stream>>>(
-      c->d_sort_vals_out, heads, n_runs, (int)n, max_m, c->d_undist, has_aux ? c->d_raw_aux : nullptr, c->d_body,
+      sorted_pts, sorted_aux, heads, n_runs, (int)n, max_m, c->d_body,
       reinterpret_cast<float*>(c->d_normvec) /*scratch: mean time*/, c->d_scan_m, c->d_prep_counters);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());

@@ -22,15 +22,20 @@ def _p4(xyz):
     return np.concatenate([xyz, np.zeros((len(xyz), 1), np.float32)], 1)
 
 
-def test_config2_trajectory_pose_parity(orc):
+@pytest.mark.parametrize("name,n_scans,seed,rings,cols,fov,max_range", [
+    ("config 2 (VLP-16, 200 scans)", N_SCANS, 2002, 16, 1800, (-15.0, 15.0), 100.0),
+    ("config 4 shape (OS1-64, one of the 64 sequences, 40 scans)", 40, 4000, 64, 1024, (-22.5, 22.5), 120.0),
+])
+def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_range):
     from agi_lidar_slam_b200 import _cabi, synth
     from agi_lidar_slam_b200.replay import LioReplay, MeasureGroup, ReplayConfig
     from replay_oracle import OracleReplay
 
-    seq = synth.sequence(N_SCANS, 2002)  # 16 rings x 1800 columns, 10 Hz, IMU 200 Hz
+    N_SCANS = n_scans
+    seq = synth.sequence(n_scans, seed, rings=rings, cols=cols, fov=fov, max_range=max_range)  # 10 Hz, IMU 200 Hz
     traj = synth.RampedTrajectory(synth.Trajectory())
     R0, p0 = traj.rot(0.0), traj.pos(0.0)
-    with _cabi.Context(0, max_scan_points=1 << 16, max_down_points=1 << 15, max_map_points=1 << 21) as ctx:
+    with _cabi.Context(0, max_scan_points=1 << 17, max_down_points=1 << 16, max_map_points=1 << 21) as ctx:
         gpu = LioReplay(ctx, ReplayConfig(max_iteration=3))
         cpu = OracleReplay(orc, max_iteration=3)
         worst_pos, worst_rot, worst_P, n_upd, exact_scans, map_resync = 0.0, 0.0, 0.0, 0, 0, 0
@@ -68,6 +73,6 @@ def test_config2_trajectory_pose_parity(orc):
     # the odometry follows the motion (scan-to-map registration on a 16-ring sensor drifts; both sides agree on it)
     pr = R0.T @ (seq[-1]["truth_pos"] - p0)
     assert np.linalg.norm(b[0:3] - pr) < 0.25 * max(1.0, np.linalg.norm(pr))
-    print(f"config 2: {n_upd} updates, worst |dpos| {worst_pos:.2e} m, worst |drot| {worst_rot:.2e} rad, worst rel |dP| "
+    print(f"{name}: {n_upd} updates, worst |dpos| {worst_pos:.2e} m, worst |drot| {worst_rot:.2e} rad, worst rel |dP| "
           f"{worst_P:.2e}, bit-identical discrete outcomes in {exact_scans}/{n_upd} scans, map resyncs {map_resync}, "
           f"map {map_valid} pts")

@@ -152,3 +152,36 @@ def test_update_scan_host_equals_upload_plus_update(ctx, orc, small_cfg):
         nv, npass = ctx.update_scan_host(np.ascontiguousarray(body[:, :4]), x, P, 0.001, 4, False)
         assert (nv, npass) == a[2:]
         assert np.array_equal(x, a[0]) and np.array_equal(P, a[1])
+
+
+@pytest.mark.parametrize("ext", [False, True])
+def test_many_tiles_per_block(ctx, orc, avia_cfg, ext):
+    """M = 20,174 (the un-downsampled Avia scan): more queries than the persistent grid holds at once, so every
+    worker loops over several search tiles and several cached tiles; same parity rules as the small cases."""
+    cfg = avia_cfg
+    mp = cfg["map"]
+    ctx.map_build(np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1))
+    body = np.ascontiguousarray(cfg["scan"][:, :4]).copy()
+    body[:, 3] = 0
+    m = len(body)
+    assert m > 2 * 295 * 32
+    ctx.scan_upload(body)
+    om = orc.Map(1.0)
+    om.build(mp)
+    x = cfg["x_prior"]
+    sc = orc.Scan(body[:, :3])
+    for do_search in (True, False):
+        V = sc.h_share_model(x, do_search, ext, om.knn_backend(), threads=8)
+        ref = sc.get()
+        hx, h, vi = sc.rows(V)
+        blob, nv = ctx.update_pass(x, do_search, ext)
+        got = ctx.get_neighbors(m)
+        assert np.array_equal(got["idx"], ref["idx"]) and np.array_equal(got["selected"], ref["selected"])
+        assert nv == V
+        HtH = hx.T @ hx
+        ref_blob = np.concatenate([HtH[np.triu_indices(12)], hx.T @ h])
+        assert rel_err(blob, ref_blob) < 1e-9
+    xr, Pr, trace, nvr = orc.Scan(body[:, :3]).update(x, cfg["P"], om.knn_backend(), 0.001, 4, ext, threads=8)
+    xg, Pg, nvg, npass = ctx.update_scan(x, cfg["P"], 0.001, 4, ext)
+    assert npass == len(trace) and nvg == nvr
+    assert np.abs(xg - xr).max() < 1e-7 and rel_err(Pg, Pr) < 1e-6
