@@ -44,60 +44,64 @@ struct TopK {
   }
 };
 
-// One bucket: the cell's float4 slots are contiguous, so a lane streams them with four loads in flight.
-// Code size matters more than instruction count here (the pass has to stay inside the 32 KB L1.5 instruction cache),
-// so the loop over buckets is NOT unrolled around this.
-__device__ __forceinline__ void scan_bucket(const MapView& map, float qx, float qy, float qz, uint32_t max_bits,
-                                            uint32_t start, uint32_t count, TopK& top) {
-#pragma unroll 1
-  for (uint32_t t = 0; t < count; t += 4) {
-    float4 p[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) p[j] = __ldg(map.pool + start + min(t + j, count - 1));
-    const uint32_t nj = min(4u, count - t);
-#pragma unroll 1
-    for (uint32_t j = 0; j < nj; ++j) {
-      float4 q = p[0];  // static selects keep p[] in registers; ONE copy of the insertion code
-      if (j == 1) q = p[1];
-      if (j == 2) q = p[2];
-      if (j == 3) q = p[3];
-      const int id = __float_as_int(q.w);
-      const uint32_t db = __float_as_uint(dist2(qx, qy, qz, q.x, q.y, q.z));
-      if (id >= 0 && db <= max_bits) top.insert(((unsigned long long)db << 32) | (uint32_t)id, start + t + j);
-    }
-  }
-}
-
 // A group of G lanes (G = 8, 16 or 32, aligned inside a warp) calls this with the SAME query; `gmask` names the
 // group's lanes, `gl` is the lane's index inside the group.
-// Stage 1: the 27 cells of the 3x3x3 block around the query's cell are dealt round-robin to the lanes; a lane
-// first issues the hash probes of all its cells (independent loads), then walks each cell's float4 bucket keeping
-// a private top-5.  The block holds every map point closer than `cell` to the query, so if the group has seen >= 5
-// points with d2 < cell^2 the result is already exact (the common case at one map point per 0.5 m voxel).
-// Otherwise stage 2 visits the remaining cells of the (2*rings+1)^3 block whose box distance is within the bound.
+// Round 0: the 27 cells of the 3x3x3 block around the query's cell are dealt round-robin to the lanes; a lane first
+// issues the hash probes of all its cells (independent loads), then streams the buckets it found as ONE virtual list,
+// four float4 loads in flight while the previous four are inserted into its private top-5.  The block holds every map
+// point closer than `cell` to the query, so if the group has seen >= 5 points with d2 < cell^2 the result is already
+// exact (the common case at one map point per 0.5 m voxel).  Otherwise further rounds visit, CPL cells per lane at a
+// time through the same code, the remaining cells of the (2*rings+1)^3 block whose box distance is within the bound.
 // The group then extracts the global top-5 with five rounds of redux.min on (d2 bits, id).
 // Outputs are group-uniform: out_key[r] (d2 bits << 32 | id; ~0 when fewer than r+1 found), out_slot[r].
 template <int G>
 __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy, float qz, float max_d2, int rings,
                                           unsigned gmask, int gl, unsigned long long out_key[LIO_K],
                                           uint32_t out_slot[LIO_K]) {
-  constexpr int CPL = (27 + G - 1) / G;  // cells per lane in stage 1
+  constexpr int CPL = (27 + G - 1) / G;  // cells per lane and round
   const int cx = cell_coord(qx, map.inv_cell), cy = cell_coord(qy, map.inv_cell), cz = cell_coord(qz, map.inv_cell);
   TopK top;
   top.init();
   const uint32_t max_bits = __float_as_uint(max_d2);
-  {
+  const int side = 2 * rings + 1;
+  const int ncell = side * side * side;
+  int nrounds = 1;
+#pragma unroll 1
+  for (int round = 0; round < nrounds; ++round) {
     unsigned long long key[CPL];
     uint32_t h[CPL];
     uint4 e[CPL];
 #pragma unroll
     for (int u = 0; u < CPL; ++u) {
-      const int c = gl + u * G;
       key[u] = LIO_EMPTY_KEY;
       h[u] = 0;
       e[u] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
-      if (c < 27) {
-        key[u] = pack_cell(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1);
+      int dx, dy, dz;
+      bool take;
+      if (round == 0) {
+        const int c = gl + u * G;
+        take = c < 27;
+        dx = c % 3 - 1;
+        dy = (c / 3) % 3 - 1;
+        dz = c / 9 - 1;
+      } else {
+        const int c = (round - 1) * (G * CPL) + gl + u * G;
+        dx = c % side - rings;
+        dy = (c / side) % side - rings;
+        dz = c / (side * side) - rings;
+        take = c < ncell && !(dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1);
+        if (take) {
+          const float lx = (float)(cx + dx) * map.cell, ly = (float)(cy + dy) * map.cell,
+                      lz = (float)(cz + dz) * map.cell;
+          const float ex = fmaxf(fmaxf(lx - qx, qx - (lx + map.cell)), 0.f);
+          const float ey = fmaxf(fmaxf(ly - qy, qy - (ly + map.cell)), 0.f);
+          const float ez = fmaxf(fmaxf(lz - qz, qz - (lz + map.cell)), 0.f);
+          // conservative (shrunk by 1e-3 relative) so rounding can never skip a cell that matters
+          take = (ex * ex + ey * ey + ez * ez) * 0.999f <= max_d2;
+        }
+      }
+      if (take) {
+        key[u] = pack_cell(cx + dx, cy + dy, cz + dz);
         h[u] = hash64(key[u]) & map.hash_mask;
         e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
       }
@@ -159,38 +163,14 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
 #pragma unroll
       for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
-  }
-  if (rings > 1) {
-    // exact already?  (0.999: any unseen point has true distance > cell, so its rounded d2 exceeds this bound)
-    const uint32_t near_bits = __float_as_uint(fminf(map.cell * map.cell * 0.999f, max_d2));
-    const int mine = (int)((uint32_t)(top.k0 >> 32) <= near_bits) + (int)((uint32_t)(top.k1 >> 32) <= near_bits) +
-                     (int)((uint32_t)(top.k2 >> 32) <= near_bits) + (int)((uint32_t)(top.k3 >> 32) <= near_bits) +
-                     (int)((uint32_t)(top.k4 >> 32) <= near_bits);
-    const int seen = __reduce_add_sync(gmask, mine);
-    if (seen < LIO_K) {
-      const int side = 2 * rings + 1;
-      const int ncell = side * side * side;
-#pragma unroll 1
-      for (int base = 0; base < ncell; base += G) {
-        const int c = base + gl;
-        if (c < ncell) {
-          const int dx = c % side - rings, dy = (c / side) % side - rings, dz = c / (side * side) - rings;
-          const bool inner = (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1);
-          if (!inner) {
-            const float lx = (float)(cx + dx) * map.cell, ly = (float)(cy + dy) * map.cell,
-                        lz = (float)(cz + dz) * map.cell;
-            const float ex = fmaxf(fmaxf(lx - qx, qx - (lx + map.cell)), 0.f);
-            const float ey = fmaxf(fmaxf(ly - qy, qy - (ly + map.cell)), 0.f);
-            const float ez = fmaxf(fmaxf(lz - qz, qz - (lz + map.cell)), 0.f);
-            // conservative (shrunk by 1e-3 relative) so rounding can never skip a cell that matters
-            if ((ex * ex + ey * ey + ez * ez) * 0.999f <= max_d2) {
-              uint32_t start, count;
-              if (map_find(map, pack_cell(cx + dx, cy + dy, cz + dz), start, count) >= 0)
-                scan_bucket(map, qx, qy, qz, max_bits, start, count, top);
-            }
-          }
-        }
-      }
+    if (round == 0 && rings > 1) {
+      // exact already?  (0.999: any unseen point has true distance > cell, so its rounded d2 exceeds this bound)
+      const uint32_t near_bits = __float_as_uint(fminf(map.cell * map.cell * 0.999f, max_d2));
+      const int mine = (int)((uint32_t)(top.k0 >> 32) <= near_bits) + (int)((uint32_t)(top.k1 >> 32) <= near_bits) +
+                       (int)((uint32_t)(top.k2 >> 32) <= near_bits) + (int)((uint32_t)(top.k3 >> 32) <= near_bits) +
+                       (int)((uint32_t)(top.k4 >> 32) <= near_bits);
+      const int seen = __reduce_add_sync(gmask, mine);
+      if (seen < LIO_K) nrounds = 1 + (ncell + G * CPL - 1) / (G * CPL);
     }
   }
   int found = 0;

@@ -874,9 +874,9 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(cons
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
     const unsigned target = epoch + (unsigned)pass_no + 1u;
     block_pass(a, search, &ps, nworkers, wid);
-    __threadfence();
-    __syncthreads();
+    __syncthreads();  // the partial row is written; the release below (one thread) publishes the block's writes
     if (tid == 0) {
+      __threadfence();
       st_release(a.arrive + wid, target);
       stamp(a.dbg, 0, 7);
       while ((ld_acquire(&s.sync[1]) - target) >= 0x40000000u) {
