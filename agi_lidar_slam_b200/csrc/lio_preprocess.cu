@@ -161,47 +161,106 @@ __global__ void gather_sorted_kernel(const uint32_t* sorted_vals, int n, const f
   if (aux) sorted_aux[j] = __ldg(aux + i);
 }
 
-// one thread per run of equal leaf indices: FP32 sums in sorted (= ascending point) order, then / count.  The order
-// is sequential by definition (bit parity with the oracle); the loads are independent and issued eight at a time.
-__global__ void centroid_kernel(const float4* sorted_pts, const float* sorted_aux, const int* heads, const int* n_runs,
-                                int n, int max_m, float4* body, float* body_time, int* scan_m, int* counters) {
+// One run of equal leaf indices per thread: FP32 sums in sorted (= ascending point) order, then / count.  The order
+// is sequential by definition (bit parity with the oracle), so a run cannot be split; what can be done is to keep its
+// adds fed.  Short runs: the owning thread streams its points eight loads at a time.  Long runs (a wall right next to
+// the sensor puts thousands of points into one leaf): the WARP takes them one after the other -- all lanes stage 256
+// points into shared memory with coalesced loads, then lanes 0-4 run the five component sums (x, y, z, time,
+// intensity) as five independent sequential chains out of shared memory.
+constexpr int LONG_RUN = 96;
+constexpr int STAGE = 256;
+__global__ void __launch_bounds__(128) centroid_kernel(const float4* sorted_pts, const float* sorted_aux,
+                                                       const int* heads, const int* n_runs, int n, int max_m,
+                                                       float4* body, float* body_time, int* scan_m, int* counters) {
+  __shared__ float s_stage[4][5][STAGE];
   const int Mtot = *n_runs;
   const int M = Mtot > max_m ? max_m : Mtot;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (m == 0) {
     *scan_m = counters[7] == 3 ? 0 : M;
     counters[0] = Mtot;
     if (Mtot > max_m && counters[7] == 0) counters[7] = 2;  // more voxels than lio_caps.max_down_points
   }
-  if (m >= M) return;
-  const int beg = heads[m], end = (m + 1 < Mtot) ? heads[m + 1] : n;
+  int beg = 0, end = 0;
+  if (m < M) {
+    beg = heads[m];
+    end = (m + 1 < Mtot) ? heads[m + 1] : n;
+  }
+  const bool is_long = (end - beg) >= LONG_RUN;
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f, st = 0.f;
-  int j = beg;
-  for (; j + 8 <= end; j += 8) {
-    float4 p[8];
-    float q[8];
+  if (m < M && !is_long) {
+    int j = beg;
+    for (; j + 8 <= end; j += 8) {
+      float4 p[8];
+      float q[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      p[u] = __ldg(sorted_pts + j + u);
-      q[u] = sorted_aux ? __ldg(sorted_aux + j + u) : 0.f;
+      for (int u = 0; u < 8; ++u) {
+        p[u] = __ldg(sorted_pts + j + u);
+        q[u] = sorted_aux ? __ldg(sorted_aux + j + u) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        sx = sx + p[u].x;
+        sy = sy + p[u].y;
+        sz = sz + p[u].z;
+        st = st + p[u].w;
+        si = si + q[u];
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      sx = sx + p[u].x;
-      sy = sy + p[u].y;
-      sz = sz + p[u].z;
-      st = st + p[u].w;
-      si = si + q[u];
+    for (; j < end; ++j) {
+      const float4 p = __ldg(sorted_pts + j);
+      sx = sx + p.x;
+      sy = sy + p.y;
+      sz = sz + p.z;
+      st = st + p.w;
+      if (sorted_aux) si = si + __ldg(sorted_aux + j);
     }
   }
-  for (; j < end; ++j) {
-    const float4 p = __ldg(sorted_pts + j);
-    sx = sx + p.x;
-    sy = sy + p.y;
-    sz = sz + p.z;
-    st = st + p.w;
-    if (sorted_aux) si = si + __ldg(sorted_aux + j);
+  // long runs of this warp, one at a time
+  unsigned todo = __ballot_sync(0xffffffffu, m < M && is_long);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int rb = __shfl_sync(0xffffffffu, beg, src), re = __shfl_sync(0xffffffffu, end, src);
+    float acc = 0.f;  // lane c < 5: running sum of component c
+    for (int base = rb; base < re; base += STAGE) {
+      const int cnt = min(STAGE, re - base);
+      __syncwarp();
+      for (int t = lane; t < cnt; t += 32) {
+        const float4 p = __ldg(sorted_pts + base + t);
+        s_stage[warp][0][t] = p.x;
+        s_stage[warp][1][t] = p.y;
+        s_stage[warp][2][t] = p.z;
+        s_stage[warp][3][t] = p.w;
+        s_stage[warp][4][t] = sorted_aux ? __ldg(sorted_aux + base + t) : 0.f;
+      }
+      __syncwarp();
+      if (lane < 5) {
+        const float* v = s_stage[warp][lane];
+        int t = 0;
+        for (; t + 8 <= cnt; t += 8) {
+          float w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = v[t + u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc = acc + w[u];
+        }
+        for (; t < cnt; ++t) acc = acc + v[t];
+      }
+    }
+    const float rx = __shfl_sync(0xffffffffu, acc, 0), ry = __shfl_sync(0xffffffffu, acc, 1),
+                rz = __shfl_sync(0xffffffffu, acc, 2), rt = __shfl_sync(0xffffffffu, acc, 3),
+                ri = __shfl_sync(0xffffffffu, acc, 4);
+    if (lane == src) {
+      sx = rx;
+      sy = ry;
+      sz = rz;
+      st = rt;
+      si = ri;
+    }
   }
+  if (m >= M) return;
   const float cnt = (float)(end - beg);
   body[m] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
   if (body_time) body_time[m] = st / cnt;

@@ -147,6 +147,15 @@ class ClockSampler:
                 "power_w_max": max(self.power) if self.power else None}
 
 
+def ncu_traffic():
+    """DRAM bytes per update_kernel launch from the committed ncu capture of this same workload (profiles/)."""
+    p = ROOT / "profiles" / "r1_update_kernel_traffic.json"
+    try:
+        return float(json.loads(p.read_text())["dram_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -324,7 +333,7 @@ def main():
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n_gpus,
             "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 filter", "data": "synthetic",
-            "config": {"workload": "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4" %
+            "config": {"workload": "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4, 1 sequence per GPU" %
                        (args.rings, args.cols, args.map_points), "M": r["m"], "passes_per_scan": r["passes"]},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                              "kind_detail": r["kind_detail"],
@@ -515,7 +524,8 @@ def main():
     alg_bytes = 116.0 * M * passes_per_scan
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "update_kernel (persistent: all h_share_model passes + Kalman steps of one scan)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                "traffic_source": "profiles/r1_update_kernel_traffic.json (ncu --set full, dram__bytes_read+write.sum)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_cold_l2": launch_ms,
                 "note": "latency-bound by construction: 116 B x M x passes is ~4 MB per scan (SURVEY.md §8d)",
                 "single_pass_kernel": {"search_ms_cold_l2": t_search_cold, "search_ms_warm_l2": t_search_warm,

@@ -114,3 +114,22 @@ def test_preprocess_then_update_resident(ctx, orc, small_cfg):
     ctx.scan_upload(out)
     x2, P2, nv2, np2 = ctx.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, False)
     assert np.array_equal(x1, x2) and nv1 == nv2 and np1 == np2
+
+
+def test_long_runs_bit_exact(ctx, orc):
+    """Thousands of points in one leaf (a wall next to the sensor): the warp-staged sequential sums keep the bits."""
+    rng = np.random.default_rng(9)
+    n = 30000
+    rec = np.zeros((n, 12), np.float32)
+    rec[:, :3] = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    rec[:7000, :3] = (np.array([0.2, 0.3, 0.1]) + rng.uniform(0, 0.05, (7000, 3))).astype(np.float32)  # one leaf
+    rec[7000:7100, :3] = (np.array([1.2, 0.3, 0.1]) + rng.uniform(0, 0.2, (100, 3))).astype(np.float32)  # ~96: boundary
+    rec[:, 3] = 1.0
+    rec[:, 8] = rng.uniform(0, 255, n).astype(np.float32)
+    rec[:, 9] = np.sort(rng.uniform(0, 100, n)).astype(np.float32)
+    rec = rec[rng.permutation(n)]  # the order of the points inside a leaf is the input order, whatever it is
+    out, _, keys = ctx.scan_preprocess(rec, None, None, 0.5, want_keys=True)
+    cen, ckeys, pkeys = orc.voxel_grid(np.concatenate([rec[:, :3], rec[:, 8:10]], 1), 0.5)
+    assert np.array_equal(keys, pkeys) and len(out) == len(cen)
+    assert np.array_equal(out[:, :3].view(np.uint32), cen[:, :3].view(np.uint32))
+    assert np.array_equal(out[:, 8], cen[:, 3]) and np.array_equal(out[:, 9], cen[:, 4])
