@@ -57,8 +57,16 @@ struct TopK {
 template <int G>
 __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy, float qz, float max_d2, int rings,
                                           unsigned gmask, int gl, unsigned long long out_key[LIO_K],
-                                          uint32_t out_slot[LIO_K]) {
+                                          uint32_t out_slot[LIO_K], long long* dbg = nullptr) {
   constexpr int CPL = (27 + G - 1) / G;  // cells per lane and round
+  auto mark = [&](int slot) {  // LIO_TIMELINE instrumentation: block 0 / thread 0 only
+    if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      dbg[slot] = t;
+    }
+  };
+  mark(240);
   const int cx = cell_coord(qx, map.inv_cell), cy = cell_coord(qy, map.inv_cell), cz = cell_coord(qz, map.inv_cell);
   TopK top;
   top.init();
@@ -130,6 +138,7 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
       total += cn;
       end[u] = total;
     }
+    if (round == 0) mark(241);
     // stream the list four points at a time, the next four already in flight while the current four are inserted
     float4 cur[4], nxt[4];
     auto slot_of = [&](uint32_t idx) -> uint32_t {
@@ -149,50 +158,70 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
 #pragma unroll
         for (int j = 0; j < 4; ++j) nxt[j] = __ldg(map.pool + slot_of(min(t + 4 + j, total - 1)));
       }
+      // distance of the four points first (no selects), against the lane's current 5th best: most candidates are
+      // farther and never reach the insertion code, of which there is ONE copy
       const uint32_t nj = min(4u, total - t);
+      const uint32_t thr = min(max_bits, (uint32_t)(top.k4 >> 32));
+      uint32_t db[4];
+      unsigned pass = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        db[j] = __float_as_uint(dist2(qx, qy, qz, cur[j].x, cur[j].y, cur[j].z));
+        if ((uint32_t)j < nj && __float_as_int(cur[j].w) >= 0 && db[j] <= thr) pass |= 1u << j;
+      }
 #pragma unroll 1
-      for (uint32_t j = 0; j < nj; ++j) {
-        float4 q = cur[0];  // static selects keep cur[] in registers; ONE copy of the insertion code
-        if (j == 1) q = cur[1];
-        if (j == 2) q = cur[2];
-        if (j == 3) q = cur[3];
-        const int id = __float_as_int(q.w);
-        const uint32_t db = __float_as_uint(dist2(qx, qy, qz, q.x, q.y, q.z));
-        if (id >= 0 && db <= max_bits) top.insert(((unsigned long long)db << 32) | (uint32_t)id, slot_of(t + j));
+      while (pass) {
+        const int j = __ffs(pass) - 1;
+        pass &= pass - 1;
+        uint32_t d = db[0], id = __float_as_uint(cur[0].w);
+        if (j == 1) { d = db[1]; id = __float_as_uint(cur[1].w); }
+        if (j == 2) { d = db[2]; id = __float_as_uint(cur[2].w); }
+        if (j == 3) { d = db[3]; id = __float_as_uint(cur[3].w); }
+        top.insert(((unsigned long long)d << 32) | id, slot_of(t + (uint32_t)j));
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
+    if (round == 0) mark(242);
     if (round == 0 && rings > 1) {
       // exact already?  (0.999: any unseen point has true distance > cell, so its rounded d2 exceeds this bound)
       const uint32_t near_bits = __float_as_uint(fminf(map.cell * map.cell * 0.999f, max_d2));
       const int mine = (int)((uint32_t)(top.k0 >> 32) <= near_bits) + (int)((uint32_t)(top.k1 >> 32) <= near_bits) +
                        (int)((uint32_t)(top.k2 >> 32) <= near_bits) + (int)((uint32_t)(top.k3 >> 32) <= near_bits) +
                        (int)((uint32_t)(top.k4 >> 32) <= near_bits);
-      const int seen = __reduce_add_sync(gmask, mine);
+      int seen = mine;
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, off);
       if (seen < LIO_K) nrounds = 1 + (ncell + G * CPL - 1) / (G * CPL);
     }
   }
+  mark(243);
+  // Global top-5 of the group: five rounds of a butterfly minimum over (key, slot).  xor offsets below G never leave
+  // the aligned group, so the shuffles use the FULL mask (the whole warp is here: no per-group masks, which cost a
+  // warp-level rendezvous each).  Keys are unique (ids are), so exactly one lane pops per round.
+  __syncwarp();
   int found = 0;
 #pragma unroll
   for (int r = 0; r < LIO_K; ++r) {
-    const uint32_t hi = (uint32_t)(top.k0 >> 32);
-    const uint32_t mhi = __reduce_min_sync(gmask, hi);
-    const uint32_t lo = (hi == mhi) ? (uint32_t)top.k0 : 0xffffffffu;
-    const uint32_t mlo = __reduce_min_sync(gmask, lo);
-    const bool win = (hi == mhi) && ((uint32_t)top.k0 == mlo) && (top.k0 != ~0ull);
-    const unsigned wmask = __ballot_sync(gmask, win) & gmask;
-    if (wmask == 0) {
-      out_key[r] = ~0ull;
-      out_slot[r] = 0;
-    } else {
-      const int wl = __ffs(wmask) - 1;
-      out_key[r] = ((unsigned long long)mhi << 32) | mlo;
-      out_slot[r] = __shfl_sync(gmask, top.s0, wl);
-      if ((int)(threadIdx.x & 31) == wl) top.pop();
+    unsigned long long k = top.k0;
+    uint32_t sl = top.s0;
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, off);
+      const uint32_t os = __shfl_xor_sync(0xffffffffu, sl, off);
+      if (ok < k) {
+        k = ok;
+        sl = os;
+      }
+    }
+    out_key[r] = k;
+    out_slot[r] = sl;
+    if (k != ~0ull) {
+      if (top.k0 == k) top.pop();
       ++found;
     }
   }
+  mark(244);
   return found;
 }
 

@@ -155,15 +155,18 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
   const int gl = lane & (G - 1);
   const unsigned gmask = group_mask<G>(lane);
   const int row = threadIdx.x / G;
-  const int i = tile * ROWS + row;
-  if (i >= M) return;  // group-uniform
+  const int i_raw = tile * ROWS + row;
+  const bool act = i_raw < M;  // group-uniform
+  const int i = act ? i_raw : M - 1;  // idle groups redo the last query: the whole warp stays together for the shuffles
   const float4 b = __ldg(a.body + i);
   const double pb[3] = {b.x, b.y, b.z};
   float pwx, pwy, pwz;
   body_to_world(pc, pb, pwx, pwy, pwz);
   unsigned long long key[LIO_K];
   uint32_t slot[LIO_K];
-  const int cnt = group_knn5<G>(a.map, pwx, pwy, pwz, a.max_d2, a.rings, gmask, gl, key, slot);
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[239] = global_ns();
+  const int cnt = group_knn5<G>(a.map, pwx, pwy, pwz, a.max_d2, a.rings, gmask, gl, key, slot, a.dbg);
+  if (!act) return;
   // lanes 0..4 of the group fetch and publish one neighbour each
   if (gl < LIO_K) {
     unsigned long long k = key[0];
@@ -191,6 +194,7 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
     s_cnt[row] = sel ? 1 : 0;
     a.near_cnt[i] = cnt;
   }
+  if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[245] = global_ns();
 }
 
 // Finish phase of one tile, one thread per point: steps 1.1-1.2 and 1.5-3 of h_share_model (esekfom.hpp:123-133,
@@ -957,11 +961,16 @@ __global__ void __launch_bounds__(256) knn_batch_kernel(MapView map, const float
   const unsigned gmask = group_mask<G>(lane);
   const int gglobal = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int ngroups = (gridDim.x * blockDim.x) / G;
-  for (int i = gglobal; i < m; i += ngroups) {
+  const int iters = (m + ngroups - 1) / ngroups;  // uniform trip count: the warp stays together for the shuffles
+  for (int it = 0; it < iters; ++it) {
+    const int i_raw = gglobal + it * ngroups;
+    const bool act = i_raw < m;
+    const int i = act ? i_raw : m - 1;
     const float4 p = __ldg(q + i);
     unsigned long long ok[LIO_K];
     uint32_t os[LIO_K];
     const int f = group_knn5<G>(map, p.x, p.y, p.z, max_d2, rings, gmask, gl, ok, os);
+    if (!act) continue;
     if (gl < LIO_K) {
       unsigned long long k = ok[0];
       uint32_t sl = os[0];

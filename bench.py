@@ -92,7 +92,7 @@ class ClockSampler:
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index, period_s=0.01):
+    def __init__(self, gpu_index, period_s=0.002):
         self.period = period_s
         self.sm, self.bits, self.power = [], [], []
         self.stop_flag = threading.Event()
@@ -297,7 +297,7 @@ def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
     line = {
         "metric": METRIC, "value": args.steps / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32 geometry / f64 filter", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": "sharded map: %d-point city map in %d x-slabs (+ sqrt(5)+0.5 m halo), OS1-128 %dx%d scans, "
                    "all-reduce of 92 doubles per pass" % (len(mp), world, args.rings, args.cols), "M": M,
                    "passes_per_scan": passes, "local_map_points": int(len(keep)),
@@ -332,7 +332,7 @@ def main():
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n_gpus,
             "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 filter", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4, 1 sequence per GPU" %
                        (args.rings, args.cols, args.map_points), "M": r["m"], "passes_per_scan": r["passes"]},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
@@ -535,7 +535,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_cold / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 geometry / f64 filter", "data": "synthetic",
+        "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4, 1 sequence per GPU" %
                    (args.rings, args.cols, n_map), "N_raw": int(np.mean([len(r) for r in raws])), "M": M,
                    "passes_per_scan": passes_per_scan, "l2": "flushed (384 MiB write) before every timed step",

@@ -54,6 +54,11 @@ def main():
         tl = ctx.debug_timeline()
         if rep == 2:
             show("single search pass (warm)", tl)
+            r = ctx.timeline_raw
+            names = ["search_tile entry .. body->world done", "probes resolved", "bucket list scanned", "(ring rounds)",
+                     "top-5 merged", "neighbours published"]
+            print("   query 0 of block 0: " + ", ".join("%s +%.2f us" % (nm, (r[240 + k] - r[239 + k]) / 1000.0)
+                                                         for k, nm in enumerate(names)))
         ctx.pass_only_enqueue(False, False)
         tl = ctx.debug_timeline()
         if rep == 2:
