@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--poses", type=int, default=4, help="distinct scan poses cycled through the steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--map-cell", type=float, default=0.0, help="kNN hash cell edge [m] (0: library default); no effect on results")
     return ap.parse_args()
 
 
@@ -362,8 +363,9 @@ def main():
 
     wl = make_workload(args, rank)
     n_map = len(wl["map"])
+    extra = {"map_cell": args.map_cell} if args.map_cell > 0 else {}
     ctx = _cabi.Context(local, max_scan_points=max(1 << 18, args.rings * args.cols), max_down_points=100000,
-                        max_map_points=max(1 << 21, int(n_map * 1.05)))
+                        max_map_points=max(1 << 21, int(n_map * 1.05)), **extra)
     stream = torch.cuda.Stream(dev)  # a real (non-legacy) stream: events, L2 flush and our kernels all run on it
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
