@@ -52,7 +52,7 @@ class Caps(C.Structure):
 EXPORTS = [
     "lio_abi_version", "lio_default_caps", "lio_create", "lio_destroy", "lio_set_stream", "lio_synchronize",
     "lio_last_error", "lio_launch_count", "lio_map_build", "lio_map_add", "lio_map_delete_boxes", "lio_map_size",
-    "lio_map_dump", "lio_knn5", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
+    "lio_map_dump", "lio_knn5", "lio_knn5_resident", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_update_scan_host", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_pass_only_enqueue", "lio_debug_timeline",
@@ -91,6 +91,7 @@ def load_library() -> C.CDLL:
         "lio_map_size": (C.c_int, [vp, P(i64), P(i64)]),
         "lio_map_dump": (C.c_int, [vp, vp, vp, i64, P(i64)]),
         "lio_knn5": (C.c_int, [vp, vp, i64, vp, vp, vp]),
+        "lio_knn5_resident": (C.c_int, [vp, i64]),
         "lio_scan_preprocess": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, f32, vp, P(i64), vp, vp]),
         "lio_scan_preprocess_resident": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, f32, P(i64)]),
         "lio_scan_upload": (C.c_int, [vp, vp, i64, C.c_int]),
@@ -247,6 +248,9 @@ class Context:
         nbr = np.zeros((m, 5, 3), np.float32) if want_xyz else None
         self._check(self._lib.lio_knn5(self._h, _ptr(q), m, _ptr(idx), _ptr(d2), _ptr(nbr)))
         return idx, d2, nbr
+
+    def knn5_resident(self, m: int):
+        self._check(self._lib.lio_knn5_resident(self._h, m))
 
     # -- scan
     def scan_preprocess(self, raw_pts, poses=None, end_state=None, leaf=0.5, want_undistorted=False, want_keys=False,

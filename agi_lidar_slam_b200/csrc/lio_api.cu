@@ -376,6 +376,15 @@ int lio_knn5(lio_ctx* c, const float* q_xyz, int64_t m, int32_t* idx5, float* d2
   return LIO_OK;
 }
 
+// Instrumentation: the batch kernel alone on the m queries the last lio_knn5 call left on the device (no copies, no
+// sync), so that a tool can bracket exactly that kernel with CUDA events.
+int lio_knn5_resident(lio_ctx* c, int64_t m) {
+  if (!c || m < 0 || m > c->caps.max_down_points) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (!c->map_built) return LIO_E_EMPTY_MAP;
+  return launch_knn_batch(c, c->d_world, m);
+}
+
 // ---------------------------------------------------------------- scan
 static int preprocess_common(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses,
                              int n_poses, const lio_state* end_state, float leaf) {

@@ -116,6 +116,10 @@ int lio_map_dump(lio_ctx* ctx, float* xyz, int32_t* ids, int64_t cap, int64_t* n
  * (d2 FP32, id): idx5 m x 5 point ids (-1 pad), d2_5 m x 5 (+inf pad), nbr_xyz m x 5 x 3. */
 int lio_knn5(lio_ctx* ctx, const float* q_xyz, int64_t m, int32_t* idx5, float* d2_5, float* nbr_xyz);
 
+/* Instrumentation: re-runs the search kernel on the (at most max_down_points) queries the last lio_knn5 call left on
+ * the device; no copies, no synchronisation (tools/knn_roofline.py brackets it with CUDA events). */
+int lio_knn5_resident(lio_ctx* ctx, int64_t m);
+
 /* ---- scan preprocessing: ImuProcess::UndistortPcl back half + pcl::VoxelGrid ------------------------ */
 /* ≙ IMU_Processing.hpp:361-401 followed by laserMapping.cpp:737-738 (leaf from :683), fused in one pass.
  * raw_pts: n records (time in w / curvature, ms).  imu_poses/n_poses = ImuProcess::IMUpose; end_state = state

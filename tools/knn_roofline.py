@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""kNN kernel against HBM: batched 5-NN (lio_knn5's kernel) on a map that does NOT fit L2.
+
+    python tools/knn_roofline.py [--map-points 50000000] [--queries 4000000] [--reps 5]
+
+BASELINE.json's north_star asks for the kNN kernel's achieved HBM bandwidth.  On the bench workload (2 M-point map =
+32 MB) the map is L2-resident and the update is latency-bound, so DRAM counters say nothing there; this
+tool builds the 50 M-point city map of config 5 (800 MB of points + 2 GB of hash table) and streams millions of
+queries through the same search code.  Prints queries/s and the candidate-streaming model of SURVEY.md §8d
+(bytes = queries x (16 + candidates x 16 + probes x 16)); run it under ncu for the measured dram__bytes."""
+import argparse
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from agi_lidar_slam_b200 import _cabi, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--map-points", type=int, default=50_000_000)
+    ap.add_argument("--queries", type=int, default=4_000_000)
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    import torch
+
+    t0 = time.time()
+    scene, mp = synth.city_map(a.map_points, 5005)
+    print(f"map: {len(mp)} points, extent {np.ptp(mp[:, 0]):.0f} x {np.ptp(mp[:, 1]):.0f} m, generated in {time.time() - t0:.1f} s",
+          flush=True)
+    rng = np.random.default_rng(1)
+    q = mp[rng.integers(0, len(mp), a.queries)] + rng.normal(0, 0.15, (a.queries, 3)).astype(np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    chunk = min(a.queries, 1_000_000)  # queries per launch (they go through the scan-sized buffers)
+    ctx = _cabi.Context(0, max_scan_points=1 << 16, max_down_points=chunk, max_map_points=int(len(mp) * 1.02))
+    t0 = time.time()
+    ctx.map_build(np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1))
+    ctx.synchronize()
+    print(f"map built on the device in {time.time() - t0:.2f} s (includes the host-to-device copy)", flush=True)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    # correctness spot check against brute force on a few queries
+    idx, d2, _ = ctx.knn5(q[:64])
+    for k in range(3):
+        d = ((mp - q[k]) ** 2)
+        dd = (d[:, 0] + d[:, 1]) + d[:, 2]
+        o = np.argsort(dd, kind="stable")[:5]
+        ok = dd[o] <= 5.0
+        assert np.array_equal(idx[k][ok], o[ok].astype(np.int32)), (idx[k], o)
+    found5 = float((idx[:, 4] >= 0).mean())
+    times = []
+    nq = (a.queries // chunk) * chunk
+    for off in range(0, nq, chunk):
+        ctx.knn5(q[off:off + chunk], want_xyz=False) if False else ctx._check(
+            ctx._lib.lio_knn5(ctx._h, q[off:off + chunk].ctypes.data, chunk, None, None, None))  # queries -> device
+        for rep in range(a.reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.knn5_resident(chunk)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            if rep:
+                times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    print(f"{chunk} queries per launch: {ms:.3f} ms -> {chunk / ms / 1e3:.1f} M queries/s; {found5:.2f} of the queries have 5 "
+          f"neighbours within sqrt(5) m")
+    print("algorithmic bytes (SURVEY.md 8d, 116 B per query): %.1f GB/s" % (116.0 * chunk / (ms * 1e-3) / 1e9))
+
+
+if __name__ == "__main__":
+    main()
