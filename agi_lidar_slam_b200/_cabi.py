@@ -55,7 +55,8 @@ EXPORTS = [
     "lio_map_dump", "lio_knn5", "lio_knn5_resident", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_update_scan_host", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
-    "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_pass_only_enqueue", "lio_debug_timeline",
+    "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_peer_handle", "lio_peer_connect",
+    "lio_update_enqueue_sharded", "lio_peer_status", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
     "lio_imu_proc_init", "lio_imu_set_param", "lio_imu_process",
 ]  # fmt: skip
@@ -108,6 +109,10 @@ def load_library() -> C.CDLL:
         "lio_blob_download": (C.c_int, [vp, vp]),
         "lio_blob_upload": (C.c_int, [vp, vp]),
         "lio_blob_bind": (C.c_int, [vp, vp]),
+        "lio_peer_handle": (C.c_int, [vp, vp]),
+        "lio_peer_connect": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "lio_update_enqueue_sharded": (C.c_int, [vp, f64, C.c_int, C.c_int, C.c_int, f32, f32]),
+        "lio_peer_status": (C.c_int, [vp, P(i32)]),
         "lio_pass_only_enqueue": (C.c_int, [vp, C.c_int, C.c_int]),
         "lio_debug_timeline": (C.c_int, [vp, vp]),
         "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
@@ -342,6 +347,25 @@ class Context:
 
     def blob_bind(self, device_ptr: int | None):
         self._check(self._lib.lio_blob_bind(self._h, C.c_void_p(device_ptr or 0)))
+
+    def peer_handle(self) -> np.ndarray:
+        h = np.zeros(64, np.uint8)
+        self._check(self._lib.lio_peer_handle(self._h, _ptr(h)))
+        return h
+
+    def peer_connect(self, rank: int, world: int, handles):
+        h = np.ascontiguousarray(handles, np.uint8).reshape(world, 64)
+        self._check(self._lib.lio_peer_connect(self._h, rank, world, _ptr(h)))
+
+    def update_enqueue_sharded(self, R=0.001, max_iter=4, extrinsic_est=False, from_snapshot=True, x_own_min=-np.inf,
+                               x_own_max=np.inf):
+        self._check(self._lib.lio_update_enqueue_sharded(self._h, R, max_iter, int(extrinsic_est), int(from_snapshot),
+                                                         x_own_min, x_own_max))
+
+    def peer_timed_out(self) -> bool:
+        v = C.c_int32(0)
+        self._check(self._lib.lio_peer_status(self._h, C.byref(v)))
+        return bool(v.value)
 
     def debug_timeline(self):
         """[(tag, ns)] of block 0 and of the solving block (needs LIO_TIMELINE=1 at context creation)."""

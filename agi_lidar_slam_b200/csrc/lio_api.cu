@@ -59,6 +59,11 @@ static int refresh_scan_m(lio_ctx* c) {
 
 using namespace lio;
 
+// peer mailbox of the sharded-map exchange: blobs [8 ranks][2 slots][LIO_BLOB] doubles, stamps [8][2] u32, error flag
+static const size_t MAILBOX_STAMPS = 8 * 2 * LIO_BLOB * sizeof(double);
+static const size_t MAILBOX_ERR = MAILBOX_STAMPS + 8 * 2 * sizeof(unsigned);
+static const size_t MAILBOX_BYTES = 12288;
+
 extern "C" {
 
 int lio_abi_version(void) { return LIO_ABI_VERSION; }
@@ -134,6 +139,8 @@ static int create_impl(lio_ctx* c) {
   c->d_blob = c->d_blob_own;
   ALLOC(c->d_prior, 8 * 288);
   ALLOC(c->d_pub, 8 * 40);
+  ALLOC(c->d_mailbox, MAILBOX_BYTES);
+  LIO_CHECK(c, cudaMemset(c->d_mailbox, 0, MAILBOX_BYTES));
   ALLOC(c->d_arrive, sizeof(unsigned) * 1024);
   LIO_CHECK(c, cudaMemset(c->d_arrive, 0, sizeof(unsigned) * 1024));
   {
@@ -230,12 +237,14 @@ void lio_destroy(lio_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int r = 0; r < 8; ++r)
+    if (c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
   void* ptrs[] = {c->map.table,   c->map.cell_cap,  c->map.cell_pend, c->map.cell_base, c->map.pool,
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
                   c->d_vox_best,  c->d_vox_key,     c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
                   c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,       c->d_add_b,
-                  c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,
+                  c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,      c->d_mailbox,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
@@ -604,6 +613,59 @@ int lio_update_scan_host(lio_ctx* c, const void* down_pts, int64_t m, int stride
   rc = launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, 1);
   if (rc) return rc;
   return lio_state_download(c, x_io, P_io, n_valid_last, n_passes);
+}
+
+// ---------------------------------------------------------------- sharded map over peer memory
+int lio_peer_handle(lio_ctx* c, unsigned char handle[64]) {
+  if (!c || !handle) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  LIO_CHECK(c, cudaIpcGetMemHandle(&h, c->d_mailbox));
+  memcpy(handle, &h, 64);
+  return LIO_OK;
+}
+
+int lio_peer_connect(lio_ctx* c, int rank, int world, const unsigned char* handles) {
+  if (!c || !handles || world < 2 || world > 8 || rank < 0 || rank >= world) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  for (int r = 0; r < world; ++r) {
+    void* base = c->d_mailbox;
+    if (r != rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + 64 * r, 64);
+      LIO_CHECK(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer_base[r] = base;
+    }
+    c->peer_mbox[r] = static_cast<double*>(base);
+    c->peer_stamp[r] = reinterpret_cast<unsigned*>(static_cast<char*>(base) + MAILBOX_STAMPS);
+  }
+  c->d_peer_err = reinterpret_cast<int*>(static_cast<char*>(c->d_mailbox) + MAILBOX_ERR);
+  c->peer_rank = rank;
+  c->peer_world = world;
+  c->peer_epoch = 0;
+  return LIO_OK;
+}
+
+int lio_update_enqueue_sharded(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot, float x_own_min,
+                               float x_own_max) {
+  if (!c || max_iter < 0 || max_iter > 32) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (!c->map_built) {
+    c->err = "update on an empty map";
+    return LIO_E_EMPTY_MAP;
+  }
+  return launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, from_snapshot ? 1 : 0, x_own_min, x_own_max, true);
+}
+
+int lio_peer_status(lio_ctx* c, int32_t* timed_out) {
+  if (!c || !timed_out) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  int v = 0;
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  LIO_CHECK(c, cudaMemcpy(&v, static_cast<char*>(c->d_mailbox) + MAILBOX_ERR, sizeof(int), cudaMemcpyDeviceToHost));
+  *timed_out = v;
+  return LIO_OK;
 }
 
 int lio_update_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot) {

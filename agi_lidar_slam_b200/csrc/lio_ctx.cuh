@@ -1,5 +1,7 @@
 // Context layout shared by the translation units of liblio_b200.so.
 #pragma once
+#include <math.h>
+
 #include <string>
 
 #include "lio_common.cuh"
@@ -48,6 +50,14 @@ struct lio_ctx {
   double* d_prior = nullptr;        // 288: P11^-1 and P21 P11^-1 of the current update
   unsigned* d_sync = nullptr;       // grid barrier words {arrivals, release}
   unsigned* d_arrive = nullptr;     // per-worker arrival stamps of update_kernel (1024 entries)
+  // sharded map: peer mailboxes (own one allocated here, the peers' mapped through cudaIpc)
+  void* d_mailbox = nullptr;        // {double blob[8][2][LIO_BLOB]; unsigned stamp[8][2]; int err}
+  int peer_world = 0, peer_rank = 0;
+  unsigned peer_epoch = 0;          // advanced by sharded launches only: stays in lockstep across the ranks
+  double* peer_mbox[8] = {nullptr};
+  unsigned* peer_stamp[8] = {nullptr};
+  void* peer_base[8] = {nullptr};   // cudaIpcOpenMemHandle results (closed in lio_destroy)
+  int* d_peer_err = nullptr;
   unsigned epoch = 0;               // stamp base of the next update_kernel launch
   double* d_pub = nullptr;          // 34 doubles published by the solving block after every Kalman step
   long long* d_dbg = nullptr;       // in-kernel timeline (only with LIO_TIMELINE=1)
@@ -101,7 +111,8 @@ namespace lio {
 // launchers implemented in lio_pass.cu / lio_map.cu / lio_preprocess.cu
 int ensure_tables(lio_ctx* c);
 int pass_grid_blocks(lio_ctx* c);
-int launch_update(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot);
+int launch_update(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot, float own_min = -INFINITY,
+                  float own_max = INFINITY, bool sharded = false);
 int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float own_max);
 int launch_solve(lio_ctx* c, double R, int extrinsic_est);
 int launch_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot);

@@ -834,13 +834,76 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nwo
   stamp(a.dbg, 0, 6);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Sharded map (SURVEY.md 8e case 2): the ranks' blobs are exchanged INSIDE the persistent kernel over NVLink peer
+// memory.  Every rank owns a mailbox {blob[world][2][LIO_BLOB], stamp[world][2]} that its peers have mapped
+// (cudaIpc); after its local reduction the solver block stores its 92 doubles into slot [rank][pass & 1] of every
+// rank's mailbox (plain peer stores), fences at system scope and stamps the slot; it then waits for the stamps of all
+// ranks in its own mailbox and adds the blobs in RANK ORDER, so that every rank forms the same bits and performs the
+// identical Kalman step.  Two slots suffice: a peer can only write pass p + 2 after it has received this rank's
+// pass p + 1 blob, which is sent after pass p has been read.  No NCCL call, no launch, no host on the path.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LIO_MAX_RANKS = 8;
+struct ShardArgs {
+  int world, rank;
+  double* mbox[LIO_MAX_RANKS];     // mailbox blobs of every rank as mapped in THIS process ([rank] = own)
+  unsigned* stamp[LIO_MAX_RANKS];  // mailbox stamps of every rank
+  int* err;                        // set to 1 when a peer did not show up in time
+  unsigned epoch;                  // stamp base of this sharded launch (advances in lockstep on all ranks)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __noinline__ void block_exchange(const ShardArgs& sh, unsigned target, int pass_no, double* s_blob) {
+  const int tid = threadIdx.x;
+  const int slot = pass_no & 1;
+  // 1. this rank's blob into everybody's mailbox (own included)
+#pragma unroll 1
+  for (int k = tid; k < sh.world * LIO_BLOB; k += THREADS) {
+    const int p = k / LIO_BLOB, e = k - p * LIO_BLOB;
+    sh.mbox[p][((size_t)sh.rank * 2 + slot) * LIO_BLOB + e] = s_blob[e];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < sh.world) st_release_sys(sh.stamp[tid] + sh.rank * 2 + slot, target);
+  // 2. wait for every rank's stamp in the own mailbox (bounded: a missing peer must not hang the GPU)
+  if (tid < sh.world) {
+    const unsigned* f = sh.stamp[sh.rank] + tid * 2 + slot;
+    long long spins = 0;
+    while ((ld_acquire_sys(f) - target) >= 0x40000000u) {
+      if (++spins > 400000000LL) {
+        *sh.err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // 3. sum in rank order
+  if (tid < LIO_BLOB) {
+    const volatile double* mine = sh.mbox[sh.rank];
+    double acc = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < sh.world; ++r) acc += mine[((size_t)r * 2 + slot) * LIO_BLOB + tid];
+    if (tid == 91) acc = s_blob[91];
+    s_blob[tid] = acc;
+  }
+  __syncthreads();
+}
+
 // The whole update_iterated_dyn_share_modified loop (esekfom.hpp:270-346).  Cooperative launch: all blocks resident.
 // Blocks 0 .. gridDim-2 are WORKERS (h_share_model passes); the last block is the SOLVER: it keeps the filter state in
 // shared memory for the whole update, sums the workers' partial blobs as they arrive, performs the Kalman step and
 // publishes the constants of the next pass.  Flags are epoch stamps (target = epoch + pass + 1), so nothing has to be
 // zeroed between launches.
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const PassArgs a, const SolveArgs s,
-                                                                            const unsigned epoch) {
+                                                                            const unsigned epoch, const ShardArgs sh) {
   __shared__ __align__(16) unsigned char smem_raw[sizeof(PassSmem) > sizeof(SolveSmem) ? sizeof(PassSmem)
                                                                                         : sizeof(SolveSmem)];
   const int tid = threadIdx.x;
@@ -855,6 +918,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(cons
       const unsigned target = epoch + (unsigned)pass_no + 1u;
       stamp(a.dbg, 128, 10);
       block_reduce_partials(a, search, nworkers, target, ss.blob, ss.warp_part);
+      if (sh.world > 1) block_exchange(sh, sh.epoch + (unsigned)pass_no + 1u, pass_no, ss.blob);
       stamp(a.dbg, 128, 11);
       block_solve(s, n, &ss);
       stamp(a.dbg, 128, 12);
@@ -1106,11 +1170,30 @@ static SolveArgs make_solve_args(lio_ctx* c, double R, int max_iter, int from_sn
   return s;
 }
 
-// The whole update as ONE cooperative launch (plus the 8-byte reset of the barrier words).
-int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot) {
+// The whole update as ONE cooperative launch.  own_min/own_max: ownership window of this rank (sharded map).
+int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot, float own_min, float own_max,
+                  bool sharded) {
   int rc = ensure_tables(c);
   if (rc) return rc;
-  PassArgs a = make_pass_args(c, ext, -INFINITY, INFINITY);
+  PassArgs a = make_pass_args(c, ext, own_min, own_max);
+  ShardArgs sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.world = 1;
+  if (sharded) {
+    if (c->peer_world < 2) {
+      c->err = "sharded update without connected peers (lio_peer_connect)";
+      return LIO_E_INVALID;
+    }
+    sh.world = c->peer_world;
+    sh.rank = c->peer_rank;
+    for (int r = 0; r < c->peer_world; ++r) {
+      sh.mbox[r] = c->peer_mbox[r];
+      sh.stamp[r] = c->peer_stamp[r];
+    }
+    sh.err = c->d_peer_err;
+    sh.epoch = c->peer_epoch;
+    c->peer_epoch += 40;
+  }
   SolveArgs s = make_solve_args(c, R, max_iter, from_snapshot);
   // arrival / release flags are epoch stamps: nothing to zero between launches (wrap-around once in ~10^8 updates)
   if (c->epoch > 0xF0000000u) {
@@ -1120,7 +1203,7 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   }
   unsigned epoch = c->epoch;
   c->epoch += 40;  // > max_iter + 2
-  void* args[] = {&a, &s, &epoch};
+  void* args[] = {&a, &s, &epoch, &sh};
   LIO_CHECK(c, cudaLaunchCooperativeKernel((const void*)update_kernel, dim3(pass_grid_blocks(c)), dim3(THREADS), args,
                                            0, c->stream));
   c->launches++;

@@ -76,3 +76,28 @@ def nccl_reduce(ctx, device):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
     return reduce, t
+
+
+def connect_peers(ctx, rank: int, world: int):
+    """One-time setup of the in-kernel exchange: all-gather the ranks' 64-byte mailbox handles (cudaIpc) and map them."""
+    import torch.distributed as dist
+
+    mine = ctx.peer_handle().tobytes()
+    allh = [None] * world
+    dist.all_gather_object(allh, mine)
+    ctx.peer_connect(rank, world, np.frombuffer(b"".join(allh), np.uint8))
+
+
+class PeerShardedUpdate:
+    """The sharded update as ONE persistent kernel per rank: the blobs travel through peer mailboxes over NVLink inside
+    the kernel (lio_update_enqueue_sharded); no NCCL call and no launch between the passes."""
+
+    def __init__(self, ctx, own):
+        self.ctx = ctx
+        self.own = (float(own[0]), float(own[1]))
+
+    def update(self, x, P, R=0.001, max_iter=4, extrinsic_est=False):
+        c = self.ctx
+        c.state_upload(x, P)
+        c.update_enqueue_sharded(R, max_iter, extrinsic_est, True, self.own[0], self.own[1])
+        return c.state_download()

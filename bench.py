@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--poses", type=int, default=4, help="distinct scan poses cycled through the steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="sharded workload: blob exchange inside the persistent kernel over NVLink peer memory (peer) "
+                         "or pass kernel -> NCCL all-reduce -> solve kernel per pass (nccl)")
     ap.add_argument("--map-cell", type=float, default=0.0, help="kNN hash cell edge [m] (0: library default); no effect on results")
     return ap.parse_args()
 
@@ -237,7 +240,11 @@ def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
         body, _, _ = ctx.scan_preprocess(s["scan"], None, None, wl["leaf"])
         bodies.append(np.ascontiguousarray(body))
     M = int(np.mean([len(b) for b in bodies]))
-    if world > 1:
+    fused = world > 1 and args.exchange == "peer"
+    if fused:
+        sharded.connect_peers(ctx, rank, world)
+        reduce = None
+    elif world > 1:
         reduce, blob_t = sharded.nccl_reduce(ctx, dev)
     else:
         reduce = lambda: None  # noqa: E731
@@ -253,11 +260,14 @@ def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            ctx.update_begin(wl["max_iter"], wl["ext"], True)
-            for _ in range(wl["max_iter"] + 1):
-                ctx.update_pass_enqueue(wl["ext"], own[0], own[1])
-                reduce()
-                ctx.update_step_enqueue(R_COV, wl["ext"])
+            if fused:
+                ctx.update_enqueue_sharded(R_COV, wl["max_iter"], wl["ext"], True, own[0], own[1])
+            else:
+                ctx.update_begin(wl["max_iter"], wl["ext"], True)
+                for _ in range(wl["max_iter"] + 1):
+                    ctx.update_pass_enqueue(wl["ext"], own[0], own[1])
+                    reduce()
+                    ctx.update_step_enqueue(R_COV, wl["ext"])
             e1.record(stream)
             x, P, nv, npz = ctx.state_download()
             if k >= warmup:
@@ -282,6 +292,8 @@ def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
     launches = ctx.launch_count - l0
     barrier()
     clocks = sampler.stop()
+    if fused and ctx.peer_timed_out():
+        raise SystemExit("peer exchange timed out")
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -300,11 +312,14 @@ def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": "sharded map: %d-point city map in %d x-slabs (+ sqrt(5)+0.5 m halo), OS1-128 %dx%d scans, "
-                   "all-reduce of 92 doubles per pass" % (len(mp), world, args.rings, args.cols), "M": M,
+                   "%s" % (len(mp), world, args.rings, args.cols,
+                           "blobs exchanged inside the persistent kernel over NVLink peer memory" if fused else
+                           "NCCL all-reduce of 92 doubles per pass between pass and solve kernels"), "M": M,
                    "passes_per_scan": passes, "local_map_points": int(len(keep)),
                    "l2": "flushed (384 MiB write) before every timed step", "states_identical_across_ranks": same},
         "matched_pts_per_s": nvalid / (ms / 1000.0), "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "pass_kernel + solve_kernel per pass (host-driven, all-reduce between)",
+        "roofline": {"bound": "hbm", "kernel": "update_kernel with in-kernel peer exchange" if fused else
+                     "pass_kernel + solve_kernel per pass (host-driven, all-reduce between)",
                      "achieved": alg / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (ms / args.steps * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
         "clocks": clocks,

@@ -167,6 +167,16 @@ int lio_update_enqueue(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, 
 int lio_update_begin(lio_ctx* ctx, int max_iter, int extrinsic_est, int from_snapshot);
 int lio_update_pass_enqueue(lio_ctx* ctx, int extrinsic_est, float x_own_min, float x_own_max);
 int lio_update_step_enqueue(lio_ctx* ctx, double R, int extrinsic_est);
+/* The same exchange INSIDE the persistent kernel, over NVLink peer memory instead of NCCL + launches: every rank's
+ * solver block stores its blob into a mailbox of every peer (mapped with cudaIpc), waits for the peers' stamps and adds
+ * the blobs in rank order; the whole sharded update is one launch per rank.  Setup once: lio_peer_handle on every rank,
+ * all-gather the 64-byte handles, lio_peer_connect.  All ranks must then enqueue the same sequence of sharded updates.
+ * lio_peer_status reports whether a peer failed to show up (the wait is bounded; the update is then garbage). */
+int lio_peer_handle(lio_ctx* ctx, unsigned char handle[64]);
+int lio_peer_connect(lio_ctx* ctx, int rank, int world, const unsigned char* handles /* world x 64 */);
+int lio_update_enqueue_sharded(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, int from_snapshot,
+                               float x_own_min, float x_own_max);
+int lio_peer_status(lio_ctx* ctx, int32_t* timed_out);
 /* Instrumentation: enqueue ONE h_share_model pass (search or cached) at the device-resident state with no Kalman
  * step behind it, so that bench.py can bracket exactly that kernel with CUDA events. */
 int lio_pass_only_enqueue(lio_ctx* ctx, int do_search, int extrinsic_est);

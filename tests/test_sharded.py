@@ -116,3 +116,21 @@ def test_two_shards_equal_unsharded_update(orc, small_cfg, ext):
     assert outs[0][2:] == ref[2:]  # matched-point count and pass count of the unsharded update
     assert np.abs(outs[0][0] - ref[0]).max() < 1e-9  # cross-rank sum order differs: 1e-9, not bitwise
     assert np.abs(outs[0][1] - ref[1]).max() < 1e-9 * np.abs(ref[1]).max()
+
+
+@pytest.mark.gpu
+def test_fused_peer_exchange_on_two_gpus():
+    """NCCL path and in-kernel NVLink mailbox path on real GPUs (skipped on a one-GPU box)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(_free_port()), str(root / "tests" / "mgpu_sharded_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
