@@ -13,8 +13,7 @@ a scan, its IMU samples, lidar_beg_time / lidar_end_time, as sync_packages (:218
     update_iterated_dyn_share_modified                                    (:772-774)    lio_update_scan
     map_incremental                                                       (:785)        lio_map_incremental
 
-lasermap_fov_segment (:309-365) is not replayed: with the launch files' cube_side_length = 1000 m the local-map box
-never moves inside the synthetic scenes.
+    lasermap_fov_segment: slide the local-map box, box-delete behind it  (:736, :309-365)  lio_map_delete_boxes
 """
 from __future__ import annotations
 
@@ -50,6 +49,17 @@ class ReplayConfig:
     acc_cov: float = 0.1
     b_gyr_cov: float = 0.0001
     b_acc_cov: float = 0.0001
+    cube_len: float = 1000.0  # cube_side_length (launch files)
+    det_range: float = 300.0  # DET_RANGE (laserMapping.cpp:39; mapping/det_range)
+
+MOV_THRESHOLD = 1.5  # laserMapping.cpp:40
+
+
+def _quat_to_mat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
 
 
 def default_state() -> np.ndarray:
@@ -74,7 +84,47 @@ class LioReplay:
         self.first_scan = True
         self.first_lidar_time = 0.0
         self.map_built = False
+        self.local_map = None  # LocalMap_Points: (2,3) float32 [vertex_min, vertex_max]
+        self.n_box_deleted = 0
         self.log = []  # per scan: dict(status, m, n_valid, n_passes, counts)
+
+    def _lasermap_fov_segment(self):
+        """laserMapping.cpp:309-365: keep the sensor MOV_THRESHOLD * DET_RANGE away from the faces of the local-map
+        cube; when it comes closer, shift the cube by mov_dist and delete the slab of map that falls out."""
+        c = self.cfg
+        R = _quat_to_mat(self.x[3:7])
+        pos_lid = self.x[0:3] + R @ self.x[11:14]  # pos + rot * offset_T_L_I (:728-729)
+        if self.local_map is None:
+            self.local_map = np.stack([pos_lid - c.cube_len / 2.0, pos_lid + c.cube_len / 2.0]).astype(np.float32)
+            return 0
+        lm = self.local_map
+        edge = np.float32(MOV_THRESHOLD * c.det_range)
+        d_min = np.abs(pos_lid - lm[0]).astype(np.float32)  # float dist_to_map_edge[3][2]
+        d_max = np.abs(pos_lid - lm[1]).astype(np.float32)
+        if not (np.any(d_min <= edge) or np.any(d_max <= edge)):
+            return 0
+        mov = np.float32(max((c.cube_len - 2.0 * MOV_THRESHOLD * c.det_range) * 0.5 * 0.9,
+                             float(np.float32(c.det_range) * np.float32(MOV_THRESHOLD - 1))))
+        new = lm.copy()
+        boxes = []
+        for i in range(3):
+            box = lm.copy()
+            if d_min[i] <= edge:
+                new[1, i] -= mov
+                new[0, i] -= mov
+                box[0, i] = lm[1, i] - mov
+                boxes.append(box.reshape(6))
+            elif d_max[i] <= edge:
+                new[1, i] += mov
+                new[0, i] += mov
+                box[1, i] = lm[0, i] + mov
+                boxes.append(box.reshape(6))
+        self.local_map = new
+        n = 0
+        if boxes and self.map_built:
+            n = self.ctx.map_delete_boxes(np.stack(boxes))
+        self.n_box_deleted += n
+        return n
 
     def process(self, meas: MeasureGroup):
         """Returns the state after this scan (the odometry the reference publishes), or None when the scan is skipped."""
@@ -93,6 +143,7 @@ class LioReplay:
             self.log.append(dict(status="imu-init"))
             return None
         ekf_inited = not ((meas.lidar_beg_time - self.first_lidar_time) < INIT_TIME)
+        self._lasermap_fov_segment()
         m = self.ctx.scan_preprocess(meas.lidar, poses, self.x, c.filter_size_surf, resident=True)
         if m < 5:
             self.log.append(dict(status="few-points", m=m))

@@ -8,7 +8,7 @@ MAX_INI_COUNT = 10
 
 class OracleReplay:
     def __init__(self, orc, filter_size_surf=0.5, filter_size_map=0.5, max_iteration=3, extrinsic_est=False, threads=8,
-                 use_ikd=False):
+                 use_ikd=False, cube_len=1000.0, det_range=300.0):
         self.orc = orc
         self.fs, self.fm, self.max_iter, self.ext, self.threads = filter_size_surf, filter_size_map, max_iteration, \
             extrinsic_est, threads
@@ -26,7 +26,47 @@ class OracleReplay:
         self.carry[19] = 0.0  # last_lidar_end_time_ (uninitialised in the reference; 0 here and in the product)
         self.map = None
         self.use_ikd = use_ikd
+        self.cube_len, self.det_range = cube_len, det_range
+        self.local_map = None
+        self.n_box_deleted = 0
         self.log = []
+
+    def fov_segment(self):
+        """lasermap_fov_segment (src/laserMapping.cpp:309-365), float arithmetic as declared there."""
+        f32 = np.float32
+        R = self.orc.quat_to_mat(self.x[3:7])
+        pos = self.x[0:3] + R @ self.x[11:14]
+        if self.local_map is None:
+            self.local_map = np.array([pos - self.cube_len / 2.0, pos + self.cube_len / 2.0]).astype(f32)
+            return
+        thr = f32(1.5 * self.det_range)
+        dist = np.zeros((3, 2), f32)
+        need = False
+        for i in range(3):
+            dist[i, 0] = abs(pos[i] - self.local_map[0, i])
+            dist[i, 1] = abs(pos[i] - self.local_map[1, i])
+            if dist[i, 0] <= thr or dist[i, 1] <= thr:
+                need = True
+        if not need:
+            return
+        mov = f32(max((self.cube_len - 2.0 * 1.5 * self.det_range) * 0.5 * 0.9, float(f32(self.det_range) * f32(0.5))))
+        new = self.local_map.copy()
+        rm = []
+        for i in range(3):
+            tmp = self.local_map.copy()
+            if dist[i, 0] <= thr:
+                new[1, i] -= mov
+                new[0, i] -= mov
+                tmp[0, i] = self.local_map[1, i] - mov
+                rm.append(tmp.reshape(6))
+            elif dist[i, 1] <= thr:
+                new[1, i] += mov
+                new[0, i] += mov
+                tmp[1, i] = self.local_map[0, i] + mov
+                rm.append(tmp.reshape(6))
+        self.local_map = new
+        if rm and self.map is not None:
+            self.n_box_deleted += self.map.delete_boxes(np.stack(rm))
 
     def process(self, meas):
         orc = self.orc
@@ -50,6 +90,7 @@ class OracleReplay:
         poses, self.x, self.P = orc.imu_forward(imu, meas["lidar_beg_time"], meas["lidar_end_time"], self.x, self.P,
                                                 self.carry)
         ekf_inited = not ((meas["lidar_beg_time"] - self.first_lidar_time) < INIT_TIME)
+        self.fov_segment()
         und, order = orc.undistort(meas["lidar"], poses, self.x)
         pts5 = np.concatenate([und[:, :3], np.zeros((len(und), 1), np.float32), und[:, 3:4]], 1)
         cen, _, _ = orc.voxel_grid(pts5, self.fs)

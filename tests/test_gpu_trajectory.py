@@ -22,11 +22,13 @@ def _p4(xyz):
     return np.concatenate([xyz, np.zeros((len(xyz), 1), np.float32)], 1)
 
 
-@pytest.mark.parametrize("name,n_scans,seed,rings,cols,fov,max_range", [
-    ("config 2 (VLP-16, 200 scans)", N_SCANS, 2002, 16, 1800, (-15.0, 15.0), 100.0),
-    ("config 4 shape (OS1-64, one of the 64 sequences, 40 scans)", 40, 4000, 64, 1024, (-22.5, 22.5), 120.0),
+@pytest.mark.parametrize("name,n_scans,seed,rings,cols,fov,max_range,cube_len,det_range", [
+    ("config 2 (VLP-16, 200 scans)", N_SCANS, 2002, 16, 1800, (-15.0, 15.0), 100.0, 1000.0, 300.0),
+    ("config 4 shape (OS1-64, one of the 64 sequences, 40 scans)", 40, 4000, 64, 1024, (-22.5, 22.5), 120.0, 1000.0, 300.0),
+    # a 40 m local-map cube: lasermap_fov_segment slides it and box-deletes the map behind the sensor
+    ("moving local map (VLP-16, 80 scans, cube 40 m)", 80, 2002, 16, 1800, (-15.0, 15.0), 100.0, 40.0, 10.0),
 ])
-def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_range):
+def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_range, cube_len, det_range):
     from agi_lidar_slam_b200 import _cabi, synth
     from agi_lidar_slam_b200.replay import LioReplay, MeasureGroup, ReplayConfig
     from replay_oracle import OracleReplay
@@ -36,8 +38,8 @@ def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_
     traj = synth.RampedTrajectory(synth.Trajectory())
     R0, p0 = traj.rot(0.0), traj.pos(0.0)
     with _cabi.Context(0, max_scan_points=1 << 17, max_down_points=1 << 16, max_map_points=1 << 21) as ctx:
-        gpu = LioReplay(ctx, ReplayConfig(max_iteration=3))
-        cpu = OracleReplay(orc, max_iteration=3)
+        gpu = LioReplay(ctx, ReplayConfig(max_iteration=3, cube_len=cube_len, det_range=det_range))
+        cpu = OracleReplay(orc, max_iteration=3, cube_len=cube_len, det_range=det_range)
         worst_pos, worst_rot, worst_P, n_upd, exact_scans, map_resync = 0.0, 0.0, 0.0, 0, 0, 0
         for m in seq:
             a = gpu.process(MeasureGroup(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"]))
@@ -70,9 +72,10 @@ def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_
     # nearly every scan; the rest differ by FP64 sin/cos library rounding behind an FP32 store
     assert exact_scans >= 0.95 * n_upd, (exact_scans, n_upd)
     assert map_resync <= 0.05 * N_SCANS
+    assert gpu.n_box_deleted == cpu.n_box_deleted and (cube_len > 100 or gpu.n_box_deleted > 0)
     # the odometry follows the motion (scan-to-map registration on a 16-ring sensor drifts; both sides agree on it)
     pr = R0.T @ (seq[-1]["truth_pos"] - p0)
     assert np.linalg.norm(b[0:3] - pr) < 0.25 * max(1.0, np.linalg.norm(pr))
     print(f"{name}: {n_upd} updates, worst |dpos| {worst_pos:.2e} m, worst |drot| {worst_rot:.2e} rad, worst rel |dP| "
           f"{worst_P:.2e}, bit-identical discrete outcomes in {exact_scans}/{n_upd} scans, map resyncs {map_resync}, "
-          f"map {map_valid} pts")
+          f"map {map_valid} pts, {gpu.n_box_deleted} points box-deleted")
