@@ -48,11 +48,20 @@ class Caps(C.Structure):
     ]
 
 
+class CloudLayout(C.Structure):
+    """lio_cloud_layout: where x/y/z/intensity/time sit in a PointCloud2 record + the handler's decimation / blind rule."""
+
+    _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
+                ("off_intensity", C.c_int32), ("off_time", C.c_int32), ("time_type", C.c_int32),
+                ("point_filter_num", C.c_int32), ("rule", C.c_int32), ("time_scale", C.c_float), ("blind", C.c_double)]
+
+
 # every symbol include/lio_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
     "lio_abi_version", "lio_default_caps", "lio_create", "lio_destroy", "lio_set_stream", "lio_synchronize",
     "lio_last_error", "lio_launch_count", "lio_map_build", "lio_map_add", "lio_map_delete_boxes", "lio_map_size",
-    "lio_map_dump", "lio_knn5", "lio_knn5_resident", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_upload",
+    "lio_map_dump", "lio_knn5", "lio_knn5_resident", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_preprocess_cloud2", "lio_scan_decoded",
+    "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_update_scan_host", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_peer_handle", "lio_peer_connect",
@@ -96,6 +105,8 @@ def load_library() -> C.CDLL:
         "lio_scan_preprocess": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, f32, vp, P(i64), vp, vp]),
         "lio_scan_preprocess_resident": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, f32, P(i64)]),
         "lio_scan_upload": (C.c_int, [vp, vp, i64, C.c_int]),
+        "lio_scan_preprocess_cloud2": (C.c_int, [vp, vp, i64, P(CloudLayout), vp, C.c_int, vp, f32, P(i64), P(i64)]),
+        "lio_scan_decoded": (C.c_int, [vp, vp, vp, i64, P(i64)]),
         "lio_update_pass": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, P(i32)]),
         "lio_update_scan": (C.c_int, [vp, vp, vp, f64, C.c_int, C.c_int, P(i32), P(i32)]),
         "lio_update_scan_host": (C.c_int, [vp, vp, i64, C.c_int, vp, vp, f64, C.c_int, C.c_int, P(i32), P(i32)]),
@@ -279,6 +290,27 @@ class Context:
         self._check(self._lib.lio_scan_preprocess(self._h, _ptr(raw), n, stride, _ptr(poses), n_poses, _ptr(end), leaf,
                                                   _ptr(out), C.byref(m), _ptr(und), _ptr(keys)))
         return out[: m.value].copy(), und, keys
+
+    def scan_preprocess_cloud2(self, data: np.ndarray, layout: CloudLayout, poses=None, end_state=None, leaf=0.5):
+        """data: (n, point_step) uint8 PointCloud2 records.  Returns (n_decoded, m)."""
+        data = np.ascontiguousarray(data, np.uint8)
+        if poses is not None:
+            poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, POSE_DOUBLES)
+            n_poses, end = poses.shape[0], _state(end_state)
+        else:
+            n_poses, end = 0, None
+        nd, m = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.lio_scan_preprocess_cloud2(self._h, _ptr(data), data.shape[0], C.byref(layout), _ptr(poses),
+                                                         n_poses, _ptr(end), leaf, C.byref(nd), C.byref(m)))
+        return nd.value, m.value
+
+    def scan_decoded(self):
+        n = C.c_int64(0)
+        self._check(self._lib.lio_scan_decoded(self._h, None, None, 0, C.byref(n)))
+        xyzt, inten = np.zeros((n.value, 4), np.float32), np.zeros(n.value, np.float32)
+        if n.value:
+            self._check(self._lib.lio_scan_decoded(self._h, _ptr(xyzt), _ptr(inten), n.value, C.byref(n)))
+        return xyzt, inten
 
     def scan_upload(self, down_pts):
         pts, stride = _points(down_pts)

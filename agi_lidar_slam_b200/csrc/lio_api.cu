@@ -245,6 +245,7 @@ void lio_destroy(lio_ctx* c) {
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
                   c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,       c->d_add_b,
                   c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,      c->d_mailbox,
+                  c->d_cloud,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
@@ -474,6 +475,60 @@ int lio_scan_preprocess_resident(lio_ctx* c, const void* raw_pts, int64_t n, int
   int rc = preprocess_common(c, raw_pts, n, stride, poses, n_poses, end_state, leaf);
   if (rc) return rc;
   if (m) return preprocess_status(c, m);
+  return LIO_OK;
+}
+
+int lio_scan_preprocess_cloud2(lio_ctx* c, const void* data, int64_t n, const lio_cloud_layout* L, const lio_pose6d* poses,
+                               int n_poses, const lio_state* end_state, float leaf, int64_t* n_decoded, int64_t* m) {
+  if (!c || n < 0 || (n > 0 && !data) || !L || !(leaf > 0.f)) return LIO_E_INVALID;
+  if (L->point_step < 12 || L->point_step > 256 || L->point_filter_num < 1 || (L->rule != 1 && L->rule != 2) ||
+      L->off_x < 0 || L->off_y < 0 || L->off_z < 0 || L->off_x + 4 > L->point_step || L->off_y + 4 > L->point_step ||
+      L->off_z + 4 > L->point_step || L->off_intensity + 4 > L->point_step ||
+      (L->off_time >= 0 && L->off_time + (L->time_type == 2 ? 8 : 4) > L->point_step) || L->time_type < 0 ||
+      L->time_type > 2)
+    return LIO_E_INVALID;
+  if (n_poses >= 2 && (!poses || !end_state)) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (n > c->caps.max_scan_points) {
+    c->err = "scan larger than lio_caps.max_scan_points";
+    return LIO_E_CAPACITY;
+  }
+  if (n_poses > 128) {
+    c->err = "more than 128 IMU poses";
+    return LIO_E_CAPACITY;
+  }
+  const size_t need = (size_t)c->caps.max_scan_points * (size_t)L->point_step;
+  if (need > c->cloud_bytes) {
+    if (c->d_cloud) LIO_CHECK(c, cudaFree(c->d_cloud));
+    c->d_cloud = nullptr;
+    c->cloud_bytes = 0;
+    LIO_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&c->d_cloud), need));
+    c->cloud_bytes = need;
+  }
+  if (n > 0) LIO_CHECK(c, cudaMemcpyAsync(c->d_cloud, data, (size_t)n * L->point_step, cudaMemcpyHostToDevice, c->stream));
+  int64_t nd = 0;
+  int rc = decode_cloud2(c, n, *L, &nd);
+  if (rc) return rc;
+  c->n_decoded = nd;
+  if (n_decoded) *n_decoded = nd;
+  if (n_poses >= 2)
+    LIO_CHECK(c, cudaMemcpyAsync(c->d_poses, poses, sizeof(lio_pose6d) * n_poses, cudaMemcpyHostToDevice, c->stream));
+  rc = preprocess(c, nd, n_poses >= 2 ? n_poses : 0, end_state, leaf, true);
+  if (rc) return rc;
+  return preprocess_status(c, m);
+}
+
+int lio_scan_decoded(lio_ctx* c, float* xyzt, float* intensity, int64_t cap, int64_t* n) {
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (n) *n = c->n_decoded;
+  const int64_t k = std::min<int64_t>(cap, c->n_decoded);
+  // preprocess() reuses d_raw as the sorted-point buffer, so the decoded order is read back from the undistorted
+  // cloud (input order; identical to the decoded cloud when no poses were given) and the intensity buffer
+  if (xyzt && k > 0) LIO_CHECK(c, cudaMemcpyAsync(xyzt, c->d_undist, 16 * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  if (intensity && k > 0)
+    LIO_CHECK(c, cudaMemcpyAsync(intensity, c->d_raw_aux, 4 * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
   return LIO_OK;
 }
 

@@ -79,6 +79,9 @@ struct lio_ctx {
   cudaEvent_t upload_done = nullptr;  // guards reuse of the upload staging area
 
   // ---- preprocess
+  unsigned char* d_cloud = nullptr; // PointCloud2 bytes of the scan being decoded (allocated on first use)
+  size_t cloud_bytes = 0;
+  int64_t n_decoded = 0;
   float4* d_raw = nullptr;          // N raw points (x,y,z,t_ms)
   float* d_raw_aux = nullptr;       // N intensity (stride-48 input)
   float4* d_undist = nullptr;       // N undistorted
@@ -127,4 +130,5 @@ int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, i
 int map_build_scan(lio_ctx* c, const lio_state* x);
 
 int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux);
+int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, int64_t* n_out);
 }  // namespace lio

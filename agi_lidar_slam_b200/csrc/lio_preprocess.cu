@@ -266,6 +266,80 @@ __global__ void __launch_bounds__(128) centroid_kernel(const float4* sorted_pts,
   if (body_time) body_time[m] = st / cnt;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// PointCloud2 decoding (src/preprocess.cpp, oust64_handler :243-268 / velodyne_handler :380-428 with point times)
+// ---------------------------------------------------------------------------------------------------------
+struct DecodeKeep {
+  const unsigned char* data;
+  lio_cloud_layout L;
+  __device__ __forceinline__ bool operator()(const int& i) const {
+    if (i % L.point_filter_num != 0) return false;
+    const unsigned char* r = data + (size_t)i * L.point_step;
+    float x, y, z;
+    memcpy(&x, r + L.off_x, 4);
+    memcpy(&y, r + L.off_y, 4);
+    memcpy(&z, r + L.off_z, 4);
+    // float products and sums (float * float stays float in C++), then compared in double with the double `blind`
+    const double range = (double)__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    const double b2 = __dmul_rn(L.blind, L.blind);
+    if (L.rule == 1) return !(range < b2);  // oust64_handler: `if (range < (blind * blind)) continue;`
+    return range > b2;                      // velodyne_handler: `if (x*x + y*y + z*z > (blind * blind)) push_back`
+  }
+};
+
+__global__ void decode_gather_kernel(const unsigned char* data, lio_cloud_layout L, const int* kept, const int* n_kept,
+                                     float4* raw, float* aux) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *n_kept) return;
+  const unsigned char* r = data + (size_t)kept[j] * L.point_step;
+  float x, y, z, inten = 0.f, t_ms = 0.f;
+  memcpy(&x, r + L.off_x, 4);
+  memcpy(&y, r + L.off_y, 4);
+  memcpy(&z, r + L.off_z, 4);
+  if (L.off_intensity >= 0) memcpy(&inten, r + L.off_intensity, 4);
+  if (L.off_time >= 0) {
+    if (L.time_type == 0) {
+      float t;
+      memcpy(&t, r + L.off_time, 4);
+      t_ms = __fmul_rn(t, L.time_scale);  // time * time_unit_scale (float * float)
+    } else if (L.time_type == 1) {
+      uint32_t t;
+      memcpy(&t, r + L.off_time, 4);
+      t_ms = __fmul_rn((float)t, L.time_scale);  // uint32 t * float time_unit_scale -> float
+    } else {
+      double t;
+      memcpy(&t, r + L.off_time, 8);
+      t_ms = (float)__dmul_rn(t, (double)L.time_scale);
+    }
+  }
+  raw[j] = make_float4(x, y, z, t_ms);
+  aux[j] = inten;
+}
+
+// data already in c->d_cloud; leaves the decoded cloud in c->d_raw / c->d_raw_aux and its size in *n_out (host sync)
+int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, int64_t* n_out) {
+  int* kept = reinterpret_cast<int*>(c->d_sort_vals_in);
+  int* n_kept = c->d_prep_counters + 12;
+  *n_out = 0;
+  if (n <= 0) {
+    LIO_CHECK(c, cudaMemsetAsync(n_kept, 0, sizeof(int), c->stream));
+    return LIO_OK;
+  }
+  size_t bytes = c->cub_tmp_bytes;
+  cub::CountingInputIterator<int> it(0);
+  DecodeKeep keep{c->d_cloud, L};
+  LIO_CHECK(c, cub::DeviceSelect::If(c->d_cub_tmp, bytes, it, kept, n_kept, (int)n, keep, c->stream));
+  decode_gather_kernel<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(c->d_cloud, L, kept, n_kept, c->d_raw,
+                                                                      c->d_raw_aux);
+  c->launches += 3;
+  LIO_CHECK(c, cudaGetLastError());
+  int h = 0;
+  LIO_CHECK(c, cudaMemcpyAsync(&h, n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  *n_out = h;
+  return LIO_OK;
+}
+
 size_t preprocess_sort_bytes(int64_t n) {
   size_t a = 0, b = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,

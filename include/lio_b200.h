@@ -137,6 +137,31 @@ int lio_scan_preprocess_resident(lio_ctx* ctx, const void* raw_pts, int64_t n, i
 /* Sets the current scan (feats_down_body, laserMapping.cpp:738) from host memory: m records. */
 int lio_scan_upload(lio_ctx* ctx, const void* down_pts, int64_t m, int stride_bytes);
 
+/* ---- sensor decoding (next row of SURVEY.md §8f): sensor_msgs::PointCloud2 bytes -> the path's input cloud ------ */
+/* Where the fields of one point record sit in a PointCloud2 `data` blob, and the decimation / blind-zone rule of the
+ * handler that would have read it (src/preprocess.cpp, feature extraction off as in every launch file). */
+typedef struct lio_cloud_layout {
+  int32_t point_step;       /* bytes per point record                                                  */
+  int32_t off_x, off_y, off_z;        /* float32 fields                                                */
+  int32_t off_intensity;    /* float32, or -1                                                          */
+  int32_t off_time;         /* per-point time field, or -1 (all points at t = 0)                       */
+  int32_t time_type;        /* 0 = float32 (velodyne_ros::Point::time), 1 = uint32 (ouster_ros::Point::t), 2 = float64 */
+  int32_t point_filter_num; /* keep every point_filter_num-th record (i % n == 0)                      */
+  int32_t rule;             /* 1 = oust64_handler (:243-268): drop when range^2 < blind^2;
+                               2 = velodyne_handler with point times (:380-428): keep when range^2 > blind^2
+                               (range^2 = FP32 x*x + y*y + z*z, compared in FP64 with the double blind) */
+  float time_scale;         /* time_unit_scale: field units -> ms (preprocess.cpp:55-66)               */
+  double blind;             /* blind radius [m] (preprocess.h:161)                                     */
+} lio_cloud_layout;
+/* ≙ Preprocess::process (preprocess.cpp:48-86) for a PointCloud2 lidar followed by lio_scan_preprocess_resident: the
+ * raw message bytes go up once, are decoded, decimated and blind-filtered on the device (order preserved) and run
+ * through undistortion + voxel filter.  *n_decoded = points that survived decoding, *m = feats_down_size. */
+int lio_scan_preprocess_cloud2(lio_ctx* ctx, const void* data, int64_t n_records, const lio_cloud_layout* layout,
+                               const lio_pose6d* imu_poses, int n_poses, const lio_state* end_state, float leaf,
+                               int64_t* n_decoded, int64_t* m);
+/* The decoded cloud of the last lio_scan_preprocess_cloud2 call: n x {x,y,z,t_ms} and n intensities (either may be NULL). */
+int lio_scan_decoded(lio_ctx* ctx, float* xyzt, float* intensity, int64_t cap, int64_t* n);
+
 /* ---- IESKF update: esekfom::esekf surface (include/esekfom.hpp) --------------------------------------- */
 /* ≙ one esekf::h_share_model call (esekfom.hpp:106-227) + the H^T H / H^T h products of :306-319 for the
  * current scan at state x.  do_search ≙ dyn_share.converge.  blob90 = upper triangle of H^T H (12x12, row-major,

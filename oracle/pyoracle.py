@@ -457,3 +457,33 @@ def map_incremental_classify(world, near_raw, near_cnt, ekf_inited=True, filter_
     cls = np.zeros(w.shape[0], np.uint8)
     lib().orc_map_incremental_classify(_p(w), w.shape[0], _p(nr), _p(nc), int(ekf_inited), filter_size_map, _p(cls))
     return cls
+
+
+# --------------------------------------------------------------------------- sensor decoding (src/preprocess.cpp)
+def decode_cloud2(data, point_step, off_x, off_y, off_z, off_intensity, off_time, time_dtype, time_scale, blind,
+                  point_filter_num, rule):
+    """oust64_handler (preprocess.cpp:243-268, rule 1) / velodyne_handler with point times (:380-428, rule 2), feature
+    extraction off: every point_filter_num-th record, blind-zone test on the FP32 squared range compared in FP64 with
+    the double `blind`, curvature = time field * time_unit_scale in FP32.  data: (n, point_step) uint8.
+    Returns (xyzt (k,4) float32, intensity (k,) float32)."""
+    data = np.ascontiguousarray(data, np.uint8).reshape(-1, point_step)
+    n = data.shape[0]
+
+    def field(off, dt):
+        w = np.dtype(dt).itemsize
+        return np.ascontiguousarray(data[:, off:off + w]).view(dt)[:, 0]
+
+    x, y, z = field(off_x, "<f4"), field(off_y, "<f4"), field(off_z, "<f4")
+    inten = field(off_intensity, "<f4") if off_intensity >= 0 else np.zeros(n, np.float32)
+    if off_time >= 0:
+        t = field(off_time, time_dtype)
+        if np.dtype(time_dtype) == np.dtype("<f8"):
+            tms = (t * np.float64(np.float32(time_scale))).astype(np.float32)
+        else:
+            tms = (t.astype(np.float32) * np.float32(time_scale)).astype(np.float32)
+    else:
+        tms = np.zeros(n, np.float32)
+    rng = ((x * x + y * y) + z * z).astype(np.float32).astype(np.float64)
+    b2 = np.float64(blind) * np.float64(blind)
+    keep = (np.arange(n) % point_filter_num == 0) & (~(rng < b2) if rule == 1 else (rng > b2))
+    return np.stack([x, y, z, tms], 1)[keep].astype(np.float32), inten[keep].astype(np.float32)
