@@ -49,12 +49,6 @@ def ctx():
     c.close()
 
 
-def canon(idx, d2):
-    """Neighbour lists are already canonical on both sides; helper kept for the ikd-Tree (traversal-order ties)."""
-    key = np.lexsort((idx, d2), axis=-1) if False else None
-    return key
-
-
 def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
