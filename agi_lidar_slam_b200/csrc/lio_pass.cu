@@ -326,10 +326,16 @@ __device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout,
 #pragma unroll 1
   for (int base = warp; base < nb; base += NW * CH) {
     if (target != 0) {
-      const int b = base + NW * lane;
+      // the lanes poll the arrival stamps of the chunk's workers in parallel (two stamps per lane when CH > 32)
       bool ready;
       do {
-        ready = (lane >= CH || b >= nb) ? true : (ld_acquire(a.arrive + b) - target) < 0x40000000u;
+        ready = true;
+#pragma unroll
+        for (int u = 0; u < (CH + 31) / 32; ++u) {
+          const int j = lane + 32 * u;
+          const int b = base + NW * j;
+          if (j < CH && b < nb) ready = ready && (ld_acquire(a.arrive + b) - target) < 0x40000000u;
+        }
       } while (!__all_sync(0xffffffffu, ready));
     }
     double v[CH][KPL];
@@ -361,7 +367,7 @@ __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool searc
   if (a.extrinsic_est)
     reduce_rows<3, 10>(a, nb, nout, target, s_warp);
   else
-    reduce_rows<1, 32>(a, nb, nout, target, s_warp);
+    reduce_rows<1, 40>(a, nb, nout, target, s_warp);  // 8 warps x 40 rows: every worker of a 296-block grid in one chunk
   __syncthreads();
   if (tid < LIO_BLOB) {
     double sum = 0.0;
