@@ -144,6 +144,11 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_arrive, sizeof(unsigned) * 1024);
   LIO_CHECK(c, cudaMemset(c->d_arrive, 0, sizeof(unsigned) * 1024));
   {
+    // LIO_ZERO_COPY=1: pass 0 reads a pinned scan in place over PCIe instead of a copy first (measured equal on B200)
+    const char* env = getenv("LIO_ZERO_COPY");
+    c->no_zero_copy = !(env && atoi(env));
+  }
+  {
     const char* env = getenv("LIO_TIMELINE");
     if (env && atoi(env)) {
       ALLOC(c->d_dbg, 256 * sizeof(long long));
@@ -178,6 +183,9 @@ static int create_impl(lio_ctx* c) {
   c->h_pinned_bytes = 8 * (1280 + LIO_BLOB + 4);
   LIO_CHECK(c, cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
   LIO_CHECK(c, cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
+  LIO_CHECK(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_out), 8 * 616, cudaHostAllocMapped));
+  memset(c->h_out, 0, 8 * 616);
+  LIO_CHECK(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->h_out_dev), c->h_out, 0));
 
   // preprocess
   const size_t N = (size_t)k.max_scan_points;
@@ -253,6 +261,7 @@ void lio_destroy(lio_ctx* c) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->h_out) cudaFreeHost(c->h_out);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->upload_done) cudaEventDestroy(c->upload_done);
   delete c;
@@ -638,7 +647,10 @@ int lio_update_scan(lio_ctx* c, lio_state* x_io, double P_io[576], double R, int
   return lio_state_download(c, x_io, P_io, n_valid_last, n_passes);
 }
 
-// The call a host makes per scan when the downsampled cloud is in host memory: 2 copies up, 1 kernel, 1 copy down.
+// The call a host makes per scan when the downsampled cloud is in host memory.  Host-direct: the prior rides in the
+// kernel parameters, the posterior comes back through mapped pinned memory (the host spins on a sequence word instead
+// of paying a copy + stream synchronisation).  With LIO_ZERO_COPY=1 a cloud in PINNED memory (cudaHostAlloc / torch
+// pin_memory) is read in place over PCIe by pass 0 instead of being copied first (no gain measured: off by default).
 int lio_update_scan_host(lio_ctx* c, const void* down_pts, int64_t m, int stride, lio_state* x_io, double P_io[576],
                          double R, int max_iter, int extrinsic_est, int32_t* n_valid_last, int32_t* n_passes) {
   if (!c || !x_io || !P_io || m < 0 || (m > 0 && !down_pts) || stride != 16 || max_iter < 0 || max_iter > 32)
@@ -652,22 +664,48 @@ int lio_update_scan_host(lio_ctx* c, const void* down_pts, int64_t m, int stride
     c->err = "scan larger than lio_caps.max_down_points";
     return LIO_E_CAPACITY;
   }
-  if (m > 0) LIO_CHECK(c, cudaMemcpyAsync(c->d_body, down_pts, 16 * (size_t)m, cudaMemcpyHostToDevice, c->stream));
-  double* up = nullptr;
-  int rc = upload_area(c, &up);
-  if (rc) return rc;
-  memcpy(up, x_io, sizeof(lio_state));
-  memcpy(up + 26, P_io, 8 * 576);
-  up[602] = 0.0;
-  up[603] = 0.0;  // barrier words
-  const int mi = (int)m;
-  memcpy(up + 602, &mi, sizeof(int));
-  LIO_CHECK(c, cudaMemcpyAsync(c->d_x0, up, 8 * 604, cudaMemcpyHostToDevice, c->stream));
-  LIO_CHECK(c, cudaEventRecord(c->upload_done, c->stream));
+  HostDirect hd;
+  hd.x0 = reinterpret_cast<const double*>(x_io);
+  hd.P0 = P_io;
+  hd.m = (int)m;
+  hd.body_src = nullptr;
+  if (m > 0) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, down_pts) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        attr.devicePointer != nullptr && !c->no_zero_copy) {
+      hd.body_src = static_cast<const float4*>(attr.devicePointer);
+    } else {
+      cudaGetLastError();  // pageable memory: not an error, just a copy
+      LIO_CHECK(c, cudaMemcpyAsync(c->d_body, down_pts, 16 * (size_t)m, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  unsigned long long* flag = reinterpret_cast<unsigned long long*>(c->h_out + 608);
+  hd.out_dev = c->h_out_dev;
+  hd.flag_dev = reinterpret_cast<unsigned long long*>(c->h_out_dev + 608);
+  hd.seq = ++c->host_seq;
   c->scan_m = m;
-  rc = launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, 1);
+  int rc = launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, 1, -INFINITY, INFINITY, false, &hd);
   if (rc) return rc;
-  return lio_state_download(c, x_io, P_io, n_valid_last, n_passes);
+  // spin on the sequence word; look at the stream now and then so that a failed launch cannot hang the caller
+  volatile unsigned long long* vf = flag;
+  for (unsigned long long spins = 0; *vf != hd.seq; ++spins) {
+    if ((spins & 0x3fff) == 0x3fff) {
+      const cudaError_t q = cudaStreamQuery(c->stream);
+      if (q != cudaErrorNotReady) {
+        if (q != cudaSuccess) LIO_CHECK(c, q);
+        if (*vf != hd.seq) {  // kernel finished without reporting: cannot happen with a healthy launch
+          c->err = "update kernel finished without writing the posterior";
+          return LIO_E_CUDA;
+        }
+      }
+    }
+  }
+  const Ctrl* hc = reinterpret_cast<const Ctrl*>(c->h_out + 602);
+  memcpy(x_io, c->h_out, sizeof(lio_state));
+  memcpy(P_io, c->h_out + 26, 8 * 576);
+  if (n_valid_last) *n_valid_last = hc->n_valid_last;
+  if (n_passes) *n_passes = hc->n_passes;
+  return LIO_OK;
 }
 
 // ---------------------------------------------------------------- sharded map over peer memory

@@ -77,6 +77,10 @@ struct lio_ctx {
   void* h_pinned = nullptr;         // pinned staging: [0,606) download area, [640, 1242) upload area, [1280, ..) blob
   size_t h_pinned_bytes = 0;
   cudaEvent_t upload_done = nullptr;  // guards reuse of the upload staging area
+  double* h_out = nullptr;            // mapped pinned: posterior {x, P, ctrl} + sequence word (host-direct path)
+  double* h_out_dev = nullptr;        // its device address
+  unsigned long long host_seq = 0;
+  bool no_zero_copy = true;
 
   // ---- preprocess
   unsigned char* d_cloud = nullptr; // PointCloud2 bytes of the scan being decoded (allocated on first use)
@@ -111,11 +115,21 @@ struct lio_ctx {
   } while (0)
 
 namespace lio {
+// what lio_update_scan_host hands to the launcher (host-direct path: no copies around the kernel)
+struct HostDirect {
+  const double* x0;              // prior, host memory
+  const double* P0;
+  int m;                         // scan size
+  const float4* body_src;        // device-accessible address of the caller's pinned scan, or nullptr (scan already in d_body)
+  double* out_dev;               // device address of the mapped pinned result buffer
+  unsigned long long* flag_dev;  // ... of its sequence word
+  unsigned long long seq;
+};
 // launchers implemented in lio_pass.cu / lio_map.cu / lio_preprocess.cu
 int ensure_tables(lio_ctx* c);
 int pass_grid_blocks(lio_ctx* c);
 int launch_update(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot, float own_min = -INFINITY,
-                  float own_max = INFINITY, bool sharded = false);
+                  float own_max = INFINITY, bool sharded = false, const HostDirect* hd = nullptr);
 int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float own_max);
 int launch_solve(lio_ctx* c, double R, int extrinsic_est);
 int launch_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot);

@@ -44,6 +44,8 @@ __constant__ unsigned char c_is_no[78];  // 1 where the HtH entry is one of the 
 struct PassArgs {
   const float4* body;
   const int* scan_m;
+  int m_value;             // >= 0: the scan size by value (host-direct path), else *scan_m
+  const float4* body_src;  // non-null: pass 0 reads the scan from here (pinned host memory) and leaves a copy in `body`
   MapView map;
   float4* near_pts;
   float* near_d2;
@@ -149,7 +151,7 @@ constexpr int SROWS_MAX = THREADS / 8;  // rows of a search tile at the smallest
 // the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.
 template <int G>
 __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int M, int tile, float4* s_nb,
-                                         int* s_cnt) {
+                                         int* s_cnt, float4* s_body, const float4* body) {
   constexpr int ROWS = THREADS / G;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
@@ -158,7 +160,8 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
   const int i_raw = tile * ROWS + row;
   const bool act = i_raw < M;  // group-uniform
   const int i = act ? i_raw : M - 1;  // idle groups redo the last query: the whole warp stays together for the shuffles
-  const float4 b = __ldg(a.body + i);
+  const float4 b = body[i];  // device copy, or the caller's pinned host buffer in pass 0 of the host-direct path
+  if (gl == 0) s_body[row] = b;
   const double pb[3] = {b.x, b.y, b.z};
   float pwx, pwy, pwz;
   body_to_world(pc, pb, pwx, pwy, pwz);
@@ -201,7 +204,7 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
 // 153-226) from the point's 5 neighbours (just found: shared memory; cached: a.near_pts with the sticky mask).
 __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int M, int tile, int rows, bool search,
                                          const float4* s_nb, const int* s_cnt, double* s_rows,
-                                         unsigned char* s_valid) {
+                                         unsigned char* s_valid, const float4* s_body, bool copy_body) {
   const int row = threadIdx.x;
   if (row >= rows) return;
   const int i = tile * rows + row;
@@ -209,7 +212,8 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
     s_valid[row] = 0;
     return;
   }
-  const float4 b = __ldg(a.body + i);
+  const float4 b = search ? s_body[row] : __ldcg(a.body + i);  // the search phase left it in shared memory
+  if (copy_body) const_cast<float4*>(a.body)[i] = b;            // host-direct path, pass 0: keep a device copy
   const double pb[3] = {b.x, b.y, b.z};
   float pwx, pwy, pwz;
   body_to_world(pc, pb, pwx, pwy, pwz);
@@ -294,7 +298,7 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
 // memory, products accumulated by thread (output o, segment seg) over rows seg, seg + nseg, ... of every tile, then
 // the segments are combined in order and the block's partial blob is written to a.partials[blockIdx.x].
 struct PassSmem;
-__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid);
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid, bool first_pass);
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -358,7 +362,7 @@ __device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout,
 __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool search, int nworkers, unsigned target,
                                                    double* s_blob, double* s_warp) {
   const int tid = threadIdx.x;
-  const int M = *a.scan_m;
+  const int M = a.m_value >= 0 ? a.m_value : *a.scan_m;
   const int G = pick_group(M, nworkers);
   const int rows = search ? THREADS / G : pick_rows_cached(M, nworkers);
   const int ntiles = tiles_of(M, rows);
@@ -491,15 +495,14 @@ struct SolveSmem {
 };
 
 // Once per update: restore the prior (from_snapshot), x_propagated = x, loop state, P11^-1 and P21 P11^-1.
-__device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* sm) {
+__device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* sm, const double* xsrc, const double* Psrc,
+                                         bool restore) {
   const int tid = threadIdx.x;
-  const double* Psrc = s.from_snapshot ? s.P0 : s.P;
-  const double* xsrc = reinterpret_cast<const double*>(s.from_snapshot ? s.x0 : s.x);
 #pragma unroll 1
   for (int k = tid; k < 576; k += THREADS) sm->P[k] = Psrc[k];
   if (tid < 26) sm->xa[tid] = xsrc[tid];
   __syncthreads();
-  if (s.from_snapshot) {
+  if (restore) {
     if (tid < 26) reinterpret_cast<double*>(s.x)[tid] = sm->xa[tid];
 #pragma unroll 1
     for (int k = tid; k < 576; k += THREADS) s.P[k] = sm->P[k];
@@ -747,13 +750,27 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
       sm->KH[k] = acc * inv_R;
     }
     __syncthreads();
+    double pnew[(576 + THREADS - 1) / THREADS];
+#pragma unroll
+    for (int u = 0; u < (576 + THREADS - 1) / THREADS; ++u) {
+      const int k = tid + u * THREADS;
+      pnew[u] = 0.0;
+      if (k < 576) {
+        const int r = k / 24, c = k % 24;
+        double acc = sm->P[k];
 #pragma unroll 1
-    for (int k = tid; k < 576; k += THREADS) {
-      const int r = k / 24, c = k % 24;
-      double acc = sm->P[k];
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) acc = fma(-sm->KH[r * n + j], sm->P[j * 24 + c], acc);
-      s.P[k] = acc;
+        for (int j = 0; j < n; ++j) acc = fma(-sm->KH[r * n + j], sm->P[j * 24 + c], acc);
+        pnew[u] = acc;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < (576 + THREADS - 1) / THREADS; ++u) {
+      const int k = tid + u * THREADS;
+      if (k < 576) {
+        s.P[k] = pnew[u];
+        sm->P[k] = pnew[u];  // the shared copy stays current (host-direct path reads the posterior from it)
+      }
     }
   }
   __syncthreads();
@@ -783,15 +800,18 @@ struct __align__(16) PassSmem {
   float4 nb[SROWS_MAX * LIO_K];  // neighbours found by the search phase of the current tile
   PassConst pc;
   int cnt[SROWS_MAX];            // gate 1 of the search phase
+  float4 body_row[SROWS_MAX];    // the search tile's scan points, for its finish phase
   unsigned char valid[ROWS_MAX];
   int flag;
 };
 
 // ps->pc holds the per-pass constants (the caller loads or computes them and synchronises the block).
 // Worker `wid` of `nworkers` takes tiles wid, wid + nworkers, ... and leaves its partial blob in a.partials[wid].
-__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid) {
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid, bool first_pass) {
   const int tid = threadIdx.x;
-  const int M = *a.scan_m;
+  const bool from_host = first_pass && a.body_src != nullptr;  // pass 0 always searches
+  const float4* body = from_host ? a.body_src : a.body;
+  const int M = a.m_value >= 0 ? a.m_value : *a.scan_m;
   stamp(a.dbg, 0, 2);
   const int G = pick_group(M, nworkers);
   const int rows = search ? THREADS / G : pick_rows_cached(M, nworkers);
@@ -809,15 +829,15 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nwo
   for (int tile = wid; tile < ntiles; tile += nworkers) {
     if (search) {
       if (G == 32)
-        search_tile<32>(a, ps->pc, M, tile, ps->nb, ps->cnt);
+        search_tile<32>(a, ps->pc, M, tile, ps->nb, ps->cnt, ps->body_row, body);
       else if (G == 16)
-        search_tile<16>(a, ps->pc, M, tile, ps->nb, ps->cnt);
+        search_tile<16>(a, ps->pc, M, tile, ps->nb, ps->cnt, ps->body_row, body);
       else
-        search_tile<8>(a, ps->pc, M, tile, ps->nb, ps->cnt);
+        search_tile<8>(a, ps->pc, M, tile, ps->nb, ps->cnt, ps->body_row, body);
       __syncthreads();
       stamp(a.dbg, 0, 3);
     }
-    finish_tile(a, ps->pc, M, tile, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid);
+    finish_tile(a, ps->pc, M, tile, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
     __syncthreads();
     stamp(a.dbg, 0, 4);
     if (seg < nseg) {
@@ -903,13 +923,26 @@ __device__ __noinline__ void block_exchange(const ShardArgs& sh, unsigned target
   __syncthreads();
 }
 
+// Host-direct path (lio_update_scan_host): nothing is copied before or after the kernel.  The prior travels in the
+// kernel parameters, the scan is read by pass 0 straight from the caller's pinned buffer, and the posterior is written
+// to mapped pinned memory followed by a sequence word the host spins on.
+struct HostPath {
+  int use_param_prior;      // 1: the prior is x0 / P0 below
+  double* host_out;         // mapped pinned {x 26, P 576, ctrl 4 (as 8 ints)} or nullptr
+  unsigned long long* host_flag;
+  unsigned long long seq;
+  double x0[26];
+  double P0[576];
+};
+
 // The whole update_iterated_dyn_share_modified loop (esekfom.hpp:270-346).  Cooperative launch: all blocks resident.
 // Blocks 0 .. gridDim-2 are WORKERS (h_share_model passes); the last block is the SOLVER: it keeps the filter state in
 // shared memory for the whole update, sums the workers' partial blobs as they arrive, performs the Kalman step and
 // publishes the constants of the next pass.  Flags are epoch stamps (target = epoch + pass + 1), so nothing has to be
 // zeroed between launches.
-__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const PassArgs a, const SolveArgs s,
-                                                                            const unsigned epoch, const ShardArgs sh) {
+template <bool HOST>
+__device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& s, const unsigned epoch,
+                                            const ShardArgs& sh, const HostPath& hp) {
   __shared__ __align__(16) unsigned char smem_raw[sizeof(PassSmem) > sizeof(SolveSmem) ? sizeof(PassSmem)
                                                                                         : sizeof(SolveSmem)];
   const int tid = threadIdx.x;
@@ -918,7 +951,12 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(cons
   if ((int)blockIdx.x == nworkers) {
     // ---------------------------------------------------------------- solver
     SolveSmem& ss = *reinterpret_cast<SolveSmem*>(smem_raw);
-    block_prior(s, n, &ss);
+    if (HOST && hp.use_param_prior)
+      block_prior(s, n, &ss, hp.x0, hp.P0, true);
+    else
+      block_prior(s, n, &ss, reinterpret_cast<const double*>(s.from_snapshot ? s.x0 : s.x),
+                  s.from_snapshot ? s.P0 : s.P, s.from_snapshot != 0);
+    if (tid == 0 && a.m_value >= 0) *const_cast<int*>(a.scan_m) = a.m_value;  // later calls read the device copy
     bool search = true;
     for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
       const unsigned target = epoch + (unsigned)pass_no + 1u;
@@ -935,19 +973,33 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(cons
       if (ss.sc.done) break;
       __syncthreads();
     }
+    if (HOST && hp.host_out != nullptr) {
+      // posterior straight into the host's mapped buffer, then the sequence word it spins on
+      __syncthreads();
+      for (int k = tid; k < 26; k += THREADS) hp.host_out[k] = ss.xa[k];
+      for (int k = tid; k < 576; k += THREADS) hp.host_out[26 + k] = ss.P[k];
+      if (tid < 8) reinterpret_cast<int*>(hp.host_out + 602)[tid] = reinterpret_cast<const int*>(&ss.sc)[tid];
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(hp.host_flag) = hp.seq;
+        __threadfence_system();
+      }
+    }
     return;
   }
   // ------------------------------------------------------------------ workers
   PassSmem& ps = *reinterpret_cast<PassSmem*>(smem_raw);
   const int wid = (int)blockIdx.x;
-  const StateD* x_first = s.from_snapshot ? s.x0 : s.x;
+  const StateD* x_first =
+      (HOST && hp.use_param_prior) ? reinterpret_cast<const StateD*>(hp.x0) : (s.from_snapshot ? s.x0 : s.x);
   stamp(a.dbg, 0, 1);
   if (tid == 0) load_pass_const(x_first, ps.pc);  // pass 0 searches at the prior
   __syncthreads();
   bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
     const unsigned target = epoch + (unsigned)pass_no + 1u;
-    block_pass(a, search, &ps, nworkers, wid);
+    block_pass(a, search, &ps, nworkers, wid, pass_no == 0);
     __syncthreads();  // the partial row is written; the release below (one thread) publishes the block's writes
     if (tid == 0) {
       __threadfence();
@@ -973,6 +1025,17 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(cons
   }
 }
 
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const PassArgs a, const SolveArgs s,
+                                                                            const unsigned epoch, const ShardArgs sh) {
+  update_body<false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a));  // the host path is compiled out
+}
+// the same loop with the host-direct prologue / epilogue; its 4.9 KB of extra parameters are only paid by that path
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host(const PassArgs a, const SolveArgs s,
+                                                                                 const unsigned epoch, const ShardArgs sh,
+                                                                                 const __grid_constant__ HostPath hp) {
+  update_body<true>(a, s, epoch, sh, hp);
+}
+
 // One pass at the state in s.x; the last block to finish reduces the partials into s.blob (same worker split and
 // the same summation order as update_kernel, so the stepwise driver reproduces its bits).
 // mode: 0 cached, 1 search, -1 as the loop state says (sharded driver).
@@ -987,7 +1050,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
   if ((int)blockIdx.x < nworkers) {
     if (tid == 0) load_pass_const(s.x, ps.pc);
     __syncthreads();
-    block_pass(a, search, &ps, nworkers, (int)blockIdx.x);
+    block_pass(a, search, &ps, nworkers, (int)blockIdx.x, false);
   }
   __threadfence();
   __syncthreads();
@@ -1019,7 +1082,8 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const SolveArgs s, int e
 
 __global__ void __launch_bounds__(THREADS) begin_kernel(const SolveArgs s, int extrinsic_est) {
   __shared__ SolveSmem ss;
-  block_prior(s, extrinsic_est ? 12 : 6, &ss);
+  block_prior(s, extrinsic_est ? 12 : 6, &ss, reinterpret_cast<const double*>(s.from_snapshot ? s.x0 : s.x),
+              s.from_snapshot ? s.P0 : s.P, s.from_snapshot != 0);
 }
 
 // Stand-alone batch of Nearest_Search calls (lio_knn5): one 8-lane group per query.
@@ -1135,6 +1199,8 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   PassArgs a;
   a.body = c->d_body;
   a.scan_m = c->d_scan_m;
+  a.m_value = -1;
+  a.body_src = nullptr;
   a.map = c->map;
   a.near_pts = c->d_near;
   a.near_d2 = c->d_near_d2;
@@ -1178,10 +1244,25 @@ static SolveArgs make_solve_args(lio_ctx* c, double R, int max_iter, int from_sn
 
 // The whole update as ONE cooperative launch.  own_min/own_max: ownership window of this rank (sharded map).
 int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot, float own_min, float own_max,
-                  bool sharded) {
+                  bool sharded, const HostDirect* hd) {
   int rc = ensure_tables(c);
   if (rc) return rc;
   PassArgs a = make_pass_args(c, ext, own_min, own_max);
+  static thread_local HostPath hp;  // 4.9 KB: kept off the stack frame of every call
+  hp.use_param_prior = 0;
+  hp.host_out = nullptr;
+  hp.host_flag = nullptr;
+  hp.seq = 0;
+  if (hd != nullptr) {
+    hp.use_param_prior = 1;
+    memcpy(hp.x0, hd->x0, sizeof(hp.x0));
+    memcpy(hp.P0, hd->P0, sizeof(hp.P0));
+    hp.host_out = hd->out_dev;
+    hp.host_flag = hd->flag_dev;
+    hp.seq = hd->seq;
+    a.m_value = hd->m;
+    a.body_src = hd->body_src;
+  }
   ShardArgs sh;
   memset(&sh, 0, sizeof(sh));
   sh.world = 1;
@@ -1209,9 +1290,9 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   }
   unsigned epoch = c->epoch;
   c->epoch += 40;  // > max_iter + 2
-  void* args[] = {&a, &s, &epoch, &sh};
-  LIO_CHECK(c, cudaLaunchCooperativeKernel((const void*)update_kernel, dim3(pass_grid_blocks(c)), dim3(THREADS), args,
-                                           0, c->stream));
+  void* args[] = {&a, &s, &epoch, &sh, &hp};
+  LIO_CHECK(c, cudaLaunchCooperativeKernel(hd != nullptr ? (const void*)update_kernel_host : (const void*)update_kernel,
+                                           dim3(pass_grid_blocks(c)), dim3(THREADS), args, 0, c->stream));
   c->launches++;
   return LIO_OK;
 }

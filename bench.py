@@ -476,7 +476,8 @@ def main():
             np.copyto(x_io, wl["scans"][j]["x_prior"])
             np.copyto(P_io, P0)
             t0 = time.perf_counter()
-            # one C-ABI call: H2D of the scan (M x 16 B, pinned) and of the prior, one kernel, D2H of the posterior
+            # one C-ABI call: H2D of the scan (M x 16 B, pinned), prior in the kernel parameters, one kernel, posterior
+            # written by the kernel into mapped pinned memory
             ctx.update_scan_host(bodies_np[j], x_io, P_io, R_COV, wl["max_iter"], wl["ext"])
             dt = time.perf_counter() - t0  # returns after the D2H of the posterior (host sync)
             if k >= warmup:
@@ -490,8 +491,8 @@ def main():
     e2e_ms = max_over_ranks(e2e_run(args.steps, 0))
     barrier()
     e2e_value = n_gpus * args.steps / (e2e_ms / 1000.0)
-    h2d = M * 16 + 604 * 8  # scan + {prior x, P, scan size, barrier words}
-    d2h = 606 * 8  # {posterior x, P, loop state}
+    h2d = M * 16 + 602 * 8  # scan (one copy) + prior {x, P} (kernel parameters)
+    d2h = 607 * 8  # posterior {x, P, loop state} + sequence word, written by the kernel into mapped pinned memory
 
     # full scan (undistort-free preprocess + update), raw scan from pinned host memory: second line of SURVEY §8d
     def full_run(steps, warmup):
