@@ -44,8 +44,9 @@ struct TopK {
   }
 };
 
-// A group of G lanes (G = 8, 16 or 32, aligned inside a warp) calls this with the SAME query; `gmask` names the
-// group's lanes, `gl` is the lane's index inside the group.
+// A group of G lanes (G = 8, 16 or 32, aligned inside a warp) calls this with the SAME query; `gl` is the lane's index
+// inside the group.  ALL 32 lanes of the warp must be here together (idle groups repeat a query): the shuffles below
+// use the full mask.
 // Round 0: the 27 cells of the 3x3x3 block around the query's cell are dealt round-robin to the lanes; a lane first
 // issues the hash probes of all its cells (independent loads), then streams the buckets it found as ONE virtual list,
 // four float4 loads in flight while the previous four are inserted into its private top-5.  The block holds every map
@@ -56,7 +57,7 @@ struct TopK {
 // Outputs are group-uniform: out_key[r] (d2 bits << 32 | id; ~0 when fewer than r+1 found), out_slot[r].
 template <int G>
 __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy, float qz, float max_d2, int rings,
-                                          unsigned gmask, int gl, unsigned long long out_key[LIO_K],
+                                          int gl, unsigned long long out_key[LIO_K],
                                           uint32_t out_slot[LIO_K], long long* dbg = nullptr) {
   constexpr int CPL = (27 + G - 1) / G;  // cells per lane and round
   auto mark = [&](int slot) {  // LIO_TIMELINE instrumentation: block 0 / thread 0 only
@@ -223,13 +224,6 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
   }
   mark(244);
   return found;
-}
-
-// Lanes of the aligned G-lane group that contains `lane`.
-template <int G>
-__device__ __forceinline__ unsigned group_mask(int lane) {
-  constexpr unsigned ones = (G >= 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-  return ones << (lane & ~(G - 1) & 31);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -4,19 +4,20 @@
 //            validity gates, 5x3 plane fit, residual, 1x12 Jacobian row, block-level FP64 reduction.
 //   solve  ≙ the rest of one loop iteration (esekfom.hpp:297-345): grid-level reduction, boxminus, Kalman step,
 //            boxplus, convergence state machine, covariance update.
-// update_kernel runs the WHOLE update_iterated_dyn_share_modified loop as one persistent cooperative launch: every
-// pass ends in a grid barrier; the block that arrives last reduces the per-block partial sums in block order and
-// performs the 24-state Kalman step while the others wait for the new state.  The loop state (lio::Ctrl) lives in
-// device memory, so there is no host round trip and no launch between passes.  pass_kernel / solve_kernel run the
-// same device code as single steps (host-driven passes, and the sharded-map driver that all-reduces the blob
-// between them).  No floating-point atomics anywhere: every sum has a fixed order.
+// update_kernel runs the WHOLE update_iterated_dyn_share_modified loop as one persistent cooperative launch.  Blocks
+// 0 .. grid-2 are workers (one h_share_model pass after the other: search tile -> finish tile -> block reduction ->
+// one partial row); the last block is the solver: it keeps the filter in shared memory, adds the workers' rows as
+// their arrival stamps come in, performs the Kalman step and publishes the constants of the next pass.  There is no
+// host round trip and no launch between passes.  pass_kernel / solve_kernel / begin_kernel run the same device code
+// as single steps (host-driven passes, and the NCCL variant of the sharded-map driver); update_kernel_host adds the
+// host-direct prologue / epilogue; block_exchange moves the sharded-map blobs through NVLink peer mailboxes.
+// No floating-point atomics anywhere: every sum has a fixed order.
 //
 // Kalman step.  The reference forms K_front = (H^T H / R + P^-1)^-1 with two 24x24 inverses per pass
 // (esekfom.hpp:311).  H has n = 6 (12 with extrinsic_est) non-zero columns, so with P11 = P[:n,:n], P21 = P[n:,:n]
 //     K_front[:, :n] = [ I ; P21 P11^-1 ] (H^T H / R + P11^-1)^-1
 // (block inversion; exact algebra).  P is constant during the loop, so P11^-1 and P21 P11^-1 are formed once per
-// update and each pass inverts one n x n matrix in a single warp (rows in registers, Gauss-Jordan, partial pivoting).
-#include <cooperative_groups.h>
+// update and each pass inverts one n x n SPD matrix (Gauss-Jordan in shared memory, one element per thread).
 #include <stdio.h>
 
 #include "lio_ctx.cuh"
@@ -155,7 +156,6 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
   constexpr int ROWS = THREADS / G;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
-  const unsigned gmask = group_mask<G>(lane);
   const int row = threadIdx.x / G;
   const int i_raw = tile * ROWS + row;
   const bool act = i_raw < M;  // group-uniform
@@ -168,7 +168,7 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
   unsigned long long key[LIO_K];
   uint32_t slot[LIO_K];
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[239] = global_ns();
-  const int cnt = group_knn5<G>(a.map, pwx, pwy, pwz, a.max_d2, a.rings, gmask, gl, key, slot, a.dbg);
+  const int cnt = group_knn5<G>(a.map, pwx, pwy, pwz, a.max_d2, a.rings, gl, key, slot, a.dbg);
   if (!act) return;
   // lanes 0..4 of the group fetch and publish one neighbour each
   if (gl < LIO_K) {
@@ -1092,7 +1092,6 @@ __global__ void __launch_bounds__(256) knn_batch_kernel(MapView map, const float
   constexpr int G = 8;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
-  const unsigned gmask = group_mask<G>(lane);
   const int gglobal = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int ngroups = (gridDim.x * blockDim.x) / G;
   const int iters = (m + ngroups - 1) / ngroups;  // uniform trip count: the warp stays together for the shuffles
@@ -1103,7 +1102,7 @@ __global__ void __launch_bounds__(256) knn_batch_kernel(MapView map, const float
     const float4 p = __ldg(q + i);
     unsigned long long ok[LIO_K];
     uint32_t os[LIO_K];
-    const int f = group_knn5<G>(map, p.x, p.y, p.z, max_d2, rings, gmask, gl, ok, os);
+    const int f = group_knn5<G>(map, p.x, p.y, p.z, max_d2, rings, gl, ok, os);
     if (!act) continue;
     if (gl < LIO_K) {
       unsigned long long k = ok[0];

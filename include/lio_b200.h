@@ -174,8 +174,10 @@ int lio_update_pass(lio_ctx* ctx, const lio_state* x, int do_search, int extrins
  * h_share_model calls made. */
 int lio_update_scan(lio_ctx* ctx, lio_state* x_io, double P_io[576], double R, int max_iter, int extrinsic_est,
                     int32_t* n_valid_last, int32_t* n_passes);
-/* The same for a downsampled cloud in HOST memory (m records of stride 16: x,y,z,intensity): scan up, prior up (one
- * copy each), one kernel, posterior down.  This is the per-scan call of a host that runs its own voxel filter. */
+/* The same for a downsampled cloud in HOST memory (m records of stride 16: x,y,z,intensity): one copy for the scan, the
+ * prior in the kernel parameters, one kernel, the posterior written by the kernel into mapped pinned memory (the call
+ * spins on a sequence word: no copy and no stream synchronisation after the kernel).  This is the per-scan call of a
+ * host that runs its own voxel filter. */
 int lio_update_scan_host(lio_ctx* ctx, const void* down_pts, int64_t m, int stride_bytes, lio_state* x_io,
                          double P_io[576], double R, int max_iter, int extrinsic_est, int32_t* n_valid_last,
                          int32_t* n_passes);
