@@ -397,6 +397,14 @@ __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool searc
 // so its cost is its code size.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WS = 25;  // odd row stride: the rows of one column land in distinct banks
+// 1/p to double precision without the IEEE division sequence: FP32 reciprocal seed + two Newton steps in FP64
+// (1e-7 -> 1e-14 -> 1e-28 relative before rounding).  Pivots of an SPD matrix: positive, far from the FP32 range limits.
+__device__ __forceinline__ double fast_rcp(double p) {
+  double r = (double)__frcp_rn((float)p);
+  r = fma(r, fma(-p, r, 1.0), r);
+  r = fma(r, fma(-p, r, 1.0), r);
+  return r;
+}
 __device__ __forceinline__ int inv_threads(int n) { return n <= 6 ? 96 : 192; }
 __device__ __forceinline__ void inv_barrier(int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
 __device__ __noinline__ void block_inverse_spd(const double* A, double* Ainv, int n, double* W) {
@@ -416,13 +424,13 @@ __device__ __noinline__ void block_inverse_spd(const double* A, double* Ainv, in
   inv_barrier(nthr);
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
-    const double pivot = W[k * WS + k];
-    if (has0 && i0 != k && c0 > k) W[i0 * WS + c0] = fma(-(W[i0 * WS + k] / pivot), W[k * WS + c0], W[i0 * WS + c0]);
-    if (has1 && i1 != k && c1 > k) W[i1 * WS + c1] = fma(-(W[i1 * WS + k] / pivot), W[k * WS + c1], W[i1 * WS + c1]);
+    const double pinv = fast_rcp(W[k * WS + k]);
+    if (has0 && i0 != k && c0 > k) W[i0 * WS + c0] = fma(-(W[i0 * WS + k] * pinv), W[k * WS + c0], W[i0 * WS + c0]);
+    if (has1 && i1 != k && c1 > k) W[i1 * WS + c1] = fma(-(W[i1 * WS + k] * pinv), W[k * WS + c1], W[i1 * WS + c1]);
     inv_barrier(nthr);
   }
-  if (has0 && c0 >= n) Ainv[i0 * n + (c0 - n)] = W[i0 * WS + c0] / W[i0 * WS + i0];
-  if (has1 && c1 >= n) Ainv[i1 * n + (c1 - n)] = W[i1 * WS + c1] / W[i1 * WS + i1];
+  if (has0 && c0 >= n) Ainv[i0 * n + (c0 - n)] = W[i0 * WS + c0] * fast_rcp(W[i0 * WS + i0]);
+  if (has1 && c1 >= n) Ainv[i1 * n + (c1 - n)] = W[i1 * WS + c1] * fast_rcp(W[i1 * WS + i1]);
   inv_barrier(nthr);
 }
 
@@ -448,13 +456,15 @@ __device__ __forceinline__ Quatd renorm(const Quatd& q) {
 }
 // q * Exp(w)
 __device__ __noinline__ void rot_plus(const Quatd* q, const double* w, Quatd* out) {
-  const double theta = sqrt((w[0] * w[0] + w[1] * w[1]) + w[2] * w[2]);
+  const double th2 = (w[0] * w[0] + w[1] * w[1]) + w[2] * w[2];
   double imag, real;
-  if (theta < 1e-10) {
-    const double t2 = theta * theta, t4 = t2 * t2;
-    imag = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
-    real = 1.0 - 0.125 * t2 + 0.00260417 * t4;
+  if (th2 < 2.5e-3) {
+    // |w| < 0.05 rad (every step after the first few centimetres of correction): sin(t/2)/t and cos(t/2) as series in
+    // t^2 -- no square root, no sincos, no division on the critical path; truncation < 1e-17
+    imag = 0.5 + th2 * (-1.0 / 48.0 + th2 * (1.0 / 3840.0 + th2 * (-1.0 / 645120.0)));
+    real = 1.0 + th2 * (-1.0 / 8.0 + th2 * (1.0 / 384.0 + th2 * (-1.0 / 46080.0)));
   } else {
+    const double theta = sqrt(th2);
     double sn, cs;
     sincos(0.5 * theta, &sn, &cs);
     imag = sn / theta;
