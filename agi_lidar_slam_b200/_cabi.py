@@ -63,7 +63,7 @@ EXPORTS = [
     "lio_map_dump", "lio_knn5", "lio_knn5_resident", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_preprocess_cloud2", "lio_scan_decoded",
     "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_update_scan_host", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
-    "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
+    "lio_update_enqueue_multi", "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_peer_handle", "lio_peer_connect",
     "lio_update_enqueue_sharded", "lio_peer_status", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
@@ -113,6 +113,7 @@ def load_library() -> C.CDLL:
         "lio_state_upload": (C.c_int, [vp, vp, vp]),
         "lio_state_download": (C.c_int, [vp, vp, vp, P(i32), P(i32)]),
         "lio_update_enqueue": (C.c_int, [vp, f64, C.c_int, C.c_int, C.c_int]),
+        "lio_update_enqueue_multi": (C.c_int, [vp, C.c_int, f64, C.c_int, C.c_int, C.c_int]),
         "lio_update_begin": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "lio_update_pass_enqueue": (C.c_int, [vp, C.c_int, f32, f32]),
         "lio_update_step_enqueue": (C.c_int, [vp, f64, C.c_int]),
@@ -433,6 +434,14 @@ class Context:
         counts = np.zeros(3, np.int32)
         self._check(self._lib.lio_map_incremental(self._h, _ptr(x), filter_size_map, int(ekf_inited), _ptr(counts)))
         return counts
+
+
+def update_enqueue_multi(ctxs, R=0.001, max_iter=4, extrinsic_est=False, from_snapshot=True):
+    """n <= 8 independent updates (one per Context, same device) in one cooperative launch."""
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    rc = load_library().lio_update_enqueue_multi(arr, len(ctxs), R, max_iter, int(extrinsic_est), int(from_snapshot))
+    if rc:
+        raise LioError(rc, (ctxs[0]._lib.lio_last_error(ctxs[0]._h) or b"").decode())
 
 
 # -- host-side sequential pieces (no context needed)

@@ -183,6 +183,7 @@ static int create_impl(lio_ctx* c) {
   c->h_pinned_bytes = 8 * (1280 + LIO_BLOB + 4);
   LIO_CHECK(c, cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
   LIO_CHECK(c, cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
+  LIO_CHECK(c, cudaEventCreateWithFlags(&c->multi_evt, cudaEventDisableTiming));
   LIO_CHECK(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_out), 8 * 616, cudaHostAllocMapped));
   memset(c->h_out, 0, 8 * 616);
   LIO_CHECK(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->h_out_dev), c->h_out, 0));
@@ -264,6 +265,7 @@ void lio_destroy(lio_ctx* c) {
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->upload_done) cudaEventDestroy(c->upload_done);
+  if (c->multi_evt) cudaEventDestroy(c->multi_evt);
   delete c;
 }
 
@@ -705,6 +707,36 @@ int lio_update_scan_host(lio_ctx* c, const void* down_pts, int64_t m, int stride
   memcpy(P_io, c->h_out + 26, 8 * 576);
   if (n_valid_last) *n_valid_last = hc->n_valid_last;
   if (n_passes) *n_passes = hc->n_passes;
+  return LIO_OK;
+}
+
+// ---------------------------------------------------------------- several independent sequences per launch
+int lio_update_enqueue_multi(lio_ctx* const* ctxs, int n, double R, int max_iter, int extrinsic_est, int from_snapshot) {
+  if (!ctxs || n < 1 || n > 8 || max_iter < 0 || max_iter > 32) return LIO_E_INVALID;
+  lio_ctx* c = ctxs[0];
+  if (!c) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  for (int q = 0; q < n; ++q) {
+    if (!ctxs[q] || ctxs[q]->device != c->device) return LIO_E_INVALID;
+    if (!ctxs[q]->map_built) {
+      c->err = "update on an empty map";
+      return LIO_E_EMPTY_MAP;
+    }
+    for (int r = 0; r < q; ++r)
+      if (ctxs[r] == ctxs[q]) return LIO_E_INVALID;
+  }
+  // whatever the other contexts have enqueued on their own streams (scan / prior uploads) comes first ...
+  for (int q = 1; q < n; ++q)
+    if (ctxs[q]->stream != c->stream) {
+      LIO_CHECK(c, cudaEventRecord(ctxs[q]->multi_evt, ctxs[q]->stream));
+      LIO_CHECK(c, cudaStreamWaitEvent(c->stream, ctxs[q]->multi_evt, 0));
+    }
+  const int rc = launch_update_multi(ctxs, n, R, max_iter, extrinsic_est ? 1 : 0, from_snapshot ? 1 : 0);
+  if (rc) return rc;
+  // ... and what they enqueue next (downloads) comes after the launch
+  LIO_CHECK(c, cudaEventRecord(c->multi_evt, c->stream));
+  for (int q = 1; q < n; ++q)
+    if (ctxs[q]->stream != c->stream) LIO_CHECK(c, cudaStreamWaitEvent(ctxs[q]->stream, c->multi_evt, 0));
   return LIO_OK;
 }
 

@@ -77,6 +77,7 @@ struct lio_ctx {
   void* h_pinned = nullptr;         // pinned staging: [0,606) download area, [640, 1242) upload area, [1280, ..) blob
   size_t h_pinned_bytes = 0;
   cudaEvent_t upload_done = nullptr;  // guards reuse of the upload staging area
+  cudaEvent_t multi_evt = nullptr;    // orders this context's stream with a multi-sequence launch on another stream
   double* h_out = nullptr;            // mapped pinned: posterior {x, P, ctrl} + sequence word (host-direct path)
   double* h_out_dev = nullptr;        // its device address
   unsigned long long host_seq = 0;
@@ -130,6 +131,7 @@ int ensure_tables(lio_ctx* c);
 int pass_grid_blocks(lio_ctx* c);
 int launch_update(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot, float own_min = -INFINITY,
                   float own_max = INFINITY, bool sharded = false, const HostDirect* hd = nullptr);
+int launch_update_multi(lio_ctx* const* cs, int n, double R, int max_iter, int extrinsic_est, int from_snapshot);
 int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float own_max);
 int launch_solve(lio_ctx* c, double R, int extrinsic_est);
 int launch_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot);

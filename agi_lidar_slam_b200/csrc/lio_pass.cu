@@ -950,15 +950,17 @@ struct HostPath {
 // shared memory for the whole update, sums the workers' partial blobs as they arrive, performs the Kalman step and
 // publishes the constants of the next pass.  Flags are epoch stamps (target = epoch + pass + 1), so nothing has to be
 // zeroed between launches.
+// nblk / bid: size of the (sub-)grid that works on this update and this block's index in it -- the whole grid for a
+// single update, a slice of it when several independent sequences share one launch (update_kernel_multi).
 template <bool HOST>
 __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& s, const unsigned epoch,
-                                            const ShardArgs& sh, const HostPath& hp) {
+                                            const ShardArgs& sh, const HostPath& hp, const int nblk, const int bid) {
   __shared__ __align__(16) unsigned char smem_raw[sizeof(PassSmem) > sizeof(SolveSmem) ? sizeof(PassSmem)
                                                                                         : sizeof(SolveSmem)];
   const int tid = threadIdx.x;
   const int n = a.extrinsic_est ? 12 : 6;
-  const int nworkers = (int)gridDim.x - 1;
-  if ((int)blockIdx.x == nworkers) {
+  const int nworkers = nblk - 1;
+  if (bid == nworkers) {
     // ---------------------------------------------------------------- solver
     SolveSmem& ss = *reinterpret_cast<SolveSmem*>(smem_raw);
     if (HOST && hp.use_param_prior)
@@ -1000,7 +1002,7 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
   }
   // ------------------------------------------------------------------ workers
   PassSmem& ps = *reinterpret_cast<PassSmem*>(smem_raw);
-  const int wid = (int)blockIdx.x;
+  const int wid = bid;
   const StateD* x_first =
       (HOST && hp.use_param_prior) ? reinterpret_cast<const StateD*>(hp.x0) : (s.from_snapshot ? s.x0 : s.x);
   stamp(a.dbg, 0, 1);
@@ -1037,13 +1039,34 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
 
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const PassArgs a, const SolveArgs s,
                                                                             const unsigned epoch, const ShardArgs sh) {
-  update_body<false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a));  // the host path is compiled out
+  update_body<false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x,
+                     (int)blockIdx.x);  // the host path is compiled out
 }
 // the same loop with the host-direct prologue / epilogue; its 4.9 KB of extra parameters are only paid by that path
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host(const PassArgs a, const SolveArgs s,
                                                                                  const unsigned epoch, const ShardArgs sh,
                                                                                  const __grid_constant__ HostPath hp) {
-  update_body<true>(a, s, epoch, sh, hp);
+  update_body<true>(a, s, epoch, sh, hp, (int)gridDim.x, (int)blockIdx.x);
+}
+
+// Several INDEPENDENT updates (different sequences, each with its own map, scan and filter: BASELINE.json config 4) in
+// one cooperative launch: the grid is cut into equal slices, one per update, each with its own workers and solver.
+// A single update is latency-bound and leaves most issue slots of the GPU idle; slices fill them.
+constexpr int LIO_MAX_MULTI = 8;
+struct MultiArgs {
+  int n;
+  unsigned epoch[LIO_MAX_MULTI];
+  PassArgs a[LIO_MAX_MULTI];
+  SolveArgs s[LIO_MAX_MULTI];
+};
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_multi(const __grid_constant__ MultiArgs m) {
+  const int per = (int)gridDim.x / m.n;
+  const int q = (int)blockIdx.x / per;
+  if (q >= m.n) return;  // left-over blocks when the grid does not divide evenly
+  ShardArgs sh;
+  sh.world = 1;
+  update_body<false>(m.a[q], m.s[q], m.epoch[q], sh, *reinterpret_cast<const HostPath*>(&m), per,
+                     (int)blockIdx.x - q * per);
 }
 
 // One pass at the state in s.x; the last block to finish reduces the partials into s.blob (same worker split and
@@ -1302,6 +1325,32 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   void* args[] = {&a, &s, &epoch, &sh, &hp};
   LIO_CHECK(c, cudaLaunchCooperativeKernel(hd != nullptr ? (const void*)update_kernel_host : (const void*)update_kernel,
                                            dim3(pass_grid_blocks(c)), dim3(THREADS), args, 0, c->stream));
+  c->launches++;
+  return LIO_OK;
+}
+
+// n independent updates (one per context, all on the same device) in one cooperative launch on cs[0]'s stream.
+int launch_update_multi(lio_ctx* const* cs, int n, double R, int max_iter, int ext, int from_snapshot) {
+  lio_ctx* c = cs[0];
+  int rc = ensure_tables(c);
+  if (rc) return rc;
+  static thread_local MultiArgs m;
+  m.n = n;
+  for (int q = 0; q < n; ++q) {
+    lio_ctx* k = cs[q];
+    m.a[q] = make_pass_args(k, ext, -INFINITY, INFINITY);
+    m.s[q] = make_solve_args(k, R, max_iter, from_snapshot);
+    if (k->epoch > 0xF0000000u) {
+      LIO_CHECK(c, cudaMemsetAsync(k->d_arrive, 0, sizeof(unsigned) * 1024, c->stream));
+      LIO_CHECK(c, cudaMemsetAsync(k->d_sync, 0, 2 * sizeof(unsigned), c->stream));
+      k->epoch = 0;
+    }
+    m.epoch[q] = k->epoch;
+    k->epoch += 40;
+  }
+  void* args[] = {&m};
+  LIO_CHECK(c, cudaLaunchCooperativeKernel((const void*)update_kernel_multi, dim3(pass_grid_blocks(c)), dim3(THREADS),
+                                           args, 0, c->stream));
   c->launches++;
   return LIO_OK;
 }

@@ -187,6 +187,12 @@ int lio_state_download(lio_ctx* ctx, lio_state* x, double P[576], int32_t* n_val
 /* Enqueue the whole update (one persistent cooperative kernel) on the context stream; no host sync.  from_snapshot != 0 first restores the state
  * uploaded by lio_state_upload (so a benchmark can repeat the same update). */
 int lio_update_enqueue(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, int from_snapshot);
+/* n <= 8 INDEPENDENT updates -- different sequences, each context with its own map, scan and filter state (BASELINE.json
+ * config 4) -- in ONE cooperative launch on ctxs[0]'s stream: the persistent grid is cut into n slices, each with its own
+ * workers and solver block.  A single update is latency-bound and leaves most of the GPU idle; slices fill it.  All
+ * contexts must live on the same device; states go in with lio_state_upload and come out with lio_state_download per
+ * context (stream order between the contexts' streams and the launch is taken care of). */
+int lio_update_enqueue_multi(lio_ctx* const* ctxs, int n, double R, int max_iter, int extrinsic_est, int from_snapshot);
 /* Sharded-map driver: begin, then per pass {pass_enqueue -> all-reduce 92 doubles at
  * lio_blob_device_ptr -> step_enqueue}.  x_own_min/max restrict the queries this rank owns to
  * x_own_min <= p_world.x < x_own_max (use -inf/+inf for a single GPU).  begin resets the loop state

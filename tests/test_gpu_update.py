@@ -185,3 +185,63 @@ def test_many_tiles_per_block(ctx, orc, avia_cfg, ext):
     xg, Pg, nvg, npass = ctx.update_scan(x, cfg["P"], 0.001, 4, ext)
     assert npass == len(trace) and nvg == nvr
     assert np.abs(xg - xr).max() < 1e-7 and rel_err(Pg, Pr) < 1e-6
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+def test_multi_sequence_launch_equals_single_updates(orc, small_cfg, avia_cfg, n):
+    """lio_update_enqueue_multi: n independent sequences (own map, scan, prior) sliced over one cooperative launch give
+    what n single launches give -- same neighbours and counts, state / covariance to 1e-9 (the worker count per update
+    differs, so the fixed summation order of the partial blobs differs)."""
+    from agi_lidar_slam_b200 import _cabi
+
+    ctxs = [_cabi.Context(0, max_scan_points=1 << 18, max_down_points=100000, max_map_points=1 << 20) for _ in range(n)]
+    try:
+        rng = np.random.default_rng(5)
+        priors, single = [], []
+        for q, c in enumerate(ctxs):
+            cfg = small_cfg if q % 2 == 0 else avia_cfg
+            _setup(c, cfg, orc)
+            x = cfg["x_prior"].copy()
+            x[0:3] += rng.normal(0, 0.02, 3)  # a different prior per sequence
+            priors.append((x, cfg["P"]))
+            single.append(c.update_scan(x, cfg["P"], 0.001, 4, q % 3 == 0))
+        # extrinsic_est is one flag per launch: run the multi launch once per flag value and compare what applies
+        for ext in (False, True):
+            for c, (x, P) in zip(ctxs, priors):
+                c.state_upload(x, P)
+            _cabi.update_enqueue_multi(ctxs, 0.001, 4, ext, from_snapshot=True)
+            for q, c in enumerate(ctxs):
+                if (q % 3 == 0) != ext:
+                    continue
+                xm, Pm, nv, npass = c.state_download()
+                xs, Ps, nvs, nps = single[q]
+                assert (nv, npass) == (nvs, nps)
+                assert rel_err(xm, xs) < 1e-9 and rel_err(Pm, Ps) < 1e-9
+        # and it is deterministic run to run
+        for c, (x, P) in zip(ctxs, priors):
+            c.state_upload(x, P)
+        _cabi.update_enqueue_multi(ctxs, 0.001, 4, False, from_snapshot=True)
+        a = [c.state_download() for c in ctxs]
+        _cabi.update_enqueue_multi(ctxs, 0.001, 4, False, from_snapshot=True)
+        b = [c.state_download() for c in ctxs]
+        for u, v in zip(a, b):
+            assert np.array_equal(u[0], v[0]) and np.array_equal(u[1], v[1])
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_multi_sequence_rejects_bad_arguments(ctx, orc, small_cfg):
+    from agi_lidar_slam_b200 import _cabi
+
+    _setup(ctx, small_cfg, orc)
+    with pytest.raises(_cabi.LioError):
+        _cabi.update_enqueue_multi([ctx, ctx])  # the same context twice
+    with pytest.raises(_cabi.LioError):
+        _cabi.update_enqueue_multi([ctx] * 9)  # more than 8
+    other = _cabi.Context(0, max_scan_points=1 << 12, max_down_points=1 << 12, max_map_points=1 << 12)
+    try:
+        with pytest.raises(_cabi.LioError):
+            _cabi.update_enqueue_multi([ctx, other])  # empty map
+    finally:
+        other.close()
