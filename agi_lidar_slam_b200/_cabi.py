@@ -36,6 +36,15 @@ class LioError(RuntimeError):
         self.code = code
 
 
+class ScanReport(C.Structure):
+    """lio_scan_report (include/lio_b200.h)."""
+    _fields_ = [("m", C.c_int64), ("status", C.c_int32), ("n_valid", C.c_int32), ("n_passes", C.c_int32),
+                ("counts", C.c_int32 * 3)]
+
+
+SCAN_UPDATED, SCAN_FEW_POINTS, SCAN_MAP_BUILT = 0, 1, 2
+
+
 class Caps(C.Structure):
     _fields_ = [
         ("max_scan_points", C.c_int64),
@@ -63,7 +72,8 @@ EXPORTS = [
     "lio_map_dump", "lio_knn5", "lio_knn5_resident", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_preprocess_cloud2", "lio_scan_decoded",
     "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_update_scan_host", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
-    "lio_update_enqueue_multi", "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
+    "lio_update_enqueue_multi", "lio_scan_step", "lio_scan_step_begin", "lio_scan_step_end",
+    "lio_scan_step_finish", "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_peer_handle", "lio_peer_connect",
     "lio_update_enqueue_sharded", "lio_peer_status", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
@@ -114,6 +124,11 @@ def load_library() -> C.CDLL:
         "lio_state_download": (C.c_int, [vp, vp, vp, P(i32), P(i32)]),
         "lio_update_enqueue": (C.c_int, [vp, f64, C.c_int, C.c_int, C.c_int]),
         "lio_update_enqueue_multi": (C.c_int, [vp, C.c_int, f64, C.c_int, C.c_int, C.c_int]),
+        "lio_scan_step": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, vp, C.c_float, C.c_float, f64, C.c_int,
+                                    C.c_int, C.c_int, vp]),
+        "lio_scan_step_begin": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, vp, C.c_float, vp]),
+        "lio_scan_step_end": (C.c_int, [vp, C.c_float, C.c_int]),
+        "lio_scan_step_finish": (C.c_int, [vp, vp, vp, vp]),
         "lio_update_begin": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
         "lio_update_pass_enqueue": (C.c_int, [vp, C.c_int, f32, f32]),
         "lio_update_step_enqueue": (C.c_int, [vp, f64, C.c_int]),
@@ -316,6 +331,42 @@ class Context:
     def scan_upload(self, down_pts):
         pts, stride = _points(down_pts)
         self._check(self._lib.lio_scan_upload(self._h, _ptr(pts), pts.shape[0], stride))
+
+    # -- one main-loop iteration per call
+    @staticmethod
+    def _step_inputs(raw_pts, poses):
+        pts, stride = _points(raw_pts)
+        if poses is None or len(poses) < 2:
+            return pts, stride, None, 0
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, POSE_DOUBLES)
+        return pts, stride, poses, poses.shape[0]
+
+    def scan_step(self, raw_pts, poses, x, P, leaf_surf, leaf_map, R=0.001, max_iter=4, extrinsic_est=False,
+                  ekf_inited=True):
+        """lio_scan_step.  x (26,) and P (24,24) float64 contiguous are updated IN PLACE; returns the ScanReport."""
+        pts, stride, poses, n_poses = self._step_inputs(raw_pts, poses)
+        rep = ScanReport()
+        self._check(self._lib.lio_scan_step(self._h, _ptr(pts), pts.shape[0], stride,
+                                            _ptr(poses) if n_poses else None, n_poses, x.ctypes.data, P.ctypes.data,
+                                            leaf_surf, leaf_map, R, max_iter, int(extrinsic_est), int(ekf_inited),
+                                            C.byref(rep)))
+        return rep
+
+    def scan_step_begin(self, raw_pts, poses, x, P, leaf_surf) -> bool:
+        pts, stride, poses, n_poses = self._step_inputs(raw_pts, poses)
+        due = C.c_int32(0)
+        self._check(self._lib.lio_scan_step_begin(self._h, _ptr(pts), pts.shape[0], stride,
+                                                  _ptr(poses) if n_poses else None, n_poses, x.ctypes.data,
+                                                  P.ctypes.data, leaf_surf, C.byref(due)))
+        return bool(due.value)
+
+    def scan_step_end(self, leaf_map, ekf_inited=True):
+        self._check(self._lib.lio_scan_step_end(self._h, leaf_map, int(ekf_inited)))
+
+    def scan_step_finish(self, x, P):
+        rep = ScanReport()
+        self._check(self._lib.lio_scan_step_finish(self._h, x.ctypes.data, P.ctypes.data, C.byref(rep)))
+        return rep
 
     # -- update
     def update_pass(self, x, do_search: bool, extrinsic_est: bool):

@@ -425,13 +425,19 @@ static int preprocess_common(lio_ctx* c, const void* raw_pts, int64_t n, int str
   if (rc) return rc;
   if (n_poses >= 2)
     LIO_CHECK(c, cudaMemcpyAsync(c->d_poses, poses, sizeof(lio_pose6d) * n_poses, cudaMemcpyHostToDevice, c->stream));
+  c->scan_m_bound = std::min<int64_t>(n, c->caps.max_down_points);
   return preprocess(c, n, n_poses >= 2 ? n_poses : 0, end_state, leaf, stride == 48);
 }
 
+static int preprocess_decode(lio_ctx* c, const int* h, int64_t* m);
 static int preprocess_status(lio_ctx* c, int64_t* m) {
   int h[8];
   LIO_CHECK(c, cudaMemcpyAsync(h, c->d_prep_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  return preprocess_decode(c, h, m);
+}
+// h = the first 8 preprocessing counters, already on the host
+static int preprocess_decode(lio_ctx* c, const int* h, int64_t* m) {
   if (h[7] == 2) {
     c->err = "more occupied voxels than lio_caps.max_down_points";
     return LIO_E_CAPACITY;
@@ -710,6 +716,120 @@ int lio_update_scan_host(lio_ctx* c, const void* down_pts, int64_t m, int stride
   return LIO_OK;
 }
 
+// ---------------------------------------------------------------- one main-loop iteration per call
+// laserMapping.cpp:737-785 for one scan -- VoxelGrid(UndistortPcl(scan)), the feats_down_size < 5 skip, the first-scan
+// Build, update_iterated_dyn_share_modified, map_incremental -- enqueued back to back: M, the class counts and the insert
+// sizes stay on the device, the host synchronises ONCE, at the end, for {posterior, M, counts, error flags}.
+int lio_scan_step_begin(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses, int n_poses,
+                        const lio_state* x, const double P[576], float leaf_surf, int32_t* update_due) {
+  if (!c || !x || !P || !update_due) return LIO_E_INVALID;
+  *update_due = 0;
+  c->step_phase = 0;
+  c->min_m = 0;
+  int rc = preprocess_common(c, raw_pts, n, stride, poses, n_poses, x, leaf_surf);
+  if (rc) return rc;
+  if (!c->map_built) {  // first scan with points: host-synchronous, happens once per sequence
+    int64_t m = 0;
+    rc = preprocess_status(c, &m);
+    if (rc) return rc;
+    c->step_m = m;
+    c->step_status = LIO_SCAN_FEW_POINTS;
+    if (m >= 5) {
+      rc = map_build_scan(c, x);
+      if (rc) return rc;
+      c->step_status = LIO_SCAN_MAP_BUILT;
+    }
+    c->step_phase = 3;
+    return LIO_OK;
+  }
+  rc = state_upload_impl(c, x, P, false);
+  if (rc) return rc;
+  c->min_m = 5;  // update and map growth see a scan of fewer than 5 points as empty
+  c->step_phase = 1;
+  *update_due = 1;
+  return LIO_OK;
+}
+
+int lio_scan_step_end(lio_ctx* c, float leaf_map, int ekf_inited) {
+  if (!c || !(leaf_map > 0.f)) return LIO_E_INVALID;
+  if (c->step_phase == 3) return LIO_OK;
+  if (c->step_phase != 1) {
+    c->err = "lio_scan_step_end without lio_scan_step_begin";
+    return LIO_E_INVALID;
+  }
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  const int rc = map_incremental_enqueue(c, leaf_map, ekf_inited ? 1 : 0, 5, c->scan_m_bound);
+  if (rc) return rc;
+  double* hp = static_cast<double*>(c->h_pinned);
+  LIO_CHECK(c, cudaMemcpyAsync(hp, c->d_x, 8 * 606, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(hp + 606, c->d_prep_counters, 4 * 16, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(hp + 614, c->map.counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  c->step_phase = 2;
+  return LIO_OK;
+}
+
+int lio_scan_step_finish(lio_ctx* c, lio_state* x_out, double P_out[576], lio_scan_report* rep) {
+  if (!c || !rep) return LIO_E_INVALID;
+  memset(rep, 0, sizeof(*rep));
+  c->min_m = 0;
+  if (c->step_phase == 3) {
+    c->step_phase = 0;
+    rep->m = c->step_m;
+    rep->status = c->step_status;
+    return LIO_OK;
+  }
+  if (c->step_phase != 2) {
+    c->err = "lio_scan_step_finish without lio_scan_step_end";
+    return LIO_E_INVALID;
+  }
+  c->step_phase = 0;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  const double* hp = static_cast<const double*>(c->h_pinned);
+  const int* prep = reinterpret_cast<const int*>(hp + 606);
+  const uint32_t* mc = reinterpret_cast<const uint32_t*>(hp + 614);
+  int64_t m = 0;
+  const int rc = preprocess_decode(c, prep, &m);
+  rep->m = m;
+  if (rc) return rc;
+  if (mc[3] != 0) {
+    c->err = mc[3] == 1 ? "map hash table full (raise lio_caps.max_map_points)"
+                        : "map point pool full (raise lio_caps.max_map_points)";
+    return LIO_E_CAPACITY;
+  }
+  if (m < 5) {
+    rep->status = LIO_SCAN_FEW_POINTS;  // state untouched, as after the reference's `continue`
+    return LIO_OK;
+  }
+  const Ctrl* hc = reinterpret_cast<const Ctrl*>(hp + 602);
+  rep->status = LIO_SCAN_UPDATED;
+  rep->n_valid = hc->n_valid_last;
+  rep->n_passes = hc->n_passes;
+  rep->counts[0] = prep[8];
+  rep->counts[1] = prep[9];
+  rep->counts[2] = (int32_t)mc[4];
+  c->next_id += prep[8] + prep[9];
+  if (x_out) memcpy(x_out, hp, sizeof(lio_state));
+  if (P_out) memcpy(P_out, hp + 26, 8 * 576);
+  return LIO_OK;
+}
+
+int lio_scan_step(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses, int n_poses,
+                  lio_state* x_io, double P_io[576], float leaf_surf, float leaf_map, double R, int max_iter,
+                  int extrinsic_est, int ekf_inited, lio_scan_report* rep) {
+  if (!c || !x_io || !P_io || !rep || max_iter < 0 || max_iter > 32 || !(leaf_map > 0.f)) return LIO_E_INVALID;
+  int32_t due = 0;
+  int rc = lio_scan_step_begin(c, raw_pts, n, stride, poses, n_poses, x_io, P_io, leaf_surf, &due);
+  if (rc) return rc;
+  if (due) {
+    rc = launch_update(c, R, max_iter, extrinsic_est ? 1 : 0, 1);
+    if (rc) return rc;
+    rc = lio_scan_step_end(c, leaf_map, ekf_inited);
+    if (rc) return rc;
+  }
+  return lio_scan_step_finish(c, x_io, P_io, rep);
+}
+
 // ---------------------------------------------------------------- several independent sequences per launch
 int lio_update_enqueue_multi(lio_ctx* const* ctxs, int n, double R, int max_iter, int extrinsic_est, int from_snapshot) {
   if (!ctxs || n < 1 || n > 8 || max_iter < 0 || max_iter > 32) return LIO_E_INVALID;
@@ -935,7 +1055,7 @@ int lio_predict(lio_state* xs, double P[576], double dt, const double Q[144], co
     f[12 + i] = (a_in[i] + x.grav[i]) * dt;
   }
   // F = I + dt * df_dx ; W = dt * df_dw
-  std::vector<double> F(576, 0.0), W(24 * 12, 0.0);
+  double F[576] = {0}, W[24 * 12] = {0};
   for (int i = 0; i < 24; ++i) F[i * 24 + i] = 1.0;
   const double hat[9] = {0, -am[2], am[1], am[2], 0, -am[0], -am[1], am[0], 0};
   double Rh[9];
@@ -956,27 +1076,39 @@ int lio_predict(lio_state* xs, double P[576], double dt, const double Q[144], co
   StateD xn;
   boxplus(x, f, xn);
   x = xn;
-  std::vector<double> T(576), Pn(576), WQ(24 * 12);
+  // P <- F P F^T + W Q W^T (esekfom.hpp:93-94).  F = I + dt df_dx has 51 non-zeros and W = dt df_dw has 18: the sums run
+  // over the non-zero terms only, in ascending k -- the terms left out are exact zeros, so the result is bit-identical
+  // to the dense triple loop at a tenth of its cost (this runs ~20 times per scan on the host).
+  double T[576], Pn[576], WQ[24 * 12];
+  int fk[24][8], fn[24], wk[24][4], wn[24];
+  for (int i = 0; i < 24; ++i) {
+    fn[i] = wn[i] = 0;
+    for (int k = 0; k < 24; ++k)
+      if (F[i * 24 + k] != 0.0) fk[i][fn[i]++] = k;  // at most 8 per row (rows 12-14: 3 + 1 + 3 + 1)
+    for (int k = 0; k < 12; ++k)
+      if (W[i * 12 + k] != 0.0) wk[i][wn[i]++] = k;  // at most 3 per row
+  }
   for (int i = 0; i < 24; ++i)
     for (int j = 0; j < 24; ++j) {
       double s = 0;
-      for (int k = 0; k < 24; ++k) s += F[i * 24 + k] * P[k * 24 + j];
+      for (int t = 0; t < fn[i]; ++t) s += F[i * 24 + fk[i][t]] * P[fk[i][t] * 24 + j];
       T[i * 24 + j] = s;
     }
   for (int i = 0; i < 24; ++i)
     for (int j = 0; j < 12; ++j) {
       double s = 0;
-      for (int k = 0; k < 12; ++k) s += W[i * 12 + k] * Q[k * 12 + j];
+      for (int t = 0; t < wn[i]; ++t) s += W[i * 12 + wk[i][t]] * Q[wk[i][t] * 12 + j];
       WQ[i * 12 + j] = s;
     }
   for (int i = 0; i < 24; ++i)
     for (int j = 0; j < 24; ++j) {
       double s = 0, s2 = 0;
-      for (int k = 0; k < 24; ++k) s += T[i * 24 + k] * F[j * 24 + k];
-      for (int k = 0; k < 12; ++k) s2 += WQ[i * 12 + k] * W[j * 12 + k];
+      for (int t = 0; t < fn[j]; ++t) s += T[i * 24 + fk[j][t]] * F[j * 24 + fk[j][t]];
+      if (wn[i] > 0)
+        for (int t = 0; t < wn[j]; ++t) s2 += WQ[i * 12 + wk[j][t]] * W[j * 12 + wk[j][t]];
       Pn[i * 24 + j] = s + s2;
     }
-  memcpy(P, Pn.data(), 8 * 576);
+  memcpy(P, Pn, 8 * 576);
   return LIO_OK;
 }
 

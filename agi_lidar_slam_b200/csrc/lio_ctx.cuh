@@ -102,7 +102,15 @@ struct lio_ctx {
   uint32_t* d_sort_vals_out = nullptr;
   void* d_cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
-  int* d_prep_counters = nullptr;   // [0] M, [1..6] key min/max, [7] error
+  int* d_prep_counters = nullptr;   // [0] M, [1..6] key min/max, [7] error, [8..9] map_incremental class counts,
+                                    // [10] voxel runs, [12] decoded points
+
+  // lio_scan_step: one main-loop iteration enqueued without intermediate host synchronisation
+  int min_m = 0;               // update / map growth treat a scan with fewer points as empty (5 inside a step)
+  int64_t scan_m_bound = 0;    // upper bound of M while only the device knows it (launch bounds)
+  int step_phase = 0;          // 0 idle, 1 begun (update due), 2 map growth + report enqueued, 3 first-scan branch done
+  int step_status = 0;         // LIO_SCAN_* of the first-scan branch
+  int64_t step_m = 0;
 
 };
 
@@ -143,6 +151,7 @@ int map_add_downsample(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_ba
 int map_delete_boxes(lio_ctx* c, const float* h_boxes6, int nb, int32_t* n_deleted);
 int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
 int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]);
+int map_incremental_enqueue(lio_ctx* c, float fsm, int ekf_inited, int min_m, int64_t bound);
 int map_build_scan(lio_ctx* c, const lio_state* x);
 
 int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux);

@@ -21,10 +21,26 @@ __global__ void map_init_kernel(MapView m, uint32_t hash_cap) {
   if (blockIdx.x == 0 && threadIdx.x < 8) m.counters[threadIdx.x] = 0;
 }
 
+// Batch size and id base of an insert: host values, or -- when the host enqueues a whole scan without waiting for the
+// counts (lio_scan_step) -- values other kernels of the same stream left on the device.  n is then the launch bound.
+struct BatchDev {
+  const int* n_dev;       // nullptr: n is exact
+  const int* id_off_dev;  // nullptr: ids start at id_base
+};
+__device__ __forceinline__ int batch_n(int n, const BatchDev& b) {
+  if (b.n_dev == nullptr) return n;
+  const int v = *b.n_dev;
+  return v < n ? v : n;
+}
+__device__ __forceinline__ int batch_id(int id_base, const BatchDev& b) {
+  return id_base + (b.id_off_dev ? *b.id_off_dev : 0);
+}
+
 // phase 1: find-or-create the cell of every point, take a rank inside this batch
-__global__ void map_reserve_kernel(MapView m, const float4* pts, int n, const uint8_t* flag, uint32_t* slot,
+__global__ void map_reserve_kernel(MapView m, const float4* pts, int n, BatchDev bd, const uint8_t* flag, uint32_t* slot,
                                    uint32_t* rank) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  n = batch_n(n, bd);
   if (i >= n) return;
   if (flag && !flag[i]) return;
   const float4 p = pts[i];
@@ -51,8 +67,10 @@ __global__ void map_reserve_kernel(MapView m, const float4* pts, int n, const ui
 }
 
 // phase 2: one thread per touched cell makes room (amortised doubling; the live points move, the old run is retired)
-__global__ void map_grow_kernel(MapView m, int n, const uint8_t* flag, const uint32_t* slot, const uint32_t* rank) {
+__global__ void map_grow_kernel(MapView m, int n, BatchDev bd, const uint8_t* flag, const uint32_t* slot,
+                                const uint32_t* rank) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  n = batch_n(n, bd);
   if (i >= n) return;
   if (flag && !flag[i]) return;
   const uint32_t h = slot[i];
@@ -87,9 +105,11 @@ __global__ void map_grow_kernel(MapView m, int n, const uint8_t* flag, const uin
 }
 
 // phase 3: write the points
-__global__ void map_fill_kernel(MapView m, const float4* pts, int n, const uint8_t* flag, const uint32_t* slot,
-                                const uint32_t* rank, int id_base) {
+__global__ void map_fill_kernel(MapView m, const float4* pts, int n, BatchDev bd, const uint8_t* flag,
+                                const uint32_t* slot, const uint32_t* rank, int id_base) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  n = batch_n(n, bd);
+  id_base = batch_id(id_base, bd);
   bool wrote = false;
   if (i < n && (!flag || flag[i])) {
     const uint32_t h = slot[i];
@@ -138,9 +158,10 @@ __global__ void vox_init_kernel(unsigned long long* vkey, unsigned long long* vb
 }
 
 // per batch voxel: nearest-to-centre new point; ties go to the LATER point (a new point wins ties, :456-462)
-__global__ void vox_best_kernel(const float4* pts, int n, float ds, unsigned long long* vkey, unsigned long long* vbest,
-                                uint32_t vmask, uint32_t* vslot) {
+__global__ void vox_best_kernel(const float4* pts, int n, BatchDev bd, float ds, unsigned long long* vkey,
+                                unsigned long long* vbest, uint32_t vmask, uint32_t* vslot) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  n = batch_n(n, bd);
   if (i >= n) return;
   const float4 p = pts[i];
   const VoxGeom g = vox_geom(p, ds);
@@ -157,9 +178,12 @@ __global__ void vox_best_kernel(const float4* pts, int n, float ds, unsigned lon
 }
 
 // the winner of each batch voxel settles it against the points already in the map
-__global__ void vox_apply_kernel(MapView m, const float4* pts, int n, float ds, const unsigned long long* vbest,
-                                 const uint32_t* vslot, int id_base, uint8_t* append_flag) {
+__global__ void vox_apply_kernel(MapView m, const float4* pts, int n, BatchDev bd, float ds,
+                                 const unsigned long long* vbest, const uint32_t* vslot, int id_base,
+                                 uint8_t* append_flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  n = batch_n(n, bd);
+  id_base = batch_id(id_base, bd);
   if (i >= n) return;
   append_flag[i] = 0;
   const unsigned long long best = vbest[vslot[i]];
@@ -264,10 +288,11 @@ __global__ void map_dump_kernel(MapView m, float4* out, uint32_t cap, uint32_t* 
 // ---- map_incremental (laserMapping.cpp:382-433) -------------------------------------------------------------------
 // class 0 = skip, 1 = PointToAdd (Add_Points with downsample), 2 = PointNoNeedDownsample
 __global__ void map_incr_classify_kernel(const float4* body, const int* scan_m, const StateD* xs, const float4* near_pts,
-                                         const int* near_cnt, int ekf_inited, float fsm, float4* world,
+                                         const int* near_cnt, int ekf_inited, float fsm, int min_m, float4* world,
                                          uint8_t* cls) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *scan_m) return;
+  const int M = *scan_m;
+  if (i >= M || M < min_m) return;  // fewer than min_m points: the main loop skips the scan (laserMapping.cpp:741-744)
   // pointBodyToWorld (laserMapping.cpp:277-288): rotation MATRICES here, FP64 -> FP32
   double R[9], Rli[9];
   quat_to_mat(xs->rot, R);
@@ -330,10 +355,10 @@ __global__ void scan_to_world_kernel(const float4* body, const int* scan_m, cons
 
 // order-preserving compaction of the two classes by a single block (M <= ~1e5; not a hot kernel)
 __global__ void __launch_bounds__(1024) map_incr_compact_kernel(const float4* world, const uint8_t* cls,
-                                                                const int* scan_m, float4* out_a, float4* out_b,
-                                                                int* counts /*[2]*/) {
+                                                                const int* scan_m, int min_m, float4* out_a,
+                                                                float4* out_b, int* counts /*[2]*/) {
   __shared__ int sa[1024], sb[1024];
-  const int M = *scan_m;
+  const int M = *scan_m < min_m ? 0 : *scan_m;
   const int chunk = (M + 1023) / 1024;
   const int lo = threadIdx.x * chunk, hi = min(M, lo + chunk);
   int na = 0, nb = 0;
@@ -392,39 +417,58 @@ int map_reset(lio_ctx* c) {
   return LIO_OK;
 }
 
-int map_append_batch(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, const uint8_t* d_flag) {
+// Enqueue only.  n is exact (n_dev == nullptr) or the launch bound of a count that lives on the device.
+int map_append_batch_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base,
+                             const int* id_off_dev, const uint8_t* d_flag) {
   if (n <= 0) return LIO_OK;
   if (n > c->batch_cap) {
     c->err = "insert batch larger than the context's batch capacity";
     return LIO_E_CAPACITY;
   }
   const int grid = (int)((n + 255) / 256);
-  map_reserve_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, d_flag, c->d_batch_slot, c->d_batch_rank);
-  map_grow_kernel<<<grid, 256, 0, c->stream>>>(c->map, (int)n, d_flag, c->d_batch_slot, c->d_batch_rank);
-  map_fill_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, d_flag, c->d_batch_slot, c->d_batch_rank,
+  const BatchDev bd{n_dev, id_off_dev};
+  map_reserve_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, bd, d_flag, c->d_batch_slot, c->d_batch_rank);
+  map_grow_kernel<<<grid, 256, 0, c->stream>>>(c->map, (int)n, bd, d_flag, c->d_batch_slot, c->d_batch_rank);
+  map_fill_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, bd, d_flag, c->d_batch_slot, c->d_batch_rank,
                                                id_base);
   c->launches += 3;
   LIO_CHECK(c, cudaGetLastError());
+  return LIO_OK;
+}
+
+int map_append_batch(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, const uint8_t* d_flag) {
+  if (n <= 0) return LIO_OK;
+  const int rc = map_append_batch_enqueue(c, d_pts, n, nullptr, id_base, nullptr, d_flag);
+  if (rc) return rc;
   return check_map_error(c);
 }
 
-int map_add_downsample(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, int32_t* n_added) {
-  if (n_added) *n_added = 0;
+// Add_Points(downsample_on = true), enqueue only; the number of points added ends up in map.counters[4].
+int map_add_downsample_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base) {
   if (n <= 0) return LIO_OK;
   if (n > c->batch_cap || (uint64_t)n * 2 > c->vox_cap) {
     c->err = "Add_Points batch larger than the context's batch capacity";
     return LIO_E_CAPACITY;
   }
   const int grid = (int)((n + 255) / 256);
+  const BatchDev bd{n_dev, nullptr};
   LIO_CHECK(c, cudaMemsetAsync(c->map.counters + 4, 0, sizeof(uint32_t), c->stream));
   vox_init_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(c->d_vox_key, c->d_vox_best, c->vox_cap);
-  vox_best_kernel<<<grid, 256, 0, c->stream>>>(d_pts, (int)n, c->caps.map_downsample, c->d_vox_key, c->d_vox_best,
+  vox_best_kernel<<<grid, 256, 0, c->stream>>>(d_pts, (int)n, bd, c->caps.map_downsample, c->d_vox_key, c->d_vox_best,
                                                c->vox_cap - 1, c->d_batch_rank /*reused as vslot*/);
-  vox_apply_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, c->caps.map_downsample, c->d_vox_best,
+  vox_apply_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, bd, c->caps.map_downsample, c->d_vox_best,
                                                 c->d_batch_rank, id_base, c->d_batch_flag);
   c->launches += 3;
   LIO_CHECK(c, cudaGetLastError());
-  int rc = map_append_batch(c, d_pts, n, id_base, c->d_batch_flag);
+  return map_append_batch_enqueue(c, d_pts, n, n_dev, id_base, nullptr, c->d_batch_flag);
+}
+
+int map_add_downsample(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, int32_t* n_added) {
+  if (n_added) *n_added = 0;
+  if (n <= 0) return LIO_OK;
+  int rc = map_add_downsample_enqueue(c, d_pts, n, nullptr, id_base);
+  if (rc) return rc;
+  rc = check_map_error(c);
   if (rc) return rc;
   if (n_added) {
     uint32_t v = 0;
@@ -518,35 +562,46 @@ int map_build_scan(lio_ctx* c, const lio_state* x) {
   return LIO_OK;
 }
 
+// map_incremental on the state at c->d_x, enqueue only: classification, ordered compaction, both Add_Points calls.  The
+// class counts stay on the device (d_prep_counters[8..9]) and size the inserts there; bound = upper bound of M.
+int map_incremental_enqueue(lio_ctx* c, float fsm, int ekf_inited, int min_m, int64_t bound) {
+  if (bound <= 0) {  // empty scan: the counts a later report reads must still be this scan's
+    LIO_CHECK(c, cudaMemsetAsync(c->d_prep_counters + 8, 0, 2 * sizeof(int), c->stream));
+    LIO_CHECK(c, cudaMemsetAsync(c->map.counters + 4, 0, sizeof(uint32_t), c->stream));
+    return LIO_OK;
+  }
+  const int grid = (int)((bound + 255) / 256);
+  int* d_counts = c->d_prep_counters + 8;
+  map_incr_classify_kernel<<<grid, 256, 0, c->stream>>>(c->d_body, c->d_scan_m, c->d_x, c->d_near, c->d_near_cnt,
+                                                        ekf_inited, fsm, min_m, c->d_world, c->d_cls);
+  map_incr_compact_kernel<<<1, 1024, 0, c->stream>>>(c->d_world, c->d_cls, c->d_scan_m, min_m, c->d_add_a, c->d_add_b,
+                                                     d_counts);
+  c->launches += 2;
+  int rc = map_add_downsample_enqueue(c, c->d_add_a, bound, d_counts, c->next_id);
+  if (rc) return rc;
+  return map_append_batch_enqueue(c, c->d_add_b, bound, d_counts + 1, c->next_id, d_counts, nullptr);
+}
+
 int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]) {
   if (!c->map_built) {
     c->err = "map_incremental needs a built map";
     return LIO_E_EMPTY_MAP;
   }
-  if (c->scan_m <= 0) {
-    counts[0] = counts[1] = counts[2] = 0;
-    return LIO_OK;
-  }
+  counts[0] = counts[1] = counts[2] = 0;
+  if (c->scan_m <= 0) return LIO_OK;
   LIO_CHECK(c, cudaMemcpyAsync(c->d_x, x, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
-  const int grid = (int)((c->scan_m + 255) / 256);
-  map_incr_classify_kernel<<<grid, 256, 0, c->stream>>>(c->d_body, c->d_scan_m, c->d_x, c->d_near, c->d_near_cnt,
-                                                        ekf_inited, fsm, c->d_world, c->d_cls);
-  int* d_counts = c->d_prep_counters + 8;
-  map_incr_compact_kernel<<<1, 1024, 0, c->stream>>>(c->d_world, c->d_cls, c->d_scan_m, c->d_add_a, c->d_add_b,
-                                                     d_counts);
-  c->launches += 2;
+  int rc = map_incremental_enqueue(c, fsm, ekf_inited, 0, c->scan_m);
+  if (rc) return rc;
   int hc[2] = {0, 0};
-  LIO_CHECK(c, cudaMemcpyAsync(hc, d_counts, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
-  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  uint32_t added = 0;
+  LIO_CHECK(c, cudaMemcpyAsync(hc, c->d_prep_counters + 8, sizeof(hc), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(&added, c->map.counters + 4, sizeof(added), cudaMemcpyDeviceToHost, c->stream));
+  rc = check_map_error(c);  // synchronises
+  if (rc) return rc;
   counts[0] = hc[0];
   counts[1] = hc[1];
-  counts[2] = 0;
-  int rc = map_add_downsample(c, c->d_add_a, hc[0], c->next_id, &counts[2]);
-  if (rc) return rc;
-  c->next_id += hc[0];
-  rc = map_append_batch(c, c->d_add_b, hc[1], c->next_id, nullptr);
-  if (rc) return rc;
-  c->next_id += hc[1];
+  counts[2] = (int32_t)added;
+  c->next_id += hc[0] + hc[1];
   return LIO_OK;
 }
 

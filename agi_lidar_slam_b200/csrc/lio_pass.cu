@@ -45,6 +45,7 @@ __constant__ unsigned char c_is_no[78];  // 1 where the HtH entry is one of the 
 struct PassArgs {
   const float4* body;
   const int* scan_m;
+  int min_m;  // a scan with fewer points is skipped by the main loop (laserMapping.cpp:741-744): treated as empty
   int m_value;             // >= 0: the scan size by value (host-direct path), else *scan_m
   const float4* body_src;  // non-null: pass 0 reads the scan from here (pinned host memory) and leaves a copy in `body`
   MapView map;
@@ -106,6 +107,10 @@ struct PassConst {
   double Rt[9], Rli[9];
 };
 
+__device__ __forceinline__ int scan_size(const PassArgs& a) {
+  const int M = a.m_value >= 0 ? a.m_value : *a.scan_m;
+  return M < a.min_m ? 0 : M;
+}
 __device__ __forceinline__ int pick_group(int M, int nblocks) {
   const long long lanes = (long long)nblocks * THREADS;
   if ((long long)M * 32 <= lanes) return 32;
@@ -362,7 +367,7 @@ __device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout,
 __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool search, int nworkers, unsigned target,
                                                    double* s_blob, double* s_warp) {
   const int tid = threadIdx.x;
-  const int M = a.m_value >= 0 ? a.m_value : *a.scan_m;
+  const int M = scan_size(a);
   const int G = pick_group(M, nworkers);
   const int rows = search ? THREADS / G : pick_rows_cached(M, nworkers);
   const int ntiles = tiles_of(M, rows);
@@ -821,7 +826,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nwo
   const int tid = threadIdx.x;
   const bool from_host = first_pass && a.body_src != nullptr;  // pass 0 always searches
   const float4* body = from_host ? a.body_src : a.body;
-  const int M = a.m_value >= 0 ? a.m_value : *a.scan_m;
+  const int M = scan_size(a);
   stamp(a.dbg, 0, 2);
   const int G = pick_group(M, nworkers);
   const int rows = search ? THREADS / G : pick_rows_cached(M, nworkers);
@@ -1232,6 +1237,7 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.body = c->d_body;
   a.scan_m = c->d_scan_m;
   a.m_value = -1;
+  a.min_m = c->min_m;
   a.body_src = nullptr;
   a.map = c->map;
   a.near_pts = c->d_near;

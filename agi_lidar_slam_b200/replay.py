@@ -3,17 +3,17 @@
 One `LioReplay.process(meas)` call is one iteration of that loop for one synchronised MeasureGroup (common_lib.h:40-49:
 a scan, its IMU samples, lidar_beg_time / lidar_end_time, as sync_packages (:218-275) hands them over):
 
-    first scan: remember first_lidar_time, continue                       (:711-716)
-    ImuProcess::Process  -> IMU_init | forward propagation (host)         (:719)        lio_imu_process
-    skip while the filter initialises (empty undistorted cloud)           (:722-725)
-    flg_EKF_inited                                                        (:731-733)
-    UndistortPcl per-point loop + VoxelGrid surf filter (fused, device)   (:719,737-738) lio_scan_preprocess_resident
+    first scan: remember first_lidar_time, continue                       (:711-716)    host
+    ImuProcess::Process  -> IMU_init | forward propagation                (:719)        host: lio_imu_process
+    skip while the filter initialises (empty undistorted cloud)           (:722-725)    host
+    flg_EKF_inited                                                        (:731-733)    host
+    lasermap_fov_segment: slide the local-map box, box-delete behind it   (:736, :309-365)  lio_map_delete_boxes
+    -- the rest is ONE call with one host synchronisation: lio_scan_step -------------------------------------------
+    UndistortPcl per-point loop + VoxelGrid surf filter (fused)           (:719,737-738)
     fewer than 5 points -> skip                                           (:741-744)
-    empty map -> pointBodyToWorld + Build, continue                       (:747-758)    lio_map_build_scan
-    update_iterated_dyn_share_modified                                    (:772-774)    lio_update_scan
-    map_incremental                                                       (:785)        lio_map_incremental
-
-    lasermap_fov_segment: slide the local-map box, box-delete behind it  (:736, :309-365)  lio_map_delete_boxes
+    empty map -> pointBodyToWorld + Build, continue                       (:747-758)
+    update_iterated_dyn_share_modified                                    (:772-774)
+    map_incremental                                                       (:785)
 """
 from __future__ import annotations
 
@@ -79,7 +79,7 @@ class LioReplay:
         c = self.cfg
         self.imu.set_param(c.extrinsic_T, c.extrinsic_R, (c.gyr_cov,) * 3, (c.acc_cov,) * 3, (c.b_gyr_cov,) * 3,
                            (c.b_acc_cov,) * 3)
-        self.x = default_state()
+        self.x = default_state()  # contiguous float64: the step calls update x and P in place
         self.P = np.eye(24)
         self.first_scan = True
         self.first_lidar_time = 0.0
@@ -126,9 +126,9 @@ class LioReplay:
         self.n_box_deleted += n
         return n
 
-    def process(self, meas: MeasureGroup):
-        """Returns the state after this scan (the odometry the reference publishes), or None when the scan is skipped."""
-        c = self.cfg
+    def host_stage(self, meas: MeasureGroup):
+        """The host part of one main-loop iteration: bookkeeping, IMU initialisation / forward propagation, the sliding
+        local-map box.  Returns the IMU poses of the scan when the device part is due, else None."""
         if self.first_scan:
             self.first_lidar_time = meas.lidar_beg_time
             self.first_scan = False
@@ -142,19 +142,62 @@ class LioReplay:
         if initialising:
             self.log.append(dict(status="imu-init"))
             return None
-        ekf_inited = not ((meas.lidar_beg_time - self.first_lidar_time) < INIT_TIME)
+        self._ekf_inited = not ((meas.lidar_beg_time - self.first_lidar_time) < INIT_TIME)
         self._lasermap_fov_segment()
-        m = self.ctx.scan_preprocess(meas.lidar, poses, self.x, c.filter_size_surf, resident=True)
-        if m < 5:
-            self.log.append(dict(status="few-points", m=m))
+        return poses
+
+    def adopt(self, rep):
+        """Book a lio_scan_report: log it, return the odometry (or None when the scan was skipped)."""
+        if rep.status == _cabi.SCAN_FEW_POINTS:
+            self.log.append(dict(status="few-points", m=int(rep.m)))
             return None
-        if not self.map_built:
-            self.ctx.map_build_scan(self.x)
+        if rep.status == _cabi.SCAN_MAP_BUILT:
             self.map_built = True
-            self.log.append(dict(status="map-built", m=m))
+            self.log.append(dict(status="map-built", m=int(rep.m)))
             return None
-        self.x, self.P, nv, npass = self.ctx.update_scan(self.x, self.P, LASER_POINT_COV, c.max_iteration,
-                                                         c.extrinsic_est)
-        counts = self.ctx.map_incremental(self.x, c.filter_size_map, ekf_inited)
-        self.log.append(dict(status="ok", m=m, n_valid=nv, n_passes=npass, counts=counts.tolist()))
+        self.log.append(dict(status="ok", m=int(rep.m), n_valid=int(rep.n_valid), n_passes=int(rep.n_passes),
+                             counts=list(rep.counts)))
         return self.x.copy()
+
+    def process(self, meas: MeasureGroup):
+        """Returns the state after this scan (the odometry the reference publishes), or None when the scan is skipped.
+        The device part is ONE C-ABI call (lio_scan_step) with one host synchronisation."""
+        poses = self.host_stage(meas)
+        if poses is None:
+            return None
+        c = self.cfg
+        rep = self.ctx.scan_step(meas.lidar, poses, self.x, self.P, c.filter_size_surf, c.filter_size_map,
+                                 LASER_POINT_COV, c.max_iteration, c.extrinsic_est, self._ekf_inited)
+        return self.adopt(rep)
+
+
+def process_many(replays, meass):
+    """One main-loop iteration of several INDEPENDENT sequences on one GPU (BASELINE.json config 4): host stage and
+    enqueue of the preprocessing per sequence (each on its context's stream), then the updates of all sequences that are
+    due in ONE cooperative launch (lio_update_enqueue_multi, <= 8 per launch), then map growth per sequence, and one
+    synchronisation per sequence at the very end.  All replays must share max_iteration and extrinsic_est.  Returns the
+    list of per-sequence results of LioReplay.process."""
+    out = [None] * len(replays)
+    begun, due = [], []
+    for k, (r, m) in enumerate(zip(replays, meass)):
+        poses = r.host_stage(m)
+        if poses is None:
+            continue
+        begun.append(k)
+        if r.ctx.scan_step_begin(m.lidar, poses, r.x, r.P, r.cfg.filter_size_surf):
+            due.append(k)
+    if due:
+        cfg = replays[due[0]].cfg
+        for a in range(0, len(due), 8):
+            grp = [replays[k].ctx for k in due[a:a + 8]]
+            if len(grp) == 1:
+                grp[0].update_enqueue(LASER_POINT_COV, cfg.max_iteration, cfg.extrinsic_est, from_snapshot=True)
+            else:
+                _cabi.update_enqueue_multi(grp, LASER_POINT_COV, cfg.max_iteration, cfg.extrinsic_est,
+                                           from_snapshot=True)
+        for k in due:
+            replays[k].ctx.scan_step_end(replays[k].cfg.filter_size_map, replays[k]._ekf_inited)
+    for k in begun:
+        r = replays[k]
+        out[k] = r.adopt(r.ctx.scan_step_finish(r.x, r.P))
+    return out

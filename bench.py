@@ -47,9 +47,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="os1_128_2m", choices=["os1_128_2m", "sharded"],
-                    help="os1_128_2m: config 3, one independent sequence per GPU (no collective); sharded: config 5, "
-                         "one map cut into x-slabs over the GPUs, NCCL all-reduce of the 92-double blob per pass")
+    ap.add_argument("--workload", default="os1_128_2m",
+                    choices=["os1_128_2m", "sharded", "avia_200k", "vlp16_traj", "os1_64_seqs"],
+                    help="os1_128_2m: config 3 (the headline), one independent sequence per GPU (no collective); sharded: "
+                         "config 5, one map cut into x-slabs over the GPUs, 92-double blob exchanged per pass; avia_200k: "
+                         "config 1, the same update on a 24k-ray Avia scan vs a 200k-point map; vlp16_traj: config 2, the "
+                         "whole per-scan main loop (propagation, undistort + voxel filter, update, map growth) along a "
+                         "VLP-16 trajectory; os1_64_seqs: config 4, the same loop for --seqs-per-gpu OS1-64 sequences "
+                         "per GPU, their updates in one cooperative launch per scan")
+    ap.add_argument("--seqs-per-gpu", type=int, default=8)
     ap.add_argument("--map-points", type=int, default=2_000_000)
     ap.add_argument("--rings", type=int, default=128)
     ap.add_argument("--cols", type=int, default=1024)
@@ -73,9 +79,31 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------ workload
+def workload_name(args, n_map):
+    if args.workload == "avia_200k":
+        return "Avia-like 24,000-ray scan vs %d-point hall map, leaf 0.5, max_iter 4, 1 sequence per GPU" % n_map
+    return "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4, 1 sequence per GPU" % (args.rings, args.cols,
+                                                                                                 n_map)
+
+
 def make_workload(args, rank):
     from agi_lidar_slam_b200 import synth
 
+    if args.workload == "avia_200k":  # config 1
+        scene = synth.hall_scene(half=110.0, height=10.0)
+        mp = synth.sample_map(scene, 200_000, 1001)
+        scans = []
+        for k in range(args.poses):
+            rng = np.random.default_rng(1001 + 17 * k + 1)
+            pos = np.array([rng.uniform(-20, 20), rng.uniform(-20, 20), 3.0])
+            R = synth.rot_zyx(rng.uniform(-np.pi, np.pi), 0.45 + rng.normal(0, 0.02), rng.normal(0, 0.02))
+            d = synth.avia_dirs(24_000, 1002 + k)
+            scan = synth.static_scan(scene, d, np.arange(24_000) / 240000.0 * 1000.0, pos, R, 100.0,
+                                     1001 + 1000 * rank + k)
+            x_true = synth.make_state(pos=pos, R=R)
+            scans.append(dict(scan=scan, x_true=x_true,
+                              x_prior=synth.perturbed_prior(x_true, 1001 + 1000 * rank + 31 * k)))
+        return dict(scene=scene, map=mp, scans=scans, P=synth.init_P(), leaf=0.5, max_iter=4, ext=False)
     scene, mp = synth.city_map(args.map_points, 3003)
     scans = []
     d, col = synth.spinning_dirs(args.rings, args.cols, -22.5, 22.5)
@@ -173,8 +201,35 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+class stdout_to_stderr:
+    """The reference ikd-Tree printf()s thread start/stop notices; stdout carries exactly one JSON line, so whatever the
+    CPU leg prints at the C level goes to stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:  # noqa: BLE001
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_arm(wl, steps, warmup, seconds_budget, threads=None):
     """The reference CPU path: reference ikd-Tree (oracle/_ref) + restated update loop.  Returns a dict with scans/s."""
+    with stdout_to_stderr():
+        r = cpu_arm_inner(wl, steps, warmup, seconds_budget, threads)
+        import gc
+        gc.collect()  # the tree's destructor prints too
+    return r
+
+
+def cpu_arm_inner(wl, steps, warmup, seconds_budget, threads=None):
     from oracle import pyoracle as orc
 
     threads = threads or (os.cpu_count() or 1)
@@ -218,6 +273,134 @@ def cpu_arm(wl, steps, warmup, seconds_budget, threads=None):
                 "oracle port (hashed-grid kNN + restated update loop)", build_s=build_s,
                 matched_pts_per_s=float(np.sum(nvalid)) / tot, m=int(np.mean([len(b) for b in bodies])),
                 passes=float(np.mean(npass)))
+
+
+# ------------------------------------------------------------------------------------------ trajectories (configs 2, 4)
+TRAJ = {"vlp16_traj": dict(rings=16, cols=1800, fov=(-15.0, 15.0), max_range=100.0, seed=2002, sensor="VLP-16"),
+        "os1_64_seqs": dict(rings=64, cols=1024, fov=(-22.5, 22.5), max_range=120.0, seed=4000, sensor="OS1-64")}
+LEAD = 4  # scans the main loop spends on first-scan bookkeeping, IMU initialisation and the first-scan map build
+
+
+def traj_sequences(args, rank, n_seq, n_scans):
+    from agi_lidar_slam_b200 import synth
+
+    t = TRAJ[args.workload]
+    return [synth.sequence(n_scans, t["seed"] + rank * n_seq + k, rings=t["rings"], cols=t["cols"], fov=t["fov"],
+                           max_range=t["max_range"]) for k in range(n_seq)]
+
+
+def traj_cpu_arm(seq, warmup, steps, seconds_budget, threads=None):
+    """The same main loop on the CPU oracle (tests/replay_oracle.py: restated stages, hashed-grid map port)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle import pyoracle as orc
+    from replay_oracle import OracleReplay
+
+    orc.build()
+    threads = threads or (os.cpu_count() or 1)
+    rep = OracleReplay(orc, max_iteration=3, threads=threads)
+    t_sum, n = 0.0, 0
+    t_start = time.perf_counter()
+    for j, m in enumerate(seq):
+        t0 = time.perf_counter()
+        r = rep.process(m)
+        dt = time.perf_counter() - t0
+        if j >= LEAD + warmup and r is not None:
+            t_sum += dt
+            n += 1
+        if n >= steps or (n >= 3 and time.perf_counter() - t_start > seconds_budget):
+            break
+    return dict(value=n / t_sum, ms_per_step=1000 * t_sum / n, steps=n, cores=threads, kind="port",
+                kind_detail="oracle port of the whole main loop (restated IMU propagation, undistort, VoxelGrid, update, "
+                            "map_incremental on the hashed-grid map port)")
+
+
+def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
+    """Configs 2 and 4: one step = one scan of every sequence through the whole main loop of laserMapping.cpp:702-800.
+    The raw scan and the IMU samples come from host memory every step by nature, so `value` is host-timed end to end
+    (= `e2e`); max over ranks; the sequences of a GPU share one cooperative update launch per scan."""
+    from agi_lidar_slam_b200.replay import LioReplay, MeasureGroup, ReplayConfig, process_many
+
+    t = TRAJ[args.workload]
+    n_seq = 1 if args.workload == "vlp16_traj" else max(1, args.seqs_per_gpu)
+    n_scans = LEAD + args.warmup + args.steps
+    seqs = traj_sequences(args, rank, n_seq, n_scans)
+    mgs = [[MeasureGroup(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"]) for m in s] for s in seqs]
+    ctxs = [_cabi.Context(local, max_scan_points=1 << 17, max_down_points=1 << 16, max_map_points=1 << 21)
+            for _ in range(n_seq)]
+    reps = [LioReplay(c, ReplayConfig(max_iteration=3)) for c in ctxs]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local)
+    launches0 = 0
+    for j in range(n_scans):
+        if j == LEAD + args.warmup:
+            barrier()
+            sampler.start()
+            launches0 = sum(c.launch_count for c in ctxs)
+            t0 = time.perf_counter()
+        if n_seq == 1:
+            reps[0].process(mgs[0][j])
+        else:
+            process_many(reps, [mg[j] for mg in mgs])
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    launches = sum(c.launch_count for c in ctxs) - launches0
+    barrier()
+    clocks = sampler.stop()
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    logs = [e for r in reps for e in r.log[-args.steps:]]
+    ok = [e for e in logs if e["status"] == "ok"]
+    n_upd = len(ok)
+    M = float(np.mean([e["m"] for e in ok]))
+    passes = float(np.mean([e["n_passes"] for e in ok]))
+    n_raw = float(np.mean([len(m["lidar"]) for s in seqs for m in s[-args.steps:]]))
+    value = world * n_seq * args.steps / dt
+    b_scan = 16.0 * n_raw + 16.0 * M + 116.0 * M * passes  # SURVEY.md §8d
+    peak, peak_src = measured_peak()
+    achieved = b_scan * (n_seq * args.steps / dt) / 1e9
+    n_imu = float(np.mean([len(m["imu"]) for s in seqs for m in s[-args.steps:]]))
+    line = {
+        "metric": "scans/sec through the whole per-scan main loop (propagation + undistort + voxel + IESKF update + map growth)",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": "%s %dx%d trajectory (10 Hz scans, 200 Hz IMU), %d sequence(s) per GPU, growing map, leaf "
+                   "0.5/0.5, max_iter 3" % (t["sensor"], t["rings"], t["cols"], n_seq), "N_raw": n_raw, "M": M,
+                   "passes_per_scan": passes, "updates_in_timed_region": n_upd,
+                   "l2": "not flushed: every scan is new data from the host, the map is the sequence's own growing map",
+                   "timing": "host clock around the loop (host stages are on the path), device synchronised both sides"},
+        "matched_pts_per_s": float(np.sum([e["n_valid"] for e in ok])) * world / dt,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(n_seq * (16 * n_raw + 200 * (n_imu + 1) + 602 * 8)),
+                "d2h_bytes_per_step": int(n_seq * (607 * 8 + 8 + 12))},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "whole scan: undistort/voxel kernels + update_kernel + map growth",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_scan": b_scan,
+                     "note": "B_scan = 16N + 16M + 116*M*I (SURVEY.md §8d); latency- and host-bound"},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = traj_cpu_arm(seqs[0], args.warmup, args.steps, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                "kind_detail": r["kind_detail"],
+                                "sample": "%d scans of sequence 0 through the same loop" % r["steps"]}
+        r3 = traj_cpu_arm(seqs[0], args.warmup, args.steps, min(8.0, args.cpu_seconds), threads=3)
+        line["cpu_baseline_3_threads"] = {"value": r3["value"], "unit": UNIT, "cores": 3}
+    if rank == 0:
+        print(json.dumps(line))
+    for c in ctxs:
+        c.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 
 # ------------------------------------------------------------------------------------------ sharded map (config 5)
@@ -345,14 +528,26 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        if args.workload in TRAJ:
+            seq = traj_sequences(args, 0, 1, LEAD + args.warmup + args.steps)[0]
+            r = traj_cpu_arm(seq, args.warmup, args.steps, seconds_budget=150.0)
+            print(json.dumps({
+                "impl": "reference", "metric": "scans/sec through the whole per-scan main loop (propagation + undistort + "
+                "voxel + IESKF update + map growth)", "value": r["value"], "unit": UNIT, "n_gpus": n_gpus,
+                "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": "%s trajectory, 1 sequence, CPU" % TRAJ[args.workload]["sensor"]},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "kind_detail": r["kind_detail"], "sample": "%d scans" % r["steps"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return 0
         wl = make_workload(args, 0)
         r = cpu_arm(wl, args.steps, args.warmup, seconds_budget=150.0)
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n_gpus,
             "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4, 1 sequence per GPU" %
-                       (args.rings, args.cols, args.map_points), "M": r["m"], "passes_per_scan": r["passes"]},
+            "config": {"workload": workload_name(args, len(wl["map"])), "M": r["m"], "passes_per_scan": r["passes"]},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                              "kind_detail": r["kind_detail"],
                              "sample": "%d whole updates of the bench scans (tree build %.1f s untimed)" %
@@ -377,6 +572,8 @@ def main():
 
     if args.workload == "sharded":
         return sharded_main(args, rank, world, local, dev, torch, dist, _cabi)
+    if args.workload in TRAJ:
+        return traj_main(args, rank, world, local, dev, torch, dist, _cabi)
 
     wl = make_workload(args, rank)
     n_map = len(wl["map"])
@@ -462,7 +659,6 @@ def main():
     ms_warm, _, _ = resident_run(args.steps, 0, False)
     barrier()
     ms_warm = max_over_ranks(ms_warm)
-    clocks = sampler.stop()
     value = n_gpus * args.steps / (ms_cold / 1000.0)
     value_warm = n_gpus * args.steps / (ms_warm / 1000.0)
     matched = sum_over_ranks(float(nvalid)) / (ms_cold / 1000.0)
@@ -493,6 +689,7 @@ def main():
     e2e_ms = max_over_ranks(e2e_run(args.steps, 0))
     barrier()
     e2e_value = n_gpus * args.steps / (e2e_ms / 1000.0)
+    clocks = sampler.stop()  # sampled over both timed regions (device-resident and end-to-end)
     h2d = M * 16 + 602 * 8  # scan (one copy) + prior {x, P} (kernel parameters)
     d2h = 607 * 8  # posterior {x, P, loop state} + sequence word, written by the kernel into mapped pinned memory
 
@@ -594,11 +791,10 @@ def main():
                                        "search_GBps_cold": 116.0 * m0 / (t_search_cold * 1e-3) / 1e9}}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_cold / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC if args.workload != "avia_200k" else METRIC.replace("OS1-128", "Avia"), "value": value,
+        "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_cold / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": "OS1-128 %dx%d scan vs %d-point city map, leaf 0.5, max_iter 4, 1 sequence per GPU" %
-                   (args.rings, args.cols, n_map), "N_raw": int(np.mean([len(r) for r in raws])), "M": M,
+        "config": {"workload": workload_name(args, n_map), "N_raw": int(np.mean([len(r) for r in raws])), "M": M,
                    "passes_per_scan": passes_per_scan, "l2": "flushed (384 MiB write) before every timed step",
                    "map_build_s": map_build_s},
         "value_l2_warm": value_warm, "matched_pts_per_s": matched,

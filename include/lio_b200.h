@@ -187,6 +187,32 @@ int lio_state_download(lio_ctx* ctx, lio_state* x, double P[576], int32_t* n_val
 /* Enqueue the whole update (one persistent cooperative kernel) on the context stream; no host sync.  from_snapshot != 0 first restores the state
  * uploaded by lio_state_upload (so a benchmark can repeat the same update). */
 int lio_update_enqueue(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, int from_snapshot);
+/* One iteration of the reference main loop for one scan (src/laserMapping.cpp:737-785): VoxelGrid(UndistortPcl back half),
+ * `feats_down_size < 5 -> continue` (:741-744), first-scan Build (:747-758), update_iterated_dyn_share_modified (:772-774),
+ * map_incremental (:785) -- enqueued back to back on the context's stream.  M, the map_incremental class counts and the
+ * insert sizes stay on the device; the host synchronises ONCE, at the end, and gets everything in the report.
+ * x_io / P_io: the propagated state at scan end (what lio_imu_process returned) in, the posterior out (untouched when
+ * the scan is skipped).  raw_pts / poses as for lio_scan_preprocess. */
+typedef struct lio_scan_report {
+  int64_t m;          /* feats_down_size */
+  int32_t status;     /* LIO_SCAN_* */
+  int32_t n_valid;    /* effct_feat_num of the last pass */
+  int32_t n_passes;
+  int32_t counts[3];  /* map_incremental: PointToAdd, PointNoNeedDownsample, points Add_Points(downsample) inserted */
+} lio_scan_report;
+enum { LIO_SCAN_UPDATED = 0, LIO_SCAN_FEW_POINTS = 1, LIO_SCAN_MAP_BUILT = 2 };
+int lio_scan_step(lio_ctx*, const void* raw_pts, int64_t n, int stride_bytes, const lio_pose6d* imu_poses, int n_poses,
+                  lio_state* x_io, double P_io[576], float leaf_surf, float leaf_map, double R, int max_iter,
+                  int extrinsic_est, int ekf_inited, lio_scan_report* report);
+/* The same in three enqueue-only pieces plus the synchronising one, for hosts that step several sequences together:
+ *   begin (preprocessing + prior; *update_due = 0 on the first-scan branch, which is complete after begin)
+ *   -> lio_update_enqueue / lio_update_enqueue_multi with from_snapshot = 1 for the contexts that are due
+ *   -> end (map growth from the posterior + report copies)  -> finish (synchronise, bookkeeping, report). */
+int lio_scan_step_begin(lio_ctx*, const void* raw_pts, int64_t n, int stride_bytes, const lio_pose6d* imu_poses,
+                        int n_poses, const lio_state* x, const double P[576], float leaf_surf, int32_t* update_due);
+int lio_scan_step_end(lio_ctx*, float leaf_map, int ekf_inited);
+int lio_scan_step_finish(lio_ctx*, lio_state* x_out, double P_out[576], lio_scan_report* report);
+
 /* n <= 8 INDEPENDENT updates -- different sequences, each context with its own map, scan and filter state (BASELINE.json
  * config 4) -- in ONE cooperative launch on ctxs[0]'s stream: the persistent grid is cut into n slices, each with its own
  * workers and solver block.  A single update is latency-bound and leaves most of the GPU idle; slices fill it.  All

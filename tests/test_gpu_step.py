@@ -1,0 +1,99 @@
+"""lio_scan_step: one main-loop iteration (laserMapping.cpp:737-785) enqueued with a single host synchronisation must
+give exactly what the same stages give when the host drives them one call at a time."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx():
+    from agi_lidar_slam_b200 import _cabi
+
+    return _cabi.Context(0, max_scan_points=1 << 16, max_down_points=1 << 15, max_map_points=1 << 19)
+
+
+def _staged(rep, meas, poses):
+    """The device part of one iteration through the per-stage entry points (what lio_scan_step fuses)."""
+    c, ctx = rep.cfg, rep.ctx
+    m = ctx.scan_preprocess(meas.lidar, poses, rep.x, c.filter_size_surf, resident=True)
+    if m < 5:
+        return dict(status="few-points", m=m)
+    if not rep.map_built:
+        ctx.map_build_scan(rep.x)
+        rep.map_built = True
+        return dict(status="map-built", m=m)
+    rep.x, rep.P, nv, npass = ctx.update_scan(rep.x, rep.P, 0.001, c.max_iteration, c.extrinsic_est)
+    counts = ctx.map_incremental(rep.x, c.filter_size_map, rep._ekf_inited)
+    return dict(status="ok", m=m, n_valid=nv, n_passes=npass, counts=counts.tolist())
+
+
+@pytest.mark.parametrize("ext", [False, True])
+def test_scan_step_equals_staged_calls(ext):
+    from agi_lidar_slam_b200 import synth
+    from agi_lidar_slam_b200.replay import LioReplay, MeasureGroup, ReplayConfig
+
+    seq = synth.sequence(16, 2002, rings=16, cols=900)
+    a_ctx, b_ctx = _ctx(), _ctx()
+    try:
+        A = LioReplay(a_ctx, ReplayConfig(max_iteration=3, extrinsic_est=ext))
+        B = LioReplay(b_ctx, ReplayConfig(max_iteration=3, extrinsic_est=ext))
+        n_ok = 0
+        few = np.array([[1.0, 0.0, 0.0, 0.0], [2.0, 0.1, 0.0, 1.0], [3.0, 0.0, 0.2, 2.0]], np.float32)
+        for j, m in enumerate(seq):
+            lidar = few if j == 9 else m["lidar"]  # one scan of three points in the middle: skipped by both
+            mg = MeasureGroup(lidar, m["imu"], m["lidar_beg_time"], m["lidar_end_time"])
+            pa = A.host_stage(mg)
+            rb = B.process(mg)
+            if pa is None:
+                assert rb is None
+                continue
+            la = _staged(A, mg, pa)
+            lb = B.log[-1]
+            assert la == lb, (j, la, lb)
+            assert np.array_equal(A.x, B.x) and np.array_equal(A.P, B.P), j
+            if la["status"] == "ok":
+                n_ok += 1
+                assert np.array_equal(rb, A.x)
+            if j == 9:
+                assert la["status"] == "few-points" and la["m"] == 3
+        assert n_ok >= 8
+        ax, ai = a_ctx.map_dump()
+        bx, bi = b_ctx.map_dump()
+        assert np.array_equal(ai, bi) and np.array_equal(ax.view(np.uint32), bx.view(np.uint32))
+        assert a_ctx.map_size() == b_ctx.map_size()
+    finally:
+        a_ctx.close()
+        b_ctx.close()
+
+
+def test_scan_step_empty_scan_and_errors():
+    from agi_lidar_slam_b200 import _cabi, synth
+    from agi_lidar_slam_b200.replay import default_state
+
+    cfg = synth.small_config()
+    ctx = _ctx()
+    try:
+        x, P = default_state(), np.eye(24) * 0.01
+        x[0:3] = cfg["x_true"][0:3]
+        x[3:7] = cfg["x_true"][3:7]
+        # first call on an empty map: builds it from the scan
+        rep = ctx.scan_step(cfg["scan"], None, x, P, 0.5, 0.5)
+        assert rep.status == _cabi.SCAN_MAP_BUILT and rep.m > 100
+        total0 = ctx.map_size()
+        x0, P0 = x.copy(), P.copy()
+        # an empty scan and a 4-point scan: skipped, nothing changes
+        for n in (0, 4):
+            rep = ctx.scan_step(cfg["scan"][:n].copy(), None, x, P, 0.5, 0.5)
+            assert rep.status == _cabi.SCAN_FEW_POINTS and rep.m <= n
+            assert np.array_equal(x, x0) and np.array_equal(P, P0) and ctx.map_size() == total0
+        # and the next full scan updates as usual
+        rep = ctx.scan_step(cfg["scan"], None, x, P, 0.5, 0.5)
+        assert rep.status == _cabi.SCAN_UPDATED and rep.n_valid > 100 and rep.n_passes >= 2
+        assert not np.array_equal(P, P0)
+        # end / finish without begin
+        with pytest.raises(_cabi.LioError):
+            ctx.scan_step_end(0.5)
+        with pytest.raises(_cabi.LioError):
+            ctx.scan_step_finish(x, P)
+    finally:
+        ctx.close()

@@ -79,3 +79,38 @@ def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_
     print(f"{name}: {n_upd} updates, worst |dpos| {worst_pos:.2e} m, worst |drot| {worst_rot:.2e} rad, worst rel |dP| "
           f"{worst_P:.2e}, bit-identical discrete outcomes in {exact_scans}/{n_upd} scans, map resyncs {map_resync}, "
           f"map {map_valid} pts, {gpu.n_box_deleted} points box-deleted")
+
+
+def test_process_many_equals_independent_replays():
+    """Config 4 shape on one GPU: three independent sequences stepped together (updates in one cooperative launch per
+    scan, replay.process_many) follow the same trajectories as the same sequences replayed one by one.  The reference
+    loop amplifies rounding differences (~5x per scan), so the horizon is short and the tolerance is 1e-6."""
+    from agi_lidar_slam_b200 import _cabi, synth
+    from agi_lidar_slam_b200.replay import LioReplay, MeasureGroup, ReplayConfig, process_many
+
+    n_seq, n_scans = 3, 12
+    seqs = [synth.sequence(n_scans, 4000 + k, rings=32, cols=512, fov=(-22.5, 22.5), max_range=120.0) for k in range(n_seq)]
+    mg = [[MeasureGroup(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"]) for m in s] for s in seqs]
+
+    def contexts():
+        return [_cabi.Context(0, max_scan_points=1 << 16, max_down_points=1 << 15, max_map_points=1 << 19)
+                for _ in range(n_seq)]
+
+    solo = []
+    for k, c in enumerate(contexts()):
+        r = LioReplay(c, ReplayConfig(max_iteration=3))
+        solo.append([r.process(m) for m in mg[k]])
+        c.close()
+    ctxs = contexts()
+    reps = [LioReplay(c, ReplayConfig(max_iteration=3)) for c in ctxs]
+    n_upd = 0
+    for j in range(n_scans):
+        res = process_many(reps, [mg[k][j] for k in range(n_seq)])
+        for k in range(n_seq):
+            assert (res[k] is None) == (solo[k][j] is None)
+            if res[k] is not None:
+                n_upd += 1
+                assert np.abs(res[k] - solo[k][j]).max() < 1e-6
+    assert n_upd >= n_seq * (n_scans - 4)
+    for c in ctxs:
+        c.close()
