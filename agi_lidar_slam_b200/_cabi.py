@@ -45,6 +45,31 @@ class ScanReport(C.Structure):
 SCAN_UPDATED, SCAN_FEW_POINTS, SCAN_MAP_BUILT = 0, 1, 2
 
 
+class SeqConfig(C.Structure):
+    """lio_seq_config (include/lio_b200.h)."""
+    _fields_ = [("filter_size_surf", C.c_float), ("filter_size_map", C.c_float), ("max_iteration", C.c_int32),
+                ("extrinsic_est", C.c_int32), ("extrinsic_T", C.c_double * 3), ("extrinsic_R", C.c_double * 9),
+                ("gyr_cov", C.c_double), ("acc_cov", C.c_double), ("b_gyr_cov", C.c_double), ("b_acc_cov", C.c_double),
+                ("cube_len", C.c_double), ("det_range", C.c_double), ("laser_point_cov", C.c_double)]
+
+
+class SeqInput(C.Structure):
+    """lio_seq_input: one MeasureGroup."""
+    _fields_ = [("lidar", C.c_void_p), ("n", C.c_int64), ("stride_bytes", C.c_int32), ("n_imu", C.c_int32),
+                ("imu", C.c_void_p), ("lidar_beg_time", C.c_double), ("lidar_end_time", C.c_double)]
+
+
+class SeqResult(C.Structure):
+    """lio_seq_result."""
+    _fields_ = [("status", C.c_int32), ("n_valid", C.c_int32), ("n_passes", C.c_int32), ("counts", C.c_int32 * 3),
+                ("m", C.c_int64), ("n_box_deleted", C.c_int64), ("x", C.c_double * 26)]
+
+
+SEQ_UPDATED, SEQ_FEW_POINTS, SEQ_MAP_BUILT, SEQ_FIRST_SCAN, SEQ_NO_IMU, SEQ_IMU_INIT = range(6)
+SEQ_STATUS_NAMES = {SEQ_UPDATED: "ok", SEQ_FEW_POINTS: "few-points", SEQ_MAP_BUILT: "map-built", SEQ_FIRST_SCAN: "first",
+                    SEQ_NO_IMU: "no-imu", SEQ_IMU_INIT: "imu-init"}
+
+
 class Caps(C.Structure):
     _fields_ = [
         ("max_scan_points", C.c_int64),
@@ -78,6 +103,8 @@ EXPORTS = [
     "lio_update_enqueue_sharded", "lio_peer_status", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
     "lio_imu_proc_init", "lio_imu_set_param", "lio_imu_process",
+    "lio_seq_default_config", "lio_seq_create", "lio_seq_destroy", "lio_seq_process", "lio_seq_process_many",
+    "lio_seq_get_state", "lio_seq_set_state", "lio_seq_local_map",
 ]  # fmt: skip
 
 _lib = None
@@ -151,6 +178,14 @@ def load_library() -> C.CDLL:
         "lio_imu_proc_init": (None, [vp]),
         "lio_imu_set_param": (None, [vp, vp, vp, vp, vp, vp, vp]),
         "lio_imu_process": (C.c_int, [vp, vp, C.c_int, f64, f64, vp, vp, vp, C.c_int, P(C.c_int), P(C.c_int)]),
+        "lio_seq_default_config": (None, [P(SeqConfig)]),
+        "lio_seq_create": (C.c_int, [vp, P(SeqConfig), P(vp)]),
+        "lio_seq_destroy": (None, [vp]),
+        "lio_seq_process": (C.c_int, [vp, P(SeqInput), P(SeqResult)]),
+        "lio_seq_process_many": (C.c_int, [vp, C.c_int, vp, vp]),
+        "lio_seq_get_state": (C.c_int, [vp, vp, vp]),
+        "lio_seq_set_state": (C.c_int, [vp, vp, vp]),
+        "lio_seq_local_map": (C.c_int, [vp, vp, P(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == header/library drift
@@ -485,6 +520,84 @@ class Context:
         counts = np.zeros(3, np.int32)
         self._check(self._lib.lio_map_incremental(self._h, _ptr(x), filter_size_map, int(ekf_inited), _ptr(counts)))
         return counts
+
+
+class Sequence:
+    """One lio_seq: the per-scan main loop (laserMapping.cpp:702-800) of one sequence on one Context, in native code."""
+
+    def __init__(self, ctx: Context, **cfg):
+        self._lib = load_library()
+        self.ctx = ctx
+        self.cfg = SeqConfig()
+        self._lib.lio_seq_default_config(C.byref(self.cfg))
+        for k, v in cfg.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError(f"unknown lio_seq_config field {k}")
+            if k in ("extrinsic_T", "extrinsic_R"):
+                v = np.asarray(v, np.float64).ravel()
+                v = (C.c_double * len(v))(*v)
+            setattr(self.cfg, k, v)
+        self._h = C.c_void_p()
+        rc = self._lib.lio_seq_create(ctx._h, C.byref(self.cfg), C.byref(self._h))
+        if rc:
+            raise LioError(rc, "lio_seq_create")
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            self._lib.lio_seq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def input(self, lidar, imu, lidar_beg_time, lidar_end_time) -> SeqInput:
+        """Pack one MeasureGroup; the arrays must stay alive until the call that consumes the SeqInput returns."""
+        pts, stride = _points(lidar)
+        imu = np.ascontiguousarray(imu, np.float64).reshape(-1, 7)
+        si = SeqInput(pts.ctypes.data, pts.shape[0], stride, imu.shape[0], imu.ctypes.data if imu.shape[0] else None,
+                      float(lidar_beg_time), float(lidar_end_time))
+        si._keep = (pts, imu)
+        return si
+
+    def process(self, lidar, imu, lidar_beg_time, lidar_end_time) -> SeqResult:
+        si = self.input(lidar, imu, lidar_beg_time, lidar_end_time)
+        res = SeqResult()
+        rc = self._lib.lio_seq_process(self._h, C.byref(si), C.byref(res))
+        if rc:
+            raise LioError(rc, (self._lib.lio_last_error(self.ctx._h) or b"").decode())
+        return res
+
+    def get_state(self):
+        x, P = np.zeros(STATE_DOUBLES), np.zeros((24, 24))
+        self._lib.lio_seq_get_state(self._h, _ptr(x), _ptr(P))
+        return x, P
+
+    def set_state(self, x, P):
+        x = _state(x)
+        P = np.ascontiguousarray(P, np.float64).reshape(576)
+        self._lib.lio_seq_set_state(self._h, _ptr(x), _ptr(P))
+
+    def local_map(self):
+        box = np.zeros(6, np.float32)
+        nd = C.c_int64(0)
+        rc = self._lib.lio_seq_local_map(self._h, _ptr(box), C.byref(nd))
+        return (box.reshape(2, 3) if rc == 0 else None), int(nd.value)
+
+
+def seq_process_many(seqs, inputs):
+    """lio_seq_process_many: one main-loop iteration of several independent sequences (one SeqInput each)."""
+    n = len(seqs)
+    hs = (C.c_void_p * n)(*[s._h for s in seqs])
+    ins = (SeqInput * n)(*inputs)
+    res = (SeqResult * n)()
+    rc = load_library().lio_seq_process_many(hs, n, ins, res)
+    if rc:
+        raise LioError(rc, "; ".join((s._lib.lio_last_error(s.ctx._h) or b"").decode() for s in seqs))
+    return list(res)
 
 
 def update_enqueue_multi(ctxs, R=0.001, max_iter=4, extrinsic_est=False, from_snapshot=True):

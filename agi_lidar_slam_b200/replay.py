@@ -201,3 +201,59 @@ def process_many(replays, meass):
         r = replays[k]
         out[k] = r.adopt(r.ctx.scan_step_finish(r.x, r.P))
     return out
+
+
+class NativeReplay:
+    """LioReplay's interface on the native loop (lio_seq_process, csrc/lio_seq.cu): the host stage, the bookkeeping and
+    the local-map box live in C++; one C-ABI call per MeasureGroup.  `x` / `P` are pushed before and pulled after every
+    call, so a caller may overwrite them between scans (relocalisation, teacher-forced parity tests)."""
+
+    def __init__(self, ctx: _cabi.Context, cfg: ReplayConfig | None = None):
+        self.ctx = ctx
+        self.cfg = c = cfg or ReplayConfig()
+        self.seq = _cabi.Sequence(ctx, filter_size_surf=c.filter_size_surf, filter_size_map=c.filter_size_map,
+                                  max_iteration=c.max_iteration, extrinsic_est=int(c.extrinsic_est),
+                                  extrinsic_T=c.extrinsic_T, extrinsic_R=np.asarray(c.extrinsic_R, np.float64),
+                                  gyr_cov=c.gyr_cov, acc_cov=c.acc_cov, b_gyr_cov=c.b_gyr_cov, b_acc_cov=c.b_acc_cov,
+                                  cube_len=c.cube_len, det_range=c.det_range, laser_point_cov=LASER_POINT_COV)
+        self.x, self.P = self.seq.get_state()
+        self.map_built = False
+        self.n_box_deleted = 0
+        self.log = []
+
+    def book(self, res):
+        """Log a lio_seq_result; returns the odometry or None when the scan was skipped."""
+        name = _cabi.SEQ_STATUS_NAMES[res.status]
+        self.n_box_deleted = int(res.n_box_deleted)
+        if res.status == _cabi.SEQ_UPDATED:
+            self.log.append(dict(status=name, m=int(res.m), n_valid=int(res.n_valid), n_passes=int(res.n_passes),
+                                 counts=list(res.counts)))
+            return self.x.copy()
+        if res.status == _cabi.SEQ_MAP_BUILT:
+            self.map_built = True
+        self.log.append(dict(status=name, m=int(res.m)) if res.status in (_cabi.SEQ_MAP_BUILT, _cabi.SEQ_FEW_POINTS)
+                        else dict(status=name))
+        return None
+
+    @property
+    def local_map(self):
+        return self.seq.local_map()[0]
+
+    def process(self, meas: MeasureGroup):
+        self.seq.set_state(self.x, self.P)
+        res = self.seq.process(meas.lidar, meas.imu, meas.lidar_beg_time, meas.lidar_end_time)
+        self.x, self.P = self.seq.get_state()
+        return self.book(res)
+
+
+def native_process_many(replays, meass):
+    """process_many on the native loop: lio_seq_process_many."""
+    for r in replays:
+        r.seq.set_state(r.x, r.P)
+    ins = [r.seq.input(m.lidar, m.imu, m.lidar_beg_time, m.lidar_end_time) for r, m in zip(replays, meass)]
+    res = _cabi.seq_process_many([r.seq for r in replays], ins)
+    out = []
+    for r, e in zip(replays, res):
+        r.x, r.P = r.seq.get_state()
+        out.append(r.book(e))
+    return out

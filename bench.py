@@ -318,16 +318,16 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
     """Configs 2 and 4: one step = one scan of every sequence through the whole main loop of laserMapping.cpp:702-800.
     The raw scan and the IMU samples come from host memory every step by nature, so `value` is host-timed end to end
     (= `e2e`); max over ranks; the sequences of a GPU share one cooperative update launch per scan."""
-    from agi_lidar_slam_b200.replay import LioReplay, MeasureGroup, ReplayConfig, process_many
-
     t = TRAJ[args.workload]
     n_seq = 1 if args.workload == "vlp16_traj" else max(1, args.seqs_per_gpu)
     n_scans = LEAD + args.warmup + args.steps
     seqs = traj_sequences(args, rank, n_seq, n_scans)
-    mgs = [[MeasureGroup(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"]) for m in s] for s in seqs]
     ctxs = [_cabi.Context(local, max_scan_points=1 << 17, max_down_points=1 << 16, max_map_points=1 << 21)
             for _ in range(n_seq)]
-    reps = [LioReplay(c, ReplayConfig(max_iteration=3)) for c in ctxs]
+    # the native main loop (lio_seq_process / lio_seq_process_many): one C-ABI call per step
+    runs = [_cabi.Sequence(c, max_iteration=3) for c in ctxs]
+    inputs = [[runs[k].input(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"]) for m in seqs[k]]
+              for k in range(n_seq)]
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -337,6 +337,10 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
 
     sampler = ClockSampler(local)
     launches0 = 0
+    results = []
+    res1 = _cabi.SeqResult()
+    lib = _cabi.load_library()
+    import ctypes
     for j in range(n_scans):
         if j == LEAD + args.warmup:
             barrier()
@@ -344,9 +348,15 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
             launches0 = sum(c.launch_count for c in ctxs)
             t0 = time.perf_counter()
         if n_seq == 1:
-            reps[0].process(mgs[0][j])
+            rc = lib.lio_seq_process(runs[0]._h, ctypes.byref(inputs[0][j]), ctypes.byref(res1))
+            if rc:
+                raise _cabi.LioError(rc, "lio_seq_process")
+            if j >= LEAD + args.warmup:
+                results.append((res1.status, res1.m, res1.n_valid, res1.n_passes))
         else:
-            process_many(reps, [mg[j] for mg in mgs])
+            rs = _cabi.seq_process_many(runs, [inputs[k][j] for k in range(n_seq)])
+            if j >= LEAD + args.warmup:
+                results += [(r.status, r.m, r.n_valid, r.n_passes) for r in rs]
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     launches = sum(c.launch_count for c in ctxs) - launches0
@@ -356,8 +366,7 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-    logs = [e for r in reps for e in r.log[-args.steps:]]
-    ok = [e for e in logs if e["status"] == "ok"]
+    ok = [dict(m=r[1], n_valid=r[2], n_passes=r[3]) for r in results if r[0] == _cabi.SEQ_UPDATED]
     n_upd = len(ok)
     M = float(np.mean([e["m"] for e in ok]))
     passes = float(np.mean([e["n_passes"] for e in ok]))
@@ -396,6 +405,8 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
         line["cpu_baseline_3_threads"] = {"value": r3["value"], "unit": UNIT, "cores": 3}
     if rank == 0:
         print(json.dumps(line))
+    for r in runs:
+        r.close()
     for c in ctxs:
         c.close()
     if world > 1:

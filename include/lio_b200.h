@@ -297,6 +297,62 @@ int lio_predict(lio_state* x, double P[576], double dt, const double Q[144], con
 int lio_boxplus(const lio_state* x, const double f[24], lio_state* out);
 int lio_boxminus(const lio_state* x1, const lio_state* x2, double out[24]);
 
+
+/* ---- the per-scan main loop as one object (src/laserMapping.cpp:702-800) ---------------------------------- */
+/* One lio_seq = one sequence (one robot / one bag) on one context: ImuProcess (IMU_Processing.hpp:79-136), the loop's
+ * bookkeeping (flg_first_scan, first_lidar_time, flg_EKF_inited), the sliding local-map box of lasermap_fov_segment
+ * (:309-365) and the filter state.  Host code; the device work of an iteration is one lio_scan_step. */
+typedef struct lio_seq lio_seq;
+typedef struct lio_seq_config {
+  float filter_size_surf, filter_size_map; /* filter_size_surf_min / filter_size_map_min (launch files) */
+  int32_t max_iteration;                   /* NUM_MAX_ITERATIONS */
+  int32_t extrinsic_est;                   /* extrinsic_est_en */
+  double extrinsic_T[3], extrinsic_R[9];   /* mapping/extrinsic_T, extrinsic_R (row-major) */
+  double gyr_cov, acc_cov, b_gyr_cov, b_acc_cov;
+  double cube_len, det_range;              /* cube_side_length, DET_RANGE */
+  double laser_point_cov;                  /* LASER_POINT_COV */
+} lio_seq_config;
+/* One synchronised MeasureGroup (common_lib.h:40-49) as sync_packages (laserMapping.cpp:218-275) hands it over. */
+typedef struct lio_seq_input {
+  const void* lidar;      /* n records of stride_bytes (16: x,y,z,t_ms; 48: PointXYZINormal, time in curvature) */
+  int64_t n;
+  int32_t stride_bytes;
+  int32_t n_imu;
+  const lio_imu_sample* imu;
+  double lidar_beg_time, lidar_end_time;
+} lio_seq_input;
+enum {
+  LIO_SEQ_UPDATED = 0,    /* the odometry in result.x is new */
+  LIO_SEQ_FEW_POINTS = 1, /* feats_down_size < 5 (:741-744) */
+  LIO_SEQ_MAP_BUILT = 2,  /* first scan with points: ikdtree.Build (:747-758) */
+  LIO_SEQ_FIRST_SCAN = 3, /* flg_first_scan (:711-716) */
+  LIO_SEQ_NO_IMU = 4,     /* meas.imu.empty() */
+  LIO_SEQ_IMU_INIT = 5    /* IMU_init still collecting (:722-725) */
+};
+typedef struct lio_seq_result {
+  int32_t status; /* LIO_SEQ_* */
+  int32_t n_valid, n_passes;
+  int32_t counts[3];
+  int64_t m;
+  int64_t n_box_deleted; /* running total of points removed by the sliding local-map box */
+  lio_state x;           /* state after this scan (what the reference publishes as odometry) */
+} lio_seq_result;
+void lio_seq_default_config(lio_seq_config* cfg);
+int lio_seq_create(lio_ctx*, const lio_seq_config* cfg, lio_seq** out);
+void lio_seq_destroy(lio_seq*);
+/* One iteration of the main loop. */
+int lio_seq_process(lio_seq*, const lio_seq_input* in, lio_seq_result* result);
+/* One iteration for n_seq <= 64 INDEPENDENT sequences (each with its own context on the same device; BASELINE.json
+ * config 4): host stages and preprocessing per sequence on its context's stream, the updates that are due in one
+ * cooperative launch per group of 8 (lio_update_enqueue_multi), map growth per sequence, one synchronisation per
+ * sequence at the end.  in / result: arrays of n_seq.  All sequences use the filter settings of the first one. */
+int lio_seq_process_many(lio_seq* const* seqs, int n_seq, const lio_seq_input* in, lio_seq_result* results);
+/* Filter state in / out between scans (relocalisation as in laserMapping_re.cpp:590-600, teacher-forced tests). */
+int lio_seq_get_state(const lio_seq*, lio_state* x, double P[576]);
+int lio_seq_set_state(lio_seq*, const lio_state* x, const double P[576]);
+/* LocalMap_Points {min, max} and the running box-delete count; LIO_E_EMPTY_MAP before the box exists. */
+int lio_seq_local_map(const lio_seq*, float box6[6], int64_t* n_box_deleted);
+
 #ifdef __cplusplus
 }
 #endif

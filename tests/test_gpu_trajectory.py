@@ -30,7 +30,7 @@ def _p4(xyz):
 ])
 def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_range, cube_len, det_range):
     from agi_lidar_slam_b200 import _cabi, synth
-    from agi_lidar_slam_b200.replay import LioReplay, MeasureGroup, ReplayConfig
+    from agi_lidar_slam_b200.replay import MeasureGroup, NativeReplay as LioReplay, ReplayConfig
     from replay_oracle import OracleReplay
 
     N_SCANS = n_scans
@@ -86,7 +86,8 @@ def test_process_many_equals_independent_replays():
     scan, replay.process_many) follow the same trajectories as the same sequences replayed one by one.  The reference
     loop amplifies rounding differences (~5x per scan), so the horizon is short and the tolerance is 1e-6."""
     from agi_lidar_slam_b200 import _cabi, synth
-    from agi_lidar_slam_b200.replay import LioReplay, MeasureGroup, ReplayConfig, process_many
+    from agi_lidar_slam_b200.replay import (LioReplay, MeasureGroup, NativeReplay, ReplayConfig, native_process_many,
+                                            process_many)
 
     n_seq, n_scans = 3, 12
     seqs = [synth.sequence(n_scans, 4000 + k, rings=32, cols=512, fov=(-22.5, 22.5), max_range=120.0) for k in range(n_seq)]
@@ -112,5 +113,16 @@ def test_process_many_equals_independent_replays():
                 n_upd += 1
                 assert np.abs(res[k] - solo[k][j]).max() < 1e-6
     assert n_upd >= n_seq * (n_scans - 4)
+    for c in ctxs:
+        c.close()
+    # the native loop (lio_seq_process_many) takes the same steps
+    ctxs = contexts()
+    reps = [NativeReplay(c, ReplayConfig(max_iteration=3)) for c in ctxs]
+    for j in range(n_scans):
+        res = native_process_many(reps, [mg[k][j] for k in range(n_seq)])
+        for k in range(n_seq):
+            assert (res[k] is None) == (solo[k][j] is None)
+            if res[k] is not None:
+                assert np.abs(res[k] - solo[k][j]).max() < 1e-6
     for c in ctxs:
         c.close()

@@ -34,14 +34,20 @@ for j, m in enumerate(seq):
         r.process(mg)
         continue
     c = r.cfg
-    r.x, r.P, poses, ini = timed("imu.process", r.imu.process, mg.imu, mg.lidar_beg_time, mg.lidar_end_time, r.x, r.P)
-    timed("fov_segment", r._lasermap_fov_segment)
-    mm = timed("scan_preprocess", ctx.scan_preprocess, mg.lidar, poses, r.x, c.filter_size_surf, resident=True)
-    x, P, nv, npz = timed("update_scan", ctx.update_scan, r.x, r.P, LASER_POINT_COV, c.max_iteration, c.extrinsic_est)
-    r.x, r.P = x, P
-    timed("map_incremental", ctx.map_incremental, r.x, c.filter_size_map, True)
-tot = 0.0
+    if j % 2 == 0:  # the product path: host stage + one lio_scan_step
+        poses = timed("host_stage (imu.process + fov_segment)", r.host_stage, mg)
+        rep = timed("lio_scan_step", ctx.scan_step, mg.lidar, poses, r.x, r.P, c.filter_size_surf, c.filter_size_map,
+                    LASER_POINT_COV, c.max_iteration, c.extrinsic_est, True)
+        r.adopt(rep)
+        mm = rep.m
+    else:  # the same scan in its pieces, synchronised after each: where the step's time goes
+        poses = r.host_stage(mg)
+        timed("  begin (H2D scan + preprocess + prior) + sync", lambda: (ctx.scan_step_begin(mg.lidar, poses, r.x, r.P,
+                                                                 c.filter_size_surf), ctx.synchronize()))
+        timed("  update kernel + sync", lambda: (ctx.update_enqueue(LASER_POINT_COV, c.max_iteration, c.extrinsic_est,
+                                                                    from_snapshot=True), ctx.synchronize()))
+        timed("  end (map growth + report) + finish", lambda: (ctx.scan_step_end(c.filter_size_map, True),
+                                                               r.adopt(ctx.scan_step_finish(r.x, r.P))))
 for k, v in acc.items():
-    print("%-18s %8.1f us" % (k, 1e6 * np.mean(v)))
-    tot += np.mean(v)
-print("%-18s %8.1f us  (%d scans, N %d, M %d)" % ("total", 1e6 * tot, len(v), len(m["lidar"]), mm))
+    print("%-48s %8.1f us" % (k, 1e6 * np.mean(v)))
+print("(%d scans, N %d, M %d)" % (len(seq) - 14, len(m["lidar"]), mm))
