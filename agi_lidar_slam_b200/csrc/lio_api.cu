@@ -184,6 +184,8 @@ static int create_impl(lio_ctx* c) {
   LIO_CHECK(c, cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
   LIO_CHECK(c, cudaEventCreateWithFlags(&c->upload_done, cudaEventDisableTiming));
   LIO_CHECK(c, cudaEventCreateWithFlags(&c->multi_evt, cudaEventDisableTiming));
+  LIO_CHECK(c, cudaEventCreateWithFlags(&c->ev_post, cudaEventDisableTiming));
+  LIO_CHECK(c, cudaEventCreateWithFlags(&c->ev_growth, cudaEventDisableTiming));
   LIO_CHECK(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_out), 8 * 616, cudaHostAllocMapped));
   memset(c->h_out, 0, 8 * 616);
   LIO_CHECK(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->h_out_dev), c->h_out, 0));
@@ -266,6 +268,8 @@ void lio_destroy(lio_ctx* c) {
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->upload_done) cudaEventDestroy(c->upload_done);
   if (c->multi_evt) cudaEventDestroy(c->multi_evt);
+  if (c->ev_post) cudaEventDestroy(c->ev_post);
+  if (c->ev_growth) cudaEventDestroy(c->ev_growth);
   delete c;
 }
 
@@ -282,13 +286,57 @@ int lio_set_stream(lio_ctx* c, void* cuda_stream) {
 int lio_synchronize(lio_ctx* c) {
   if (!c) return LIO_E_INVALID;
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  return settle_growth(c);
+}
+
+// ---------------------------------------------------------------- deferred map growth
+// The reference publishes the odometry of a scan before map_incremental runs (laserMapping.cpp:776-785).  With
+// lio_set_deferred_growth the step does the same: lio_scan_step_finish hands the posterior back as soon as it is on
+// the host while the map growth of that scan is still running on the stream, under the host stage (IMU propagation)
+// and the upload of the next scan.  The counts and errors of the growth are booked by the next call that needs the
+// host's view of the map (settle_growth), at the latest by the growth of the next scan.
+}  // extern "C"
+namespace lio {
+int settle_growth(lio_ctx* c) {
+  if (!c->growth_pending) return LIO_OK;
+  c->growth_pending = false;
+  LIO_CHECK(c, cudaEventSynchronize(c->ev_growth));
+  const double* hp = static_cast<const double*>(c->h_pinned);
+  const int* cls = reinterpret_cast<const int*>(hp + 620);
+  const uint32_t* mc = reinterpret_cast<const uint32_t*>(hp + 622);
+  c->last_counts[0] = cls[0];
+  c->last_counts[1] = cls[1];
+  c->last_counts[2] = (int32_t)mc[4];
+  c->next_id += cls[0] + cls[1];
+  if (mc[3] != 0) {
+    c->err = mc[3] == 1 ? "map hash table full (raise lio_caps.max_map_points)"
+                        : "map point pool full (raise lio_caps.max_map_points)";
+    return LIO_E_CAPACITY;
+  }
   return LIO_OK;
+}
+}  // namespace lio
+extern "C" {
+
+int lio_set_deferred_growth(lio_ctx* c, int on) {
+  if (!c) return LIO_E_INVALID;
+  const int rc = settle_growth(c);
+  c->deferred_growth = on != 0;
+  return rc;
+}
+
+int lio_scan_step_settle(lio_ctx* c, int32_t counts[3]) {
+  if (!c) return LIO_E_INVALID;
+  const int rc = settle_growth(c);
+  if (counts) memcpy(counts, c->last_counts, sizeof(c->last_counts));
+  return rc;
 }
 
 // ---------------------------------------------------------------- map
 int lio_map_build(lio_ctx* c, const void* pts, int64_t n, int stride) {
   if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !pts)) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
   if (n > c->caps.max_map_points) {
     c->err = "Build: more points than lio_caps.max_map_points";
     return LIO_E_CAPACITY;
@@ -308,6 +356,7 @@ int lio_map_build(lio_ctx* c, const void* pts, int64_t n, int stride) {
 int lio_map_add(lio_ctx* c, const void* pts, int64_t n, int stride, int downsample_on, int32_t* n_added) {
   if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !pts)) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
   if (n_added) *n_added = 0;
   if (!c->map_built) {
     c->err = "Add_Points on an empty map (the reference dereferences Root_Node here)";
@@ -334,12 +383,14 @@ int lio_map_add(lio_ctx* c, const void* pts, int64_t n, int stride, int downsamp
 int lio_map_delete_boxes(lio_ctx* c, const float* boxes6, int nb, int32_t* n_deleted) {
   if (!c || nb < 0 || (nb > 0 && !boxes6)) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
   return map_delete_boxes(c, boxes6, nb, n_deleted);
 }
 
 int lio_map_size(lio_ctx* c, int64_t* total, int64_t* valid) {
   if (!c) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
   uint32_t h[8];
   LIO_CHECK(c, cudaMemcpyAsync(h, c->map.counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
@@ -351,6 +402,7 @@ int lio_map_size(lio_ctx* c, int64_t* total, int64_t* valid) {
 int lio_map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n) {
   if (!c) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
   return map_dump(c, xyz, ids, cap, n);
 }
 
@@ -758,12 +810,19 @@ int lio_scan_step_end(lio_ctx* c, float leaf_map, int ekf_inited) {
     return LIO_E_INVALID;
   }
   LIO_CHECK(c, cudaSetDevice(c->device));
-  const int rc = map_incremental_enqueue(c, leaf_map, ekf_inited ? 1 : 0, 5, c->scan_m_bound);
+  int rc = settle_growth(c);  // the previous scan's growth is long done by now: books next_id for this one
   if (rc) return rc;
+  // posterior + preprocess counters first: with deferred growth the host resumes as soon as these have landed
   double* hp = static_cast<double*>(c->h_pinned);
   LIO_CHECK(c, cudaMemcpyAsync(hp, c->d_x, 8 * 606, cudaMemcpyDeviceToHost, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(hp + 606, c->d_prep_counters, 4 * 16, cudaMemcpyDeviceToHost, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(hp + 614, c->map.counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(hp + 606, c->d_prep_counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaEventRecord(c->ev_post, c->stream));
+  rc = map_incremental_enqueue(c, leaf_map, ekf_inited ? 1 : 0, 5, c->scan_m_bound);
+  if (rc) return rc;
+  LIO_CHECK(c, cudaMemcpyAsync(hp + 620, c->d_prep_counters + 8, 4 * 2, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(hp + 622, c->map.counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaEventRecord(c->ev_growth, c->stream));
+  c->growth_pending = true;
   c->step_phase = 2;
   return LIO_OK;
 }
@@ -784,18 +843,23 @@ int lio_scan_step_finish(lio_ctx* c, lio_state* x_out, double P_out[576], lio_sc
   }
   c->step_phase = 0;
   LIO_CHECK(c, cudaSetDevice(c->device));
-  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (c->deferred_growth) {
+    cudaError_t q;
+    while ((q = cudaEventQuery(c->ev_post)) == cudaErrorNotReady) {
+    }
+    LIO_CHECK(c, q);
+  } else {
+    LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
   const double* hp = static_cast<const double*>(c->h_pinned);
   const int* prep = reinterpret_cast<const int*>(hp + 606);
-  const uint32_t* mc = reinterpret_cast<const uint32_t*>(hp + 614);
   int64_t m = 0;
-  const int rc = preprocess_decode(c, prep, &m);
+  int rc = preprocess_decode(c, prep, &m);
   rep->m = m;
   if (rc) return rc;
-  if (mc[3] != 0) {
-    c->err = mc[3] == 1 ? "map hash table full (raise lio_caps.max_map_points)"
-                        : "map point pool full (raise lio_caps.max_map_points)";
-    return LIO_E_CAPACITY;
+  if (!c->deferred_growth) {
+    rc = settle_growth(c);
+    if (rc) return rc;
   }
   if (m < 5) {
     rep->status = LIO_SCAN_FEW_POINTS;  // state untouched, as after the reference's `continue`
@@ -805,10 +869,7 @@ int lio_scan_step_finish(lio_ctx* c, lio_state* x_out, double P_out[576], lio_sc
   rep->status = LIO_SCAN_UPDATED;
   rep->n_valid = hc->n_valid_last;
   rep->n_passes = hc->n_passes;
-  rep->counts[0] = prep[8];
-  rep->counts[1] = prep[9];
-  rep->counts[2] = (int32_t)mc[4];
-  c->next_id += prep[8] + prep[9];
+  for (int k = 0; k < 3; ++k) rep->counts[k] = c->deferred_growth ? -1 : c->last_counts[k];
   if (x_out) memcpy(x_out, hp, sizeof(lio_state));
   if (P_out) memcpy(P_out, hp + 26, 8 * 576);
   return LIO_OK;
@@ -1010,6 +1071,7 @@ int lio_get_neighbors(lio_ctx* c, int32_t* idx5, float* d2_5, float* nbr_xyz, fl
 int lio_map_incremental(lio_ctx* c, const lio_state* x, float filter_size_map, int ekf_inited, int32_t counts[3]) {
   if (!c || !x || !counts) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
   int rc = refresh_scan_m(c);
   if (rc) return rc;
   return map_incremental(c, x, filter_size_map, ekf_inited, counts);
@@ -1018,6 +1080,7 @@ int lio_map_incremental(lio_ctx* c, const lio_state* x, float filter_size_map, i
 int lio_map_build_scan(lio_ctx* c, const lio_state* x) {
   if (!c || !x) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
   int rc = refresh_scan_m(c);
   if (rc) return rc;
   return map_build_scan(c, x);

@@ -111,7 +111,14 @@ struct lio_ctx {
   int step_phase = 0;          // 0 idle, 1 begun (update due), 2 map growth + report enqueued, 3 first-scan branch done
   int step_status = 0;         // LIO_SCAN_* of the first-scan branch
   int64_t step_m = 0;
-
+  // deferred map growth (lio_set_deferred_growth): lio_scan_step_finish returns once the posterior is on the host;
+  // the growth counts of that scan are collected by settle_growth() before the next host use of the map
+  bool deferred_growth = false;
+  bool growth_pending = false;
+  cudaEvent_t ev_post = nullptr;    // posterior + preprocess counters are in h_pinned
+  cudaEvent_t ev_growth = nullptr;  // map growth done, its counts are in h_pinned[620..626)
+  int32_t last_counts[3] = {0, 0, 0};
+  int growth_rc = 0;                // error of a deferred growth, reported by the next call that settles it
 };
 
 #define LIO_CHECK(ctx, call)                                                                   \
@@ -153,6 +160,7 @@ int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
 int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]);
 int map_incremental_enqueue(lio_ctx* c, float fsm, int ekf_inited, int min_m, int64_t bound);
 int map_build_scan(lio_ctx* c, const lio_state* x);
+int settle_growth(lio_ctx* c);  // lio_api.cu: waits for a deferred map growth and books its counts (no-op otherwise)
 
 int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux);
 int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, int64_t* n_out);

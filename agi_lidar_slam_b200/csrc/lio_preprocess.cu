@@ -163,20 +163,23 @@ __global__ void gather_sorted_kernel(const uint32_t* sorted_vals, int n, const f
 
 // One run of equal leaf indices per thread: FP32 sums in sorted (= ascending point) order, then / count.  The order
 // is sequential by definition (bit parity with the oracle), so a run cannot be split; what can be done is to keep its
-// adds fed.  Short runs: the owning thread streams its points eight loads at a time.  Long runs (a wall right next to
-// the sensor puts thousands of points into one leaf): the WARP takes them one after the other -- all lanes stage 256
-// points into shared memory with coalesced loads, then lanes 0-4 run the five component sums (x, y, z, time,
-// intensity) as five independent sequential chains out of shared memory.
+// adds fed and to keep long runs out of each other's way.  Runs are dealt to the threads warp-first (run m -> warp
+// m % n_warps, lane m / n_warps): neighbouring leaves -- a wall next to the sensor puts thousands of points into each of
+// a few dozen consecutive leaves -- land in different warps instead of queueing up in one.  Short runs: the owning
+// thread streams its points eight loads at a time.  Long runs: the WARP takes them one after the other -- all lanes
+// stage 256 points into shared memory with coalesced loads (the next stage's loads are in flight during the sums), then
+// lanes 0-4 run the five component sums (x, y, z, time, intensity) as five independent sequential chains.
 constexpr int LONG_RUN = 96;
 constexpr int STAGE = 256;
 __global__ void __launch_bounds__(128) centroid_kernel(const float4* sorted_pts, const float* sorted_aux,
                                                        const int* heads, const int* n_runs, int n, int max_m,
                                                        float4* body, float* body_time, int* scan_m, int* counters) {
-  __shared__ float s_stage[4][5][STAGE];
+  __shared__ __align__(16) float s_stage[4][5][STAGE];
   const int Mtot = *n_runs;
   const int M = Mtot > max_m ? max_m : Mtot;
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
+  const int m = lane * n_warps + blockIdx.x * (blockDim.x >> 5) + warp;
   if (m == 0) {
     *scan_m = counters[7] == 3 ? 0 : M;
     counters[0] = Mtot;
@@ -224,27 +227,45 @@ __global__ void __launch_bounds__(128) centroid_kernel(const float4* sorted_pts,
     todo &= todo - 1;
     const int rb = __shfl_sync(0xffffffffu, beg, src), re = __shfl_sync(0xffffffffu, end, src);
     float acc = 0.f;  // lane c < 5: running sum of component c
+    float4 pre[STAGE / 32];
+    float preq[STAGE / 32];
+#pragma unroll
+    for (int u = 0; u < STAGE / 32; ++u) {
+      const int j = rb + lane + 32 * u;
+      pre[u] = j < re ? __ldg(sorted_pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      preq[u] = (sorted_aux && j < re) ? __ldg(sorted_aux + j) : 0.f;
+    }
     for (int base = rb; base < re; base += STAGE) {
       const int cnt = min(STAGE, re - base);
       __syncwarp();
-      for (int t = lane; t < cnt; t += 32) {
-        const float4 p = __ldg(sorted_pts + base + t);
-        s_stage[warp][0][t] = p.x;
-        s_stage[warp][1][t] = p.y;
-        s_stage[warp][2][t] = p.z;
-        s_stage[warp][3][t] = p.w;
-        s_stage[warp][4][t] = sorted_aux ? __ldg(sorted_aux + base + t) : 0.f;
+#pragma unroll
+      for (int u = 0; u < STAGE / 32; ++u) {
+        const int t = lane + 32 * u;
+        s_stage[warp][0][t] = pre[u].x;
+        s_stage[warp][1][t] = pre[u].y;
+        s_stage[warp][2][t] = pre[u].z;
+        s_stage[warp][3][t] = pre[u].w;
+        s_stage[warp][4][t] = preq[u];
       }
       __syncwarp();
+      if (base + STAGE < re) {
+#pragma unroll
+        for (int u = 0; u < STAGE / 32; ++u) {
+          const int j = base + STAGE + lane + 32 * u;
+          pre[u] = j < re ? __ldg(sorted_pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          preq[u] = (sorted_aux && j < re) ? __ldg(sorted_aux + j) : 0.f;
+        }
+      }
       if (lane < 5) {
         const float* v = s_stage[warp][lane];
         int t = 0;
-        for (; t + 8 <= cnt; t += 8) {
-          float w[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) w[u] = v[t + u];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc = acc + w[u];
+        for (; t + 16 <= cnt; t += 16) {
+          const float4 w0 = *reinterpret_cast<const float4*>(v + t), w1 = *reinterpret_cast<const float4*>(v + t + 4),
+                       w2 = *reinterpret_cast<const float4*>(v + t + 8), w3 = *reinterpret_cast<const float4*>(v + t + 12);
+          acc = acc + w0.x; acc = acc + w0.y; acc = acc + w0.z; acc = acc + w0.w;
+          acc = acc + w1.x; acc = acc + w1.y; acc = acc + w1.z; acc = acc + w1.w;
+          acc = acc + w2.x; acc = acc + w2.y; acc = acc + w2.z; acc = acc + w2.w;
+          acc = acc + w3.x; acc = acc + w3.y; acc = acc + w3.z; acc = acc + w3.w;
         }
         for (; t < cnt; ++t) acc = acc + v[t];
       }

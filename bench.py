@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="sharded workload: blob exchange inside the persistent kernel over NVLink peer memory (peer) "
                          "or pass kernel -> NCCL all-reduce -> solve kernel per pass (nccl)")
+    ap.add_argument("--sync-growth", action="store_true",
+                    help="trajectory workloads: wait for each scan's map growth inside its step (default: deferred, the "
+                         "step returns with the posterior as the reference publishes before map_incremental)")
     ap.add_argument("--map-cell", type=float, default=0.0, help="kNN hash cell edge [m] (0: library default); no effect on results")
     return ap.parse_args()
 
@@ -325,6 +328,8 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
     ctxs = [_cabi.Context(local, max_scan_points=1 << 17, max_down_points=1 << 16, max_map_points=1 << 21)
             for _ in range(n_seq)]
     # the native main loop (lio_seq_process / lio_seq_process_many): one C-ABI call per step
+    for c in ctxs:
+        c.set_deferred_growth(not args.sync_growth)
     runs = [_cabi.Sequence(c, max_iteration=3) for c in ctxs]
     inputs = [[runs[k].input(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"]) for m in seqs[k]]
               for k in range(n_seq)]
@@ -357,6 +362,8 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
             rs = _cabi.seq_process_many(runs, [inputs[k][j] for k in range(n_seq)])
             if j >= LEAD + args.warmup:
                 results += [(r.status, r.m, r.n_valid, r.n_passes) for r in rs]
+    for c in ctxs:
+        c.scan_step_settle()  # the last scan's map growth belongs to the timed region
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     launches = sum(c.launch_count for c in ctxs) - launches0
@@ -385,7 +392,9 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
                    "0.5/0.5, max_iter 3" % (t["sensor"], t["rings"], t["cols"], n_seq), "N_raw": n_raw, "M": M,
                    "passes_per_scan": passes, "updates_in_timed_region": n_upd,
                    "l2": "not flushed: every scan is new data from the host, the map is the sequence's own growing map",
-                   "timing": "host clock around the loop (host stages are on the path), device synchronised both sides"},
+                   "timing": "host clock around the loop (host stages are on the path), device synchronised both sides",
+                   "map_growth": "inside the step" if args.sync_growth else
+                   "deferred: runs under the next scan's host stage and upload (lio_set_deferred_growth)"},
         "matched_pts_per_s": float(np.sum([e["n_valid"] for e in ok])) * world / dt,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(n_seq * (16 * n_raw + 200 * (n_imu + 1) + 602 * 8)),
                 "d2h_bytes_per_step": int(n_seq * (607 * 8 + 8 + 12))},

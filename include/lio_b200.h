@@ -212,6 +212,14 @@ int lio_scan_step_begin(lio_ctx*, const void* raw_pts, int64_t n, int stride_byt
                         int n_poses, const lio_state* x, const double P[576], float leaf_surf, int32_t* update_due);
 int lio_scan_step_end(lio_ctx*, float leaf_map, int ekf_inited);
 int lio_scan_step_finish(lio_ctx*, lio_state* x_out, double P_out[576], lio_scan_report* report);
+/* Deferred map growth.  The reference publishes a scan's odometry BEFORE map_incremental runs (laserMapping.cpp:776-785).
+ * With on != 0 the step does the same: lio_scan_step / lio_scan_step_finish (and lio_seq_process*) return as soon as the
+ * posterior is on the host, while the map growth of that scan still runs on the context's stream underneath the host's
+ * IMU propagation and the upload of the next scan (stream order keeps the next update behind it).  report.counts is
+ * then {-1,-1,-1}; lio_scan_step_settle waits for the growth and returns its counts (and a capacity error, if any).
+ * Every other entry point that needs the host's view of the map settles implicitly.  Results are unchanged. */
+int lio_set_deferred_growth(lio_ctx*, int on);
+int lio_scan_step_settle(lio_ctx*, int32_t counts[3]);
 
 /* n <= 8 INDEPENDENT updates -- different sequences, each context with its own map, scan and filter state (BASELINE.json
  * config 4) -- in ONE cooperative launch on ctxs[0]'s stream: the persistent grid is cut into n slices, each with its own

@@ -126,3 +126,42 @@ def test_native_loop_equals_python_loop():
     finally:
         a_ctx.close()
         b_ctx.close()
+
+
+def test_deferred_map_growth_changes_nothing():
+    """lio_set_deferred_growth: the step returns with the posterior while the scan's map growth still runs (the reference
+    publishes before map_incremental, laserMapping.cpp:776-785).  Same states, same counts (collected by
+    lio_scan_step_settle), same map, same box deletes -- with a sliding local-map cube that touches the map between scans."""
+    from agi_lidar_slam_b200 import synth
+    from agi_lidar_slam_b200.replay import MeasureGroup, NativeReplay, ReplayConfig
+
+    seq = synth.sequence(50, 2002, rings=16, cols=600)
+    a_ctx, b_ctx = _ctx(), _ctx()
+    try:
+        cfg = ReplayConfig(max_iteration=3, cube_len=40.0, det_range=10.0)
+        b_ctx.set_deferred_growth(True)
+        A, B = NativeReplay(a_ctx, cfg), NativeReplay(b_ctx, cfg)
+        n_ok = 0
+        for j, m in enumerate(seq):
+            mg = MeasureGroup(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"])
+            ra, rb = A.process(mg), B.process(mg)
+            assert (ra is None) == (rb is None), j
+            la, lb = dict(A.log[-1]), dict(B.log[-1])
+            if la["status"] == "ok":
+                n_ok += 1
+                assert lb.pop("counts") == [-1, -1, -1]
+                ca = la.pop("counts")
+                if j % 3 == 0:  # settle explicitly now and then; otherwise the next step settles on its own
+                    assert b_ctx.scan_step_settle() == ca, j
+            assert la == lb, (j, la, lb)
+            assert np.array_equal(A.x, B.x) and np.array_equal(A.P, B.P), j
+        assert n_ok >= 40
+        assert b_ctx.scan_step_settle() == A.log[-1]["counts"]
+        assert A.seq.local_map()[1] == B.seq.local_map()[1] and A.seq.local_map()[1] > 0
+        ax, ai = a_ctx.map_dump()
+        bx, bi = b_ctx.map_dump()
+        assert np.array_equal(ai, bi) and np.array_equal(ax.view(np.uint32), bx.view(np.uint32))
+        assert a_ctx.map_size() == b_ctx.map_size()
+    finally:
+        a_ctx.close()
+        b_ctx.close()
