@@ -104,7 +104,7 @@ EXPORTS = [
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
     "lio_imu_proc_init", "lio_imu_set_param", "lio_imu_process",
     "lio_seq_default_config", "lio_seq_create", "lio_seq_destroy", "lio_seq_process", "lio_seq_process_many",
-    "lio_seq_get_state", "lio_seq_set_state", "lio_seq_local_map",
+    "lio_seq_get_state", "lio_seq_set_state", "lio_seq_local_map", "lio_set_host_threads",
 ]  # fmt: skip
 
 _lib = None
@@ -188,6 +188,7 @@ def load_library() -> C.CDLL:
         "lio_seq_get_state": (C.c_int, [vp, vp, vp]),
         "lio_seq_set_state": (C.c_int, [vp, vp, vp]),
         "lio_seq_local_map": (C.c_int, [vp, vp, P(i64)]),
+        "lio_set_host_threads": (C.c_int, [C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == header/library drift
@@ -598,6 +599,12 @@ class Sequence:
         nd = C.c_int64(0)
         rc = self._lib.lio_seq_local_map(self._h, _ptr(box), C.byref(nd))
         return (box.reshape(2, 3) if rc == 0 else None), int(nd.value)
+
+
+def set_host_threads(n: int):
+    """lio_set_host_threads: host threads of lio_seq_process_many (0 = default)."""
+    if load_library().lio_set_host_threads(int(n)):
+        raise ValueError("host threads must be in [0, 64]")
 
 
 def seq_process_many(seqs, inputs):

@@ -186,6 +186,8 @@ static int create_impl(lio_ctx* c) {
   LIO_CHECK(c, cudaEventCreateWithFlags(&c->multi_evt, cudaEventDisableTiming));
   LIO_CHECK(c, cudaEventCreateWithFlags(&c->ev_post, cudaEventDisableTiming));
   LIO_CHECK(c, cudaEventCreateWithFlags(&c->ev_growth, cudaEventDisableTiming));
+  LIO_CHECK(c, cudaEventCreateWithFlags(&c->ev_prep, cudaEventDisableTiming));
+  LIO_CHECK(c, cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking));
   LIO_CHECK(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_out), 8 * 616, cudaHostAllocMapped));
   memset(c->h_out, 0, 8 * 616);
   LIO_CHECK(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->h_out_dev), c->h_out, 0));
@@ -270,6 +272,8 @@ void lio_destroy(lio_ctx* c) {
   if (c->multi_evt) cudaEventDestroy(c->multi_evt);
   if (c->ev_post) cudaEventDestroy(c->ev_post);
   if (c->ev_growth) cudaEventDestroy(c->ev_growth);
+  if (c->ev_prep) cudaEventDestroy(c->ev_prep);
+  if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
   delete c;
 }
 
@@ -778,7 +782,25 @@ int lio_scan_step_begin(lio_ctx* c, const void* raw_pts, int64_t n, int stride, 
   *update_due = 0;
   c->step_phase = 0;
   c->min_m = 0;
+  // A deferred growth of the previous scan is still on the stream: upload, undistort and sort this scan on the second
+  // stream next to it.  The growth reads d_body / d_scan_m (classification), so the one kernel that overwrites them
+  // (centroids) waits for it; everything before touches preprocessing buffers only.  The host has the previous
+  // posterior (ev_post), so the previous update is complete and nothing else reads those buffers.
+  const bool split = c->deferred_growth && c->growth_pending && c->map_built;
+  cudaStream_t main_stream = c->stream;
+  if (split) {
+    LIO_CHECK(c, cudaSetDevice(c->device));
+    LIO_CHECK(c, cudaStreamWaitEvent(c->prep_stream, c->ev_post, 0));
+    c->stream = c->prep_stream;
+    c->centroid_wait = c->ev_growth;
+  }
   int rc = preprocess_common(c, raw_pts, n, stride, poses, n_poses, x, leaf_surf);
+  if (split) {
+    c->stream = main_stream;
+    c->centroid_wait = nullptr;
+    LIO_CHECK(c, cudaEventRecord(c->ev_prep, c->prep_stream));
+    LIO_CHECK(c, cudaStreamWaitEvent(main_stream, c->ev_prep, 0));
+  }
   if (rc) return rc;
   if (!c->map_built) {  // first scan with points: host-synchronous, happens once per sequence
     int64_t m = 0;
@@ -1117,60 +1139,92 @@ int lio_predict(lio_state* xs, double P[576], double dt, const double Q[144], co
     f[3 + i] = (gyro[i] - x.bg[i]) * dt;
     f[12 + i] = (a_in[i] + x.grav[i]) * dt;
   }
-  // F = I + dt * df_dx ; W = dt * df_dw
-  double F[576] = {0}, W[24 * 12] = {0};
-  for (int i = 0; i < 24; ++i) F[i * 24 + i] = 1.0;
   const double hat[9] = {0, -am[2], am[1], am[2], 0, -am[0], -am[1], am[0], 0};
   double Rh[9];
   mat3_mul(R, hat, Rh);
-  for (int i = 0; i < 3; ++i) {
-    F[i * 24 + 12 + i] += dt;
-    F[(3 + i) * 24 + 15 + i] += -dt;
-    F[(12 + i) * 24 + 21 + i] += dt;
-    W[(3 + i) * 12 + i] = -dt;
-    W[(15 + i) * 12 + 6 + i] = dt;
-    W[(18 + i) * 12 + 9 + i] = dt;
-    for (int j = 0; j < 3; ++j) {
-      F[(12 + i) * 24 + 3 + j] += -Rh[3 * i + j] * dt;
-      F[(12 + i) * 24 + 18 + j] += -R[3 * i + j] * dt;
-      W[(12 + i) * 12 + 3 + j] = -R[3 * i + j] * dt;
-    }
-  }
   StateD xn;
   boxplus(x, f, xn);
   x = xn;
-  // P <- F P F^T + W Q W^T (esekfom.hpp:93-94).  F = I + dt df_dx has 51 non-zeros and W = dt df_dw has 18: the sums run
-  // over the non-zero terms only, in ascending k -- the terms left out are exact zeros, so the result is bit-identical
-  // to the dense triple loop at a tenth of its cost (this runs ~20 times per scan on the host).
-  double T[576], Pn[576], WQ[24 * 12];
-  int fk[24][8], fn[24], wk[24][4], wn[24];
-  for (int i = 0; i < 24; ++i) {
-    fn[i] = wn[i] = 0;
-    for (int k = 0; k < 24; ++k)
-      if (F[i * 24 + k] != 0.0) fk[i][fn[i]++] = k;  // at most 8 per row (rows 12-14: 3 + 1 + 3 + 1)
-    for (int k = 0; k < 12; ++k)
-      if (W[i * 12 + k] != 0.0) wk[i][wn[i]++] = k;  // at most 3 per row
+  // P <- F P F^T + W Q W^T (esekfom.hpp:93-94) with F = I + dt df_dx, W = dt df_dw (use-ikfom.hpp:82-123).  The
+  // Jacobians are sparse and their pattern is fixed, so the products are written out over the non-zero terms, every sum
+  // in ascending k exactly as the dense triple loop adds them (the terms left out are exact zeros: same bits).  Rows of F:
+  //   pos  i     : 1 at (i,i), dt at (i,12+i)           rot 3+i : 1 at (3+i,3+i), -dt at (3+i,15+i)
+  //   vel  12+i  : A = -R hat(a) dt at cols 3..5, 1 at (12+i,12+i), Cm = -R dt at cols 18..20, dt at (12+i,21+i)
+  //   all other rows: identity.       Rows of W: rot -dt at col i; vel -R dt at cols 3..5; bg dt at 6+i; ba dt at 9+i.
+  // This runs ~20 times per scan on the host, on the critical path between two updates.
+  double A[9], Cm[9];
+  for (int i = 0; i < 9; ++i) {
+    A[i] = -Rh[i] * dt;
+    Cm[i] = -R[i] * dt;
   }
-  for (int i = 0; i < 24; ++i)
-    for (int j = 0; j < 24; ++j) {
-      double s = 0;
-      for (int t = 0; t < fn[i]; ++t) s += F[i * 24 + fk[i][t]] * P[fk[i][t] * 24 + j];
-      T[i * 24 + j] = s;
+  const double ndt = -dt;
+  double T[576], Pn[576], WQ[24 * 12];
+  for (int i = 0; i < 24; ++i) {
+    const double* Pi = P + i * 24;
+    double* Ti = T + i * 24;
+    if (i < 3) {
+      const double* Pb = P + (12 + i) * 24;
+      for (int j = 0; j < 24; ++j) Ti[j] = (0.0 + Pi[j]) + dt * Pb[j];
+    } else if (i < 6) {
+      const double* Pb = P + (12 + i) * 24;  // 15 + (i - 3)
+      for (int j = 0; j < 24; ++j) Ti[j] = (0.0 + Pi[j]) + ndt * Pb[j];
+    } else if (i >= 12 && i < 15) {
+      const double* a = A + 3 * (i - 12);
+      const double* cm = Cm + 3 * (i - 12);
+      const double *P3 = P + 3 * 24, *P4 = P + 4 * 24, *P5 = P + 5 * 24, *P18 = P + 18 * 24, *P19 = P + 19 * 24,
+                   *P20 = P + 20 * 24, *Pg = P + (9 + i) * 24;  // 21 + (i - 12)
+      for (int j = 0; j < 24; ++j) {
+        double v = 0.0 + a[0] * P3[j];
+        v += a[1] * P4[j];
+        v += a[2] * P5[j];
+        v += Pi[j];
+        v += cm[0] * P18[j];
+        v += cm[1] * P19[j];
+        v += cm[2] * P20[j];
+        v += dt * Pg[j];
+        Ti[j] = v;
+      }
+    } else {
+      for (int j = 0; j < 24; ++j) Ti[j] = 0.0 + Pi[j];
     }
-  for (int i = 0; i < 24; ++i)
+  }
+  for (int i = 0; i < 24 * 12; ++i) WQ[i] = 0.0;
+  for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 12; ++j) {
-      double s = 0;
-      for (int t = 0; t < wn[i]; ++t) s += W[i * 12 + wk[i][t]] * Q[wk[i][t] * 12 + j];
-      WQ[i * 12 + j] = s;
+      WQ[(3 + i) * 12 + j] = 0.0 + ndt * Q[i * 12 + j];
+      double v = 0.0 + Cm[3 * i] * Q[3 * 12 + j];
+      v += Cm[3 * i + 1] * Q[4 * 12 + j];
+      v += Cm[3 * i + 2] * Q[5 * 12 + j];
+      WQ[(12 + i) * 12 + j] = v;
+      WQ[(15 + i) * 12 + j] = 0.0 + dt * Q[(6 + i) * 12 + j];
+      WQ[(18 + i) * 12 + j] = 0.0 + dt * Q[(9 + i) * 12 + j];
     }
-  for (int i = 0; i < 24; ++i)
-    for (int j = 0; j < 24; ++j) {
-      double s = 0, s2 = 0;
-      for (int t = 0; t < fn[j]; ++t) s += T[i * 24 + fk[j][t]] * F[j * 24 + fk[j][t]];
-      if (wn[i] > 0)
-        for (int t = 0; t < wn[j]; ++t) s2 += WQ[i * 12 + wk[j][t]] * W[j * 12 + wk[j][t]];
-      Pn[i * 24 + j] = s + s2;
+  for (int i = 0; i < 24; ++i) {
+    const double* Ti = T + i * 24;
+    const double* Wi = WQ + i * 12;
+    double* Pi = Pn + i * 24;
+    for (int j = 0; j < 3; ++j) {
+      Pi[j] = ((0.0 + Ti[j]) + Ti[12 + j] * dt) + 0.0;
+      Pi[3 + j] = ((0.0 + Ti[3 + j]) + Ti[15 + j] * ndt) + (0.0 + Wi[j] * ndt);
+      Pi[6 + j] = 0.0 + Ti[6 + j];
+      Pi[9 + j] = 0.0 + Ti[9 + j];
+      double v = 0.0 + Ti[3] * A[3 * j];
+      v += Ti[4] * A[3 * j + 1];
+      v += Ti[5] * A[3 * j + 2];
+      v += Ti[12 + j];
+      v += Ti[18] * Cm[3 * j];
+      v += Ti[19] * Cm[3 * j + 1];
+      v += Ti[20] * Cm[3 * j + 2];
+      v += Ti[21 + j] * dt;
+      double w = 0.0 + Wi[3] * Cm[3 * j];
+      w += Wi[4] * Cm[3 * j + 1];
+      w += Wi[5] * Cm[3 * j + 2];
+      Pi[12 + j] = v + w;
+      Pi[15 + j] = (0.0 + Ti[15 + j]) + (0.0 + Wi[6 + j] * dt);
+      Pi[18 + j] = (0.0 + Ti[18 + j]) + (0.0 + Wi[9 + j] * dt);
+      Pi[21 + j] = 0.0 + Ti[21 + j];
     }
+  }
   memcpy(P, Pn, 8 * 576);
   return LIO_OK;
 }

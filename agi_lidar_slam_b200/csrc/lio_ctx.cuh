@@ -117,6 +117,9 @@ struct lio_ctx {
   bool growth_pending = false;
   cudaEvent_t ev_post = nullptr;    // posterior + preprocess counters are in h_pinned
   cudaEvent_t ev_growth = nullptr;  // map growth done, its counts are in h_pinned[620..626)
+  cudaStream_t prep_stream = nullptr;  // the next scan's upload + undistort + sort run here next to the pending growth
+  cudaEvent_t ev_prep = nullptr;       // preprocessing on prep_stream done
+  cudaEvent_t centroid_wait = nullptr; // preprocess(): make the kernel that writes d_body / d_scan_m wait for this
   int32_t last_counts[3] = {0, 0, 0};
   int growth_rc = 0;                // error of a deferred growth, reported by the next call that settles it
 };

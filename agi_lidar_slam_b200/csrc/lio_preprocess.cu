@@ -423,6 +423,7 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
                                                       has_aux ? c->d_raw_aux : nullptr, sorted_pts, sorted_aux);
     c->launches++;
   }
+  if (c->centroid_wait) LIO_CHECK(c, cudaStreamWaitEvent(c->stream, c->centroid_wait, 0));
   centroid_kernel<<<cgrid > 0 ? cgrid : 1, 128, 0, c->stream>>>(
       sorted_pts, sorted_aux, heads, n_runs, (int)n, max_m, c->d_body,
       reinterpret_cast<float*>(c->d_normvec) /*scratch: mean time*/, c->d_scan_m, c->d_prep_counters);

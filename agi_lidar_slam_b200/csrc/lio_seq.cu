@@ -5,7 +5,10 @@
 //
 // Host code only (no kernels here): everything the device does goes through the lio_* entry points.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
+#include <thread>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -15,6 +18,16 @@
 namespace {
 constexpr double kInitTime = 0.1;        // INIT_TIME (laserMapping.cpp:28)
 constexpr double kMovThreshold = 1.5;    // MOV_THRESHOLD (laserMapping.cpp:40)
+std::atomic<int> g_host_threads{0};      // lio_set_host_threads; 0 = default
+int host_threads() {
+  int n = g_host_threads.load(std::memory_order_relaxed);
+  if (n <= 0) {
+    const char* e = getenv("LIO_HOST_THREADS");
+    n = e ? atoi(e) : 0;
+    if (n <= 0) n = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+  }
+  return std::max(1, std::min(n, 64));
+}
 }  // namespace
 
 struct lio_seq {
@@ -191,6 +204,12 @@ int lio_seq_create(lio_ctx* ctx, const lio_seq_config* cfg, lio_seq** out) {
 
 void lio_seq_destroy(lio_seq* s) { delete s; }
 
+int lio_set_host_threads(int n) {
+  if (n < 0 || n > 64) return LIO_E_INVALID;
+  g_host_threads.store(n, std::memory_order_relaxed);
+  return LIO_OK;
+}
+
 int lio_seq_get_state(const lio_seq* s, lio_state* x, double P[576]) {
   if (!s) return LIO_E_INVALID;
   if (x) *x = s->x;
@@ -236,22 +255,33 @@ int lio_seq_process_many(lio_seq* const* seqs, int n_seq, const lio_seq_input* i
   lio_ctx* due[64];
   int idx_of[64], n_begun = 0, n_due = 0;
   int first_err = LIO_OK;
+  // host stage (IMU propagation) + upload + preprocessing enqueue of every sequence: independent contexts and streams,
+  // so the host side of the sequences runs on a few threads instead of queueing behind one
+  int h_of[64], rc_of[64];
+  int32_t d_of[64];
+  const int nt = std::min(host_threads(), n_seq);
+#pragma omp parallel for num_threads(nt) schedule(static, 1) if (nt > 1)
   for (int k = 0; k < n_seq; ++k) {
     lio_seq* s = seqs[k];
-    const int h = host_stage(s, &in[k], &res[k]);
-    if (h < 0 && first_err == LIO_OK) first_err = h;
-    if (h <= 0) continue;
-    int32_t d = 0;
-    const int rc = lio_scan_step_begin(s->ctx, in[k].lidar, in[k].n, in[k].stride_bytes, s->poses.data(), s->n_poses,
-                                       &s->x, s->P, s->cfg.filter_size_surf, &d);
-    if (rc) {
-      if (first_err == LIO_OK) first_err = rc;
+    d_of[k] = 0;
+    rc_of[k] = LIO_OK;
+    h_of[k] = host_stage(s, &in[k], &res[k]);
+    if (h_of[k] <= 0) continue;
+    rc_of[k] = lio_scan_step_begin(s->ctx, in[k].lidar, in[k].n, in[k].stride_bytes, s->poses.data(), s->n_poses,
+                                   &s->x, s->P, s->cfg.filter_size_surf, &d_of[k]);
+  }
+  for (int k = 0; k < n_seq; ++k) {
+    lio_seq* s = seqs[k];
+    if (h_of[k] < 0 && first_err == LIO_OK) first_err = h_of[k];
+    if (h_of[k] <= 0) continue;
+    if (rc_of[k]) {
+      if (first_err == LIO_OK) first_err = rc_of[k];
       continue;
     }
     idx_of[n_begun] = k;
     begun[n_begun++] = s;
-    if (d) due[n_due++] = s->ctx;
-    s->phase = d ? 1 : 0;
+    if (d_of[k]) due[n_due++] = s->ctx;
+    s->phase = d_of[k] ? 1 : 0;
   }
   // the updates that are due: one cooperative launch per group of <= 8 (all sequences share the filter settings of
   // the first one, as BASELINE.json config 4 has them)
@@ -265,13 +295,13 @@ int lio_seq_process_many(lio_seq* const* seqs, int n_seq, const lio_seq_input* i
       if (rc && first_err == LIO_OK) first_err = rc;
     }
   }
+#pragma omp parallel for num_threads(nt) schedule(static, 1) if (nt > 1)
   for (int j = 0; j < n_begun; ++j) {
     lio_seq* s = begun[j];
-    if (s->phase == 1) {
-      const int rc = lio_scan_step_end(s->ctx, s->cfg.filter_size_map, s->ekf_inited ? 1 : 0);
-      if (rc && first_err == LIO_OK) first_err = rc;
-    }
+    rc_of[j] = s->phase == 1 ? lio_scan_step_end(s->ctx, s->cfg.filter_size_map, s->ekf_inited ? 1 : 0) : LIO_OK;
   }
+  for (int j = 0; j < n_begun; ++j)
+    if (rc_of[j] && first_err == LIO_OK) first_err = rc_of[j];
   for (int j = 0; j < n_begun; ++j) {
     lio_seq* s = begun[j];
     s->phase = 0;

@@ -355,6 +355,10 @@ int lio_seq_process(lio_seq*, const lio_seq_input* in, lio_seq_result* result);
  * cooperative launch per group of 8 (lio_update_enqueue_multi), map growth per sequence, one synchronisation per
  * sequence at the end.  in / result: arrays of n_seq.  All sequences use the filter settings of the first one. */
 int lio_seq_process_many(lio_seq* const* seqs, int n_seq, const lio_seq_input* in, lio_seq_result* results);
+/* Host threads lio_seq_process_many spreads the per-sequence host work over (IMU propagation, uploads, kernel enqueues:
+ * independent contexts and streams).  0 = default: LIO_HOST_THREADS from the environment, else min(8, cores / 2).
+ * Process-wide.  Results do not depend on it. */
+int lio_set_host_threads(int n);
 /* Filter state in / out between scans (relocalisation as in laserMapping_re.cpp:590-600, teacher-forced tests). */
 int lio_seq_get_state(const lio_seq*, lio_state* x, double P[576]);
 int lio_seq_set_state(lio_seq*, const lio_state* x, const double P[576]);

@@ -118,11 +118,32 @@ def test_process_many_equals_independent_replays():
     # the native loop (lio_seq_process_many) takes the same steps
     ctxs = contexts()
     reps = [NativeReplay(c, ReplayConfig(max_iteration=3)) for c in ctxs]
+    native = []
     for j in range(n_scans):
         res = native_process_many(reps, [mg[k][j] for k in range(n_seq)])
+        native.append(res)
         for k in range(n_seq):
             assert (res[k] is None) == (solo[k][j] is None)
             if res[k] is not None:
                 assert np.abs(res[k] - solo[k][j]).max() < 1e-6
+    maps = [c.map_dump() for c in ctxs]
     for c in ctxs:
         c.close()
+    # host threads and deferred map growth change nothing: same bits with one thread / growth inside the step ...
+    for threads, deferred in ((1, False), (3, True)):
+        _cabi.set_host_threads(threads)
+        ctxs = contexts()
+        for c in ctxs:
+            c.set_deferred_growth(deferred)
+        reps = [NativeReplay(c, ReplayConfig(max_iteration=3)) for c in ctxs]
+        for j in range(n_scans):
+            res = native_process_many(reps, [mg[k][j] for k in range(n_seq)])
+            for k in range(n_seq):
+                assert (res[k] is None) == (native[j][k] is None)
+                if res[k] is not None:
+                    assert np.array_equal(res[k], native[j][k]), (threads, deferred, j, k)
+        for k, c in enumerate(ctxs):
+            xyz, ids = c.map_dump()
+            assert np.array_equal(ids, maps[k][1]) and np.array_equal(xyz.view(np.uint32), maps[k][0].view(np.uint32))
+            c.close()
+    _cabi.set_host_threads(0)
