@@ -87,7 +87,9 @@ class CloudLayout(C.Structure):
 
     _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
                 ("off_intensity", C.c_int32), ("off_time", C.c_int32), ("time_type", C.c_int32),
-                ("point_filter_num", C.c_int32), ("rule", C.c_int32), ("time_scale", C.c_float), ("blind", C.c_double)]
+                ("point_filter_num", C.c_int32), ("rule", C.c_int32), ("time_scale", C.c_float), ("blind", C.c_double),
+                ("off_ring", C.c_int32), ("ring_type", C.c_int32), ("off_tag", C.c_int32), ("intensity_type", C.c_int32),
+                ("n_scans", C.c_int32), ("scan_rate", C.c_int32), ("yaw_time", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/lio_b200.h declares (tests/test_abi.py checks the library exports all of them)

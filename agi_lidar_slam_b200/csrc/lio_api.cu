@@ -554,12 +554,42 @@ int lio_scan_preprocess_resident(lio_ctx* c, const void* raw_pts, int64_t n, int
 int lio_scan_preprocess_cloud2(lio_ctx* c, const void* data, int64_t n, const lio_cloud_layout* L, const lio_pose6d* poses,
                                int n_poses, const lio_state* end_state, float leaf, int64_t* n_decoded, int64_t* m) {
   if (!c || n < 0 || (n > 0 && !data) || !L || !(leaf > 0.f)) return LIO_E_INVALID;
-  if (L->point_step < 12 || L->point_step > 256 || L->point_filter_num < 1 || (L->rule != 1 && L->rule != 2) ||
+  const int time_bytes = L->time_type >= 2 ? 8 : 4;
+  if (L->point_step < 12 || L->point_step > 256 || L->point_filter_num < 1 || L->rule < 1 || L->rule > 4 ||
       L->off_x < 0 || L->off_y < 0 || L->off_z < 0 || L->off_x + 4 > L->point_step || L->off_y + 4 > L->point_step ||
-      L->off_z + 4 > L->point_step || L->off_intensity + 4 > L->point_step ||
-      (L->off_time >= 0 && L->off_time + (L->time_type == 2 ? 8 : 4) > L->point_step) || L->time_type < 0 ||
-      L->time_type > 2)
+      L->off_z + 4 > L->point_step || L->intensity_type < 0 || L->intensity_type > 1 ||
+      L->off_intensity + (L->intensity_type == 1 ? 1 : 4) > L->point_step ||
+      (L->off_time >= 0 && L->off_time + time_bytes > L->point_step) || L->time_type < 0 || L->time_type > 3)
     return LIO_E_INVALID;
+  const bool needs_ring = L->rule == 3 || ((L->rule == 2 || L->rule == 4) && L->yaw_time);
+  if (needs_ring && (L->off_ring < 0 || L->ring_type < 0 || L->ring_type > 1 ||
+                     L->off_ring + (L->ring_type == 1 ? 1 : 2) > L->point_step || L->n_scans < 1 || L->n_scans > 256))
+    return LIO_E_INVALID;
+  if (L->rule == 3 && (L->off_tag < 0 || L->off_tag + 1 > L->point_step || L->ring_type != 1 || L->off_time < 0 ||
+                       L->time_type != 1))
+    return LIO_E_INVALID;
+  // given_offset_time (velodyne_handler :296-298, rs_handler :849-851): the LAST record's time field decides
+  bool yaw_times = false;
+  if ((L->rule == 2 || L->rule == 4) && L->yaw_time && n > 0) {
+    if (L->scan_rate < 1) return LIO_E_INVALID;
+    yaw_times = true;
+    if (L->off_time >= 0) {
+      const unsigned char* last = static_cast<const unsigned char*>(data) + (size_t)(n - 1) * L->point_step + L->off_time;
+      if (L->time_type == 0) {
+        float t;
+        memcpy(&t, last, 4);
+        yaw_times = !(t > 0);
+      } else if (L->time_type == 1) {
+        uint32_t t;
+        memcpy(&t, last, 4);
+        yaw_times = !(t > 0);
+      } else {
+        double t;
+        memcpy(&t, last, 8);
+        yaw_times = !(t > 0);
+      }
+    }
+  }
   if (n_poses >= 2 && (!poses || !end_state)) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
   if (n > c->caps.max_scan_points) {
@@ -580,7 +610,7 @@ int lio_scan_preprocess_cloud2(lio_ctx* c, const void* data, int64_t n, const li
   }
   if (n > 0) LIO_CHECK(c, cudaMemcpyAsync(c->d_cloud, data, (size_t)n * L->point_step, cudaMemcpyHostToDevice, c->stream));
   int64_t nd = 0;
-  int rc = decode_cloud2(c, n, *L, &nd);
+  int rc = decode_cloud2(c, n, *L, yaw_times, &nd);
   if (rc) return rc;
   c->n_decoded = nd;
   if (n_decoded) *n_decoded = nd;

@@ -166,5 +166,5 @@ int map_build_scan(lio_ctx* c, const lio_state* x);
 int settle_growth(lio_ctx* c);  // lio_api.cu: waits for a deferred map growth and books its counts (no-op otherwise)
 
 int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux);
-int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, int64_t* n_out);
+int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, bool yaw_times, int64_t* n_out);
 }  // namespace lio

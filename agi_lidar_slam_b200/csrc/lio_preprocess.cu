@@ -10,8 +10,10 @@
 // neighbour sets and validity gates need (the filter loop amplifies 1e-9 input differences to millimetres within
 // ten scans).  The only library calls are cub::DeviceRadixSort / cub::DeviceSelect.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <algorithm>
 
@@ -290,11 +292,29 @@ __global__ void __launch_bounds__(128) centroid_kernel(const float4* sorted_pts,
 // ---------------------------------------------------------------------------------------------------------
 // PointCloud2 decoding (src/preprocess.cpp, oust64_handler :243-268 / velodyne_handler :380-428 with point times)
 // ---------------------------------------------------------------------------------------------------------
+// avia_handler (:160-183, feature extraction off).  A record is `valid` when its line is below N_SCANS and its tag says
+// single / strongest return; valid_num counts the valid records from index 1 on, every point_filter_num-th of them is
+// written into pl_full[i] and kept when it differs from pl_full[i - 1] -- which is the previous RECORD if that one was
+// written too, else the zero-initialised point of pl_full.resize() -- by more than 1e-7 in x or in y, or in z while
+// outside the blind zone (the reference's `a || b || c && d`).
+__device__ __forceinline__ bool avia_valid(const unsigned char* data, const lio_cloud_layout& L, int i) {
+  if (i < 1) return false;  // the handler's loops start at 1
+  const unsigned char* r = data + (size_t)i * L.point_step;
+  const unsigned line = r[L.off_ring], tag = r[L.off_tag];
+  return line < (unsigned)L.n_scans && ((tag & 0x30) == 0x10 || (tag & 0x30) == 0x00);
+}
+struct AviaValid {
+  const unsigned char* data;
+  lio_cloud_layout L;
+  __device__ __forceinline__ int operator()(const int& i) const { return avia_valid(data, L, i) ? 1 : 0; }
+};
+
 struct DecodeKeep {
   const unsigned char* data;
   lio_cloud_layout L;
+  const int* valid_num;  // rule 3: inclusive count of valid records
+  const float* tms;      // yaw-derived times per record (< 0: first point of its ring, dropped), or nullptr
   __device__ __forceinline__ bool operator()(const int& i) const {
-    if (i % L.point_filter_num != 0) return false;
     const unsigned char* r = data + (size_t)i * L.point_step;
     float x, y, z;
     memcpy(&x, r + L.off_x, 4);
@@ -303,13 +323,26 @@ struct DecodeKeep {
     // float products and sums (float * float stays float in C++), then compared in double with the double `blind`
     const double range = (double)__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
     const double b2 = __dmul_rn(L.blind, L.blind);
+    if (L.rule == 3) {
+      if (!avia_valid(data, L, i) || valid_num[i] % L.point_filter_num != 0) return false;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (avia_valid(data, L, i - 1) && valid_num[i - 1] % L.point_filter_num == 0) {
+        memcpy(&px, r - L.point_step + L.off_x, 4);
+        memcpy(&py, r - L.point_step + L.off_y, 4);
+        memcpy(&pz, r - L.point_step + L.off_z, 4);
+      }
+      return (double)fabsf(__fsub_rn(x, px)) > 1e-7 || (double)fabsf(__fsub_rn(y, py)) > 1e-7 ||
+             ((double)fabsf(__fsub_rn(z, pz)) > 1e-7 && range > b2);
+    }
+    if (tms && tms[i] < 0.f) return false;  // first point of its ring: `continue` before the decimation test
+    if (i % L.point_filter_num != 0) return false;
     if (L.rule == 1) return !(range < b2);  // oust64_handler: `if (range < (blind * blind)) continue;`
-    return range > b2;                      // velodyne_handler: `if (x*x + y*y + z*z > (blind * blind)) push_back`
+    return range > b2;                      // velodyne_handler / rs_handler: `if (x*x + y*y + z*z > (blind * blind)) push_back`
   }
 };
 
 __global__ void decode_gather_kernel(const unsigned char* data, lio_cloud_layout L, const int* kept, const int* n_kept,
-                                     float4* raw, float* aux) {
+                                     const float* tms, float4* raw, float* aux) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= *n_kept) return;
   const unsigned char* r = data + (size_t)kept[j] * L.point_step;
@@ -317,9 +350,20 @@ __global__ void decode_gather_kernel(const unsigned char* data, lio_cloud_layout
   memcpy(&x, r + L.off_x, 4);
   memcpy(&y, r + L.off_y, 4);
   memcpy(&z, r + L.off_z, 4);
-  if (L.off_intensity >= 0) memcpy(&inten, r + L.off_intensity, 4);
-  if (L.off_time >= 0) {
-    if (L.time_type == 0) {
+  if (L.off_intensity >= 0) {
+    if (L.intensity_type == 1)
+      inten = (float)r[L.off_intensity];  // livox reflectivity (uint8)
+    else
+      memcpy(&inten, r + L.off_intensity, 4);
+  }
+  if (tms) {
+    t_ms = tms[kept[j]];
+  } else if (L.off_time >= 0) {
+    if (L.rule == 3) {
+      uint32_t t;
+      memcpy(&t, r + L.off_time, 4);
+      t_ms = __fdiv_rn((float)t, 1000000.0f);  // offset_time / float(1000000)  (:165-167)
+    } else if (L.time_type == 0) {
       float t;
       memcpy(&t, r + L.off_time, 4);
       t_ms = __fmul_rn(t, L.time_scale);  // time * time_unit_scale (float * float)
@@ -327,37 +371,140 @@ __global__ void decode_gather_kernel(const unsigned char* data, lio_cloud_layout
       uint32_t t;
       memcpy(&t, r + L.off_time, 4);
       t_ms = __fmul_rn((float)t, L.time_scale);  // uint32 t * float time_unit_scale -> float
-    } else {
+    } else if (L.time_type == 2) {
       double t;
       memcpy(&t, r + L.off_time, 8);
       t_ms = (float)__dmul_rn(t, (double)L.time_scale);
+    } else {  // rs_handler (:880-882): (timestamp - points[0].timestamp) * 1000.0
+      double t, t0;
+      memcpy(&t, r + L.off_time, 8);
+      memcpy(&t0, data + L.off_time, 8);
+      t_ms = (float)__dmul_rn(__dsub_rn(t, t0), 1000.0);
     }
   }
   raw[j] = make_float4(x, y, z, t_ms);
   aux[j] = inten;
 }
 
-// data already in c->d_cloud; leaves the decoded cloud in c->d_raw / c->d_raw_aux and its size in *n_out (host sync)
-int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, int64_t* n_out) {
+// ---- point times from the azimuth, for drivers that give none (velodyne_handler :395-421, rs_handler :886-912)
+__device__ __forceinline__ unsigned record_ring(const unsigned char* r, const lio_cloud_layout& L) {
+  if (L.ring_type == 1) return r[L.off_ring];
+  uint16_t v;
+  memcpy(&v, r + L.off_ring, 2);
+  return v;
+}
+__global__ void ring_key_kernel(const unsigned char* data, lio_cloud_layout L, int n, uint32_t* keys, uint32_t* vals,
+                                int* err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned ring = record_ring(data + (size_t)i * L.point_step, L);
+  if (ring >= (unsigned)L.n_scans) {  // the reference indexes its per-ring vectors out of bounds here
+    *err = 1;
+    ring = (unsigned)L.n_scans - 1;
+  }
+  keys[i] = ring;
+  vals[i] = (uint32_t)i;
+}
+// yaw of every record, in ring-sorted order: atan2(float, float) resolves to the FP32 overload (preprocess.h:6 has
+// `using namespace std`), the product with 57.2957 is FP64
+__global__ void yaw_sorted_kernel(const unsigned char* data, lio_cloud_layout L, const uint32_t* vals_sorted, int n,
+                                  double* yaw) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned char* r = data + (size_t)vals_sorted[j] * L.point_step;
+  float x, y;
+  memcpy(&x, r + L.off_x, 4);
+  memcpy(&y, r + L.off_y, 4);
+  yaw[j] = __dmul_rn((double)atan2f(y, x), 57.2957);
+}
+// One thread per ring walks its records in message order: the first fixes yaw_fp and is dropped, every later one gets
+// (yaw_fp - yaw [+ 360]) / omega_l, plus one revolution when that falls behind the ring's previous time.
+__global__ void yaw_chain_kernel(const uint32_t* keys_sorted, const uint32_t* vals_sorted, const double* yaw, int n,
+                                 int n_scans, double omega_l, float* tms) {
+  const int ring = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ring >= n_scans) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {  // first record of this ring
+    const int mid = (lo + hi) >> 1;
+    if (keys_sorted[mid] < (uint32_t)ring) lo = mid + 1; else hi = mid;
+  }
+  const int beg = lo;
+  hi = n;
+  while (lo < hi) {  // first record of the next ring
+    const int mid = (lo + hi) >> 1;
+    if (keys_sorted[mid] <= (uint32_t)ring) lo = mid + 1; else hi = mid;
+  }
+  const int end = lo;
+  if (beg >= end) return;
+  const double yaw_fp = yaw[beg];
+  const double rev = __ddiv_rn(360.0, omega_l);
+  tms[vals_sorted[beg]] = -1.f;
+  float time_last = 0.f;
+  for (int j = beg + 1; j < end; ++j) {
+    const double ya = yaw[j];
+    float cur = ya <= yaw_fp ? (float)__ddiv_rn(__dsub_rn(yaw_fp, ya), omega_l)
+                             : (float)__ddiv_rn(__dadd_rn(__dsub_rn(yaw_fp, ya), 360.0), omega_l);
+    if (cur < time_last) cur = (float)__dadd_rn((double)cur, rev);
+    time_last = cur;
+    tms[vals_sorted[j]] = cur;
+  }
+}
+
+// data already in c->d_cloud; leaves the decoded cloud in c->d_raw / c->d_raw_aux and its size in *n_out (host sync).
+// yaw_times: the driver gave no point times (the handlers' given_offset_time == false).
+int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, bool yaw_times, int64_t* n_out) {
   int* kept = reinterpret_cast<int*>(c->d_sort_vals_in);
   int* n_kept = c->d_prep_counters + 12;
+  int* d_err = c->d_prep_counters + 13;
   *n_out = 0;
   if (n <= 0) {
     LIO_CHECK(c, cudaMemsetAsync(n_kept, 0, sizeof(int), c->stream));
     return LIO_OK;
   }
-  size_t bytes = c->cub_tmp_bytes;
+  const int grid = (int)((n + 255) / 256);
+  LIO_CHECK(c, cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+  int* valid_num = nullptr;
+  float* tms = nullptr;
   cub::CountingInputIterator<int> it(0);
-  DecodeKeep keep{c->d_cloud, L};
+  if (L.rule == 3) {
+    valid_num = reinterpret_cast<int*>(c->d_sort_vals_out);
+    AviaValid av{c->d_cloud, L};
+    cub::TransformInputIterator<int, AviaValid, cub::CountingInputIterator<int>> flags(it, av);
+    size_t bytes = c->cub_tmp_bytes;
+    LIO_CHECK(c, cub::DeviceScan::InclusiveSum(c->d_cub_tmp, bytes, flags, valid_num, (int)n, c->stream));
+    c->launches += 2;
+  } else if (yaw_times) {
+    uint32_t* keys_in = reinterpret_cast<uint32_t*>(c->d_sort_keys_in);
+    uint32_t* keys_out = reinterpret_cast<uint32_t*>(c->d_sort_keys_out);
+    uint32_t* vals_in = reinterpret_cast<uint32_t*>(c->d_vkeys);
+    uint32_t* vals_out = vals_in + n;
+    double* yaw = reinterpret_cast<double*>(c->d_undist);
+    tms = reinterpret_cast<float*>(c->d_sort_vals_out);
+    ring_key_kernel<<<grid, 256, 0, c->stream>>>(c->d_cloud, L, (int)n, keys_in, vals_in, d_err);
+    int bits = 1;
+    while ((1 << bits) < L.n_scans) ++bits;
+    size_t bytes = c->cub_tmp_bytes;
+    LIO_CHECK(c, cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0,
+                                                 bits, c->stream));  // stable: message order within a ring
+    yaw_sorted_kernel<<<grid, 256, 0, c->stream>>>(c->d_cloud, L, vals_out, (int)n, yaw);
+    yaw_chain_kernel<<<(L.n_scans + 31) / 32, 32, 0, c->stream>>>(keys_out, vals_out, yaw, (int)n, L.n_scans,
+                                                                  0.361 * (double)L.scan_rate, tms);
+    c->launches += 6;
+  }
+  size_t bytes = c->cub_tmp_bytes;
+  DecodeKeep keep{c->d_cloud, L, valid_num, tms};
   LIO_CHECK(c, cub::DeviceSelect::If(c->d_cub_tmp, bytes, it, kept, n_kept, (int)n, keep, c->stream));
-  decode_gather_kernel<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(c->d_cloud, L, kept, n_kept, c->d_raw,
-                                                                      c->d_raw_aux);
+  decode_gather_kernel<<<grid, 256, 0, c->stream>>>(c->d_cloud, L, kept, n_kept, tms, c->d_raw, c->d_raw_aux);
   c->launches += 3;
   LIO_CHECK(c, cudaGetLastError());
-  int h = 0;
-  LIO_CHECK(c, cudaMemcpyAsync(&h, n_kept, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int h[2] = {0, 0};
+  LIO_CHECK(c, cudaMemcpyAsync(h, n_kept, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
-  *n_out = h;
+  if (h[1]) {
+    c->err = "a ring index is >= n_scans (the reference indexes its per-ring state out of bounds)";
+    return LIO_E_INVALID;
+  }
+  *n_out = h[0];
   return LIO_OK;
 }
 
@@ -368,6 +515,9 @@ size_t preprocess_sort_bytes(int64_t n) {
   cub::CountingInputIterator<int> it(0);
   HeadFlag hf{nullptr};
   cub::DeviceSelect::If(nullptr, b, it, (int*)nullptr, (int*)nullptr, (int)n, hf);
+  size_t d = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, d, (const int*)nullptr, (int*)nullptr, (int)n);
+  a = a > d ? a : d;
   return a > b ? a : b;
 }
 

@@ -143,15 +143,33 @@ int lio_scan_upload(lio_ctx* ctx, const void* down_pts, int64_t m, int stride_by
 typedef struct lio_cloud_layout {
   int32_t point_step;       /* bytes per point record                                                  */
   int32_t off_x, off_y, off_z;        /* float32 fields                                                */
-  int32_t off_intensity;    /* float32, or -1                                                          */
+  int32_t off_intensity;    /* intensity field (see intensity_type), or -1                             */
   int32_t off_time;         /* per-point time field, or -1 (all points at t = 0)                       */
-  int32_t time_type;        /* 0 = float32 (velodyne_ros::Point::time), 1 = uint32 (ouster_ros::Point::t), 2 = float64 */
-  int32_t point_filter_num; /* keep every point_filter_num-th record (i % n == 0)                      */
+  int32_t time_type;        /* 0 = float32 (velodyne_ros::Point::time), 1 = uint32 (ouster_ros::Point::t,
+                               livox offset_time), 2 = float64, 3 = float64 relative to record 0, in seconds
+                               (rslidar_ros::Point::timestamp: (t - t0) * 1000.0, :880-882)            */
+  int32_t point_filter_num; /* keep every point_filter_num-th record (i % n == 0; rule 3: every n-th VALID record) */
   int32_t rule;             /* 1 = oust64_handler (:243-268): drop when range^2 < blind^2;
-                               2 = velodyne_handler with point times (:380-428): keep when range^2 > blind^2
+                               2 = velodyne_handler (:380-428): keep when range^2 > blind^2
+                               3 = avia_handler (:160-183) on livox CustomPoint records: line / tag test, decimation
+                                   over the valid records, "differs from the previous record" test, time =
+                                   offset_time / float(1000000) (time_scale unused)
+                               4 = rs_handler (:872-921): as rule 2
                                (range^2 = FP32 x*x + y*y + z*z, compared in FP64 with the double blind) */
   float time_scale;         /* time_unit_scale: field units -> ms (preprocess.cpp:55-66)               */
   double blind;             /* blind radius [m] (preprocess.h:161)                                     */
+  /* zero-initialise what a sensor does not have */
+  int32_t off_ring;         /* ring (rules 2, 4 with yaw_time) / line (rule 3) field, or -1            */
+  int32_t ring_type;        /* 0 = uint16, 1 = uint8                                                   */
+  int32_t off_tag;          /* rule 3: livox tag (uint8)                                               */
+  int32_t intensity_type;   /* 0 = float32, 1 = uint8 (livox reflectivity)                             */
+  int32_t n_scans;          /* N_SCANS: rule 3 keeps line < n_scans; yaw_time: rings must be < n_scans */
+  int32_t scan_rate;        /* SCAN_RATE [Hz] (omega_l = 0.361 * SCAN_RATE deg/ms)                     */
+  int32_t yaw_time;         /* rules 2, 4: 1 = do as the handlers do when the LAST record's time field is not > 0
+                               (given_offset_time == false, :296-310): per ring, the first record fixes yaw_fp and is
+                               dropped, later ones get (yaw_fp - yaw [+ 360]) / omega_l, plus a revolution when that
+                               falls behind the ring's previous time; 0 = always read the time field  */
+  int32_t reserved;
 } lio_cloud_layout;
 /* ≙ Preprocess::process (preprocess.cpp:48-86) for a PointCloud2 lidar followed by lio_scan_preprocess_resident: the
  * raw message bytes go up once, are decoded, decimated and blind-filtered on the device (order preserved) and run

@@ -487,3 +487,98 @@ def decode_cloud2(data, point_step, off_x, off_y, off_z, off_intensity, off_time
     b2 = np.float64(blind) * np.float64(blind)
     keep = (np.arange(n) % point_filter_num == 0) & (~(rng < b2) if rule == 1 else (rng > b2))
     return np.stack([x, y, z, tms], 1)[keep].astype(np.float32), inten[keep].astype(np.float32)
+
+
+def _fields(data, point_step):
+    data = np.ascontiguousarray(data, np.uint8).reshape(-1, point_step)
+
+    def field(off, dt):
+        w = np.dtype(dt).itemsize
+        return np.ascontiguousarray(data[:, off:off + w]).view(dt)[:, 0]
+
+    return data.shape[0], field
+
+
+def decode_avia(data, point_step, off_x, off_y, off_z, off_refl, off_time, off_tag, off_line, n_scans, blind,
+                point_filter_num):
+    """avia_handler, feature extraction off (preprocess.cpp:160-183), over livox CustomPoint records, as written: the
+    loop starts at record 1; a record is valid when line < N_SCANS and (tag & 0x30) is 0x10 or 0x00; every
+    point_filter_num-th VALID record is copied into pl_full[i] with curvature = offset_time / float(1000000), and pushed
+    when it differs from pl_full[i - 1] (zero-initialised unless record i - 1 was copied too) by more than 1e-7 in x, or
+    in y, or (in z and the squared range exceeds blind^2) -- `a || b || c && d`.
+    Returns (xyzt (k,4) float32, intensity (k,) float32)."""
+    n, field = _fields(data, point_step)
+    x, y, z = field(off_x, "<f4"), field(off_y, "<f4"), field(off_z, "<f4")
+    refl, tag, line, t = field(off_refl, "u1"), field(off_tag, "u1"), field(off_line, "u1"), field(off_time, "<u4")
+    pl_full = np.zeros((max(n, 1), 3), np.float32)
+    b2 = np.float64(blind) * np.float64(blind)
+    valid_num = 0
+    out, inten = [], []
+    for i in range(1, n):
+        if line[i] < n_scans and ((tag[i] & 0x30) == 0x10 or (tag[i] & 0x30) == 0x00):
+            valid_num += 1
+            if valid_num % point_filter_num == 0:
+                pl_full[i] = (x[i], y[i], z[i])
+                cur = np.float32(t[i]) / np.float32(1000000)
+                dx = np.abs(np.float32(x[i] - pl_full[i - 1, 0]))
+                dy = np.abs(np.float32(y[i] - pl_full[i - 1, 1]))
+                dz = np.abs(np.float32(z[i] - pl_full[i - 1, 2]))
+                rng = np.float64(np.float32(np.float32(x[i] * x[i] + y[i] * y[i]) + z[i] * z[i]))
+                if np.float64(dx) > 1e-7 or np.float64(dy) > 1e-7 or (np.float64(dz) > 1e-7 and rng > b2):
+                    out.append((x[i], y[i], z[i], cur))
+                    inten.append(np.float32(refl[i]))
+    return np.array(out, np.float32).reshape(-1, 4), np.array(inten, np.float32)
+
+
+def decode_yaw_times(data, point_step, off_x, off_y, off_z, off_intensity, intensity_dtype, off_ring, ring_dtype, n_scans,
+                     scan_rate, blind, point_filter_num):
+    """velodyne_handler (preprocess.cpp:380-428) / rs_handler (:872-921) when the driver gives no point times
+    (given_offset_time == false), feature extraction off.  Per ring: the first record fixes yaw_fp and is skipped
+    (`continue`), every later record gets curvature = (yaw_fp - yaw) / omega_l, or (yaw_fp - yaw + 360) / omega_l when
+    yaw > yaw_fp, plus 360 / omega_l when that is smaller than the ring's previous curvature.  yaw = atan2(y, x) in FP32
+    (std::atan2(float, float): preprocess.h:6 has `using namespace std`) times the double 57.2957; yaw_fp is double,
+    time_last and curvature are float.  Then every point_filter_num-th RECORD (by index) outside the blind zone is kept."""
+    n, field = _fields(data, point_step)
+    x, y, z = field(off_x, "<f4"), field(off_y, "<f4"), field(off_z, "<f4")
+    inten = field(off_intensity, intensity_dtype).astype(np.float32) if off_intensity >= 0 else np.zeros(n, np.float32)
+    ring = field(off_ring, ring_dtype)
+    omega_l = 0.361 * scan_rate
+    yaw = np.arctan2(y, x).astype(np.float32).astype(np.float64) * 57.2957
+    rng = ((x * x + y * y) + z * z).astype(np.float32).astype(np.float64)
+    b2 = np.float64(blind) * np.float64(blind)
+    is_first = [True] * n_scans
+    yaw_fp = [0.0] * n_scans
+    time_last = [np.float32(0)] * n_scans
+    out, oi = [], []
+    for i in range(n):
+        layer = int(ring[i])
+        ya = yaw[i]
+        if is_first[layer]:
+            yaw_fp[layer] = ya
+            is_first[layer] = False
+            time_last[layer] = np.float32(0)
+            continue
+        if ya <= yaw_fp[layer]:
+            cur = np.float32((yaw_fp[layer] - ya) / omega_l)
+        else:
+            cur = np.float32((yaw_fp[layer] - ya + 360.0) / omega_l)
+        if cur < time_last[layer]:
+            cur = np.float32(np.float64(cur) + 360.0 / omega_l)
+        time_last[layer] = cur
+        if i % point_filter_num == 0 and rng[i] > b2:
+            out.append((x[i], y[i], z[i], cur))
+            oi.append(inten[i])
+    return np.array(out, np.float32).reshape(-1, 4), np.array(oi, np.float32)
+
+
+def decode_rs(data, point_step, off_x, off_y, off_z, off_intensity, off_time, blind, point_filter_num):
+    """rs_handler with point timestamps (preprocess.cpp:872-921): curvature = (timestamp - points[0].timestamp) * 1000.0
+    in FP64, stored as FP32; uint8 intensity; every point_filter_num-th record with squared range > blind^2."""
+    n, field = _fields(data, point_step)
+    x, y, z = field(off_x, "<f4"), field(off_y, "<f4"), field(off_z, "<f4")
+    inten = field(off_intensity, "u1").astype(np.float32)
+    ts = field(off_time, "<f8")
+    tms = ((ts - ts[0]) * 1000.0).astype(np.float32) if n else np.zeros(0, np.float32)
+    rng = ((x * x + y * y) + z * z).astype(np.float32).astype(np.float64)
+    keep = (np.arange(n) % point_filter_num == 0) & (rng > np.float64(blind) * np.float64(blind))
+    return np.stack([x, y, z, tms], 1)[keep].astype(np.float32), inten[keep]
