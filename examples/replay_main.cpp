@@ -72,9 +72,19 @@ int main() {
   x.rot[0] = std::cos((yaw + 0.0175) / 2);
   x.rot[3] = std::sin((yaw + 0.0175) / 2);
   kf.change_x(x);
-  kf.update_iterated_dyn_share_modified(0.001 /*LASER_POINT_COV*/, feats_down_body.data(),
-                                        (int64_t)feats_down_body.size(), ikdtree, 4, false);
+  // the reference's call, argument for argument (laserMapping.cpp:771-774): a cloud pointer and the Nearest_Points
+  // container that map_incremental reads afterwards
+  struct Cloud {
+    Tree::PointVector points;
+  };
+  auto feats_down = std::make_shared<Cloud>();
+  feats_down->points = feats_down_body;
+  std::vector<Tree::PointVector> Nearest_Points;
+  kf.update_iterated_dyn_share_modified(0.001 /*LASER_POINT_COV*/, feats_down, ikdtree, Nearest_Points, 4, false);
   if (kf.last_error != LIO_OK) return 4;
+  size_t with5 = 0;
+  for (const auto& v : Nearest_Points) with5 += v.size() == 5;
+  if (Nearest_Points.size() != feats_down_body.size() || with5 < (size_t)kf.effct_feat_num) return 5;
   const lio_state xs = kf.get_x();
   const double ex = xs.pos[0] - tx, ey = xs.pos[1] - ty, ez = xs.pos[2] - tz;
   const double eyaw = 2.0 * std::atan2(xs.rot[3], xs.rot[0]) - yaw;

@@ -167,8 +167,8 @@ class esekf {
     last_error = lio_predict(&x_, P_, dt, Q, i_in.acc, i_in.gyro);
   }
   // esekfom.hpp:270-346.  feats_down_body: the downsampled scan; when it is the cloud lio_scan_preprocess just left on
-  // the device pass nullptr / 0 and nothing is copied.  Nearest_Points is filled lazily: map_incremental should use
-  // lio_map_incremental (device side); fetch_neighbors() copies the cache for host code that still wants it.
+  // the device pass nullptr / 0 and nothing is copied.  Nearest_Points stays on the device: map_incremental should use
+  // lio_map_incremental (device side); the overload below / fetch_neighbors() copy the cache for host code that wants it.
   template <typename PointType, typename Alloc>
   void update_iterated_dyn_share_modified(double R, const PointType* feats_down_body, int64_t feats_down_size,
                                           KD_TREE<PointType, Alloc>& ikdtree, int maximum_iter, bool extrinsic_est) {
@@ -178,6 +178,37 @@ class esekf {
       if (last_error != LIO_OK) return;
     }
     last_error = lio_update_scan(c, &x_, P_, R, maximum_iter, extrinsic_est ? 1 : 0, &effct_feat_num, &n_passes);
+  }
+  // The reference's own argument list (esekfom.hpp:270-275): feats_down_body is anything that points at an object with a
+  // `points` vector (PointCloudXYZI::Ptr qualifies), Nearest_Points comes back filled as the reference leaves it -- the
+  // neighbours of the last SEARCH pass, ascending by distance, fewer than 5 where the map had fewer within range -- for
+  // host code that still runs map_incremental (laserMapping.cpp:382-433) itself.
+  template <typename CloudPtr, typename PointType, typename Alloc>
+  void update_iterated_dyn_share_modified(double R, CloudPtr& feats_down_body, KD_TREE<PointType, Alloc>& ikdtree,
+                                          std::vector<std::vector<PointType, Alloc>>& Nearest_Points, int maximum_iter,
+                                          bool extrinsic_est) {
+    const auto& pts = feats_down_body->points;
+    update_iterated_dyn_share_modified(R, pts.data(), (int64_t)pts.size(), ikdtree, maximum_iter, extrinsic_est);
+    if (last_error == LIO_OK) fetch_neighbors(ikdtree, pts.size(), Nearest_Points);
+  }
+  // Copies the device-side Nearest_Points cache of the last update (m = feats_down_size) into the reference's container.
+  template <typename PointType, typename Alloc>
+  void fetch_neighbors(KD_TREE<PointType, Alloc>& ikdtree, size_t m,
+                       std::vector<std::vector<PointType, Alloc>>& Nearest_Points) {
+    std::vector<int32_t> idx(5 * m);
+    std::vector<float> xyz(15 * m);
+    last_error = lio_get_neighbors(ikdtree.context()->get(), idx.data(), nullptr, xyz.data(), nullptr, nullptr, nullptr);
+    if (last_error != LIO_OK) return;
+    Nearest_Points.resize(m);  // laserMapping.cpp:771
+    for (size_t i = 0; i < m; ++i) {
+      Nearest_Points[i].clear();
+      for (int r = 0; r < 5 && idx[5 * i + r] >= 0; ++r) {
+        PointType p;
+        std::memset(&p, 0, sizeof(p));
+        std::memcpy(&p, &xyz[15 * i + 3 * r], 12);
+        Nearest_Points[i].push_back(p);
+      }
+    }
   }
   int32_t effct_feat_num = 0;  // esekfom.hpp:26
   int32_t n_passes = 0;
