@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--poses", type=int, default=1)
     a = ap.parse_args()
+    a.workload = "os1_128_2m"
     wl = bench.make_workload(a, 0)
     mp = wl["map"]
     ctx = _cabi.Context(0, max_scan_points=max(1 << 18, a.rings * a.cols), max_down_points=100000,
