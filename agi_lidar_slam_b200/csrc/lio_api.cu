@@ -199,12 +199,10 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_undist, sizeof(float4) * N);
   ALLOC(c->d_vkeys, 12 * N);
   ALLOC(c->d_poses, sizeof(lio_pose6d) * 128);
-  c->svox_cap = pow2_at_least((uint64_t)N * 2);
-  ALLOC(c->d_svox_key, 8 * (size_t)c->svox_cap);
-  ALLOC(c->d_svox_acc, 8 * 5 * (size_t)c->svox_cap);
-  ALLOC(c->d_svox_cnt, 4 * (size_t)c->svox_cap);
-  ALLOC(c->d_sort_keys_in, 8 * N);
-  ALLOC(c->d_sort_keys_out, 8 * N);
+  ALLOC(c->d_sorted_aux, 4 * N);
+  ALLOC(c->d_run_heads, 4 * N);
+  ALLOC(c->d_sort_keys_in, 4 * N);
+  ALLOC(c->d_sort_keys_out, 4 * N);
   ALLOC(c->d_sort_vals_in, 4 * N);
   ALLOC(c->d_sort_vals_out, 4 * N);
   c->cub_tmp_bytes = preprocess_sort_bytes((int64_t)N);
@@ -260,7 +258,7 @@ void lio_destroy(lio_ctx* c) {
                   c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,      c->d_mailbox,
                   c->d_cloud,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
-                  c->d_vkeys,     c->d_poses,       c->d_svox_key,    c->d_svox_acc,    c->d_svox_cnt,
+                  c->d_vkeys,     c->d_poses,       c->d_sorted_aux,  c->d_run_heads,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
                   c->d_prep_counters};
   for (void* p : ptrs)

@@ -92,12 +92,10 @@ struct lio_ctx {
   float4* d_undist = nullptr;       // N undistorted
   int* d_vkeys = nullptr;           // N x 3
   lio_pose6d* d_poses = nullptr;    // up to 256
-  uint32_t svox_cap = 0;            // scan-voxel hash capacity
-  unsigned long long* d_svox_key = nullptr;
-  long long* d_svox_acc = nullptr;  // cap x 5 fixed-point sums (x,y,z,intensity,time)
-  uint32_t* d_svox_cnt = nullptr;
-  unsigned long long* d_sort_keys_in = nullptr;
-  unsigned long long* d_sort_keys_out = nullptr;
+  float* d_sorted_aux = nullptr;    // N intensities in leaf-sorted order
+  int* d_run_heads = nullptr;       // first sorted position of every occupied leaf
+  uint32_t* d_sort_keys_in = nullptr;  // N linear leaf indices (and ring keys while decoding)
+  uint32_t* d_sort_keys_out = nullptr;
   uint32_t* d_sort_vals_in = nullptr;
   uint32_t* d_sort_vals_out = nullptr;
   void* d_cub_tmp = nullptr;

@@ -474,8 +474,8 @@ int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, bool yaw_tim
     LIO_CHECK(c, cub::DeviceScan::InclusiveSum(c->d_cub_tmp, bytes, flags, valid_num, (int)n, c->stream));
     c->launches += 2;
   } else if (yaw_times) {
-    uint32_t* keys_in = reinterpret_cast<uint32_t*>(c->d_sort_keys_in);
-    uint32_t* keys_out = reinterpret_cast<uint32_t*>(c->d_sort_keys_out);
+    uint32_t* keys_in = c->d_sort_keys_in;
+    uint32_t* keys_out = c->d_sort_keys_out;
     uint32_t* vals_in = reinterpret_cast<uint32_t*>(c->d_vkeys);
     uint32_t* vals_out = vals_in + n;
     double* yaw = reinterpret_cast<double*>(c->d_undist);
@@ -543,9 +543,9 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
   a.vkeys = c->d_vkeys;
   a.counters = c->d_prep_counters;
   const int grid = (int)((n + 255) / 256);
-  uint32_t* keys_in = reinterpret_cast<uint32_t*>(c->d_sort_keys_in);
-  uint32_t* keys_out = reinterpret_cast<uint32_t*>(c->d_sort_keys_out);
-  int* heads = reinterpret_cast<int*>(c->d_svox_cnt);
+  uint32_t* keys_in = c->d_sort_keys_in;
+  uint32_t* keys_out = c->d_sort_keys_out;
+  int* heads = c->d_run_heads;
   int* n_runs = c->d_prep_counters + 10;
   prep_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_prep_counters);
   c->launches++;
@@ -567,7 +567,7 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
   const int max_m = (int)c->caps.max_down_points;
   const int cgrid = (int)((std::min<int64_t>(n, max_m) + 127) / 128);
   float4* sorted_pts = c->d_raw;  // the raw scan has been consumed by now
-  float* sorted_aux = has_aux ? reinterpret_cast<float*>(c->d_svox_acc) : nullptr;
+  float* sorted_aux = has_aux ? c->d_sorted_aux : nullptr;
   if (n > 0) {
     gather_sorted_kernel<<<grid, 256, 0, c->stream>>>(c->d_sort_vals_out, (int)n, c->d_undist,
                                                       has_aux ? c->d_raw_aux : nullptr, sorted_pts, sorted_aux);
