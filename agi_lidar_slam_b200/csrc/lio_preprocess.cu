@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
     a.vkeys[3 * i + 1] = ky;
     a.vkeys[3 * i + 2] = kz;
   }
-  // voxel index bounds (PCL: min_b / max_b from getMinMax3D): warp-reduce, then 6 atomics per warp
+  // voxel index bounds (PCL: min_b / max_b from getMinMax3D): warp-reduce, block-reduce, 6 atomics per block
   const unsigned FULL = 0xffffffffu;
   const int big = 0x7fffffff;
   int mnx = act ? kx : big, mny = act ? ky : big, mnz = act ? kz : big;
@@ -113,13 +113,30 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
   mxx = __reduce_max_sync(FULL, mxx);
   mxy = __reduce_max_sync(FULL, mxy);
   mxz = __reduce_max_sync(FULL, mxz);
-  if ((threadIdx.x & 31) == 0 && mnx != big) {
-    atomicMin(&a.counters[1], mnx);
-    atomicMin(&a.counters[2], mny);
-    atomicMin(&a.counters[3], mnz);
-    atomicMax(&a.counters[4], mxx);
-    atomicMax(&a.counters[5], mxy);
-    atomicMax(&a.counters[6], mxz);
+  // Six words of one L2 sector are the target: 4,096 warps sending their own atomics (or even just reading the words to
+  // filter them) queue up on that sector -- 75 % of this kernel's samples at 131 k points.  So the block reduces first
+  // and six of its threads send one atomic each: 3 k requests instead of 25 k.
+  __shared__ int s_red[6][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_red[0][warp] = mnx;
+    s_red[1][warp] = mny;
+    s_red[2][warp] = mnz;
+    s_red[3][warp] = mxx;
+    s_red[4][warp] = mxy;
+    s_red[5][warp] = mxz;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const bool is_min = threadIdx.x < 3;
+    int v = s_red[threadIdx.x][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) v = is_min ? min(v, s_red[threadIdx.x][w]) : max(v, s_red[threadIdx.x][w]);
+    if (is_min) {
+      if (v != big) atomicMin(&a.counters[1 + threadIdx.x], v);
+    } else {
+      if (v != -big) atomicMax(&a.counters[1 + threadIdx.x], v);
+    }
   }
 }
 
