@@ -165,3 +165,29 @@ def test_deferred_map_growth_changes_nothing():
     finally:
         a_ctx.close()
         b_ctx.close()
+
+
+def test_deferred_growth_reports_capacity_errors_one_call_later():
+    """A map that outgrows lio_caps.max_map_points: the synchronous loop fails in the scan whose growth overflowed, the
+    deferred loop in the next call that settles that growth -- never silently."""
+    from agi_lidar_slam_b200 import _cabi, synth
+    from agi_lidar_slam_b200.replay import MeasureGroup, NativeReplay, ReplayConfig
+
+    seq = synth.sequence(40, 2002, rings=16, cols=600)
+    failed_at = {}
+    for deferred in (False, True):
+        ctx = _cabi.Context(0, max_scan_points=1 << 16, max_down_points=1 << 15, max_map_points=6000)
+        try:
+            ctx.set_deferred_growth(deferred)
+            rep = NativeReplay(ctx, ReplayConfig(max_iteration=3))
+            for j, m in enumerate(seq):
+                try:
+                    rep.process(MeasureGroup(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"]))
+                except _cabi.LioError as e:
+                    assert e.code == _cabi.LIO_E_CAPACITY, e
+                    failed_at[deferred] = j
+                    break
+        finally:
+            ctx.close()
+    assert False in failed_at and True in failed_at, failed_at
+    assert failed_at[True] in (failed_at[False], failed_at[False] + 1), failed_at
