@@ -68,7 +68,7 @@ def parse():
                     help="sharded workload: blob exchange inside the persistent kernel over NVLink peer memory (peer) "
                          "or pass kernel -> NCCL all-reduce -> solve kernel per pass (nccl)")
     ap.add_argument("--host-threads", type=int, default=0, help="trajectory workloads: host threads of lio_seq_process_many "
-                    "(0: min(8, sequences, cores / ranks))")
+                    "(0: min(8, sequences, cores / ranks - 1))")
     ap.add_argument("--sync-growth", action="store_true",
                     help="trajectory workloads: wait for each scan's map growth inside its step (default: deferred, the "
                          "step returns with the posterior as the reference publishes before map_incremental)")
@@ -332,7 +332,9 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
     # the native main loop (lio_seq_process / lio_seq_process_many): one C-ABI call per step
     for c in ctxs:
         c.set_deferred_growth(not args.sync_growth)
-    host_threads = args.host_threads or max(1, min(8, n_seq, (os.cpu_count() or 1) // max(1, world)))
+    # one core per rank stays free for the rank's main / NCCL / sampler threads: with every core in an OpenMP team the
+    # spinning teams starve each other (8 ranks on 32 cores: 4 threads per rank 32.7 k scans/s, 3 threads 48.1 k)
+    host_threads = args.host_threads or max(1, min(8, n_seq, (os.cpu_count() or 1) // max(1, world) - 1))
     _cabi.set_host_threads(host_threads)
     runs = [_cabi.Sequence(c, max_iteration=3) for c in ctxs]
     # scans wait in pinned host memory (what a driver's receive buffer is), as the e2e rule of the bench contract asks
