@@ -100,7 +100,7 @@ EXPORTS = [
     "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_update_scan_host", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_enqueue_multi", "lio_scan_step", "lio_scan_step_begin", "lio_scan_step_end",
-    "lio_scan_step_finish", "lio_set_deferred_growth", "lio_scan_step_settle", "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
+    "lio_scan_step_finish", "lio_scan_step_prefetch", "lio_set_deferred_growth", "lio_scan_step_settle", "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_peer_handle", "lio_peer_connect",
     "lio_update_enqueue_sharded", "lio_peer_status", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
@@ -158,6 +158,7 @@ def load_library() -> C.CDLL:
         "lio_scan_step_begin": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, vp, C.c_float, vp]),
         "lio_scan_step_end": (C.c_int, [vp, C.c_float, C.c_int]),
         "lio_scan_step_finish": (C.c_int, [vp, vp, vp, vp]),
+        "lio_scan_step_prefetch": (C.c_int, [vp, vp, i64, C.c_int]),
         "lio_set_deferred_growth": (C.c_int, [vp, C.c_int]),
         "lio_scan_step_settle": (C.c_int, [vp, vp]),
         "lio_update_begin": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),

@@ -157,7 +157,6 @@ static int create_impl(lio_ctx* c) {
   }
   ALLOC(c->d_cls, M);
   ALLOC(c->d_add_a, sizeof(float4) * M);
-  ALLOC(c->d_add_b, sizeof(float4) * M);
   LIO_CHECK(c, cudaMemset(c->d_selected, 0, M));
   LIO_CHECK(c, cudaMemset(c->d_near_cnt, 0, 4 * M));
   LIO_CHECK(c, cudaMemset(c->d_blob, 0, 8 * LIO_BLOB));
@@ -254,7 +253,7 @@ void lio_destroy(lio_ctx* c) {
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
                   c->d_vox_best,  c->d_vox_key,     c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
-                  c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,       c->d_add_b,
+                  c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,
                   c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,      c->d_mailbox,
                   c->d_cloud,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
@@ -462,7 +461,7 @@ int lio_knn5_resident(lio_ctx* c, int64_t m) {
 
 // ---------------------------------------------------------------- scan
 static int preprocess_common(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses,
-                             int n_poses, const lio_state* end_state, float leaf) {
+                             int n_poses, const lio_state* end_state, float leaf, bool staged = false) {
   if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !raw_pts) || !(leaf > 0.f)) return LIO_E_INVALID;
   if (n_poses >= 2 && (!poses || !end_state)) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
@@ -475,7 +474,8 @@ static int preprocess_common(lio_ctx* c, const void* raw_pts, int64_t n, int str
     return LIO_E_CAPACITY;
   }
   // stride 48: time = curvature (offset 36), intensity (offset 32) rides along as aux
-  int rc = stage_points(c, raw_pts, n, stride, 36, c->d_raw, 32, c->d_raw_aux, reinterpret_cast<float*>(c->d_vkeys));
+  int rc = staged ? LIO_OK
+                  : stage_points(c, raw_pts, n, stride, 36, c->d_raw, 32, c->d_raw_aux, reinterpret_cast<float*>(c->d_vkeys));
   if (rc) return rc;
   if (n_poses >= 2)
     LIO_CHECK(c, cudaMemcpyAsync(c->d_poses, poses, sizeof(lio_pose6d) * n_poses, cudaMemcpyHostToDevice, c->stream));
@@ -804,12 +804,37 @@ int lio_update_scan_host(lio_ctx* c, const void* down_pts, int64_t m, int stride
 // laserMapping.cpp:737-785 for one scan -- VoxelGrid(UndistortPcl(scan)), the feats_down_size < 5 skip, the first-scan
 // Build, update_iterated_dyn_share_modified, map_incremental -- enqueued back to back: M, the class counts and the insert
 // sizes stay on the device, the host synchronises ONCE, at the end, for {posterior, M, counts, error flags}.
+// The raw records of the next scan do not depend on the filter state: a host that still has the IMU propagation to do
+// (lio_seq_process) sends them first, so the copy runs underneath that host work instead of after it.
+int lio_scan_step_prefetch(lio_ctx* c, const void* raw_pts, int64_t n, int stride) {
+  if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !raw_pts)) return LIO_E_INVALID;
+  c->staged_ptr = nullptr;
+  if (n == 0 || !c->map_built || n > c->caps.max_scan_points) return LIO_OK;  // nothing to gain / lio_scan_step_begin reports
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  const bool split = c->deferred_growth && c->growth_pending;
+  cudaStream_t main_stream = c->stream;
+  if (split) {
+    LIO_CHECK(c, cudaStreamWaitEvent(c->prep_stream, c->ev_post, 0));
+    c->stream = c->prep_stream;
+  }
+  const int rc = stage_points(c, raw_pts, n, stride, 36, c->d_raw, 32, c->d_raw_aux, reinterpret_cast<float*>(c->d_vkeys));
+  c->stream = main_stream;
+  if (rc) return rc;
+  c->staged_ptr = raw_pts;
+  c->staged_n = n;
+  c->staged_stride = stride;
+  c->staged_on_prep = split;
+  return LIO_OK;
+}
+
 int lio_scan_step_begin(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses, int n_poses,
                         const lio_state* x, const double P[576], float leaf_surf, int32_t* update_due) {
   if (!c || !x || !P || !update_due) return LIO_E_INVALID;
   *update_due = 0;
   c->step_phase = 0;
   c->min_m = 0;
+  const bool staged = c->staged_ptr != nullptr && c->staged_ptr == raw_pts && c->staged_n == n && c->staged_stride == stride;
+  c->staged_ptr = nullptr;
   // A deferred growth of the previous scan is still on the stream: upload, undistort and sort this scan on the second
   // stream next to it.  The growth reads d_body / d_scan_m (classification), so the one kernel that overwrites them
   // (centroids) waits for it; everything before touches preprocessing buffers only.  The host has the previous
@@ -822,7 +847,11 @@ int lio_scan_step_begin(lio_ctx* c, const void* raw_pts, int64_t n, int stride, 
     c->stream = c->prep_stream;
     c->centroid_wait = c->ev_growth;
   }
-  int rc = preprocess_common(c, raw_pts, n, stride, poses, n_poses, x, leaf_surf);
+  if (staged && c->staged_on_prep && !split) {  // the growth was settled in between: order the copy before this stream
+    LIO_CHECK(c, cudaEventRecord(c->ev_prep, c->prep_stream));
+    LIO_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_prep, 0));
+  }
+  int rc = preprocess_common(c, raw_pts, n, stride, poses, n_poses, x, leaf_surf, staged);
   if (split) {
     c->stream = main_stream;
     c->centroid_wait = nullptr;

@@ -62,8 +62,7 @@ struct lio_ctx {
   double* d_pub = nullptr;          // 34 doubles published by the solving block after every Kalman step
   long long* d_dbg = nullptr;       // in-kernel timeline (only with LIO_TIMELINE=1)
   uint8_t* d_cls = nullptr;         // map_incremental class per point
-  float4* d_add_a = nullptr;        // compacted PointToAdd
-  float4* d_add_b = nullptr;        // compacted PointNoNeedDownsample
+  float4* d_add_a = nullptr;        // compacted PointToAdd, PointNoNeedDownsample right behind it
 
   // ---- filter state
   double* d_state_blk = nullptr;    // one allocation: {x 26, P 576, ctrl 4} {x0 26, P0 576} {xprop 26} {dx 24}
@@ -100,7 +99,7 @@ struct lio_ctx {
   uint32_t* d_sort_vals_out = nullptr;
   void* d_cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
-  int* d_prep_counters = nullptr;   // [0] M, [1..6] key min/max, [7] error, [8..9] map_incremental class counts,
+  int* d_prep_counters = nullptr;   // [0] M, [1..6] key min/max, [7] error, [8..9] map_incremental class counts, [11] their sum,
                                     // [10] voxel runs, [12] decoded points
 
   // lio_scan_step: one main-loop iteration enqueued without intermediate host synchronisation
@@ -118,6 +117,10 @@ struct lio_ctx {
   cudaStream_t prep_stream = nullptr;  // the next scan's upload + undistort + sort run here next to the pending growth
   cudaEvent_t ev_prep = nullptr;       // preprocessing on prep_stream done
   cudaEvent_t centroid_wait = nullptr; // preprocess(): make the kernel that writes d_body / d_scan_m wait for this
+  const void* staged_ptr = nullptr;    // lio_scan_step_prefetch: this scan's records are already in d_raw / d_raw_aux
+  int64_t staged_n = 0;
+  int staged_stride = 0;
+  bool staged_on_prep = false;         // ... copied on prep_stream
   int32_t last_counts[3] = {0, 0, 0};
   int growth_rc = 0;                // error of a deferred growth, reported by the next call that settles it
 };

@@ -194,8 +194,10 @@ __global__ void vox_apply_kernel(MapView m, const float4* pts, int n, BatchDev b
   int c0[3], c1[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
+    // the box is half open: its last cell is the one of the largest float below bmax (cell_coord is monotone), not the
+    // one of bmax itself -- with 0.5 m boxes in 1.5 m cells that is one cell instead of up to eight
     c0[a] = cell_coord(g.bmin[a], m.inv_cell);
-    c1[a] = cell_coord(g.bmax[a], m.inv_cell);
+    c1[a] = cell_coord(nextafterf(g.bmax[a], -INFINITY), m.inv_cell);
   }
   // pass 1: existing points inside the half-open box
   int E = 0;
@@ -353,41 +355,66 @@ __global__ void scan_to_world_kernel(const float4* body, const int* scan_m, cons
   world[i] = make_float4((float)(w[0] + xs->pos[0]), (float)(w[1] + xs->pos[1]), (float)(w[2] + xs->pos[2]), b.w);
 }
 
-// order-preserving compaction of the two classes by a single block (M <= ~1e5; not a hot kernel)
+// Order-preserving compaction of the two classes by a single block (M <= ~1e5): PointToAdd first, then
+// PointNoNeedDownsample right behind it in the SAME array, so that both Add_Points calls of laserMapping.cpp:430-431 end in
+// one reserve / grow / fill sequence: vox_apply_kernel decides append_flag for the first n_a points, the others are
+// appended unconditionally (flag 1, written here).  The id of a point is id_base + its position, exactly what the two
+// separate calls hand out (the second call's ids start after all n_a points of the first).
 __global__ void __launch_bounds__(1024) map_incr_compact_kernel(const float4* world, const uint8_t* cls,
-                                                                const int* scan_m, int min_m, float4* out_a,
-                                                                float4* out_b, int* counts /*[2]*/) {
-  __shared__ int sa[1024], sb[1024];
+                                                                const int* scan_m, int min_m, float4* out,
+                                                                uint8_t* append_flag, int* counts /*[0] n_a [1] n_b [3] sum*/) {
+  __shared__ int wa[32], wb[32];
   const int M = *scan_m < min_m ? 0 : *scan_m;
   const int chunk = (M + 1023) / 1024;
-  const int lo = threadIdx.x * chunk, hi = min(M, lo + chunk);
+  const int lo = min(M, (int)threadIdx.x * chunk), hi = min(M, lo + chunk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int na = 0, nb = 0;
   for (int i = lo; i < hi; ++i) {
     na += cls[i] == 1;
     nb += cls[i] == 2;
   }
-  sa[threadIdx.x] = na;
-  sb[threadIdx.x] = nb;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    int va = 0, vb = 0;
-    if (threadIdx.x >= off) {
-      va = sa[threadIdx.x - off];
-      vb = sb[threadIdx.x - off];
+  int ia = na, ib = nb;  // inclusive scans: warp, then the 32 warp totals
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int ta = __shfl_up_sync(0xffffffffu, ia, off), tb = __shfl_up_sync(0xffffffffu, ib, off);
+    if (lane >= off) {
+      ia += ta;
+      ib += tb;
     }
-    __syncthreads();
-    sa[threadIdx.x] += va;
-    sb[threadIdx.x] += vb;
-    __syncthreads();
   }
-  int oa = sa[threadIdx.x] - na, ob = sb[threadIdx.x] - nb;
+  if (lane == 31) {
+    wa[warp] = ia;
+    wb[warp] = ib;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int va = wa[lane], vb = wb[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int ta = __shfl_up_sync(0xffffffffu, va, off), tb = __shfl_up_sync(0xffffffffu, vb, off);
+      if (lane >= off) {
+        va += ta;
+        vb += tb;
+      }
+    }
+    wa[lane] = va;
+    wb[lane] = vb;
+  }
+  __syncthreads();
+  const int tot_a = wa[31], tot_b = wb[31];
+  int oa = (warp ? wa[warp - 1] : 0) + ia - na;
+  int ob = tot_a + (warp ? wb[warp - 1] : 0) + ib - nb;
   for (int i = lo; i < hi; ++i) {
-    if (cls[i] == 1) out_a[oa++] = world[i];
-    if (cls[i] == 2) out_b[ob++] = world[i];
+    if (cls[i] == 1) out[oa++] = world[i];
+    if (cls[i] == 2) {
+      append_flag[ob] = 1;
+      out[ob++] = world[i];
+    }
   }
-  if (threadIdx.x == 1023) {
-    counts[0] = sa[1023];
-    counts[1] = sb[1023];
+  if (threadIdx.x == 0) {
+    counts[0] = tot_a;
+    counts[1] = tot_b;
+    counts[3] = tot_a + tot_b;
   }
 }
 
@@ -443,9 +470,9 @@ int map_append_batch(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base
   return check_map_error(c);
 }
 
-// Add_Points(downsample_on = true), enqueue only; the number of points added ends up in map.counters[4].
-int map_add_downsample_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base) {
-  if (n <= 0) return LIO_OK;
+// Add_Points(downsample_on = true), first half, enqueue only: per batch voxel the winner settles it against the map and
+// append_flag says which points remain to be appended; the number of points added ends up in map.counters[4].
+static int vox_phase_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base) {
   if (n > c->batch_cap || (uint64_t)n * 2 > c->vox_cap) {
     c->err = "Add_Points batch larger than the context's batch capacity";
     return LIO_E_CAPACITY;
@@ -460,6 +487,13 @@ int map_add_downsample_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const
                                                 c->d_batch_rank, id_base, c->d_batch_flag);
   c->launches += 3;
   LIO_CHECK(c, cudaGetLastError());
+  return LIO_OK;
+}
+
+int map_add_downsample_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base) {
+  if (n <= 0) return LIO_OK;
+  const int rc = vox_phase_enqueue(c, d_pts, n, n_dev, id_base);
+  if (rc) return rc;
   return map_append_batch_enqueue(c, d_pts, n, n_dev, id_base, nullptr, c->d_batch_flag);
 }
 
@@ -574,12 +608,14 @@ int map_incremental_enqueue(lio_ctx* c, float fsm, int ekf_inited, int min_m, in
   int* d_counts = c->d_prep_counters + 8;
   map_incr_classify_kernel<<<grid, 256, 0, c->stream>>>(c->d_body, c->d_scan_m, c->d_x, c->d_near, c->d_near_cnt,
                                                         ekf_inited, fsm, min_m, c->d_world, c->d_cls);
-  map_incr_compact_kernel<<<1, 1024, 0, c->stream>>>(c->d_world, c->d_cls, c->d_scan_m, min_m, c->d_add_a, c->d_add_b,
-                                                     d_counts);
+  map_incr_compact_kernel<<<1, 1024, 0, c->stream>>>(c->d_world, c->d_cls, c->d_scan_m, min_m, c->d_add_a,
+                                                     c->d_batch_flag, d_counts);
   c->launches += 2;
-  int rc = map_add_downsample_enqueue(c, c->d_add_a, bound, d_counts, c->next_id);
+  // Add_Points(PointToAdd, true) decides on the first n_a points; one reserve / grow / fill appends what it leaves of
+  // them together with Add_Points(PointNoNeedDownsample, false)
+  const int rc = vox_phase_enqueue(c, c->d_add_a, bound, d_counts, c->next_id);
   if (rc) return rc;
-  return map_append_batch_enqueue(c, c->d_add_b, bound, d_counts + 1, c->next_id, d_counts, nullptr);
+  return map_append_batch_enqueue(c, c->d_add_a, bound, d_counts + 3, c->next_id, nullptr, c->d_batch_flag);
 }
 
 int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]) {

@@ -236,8 +236,16 @@ int lio_seq_local_map(const lio_seq* s, float box6[6], int64_t* n_box_deleted) {
 
 int lio_seq_process(lio_seq* s, const lio_seq_input* in, lio_seq_result* res) {
   if (!s || !in || !res || in->n < 0 || in->n_imu < 0 || (in->n_imu > 0 && !in->imu)) return LIO_E_INVALID;
+  // the records go up while the host propagates the IMU samples
+  if (!s->first_scan && in->n_imu > 0) {
+    const int rp = lio_scan_step_prefetch(s->ctx, in->lidar, in->n, in->stride_bytes);
+    if (rp) return rp;
+  }
   const int h = host_stage(s, in, res);
-  if (h <= 0) return h;
+  if (h <= 0) {
+    lio_scan_step_prefetch(s->ctx, nullptr, 0, 16);  // scan skipped: drop the staged copy
+    return h;
+  }
   lio_scan_report rep;
   const int rc = lio_scan_step(s->ctx, in->lidar, in->n, in->stride_bytes, s->poses.data(), s->n_poses, &s->x, s->P,
                                s->cfg.filter_size_surf, s->cfg.filter_size_map, s->cfg.laser_point_cov,
@@ -265,8 +273,19 @@ int lio_seq_process_many(lio_seq* const* seqs, int n_seq, const lio_seq_input* i
     lio_seq* s = seqs[k];
     d_of[k] = 0;
     rc_of[k] = LIO_OK;
+    memset(&res[k], 0, sizeof(res[k]));
+    if (!s->first_scan && in[k].n_imu > 0) {
+      rc_of[k] = lio_scan_step_prefetch(s->ctx, in[k].lidar, in[k].n, in[k].stride_bytes);
+      if (rc_of[k]) {
+        h_of[k] = 1;  // reported through rc_of below
+        continue;
+      }
+    }
     h_of[k] = host_stage(s, &in[k], &res[k]);
-    if (h_of[k] <= 0) continue;
+    if (h_of[k] <= 0) {
+      lio_scan_step_prefetch(s->ctx, nullptr, 0, 16);
+      continue;
+    }
     rc_of[k] = lio_scan_step_begin(s->ctx, in[k].lidar, in[k].n, in[k].stride_bytes, s->poses.data(), s->n_poses,
                                    &s->x, s->P, s->cfg.filter_size_surf, &d_of[k]);
   }

@@ -229,6 +229,10 @@ int lio_scan_step(lio_ctx*, const void* raw_pts, int64_t n, int stride_bytes, co
 int lio_scan_step_begin(lio_ctx*, const void* raw_pts, int64_t n, int stride_bytes, const lio_pose6d* imu_poses,
                         int n_poses, const lio_state* x, const double P[576], float leaf_surf, int32_t* update_due);
 int lio_scan_step_end(lio_ctx*, float leaf_map, int ekf_inited);
+/* Optional, before the host's IMU propagation of the same scan: starts the upload of the raw records (they do not depend
+ * on the filter state).  A following lio_scan_step / lio_scan_step_begin with the SAME pointer, n and stride uses the
+ * staged copy instead of copying again; any other call, or n == 0, drops it.  The buffer must stay untouched in between. */
+int lio_scan_step_prefetch(lio_ctx*, const void* raw_pts, int64_t n, int stride_bytes);
 int lio_scan_step_finish(lio_ctx*, lio_state* x_out, double P_out[576], lio_scan_report* report);
 /* Deferred map growth.  The reference publishes a scan's odometry BEFORE map_incremental runs (laserMapping.cpp:776-785).
  * With on != 0 the step does the same: lio_scan_step / lio_scan_step_finish (and lio_seq_process*) return as soon as the
