@@ -200,6 +200,10 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_poses, sizeof(lio_pose6d) * 128);
   ALLOC(c->d_sorted_aux, 4 * N);
   ALLOC(c->d_run_heads, 4 * N);
+  ALLOC(c->d_runs_status, 8 * (N / 2048 + 2));
+  ALLOC(c->d_runs_ticket, 4);
+  LIO_CHECK(c, cudaMemset(c->d_runs_status, 0, 8 * (N / 2048 + 2)));
+  LIO_CHECK(c, cudaMemset(c->d_runs_ticket, 0, 4));
   ALLOC(c->d_sort_keys_in, 4 * N);
   ALLOC(c->d_sort_keys_out, 4 * N);
   ALLOC(c->d_sort_vals_in, 4 * N);
@@ -257,7 +261,7 @@ void lio_destroy(lio_ctx* c) {
                   c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,      c->d_mailbox,
                   c->d_cloud,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
-                  c->d_vkeys,     c->d_poses,       c->d_sorted_aux,  c->d_run_heads,
+                  c->d_vkeys,     c->d_poses,       c->d_sorted_aux,  c->d_run_heads,   c->d_runs_status, c->d_runs_ticket,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
                   c->d_prep_counters};
   for (void* p : ptrs)

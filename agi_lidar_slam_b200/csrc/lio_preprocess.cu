@@ -8,7 +8,8 @@
 // oracle defines (PCL's std::sort is unstable, so PCL itself leaves it open).  Sequential FP32 sums in a defined
 // order make the centroids BIT-EXACT against the oracle, and run-to-run deterministic, which the downstream
 // neighbour sets and validity gates need (the filter loop amplifies 1e-9 input differences to millimetres within
-// ten scans).  The only library calls are cub::DeviceRadixSort / cub::DeviceSelect.
+// ten scans).  The only library call on the scan path is cub::DeviceRadixSort (the sensor decoders also
+// use cub::DeviceSelect / DeviceScan).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
@@ -165,19 +166,108 @@ __global__ void linear_index_kernel(const int* vkeys, int n, int* counters, uint
   vals[i] = (uint32_t)i;
 }
 
-struct HeadFlag {
-  const uint32_t* keys;
-  __device__ __forceinline__ bool operator()(const int& j) const { return j == 0 || keys[j] != keys[j - 1]; }
-};
-
-// points (and intensities) in sorted order: the runs become contiguous, so the sequential sums below stream memory
-__global__ void gather_sorted_kernel(const uint32_t* sorted_vals, int n, const float4* undist, const float* aux,
-                                     float4* sorted_pts, float* sorted_aux) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const uint32_t i = sorted_vals[j];
-  sorted_pts[j] = __ldg(undist + i);
-  if (aux) sorted_aux[j] = __ldg(aux + i);
+// Run heads + gather in one pass over the sorted order (what cub::DeviceSelect + a gather kernel did in three launches).
+// A tile of RT sorted positions per block: head flags (leaf index differs from its predecessor's), block scan, then the
+// tile's exclusive prefix by a decoupled look-back over the tiles before it -- each tile publishes {launch tag, state,
+// count} in one 64-bit word as soon as it knows its own count, a warp sums the published counts of up to 32 predecessors
+// per round until it meets one that already carries its inclusive prefix.  Tiles take their number from a ticket, so a
+// tile only ever waits for tiles that have already started.  Nothing is reset between launches: words are recognised by
+// the launch tag, tickets count on from ticket_base.
+constexpr int RT = 2048;
+__global__ void __launch_bounds__(256) runs_gather_kernel(const uint32_t* keys, const uint32_t* vals, int n,
+                                                          const float4* undist, const float* aux, float4* sorted_pts,
+                                                          float* sorted_aux, int* heads, int* n_runs,
+                                                          unsigned long long* status, unsigned* ticket,
+                                                          unsigned ticket_base, unsigned tag) {
+  __shared__ int s_tile, s_prefix, s_warp[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = (int)(atomicAdd(ticket, 1u) - ticket_base);
+  __syncthreads();
+  const int tile = s_tile;
+  const int j0 = tile * RT + tid * 8;
+  uint32_t k[8], prev = 0;
+  bool f[8];
+  int cnt = 0;
+  if (j0 < n) {
+    if (j0 + 8 <= n) {
+      const uint4 a = *reinterpret_cast<const uint4*>(keys + j0), b = *reinterpret_cast<const uint4*>(keys + j0 + 4);
+      k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) k[u] = j0 + u < n ? keys[j0 + u] : 0u;
+    }
+    if (j0 > 0) prev = keys[j0 - 1];
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = j0 + u;
+    f[u] = j < n && (j == 0 || k[u] != (u ? k[u - 1] : prev));
+    cnt += f[u];
+  }
+  // block-exclusive scan of the per-thread counts
+  int inc = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int warp_base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) warp_base += s_warp[w];
+    total += s_warp[w];
+  }
+  int local = warp_base + inc - cnt;
+  // look-back (warp 0).  word = tag << 32 | state << 30 | count, state 1 = the tile's own count, 2 = inclusive prefix
+  if (warp == 0) {
+    const unsigned long long mine = ((unsigned long long)tag << 32);
+    if (lane == 0)
+      *reinterpret_cast<volatile unsigned long long*>(status + tile) =
+          mine | ((tile == 0 ? 2ull : 1ull) << 30) | (unsigned)total;
+    int prefix = 0;
+    for (int p = tile - 1;; p -= 32) {
+      const int idx = p - lane;
+      unsigned st = 2, val = 0;  // before tile 0: an inclusive prefix of nothing
+      if (idx >= 0) {
+        unsigned long long w;
+        do {
+          w = *reinterpret_cast<volatile unsigned long long*>(status + idx);
+        } while ((unsigned)(w >> 32) != tag || (((unsigned)w >> 30) & 3u) == 0);
+        st = ((unsigned)w >> 30) & 3u;
+        val = (unsigned)w & 0x3fffffffu;
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, st == 2);
+      const int first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor that already knows its inclusive prefix
+      int v = lane <= first ? (int)val : 0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      prefix += v;
+      if (pm) break;
+    }
+    if (lane == 0) {
+      if (tile > 0)
+        *reinterpret_cast<volatile unsigned long long*>(status + tile) = mine | (2ull << 30) | (unsigned)(prefix + total);
+      s_prefix = prefix;
+    }
+  }
+  __syncthreads();
+  const int base = s_prefix;
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (f[u]) heads[base + local++] = j0 + u;
+  if (tid == 0 && tile == (n + RT - 1) / RT - 1) *n_runs = base + total;
+  // gather into sorted order: the runs become contiguous, so the sequential sums of centroid_kernel stream memory
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = j0 + u;
+    if (j < n) {
+      const uint32_t i = vals[j];
+      sorted_pts[j] = __ldg(undist + i);
+      if (aux) sorted_aux[j] = __ldg(aux + i);
+    }
+  }
 }
 
 // One run of equal leaf indices per thread: FP32 sums in sorted (= ascending point) order, then / count.  The order
@@ -530,8 +620,8 @@ size_t preprocess_sort_bytes(int64_t n) {
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                   (uint32_t*)nullptr, (int)n, 0, 31);
   cub::CountingInputIterator<int> it(0);
-  HeadFlag hf{nullptr};
-  cub::DeviceSelect::If(nullptr, b, it, (int*)nullptr, (int*)nullptr, (int)n, hf);
+  DecodeKeep keep{};  // the decoders' compaction (lio_scan_preprocess_cloud2)
+  cub::DeviceSelect::If(nullptr, b, it, (int*)nullptr, (int*)nullptr, (int)n, keep);
   size_t d = 0;
   cub::DeviceScan::InclusiveSum(nullptr, d, (const int*)nullptr, (int*)nullptr, (int)n);
   a = a > d ? a : d;
@@ -574,10 +664,6 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
     size_t bytes = c->cub_tmp_bytes;
     LIO_CHECK(c, cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, bytes, keys_in, keys_out, c->d_sort_vals_in,
                                                  c->d_sort_vals_out, (int)n, 0, 31, c->stream));
-    bytes = c->cub_tmp_bytes;
-    cub::CountingInputIterator<int> it(0);
-    HeadFlag hf{keys_out};
-    LIO_CHECK(c, cub::DeviceSelect::If(c->d_cub_tmp, bytes, it, heads, n_runs, (int)n, hf, c->stream));
   } else {
     LIO_CHECK(c, cudaMemsetAsync(n_runs, 0, sizeof(int), c->stream));
   }
@@ -586,8 +672,12 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
   float4* sorted_pts = c->d_raw;  // the raw scan has been consumed by now
   float* sorted_aux = has_aux ? c->d_sorted_aux : nullptr;
   if (n > 0) {
-    gather_sorted_kernel<<<grid, 256, 0, c->stream>>>(c->d_sort_vals_out, (int)n, c->d_undist,
-                                                      has_aux ? c->d_raw_aux : nullptr, sorted_pts, sorted_aux);
+    const unsigned ntiles = (unsigned)((n + RT - 1) / RT);
+    runs_gather_kernel<<<ntiles, 256, 0, c->stream>>>(keys_out, c->d_sort_vals_out, (int)n, c->d_undist,
+                                                      has_aux ? c->d_raw_aux : nullptr, sorted_pts, sorted_aux, heads,
+                                                      n_runs, c->d_runs_status, c->d_runs_ticket, c->runs_ticket_base,
+                                                      ++c->runs_tag);
+    c->runs_ticket_base += ntiles;
     c->launches++;
   }
   if (c->centroid_wait) LIO_CHECK(c, cudaStreamWaitEvent(c->stream, c->centroid_wait, 0));
