@@ -886,7 +886,7 @@ int lio_scan_step_begin(lio_ctx* c, const void* raw_pts, int64_t n, int stride, 
 }
 
 int lio_scan_step_end(lio_ctx* c, float leaf_map, int ekf_inited) {
-  if (!c || !(leaf_map > 0.f)) return LIO_E_INVALID;
+  if (!c || !(leaf_map >= 0.f)) return LIO_E_INVALID;
   if (c->step_phase == 3) return LIO_OK;
   if (c->step_phase != 1) {
     c->err = "lio_scan_step_end without lio_scan_step_begin";
@@ -900,7 +900,9 @@ int lio_scan_step_end(lio_ctx* c, float leaf_map, int ekf_inited) {
   LIO_CHECK(c, cudaMemcpyAsync(hp, c->d_x, 8 * 606, cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaMemcpyAsync(hp + 606, c->d_prep_counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaEventRecord(c->ev_post, c->stream));
-  rc = map_incremental_enqueue(c, leaf_map, ekf_inited ? 1 : 0, 5, c->scan_m_bound);
+  // leaf_map == 0: the map is static -- the relocalisation loop, where map_incremental() is commented out
+  // (src/laserMapping_re.cpp:676); the counts of the report are then zero
+  rc = map_incremental_enqueue(c, leaf_map, ekf_inited ? 1 : 0, 5, leaf_map > 0.f ? c->scan_m_bound : 0);
   if (rc) return rc;
   LIO_CHECK(c, cudaMemcpyAsync(hp + 620, c->d_prep_counters + 8, 4 * 2, cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaMemcpyAsync(hp + 622, c->map.counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -961,7 +963,7 @@ int lio_scan_step_finish(lio_ctx* c, lio_state* x_out, double P_out[576], lio_sc
 int lio_scan_step(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses, int n_poses,
                   lio_state* x_io, double P_io[576], float leaf_surf, float leaf_map, double R, int max_iter,
                   int extrinsic_est, int ekf_inited, lio_scan_report* rep) {
-  if (!c || !x_io || !P_io || !rep || max_iter < 0 || max_iter > 32 || !(leaf_map > 0.f)) return LIO_E_INVALID;
+  if (!c || !x_io || !P_io || !rep || max_iter < 0 || max_iter > 32 || !(leaf_map >= 0.f)) return LIO_E_INVALID;
   int32_t due = 0;
   int rc = lio_scan_step_begin(c, raw_pts, n, stride, poses, n_poses, x_io, P_io, leaf_surf, &due);
   if (rc) return rc;

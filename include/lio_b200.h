@@ -210,7 +210,8 @@ int lio_update_enqueue(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, 
  * map_incremental (:785) -- enqueued back to back on the context's stream.  M, the map_incremental class counts and the
  * insert sizes stay on the device; the host synchronises ONCE, at the end, and gets everything in the report.
  * x_io / P_io: the propagated state at scan end (what lio_imu_process returned) in, the posterior out (untouched when
- * the scan is skipped).  raw_pts / poses as for lio_scan_preprocess. */
+ * the scan is skipped).  raw_pts / poses as for lio_scan_preprocess.  leaf_map = filter_size_map_min; leaf_map == 0 keeps
+ * the map static -- the relocalisation loop, where map_incremental() is commented out (src/laserMapping_re.cpp:676). */
 typedef struct lio_scan_report {
   int64_t m;          /* feats_down_size */
   int32_t status;     /* LIO_SCAN_* */

@@ -191,3 +191,32 @@ def test_deferred_growth_reports_capacity_errors_one_call_later():
             ctx.close()
     assert False in failed_at and True in failed_at, failed_at
     assert failed_at[True] in (failed_at[False], failed_at[False] + 1), failed_at
+
+
+def test_static_map_step_is_preprocess_plus_update():
+    """leaf_map = 0: the relocalisation loop (laserMapping_re.cpp, map_incremental() commented out at :676) -- one call
+    gives what lio_scan_preprocess + lio_update_scan give, and the map stays as it was."""
+    from agi_lidar_slam_b200 import _cabi, synth
+
+    cfg = synth.small_config()
+    a, b = _ctx(), _ctx()
+    try:
+        mp = np.concatenate([cfg["map"], np.zeros((len(cfg["map"]), 1), np.float32)], 1)
+        a.map_build(mp)
+        b.map_build(mp)
+        size0 = b.map_size()
+        m = a.scan_preprocess(cfg["scan"], None, None, 0.5, resident=True)
+        xa, Pa, nv, npass = a.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, False)
+        xb = np.ascontiguousarray(cfg["x_prior"], np.float64).copy()
+        Pb = np.ascontiguousarray(cfg["P"], np.float64).reshape(24, 24).copy()
+        rep = b.scan_step(cfg["scan"], None, xb, Pb, 0.5, 0.0, 0.001, 4, False, True)
+        assert rep.status == _cabi.SCAN_UPDATED and rep.m == m and rep.n_valid == nv and rep.n_passes == npass
+        assert list(rep.counts) == [0, 0, 0]
+        assert np.array_equal(xa, xb) and np.array_equal(np.asarray(Pa).reshape(24, 24), Pb)
+        assert b.map_size() == size0
+        xyz_a, ids_a = a.map_dump()
+        xyz_b, ids_b = b.map_dump()
+        assert np.array_equal(ids_a, ids_b) and np.array_equal(xyz_a.view(np.uint32), xyz_b.view(np.uint32))
+    finally:
+        a.close()
+        b.close()
