@@ -464,6 +464,17 @@ int lio_knn5_resident(lio_ctx* c, int64_t m) {
 }
 
 // ---------------------------------------------------------------- scan
+// A lio_scan_step_prefetch copy may still be running on the second stream: order it before anything else touches d_raw
+// on another stream (the growth was settled in between, or the caller came back with another buffer / entry point).
+static int order_after_prefetch(lio_ctx* c) {
+  if (c->staged_on_prep && c->stream != c->prep_stream) {
+    LIO_CHECK(c, cudaEventRecord(c->ev_prep, c->prep_stream));
+    LIO_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_prep, 0));
+  }
+  c->staged_on_prep = false;
+  return LIO_OK;
+}
+
 static int preprocess_common(lio_ctx* c, const void* raw_pts, int64_t n, int stride, const lio_pose6d* poses,
                              int n_poses, const lio_state* end_state, float leaf, bool staged = false) {
   if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !raw_pts) || !(leaf > 0.f)) return LIO_E_INVALID;
@@ -477,8 +488,10 @@ static int preprocess_common(lio_ctx* c, const void* raw_pts, int64_t n, int str
     c->err = "more than 128 IMU poses";
     return LIO_E_CAPACITY;
   }
+  int rc = order_after_prefetch(c);
+  if (rc) return rc;
   // stride 48: time = curvature (offset 36), intensity (offset 32) rides along as aux
-  int rc = staged ? LIO_OK
+  rc = staged ? LIO_OK
                   : stage_points(c, raw_pts, n, stride, 36, c->d_raw, 32, c->d_raw_aux, reinterpret_cast<float*>(c->d_vkeys));
   if (rc) return rc;
   if (n_poses >= 2)
@@ -610,6 +623,7 @@ int lio_scan_preprocess_cloud2(lio_ctx* c, const void* data, int64_t n, const li
     LIO_CHECK(c, cudaMalloc(reinterpret_cast<void**>(&c->d_cloud), need));
     c->cloud_bytes = need;
   }
+  if (const int ro = order_after_prefetch(c)) return ro;
   if (n > 0) LIO_CHECK(c, cudaMemcpyAsync(c->d_cloud, data, (size_t)n * L->point_step, cudaMemcpyHostToDevice, c->stream));
   int64_t nd = 0;
   int rc = decode_cloud2(c, n, *L, yaw_times, &nd);
@@ -820,6 +834,8 @@ int lio_scan_step_prefetch(lio_ctx* c, const void* raw_pts, int64_t n, int strid
   if (split) {
     LIO_CHECK(c, cudaStreamWaitEvent(c->prep_stream, c->ev_post, 0));
     c->stream = c->prep_stream;
+  } else if (const int ro = order_after_prefetch(c)) {  // an earlier, dropped prefetch may still be copying there
+    return ro;
   }
   const int rc = stage_points(c, raw_pts, n, stride, 36, c->d_raw, 32, c->d_raw_aux, reinterpret_cast<float*>(c->d_vkeys));
   c->stream = main_stream;
@@ -851,10 +867,7 @@ int lio_scan_step_begin(lio_ctx* c, const void* raw_pts, int64_t n, int stride, 
     c->stream = c->prep_stream;
     c->centroid_wait = c->ev_growth;
   }
-  if (staged && c->staged_on_prep && !split) {  // the growth was settled in between: order the copy before this stream
-    LIO_CHECK(c, cudaEventRecord(c->ev_prep, c->prep_stream));
-    LIO_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_prep, 0));
-  }
+
   int rc = preprocess_common(c, raw_pts, n, stride, poses, n_poses, x, leaf_surf, staged);
   if (split) {
     c->stream = main_stream;

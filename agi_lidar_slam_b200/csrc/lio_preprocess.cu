@@ -220,12 +220,24 @@ __global__ void __launch_bounds__(256) runs_gather_kernel(const uint32_t* keys, 
     total += s_warp[w];
   }
   int local = warp_base + inc - cnt;
-  // look-back (warp 0).  word = tag << 32 | state << 30 | count, state 1 = the tile's own count, 2 = inclusive prefix
+  // word = tag << 32 | state << 30 | count, state 1 = the tile's own count, 2 = inclusive prefix.  The own count goes out
+  // first, then the tile does its gather (independent of the prefix) while the other tiles publish theirs.
+  const unsigned long long mine = ((unsigned long long)tag << 32);
+  if (tid == 0)
+    *reinterpret_cast<volatile unsigned long long*>(status + tile) =
+        mine | ((tile == 0 ? 2ull : 1ull) << 30) | (unsigned)total;
+  // gather into sorted order: the runs become contiguous, so the sequential sums of centroid_kernel stream memory
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int j = j0 + u;
+    if (j < n) {
+      const uint32_t i = vals[j];
+      sorted_pts[j] = __ldg(undist + i);
+      if (aux) sorted_aux[j] = __ldg(aux + i);
+    }
+  }
+  // look-back (warp 0)
   if (warp == 0) {
-    const unsigned long long mine = ((unsigned long long)tag << 32);
-    if (lane == 0)
-      *reinterpret_cast<volatile unsigned long long*>(status + tile) =
-          mine | ((tile == 0 ? 2ull : 1ull) << 30) | (unsigned)total;
     int prefix = 0;
     for (int p = tile - 1;; p -= 32) {
       const int idx = p - lane;
@@ -258,16 +270,6 @@ __global__ void __launch_bounds__(256) runs_gather_kernel(const uint32_t* keys, 
   for (int u = 0; u < 8; ++u)
     if (f[u]) heads[base + local++] = j0 + u;
   if (tid == 0 && tile == (n + RT - 1) / RT - 1) *n_runs = base + total;
-  // gather into sorted order: the runs become contiguous, so the sequential sums of centroid_kernel stream memory
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int j = j0 + u;
-    if (j < n) {
-      const uint32_t i = vals[j];
-      sorted_pts[j] = __ldg(undist + i);
-      if (aux) sorted_aux[j] = __ldg(aux + i);
-    }
-  }
 }
 
 // One run of equal leaf indices per thread: FP32 sums in sorted (= ascending point) order, then / count.  The order
