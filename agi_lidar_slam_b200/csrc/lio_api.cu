@@ -10,6 +10,7 @@
 
 namespace lio {
 size_t preprocess_sort_bytes(int64_t n);
+int preprocess_init_counters(lio_ctx* c);
 int preprocess_init_tables(lio_ctx* c);
 
 __global__ void set_w_kernel(float4* dst, const float* w, int n) {
@@ -210,14 +211,16 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_sort_vals_out, 4 * N);
   c->cub_tmp_bytes = preprocess_sort_bytes((int64_t)N);
   ALLOC(c->d_cub_tmp, c->cub_tmp_bytes + 16);
-  ALLOC(c->d_prep_counters, 4 * 16);
-  LIO_CHECK(c, cudaMemset(c->d_prep_counters, 0, 4 * 16));
+  ALLOC(c->d_prep_counters, 4 * 32);
+  LIO_CHECK(c, cudaMemset(c->d_prep_counters, 0, 4 * 32));
 
   int rc = ensure_tables(c);
   if (rc) return rc;
   rc = map_reset(c);
   if (rc) return rc;
   rc = preprocess_init_tables(c);
+  if (rc) return rc;
+  rc = preprocess_init_counters(c);
   if (rc) return rc;
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
   return LIO_OK;
@@ -503,7 +506,7 @@ static int preprocess_common(lio_ctx* c, const void* raw_pts, int64_t n, int str
 static int preprocess_decode(lio_ctx* c, const int* h, int64_t* m);
 static int preprocess_status(lio_ctx* c, int64_t* m) {
   int h[8];
-  LIO_CHECK(c, cudaMemcpyAsync(h, c->d_prep_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(h, c->d_prep_counters + 16, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
   return preprocess_decode(c, h, m);
 }
@@ -911,7 +914,7 @@ int lio_scan_step_end(lio_ctx* c, float leaf_map, int ekf_inited) {
   // posterior + preprocess counters first: with deferred growth the host resumes as soon as these have landed
   double* hp = static_cast<double*>(c->h_pinned);
   LIO_CHECK(c, cudaMemcpyAsync(hp, c->d_x, 8 * 606, cudaMemcpyDeviceToHost, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(hp + 606, c->d_prep_counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemcpyAsync(hp + 606, c->d_prep_counters + 16, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
   LIO_CHECK(c, cudaEventRecord(c->ev_post, c->stream));
   // leaf_map == 0: the map is static -- the relocalisation loop, where map_incremental() is commented out
   // (src/laserMapping_re.cpp:676); the counts of the report are then zero

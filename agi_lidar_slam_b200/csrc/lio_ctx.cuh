@@ -102,7 +102,8 @@ struct lio_ctx {
   uint32_t* d_sort_vals_out = nullptr;
   void* d_cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
-  int* d_prep_counters = nullptr;   // [0] M, [1..6] key min/max, [7] error, [8..9] map_incremental class counts, [11] their sum,
+  int* d_prep_counters = nullptr;   // working set (reset by centroid_kernel): [0] M, [1..6] key min/max, [7] error; [16..23] = the same
+                                    // as filed for the host at the end of the preprocessing; [8..9] map_incremental class counts, [11] their sum,
                                     // [10] voxel runs, [12] decoded points
 
   // lio_scan_step: one main-loop iteration enqueued without intermediate host synchronisation

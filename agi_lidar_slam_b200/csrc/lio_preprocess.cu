@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
   }
 }
 
+// working counters of the first scan; afterwards centroid_kernel leaves them reset
 __global__ void prep_reset_kernel(int* counters) {
   counters[0] = 0;
   counters[1] = counters[2] = counters[3] = 0x7fffffff;
@@ -292,9 +293,19 @@ __global__ void __launch_bounds__(128) centroid_kernel(const float4* sorted_pts,
   const int n_warps = gridDim.x * (blockDim.x >> 5);
   const int m = lane * n_warps + blockIdx.x * (blockDim.x >> 5) + warp;
   if (m == 0) {
-    *scan_m = counters[7] == 3 ? 0 : M;
-    counters[0] = Mtot;
-    if (Mtot > max_m && counters[7] == 0) counters[7] = 2;  // more voxels than lio_caps.max_down_points
+    // the last kernel of the preprocessing files this scan's counters as the report the host reads (counters[16..23])
+    // and leaves the working set reset for the next scan -- what a one-thread reset kernel used to do before every scan
+    int err = counters[7];
+    *scan_m = err == 3 ? 0 : M;
+    if (Mtot > max_m && err == 0) err = 2;  // more voxels than lio_caps.max_down_points
+    counters[16] = Mtot;
+#pragma unroll
+    for (int k = 1; k < 7; ++k) counters[16 + k] = counters[k];
+    counters[23] = err;
+    counters[0] = 0;
+    counters[1] = counters[2] = counters[3] = 0x7fffffff;
+    counters[4] = counters[5] = counters[6] = -0x7fffffff;
+    counters[7] = 0;
   }
   int beg = 0, end = 0;
   if (m < M) {
@@ -617,6 +628,12 @@ int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, bool yaw_tim
   return LIO_OK;
 }
 
+int preprocess_init_counters(lio_ctx* c) {
+  prep_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_prep_counters);
+  LIO_CHECK(c, cudaGetLastError());
+  return LIO_OK;
+}
+
 size_t preprocess_sort_bytes(int64_t n) {
   size_t a = 0, b = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
@@ -656,8 +673,6 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
   uint32_t* keys_out = c->d_sort_keys_out;
   int* heads = c->d_run_heads;
   int* n_runs = c->d_prep_counters + 10;
-  prep_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_prep_counters);
-  c->launches++;
   if (n > 0) {
     undistort_key_kernel<<<grid, 256, 0, c->stream>>>(a);
     linear_index_kernel<<<grid, 256, 0, c->stream>>>(c->d_vkeys, (int)n, c->d_prep_counters, keys_in,
