@@ -254,6 +254,7 @@ void lio_destroy(lio_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->prep_stream) cudaStreamSynchronize(c->prep_stream);  // a prefetched scan may still be on its way
   for (int r = 0; r < 8; ++r)
     if (c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
   void* ptrs[] = {c->map.table,   c->map.cell_cap,  c->map.cell_pend, c->map.cell_base, c->map.pool,
