@@ -286,10 +286,14 @@ int lio_set_stream(lio_ctx* c, void* cuda_stream) {
   if (!c) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->prep_stream));
+  const int rs = settle_growth(c);  // nothing of the old stream is left pending
+  c->staged_ptr = nullptr;
+  c->staged_on_prep = false;
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   c->stream = static_cast<cudaStream_t>(cuda_stream);
   c->own_stream = false;
-  return LIO_OK;
+  return rs;
 }
 
 int lio_synchronize(lio_ctx* c) {
