@@ -521,6 +521,10 @@ static int preprocess_decode(lio_ctx* c, const int* h, int64_t* m) {
     c->err = "more occupied voxels than lio_caps.max_down_points";
     return LIO_E_CAPACITY;
   }
+  if (h[7] == 4) {
+    c->err = "voxel filter: a tile of the run scan never reported (internal error)";
+    return LIO_E_CUDA;
+  }
   c->scan_m = std::min<int64_t>(h[0], c->caps.max_down_points);
   if (m) *m = c->scan_m;
   if (h[0] > 0) {

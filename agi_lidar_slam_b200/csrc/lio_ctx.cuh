@@ -94,8 +94,8 @@ struct lio_ctx {
   float* d_sorted_aux = nullptr;    // N intensities in leaf-sorted order
   int* d_run_heads = nullptr;       // first sorted position of every occupied leaf
   unsigned long long* d_runs_status = nullptr;  // runs_gather_kernel: one look-back word per tile
-  unsigned* d_runs_ticket = nullptr;            // ... tile tickets (never reset: counts on from runs_ticket_base)
-  unsigned runs_ticket_base = 0, runs_tag = 0;
+  unsigned* d_runs_ticket = nullptr;            // ... tile tickets (the last tile of a launch puts it back to zero)
+  unsigned runs_tag = 0;
   uint32_t* d_sort_keys_in = nullptr;  // N linear leaf indices (and ring keys while decoding)
   uint32_t* d_sort_keys_out = nullptr;
   uint32_t* d_sort_vals_in = nullptr;

@@ -172,17 +172,17 @@ __global__ void linear_index_kernel(const int* vkeys, int n, int* counters, uint
 // tile's exclusive prefix by a decoupled look-back over the tiles before it -- each tile publishes {launch tag, state,
 // count} in one 64-bit word as soon as it knows its own count, a warp sums the published counts of up to 32 predecessors
 // per round until it meets one that already carries its inclusive prefix.  Tiles take their number from a ticket, so a
-// tile only ever waits for tiles that have already started.  Nothing is reset between launches: words are recognised by
-// the launch tag, tickets count on from ticket_base.
+// tile only ever waits for tiles that have already started.  Nothing is reset by the host between launches: words are
+// recognised by the launch tag, and the tile with the highest ticket puts the ticket counter back to zero.
 constexpr int RT = 2048;
 __global__ void __launch_bounds__(256) runs_gather_kernel(const uint32_t* keys, const uint32_t* vals, int n,
                                                           const float4* undist, const float* aux, float4* sorted_pts,
                                                           float* sorted_aux, int* heads, int* n_runs,
                                                           unsigned long long* status, unsigned* ticket,
-                                                          unsigned ticket_base, unsigned tag) {
+                                                          unsigned tag, int* stalled) {
   __shared__ int s_tile, s_prefix, s_warp[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = (int)(atomicAdd(ticket, 1u) - ticket_base);
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
   __syncthreads();
   const int tile = s_tile;
   const int j0 = tile * RT + tid * 8;
@@ -245,9 +245,14 @@ __global__ void __launch_bounds__(256) runs_gather_kernel(const uint32_t* keys, 
       unsigned st = 2, val = 0;  // before tile 0: an inclusive prefix of nothing
       if (idx >= 0) {
         unsigned long long w;
+        unsigned spins = 0;
         do {
           w = *reinterpret_cast<volatile unsigned long long*>(status + idx);
-        } while ((unsigned)(w >> 32) != tag || (((unsigned)w >> 30) & 3u) == 0);
+        } while (((unsigned)(w >> 32) != tag || (((unsigned)w >> 30) & 3u) == 0) && ++spins < (1u << 20));
+        if (spins >= (1u << 20)) {  // cannot happen with a healthy launch; never hang the device over it
+          *stalled = 1;
+          w = ((unsigned long long)tag << 32) | (2ull << 30);
+        }
         st = ((unsigned)w >> 30) & 3u;
         val = (unsigned)w & 0x3fffffffu;
       }
@@ -270,7 +275,10 @@ __global__ void __launch_bounds__(256) runs_gather_kernel(const uint32_t* keys, 
 #pragma unroll
   for (int u = 0; u < 8; ++u)
     if (f[u]) heads[base + local++] = j0 + u;
-  if (tid == 0 && tile == (n + RT - 1) / RT - 1) *n_runs = base + total;
+  if (tid == 0 && tile == (n + RT - 1) / RT - 1) {
+    *n_runs = base + total;
+    *ticket = 0;  // every ticket of this launch has been handed out (this is the highest): ready for the next launch
+  }
 }
 
 // One run of equal leaf indices per thread: FP32 sums in sorted (= ascending point) order, then / count.  The order
@@ -296,7 +304,11 @@ __global__ void __launch_bounds__(128) centroid_kernel(const float4* sorted_pts,
     // the last kernel of the preprocessing files this scan's counters as the report the host reads (counters[16..23])
     // and leaves the working set reset for the next scan -- what a one-thread reset kernel used to do before every scan
     int err = counters[7];
-    *scan_m = err == 3 ? 0 : M;
+    if (counters[14]) {  // runs_gather_kernel gave up waiting for a tile: the run heads are not to be trusted
+      err = 4;
+      counters[14] = 0;
+    }
+    *scan_m = err >= 3 ? 0 : M;
     if (Mtot > max_m && err == 0) err = 2;  // more voxels than lio_caps.max_down_points
     counters[16] = Mtot;
 #pragma unroll
@@ -692,9 +704,8 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
     const unsigned ntiles = (unsigned)((n + RT - 1) / RT);
     runs_gather_kernel<<<ntiles, 256, 0, c->stream>>>(keys_out, c->d_sort_vals_out, (int)n, c->d_undist,
                                                       has_aux ? c->d_raw_aux : nullptr, sorted_pts, sorted_aux, heads,
-                                                      n_runs, c->d_runs_status, c->d_runs_ticket, c->runs_ticket_base,
-                                                      ++c->runs_tag);
-    c->runs_ticket_base += ntiles;
+                                                      n_runs, c->d_runs_status, c->d_runs_ticket, ++c->runs_tag,
+                                                      c->d_prep_counters + 14);
     c->launches++;
   }
   if (c->centroid_wait) LIO_CHECK(c, cudaStreamWaitEvent(c->stream, c->centroid_wait, 0));
