@@ -86,3 +86,38 @@ def test_host_side_math_matches_oracle(orc):
     xo, Po = orc.predict(x, P, 0.005, Q, acc, gyr)
     assert np.allclose(xg, xo, rtol=0, atol=1e-14)
     assert np.abs(Pg - Po).max() <= 1e-12 * np.abs(Po).max()
+
+
+def test_covariance_propagation_is_bit_identical_to_the_dense_loop(orc):
+    """lio_predict writes P <- F P F^T + W Q W^T out over the fixed sparsity pattern of F and W (csrc/lio_api.cu); the
+    oracle runs the dense triple loops of esekfom.hpp:93-94.  Same sums in the same order: same bits, also for an identity
+    rotation (exact zeros in R), dt = 0 and chained steps."""
+    from agi_lidar_slam_b200 import _cabi
+
+    rng = np.random.default_rng(1)
+    for t in range(60):
+        x = orc.default_state()
+        x[0:3] = rng.normal(size=3)
+        x[3:7] = orc.so3_exp(rng.normal(size=3) * 0.7) if t % 4 else np.array([1.0, 0, 0, 0])
+        x[7:11] = orc.so3_exp(rng.normal(size=3) * 0.1)
+        x[11:23] = rng.normal(size=12) * 0.1
+        A = rng.normal(size=(24, 24))
+        P = A @ A.T * 1e-3 + np.eye(24) * 1e-4
+        Q = np.diag(rng.uniform(1e-5, 1e-1, 12))
+        acc, gyr = rng.normal(size=3) * 3, rng.normal(size=3) * 0.3
+        dt = 0.0 if t == 5 else float(rng.uniform(1e-4, 2e-2))
+        for _ in range(3):
+            xg, Pg = _cabi.predict(x, P, dt, Q, acc, gyr)
+            xo, Po = orc.predict(x, P, dt, Q, acc, gyr)
+            assert np.array_equal(xg, xo) and np.array_equal(Pg, Po), t
+            x, P = xo, Po
+
+
+def test_host_thread_setting_is_validated():
+    from agi_lidar_slam_b200 import _cabi
+
+    for bad in (-1, 65):
+        with pytest.raises(ValueError):
+            _cabi.set_host_threads(bad)
+    _cabi.set_host_threads(3)
+    _cabi.set_host_threads(0)
