@@ -96,7 +96,7 @@ class CloudLayout(C.Structure):
 EXPORTS = [
     "lio_abi_version", "lio_default_caps", "lio_create", "lio_destroy", "lio_set_stream", "lio_synchronize",
     "lio_last_error", "lio_launch_count", "lio_map_build", "lio_map_add", "lio_map_delete_boxes", "lio_map_size",
-    "lio_map_dump", "lio_knn5", "lio_knn5_resident", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_preprocess_cloud2", "lio_scan_decoded",
+    "lio_map_dump", "lio_map_set_downsample", "lio_knn5", "lio_knn5_resident", "lio_scan_preprocess", "lio_scan_preprocess_resident", "lio_scan_preprocess_cloud2", "lio_scan_decoded",
     "lio_scan_upload",
     "lio_update_pass", "lio_update_scan", "lio_update_scan_host", "lio_state_upload", "lio_state_download", "lio_update_enqueue",
     "lio_update_enqueue_multi", "lio_scan_step", "lio_scan_step_begin", "lio_scan_step_end",
@@ -139,7 +139,8 @@ def load_library() -> C.CDLL:
         "lio_map_delete_boxes": (C.c_int, [vp, vp, C.c_int, P(i32)]),
         "lio_map_size": (C.c_int, [vp, P(i64), P(i64)]),
         "lio_map_dump": (C.c_int, [vp, vp, vp, i64, P(i64)]),
-        "lio_knn5": (C.c_int, [vp, vp, i64, vp, vp, vp]),
+        "lio_knn5": (C.c_int, [vp, vp, i64, C.c_float, vp, vp, vp]),
+        "lio_map_set_downsample": (C.c_int, [vp, C.c_float]),
         "lio_knn5_resident": (C.c_int, [vp, i64]),
         "lio_scan_preprocess": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, f32, vp, P(i64), vp, vp]),
         "lio_scan_preprocess_resident": (C.c_int, [vp, vp, i64, C.c_int, vp, C.c_int, vp, f32, P(i64)]),
@@ -313,13 +314,17 @@ class Context:
             self._check(self._lib.lio_map_dump(self._h, _ptr(xyz), _ptr(ids), n.value, C.byref(n)))
         return xyz, ids
 
-    def knn5(self, q_xyz, want_xyz=True):
+    def map_set_downsample(self, downsample_size: float):
+        self._check(self._lib.lio_map_set_downsample(self._h, float(downsample_size)))
+
+    def knn5(self, q_xyz, want_xyz=True, max_d2=5.0):
+        """max_d2 = max_dist ** 2 of KD_TREE::Nearest_Search; np.inf is the reference's default (unbounded)."""
         q = _f32(q_xyz, 3)
         m = q.shape[0]
         idx = np.full((m, 5), -1, np.int32)
         d2 = np.full((m, 5), np.inf, np.float32)
         nbr = np.zeros((m, 5, 3), np.float32) if want_xyz else None
-        self._check(self._lib.lio_knn5(self._h, _ptr(q), m, _ptr(idx), _ptr(d2), _ptr(nbr)))
+        self._check(self._lib.lio_knn5(self._h, _ptr(q), m, float(max_d2), _ptr(idx), _ptr(d2), _ptr(nbr)))
         return idx, d2, nbr
 
     def knn5_resident(self, m: int):

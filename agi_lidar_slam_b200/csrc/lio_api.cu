@@ -114,7 +114,8 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->map.cell_pend, 4 * (size_t)c->hash_cap);
   ALLOC(c->map.cell_base, 4 * (size_t)c->hash_cap);
   ALLOC(c->map.pool, sizeof(float4) * (size_t)c->map.pool_cap);
-  ALLOC(c->map.counters, 4 * 8);
+  ALLOC(c->map.counters, 4 * 16);
+  c->map_downsample = k.map_downsample;
   c->batch_cap = std::max<int64_t>(k.max_map_points, k.max_down_points);
   ALLOC(c->d_batch_pts, sizeof(float4) * (size_t)c->batch_cap);
   ALLOC(c->d_batch_slot, 4 * (size_t)c->batch_cap);
@@ -131,6 +132,9 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_near, sizeof(float4) * M * LIO_K);
   ALLOC(c->d_near_d2, 4 * M * LIO_K);
   ALLOC(c->d_near_cnt, 4 * M);
+  ALLOC(c->d_near_q, sizeof(float4) * M);
+  ALLOC(c->d_far_list, 4 * M);
+  ALLOC(c->d_far_n, 4);
   ALLOC(c->d_selected, M);
   ALLOC(c->d_normvec, sizeof(float4) * M);
   ALLOC(c->d_plane, sizeof(float4) * M);
@@ -261,6 +265,7 @@ void lio_destroy(lio_ctx* c) {
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
                   c->d_vox_best,  c->d_vox_key,     c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
+                  c->d_near_q,    c->d_far_list,    c->d_far_n,
                   c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,
                   c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,      c->d_mailbox,
                   c->d_cloud,
@@ -310,6 +315,15 @@ int lio_synchronize(lio_ctx* c) {
 // host's view of the map (settle_growth), at the latest by the growth of the next scan.
 }  // extern "C"
 namespace lio {
+// Point ids are int32 and a negative id marks a dead slot: the id space must not wrap.  Every candidate of every insert
+// takes an id (the rejected ones too), so a long run can use it up (~2^31 candidates: tens of hours at 10 Hz).
+int check_id_space(lio_ctx* c, int64_t n_new) {
+  if ((int64_t)c->next_id + n_new > (int64_t)INT32_MAX - 1) {
+    c->err = "map point ids exhausted (2^31 insert candidates): rebuild the map from lio_map_dump to renumber";
+    return LIO_E_CAPACITY;
+  }
+  return LIO_OK;
+}
 int settle_growth(lio_ctx* c) {
   if (!c->growth_pending) return LIO_OK;
   c->growth_pending = false;
@@ -366,6 +380,12 @@ int lio_map_build(lio_ctx* c, const void* pts, int64_t n, int stride) {
   return LIO_OK;
 }
 
+int lio_map_set_downsample(lio_ctx* c, float downsample_size) {
+  if (!c || !(downsample_size > 0.f)) return LIO_E_INVALID;
+  c->map_downsample = downsample_size;
+  return LIO_OK;
+}
+
 int lio_map_add(lio_ctx* c, const void* pts, int64_t n, int stride, int downsample_on, int32_t* n_added) {
   if (!c || n < 0 || (stride != 16 && stride != 48) || (n > 0 && !pts)) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
@@ -380,6 +400,7 @@ int lio_map_add(lio_ctx* c, const void* pts, int64_t n, int stride, int downsamp
     c->err = "Add_Points batch too large";
     return LIO_E_CAPACITY;
   }
+  if (const int ri = check_id_space(c, n)) return ri;
   int rc = stage_points(c, pts, n, stride, 32, c->d_batch_pts, 0, nullptr, reinterpret_cast<float*>(c->d_batch_slot));
   if (rc) return rc;
   if (downsample_on) {
@@ -441,9 +462,13 @@ static int download_neighbors(lio_ctx* c, int64_t m, int32_t* idx5, float* d2_5,
   return LIO_OK;
 }
 
-int lio_knn5(lio_ctx* c, const float* q_xyz, int64_t m, int32_t* idx5, float* d2_5, float* nbr_xyz) {
-  if (!c || m < 0 || (m > 0 && !q_xyz)) return LIO_E_INVALID;
+int lio_knn5(lio_ctx* c, const float* q_xyz, int64_t m, float max_d2, int32_t* idx5, float* d2_5, float* nbr_xyz) {
+  if (!c || m < 0 || (m > 0 && !q_xyz) || !(max_d2 >= 0.f)) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
+  // a bound beyond the hot search's (caps.knn_max_d2): the rows that search leaves short are completed by the
+  // unbounded search, and whatever lies beyond max_d2 is cut off again below
+  const bool beyond = max_d2 > c->caps.knn_max_d2;
   // processed in chunks of max_down_points through the scan-sized buffers (this invalidates cached neighbours)
   const int64_t chunk = c->caps.max_down_points;
   for (int64_t off = 0; off < m; off += chunk) {
@@ -454,9 +479,27 @@ int lio_knn5(lio_ctx* c, const float* q_xyz, int64_t m, int32_t* idx5, float* d2
     c->launches++;
     int rc = launch_knn_batch(c, c->d_world, cm);
     if (rc) return rc;
-    rc = download_neighbors(c, cm, idx5 ? idx5 + off * LIO_K : nullptr, d2_5 ? d2_5 + off * LIO_K : nullptr,
-                            nbr_xyz ? nbr_xyz + off * LIO_K * 3 : nullptr);
+    if (beyond) {
+      rc = launch_far_complete(c, c->d_world, cm, 0, cm, LIO_K);
+      if (rc) return rc;
+    }
+    int32_t* ip = idx5 ? idx5 + off * LIO_K : nullptr;
+    float* dp = d2_5 ? d2_5 + off * LIO_K : nullptr;
+    float* xp = nbr_xyz ? nbr_xyz + off * LIO_K * 3 : nullptr;
+    std::vector<float> dtmp;
+    if (!dp && (beyond || max_d2 < c->caps.knn_max_d2)) {  // the cut needs the distances
+      dtmp.resize((size_t)cm * LIO_K);
+      dp = dtmp.data();
+    }
+    rc = download_neighbors(c, cm, ip, dp, xp);
     if (rc) return rc;
+    if (dp && max_d2 != c->caps.knn_max_d2)
+      for (int64_t j = 0; j < cm * LIO_K; ++j)
+        if (!(dp[j] <= max_d2)) {  // `dist <= max_dist_sqr` (ikd_Tree.cpp:980)
+          dp[j] = INFINITY;
+          if (ip) ip[j] = -1;
+          if (xp) xp[3 * j] = xp[3 * j + 1] = xp[3 * j + 2] = 0.f;
+        }
   }
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
   return LIO_OK;
@@ -920,6 +963,7 @@ int lio_scan_step_end(lio_ctx* c, float leaf_map, int ekf_inited) {
   LIO_CHECK(c, cudaSetDevice(c->device));
   int rc = settle_growth(c);  // the previous scan's growth is long done by now: books next_id for this one
   if (rc) return rc;
+  if (leaf_map > 0.f && (rc = check_id_space(c, c->scan_m_bound)) != LIO_OK) return rc;
   // posterior + preprocess counters first: with deferred growth the host resumes as soon as these have landed
   double* hp = static_cast<double*>(c->h_pinned);
   LIO_CHECK(c, cudaMemcpyAsync(hp, c->d_x, 8 * 606, cudaMemcpyDeviceToHost, c->stream));
@@ -1159,6 +1203,13 @@ int lio_get_neighbors(lio_ctx* c, int32_t* idx5, float* d2_5, float* nbr_xyz, fl
   if (rc) return rc;
   const int64_t m = c->scan_m;
   if (m <= 0) return LIO_OK;
+  if (idx5 || d2_5 || nbr_xyz) {
+    // the rows the update's bounded search left short become what the reference's unbounded Nearest_Search leaves in
+    // Nearest_Points (esekfom.hpp:140-141): five neighbours wherever the map holds five points
+    if (!c->map_built) return LIO_E_EMPTY_MAP;
+    rc = launch_far_complete(c, c->d_near_q, m, 0, m, LIO_K);
+    if (rc) return rc;
+  }
   rc = download_neighbors(c, m, idx5, d2_5, nbr_xyz);
   if (rc) return rc;
   std::vector<float4> h;

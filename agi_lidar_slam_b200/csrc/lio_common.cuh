@@ -33,6 +33,8 @@ struct MapView {
   uint32_t hash_mask;
   uint32_t pool_cap;
   uint32_t* counters;  // [0] pool_top  [1] n_cells  [2] n_live  [3] error flag  [4] scratch count  [5] slots used
+                       // [8..10] / [11..13] smallest / largest cell index (as int) that ever held a point: the box an
+                       // unbounded search has to cover (warp_knn_far)
   float inv_cell;
   float cell;
 };

@@ -22,6 +22,7 @@ struct lio_ctx {
   int32_t next_id = 0;     // id given to the next inserted point (host mirror)
   bool map_built = false;  // ≙ ikdtree.Root_Node != nullptr
   int knn_rings = 3;
+  float map_downsample = 0.5f;  // ≙ KD_TREE::downsample_size (set_downsample_param, laserMapping.cpp:748)
   // batch scratch (sized for max(max_down_points, build chunk))
   int64_t batch_cap = 0;
   float4* d_batch_pts = nullptr;    // staged points of the current insert batch
@@ -39,7 +40,10 @@ struct lio_ctx {
   float4* d_world = nullptr;        // M x FP32 p_world of the last pass
   float4* d_near = nullptr;         // M x 5 cached Nearest_Points (x,y,z,id bits)
   float* d_near_d2 = nullptr;       // M x 5
-  int* d_near_cnt = nullptr;        // M
+  int* d_near_cnt = nullptr;        // M: length of the row's known prefix of the unbounded neighbour list
+  float4* d_near_q = nullptr;       // M: FP32 p_world the row was searched at
+  int* d_far_list = nullptr;        // M: rows handed to far_search_kernel
+  int* d_far_n = nullptr;           // their number
   uint8_t* d_selected = nullptr;    // M point_selected_surf
   float4* d_normvec = nullptr;      // M x (a,b,c,pd2)
   float4* d_plane = nullptr;        // M x pabcd fitted by the last search pass
@@ -159,6 +163,7 @@ int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float ow
 int launch_solve(lio_ctx* c, double R, int extrinsic_est);
 int launch_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot);
 int launch_knn_batch(lio_ctx* c, const float4* d_q, int64_t m);
+int launch_far_complete(lio_ctx* c, const float4* d_q, int64_t m, int min_m, int64_t bound, int need);
 
 int map_reset(lio_ctx* c);
 int map_append_batch(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, const uint8_t* d_flag);
@@ -168,6 +173,7 @@ int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
 int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]);
 int map_incremental_enqueue(lio_ctx* c, float fsm, int ekf_inited, int min_m, int64_t bound);
 int map_build_scan(lio_ctx* c, const lio_state* x);
+int check_id_space(lio_ctx* c, int64_t n_new);  // lio_api.cu: LIO_E_CAPACITY when n_new more ids would wrap int32
 int settle_growth(lio_ctx* c);  // lio_api.cu: waits for a deferred map growth and books its counts (no-op otherwise)
 
 int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux);

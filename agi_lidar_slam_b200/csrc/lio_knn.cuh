@@ -227,6 +227,152 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// UNBOUNDED k-nearest search of one query by one warp: what KD_TREE::Nearest_Search returns with its default
+// max_dist = INFINITY (ikd_Tree.h:285), the way esekfom.hpp:140-141 calls it.  The hot search above is bounded at
+// d2 <= 5 (all the update's gate needs, esekfom.hpp:144-147); this one serves the rows it left incomplete -- map-frontier
+// points whose neighbours lie farther away, which map_incremental still reads (laserMapping.cpp:391-423).
+// Shells of cells at Chebyshev distance r = 0, 1, 2, ... around the query's cell, dealt to the 32 lanes and clipped to
+// the bounding box of the cells the map has ever used (MapView::counters[8..13]).  After shell r every unseen point is
+// farther than r * cell, so the search stops once the `need`-th best is closer than that, or the box is exhausted.
+// `need` = 1 ... 5 neighbours wanted (the stop rule only; the lanes always keep five).  Outputs as group_knn5.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
+    if (o < k) k = o;
+  }
+  return k;
+}
+// d2 bits of the need-th smallest key held by the warp's lanes (0xFFFFFFFF when there are fewer); `top` is not changed
+__device__ __forceinline__ uint32_t warp_kth_bits(TopK t, int need) {
+  unsigned long long k = ~0ull;
+#pragma unroll 1
+  for (int r = 0; r < need; ++r) {
+    k = warp_min_u64(t.k0);
+    if (k == ~0ull) break;
+    if (t.k0 == k) t.pop();
+  }
+  return (uint32_t)(k >> 32);
+}
+
+__device__ __noinline__ int warp_knn_far(const MapView& map, float qx, float qy, float qz, int need,
+                                         unsigned long long out_key[LIO_K], uint32_t out_slot[LIO_K]) {
+  const int lane = threadIdx.x & 31;
+  const int c[3] = {cell_coord(qx, map.inv_cell), cell_coord(qy, map.inv_cell), cell_coord(qz, map.inv_cell)};
+  int lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = (int)__ldcg(map.counters + 8 + a);
+    hi[a] = (int)__ldcg(map.counters + 11 + a);
+  }
+  TopK top;
+  top.init();
+  int r0 = 0, rmax = -1;  // first shell that touches the box, last shell that does
+  if (lo[0] <= hi[0]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      r0 = max(r0, max(lo[a] - c[a], c[a] - hi[a]));
+      rmax = max(rmax, max(abs(c[a] - lo[a]), abs(c[a] - hi[a])));
+    }
+  }
+  uint32_t kth = 0xFFFFFFFFu;  // d2 bits of the need-th best after the last completed shell
+  if (r0 > 256) {
+    // the query is hundreds of cells away from everything: walking empty shells towards the box would cost more than
+    // the box itself, so its cells are simply all visited (no LiDAR return is that far from its map; this keeps the
+    // call exact and bounded whatever it is handed)
+    const long long nx = (long long)hi[0] - lo[0] + 1, ny = (long long)hi[1] - lo[1] + 1, nz = (long long)hi[2] - lo[2] + 1;
+#pragma unroll 1
+    for (long long t = lane; t < nx * ny * nz; t += 32) {
+      const int x = lo[0] + (int)(t % nx), y = lo[1] + (int)((t / nx) % ny), z = lo[2] + (int)(t / (nx * ny));
+      uint32_t start, count;
+      if (map_find(map, pack_cell(x, y, z), start, count) < 0) continue;
+#pragma unroll 1
+      for (uint32_t j = 0; j < count; ++j) {
+        const float4 p = __ldg(map.pool + start + j);
+        if (__float_as_int(p.w) < 0) continue;
+        const uint32_t d = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
+        top.insert(((unsigned long long)d << 32) | __float_as_uint(p.w), start + j);
+      }
+    }
+    rmax = -1;  // skip the shells
+  }
+#pragma unroll 1
+  for (int r = r0; r <= rmax; ++r) {
+    if (r > r0 && kth != 0xFFFFFFFFu) {
+      // every cell of shell r and beyond is farther than (r - 1) * cell from the query's cell, hence from the query.
+      // 0.999: cell_coord rounds x * inv_cell, so a point can sit one ulp across the border of the cell it is filed in
+      const float cover = (float)(r - 1) * map.cell * 0.999f;
+      if (__uint_as_float(kth) < cover * cover) break;
+    }
+    const int side = 2 * r + 1;
+    const int n_face = side * side;
+    const int n_cells = r == 0 ? 1 : 2 * n_face + (side - 2) * 8 * r;
+#pragma unroll 1
+    for (int t = lane; t < n_cells; t += 32) {
+      int dx, dy, dz;
+      if (t < 2 * n_face || r == 0) {  // the two full faces dz = -r, +r
+        const int f = t >= n_face ? 1 : 0;
+        const int e = t - f * n_face;
+        dz = f ? r : -r;
+        dy = e / side - r;
+        dx = e % side - r;
+      } else {  // the perimeter of the layers in between: 8r cells each
+        const int e = t - 2 * n_face;
+        const int layer = e / (8 * r), o = e % (8 * r);
+        dz = -r + 1 + layer;
+        const int s = o / (2 * r), u = o % (2 * r);
+        dx = s == 0 ? -r + u : (s == 1 ? r : (s == 2 ? r - u : -r));
+        dy = s == 0 ? -r : (s == 1 ? -r + u : (s == 2 ? r : r - u));
+      }
+      const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+      if (x < lo[0] || x > hi[0] || y < lo[1] || y > hi[1] || z < lo[2] || z > hi[2]) continue;
+      if (kth != 0xFFFFFFFFu) {  // cell farther than the need-th best already: nothing in it can matter
+        const float lx = (float)x * map.cell, ly = (float)y * map.cell, lz = (float)z * map.cell;
+        const float ex = fmaxf(fmaxf(lx - qx, qx - (lx + map.cell)), 0.f);
+        const float ey = fmaxf(fmaxf(ly - qy, qy - (ly + map.cell)), 0.f);
+        const float ez = fmaxf(fmaxf(lz - qz, qz - (lz + map.cell)), 0.f);
+        if ((ex * ex + ey * ey + ez * ez) * 0.998f > __uint_as_float(kth)) continue;
+      }
+      uint32_t start, count;
+      if (map_find(map, pack_cell(x, y, z), start, count) < 0) continue;
+#pragma unroll 1
+      for (uint32_t j = 0; j < count; ++j) {
+        const float4 p = __ldg(map.pool + start + j);
+        if (__float_as_int(p.w) < 0) continue;
+        const uint32_t d = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
+        top.insert(((unsigned long long)d << 32) | __float_as_uint(p.w), start + j);
+      }
+    }
+    __syncwarp();
+    kth = warp_kth_bits(top, need);
+  }
+  __syncwarp();
+  int found = 0;
+#pragma unroll
+  for (int r = 0; r < LIO_K; ++r) {
+    unsigned long long k = top.k0;
+    uint32_t sl = top.s0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, off);
+      const uint32_t os = __shfl_xor_sync(0xffffffffu, sl, off);
+      if (ok < k) {
+        k = ok;
+        sl = os;
+      }
+    }
+    out_key[r] = k;
+    out_slot[r] = sl;
+    if (k != ~0ull) {
+      if (top.k0 == k) top.pop();
+      ++found;
+    }
+  }
+  return found;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // esti_plane<float> (common_lib.h:102-134): 5x3 FP32 column-pivoted Householder QR solve of A n = -1 in the
 // operation order of SURVEY.md App. B.1 (Eigen ColPivHouseholderQR recipe), one IEEE rounding per operation.
 // P[j] = neighbour j (x,y,z).  Returns true when all 5 neighbours lie within `thr` of the fitted plane.

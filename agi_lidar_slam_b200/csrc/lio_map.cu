@@ -18,7 +18,10 @@ __global__ void map_init_kernel(MapView m, uint32_t hash_cap) {
     m.cell_pend[h] = 0;
     m.cell_base[h] = 0;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 8) m.counters[threadIdx.x] = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 16)
+    m.counters[threadIdx.x] = threadIdx.x >= 8 && threadIdx.x < 11    ? 0x7fffffffu               // cell box: empty
+                              : threadIdx.x >= 11 && threadIdx.x < 14 ? (uint32_t)(-0x7fffffff)
+                                                                      : 0u;
 }
 
 // Batch size and id base of an insert: host values, or -- when the host enqueues a whole scan without waiting for the
@@ -36,34 +39,70 @@ __device__ __forceinline__ int batch_id(int id_base, const BatchDev& b) {
   return id_base + (b.id_off_dev ? *b.id_off_dev : 0);
 }
 
-// phase 1: find-or-create the cell of every point, take a rank inside this batch
-__global__ void map_reserve_kernel(MapView m, const float4* pts, int n, BatchDev bd, const uint8_t* flag, uint32_t* slot,
-                                   uint32_t* rank) {
+// phase 1: find-or-create the cell of every point, take a rank inside this batch; the box of cells ever used
+// (counters[8..13], what an unbounded search has to cover) grows by a block-level reduction and at most six atomics
+__global__ void __launch_bounds__(256) map_reserve_kernel(MapView m, const float4* pts, int n, BatchDev bd,
+                                                          const uint8_t* flag, uint32_t* slot, uint32_t* rank) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   n = batch_n(n, bd);
-  if (i >= n) return;
-  if (flag && !flag[i]) return;
-  const float4 p = pts[i];
-  const unsigned long long key =
-      pack_cell(cell_coord(p.x, m.inv_cell), cell_coord(p.y, m.inv_cell), cell_coord(p.z, m.inv_cell));
-  uint32_t h = hash64(key) & m.hash_mask;
-  uint32_t probes = 0;
-  for (;;) {
-    const unsigned long long prev = atomicCAS(&m.table[h].key, LIO_EMPTY_KEY, key);
-    if (prev == LIO_EMPTY_KEY) {
-      atomicAdd(&m.counters[1], 1u);
-      break;
+  const bool act = i < n && (!flag || flag[i]);
+  int cc[3] = {0, 0, 0};
+  if (act) {
+    const float4 p = pts[i];
+    cc[0] = cell_coord(p.x, m.inv_cell);
+    cc[1] = cell_coord(p.y, m.inv_cell);
+    cc[2] = cell_coord(p.z, m.inv_cell);
+    const unsigned long long key = pack_cell(cc[0], cc[1], cc[2]);
+    uint32_t h = hash64(key) & m.hash_mask;
+    uint32_t probes = 0;
+    bool full = false;
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&m.table[h].key, LIO_EMPTY_KEY, key);
+      if (prev == LIO_EMPTY_KEY) {
+        atomicAdd(&m.counters[1], 1u);
+        break;
+      }
+      if (prev == key) break;
+      h = (h + 1) & m.hash_mask;
+      if (++probes > m.hash_mask) {
+        full = true;
+        break;
+      }
     }
-    if (prev == key) break;
-    h = (h + 1) & m.hash_mask;
-    if (++probes > m.hash_mask) {
+    if (full) {
       atomicExch(&m.counters[3], 1u);
       slot[i] = BASE_SENTINEL;
-      return;
+    } else {
+      slot[i] = h;
+      rank[i] = atomicAdd(&m.cell_pend[h], 1u);
     }
   }
-  slot[i] = h;
-  rank[i] = atomicAdd(&m.cell_pend[h], 1u);
+  __shared__ int s_red[6][8];
+  const int big = 0x7fffffff;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int mn = __reduce_min_sync(0xffffffffu, act ? cc[a] : big);
+    const int mx = __reduce_max_sync(0xffffffffu, act ? cc[a] : -big);
+    if (lane == 0) {
+      s_red[a][warp] = mn;
+      s_red[3 + a][warp] = mx;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const bool is_min = threadIdx.x < 3;
+    int v = s_red[threadIdx.x][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) v = is_min ? min(v, s_red[threadIdx.x][w]) : max(v, s_red[threadIdx.x][w]);
+    int* g = reinterpret_cast<int*>(m.counters) + 8 + threadIdx.x;
+    const int cur = *reinterpret_cast<volatile int*>(g);  // most blocks do not extend the box: a load, no atomic
+    if (is_min) {
+      if (v < cur) atomicMin(g, v);
+    } else {
+      if (v > cur) atomicMax(g, v);
+    }
+  }
 }
 
 // phase 2: one thread per touched cell makes room (amortised doubling; the live points move, the old run is retired)
@@ -203,7 +242,7 @@ __global__ void vox_apply_kernel(MapView m, const float4* pts, int n, BatchDev b
   int E = 0;
   float best_d = dnew;
   int best_id = -1;
-  uint32_t best_slot = 0, first_slot = 0;
+  uint32_t best_slot = 0;
   for (int cz = c0[2]; cz <= c1[2]; ++cz)
     for (int cy = c0[1]; cy <= c1[1]; ++cy)
       for (int cx = c0[0]; cx <= c1[0]; ++cx) {
@@ -215,7 +254,6 @@ __global__ void vox_apply_kernel(MapView m, const float4* pts, int n, BatchDev b
           if (id < 0) continue;
           if (g.bmin[0] <= q.x && g.bmax[0] > q.x && g.bmin[1] <= q.y && g.bmax[1] > q.y && g.bmin[2] <= q.z &&
               g.bmax[2] > q.z) {
-            if (E == 0) first_slot = start + t;
             ++E;
             const float d = dist2(q.x, q.y, q.z, g.mid[0], g.mid[1], g.mid[2]);
             if (d < best_d || (best_id >= 0 && d == best_d && id < best_id)) {
@@ -232,8 +270,10 @@ __global__ void vox_apply_kernel(MapView m, const float4* pts, int n, BatchDev b
     atomicAdd(&m.counters[4], 1u);
     return;
   }
-  // collapse the voxel to the winner
-  const uint32_t keep_slot = best_id >= 0 ? best_slot : first_slot;
+  // collapse the voxel to the winner: an existing winner keeps its slot; a new winner retires every point of the box
+  // and goes through the normal append (reserve / grow / fill) so that it is filed in the bucket of ITS OWN cell -- the
+  // voxel need not lie inside one kNN cell (any downsample size is allowed), and a point filed under a neighbour's
+  // cell would be invisible to the searches that rely on "the 3x3x3 block holds everything within one cell edge"
   for (int cz = c0[2]; cz <= c1[2]; ++cz)
     for (int cy = c0[1]; cy <= c1[1]; ++cy)
       for (int cx = c0[0]; cx <= c1[0]; ++cx) {
@@ -243,18 +283,19 @@ __global__ void vox_apply_kernel(MapView m, const float4* pts, int n, BatchDev b
           float4 q = m.pool[start + t];
           if (__float_as_int(q.w) < 0) continue;
           if (g.bmin[0] <= q.x && g.bmax[0] > q.x && g.bmin[1] <= q.y && g.bmax[1] > q.y && g.bmin[2] <= q.z &&
-              g.bmax[2] > q.z && start + t != keep_slot) {
+              g.bmax[2] > q.z && (best_id < 0 || start + t != best_slot)) {
             q.w = __int_as_float(-1);
             m.pool[start + t] = q;
           }
         }
       }
   if (best_id < 0) {
-    // the new point wins and reuses the first slot of its voxel
-    m.pool[keep_slot] = make_float4(p.x, p.y, p.z, __int_as_float(id_base + i));
+    append_flag[i] = 1;
     atomicAdd(&m.counters[4], 1u);
+    atomicSub(&m.counters[2], (uint32_t)E);
+  } else {
+    atomicSub(&m.counters[2], (uint32_t)(E - 1));
   }
-  if (E > 1) atomicSub(&m.counters[2], (uint32_t)(E - 1));
 }
 
 // ---- Delete_Point_Boxes / flatten: pool sweeps --------------------------------------------------------------------
@@ -288,10 +329,19 @@ __global__ void map_dump_kernel(MapView m, float4* out, uint32_t cap, uint32_t* 
 }
 
 // ---- map_incremental (laserMapping.cpp:382-433) -------------------------------------------------------------------
-// class 0 = skip, 1 = PointToAdd (Add_Points with downsample), 2 = PointNoNeedDownsample
+// class 0 = skip, 1 = PointToAdd (Add_Points with downsample), 2 = PointNoNeedDownsample.
+// The reference reads Nearest_Points[i] as its UNBOUNDED search left it (esekfom.hpp:140-141: min(5, #live points)
+// neighbours, however far).  Here a row holds a known PREFIX of that list, near_cnt[i] long: the neighbours within
+// d2 <= 5 from the update's search, extended by far_search_kernel to at least one entry (map_incremental_enqueue).
+// That decides every row exactly as the full list would:
+//   * `!Nearest_Points[i].empty()` and `points_near.size() < NUM_MATCH_POINTS` depend on the map only (n_live);
+//   * points_near[0] is in the prefix;
+//   * a neighbour beyond the prefix is farther than sqrt(5) m from the point, which itself lies within sqrt(3)/2 * fs
+//     of its voxel centre: for 3 fs^2 <= 5 it cannot be closer to the centre than the point is (:416-422 stays false).
+//     For larger filter_size_map the caller completes the rows to all five entries first.
 __global__ void map_incr_classify_kernel(const float4* body, const int* scan_m, const StateD* xs, const float4* near_pts,
-                                         const int* near_cnt, int ekf_inited, float fsm, int min_m, float4* world,
-                                         uint8_t* cls) {
+                                         const int* near_cnt, const uint32_t* map_counters, int ekf_inited, float fsm,
+                                         int min_m, float4* world, uint8_t* cls) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int M = *scan_m;
   if (i >= M || M < min_m) return;  // fewer than min_m points: the main loop skips the scan (laserMapping.cpp:741-744)
@@ -311,6 +361,7 @@ __global__ void map_incr_classify_kernel(const float4* body, const int* scan_m, 
   world[i] = make_float4(pw[0], pw[1], pw[2], b.w);
   uint8_t c = 1;
   const int cnt = near_cnt[i];
+  const uint32_t n_live = map_counters[2];  // size of the reference's list = min(5, n_live)
   if (cnt > 0 && ekf_inited) {
     const double fs = (double)fsm;
     float mid[3];
@@ -323,12 +374,13 @@ __global__ void map_incr_classify_kernel(const float4* body, const int* scan_m, 
       c = 2;
     } else {
       bool need_add = true;
-      for (int j = 0; j < LIO_K; ++j) {
-        if (cnt < LIO_K) break;
-        const float4 q = near_pts[(size_t)i * LIO_K + j];
-        if (dist2(q.x, q.y, q.z, mid[0], mid[1], mid[2]) < dist) {
-          need_add = false;
-          break;
+      if (n_live >= LIO_K) {  // `if (points_near.size() < NUM_MATCH_POINTS) break;`
+        for (int j = 0; j < cnt; ++j) {
+          const float4 q = near_pts[(size_t)i * LIO_K + j];
+          if (dist2(q.x, q.y, q.z, mid[0], mid[1], mid[2]) < dist) {
+            need_add = false;
+            break;
+          }
         }
       }
       c = need_add ? 1 : 0;
@@ -472,7 +524,7 @@ int map_append_batch(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base
 
 // Add_Points(downsample_on = true), first half, enqueue only: per batch voxel the winner settles it against the map and
 // append_flag says which points remain to be appended; the number of points added ends up in map.counters[4].
-static int vox_phase_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base) {
+static int vox_phase_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base, float ds) {
   if (n > c->batch_cap || (uint64_t)n * 2 > c->vox_cap) {
     c->err = "Add_Points batch larger than the context's batch capacity";
     return LIO_E_CAPACITY;
@@ -481,18 +533,18 @@ static int vox_phase_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const i
   const BatchDev bd{n_dev, nullptr};
   LIO_CHECK(c, cudaMemsetAsync(c->map.counters + 4, 0, sizeof(uint32_t), c->stream));
   vox_init_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(c->d_vox_key, c->d_vox_best, c->vox_cap);
-  vox_best_kernel<<<grid, 256, 0, c->stream>>>(d_pts, (int)n, bd, c->caps.map_downsample, c->d_vox_key, c->d_vox_best,
-                                               c->vox_cap - 1, c->d_batch_rank /*reused as vslot*/);
-  vox_apply_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, bd, c->caps.map_downsample, c->d_vox_best,
-                                                c->d_batch_rank, id_base, c->d_batch_flag);
+  vox_best_kernel<<<grid, 256, 0, c->stream>>>(d_pts, (int)n, bd, ds, c->d_vox_key, c->d_vox_best, c->vox_cap - 1,
+                                               c->d_batch_rank /*reused as vslot*/);
+  vox_apply_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_pts, (int)n, bd, ds, c->d_vox_best, c->d_batch_rank, id_base,
+                                                c->d_batch_flag);
   c->launches += 3;
   LIO_CHECK(c, cudaGetLastError());
   return LIO_OK;
 }
 
-int map_add_downsample_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base) {
+int map_add_downsample_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const int* n_dev, int32_t id_base, float ds) {
   if (n <= 0) return LIO_OK;
-  const int rc = vox_phase_enqueue(c, d_pts, n, n_dev, id_base);
+  const int rc = vox_phase_enqueue(c, d_pts, n, n_dev, id_base, ds);
   if (rc) return rc;
   return map_append_batch_enqueue(c, d_pts, n, n_dev, id_base, nullptr, c->d_batch_flag);
 }
@@ -500,7 +552,7 @@ int map_add_downsample_enqueue(lio_ctx* c, const float4* d_pts, int64_t n, const
 int map_add_downsample(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, int32_t* n_added) {
   if (n_added) *n_added = 0;
   if (n <= 0) return LIO_OK;
-  int rc = map_add_downsample_enqueue(c, d_pts, n, nullptr, id_base);
+  int rc = map_add_downsample_enqueue(c, d_pts, n, nullptr, id_base, c->map_downsample);
   if (rc) return rc;
   rc = check_map_error(c);
   if (rc) return rc;
@@ -606,14 +658,20 @@ int map_incremental_enqueue(lio_ctx* c, float fsm, int ekf_inited, int min_m, in
   }
   const int grid = (int)((bound + 255) / 256);
   int* d_counts = c->d_prep_counters + 8;
+  // rows the update's bounded search left empty get their nearest neighbour from the unbounded search -- all five
+  // when filter_size_map is so large that the prefix argument of map_incr_classify_kernel does not hold
+  const int need = (3.0f * fsm * fsm <= 0.95f * c->caps.knn_max_d2) ? 1 : LIO_K;
+  int rc = launch_far_complete(c, c->d_near_q, -1, min_m, bound, need);
+  if (rc) return rc;
   map_incr_classify_kernel<<<grid, 256, 0, c->stream>>>(c->d_body, c->d_scan_m, c->d_x, c->d_near, c->d_near_cnt,
-                                                        ekf_inited, fsm, min_m, c->d_world, c->d_cls);
+                                                        c->map.counters, ekf_inited, fsm, min_m, c->d_world, c->d_cls);
   map_incr_compact_kernel<<<1, 1024, 0, c->stream>>>(c->d_world, c->d_cls, c->d_scan_m, min_m, c->d_add_a,
                                                      c->d_batch_flag, d_counts);
   c->launches += 2;
   // Add_Points(PointToAdd, true) decides on the first n_a points; one reserve / grow / fill appends what it leaves of
-  // them together with Add_Points(PointNoNeedDownsample, false)
-  const int rc = vox_phase_enqueue(c, c->d_add_a, bound, d_counts, c->next_id);
+  // them together with Add_Points(PointNoNeedDownsample, false).  The downsample size is filter_size_map_min, as for
+  // the classification (laserMapping.cpp:748: the same value goes into set_downsample_param).
+  rc = vox_phase_enqueue(c, c->d_add_a, bound, d_counts, c->next_id, fsm);
   if (rc) return rc;
   return map_append_batch_enqueue(c, c->d_add_a, bound, d_counts + 3, c->next_id, nullptr, c->d_batch_flag);
 }
@@ -625,6 +683,7 @@ int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, i
   }
   counts[0] = counts[1] = counts[2] = 0;
   if (c->scan_m <= 0) return LIO_OK;
+  if (const int ri = check_id_space(c, c->scan_m)) return ri;
   LIO_CHECK(c, cudaMemcpyAsync(c->d_x, x, sizeof(lio_state), cudaMemcpyHostToDevice, c->stream));
   int rc = map_incremental_enqueue(c, fsm, ekf_inited, 0, c->scan_m);
   if (rc) return rc;

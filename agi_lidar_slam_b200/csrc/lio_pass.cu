@@ -20,6 +20,8 @@
 // update and each pass inverts one n x n SPD matrix (Gauss-Jordan in shared memory, one element per thread).
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "lio_ctx.cuh"
 #include "lio_knn.cuh"
 
@@ -52,6 +54,8 @@ struct PassArgs {
   float4* near_pts;
   float* near_d2;
   int* near_cnt;
+  float4* near_q;    // the FP32 p_world every row was searched at (its last search pass): what an unbounded completion of
+                     // the row (far_search_kernel) has to use as the query
   uint8_t* selected;
   float4* normvec;
   float4* plane;     // pabcd of the last search pass (the fit depends on the neighbours only)
@@ -201,6 +205,7 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
     const bool sel = (cnt < LIO_K) ? false : (d4 > 5.0f ? false : true);
     s_cnt[row] = sel ? 1 : 0;
     a.near_cnt[i] = cnt;
+    a.near_q[i] = make_float4(pwx, pwy, pwz, 0.f);
   }
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[245] = global_ns();
 }
@@ -1165,6 +1170,63 @@ __global__ void __launch_bounds__(256) knn_batch_kernel(MapView map, const float
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Unbounded completion of neighbour rows (esekfom.hpp:140-141: Nearest_Search gets no max_dist, so the reference's
+// Nearest_Points[i] holds min(5, #live points) neighbours however far away).  near_cnt[i] is the length of the row's
+// KNOWN PREFIX of that list: the bounded search of the update leaves the neighbours within d2 <= 5 (all of them when
+// it found five), far_search_kernel extends the rows listed by far_list_kernel to `need` entries.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void far_list_kernel(const int* near_cnt, const int* scan_m, int m_value, int min_m, int need, int* list,
+                                int* n_list) {
+  int M = m_value >= 0 ? m_value : *scan_m;
+  if (M < min_m) M = 0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool want = i < M && near_cnt[i] < need;
+  const unsigned b = __ballot_sync(0xffffffffu, want);
+  if (b == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(n_list, __popc(b));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (want) list[base + __popc(b & ((1u << lane) - 1u))] = i;
+}
+
+__global__ void __launch_bounds__(256) far_search_kernel(MapView map, const float4* q, const int* list, const int* n_list,
+                                                         int need, float4* near_pts, float* near_d2, int* near_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n = *n_list;
+#pragma unroll 1
+  for (int w = warp; w < n; w += n_warps) {
+    const int i = list[w];
+    const float4 p = __ldg(q + i);
+    unsigned long long key[LIO_K];
+    uint32_t slot[LIO_K];
+    int found = warp_knn_far(map, p.x, p.y, p.z, need, key, slot);
+    if (found > need) found = need;  // only the first `need` entries are the true nearest ones
+    if (lane < LIO_K) {
+      unsigned long long k = key[0];
+      uint32_t sl = slot[0];
+#pragma unroll
+      for (int r = 1; r < LIO_K; ++r)
+        if (lane == r) {
+          k = key[r];
+          sl = slot[r];
+        }
+      float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      float d = CUDART_INF_F;
+      if (lane < found) {
+        v = __ldg(map.pool + sl);
+        d = __uint_as_float((uint32_t)(k >> 32));
+      }
+      near_pts[(size_t)i * LIO_K + lane] = v;
+      near_d2[(size_t)i * LIO_K + lane] = d;
+    }
+    if (lane == 0) near_cnt[i] = found;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------
 static bool g_tables_ready[64] = {false};
@@ -1243,6 +1305,7 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.near_pts = c->d_near;
   a.near_d2 = c->d_near_d2;
   a.near_cnt = c->d_near_cnt;
+  a.near_q = c->d_near_q;
   a.selected = c->d_selected;
   a.normvec = c->d_normvec;
   a.plane = c->d_plane;
@@ -1389,6 +1452,23 @@ int launch_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot)
   LIO_CHECK(c, cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
   begin_kernel<<<1, THREADS, 0, c->stream>>>(s, extrinsic_est);
   c->launches++;
+  LIO_CHECK(c, cudaGetLastError());
+  return LIO_OK;
+}
+
+// Extends the rows of the neighbour cache (c->d_near*) whose known prefix is shorter than `need` (1 ... 5) to `need`
+// entries of the UNBOUNDED nearest-neighbour list of their query q[i].  m >= 0: exact row count; m < 0: the device-side
+// scan size (a scan of fewer than min_m points counts as empty), `bound` rows at most.  Enqueue only.
+int launch_far_complete(lio_ctx* c, const float4* d_q, int64_t m, int min_m, int64_t bound, int need) {
+  if (bound <= 0) return LIO_OK;
+  LIO_CHECK(c, cudaMemsetAsync(c->d_far_n, 0, sizeof(int), c->stream));
+  far_list_kernel<<<(int)((bound + 255) / 256), 256, 0, c->stream>>>(c->d_near_cnt, c->d_scan_m, m >= 0 ? (int)m : -1,
+                                                                      m >= 0 ? 0 : min_m, need, c->d_far_list,
+                                                                      c->d_far_n);
+  const int grid = (int)std::min<int64_t>((bound + 7) / 8, (int64_t)c->sm_count * 8);
+  far_search_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_q, c->d_far_list, c->d_far_n, need, c->d_near, c->d_near_d2,
+                                                 c->d_near_cnt);
+  c->launches += 2;
   LIO_CHECK(c, cudaGetLastError());
   return LIO_OK;
 }

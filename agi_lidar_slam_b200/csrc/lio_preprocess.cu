@@ -49,8 +49,11 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
     float ox = r.x, oy = r.y, oz = r.z;
     if (a.n_poses >= 2) {
       const double t = (double)r.w / double(1000);
-      // head = last pose with offset_time < t among poses[0 .. n_poses-2]  (:361-373)
-      int lo = 0, hi = a.n_poses - 2, head = -1;
+      // head = last pose with offset_time < t among poses[0 .. n_poses-2]: the first segment the reference's walk from the
+      // back (:361-398) compensates the point with.  poses[1 ..] carry IMU stamps and ascend; poses[0] is the previous
+      // scan end with offset_time hard-coded to 0.0 (:273-276) and may exceed poses[1] when an IMU sample falls between
+      // the two scans (A.9) -- so the search runs over [1, n-2] and falls back to 0.
+      int lo = 1, hi = a.n_poses - 2, head = -1;
       while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
         if (s_pose[mid].offset_time < t) {
@@ -60,6 +63,7 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
           hi = mid - 1;
         }
       }
+      if (head < 0 && s_pose[0].offset_time < t) head = 0;
       if (head >= 0) {
         const lio_pose6d& H = s_pose[head];
         const lio_pose6d& T = s_pose[head + 1];

@@ -257,8 +257,17 @@ int lio_seq_process(lio_seq* s, const lio_seq_input* in, lio_seq_result* res) {
 
 int lio_seq_process_many(lio_seq* const* seqs, int n_seq, const lio_seq_input* in, lio_seq_result* res) {
   if (!seqs || n_seq < 1 || n_seq > 64 || !in || !res) return LIO_E_INVALID;
-  for (int k = 0; k < n_seq; ++k)
+  for (int k = 0; k < n_seq; ++k) {
     if (!seqs[k] || in[k].n < 0 || in[k].n_imu < 0 || (in[k].n_imu > 0 && !in[k].imu)) return LIO_E_INVALID;
+    // one context per sequence (a context is not re-entrant, and the host stages below run concurrently), and one set
+    // of filter settings for the shared update launch
+    for (int j = 0; j < k; ++j)
+      if (seqs[j] == seqs[k] || seqs[j]->ctx == seqs[k]->ctx) return LIO_E_INVALID;
+    const lio_seq_config &a = seqs[0]->cfg, &b = seqs[k]->cfg;
+    if (a.max_iteration != b.max_iteration || a.extrinsic_est != b.extrinsic_est ||
+        a.laser_point_cov != b.laser_point_cov)
+      return LIO_E_INVALID;
+  }
   lio_seq* begun[64];
   lio_ctx* due[64];
   int idx_of[64], n_begun = 0, n_due = 0;

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LIO_ABI_VERSION 1
+#define LIO_ABI_VERSION 2
 #define LIO_NUM_MATCH_POINTS 5 /* common_lib.h:18 */
 
 enum {
@@ -104,6 +104,10 @@ int lio_map_build(lio_ctx* ctx, const void* pts, int64_t n, int stride_bytes);
  * of its sequential loop, re-insertions of surviving old points included; it is only printed).  New point i gets
  * id = next_id + i. */
 int lio_map_add(lio_ctx* ctx, const void* pts, int64_t n, int stride_bytes, int downsample_on, int32_t* n_added);
+/* ≙ KD_TREE::set_downsample_param (ikd_Tree.h:274; laserMapping.cpp:748): the voxel edge lio_map_add downsamples with
+ * (initially caps.map_downsample).  Any size > 0; it need not divide the kNN cell.  lio_map_incremental / lio_scan_step
+ * downsample with their own filter_size_map argument, the one value the reference uses for both (laserMapping.cpp:748). */
+int lio_map_set_downsample(lio_ctx* ctx, float downsample_size);
 /* ≙ KD_TREE::Delete_Point_Boxes (ikd_Tree.cpp:559-579; laserMapping.cpp:361-364). boxes6 = nb x {min xyz, max xyz}, half-open. */
 int lio_map_delete_boxes(lio_ctx* ctx, const float* boxes6, int nb, int32_t* n_deleted);
 /* ≙ KD_TREE::size() / validnum() (ikd_Tree.cpp:66-128): total = slots ever used, valid = live points. */
@@ -111,10 +115,13 @@ int lio_map_size(lio_ctx* ctx, int64_t* total, int64_t* valid);
 /* ≙ KD_TREE::flatten(Root_Node, PCL_Storage, NOT_RECORD) (ikd_Tree.cpp:1490-1516): live points, ascending id.
  * xyz (cap x 3) and ids (cap) may be NULL; *n = live count. */
 int lio_map_dump(lio_ctx* ctx, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
-/* ≙ a batch of KD_TREE::Nearest_Search(point, 5, ...) (ikd_Tree.cpp:370-402; esekfom.hpp:140) bounded at
- * d2 <= caps.knn_max_d2.  q_xyz: m x 3 world-frame points.  Outputs (each may be NULL), per query ascending by
- * (d2 FP32, id): idx5 m x 5 point ids (-1 pad), d2_5 m x 5 (+inf pad), nbr_xyz m x 5 x 3. */
-int lio_knn5(lio_ctx* ctx, const float* q_xyz, int64_t m, int32_t* idx5, float* d2_5, float* nbr_xyz);
+/* ≙ a batch of KD_TREE::Nearest_Search(point, 5, Nearest_Points, Point_Distance, max_dist) (ikd_Tree.cpp:370-402;
+ * esekfom.hpp:140).  max_d2 = max_dist * max_dist, as the tree squares it (ikd_Tree.cpp:965) and tests `dist <= max_d2`
+ * (:980); INFINITY is the reference's default (ikd_Tree.h:285) and what esekfom.hpp:140-141 gets.  Up to
+ * caps.knn_max_d2 the call is one launch of the hot group search; beyond it the rows that search leaves short are
+ * completed by the unbounded shell search (exact; slower).  q_xyz: m x 3 world-frame points.  Outputs (each may be
+ * NULL), per query ascending by (d2 FP32, id): idx5 m x 5 point ids (-1 pad), d2_5 m x 5 (+inf pad), nbr_xyz m x 5 x 3. */
+int lio_knn5(lio_ctx* ctx, const float* q_xyz, int64_t m, float max_d2, int32_t* idx5, float* d2_5, float* nbr_xyz);
 
 /* Instrumentation: re-runs the search kernel on the (at most max_down_points) queries the last lio_knn5 call left on
  * the device; no copies, no synchronisation (tools/knn_roofline.py brackets it with CUDA events). */
@@ -286,13 +293,20 @@ int lio_blob_download(lio_ctx* ctx, double blob92[92]);
 
 /* ≙ the global Nearest_Points the update fills (esekfom.hpp:136; laserMapping.cpp:62,771) plus the per-point
  * intermediates of the last pass.  All outputs optional (NULL): idx5 m x 5, d2_5 m x 5, nbr_xyz m x 5 x 3,
- * world_xyz m x 3 (FP32 p_world), selected m (point_selected_surf), normvec m x 4 (a,b,c,pd2). */
+ * world_xyz m x 3 (FP32 p_world), selected m (point_selected_surf), normvec m x 4 (a,b,c,pd2).
+ * The neighbour rows are the reference's: Nearest_Search is called WITHOUT a distance bound (esekfom.hpp:140-141), so a
+ * row holds min(5, live map points) neighbours of the point's last search pass however far away they are.  The update
+ * itself only searches within d2 <= caps.knn_max_d2 (its gate, esekfom.hpp:144-147, needs no more); asking for the rows
+ * here completes the short ones with the unbounded search first (one extra pass over those rows only). */
 int lio_get_neighbors(lio_ctx* ctx, int32_t* idx5, float* d2_5, float* nbr_xyz, float* world_xyz, uint8_t* selected,
                       float* normvec);
 
 /* ---- map maintenance: map_incremental (src/laserMapping.cpp:382-433) ----------------------------------- */
 /* Classifies the current scan with the cached neighbours at state x and performs both Add_Points calls
- * (:430-431).  counts[0] = |PointToAdd|, counts[1] = |PointNoNeedDownsample|, counts[2] = added by the first call. */
+ * (:430-431).  counts[0] = |PointToAdd|, counts[1] = |PointNoNeedDownsample|, counts[2] = added by the first call.
+ * The classification is the reference's on its unbounded Nearest_Points: rows without a neighbour within
+ * sqrt(caps.knn_max_d2) get their nearest map point from the unbounded search first (points_near[0] decides
+ * PointNoNeedDownsample, :408-414).  filter_size_map is also the downsample size of the first Add_Points call. */
 int lio_map_incremental(lio_ctx* ctx, const lio_state* x, float filter_size_map, int ekf_inited, int32_t counts[3]);
 
 /* ≙ the first-scan branch of the main loop (laserMapping.cpp:747-758): every point of the current scan goes through

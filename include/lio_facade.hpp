@@ -60,7 +60,10 @@ class KD_TREE {
   explicit KD_TREE(std::shared_ptr<Context> ctx, float = 0.5f, float = 0.6f, float = 0.2f) : ctx_(std::move(ctx)) {}
   void Set_delete_criterion_param(float) {}   // a hash map has no balance / lazy-delete criteria
   void Set_balance_criterion_param(float) {}
-  void set_downsample_param(float downsample_param) { downsample_size = downsample_param; }
+  void set_downsample_param(float downsample_param) {
+    downsample_size = downsample_param;
+    last_error = lio_map_set_downsample(ctx_->get(), downsample_param);
+  }
   void InitializeKDTree(float = 0.5f, float = 0.7f, float = 0.2f) {}
 
   int size() {
@@ -78,8 +81,8 @@ class KD_TREE {
     last_error = lio_map_build(ctx_->get(), point_cloud.data(), (int64_t)point_cloud.size(), (int)sizeof(PointType));
     Root_Node = (last_error == LIO_OK && !point_cloud.empty()) ? &root_token_ : nullptr;
   }
-  // ikd_Tree.cpp:370-402.  Only k_nearest <= 5 within sqrt(lio_caps.knn_max_d2) is served (what the path asks for);
-  // outputs ascending by distance; fewer than k results on a small / far map, exactly as the reference.
+  // ikd_Tree.cpp:370-402.  k_nearest <= 5 is served (NUM_MATCH_POINTS, what the path asks for); outputs ascending by
+  // distance; fewer than k results only where the map holds fewer points within max_dist, exactly as the reference.
   void Nearest_Search(PointType point, int k_nearest, PointVector& Nearest_Points, std::vector<float>& Point_Distance,
                       float max_dist = INFINITY) {
     PointVector().swap(Nearest_Points);
@@ -87,10 +90,10 @@ class KD_TREE {
     const float* q = reinterpret_cast<const float*>(&point);
     int32_t idx[5];
     float d2[5], xyz[15];
-    last_error = lio_knn5(ctx_->get(), q, 1, idx, d2, xyz);
+    last_error = lio_knn5(ctx_->get(), q, 1, max_dist * max_dist, idx, d2, xyz);  // ikd_Tree.cpp:965
     if (last_error != LIO_OK) return;
     for (int r = 0; r < 5 && r < k_nearest; ++r) {
-      if (idx[r] < 0 || d2[r] > max_dist * max_dist) break;
+      if (idx[r] < 0) break;
       PointType p;
       std::memset(&p, 0, sizeof(p));
       std::memcpy(&p, xyz + 3 * r, 12);
@@ -181,8 +184,9 @@ class esekf {
   }
   // The reference's own argument list (esekfom.hpp:270-275): feats_down_body is anything that points at an object with a
   // `points` vector (PointCloudXYZI::Ptr qualifies), Nearest_Points comes back filled as the reference leaves it -- the
-  // neighbours of the last SEARCH pass, ascending by distance, fewer than 5 where the map had fewer within range -- for
-  // host code that still runs map_incremental (laserMapping.cpp:382-433) itself.
+  // neighbours of the last SEARCH pass from an UNBOUNDED search (esekfom.hpp:140-141), ascending by distance, five per
+  // point wherever the map holds five points -- for host code that still runs map_incremental
+  // (laserMapping.cpp:382-433) itself.
   template <typename CloudPtr, typename PointType, typename Alloc>
   void update_iterated_dyn_share_modified(double R, CloudPtr& feats_down_body, KD_TREE<PointType, Alloc>& ikdtree,
                                           std::vector<std::vector<PointType, Alloc>>& Nearest_Points, int maximum_iter,

@@ -687,6 +687,7 @@ struct Map {
   int32_t next_id = 0;
   int64_t n_live = 0;
   std::unordered_map<CellKey, std::vector<MapPoint>, CellHash> cells;
+  int32_t lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};  // cells ever used
   explicit Map(float c) : cell(c), inv_cell(1.0f / c) {}
   CellKey key_of(float x, float y, float z) const {
     return CellKey{(int32_t)std::floor(x * inv_cell), (int32_t)std::floor(y * inv_cell),
@@ -696,9 +697,19 @@ struct Map {
     cells.clear();
     next_id = 0;
     n_live = 0;
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = INT32_MAX;
+      hi[a] = INT32_MIN;
+    }
   }
   void insert(float x, float y, float z, int32_t id) {
-    cells[key_of(x, y, z)].push_back(MapPoint{x, y, z, id});
+    const CellKey k = key_of(x, y, z);
+    const int32_t kk[3] = {k.x, k.y, k.z};
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = std::min(lo[a], kk[a]);
+      hi[a] = std::max(hi[a], kk[a]);
+    }
+    cells[k].push_back(MapPoint{x, y, z, id});
     ++n_live;
   }
   void build(const float* xyz, int64_t n) {
@@ -707,7 +718,9 @@ struct Map {
     next_id = (int32_t)n;
   }
   // Exact k-NN among points with d2 <= max_d2 (the reference's `dist <= max_dist_sqr`, ikd_Tree.cpp:980),
-  // canonical order.  Returns count found (<= k).
+  // canonical order.  max_d2 = INFINITY is the reference's default (ikd_Tree.h:285; what esekfom.hpp:140 gets): the
+  // shells then grow until the k-th best beats them or every cell ever used has been visited.
+  // Returns count found (<= k).
   int knn(const float q[3], int k, float max_d2, MapPoint* out, float* out_d2) const {
     struct Cand {
       float d2;
@@ -716,29 +729,56 @@ struct Map {
     };
     std::vector<Cand> best;  // kept sorted, size <= k
     const CellKey c = key_of(q[0], q[1], q[2]);
-    const int rmax = (int)std::ceil(std::sqrt((double)max_d2) * (double)inv_cell) + 1;
-    for (int r = 0; r <= rmax; ++r) {
+    int rmax = 0, r0 = 0;
+    const int32_t cc[3] = {c.x, c.y, c.z};
+    for (int a = 0; a < 3; ++a)
+      if (lo[a] <= hi[a]) {
+        rmax = std::max(rmax, std::max(std::abs(cc[a] - lo[a]), std::abs(cc[a] - hi[a])));  // farthest used cell
+        r0 = std::max(r0, std::max(lo[a] - cc[a], cc[a] - hi[a]));                          // nearest used cell
+      }
+    if (!std::isinf(max_d2)) rmax = std::min(rmax, (int)std::ceil(std::sqrt((double)max_d2) * (double)inv_cell) + 1);
+    auto visit = [&](int dx, int dy, int dz) {
+      const CellKey ck{c.x + dx, c.y + dy, c.z + dz};
+      if (ck.x < lo[0] || ck.x > hi[0] || ck.y < lo[1] || ck.y > hi[1] || ck.z < lo[2] || ck.z > hi[2]) return;
+      auto it = cells.find(ck);
+      if (it == cells.end()) return;
+      for (const MapPoint& p : it->second) {
+        const float d2 = dist2_f(q[0], q[1], q[2], p.x, p.y, p.z);
+        if (!(d2 <= max_d2)) continue;
+        Cand cd{d2, p.id, p};
+        auto less = [](const Cand& a, const Cand& b) { return a.d2 < b.d2 || (a.d2 == b.d2 && a.id < b.id); };
+        if ((int)best.size() == k && !less(cd, best.back())) continue;
+        best.insert(std::upper_bound(best.begin(), best.end(), cd, less), cd);
+        if ((int)best.size() > k) best.pop_back();
+      }
+    };
+    if (std::isinf(max_d2) && r0 > 64) {
+      // query far outside everything the map holds: walking empty shells would cost more than looking at every cell
+      for (const auto& kv : cells) visit(kv.first.x - c.x, kv.first.y - c.y, kv.first.z - c.z);
+      rmax = -1;
+    }
+    for (int r = r0; r <= rmax; ++r) {
       // shell r can only hold points at distance >= (r-1)*cell from q; stop once the k-th best beats it
       if (r >= 1 && (int)best.size() == k) {
         const double cover = (double)(r - 1) * (double)cell;
         if ((double)best.back().d2 < cover * cover) break;
       }
-      for (int dz = -r; dz <= r; ++dz)
-        for (int dy = -r; dy <= r; ++dy)
+      // the cells at Chebyshev distance exactly r: two full faces, and the perimeter of every layer between them
+      for (int dz = -r; dz <= r; ++dz) {
+        if (dz == -r || dz == r) {
+          for (int dy = -r; dy <= r; ++dy)
+            for (int dx = -r; dx <= r; ++dx) visit(dx, dy, dz);
+        } else {
           for (int dx = -r; dx <= r; ++dx) {
-            if (std::max(std::abs(dx), std::max(std::abs(dy), std::abs(dz))) != r) continue;
-            auto it = cells.find(CellKey{c.x + dx, c.y + dy, c.z + dz});
-            if (it == cells.end()) continue;
-            for (const MapPoint& p : it->second) {
-              const float d2 = dist2_f(q[0], q[1], q[2], p.x, p.y, p.z);
-              if (!(d2 <= max_d2)) continue;
-              Cand cd{d2, p.id, p};
-              auto less = [](const Cand& a, const Cand& b) { return a.d2 < b.d2 || (a.d2 == b.d2 && a.id < b.id); };
-              if ((int)best.size() == k && !less(cd, best.back())) continue;
-              best.insert(std::upper_bound(best.begin(), best.end(), cd, less), cd);
-              if ((int)best.size() > k) best.pop_back();
-            }
+            visit(dx, -r, dz);
+            visit(dx, r, dz);
           }
+          for (int dy = -r + 1; dy <= r - 1; ++dy) {
+            visit(-r, dy, dz);
+            visit(r, dy, dz);
+          }
+        }
+      }
     }
     for (size_t i = 0; i < best.size(); ++i) {
       out[i] = best[i].p;
@@ -940,7 +980,7 @@ struct Scan {
 };
 
 struct Params {
-  float max_d2 = 5.0f;        // esekfom.hpp:147
+  float max_d2 = INFINITY;    // Nearest_Search's max_dist: esekfom.hpp:140-141 passes none => ikd_Tree.h:285 default
   float plane_thr = 0.1f;     // esekfom.hpp:157
   int k = 5;                  // NUM_MATCH_POINTS
   int threads = 1;            // MP_PROC_NUM
@@ -972,8 +1012,8 @@ static bool h_share_model(const State& x, Scan& s, bool converge, bool extrinsic
         std::memcpy(&np[4 * j + 3], &neg, 4);
         nd[j] = INFINITY;
       }
-      // The reference searches with max_dist = INFINITY and then requires d2[4] <= 5; a search bounded
-      // at d2 <= 5 returns 5 points exactly when that gate passes (see DESIGN.md "bounded search").
+      // esekfom.hpp:140-141: no max_dist argument, so Nearest_Points[i] holds min(5, #live map points) neighbours
+      // however far away they are; map_incremental reads them later (laserMapping.cpp:391-423) whatever gate 1 says.
       const int cnt = knn(knn_ctx, pw, K, prm.max_d2, np, nd);
       s.near_cnt[i] = cnt;
       s.selected[i] = (cnt < K) ? 0 : (nd[K - 1] > 5 ? 0 : 1);

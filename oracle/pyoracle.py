@@ -317,6 +317,7 @@ class Map:
         return xyz, ids
 
     def knn(self, q, k=5, max_d2=5.0, threads=1):
+        """max_d2 = np.inf: the reference's unbounded Nearest_Search (ikd_Tree.h:285)."""
         q = np.ascontiguousarray(q, np.float32).reshape(-1, 3)
         m = q.shape[0]
         idx = np.zeros((m, k), np.int32)
@@ -383,6 +384,56 @@ class IkdTree:
 
     def knn_backend(self):
         return ikd().ikd_knn_callback(), self.h
+
+
+class IkdLiveMap:
+    """The REFERENCE ikd-Tree as the live map of a whole replay (Build at laserMapping.cpp:747-758, unbounded
+    Nearest_Search at esekfom.hpp:140, both Add_Points calls of laserMapping.cpp:430-431, Delete_Point_Boxes at :361-364)
+    behind the interface of `Map`.  Points carry an id (in normal_x, which the tree copies through verbatim) handed out
+    as the product and the Map port hand them out: input index of Build, then next_id + batch index."""
+
+    def __init__(self, downsample=0.5):
+        self.tree = IkdTree()
+        self.tree.set_downsample_param(downsample)  # laserMapping.cpp:748
+        self.next_id = 0
+
+    def build(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        self.tree.build(xyz, np.arange(len(xyz), dtype=np.int32))
+        self.next_id = len(xyz)
+
+    def add(self, xyz, downsample_on, ds=0.5):
+        """Returns the number of NEW points that are in the map afterwards (the tree's own return value counts the
+        insert operations of its sequential loop instead; the reference only prints it)."""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        n = len(xyz)
+        if n == 0:
+            return 0
+        ids = np.arange(self.next_id, self.next_id + n, dtype=np.int32)
+        self.tree.add_points(xyz, downsample_on, ids)
+        base = self.next_id
+        self.next_id += n
+        if not downsample_on:
+            return n
+        return int((self.tree.flatten()[1] >= base).sum())
+
+    def delete_boxes(self, boxes6):
+        return self.tree.delete_boxes(boxes6)
+
+    def size(self):
+        return self.tree.validnum()
+
+    def dump(self):
+        xyz, ids = self.tree.flatten()
+        o = np.argsort(ids, kind="stable")
+        return xyz[o], ids[o]
+
+    def knn(self, q, k=5, max_d2=np.inf, threads=1):
+        idx, d2, nbr = self.tree.knn(q, k, np.inf, threads)
+        return idx, d2, nbr
+
+    def knn_backend(self):
+        return self.tree.knn_backend()
 
 
 # --------------------------------------------------------------------------- h_share_model / update

@@ -99,7 +99,9 @@ class OracleReplay:
             return None
         if self.map is None:
             world = orc.body_to_world(self.x, body)
-            self.map = orc.Map(1.0)
+            # use_ikd: the reference's own ikd-Tree is the live map (Build / unbounded Nearest_Search / Add_Points /
+            # Delete_Point_Boxes), not the hashed-grid port
+            self.map = orc.IkdLiveMap(self.fm) if self.use_ikd else orc.Map(1.0)
             self.map.build(world)
             self.log.append(dict(status="map-built", m=len(body)))
             return None
@@ -111,6 +113,8 @@ class OracleReplay:
         cls = orc.map_incremental_classify(world, ref["near_raw"], ref["cnt"], ekf_inited, self.fm)
         na = self.map.add(world[cls == 1], True, self.fm)
         self.map.add(world[cls == 2], False)
+        self.last = dict(cls=cls, cnt=ref["cnt"].copy(), d2=ref["d2"].copy(), world=world, near_raw=ref["near_raw"].copy(),
+                         idx=ref["idx"].copy(), body=body)
         self.log.append(dict(status="ok", m=len(body), n_valid=nv, n_passes=len(trace),
                              counts=[int((cls == 1).sum()), int((cls == 2).sum()), int(na)]))
         return self.x.copy()

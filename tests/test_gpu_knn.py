@@ -90,3 +90,56 @@ def test_sparse_map_needs_ring_expansion(ctx, orc):
     assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
     far = np.isfinite(d2[:, 4]) & (d2[:, 4] > 1.0)
     assert far.sum() > 100
+
+
+def _p4(xyz):
+    return np.concatenate([xyz, np.zeros((len(xyz), 1), np.float32)], 1)
+
+
+def test_knn5_unbounded_matches_reference_tree(ctx, orc, small_cfg):
+    """Nearest_Search with its default max_dist = INFINITY (ikd_Tree.h:285; what esekfom.hpp:140-141 gets): five
+    neighbours for every query however far from the map, bit-equal to the reference's own tree."""
+    if not orc.ikd_available():
+        pytest.skip("oracle/_ref/libikd_ref.so not present")
+    mp = small_cfg["map"]
+    ctx.map_build(_p4(mp))
+    tree = orc.IkdTree()
+    tree.build(mp)
+    rng = np.random.default_rng(5)
+    lo, hi = mp.min(0), mp.max(0)
+    q = np.concatenate([
+        rng.uniform(lo - 30, hi + 30, (3000, 3)),           # around and outside the map
+        rng.uniform(lo, hi, (1000, 3)) + [0, 0, 40.0],       # high above it
+        mp[rng.integers(0, len(mp), 500)] + rng.normal(0, 0.3, (500, 3)),
+        np.array([[900.0, -700.0, 300.0], [1e4, -2e4, 3e3]]),  # hundreds of cells away: the box-sweep path
+    ]).astype(np.float32)
+    gi, gd, gx = ctx.knn5(q, max_d2=np.inf)
+    ti, td, tx = tree.knn(q, 5, np.inf, threads=4)
+    assert np.all(gi >= 0) and np.all(np.isfinite(gd))
+    assert np.array_equal(gd.view(np.uint32), td.view(np.uint32))
+    same = gi == ti
+    assert same.mean() > 0.999  # the tree's order among exactly equal distances is traversal-dependent
+    assert np.array_equal(gx[same].view(np.uint32), tx[same].view(np.uint32))
+    # an intermediate bound: the prefix of the unbounded list, cut with `dist <= max_dist^2` (ikd_Tree.cpp:980)
+    bi, bd, _ = ctx.knn5(q, max_d2=40.0)
+    inside = gd <= 40.0
+    assert np.array_equal(bi[inside], gi[inside]) and np.all(bi[~inside] == -1) and np.all(np.isinf(bd[~inside]))
+    # after a box delete the cell box of the map does not shrink; the search must still be exact
+    box = np.array([[lo[0] - 1, lo[1] - 1, lo[2] - 1, (lo[0] + hi[0]) / 2, hi[1] + 1, hi[2] + 1]], np.float32)
+    assert ctx.map_delete_boxes(box) == tree.delete_boxes(box) > 0
+    gi, gd, _ = ctx.knn5(q, max_d2=np.inf)
+    ti, td, _ = tree.knn(q, 5, np.inf, threads=4)
+    assert np.array_equal(gd.view(np.uint32), td.view(np.uint32)) and (gi == ti).mean() > 0.999
+
+
+def test_knn5_unbounded_tiny_map(ctx, orc):
+    """Fewer than five live points: the reference returns what there is, so does the unbounded search."""
+    mp = np.array([[0, 0, 0], [10, 0, 0], [0, 30, 1]], np.float32)
+    ctx.map_build(_p4(mp))
+    q = np.array([[1, 1, 1], [100, 100, 100], [-50, 3, 0]], np.float32)
+    gi, gd, _ = ctx.knn5(q, max_d2=np.inf)
+    om = orc.Map(1.0)
+    om.build(mp)
+    oi, od, _ = om.knn(q, 5, np.inf)
+    assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    assert np.all(gi[:, :3] >= 0) and np.all(gi[:, 3:] == -1)

@@ -113,3 +113,57 @@ def test_map_incremental_matches_oracle(ctx, orc, small_cfg):
     counts = ctx.map_incremental(xr, 0.5, True)  # same state on both sides: stage-wise comparison
     assert counts.tolist() == [int((cls == 1).sum()), int((cls == 2).sum()), na]
     _same_map(ctx, om)
+
+
+@pytest.mark.parametrize("ds", [0.2, 0.4, 0.75])
+def test_add_points_any_downsample_size_equals_reference_tree(ctx, orc, ds):
+    """set_downsample_param with a voxel that does not divide the 1.5 m kNN cell: the survivors are the
+    reference tree's, every one of them filed where the searches look for it (kNN against the tree afterwards)."""
+    if not orc.ikd_available():
+        pytest.skip("oracle/_ref/libikd_ref.so not present")
+    rng = np.random.default_rng(11)
+    sc = np.array([1, 1, 0.15], np.float32)
+    base = rng.uniform(-9, 9, (6000, 3)).astype(np.float32) * sc
+    ctx.map_set_downsample(ds)
+    ctx.map_build(_p4(base))
+    ref = orc.IkdLiveMap(ds)
+    ref.build(base)
+    for it in range(5):
+        new = rng.uniform(-10, 10, (5000, 3)).astype(np.float32) * sc
+        a = ctx.map_add(_p4(new), True)
+        b = ref.add(new, True, ds)
+        assert a == b, (it, a, b)
+        gx, gi = ctx.map_dump()
+        rx, ri = ref.dump()
+        assert np.array_equal(gi, ri) and np.array_equal(gx.view(np.uint32), rx.view(np.uint32)), it
+        q = rng.uniform(-11, 11, (4000, 3)).astype(np.float32) * sc
+        idx, d2, _ = ctx.knn5(q, max_d2=np.inf)
+        ti, td, _ = ref.knn(q, 5)
+        assert np.array_equal(d2.view(np.uint32), td.view(np.uint32)) and (idx == ti).mean() > 0.999, it
+
+
+def test_map_incremental_large_filter_size(ctx, orc, small_cfg):
+    """filter_size_map so large (3 fs^2 > 5) that neighbours beyond sqrt(5) m can decide need_add: the rows are
+    completed to the reference's five unbounded neighbours before the classification."""
+    cfg = small_cfg
+    mp = cfg["map"][::6]  # thin map: most rows are short after the bounded search
+    ctx.map_build(_p4(mp))
+    om = orc.Map(1.0)
+    om.build(mp)
+    s = cfg["scan"]
+    pts5 = np.concatenate([s[:, :3], np.zeros((len(s), 1), np.float32), s[:, 3:4]], 1)
+    body = np.ascontiguousarray(orc.voxel_grid(pts5, 0.5)[0][:, :4])
+    ctx.scan_upload(body)
+    ctx.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, False)
+    sc = orc.Scan(body[:, :3])
+    xr, Pr, trace, _ = sc.update(cfg["x_prior"], cfg["P"], om.knn_backend(), 0.001, 4, False, threads=8)
+    ref = sc.get()
+    assert (ref["d2"][:, 4] > 5).mean() > 0.05
+    world = orc.body_to_world(xr, body[:, :3])
+    for fs in (1.5, 2.0):
+        cls = orc.map_incremental_classify(world, ref["near_raw"], ref["cnt"], True, fs)
+        na = om.add(world[cls == 1], True, fs)
+        om.add(world[cls == 2], False)
+        counts = ctx.map_incremental(xr, fs, True)
+        assert counts.tolist() == [int((cls == 1).sum()), int((cls == 2).sum()), na], fs
+        _same_map(ctx, om)

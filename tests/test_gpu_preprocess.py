@@ -133,3 +133,22 @@ def test_long_runs_bit_exact(ctx, orc):
     assert np.array_equal(keys, pkeys) and len(out) == len(cen)
     assert np.array_equal(out[:, :3].view(np.uint32), cen[:, :3].view(np.uint32))
     assert np.array_equal(out[:, 8], cen[:, 3]) and np.array_equal(out[:, 9], cen[:, 4])
+
+
+def test_undistort_imu_sample_before_scan_begin(ctx, orc, small_cfg):
+    """IMUpose[1].offset_time < 0 (an IMU sample between the previous scan end and this scan's begin) while
+    IMUpose[0].offset_time is hard-coded to 0.0: the reference's walk from the back compensates a point at t = 0 with
+    the segment (1, 2); the segment lookup must not assume that the offsets ascend from index 0."""
+    poses, x_end = _motion(orc)
+    poses = poses.copy()
+    assert poses[0, 0] == 0.0 and poses[1, 0] > 0
+    poses[1, 0] = -0.002
+    raw = small_cfg["scan"].copy()
+    raw[:, 3] = np.linspace(0, 99.9, len(raw)).astype(np.float32)
+    raw[:50, 3] = 0.0  # several points at t = 0
+    ref_sorted, order = orc.undistort(raw, poses, x_end)
+    ref = np.zeros_like(ref_sorted)
+    ref[order] = ref_sorted
+    assert np.abs(ref[:50, :3] - raw[:50, :3]).max() > 1e-4  # the reference does compensate them
+    _, und, _ = ctx.scan_preprocess(raw, poses, x_end, 0.5, want_undistorted=True)
+    assert np.abs(und[:, :3] - ref[:, :3]).max() <= 1e-5 * np.abs(ref[:, :3]).max()

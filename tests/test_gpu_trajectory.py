@@ -22,33 +22,50 @@ def _p4(xyz):
     return np.concatenate([xyz, np.zeros((len(xyz), 1), np.float32)], 1)
 
 
-@pytest.mark.parametrize("name,n_scans,seed,rings,cols,fov,max_range,cube_len,det_range", [
-    ("config 2 (VLP-16, 200 scans)", N_SCANS, 2002, 16, 1800, (-15.0, 15.0), 100.0, 1000.0, 300.0),
-    ("config 4 shape (OS1-64, one of the 64 sequences, 40 scans)", 40, 4000, 64, 1024, (-22.5, 22.5), 120.0, 1000.0, 300.0),
+@pytest.mark.parametrize("name,n_scans,seed,rings,cols,fov,max_range,cube_len,det_range,extent,ref_tree", [
+    ("config 2 (VLP-16, 200 scans)", N_SCANS, 2002, 16, 1800, (-15.0, 15.0), 100.0, 1000.0, 300.0, 120.0, False),
+    ("config 4 shape (OS1-64, one of the 64 sequences, 40 scans)", 40, 4000, 64, 1024, (-22.5, 22.5), 120.0, 1000.0, 300.0,
+     120.0, False),
     # a 40 m local-map cube: lasermap_fov_segment slides it and box-deletes the map behind the sensor
-    ("moving local map (VLP-16, 80 scans, cube 40 m)", 80, 2002, 16, 1800, (-15.0, 15.0), 100.0, 40.0, 10.0),
+    ("moving local map (VLP-16, 80 scans, cube 40 m)", 80, 2002, 16, 1800, (-15.0, 15.0), 100.0, 40.0, 10.0, 120.0, False),
+    # sparse scene, and the checker's live map is the REFERENCE ikd-Tree (Build / unbounded Nearest_Search / Add_Points):
+    # ~6 % of the points fail gate 1 and map_incremental classifies them from neighbours beyond sqrt(5) m
+    # (tests/test_oracle_reference_map.py is the CPU twin of this case)
+    ("sparse 240 m yard on the reference ikd-Tree (36 scans)", 36, 2002, 16, 900, (-15.0, 15.0), 200.0, 1000.0, 300.0, 240.0,
+     True),
 ])
-def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_range, cube_len, det_range):
+def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_range, cube_len, det_range, extent,
+                                ref_tree):
     from agi_lidar_slam_b200 import _cabi, synth
     from agi_lidar_slam_b200.replay import MeasureGroup, NativeReplay as LioReplay, ReplayConfig
     from replay_oracle import OracleReplay
 
+    if ref_tree and not orc.ikd_available():
+        pytest.skip("oracle/_ref/libikd_ref.so not present")
     N_SCANS = n_scans
-    seq = synth.sequence(n_scans, seed, rings=rings, cols=cols, fov=fov, max_range=max_range)  # 10 Hz, IMU 200 Hz
+    seq = synth.sequence(n_scans, seed, rings=rings, cols=cols, fov=fov, max_range=max_range,
+                         scene=synth.block_scene(extent=extent))  # 10 Hz, IMU 200 Hz
     traj = synth.RampedTrajectory(synth.Trajectory())
     R0, p0 = traj.rot(0.0), traj.pos(0.0)
-    with _cabi.Context(0, max_scan_points=1 << 17, max_down_points=1 << 16, max_map_points=1 << 21) as ctx:
+    with _cabi.Context(0, max_scan_points=1 << 17, max_down_points=1 << 16, max_map_points=1 << 21) as ctx, \
+            _cabi.Context(0, max_scan_points=1 << 17, max_down_points=1 << 16, max_map_points=1 << 21) as ctx_free:
         gpu = LioReplay(ctx, ReplayConfig(max_iteration=3, cube_len=cube_len, det_range=det_range))
-        cpu = OracleReplay(orc, max_iteration=3, cube_len=cube_len, det_range=det_range)
+        free = LioReplay(ctx_free, ReplayConfig(max_iteration=3, cube_len=cube_len, det_range=det_range))
+        cpu = OracleReplay(orc, max_iteration=3, cube_len=cube_len, det_range=det_range, use_ikd=ref_tree)
         worst_pos, worst_rot, worst_P, n_upd, exact_scans, map_resync = 0.0, 0.0, 0.0, 0, 0, 0
-        for m in seq:
-            a = gpu.process(MeasureGroup(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"]))
+        gate1_fail = rows = 0
+        horizon, free_worst = None, 0.0  # free-running product (never re-synchronised) against the oracle
+        for k, m in enumerate(seq):
+            mg = MeasureGroup(m["lidar"], m["imu"], m["lidar_beg_time"], m["lidar_end_time"])
+            a = gpu.process(mg)
+            f = free.process(mg)
             b = cpu.process(m)
             assert (a is None) == (b is None)  # same skip decisions (first scan, IMU init, map build)
             if gpu.map_built:
                 gx, gi = ctx.map_dump()
                 ox, oi = cpu.map.dump()
-                same_map = gx.shape == ox.shape and np.array_equal(gx.view(np.uint32), ox.view(np.uint32))
+                same_map = gx.shape == ox.shape and np.array_equal(gi, oi) and \
+                    np.array_equal(gx.view(np.uint32), ox.view(np.uint32))
             else:
                 same_map = True
             if a is not None:
@@ -57,8 +74,17 @@ def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_
                 worst_rot = max(worst_rot, float(np.linalg.norm(orc.boxminus(a, b)[3:6])))
                 worst_P = max(worst_P, float(np.abs(gpu.P - cpu.P).max() / np.abs(cpu.P).max()))
                 ga, gb = gpu.log[-1], cpu.log[-1]
-                exact_scans += (ga["m"] == gb["m"] and ga["n_valid"] == gb["n_valid"] and ga["n_passes"] == gb["n_passes"]
-                                and ga["counts"] == gb["counts"] and same_map)
+                exact = (ga["m"] == gb["m"] and ga["n_valid"] == gb["n_valid"] and ga["n_passes"] == gb["n_passes"]
+                         and ga["counts"] == gb["counts"] and same_map)
+                assert exact, (k, ga, gb, same_map)
+                exact_scans += exact
+                rows += len(cpu.last["d2"])
+                gate1_fail += int((cpu.last["d2"][:, 4] > 5).sum())
+                if f is not None:
+                    df = max(float(np.abs(f[0:3] - b[0:3]).max()), float(np.linalg.norm(orc.boxminus(f, b)[3:6])))
+                    free_worst = max(free_worst, df)
+                    if horizon is None and df > TOL_POS:
+                        horizon = n_upd
             # next scan starts from the oracle's posterior on both sides
             gpu.x, gpu.P = cpu.x.copy(), cpu.P.copy()
             if not same_map:
@@ -69,16 +95,21 @@ def test_trajectory_pose_parity(orc, name, n_scans, seed, rings, cols, fov, max_
     assert worst_pos < TOL_POS and worst_rot < TOL_ROT, (worst_pos, worst_rot)
     assert worst_P < 1e-6
     # discrete outcomes (M, matched-point count, pass count, map_incremental classes, the map itself) identical in
-    # nearly every scan; the rest differ by FP64 sin/cos library rounding behind an FP32 store
-    assert exact_scans >= 0.95 * n_upd, (exact_scans, n_upd)
-    assert map_resync <= 0.05 * N_SCANS
+    # EVERY scan (asserted per scan above), hence nothing was ever re-synchronised
+    assert exact_scans == n_upd and map_resync == 0
     assert gpu.n_box_deleted == cpu.n_box_deleted and (cube_len > 100 or gpu.n_box_deleted > 0)
+    if ref_tree:
+        assert gate1_fail >= 0.05 * rows, (gate1_fail, rows)
     # the odometry follows the motion (scan-to-map registration on a 16-ring sensor drifts; both sides agree on it)
     pr = R0.T @ (seq[-1]["truth_pos"] - p0)
     assert np.linalg.norm(b[0:3] - pr) < 0.25 * max(1.0, np.linalg.norm(pr))
+    # the reference loop amplifies any rounding difference (test_reference_loop_is_chaotic): how long a product that is
+    # never re-synchronised stays within the tolerance is reported, not required
     print(f"{name}: {n_upd} updates, worst |dpos| {worst_pos:.2e} m, worst |drot| {worst_rot:.2e} rad, worst rel |dP| "
           f"{worst_P:.2e}, bit-identical discrete outcomes in {exact_scans}/{n_upd} scans, map resyncs {map_resync}, "
-          f"map {map_valid} pts, {gpu.n_box_deleted} points box-deleted")
+          f"map {map_valid} pts, {gpu.n_box_deleted} points box-deleted, gate-1 failures {100.0 * gate1_fail / max(rows, 1):.1f} %; "
+          f"free-running: within 1e-4 for {'all ' + str(n_upd) if horizon is None else 'the first ' + str(horizon - 1)} "
+          f"updates (worst {free_worst:.2e})")
 
 
 def test_process_many_equals_independent_replays():

@@ -58,7 +58,7 @@ def main():
     nq = (a.queries // chunk) * chunk
     for off in range(0, nq, chunk):
         ctx.knn5(q[off:off + chunk], want_xyz=False) if False else ctx._check(
-            ctx._lib.lio_knn5(ctx._h, q[off:off + chunk].ctypes.data, chunk, None, None, None))  # queries -> device
+            ctx._lib.lio_knn5(ctx._h, q[off:off + chunk].ctypes.data, chunk, 5.0, None, None, None))  # queries -> device
         for rep in range(a.reps + 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
