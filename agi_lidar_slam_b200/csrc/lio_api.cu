@@ -138,16 +138,15 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_selected, M);
   ALLOC(c->d_normvec, sizeof(float4) * M);
   ALLOC(c->d_plane, sizeof(float4) * M);
-  ALLOC(c->d_partials, 8 * (size_t)LIO_BLOB * pass_grid_blocks(c));
-  LIO_CHECK(c, cudaMemset(c->d_partials, 0, 8 * (size_t)LIO_BLOB * pass_grid_blocks(c)));
+  ALLOC(c->d_partials, 8 * (size_t)(2 * LIO_BLOB) * pass_grid_blocks(c));
+  LIO_CHECK(c, cudaMemset(c->d_partials, 0, 8 * (size_t)(2 * LIO_BLOB) * pass_grid_blocks(c)));
   ALLOC(c->d_blob_own, 8 * LIO_BLOB);
   c->d_blob = c->d_blob_own;
   ALLOC(c->d_prior, 8 * 288);
-  ALLOC(c->d_pub, 8 * 40);
+  ALLOC(c->d_pub, 8 * 1024);  // PUB_COPIES x PUB_STRIDE stamped words (lio_pass.cu)
+  LIO_CHECK(c, cudaMemset(c->d_pub, 0, 8 * 1024));
   ALLOC(c->d_mailbox, MAILBOX_BYTES);
   LIO_CHECK(c, cudaMemset(c->d_mailbox, 0, MAILBOX_BYTES));
-  ALLOC(c->d_arrive, sizeof(unsigned) * 1024);
-  LIO_CHECK(c, cudaMemset(c->d_arrive, 0, sizeof(unsigned) * 1024));
   {
     // LIO_ZERO_COPY=1: pass 0 reads a pinned scan in place over PCIe instead of a copy first (measured equal on B200)
     const char* env = getenv("LIO_ZERO_COPY");
@@ -267,7 +266,7 @@ void lio_destroy(lio_ctx* c) {
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
                   c->d_near_q,    c->d_far_list,    c->d_far_n,
                   c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,
-                  c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_arrive,      c->d_mailbox,
+                  c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_mailbox,
                   c->d_cloud,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_sorted_aux,  c->d_run_heads,   c->d_runs_status, c->d_runs_ticket,

@@ -47,13 +47,12 @@ struct lio_ctx {
   uint8_t* d_selected = nullptr;    // M point_selected_surf
   float4* d_normvec = nullptr;      // M x (a,b,c,pd2)
   float4* d_plane = nullptr;        // M x pabcd fitted by the last search pass
-  double* d_partials = nullptr;     // pass_grid x LIO_BLOB: per-block partial sums of one pass
+  unsigned long long* d_partials = nullptr;  // pass_grid x 2 LIO_BLOB stamped words: per-block partial sums of one pass
   int pass_grid = 0;                // blocks of the persistent update grid (all co-resident)
   double* d_blob = nullptr;         // LIO_BLOB (own buffer, or the one given to lio_blob_bind)
   double* d_blob_own = nullptr;
   double* d_prior = nullptr;        // 288: P11^-1 and P21 P11^-1 of the current update
   unsigned* d_sync = nullptr;       // grid barrier words {arrivals, release}
-  unsigned* d_arrive = nullptr;     // per-worker arrival stamps of update_kernel (1024 entries)
   // sharded map: peer mailboxes (own one allocated here, the peers' mapped through cudaIpc)
   void* d_mailbox = nullptr;        // {double blob[8][2][LIO_BLOB]; unsigned stamp[8][2]; int err}
   int peer_world = 0, peer_rank = 0;
@@ -63,7 +62,7 @@ struct lio_ctx {
   void* peer_base[8] = {nullptr};   // cudaIpcOpenMemHandle results (closed in lio_destroy)
   int* d_peer_err = nullptr;
   unsigned epoch = 0;               // stamp base of the next update_kernel launch
-  double* d_pub = nullptr;          // 34 doubles published by the solving block after every Kalman step
+  unsigned long long* d_pub = nullptr;  // 29 stamped words published by the solving block after every Kalman step
   long long* d_dbg = nullptr;       // in-kernel timeline (only with LIO_TIMELINE=1)
   uint8_t* d_cls = nullptr;         // map_incremental class per point
   float4* d_add_a = nullptr;        // compacted PointToAdd, PointNoNeedDownsample right behind it

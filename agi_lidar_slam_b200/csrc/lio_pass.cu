@@ -27,12 +27,15 @@
 
 namespace lio {
 
+// One block of 512 threads per SM.  The grid reduction costs the solving block a load of every worker row through its
+// one SM (~1 us per 100 KB), so half as many, fatter blocks halve it; and a lone block per SM keeps its instruction
+// stream to itself.  Measured on the bench workload: 2 x 256 threads per SM 146 us, 1 x 512 threads 124 us per update.
 #ifndef LIO_THREADS
-#define LIO_THREADS 256
+#define LIO_THREADS 512
 #endif
 constexpr int THREADS = LIO_THREADS;  // threads per block of every kernel in this file
 #ifndef LIO_BLOCKS_PER_SM
-#define LIO_BLOCKS_PER_SM 2
+#define LIO_BLOCKS_PER_SM 1
 #endif
 constexpr int ROWS_MAX = 256;    // Jacobian rows staged per tile (cached passes: one thread per point)
 constexpr int RS = 14;           // row stride: 12 Jacobian columns, residual, 1.0 (row counter)
@@ -64,8 +67,7 @@ struct PassArgs {
   float max_d2, plane_thr;
   int rings;
   float own_min, own_max;
-  double* partials;  // [workers][LIO_BLOB]: one 92-double row per worker block
-  unsigned* arrive;  // [workers]: epoch stamp a worker stores (release) once its partial of the current pass is written
+  unsigned long long* partials;  // [workers][ROW_WORDS]: one row of stamped words per worker block (st_stamped)
   long long* dbg;    // optional timeline (LIO_TIMELINE=1): [0] = entries used by block 0, [1..] = (tag, globaltimer ns)
 };
 
@@ -74,9 +76,11 @@ __device__ __forceinline__ long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// block 0 / thread 0 appends (tag, time) pairs from slot 1; the solving block's thread 0 appends from slot 129
+// Timeline instrumentation (LIO_TIMELINE=1).  The LAST thread of block 0 appends (tag, time) pairs from slot 1, the last
+// thread of the solving block from slot 129.  The last thread, because a lane that branches off on its own leaves its
+// warp split for the code that follows (see warp_gauss_jordan), and warp 0 is where the solver runs its collectives.
 __device__ __forceinline__ void stamp(long long* dbg, int base, int tag) {
-  if (dbg == nullptr || threadIdx.x != 0) return;
+  if (dbg == nullptr || threadIdx.x != blockDim.x - 1) return;
   if (base == 0 && blockIdx.x != 0) return;
   const long long n = dbg[base];
   if (n < 62) {
@@ -97,7 +101,7 @@ struct SolveArgs {
   double* blob;      // LIO_BLOB: reduced blob of the last pass (also the all-reduce buffer of the sharded driver)
   double* prior;     // 144 (P11^-1) + 144 (P21 P11^-1, (24-n) x n)
   unsigned* sync;    // [0] arrival counter, [1] release flag
-  double* pub;       // 34: PassConst of the new state, converge, done -- what every block needs for the next pass
+  unsigned long long* pub;  // PUB_WORDS stamped words: x[0..13] of the new state and {converge, done} (publish_state)
   double R;
   int max_iter;
   int from_snapshot;
@@ -115,18 +119,38 @@ __device__ __forceinline__ int scan_size(const PassArgs& a) {
   const int M = a.m_value >= 0 ? a.m_value : *a.scan_m;
   return M < a.min_m ? 0 : M;
 }
-__device__ __forceinline__ int pick_group(int M, int nblocks) {
-  const long long lanes = (long long)nblocks * THREADS;
-  if ((long long)M * 32 <= lanes) return 32;
-  if ((long long)M * 16 <= lanes) return 16;
-  return 8;
+// Ownership of the scan points: worker w owns the contiguous chunk [w * C, (w + 1) * C) in EVERY pass, search or cached.
+// The per-point arrays (neighbour cache, plane, selected, normvec, ...) are then private to one block for the whole
+// update, so no pass has to wait for another block's writes to become visible -- the only traffic between blocks is the
+// partial rows up and the new state down, both made of self-validating words (st_stamped / ld_stamped): no fences.
+__device__ __forceinline__ int chunk_points(int M, int nworkers) {
+  int c = (M + nworkers - 1) / nworkers;
+  c = (c + 7) & ~7;
+  return c < 8 ? 8 : c;
 }
-__device__ __forceinline__ int pick_rows_cached(int M, int nblocks) {
-  int r = (M + nblocks - 1) / nblocks;
-  r = (r + 31) & ~31;
-  return r < 32 ? 32 : (r > ROWS_MAX ? ROWS_MAX : r);
+__device__ __forceinline__ int workers_used(int M, int nworkers) {
+  const int c = chunk_points(M, nworkers);
+  return (M + c - 1) / c;  // <= nworkers
 }
-__device__ __forceinline__ int tiles_of(int M, int rows) { return (M + rows - 1) / rows; }
+// lanes per query in a search: all queries of the chunk in flight at once when it is small (the pass is latency-bound)
+__device__ __forceinline__ int pick_group(int C) { return C <= THREADS / 32 ? 32 : (C <= THREADS / 16 ? 16 : 8); }
+
+// A double as two 64-bit words {stamp << 32 | low half, stamp << 32 | high half}: each word is written by one 8-byte
+// store, so a reader that finds the expected stamp in both holds the value that was written with it -- no fence, no flag,
+// no second round trip.  Stamps are epoch + pass + 1 and never repeat between launches.
+__device__ __forceinline__ void st_stamped(unsigned long long* p, double v, unsigned stamp) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long hs = (unsigned long long)stamp << 32;
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(hs | (b & 0xffffffffull)), "l"(hs | (b >> 32))
+               : "memory");
+}
+__device__ __forceinline__ bool ld_stamped(const unsigned long long* p, unsigned stamp, double& v) {
+  unsigned long long lo, hi;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+  return (unsigned)(lo >> 32) == stamp && (unsigned)(hi >> 32) == stamp;
+}
+constexpr int ROW_WORDS = 2 * LIO_BLOB;  // 64-bit words of one worker's partial row
 
 __device__ __forceinline__ void load_pass_const(const StateD* x, PassConst& pc) {
   const double* s = reinterpret_cast<const double*>(x);
@@ -160,15 +184,14 @@ constexpr int SROWS_MAX = THREADS / 8;  // rows of a search tile at the smallest
 // Search phase of one tile: THREADS / G queries, one per G-lane group (esekfom.hpp:140).  The 5 neighbours go to
 // the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.
 template <int G>
-__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int M, int tile, float4* s_nb,
+__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int i0, int end, float4* s_nb,
                                          int* s_cnt, float4* s_body, const float4* body) {
-  constexpr int ROWS = THREADS / G;
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int row = threadIdx.x / G;
-  const int i_raw = tile * ROWS + row;
-  const bool act = i_raw < M;  // group-uniform
-  const int i = act ? i_raw : M - 1;  // idle groups redo the last query: the whole warp stays together for the shuffles
+  const int i_raw = i0 + row;
+  const bool act = i_raw < end;  // group-uniform
+  const int i = act ? i_raw : end - 1;  // idle groups redo the last query: the whole warp stays together for the shuffles
   const float4 b = body[i];  // device copy, or the caller's pinned host buffer in pass 0 of the host-direct path
   if (gl == 0) s_body[row] = b;
   const double pb[3] = {b.x, b.y, b.z};
@@ -212,13 +235,13 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
 
 // Finish phase of one tile, one thread per point: steps 1.1-1.2 and 1.5-3 of h_share_model (esekfom.hpp:123-133,
 // 153-226) from the point's 5 neighbours (just found: shared memory; cached: a.near_pts with the sticky mask).
-__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int M, int tile, int rows, bool search,
+__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int i0, int end, int rows, bool search,
                                          const float4* s_nb, const int* s_cnt, double* s_rows,
                                          unsigned char* s_valid, const float4* s_body, bool copy_body) {
   const int row = threadIdx.x;
   if (row >= rows) return;
-  const int i = tile * rows + row;
-  if (i >= M) {
+  const int i = i0 + row;
+  if (i >= end) {
     s_valid[row] = 0;
     return;
   }
@@ -308,7 +331,8 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
 // memory, products accumulated by thread (output o, segment seg) over rows seg, seg + nseg, ... of every tile, then
 // the segments are combined in order and the block's partial blob is written to a.partials[blockIdx.x].
 struct PassSmem;
-__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid, bool first_pass);
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid, bool first_pass,
+                           unsigned target);
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -319,46 +343,72 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Sum of the workers' partial rows into s_blob[LIO_BLOB] in a FIXED order: warp w adds the rows of workers
-// w, w + nwarps, ... in ascending order (lane = output, one coalesced row load per worker, CH rows in flight), then
-// the per-warp sums are added in warp order.  With target != 0 the warp first waits until the workers of the chunk
-// have stamped their arrival flag (the lanes poll the chunk's flags in parallel), so the reduction runs WHILE the
-// slower workers are still busy and only the last chunk is left when the last one arrives.  The waiting does not
-// change the order, hence not the bits.
+// Sum of the workers' partial rows into s_warp[warp][LIO_BLOB] in a FIXED order: warp w adds the rows of workers
+// w, w + nwarps, ... in ascending order (lane = output, one coalesced 16-byte load per output and row, CH rows in
+// flight).  A row is taken when every word of it carries `target` (ld_stamped); until then the chunk is simply loaded
+// again, so the reduction runs WHILE the slower workers are still busy and only the last chunk is left when the last
+// one is done.  The waiting does not change the order, hence not the bits.
 template <int KPL, int CH>
 __device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout, unsigned target, double* s_warp) {
+  static_assert(CH <= 32, "one lane watches one row of the chunk");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = THREADS / 32;
-  int e[KPL];
+  // NO lane-dependent branch in here: a warp that splits can stay split, and every vote behind the split costs a
+  // rendezvous of ~1,000 cycles instead of ~30 (measured).  Lanes without an output load output 0 and drop it; rows
+  // beyond the last one are clamped to it and dropped.
+  // A worker's row holds its nout outputs back to back (2 words each); s_warp is indexed by blob position.
+  int e[KPL], o[KPL];
+  bool use[KPL];
   double acc[KPL];
 #pragma unroll
   for (int k = 0; k < KPL; ++k) {
-    const int o = lane + 32 * k;
-    e[k] = o < nout ? (a.extrinsic_est ? c_oe_ext[o] : c_oe_no[o]) : -1;
+    o[k] = lane + 32 * k;
+    use[k] = o[k] < nout;
+    if (!use[k]) o[k] = 0;
+    e[k] = a.extrinsic_est ? c_oe_ext[o[k]] : c_oe_no[o[k]];
     acc[k] = 0.0;
   }
 #pragma unroll 1
   for (int base = warp; base < nb; base += NW * CH) {
-    if (target != 0) {
-      // the lanes poll the arrival stamps of the chunk's workers in parallel (two stamps per lane when CH > 32)
-      bool ready;
+    // 1. wait: lane j watches ONE word of row j of the chunk until all of them have shown up.  Cheap (a few dozen
+    //    requests per round trip for the whole block), and the bulk load below -- all the rows through one SM: ~100 KB,
+    //    a microsecond -- is then issued once, not over and over while the slowest worker is still busy.
+    {
+      const int jj = lane < CH ? lane : CH - 1;
+      const int b = base + NW * jj;
+      const unsigned long long* w0 = a.partials + (size_t)(b < nb ? b : nb - 1) * ROW_WORDS;
+      bool seen;
       do {
-        ready = true;
-#pragma unroll
-        for (int u = 0; u < (CH + 31) / 32; ++u) {
-          const int j = lane + 32 * u;
-          const int b = base + NW * j;
-          if (j < CH && b < nb) ready = ready && (ld_acquire(a.arrive + b) - target) < 0x40000000u;
-        }
-      } while (!__all_sync(0xffffffffu, ready));
+        unsigned long long w;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(w0) : "memory");
+        seen = (unsigned)(w >> 32) == target;
+      } while (!__all_sync(0xffffffffu, seen));
     }
+    stamp(a.dbg, 128, 13);
+    // 2. load: one coalesced 16-byte load per output and row, all CH rows in flight; every word validates itself (the
+    //    other words of a row may lag a little behind the watched one: then simply once more)
     double v[CH][KPL];
+    bool ready;
+    do {
+      ready = true;
 #pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int b = base + NW * j;
+      for (int j = 0; j < CH; ++j) {
+        const int b = base + NW * j;  // the same for the whole warp: this branch does not split it
+        if (b < nb) {
 #pragma unroll
-      for (int k = 0; k < KPL; ++k) v[j][k] = (b < nb && e[k] >= 0) ? __ldcg(a.partials + (size_t)b * LIO_BLOB + e[k]) : 0.0;
-    }
+          for (int k = 0; k < KPL; ++k) {
+            double x;
+            const bool ok = ld_stamped(a.partials + (size_t)b * ROW_WORDS + 2 * o[k], target, x);
+            v[j][k] = use[k] ? x : 0.0;
+            ready = ready && ok;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KPL; ++k) v[j][k] = 0.0;
+        }
+      }
+    } while (!__all_sync(0xffffffffu, ready));
+    // 3. add, in row order
 #pragma unroll
     for (int j = 0; j < CH; ++j)
 #pragma unroll
@@ -366,28 +416,24 @@ __device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout,
   }
 #pragma unroll
   for (int k = 0; k < KPL; ++k)
-    if (e[k] >= 0) s_warp[warp * LIO_BLOB + e[k]] = acc[k];
+    if (use[k]) s_warp[warp * LIO_BLOB + e[k]] = acc[k];
 }
 
 __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool search, int nworkers, unsigned target,
                                                    double* s_blob, double* s_warp) {
   const int tid = threadIdx.x;
-  const int M = scan_size(a);
-  const int G = pick_group(M, nworkers);
-  const int rows = search ? THREADS / G : pick_rows_cached(M, nworkers);
-  const int ntiles = tiles_of(M, rows);
-  const int nb = ntiles < nworkers ? ntiles : nworkers;
+  const int nb = workers_used(scan_size(a), nworkers);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   if (a.extrinsic_est)
-    reduce_rows<3, 10>(a, nb, nout, target, s_warp);
+    reduce_rows<3, 8>(a, nb, nout, target, s_warp);
   else
-    reduce_rows<1, 40>(a, nb, nout, target, s_warp);  // 8 warps x 40 rows: every worker of a 296-block grid in one chunk
+    reduce_rows<1, 32>(a, nb, nout, target, s_warp);  // 8 warps x 32 rows: (nearly) every worker row in one chunk
   __syncthreads();
   if (tid < LIO_BLOB) {
     double sum = 0.0;
     const int o_valid = a.extrinsic_est ? 1 : ((tid < 78 && c_is_no[tid]) || (tid >= 78 && tid < 84) || tid == 90);
     if (tid < 91 && o_valid) {
-#pragma unroll 1
+#pragma unroll
       for (int w = 0; w < THREADS / 32; ++w) sum += s_warp[w * LIO_BLOB + tid];
     }
     if (tid == 91) sum = search ? 1.0 : 0.0;
@@ -505,12 +551,11 @@ struct SolveSmem {
   double blob[LIO_BLOB];
   double warp_part[(THREADS / 32) * LIO_BLOB];  // per-warp sums of the grid reduction
   Ctrl sc;                                      // loop state (mirrored to SolveArgs::ctrl after every step)
-  double S[144], Sinv[144], Kf[288], KH[288], Kh[24], dxn[24], dx[24];
+  double S[144], Sinv[144], Kf[288], KH[288], dxn[24], dx[24];
   double W[12 * WS];   // [A | I] of block_inverse_spd
   double prior[288];   // P11^-1 (n x n) and P21 P11^-1 ((24-n) x n) of this update
   double P[576];
   double xa[26], xb[26], xn[26];  // x, x_propagated, x [+] dx
-  double pubrec[34];              // staging of SolveArgs::pub
   int fin;
 };
 
@@ -531,6 +576,7 @@ __device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* s
     reinterpret_cast<double*>(s.xprop)[tid] = sm->xa[tid];  // esekfom.hpp:287
     sm->xb[tid] = sm->xa[tid];
   }
+  if (tid < 24) sm->dxn[tid] = 0.0;  // x [-] x_propagated of the first step: x IS x_propagated
   if (tid == 0) {
     Ctrl c0;
     c0.iter = -1;
@@ -567,7 +613,9 @@ __device__ __noinline__ void block_prior(const SolveArgs& s, int n, SolveSmem* s
 }
 
 // The stepwise driver keeps nothing in shared memory between its launches: filter state and constants come back from
-// global memory in ONE round of loads (all issued before the first use).
+// global memory in ONE round of loads (all issued before the first use); x [-] x_propagated is formed again from them
+// (same function, same inputs, same bits as the copy the persistent kernel carries along).
+__device__ __forceinline__ void step_boxminus(SolveSmem* sm);
 __device__ __forceinline__ void solve_load_inputs(const SolveArgs& s, SolveSmem* sm) {
   const int tid = threadIdx.x;
   double vp[(576 + THREADS - 1) / THREADS], vq[(288 + THREADS - 1) / THREADS], va = 0.0, vb = 0.0;
@@ -595,123 +643,235 @@ __device__ __forceinline__ void solve_load_inputs(const SolveArgs& s, SolveSmem*
   }
   if (tid < 8) reinterpret_cast<int*>(&sm->sc)[tid] = cv;
   __syncthreads();
+  step_boxminus(sm);
+  __syncthreads();
 }
 
-struct SolveSmem;
-__device__ __forceinline__ void block_publish_unchanged(const SolveArgs& s, SolveSmem* sm);
+// ---------------------------------------------------------------------------------------------------------
+// The Kalman step (esekfom.hpp:297-345).  It sits on the critical path of every pass (all workers wait for it), so what
+// counts is the length of its dependent chain:
+//   S = HtH[:n,:n] / R + P11^-1,  v = Hth / R + (HtH / R) dx_new[:n],  u = S^-1 v     one warp, registers + shuffles
+//   dx[:n] = u - dx_new[:n],  dx[n:] = (P21 P11^-1) u - dx_new[n:]                       (esekfom.hpp:319, regrouped)
+//   x = x [+] dx (the two rotations in two warps), loop state, publication of the new state to the workers;
+//   x [-] x_propagated for the NEXT step and (after the last step) S^-1 for the covariance come after the publication.
+// S is SPD (HtH / R is PSD, P11^-1 is PD): elimination needs no pivot search.
+//
+// Warp collectives and divergence.  A lane-dependent branch can leave a warp split for a long stretch of the code
+// behind it (measured here: __activemask() == 1 some hundred instructions after an `if (lane == 0)`), and a split warp
+// pays a rendezvous of ~750-1,400 cycles for every shuffle, vote or __syncwarp instead of ~30: the 6 x 6 elimination
+// took 15,400 cycles that way and 980 in a converged warp.  So: collectives only in code that is reached straight
+// from a block barrier, with no lane-dependent branch in between (selects instead); lane-specific work (one rotation,
+// one flag) goes to OTHER warps between barriers.
+// ---------------------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+// lane i < N holds row i of A in a[] and of B in b[]; on return b = A^-1 B (row i in lane i).  Lanes >= N carry zero
+// rows and only take part in the shuffles.  Branch-free.
+template <int N, int NR>
+__device__ __forceinline__ void warp_gauss_jordan(double (&a)[N], double (&b)[NR], int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double pinv = 1.0 / __shfl_sync(FULL, a[k], k);
+    const bool piv = lane == k;
+    const double f = a[k];  // a_ik: this row's entry in the pivot column
+#pragma unroll
+    for (int c = k + 1; c < N; ++c) {
+      const double t = a[c] * pinv;  // what the pivot row becomes (normalised); only lane k's is taken
+      const double pc = __shfl_sync(FULL, t, k);
+      a[c] = piv ? t : fma(-f, pc, a[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NR; ++c) {
+      const double t = b[c] * pinv;
+      const double pc = __shfl_sync(FULL, t, k);
+      b[c] = piv ? t : fma(-f, pc, b[c]);
+    }
+  }
+}
+__device__ __forceinline__ int blob_index(int r, int c) {  // upper triangle of the 12 x 12 HtH, row-major
+  const int lo = r < c ? r : c, hi = r < c ? c : r;
+  return lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo);
+}
+// row `lane` of S = HtH[:N,:N] / R + P11^-1; lanes >= N read row 0 and get zeros (no branch)
+template <int N>
+__device__ __forceinline__ void load_S_row(const SolveSmem* sm, double inv_R, int lane, double (&a)[N]) {
+  const int r = lane < N ? lane : 0;
+  const double keep = lane < N ? 1.0 : 0.0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) a[j] = keep * fma(sm->blob[blob_index(r, j)], inv_R, sm->prior[r * N + j]);
+}
 
-// One Kalman step from the reduced blob in sm->blob (esekfom.hpp:297-345) on the filter state held in shared memory
-// (sm->xa = x, sm->xb = x_propagated, sm->P, sm->sc); x, the loop state and -- at the end -- P are mirrored to global.
-__device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* sm) {
+// What the workers need of a step: x[0..13] = pos, rot, R_LI, t_LI as 28 stamped halves, and {converge, done} in word 28.
+// PUB_COPIES copies 1 KB apart (different L2 slices): worker w polls copy w % PUB_COPIES, so that ~300 spinning blocks
+// do not queue up on one slice.  Called by one converged warp.
+constexpr int PUB_WORDS = 29;
+constexpr int PUB_COPIES = 8;
+constexpr int PUB_STRIDE = 128;  // 64-bit words between two copies
+__device__ __forceinline__ void publish_state(unsigned long long* pub, const double* x14, int flags, unsigned target,
+                                              int lane) {
+  const int l = lane < PUB_WORDS ? lane : PUB_WORDS - 1;  // lanes 29..31 repeat word 28 (same value, same address)
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x14[l < 28 ? (l >> 1) : 0]);
+  const unsigned half = l < 28 ? ((l & 1) ? (unsigned)(b >> 32) : (unsigned)b) : (unsigned)flags;
+  const unsigned long long w = ((unsigned long long)target << 32) | half;
+#pragma unroll
+  for (int c = 0; c < PUB_COPIES; ++c)
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(pub + c * PUB_STRIDE + l), "l"(w) : "memory");
+}
+
+// u = S^-1 v into sm->S[0..N) (scratch), by warp 0, reached straight from a block barrier
+template <int N>
+__device__ __forceinline__ void warp_solve(SolveSmem* sm, double inv_R, int lane) {
+  double a[N], v[1];
+  load_S_row<N>(sm, inv_R, lane, a);
+  {
+    const int r = lane < N ? lane : 0;
+    double acc = sm->blob[78 + r];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc = fma(sm->blob[blob_index(r, j)], sm->dxn[j], acc);
+    v[0] = (lane < N ? 1.0 : 0.0) * (acc * inv_R);
+  }
+  warp_gauss_jordan<N, 1>(a, v, lane);
+  if (lane < N) sm->S[lane] = v[0];  // (no collective behind this branch)
+}
+// S^-1 into sm->Sinv, by one warp reached straight from a block barrier (only after the last step: the covariance)
+template <int N>
+__device__ __forceinline__ void warp_invert(SolveSmem* sm, double inv_R, int lane) {
+  double a[N], b[N];
+  load_S_row<N>(sm, inv_R, lane, a);
+#pragma unroll
+  for (int j = 0; j < N; ++j) b[j] = (lane == j) ? 1.0 : 0.0;
+  warp_gauss_jordan<N, N>(a, b, lane);
+  if (lane < N) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) sm->Sinv[lane * N + j] = b[j];
+  }
+}
+
+// dx_new = x [-] x_propagated (esekfom.hpp:303) for the state in sm->xa: the two rotations in two warps, the vector parts
+// in a third.  Whole block; the caller synchronises.
+__device__ __forceinline__ void step_boxminus(SolveSmem* sm) {
   const int tid = threadIdx.x;
-  Ctrl* ctrl = s.ctrl;
-  const int iter = sm->sc.iter, max_iter = sm->sc.max_iter, t_old = sm->sc.t, np_old = sm->sc.n_passes;
-  if (tid < LIO_BLOB) s.blob[tid] = sm->blob[tid];
-  const int n_valid = (int)sm->blob[90];
+  if (tid == 0) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 3), reinterpret_cast<const Quatd*>(sm->xb + 3), sm->dxn + 3);
+  if (tid == 32) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 7), reinterpret_cast<const Quatd*>(sm->xb + 7), sm->dxn + 6);
+  if (tid >= 64 && tid < 64 + 24) {
+    const int j = tid - 64;  // error-state index; state index: pos 0-2 | t_LI 11-13 | vel.. 14-25
+    if (j < 3) sm->dxn[j] = sm->xa[j] - sm->xb[j];
+    if (j >= 9) sm->dxn[j] = sm->xa[j + 2] - sm->xb[j + 2];
+  }
+}
+
+
+// P = (I - K H) P (esekfom.hpp:342), K H = K_front[:, :n] HtH / R with K_front[:, :n] = [Sinv ; (P21 P11^-1) Sinv]; whole
+// block, once per update (after the step that set sm->fin; sm->Sinv is in place).
+__device__ __noinline__ void block_final_P(const SolveArgs& s, int n, SolveSmem* sm) {
+  const int tid = threadIdx.x;
+  const double inv_R = 1.0 / s.R;
+#pragma unroll 1
+  for (int k = tid; k < 24 * n; k += THREADS) {
+    const int r = k / n, c = k % n;
+    double acc;
+    if (r < n) {
+      acc = sm->Sinv[r * n + c];
+    } else {
+      acc = 0.0;
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) acc = fma(sm->prior[144 + (r - n) * n + j], sm->Sinv[j * n + c], acc);
+    }
+    sm->Kf[k] = acc;
+  }
   __syncthreads();
+#pragma unroll 1
+  for (int k = tid; k < 24 * n; k += THREADS) {
+    const int r = k / n, c = k % n;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) acc = fma(sm->Kf[r * n + j], sm->blob[blob_index(j, c)], acc);
+    sm->KH[k] = acc * inv_R;
+  }
+  __syncthreads();
+  double pnew[(576 + THREADS - 1) / THREADS];
+#pragma unroll
+  for (int u = 0; u < (576 + THREADS - 1) / THREADS; ++u) {
+    const int k = tid + u * THREADS;
+    pnew[u] = 0.0;
+    if (k < 576) {
+      const int r = k / 24, c = k % 24;
+      double acc = sm->P[k];
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) acc = fma(-sm->KH[r * n + j], sm->P[j * 24 + c], acc);
+      pnew[u] = acc;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < (576 + THREADS - 1) / THREADS; ++u) {
+    const int k = tid + u * THREADS;
+    if (k < 576) {
+      s.P[k] = pnew[u];
+      sm->P[k] = pnew[u];  // the shared copy stays current (host-direct path reads the posterior from it)
+    }
+  }
+  __syncthreads();
+}
+
+// One Kalman step of the solving block on the reduced blob in sm->blob (esekfom.hpp:297-345); the caller has just
+// synchronised the block.  On return the new state has been published (stamp `target`), mirrored to global memory, and
+// sm->dxn holds x [-] x_propagated for the next step; after the last step P has been updated.
+__device__ __noinline__ void block_step(const SolveArgs& s, int n, SolveSmem* sm, unsigned target) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int iter = sm->sc.iter, max_iter = sm->sc.max_iter, t_old = sm->sc.t, np_old = sm->sc.n_passes;
+  const int n_valid = (int)sm->blob[90];
+  const double inv_R = 1.0 / s.R;
   if (n_valid < 1) {
     // `if (!dyn_share.valid) continue;` (esekfom.hpp:297-299): nothing changes, the loop counter advances
+    const int done = (iter + 1 >= max_iter) ? 1 : sm->sc.done;
+    if (tid < 32) publish_state(s.pub, sm->xa, (sm->sc.converge ? 1 : 0) | (done ? 2 : 0), target, lane);
+    if (tid >= 32 && tid < 32 + LIO_BLOB) s.blob[tid - 32] = sm->blob[tid - 32];
+    __syncthreads();
     if (tid == 0) {
       sm->sc.n_valid_last = 0;
       sm->sc.n_passes = np_old + 1;
       sm->sc.iter = iter + 1;
-      if (iter + 1 >= max_iter) sm->sc.done = 1;
-      *ctrl = sm->sc;
-      sm->pubrec[32] = (double)sm->sc.converge;
-      sm->pubrec[33] = (double)sm->sc.done;
+      sm->sc.done = done;
+      *s.ctrl = sm->sc;
+      sm->fin = 0;
     }
-    if (tid < 26) sm->xn[tid] = sm->xa[tid];
     __syncthreads();
-    block_publish_unchanged(s, sm);
     return;
   }
-  __syncthreads();
   stamp(s.dbg, 128, 20);
-  const double inv_R = 1.0 / s.R;
-  // S = HtH[:n,:n] / R + P11^-1
-#pragma unroll 1
-  for (int k = tid; k < n * n; k += THREADS) {
-    const int r = k / n, c = k % n;
-    const int lo = r < c ? r : c, hi = r < c ? c : r;
-    sm->S[k] = sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)] * inv_R + sm->prior[k];
-  }
-  __syncthreads();
-  // warps 0-2 (0-5 when n = 12) invert S while the last two warps form dx_new = x [-] x_propagated (esekfom.hpp:303):
-  // one rotation per thread, the vector parts next to them
-  {
-    const int nthr = inv_threads(n);
-    if (tid < nthr) block_inverse_spd(sm->S, sm->Sinv, n, sm->W);
-    if (tid == THREADS - 32) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 3), reinterpret_cast<const Quatd*>(sm->xb + 3), sm->dxn + 3);
-    if (tid == THREADS - 64) rot_minus(reinterpret_cast<const Quatd*>(sm->xa + 7), reinterpret_cast<const Quatd*>(sm->xb + 7), sm->dxn + 6);
-    if (tid >= THREADS - 31 && tid < THREADS - 31 + 24) {
-      const int j = tid - (THREADS - 31);  // error-state index; state index: pos 0-2 | t_LI 11-13 | vel.. 14-25
-      if (j < 3) sm->dxn[j] = sm->xa[j] - sm->xb[j];
-      if (j >= 9) sm->dxn[j] = sm->xa[j + 2] - sm->xb[j + 2];
-    }
+  // ---- u = S^-1 v: warp 0, converged (straight from the caller's barrier)
+  if (tid < 32) {
+    if (n == 6)
+      warp_solve<6>(sm, inv_R, lane);
+    else
+      warp_solve<12>(sm, inv_R, lane);
   }
   __syncthreads();
   stamp(s.dbg, 128, 21);
-  // dx = K h + (K H - I) dx_new (esekfom.hpp:319) with K_front[:, :n] = [I ; P21 P11^-1] Sinv, regrouped so that only
-  // three n-sized products are on the way:  v = Hth/R + (HtH/R) dx_new[:n] ;  u = Sinv v ;
-  // dx[:n] = u - dx_new[:n] ;  dx[n:] = (P21 P11^-1) u - dx_new[n:].   One warp, no block barrier.
-  if (tid < 32) {
-    double* v = sm->Kh;       // n
-    double* u = sm->Kh + 12;  // n
+  // ---- dx (esekfom.hpp:319)
+  if (tid < 24) {
+    double acc;
     if (tid < n) {
-      double acc = sm->blob[78 + tid];
+      acc = sm->S[tid];
+    } else {
+      acc = 0.0;
 #pragma unroll 1
-      for (int j = 0; j < n; ++j) {
-        const int lo = j < tid ? j : tid, hi = j < tid ? tid : j;
-        acc = fma(sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)], sm->dxn[j], acc);
-      }
-      v[tid] = acc * inv_R;
+      for (int j = 0; j < n; ++j) acc = fma(sm->prior[144 + (tid - n) * n + j], sm->S[j], acc);
     }
-    __syncwarp();
-    if (tid < n) {
-      double acc = 0.0;
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) acc = fma(sm->Sinv[tid * n + j], v[j], acc);
-      u[tid] = acc;
-    }
-    __syncwarp();
-    if (tid < 24) {
-      double acc;
-      if (tid < n) {
-        acc = u[tid];
-      } else {
-        acc = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) acc = fma(sm->prior[144 + (tid - n) * n + j], u[j], acc);
-      }
-      sm->dx[tid] = acc - sm->dxn[tid];
-    }
+    sm->dx[tid] = acc - sm->dxn[tid];
   }
   __syncthreads();
   stamp(s.dbg, 128, 22);
-  // x = x [+] dx (esekfom.hpp:321): one rotation per thread (each goes straight on to the per-pass constants of the
-  // new state that every worker needs next: SolveArgs::pub), the vector parts and the loop state in other warps
-  PassConst* pc = reinterpret_cast<PassConst*>(sm->pubrec);
-  if (tid == 0) {
-    rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 3), sm->dx + 3, reinterpret_cast<Quatd*>(sm->xn + 3));
-    pc->rot = Quatd{sm->xn[3], sm->xn[4], sm->xn[5], sm->xn[6]};
-    quat_to_mat(pc->rot, pc->Rt);
-  }
-  if (tid == 32) {
-    rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 7), sm->dx + 6, reinterpret_cast<Quatd*>(sm->xn + 7));
-    pc->rli = Quatd{sm->xn[7], sm->xn[8], sm->xn[9], sm->xn[10]};
-    quat_to_mat(pc->rli, pc->Rli);
-  }
+  // ---- x = x [+] dx (esekfom.hpp:321): one rotation per warp, the vector parts and the loop state in two more
+  if (tid == 0) rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 3), sm->dx + 3, reinterpret_cast<Quatd*>(sm->xn + 3));
+  if (tid == 32) rot_plus(reinterpret_cast<const Quatd*>(sm->xa + 7), sm->dx + 6, reinterpret_cast<Quatd*>(sm->xn + 7));
   if (tid >= 64 && tid < 64 + 24) {
     const int j = tid - 64;
-    if (j < 3) {
-      sm->xn[j] = sm->xa[j] + sm->dx[j];
-      pc->pos[j] = sm->xn[j];
-    }
+    if (j < 3) sm->xn[j] = sm->xa[j] + sm->dx[j];
     if (j >= 9) sm->xn[j + 2] = sm->xa[j + 2] + sm->dx[j];
-    if (j >= 9 && j < 12) pc->tli[j - 9] = sm->xn[j + 2];
   }
   if (tid == 96) {
-    bool converge = true;
+    bool converge = true;  // esekfom.hpp:324-330: every one of the 24 components
 #pragma unroll 1
     for (int jj = 0; jj < 24; ++jj)
       if (fabs(sm->dx[jj]) > 0.001) {
@@ -720,7 +880,7 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
       }
     int t = t_old;
     if (converge) t++;
-    if (!t && iter == max_iter - 2) converge = true;
+    if (!t && iter == max_iter - 2) converge = true;  // forced re-search (esekfom.hpp:333)
     const int fin = (t > 1 || iter == max_iter - 1) ? 1 : 0;
     sm->sc.converge = converge ? 1 : 0;
     sm->sc.t = t;
@@ -728,90 +888,36 @@ __device__ __noinline__ void block_solve(const SolveArgs& s, int n, SolveSmem* s
     sm->sc.n_passes = np_old + 1;
     sm->sc.iter = iter + 1;
     if (fin) sm->sc.done = 1;
-    *ctrl = sm->sc;
     sm->fin = fin;
-    sm->pubrec[32] = converge ? 1.0 : 0.0;
-    sm->pubrec[33] = fin ? 1.0 : 0.0;
   }
-  if (tid < 24 && s.dx_out) s.dx_out[tid] = sm->dx[tid];
   __syncthreads();
+  // ---- the workers are waiting for exactly this
+  if (tid < 32) publish_state(s.pub, sm->xn, (sm->sc.converge ? 1 : 0) | (sm->fin ? 2 : 0), target, lane);
   stamp(s.dbg, 128, 23);
-  if (tid < 34) s.pub[tid] = sm->pubrec[tid];
-  if (tid < 26) {
-    reinterpret_cast<double*>(s.x)[tid] = sm->xn[tid];
-    sm->xa[tid] = sm->xn[tid];  // the next step starts here
+  // ---- off the workers' critical path from here on
+  if (tid >= 32 && tid < 32 + 26) {
+    const double xv = sm->xn[tid - 32];
+    sm->xa[tid - 32] = xv;  // the next step starts here
+    reinterpret_cast<double*>(s.x)[tid - 32] = xv;
   }
+  if (tid >= 64 && tid < 64 + 24 && s.dx_out) s.dx_out[tid - 64] = sm->dx[tid - 64];
+  if (tid >= 96 && tid < 96 + LIO_BLOB) s.blob[tid - 96] = sm->blob[tid - 96];
+  if (tid == 0) *s.ctrl = sm->sc;
+  __syncthreads();
   if (sm->fin) {
-    // P = (I - K H) P (esekfom.hpp:342), K H = K_front[:, :n] HtH / R with K_front[:, :n] = [Sinv ; (P21 P11^-1) Sinv];
-    // only needed once, after the last step
-#pragma unroll 1
-    for (int k = tid; k < 24 * n; k += THREADS) {
-      const int r = k / n, c = k % n;
-      double acc;
-      if (r < n) {
-        acc = sm->Sinv[r * n + c];
-      } else {
-        acc = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) acc = fma(sm->prior[144 + (r - n) * n + j], sm->Sinv[j * n + c], acc);
-      }
-      sm->Kf[k] = acc;
+    // S^-1 itself is only needed for the covariance, once, after the last step
+    if (tid < 32) {
+      if (n == 6)
+        warp_invert<6>(sm, inv_R, lane);
+      else
+        warp_invert<12>(sm, inv_R, lane);
     }
     __syncthreads();
-#pragma unroll 1
-    for (int k = tid; k < 24 * n; k += THREADS) {
-      const int r = k / n, c = k % n;
-      double acc = 0.0;
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) {
-        const int lo = j < c ? j : c, hi = j < c ? c : j;
-        acc = fma(sm->Kf[r * n + j], sm->blob[lo * 12 - (lo * (lo - 1)) / 2 + (hi - lo)], acc);
-      }
-      sm->KH[k] = acc * inv_R;
-    }
+    block_final_P(s, n, sm);
+  } else {
+    step_boxminus(sm);  // dx_new of the next step, while the workers run their pass
     __syncthreads();
-    double pnew[(576 + THREADS - 1) / THREADS];
-#pragma unroll
-    for (int u = 0; u < (576 + THREADS - 1) / THREADS; ++u) {
-      const int k = tid + u * THREADS;
-      pnew[u] = 0.0;
-      if (k < 576) {
-        const int r = k / 24, c = k % 24;
-        double acc = sm->P[k];
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) acc = fma(-sm->KH[r * n + j], sm->P[j * 24 + c], acc);
-        pnew[u] = acc;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < (576 + THREADS - 1) / THREADS; ++u) {
-      const int k = tid + u * THREADS;
-      if (k < 576) {
-        s.P[k] = pnew[u];
-        sm->P[k] = pnew[u];  // the shared copy stays current (host-direct path reads the posterior from it)
-      }
-    }
   }
-  __syncthreads();
-}
-
-// The skipped step (no valid point) leaves the state as it was: its per-pass constants still have to go out.
-__device__ __forceinline__ void block_publish_unchanged(const SolveArgs& s, SolveSmem* sm) {
-  const int tid = threadIdx.x;
-  PassConst* pc = reinterpret_cast<PassConst*>(sm->pubrec);
-  if (tid == 0) {
-    pc->pos[0] = sm->xn[0]; pc->pos[1] = sm->xn[1]; pc->pos[2] = sm->xn[2];
-    pc->rot = Quatd{sm->xn[3], sm->xn[4], sm->xn[5], sm->xn[6]};
-    quat_to_mat(pc->rot, pc->Rt);
-  }
-  if (tid == 32) {
-    pc->rli = Quatd{sm->xn[7], sm->xn[8], sm->xn[9], sm->xn[10]};
-    pc->tli[0] = sm->xn[11]; pc->tli[1] = sm->xn[12]; pc->tli[2] = sm->xn[13];
-    quat_to_mat(pc->rli, pc->Rli);
-  }
-  __syncthreads();
-  if (tid < 34) s.pub[tid] = sm->pubrec[tid];
 }
 
 struct __align__(16) PassSmem {
@@ -822,20 +928,26 @@ struct __align__(16) PassSmem {
   int cnt[SROWS_MAX];            // gate 1 of the search phase
   float4 body_row[SROWS_MAX];    // the search tile's scan points, for its finish phase
   unsigned char valid[ROWS_MAX];
+  double xrecv[15];  // worker_receive: the published x[0..13] and, in the low half of [14], the flags
   int flag;
 };
 
 // ps->pc holds the per-pass constants (the caller loads or computes them and synchronises the block).
-// Worker `wid` of `nworkers` takes tiles wid, wid + nworkers, ... and leaves its partial blob in a.partials[wid].
-__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid, bool first_pass) {
+// Worker `wid` of `nworkers` runs its chunk of the scan (chunk_points) and leaves its partial blob, stamped `target`, in
+// row wid of a.partials; a worker whose chunk is empty writes nothing (the reduction knows: workers_used).
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid, bool first_pass,
+                           unsigned target) {
   const int tid = threadIdx.x;
   const bool from_host = first_pass && a.body_src != nullptr;  // pass 0 always searches
   const float4* body = from_host ? a.body_src : a.body;
   const int M = scan_size(a);
   stamp(a.dbg, 0, 2);
-  const int G = pick_group(M, nworkers);
-  const int rows = search ? THREADS / G : pick_rows_cached(M, nworkers);
-  const int ntiles = tiles_of(M, rows);
+  const int C = chunk_points(M, nworkers);
+  const int beg = wid * C;
+  if (beg >= M) return;  // block-uniform
+  const int end = min(M, beg + C);
+  const int G = pick_group(C);
+  const int rows = search ? THREADS / G : (C < ROWS_MAX ? C : ROWS_MAX);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   const int nseg = THREADS / nout;
   const int o = tid % nout, seg = tid / nout;
@@ -846,18 +958,18 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nwo
   }
   double acc = 0.0;
 #pragma unroll 1
-  for (int tile = wid; tile < ntiles; tile += nworkers) {
+  for (int i0 = beg; i0 < end; i0 += rows) {
     if (search) {
       if (G == 32)
-        search_tile<32>(a, ps->pc, M, tile, ps->nb, ps->cnt, ps->body_row, body);
+        search_tile<32>(a, ps->pc, i0, end, ps->nb, ps->cnt, ps->body_row, body);
       else if (G == 16)
-        search_tile<16>(a, ps->pc, M, tile, ps->nb, ps->cnt, ps->body_row, body);
+        search_tile<16>(a, ps->pc, i0, end, ps->nb, ps->cnt, ps->body_row, body);
       else
-        search_tile<8>(a, ps->pc, M, tile, ps->nb, ps->cnt, ps->body_row, body);
+        search_tile<8>(a, ps->pc, i0, end, ps->nb, ps->cnt, ps->body_row, body);
       __syncthreads();
       stamp(a.dbg, 0, 3);
     }
-    finish_tile(a, ps->pc, M, tile, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
+    finish_tile(a, ps->pc, i0, end, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
     __syncthreads();
     stamp(a.dbg, 0, 4);
     if (seg < nseg) {
@@ -868,14 +980,12 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nwo
     __syncthreads();
     stamp(a.dbg, 0, 5);
   }
-  if (wid < ntiles) {
-    if (seg < nseg) ps->acc[seg * nout + o] = acc;
-    __syncthreads();
-    if (tid < nout) {
-      double s = 0.0;
-      for (int g = 0; g < nseg; ++g) s += ps->acc[g * nout + tid];
-      a.partials[(size_t)wid * LIO_BLOB + (a.extrinsic_est ? c_oe_ext[tid] : c_oe_no[tid])] = s;
-    }
+  if (seg < nseg) ps->acc[seg * nout + o] = acc;
+  __syncthreads();
+  if (tid < nout) {
+    double sum = 0.0;
+    for (int g = 0; g < nseg; ++g) sum += ps->acc[g * nout + tid];
+    st_stamped(a.partials + (size_t)wid * ROW_WORDS + 2 * tid, sum, target);  // outputs back to back
   }
   stamp(a.dbg, 0, 6);
 }
@@ -955,11 +1065,17 @@ struct HostPath {
   double P0[576];
 };
 
+// Workers: wait for the publication of step `target` (warp 0: one stamped word per lane, polled until its stamp shows
+// up -- data and flag arrive in the same word, one L2 round trip after the solver's store), rebuild the per-pass
+// constants from the 14 doubles, hand {converge, done} to the block.
+__device__ __forceinline__ void worker_receive(const SolveArgs& s, PassSmem* ps, unsigned target, int* flags_out,
+                                               int wid);
+
 // The whole update_iterated_dyn_share_modified loop (esekfom.hpp:270-346).  Cooperative launch: all blocks resident.
-// Blocks 0 .. gridDim-2 are WORKERS (h_share_model passes); the last block is the SOLVER: it keeps the filter state in
-// shared memory for the whole update, sums the workers' partial blobs as they arrive, performs the Kalman step and
-// publishes the constants of the next pass.  Flags are epoch stamps (target = epoch + pass + 1), so nothing has to be
-// zeroed between launches.
+// Blocks 0 .. gridDim-2 are WORKERS (h_share_model passes over their own chunk of the scan); the last block is the
+// SOLVER: it keeps the filter state in shared memory for the whole update, sums the workers' partial rows as they
+// arrive, performs the Kalman step (one warp) and publishes the new state.  Rows and publication are stamped words
+// (target = epoch + pass + 1): nothing is zeroed between launches and there is no fence on the per-pass path.
 // nblk / bid: size of the (sub-)grid that works on this update and this block's index in it -- the whole grid for a
 // single update, a slice of it when several independent sequences share one launch (update_kernel_multi).
 template <bool HOST>
@@ -986,11 +1102,8 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
       block_reduce_partials(a, search, nworkers, target, ss.blob, ss.warp_part);
       if (sh.world > 1) block_exchange(sh, sh.epoch + (unsigned)pass_no + 1u, pass_no, ss.blob);
       stamp(a.dbg, 128, 11);
-      block_solve(s, n, &ss);
+      block_step(s, n, &ss, target);
       stamp(a.dbg, 128, 12);
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release(&s.sync[1], target);
       search = ss.sc.converge != 0;
       if (ss.sc.done) break;
       __syncthreads();
@@ -1021,29 +1134,47 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
   bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
     const unsigned target = epoch + (unsigned)pass_no + 1u;
-    block_pass(a, search, &ps, nworkers, wid, pass_no == 0);
-    __syncthreads();  // the partial row is written; the release below (one thread) publishes the block's writes
-    if (tid == 0) {
-      __threadfence();
-      st_release(a.arrive + wid, target);
-      stamp(a.dbg, 0, 7);
-      while ((ld_acquire(&s.sync[1]) - target) >= 0x40000000u) {
-      }
-    }
-    __syncthreads();
-    // one round of loads: constants of the new state + loop flags
-    double* pcd = reinterpret_cast<double*>(&ps.pc);
-    double v = 0.0;
-    if (tid < 34) v = __ldcg(s.pub + tid);
-    if (tid < 32) pcd[tid] = v;
-    if (tid == 32) ps.cnt[0] = (int)v;  // converge -> search next
-    if (tid == 33) ps.cnt[1] = (int)v;  // done
+    block_pass(a, search, &ps, nworkers, wid, pass_no == 0, target);
+    stamp(a.dbg, 0, 7);
+    worker_receive(s, &ps, target, &ps.flag, wid);
     __syncthreads();
     stamp(a.dbg, 0, 8);
-    search = ps.cnt[0] != 0;
-    const bool done = ps.cnt[1] != 0;
-    __syncthreads();  // ps.cnt is reused by the next search tile
-    if (done) break;
+    const int fl = ps.flag;
+    search = (fl & 1) != 0;
+    __syncthreads();  // ps.flag / ps.pc are rewritten by the next round
+    if (fl & 2) break;
+  }
+}
+
+__device__ __forceinline__ void worker_receive(const SolveArgs& s, PassSmem* ps, unsigned target, int* flags_out,
+                                               int wid) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const unsigned long long* pub = s.pub + (wid % PUB_COPIES) * PUB_STRIDE;
+  // Uniform control flow only (see block_step on split warps): every lane watches its own word (232 bytes per round
+  // trip and block) and the warp leaves the loop together once all of them carry the stamp -- each word validates
+  // itself, so the order in which the solver's stores become visible does not matter.
+  unsigned long long w;
+  const int l = lane < PUB_WORDS ? lane : PUB_WORDS - 1;
+  bool ok;
+  do {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(pub + l) : "memory");
+    ok = (unsigned)(w >> 32) == target;
+  } while (!__all_sync(FULL, ok));
+  reinterpret_cast<unsigned*>(ps->xrecv)[l] = (unsigned)w;  // halves 0..27 are x[0..13]; word 28 lands in xrecv[14]'s low half
+  __syncwarp();
+  const double* x14 = ps->xrecv;
+  PassConst& pc = ps->pc;
+  if (lane == 0) {
+    pc.pos[0] = x14[0]; pc.pos[1] = x14[1]; pc.pos[2] = x14[2];
+    pc.rot = Quatd{x14[3], x14[4], x14[5], x14[6]};
+    quat_to_mat(pc.rot, pc.Rt);
+    *flags_out = (int)reinterpret_cast<const unsigned*>(ps->xrecv)[28];
+  }
+  if (lane == 1) {
+    pc.rli = Quatd{x14[7], x14[8], x14[9], x14[10]};
+    pc.tli[0] = x14[11]; pc.tli[1] = x14[12]; pc.tli[2] = x14[13];
+    quat_to_mat(pc.rli, pc.Rli);
   }
 }
 
@@ -1082,10 +1213,13 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_mult
 // One pass at the state in s.x; the last block to finish reduces the partials into s.blob (same worker split and
 // the same summation order as update_kernel, so the stepwise driver reproduces its bits).
 // mode: 0 cached, 1 search, -1 as the loop state says (sharded driver).
-__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const PassArgs a, const SolveArgs s, int mode) {
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const PassArgs a, const SolveArgs s, int mode,
+                                                                          unsigned target) {
   __shared__ PassSmem ps;
-  __shared__ double s_blob[LIO_BLOB];
-  __shared__ double s_warp[(THREADS / 32) * LIO_BLOB];
+  // the reduction of the last block runs after its pass: its scratch lies over the row staging area
+  static_assert(sizeof(ps.rows) >= sizeof(double) * (THREADS / 32) * LIO_BLOB && THREADS >= LIO_BLOB, "reduce scratch");
+  double* s_warp = ps.rows;
+  double* s_blob = ps.acc;
   const int tid = threadIdx.x;
   const int nworkers = (int)gridDim.x - 1;
   if (mode < 0 && s.ctrl->done) return;
@@ -1093,7 +1227,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
   if ((int)blockIdx.x < nworkers) {
     if (tid == 0) load_pass_const(s.x, ps.pc);
     __syncthreads();
-    block_pass(a, search, &ps, nworkers, (int)blockIdx.x, false);
+    block_pass(a, search, &ps, nworkers, (int)blockIdx.x, false, target);
   }
   __threadfence();
   __syncthreads();
@@ -1106,7 +1240,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
   if (ps.flag) {
     __threadfence();
     stamp(a.dbg, 128, 10);
-    block_reduce_partials(a, search, nworkers, 0u, s_blob, s_warp);
+    block_reduce_partials(a, search, nworkers, target, s_blob, s_warp);
     stamp(a.dbg, 128, 11);
     if (tid < LIO_BLOB) s.blob[tid] = s_blob[tid];
     if (tid == 0) s.sync[0] = 0;  // ready for the next pass launch
@@ -1114,13 +1248,13 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
 }
 
 // Kalman step from the blob in s.blob (already summed over ranks by the sharded driver).
-__global__ void __launch_bounds__(THREADS) solve_kernel(const SolveArgs s, int extrinsic_est) {
+__global__ void __launch_bounds__(THREADS) solve_kernel(const SolveArgs s, int extrinsic_est, unsigned target) {
   __shared__ SolveSmem ss;
   if (s.ctrl->done) return;
   solve_load_inputs(s, &ss);
   if (threadIdx.x < LIO_BLOB) ss.blob[threadIdx.x] = s.blob[threadIdx.x];
   __syncthreads();
-  block_solve(s, extrinsic_est ? 12 : 6, &ss);
+  block_step(s, extrinsic_est ? 12 : 6, &ss, target);
 }
 
 __global__ void __launch_bounds__(THREADS) begin_kernel(const SolveArgs s, int extrinsic_est) {
@@ -1317,7 +1451,6 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.own_min = own_min;
   a.own_max = own_max;
   a.partials = c->d_partials;
-  a.arrive = c->d_arrive;
   a.dbg = c->d_dbg;
   if (c->d_dbg) cudaMemsetAsync(c->d_dbg, 0, 256 * sizeof(long long), c->stream);
   return a;
@@ -1341,6 +1474,17 @@ static SolveArgs make_solve_args(lio_ctx* c, double R, int max_iter, int from_sn
   s.from_snapshot = from_snapshot;
   s.dbg = c->d_dbg;
   return s;
+}
+
+// Stamps are epoch + pass + 1 and only ever grow; long before they wrap (once in ~10^8 updates) every stamped word is
+// cleared (on `on`'s stream: the one the next launch of k's buffers goes to) and the count starts again.
+static int epoch_guard(lio_ctx* k, lio_ctx* on) {
+  if (k->epoch <= 0xF0000000u) return LIO_OK;
+  LIO_CHECK(on, cudaMemsetAsync(k->d_partials, 0, 8 * (size_t)ROW_WORDS * pass_grid_blocks(k), on->stream));
+  LIO_CHECK(on, cudaMemsetAsync(k->d_pub, 0, 8 * PUB_COPIES * PUB_STRIDE, on->stream));
+  LIO_CHECK(on, cudaMemsetAsync(k->d_sync, 0, 2 * sizeof(unsigned), on->stream));
+  k->epoch = 0;
+  return LIO_OK;
 }
 
 // The whole update as ONE cooperative launch.  own_min/own_max: ownership window of this rank (sharded map).
@@ -1384,11 +1528,7 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   }
   SolveArgs s = make_solve_args(c, R, max_iter, from_snapshot);
   // arrival / release flags are epoch stamps: nothing to zero between launches (wrap-around once in ~10^8 updates)
-  if (c->epoch > 0xF0000000u) {
-    LIO_CHECK(c, cudaMemsetAsync(c->d_arrive, 0, sizeof(unsigned) * 1024, c->stream));
-    LIO_CHECK(c, cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
-    c->epoch = 0;
-  }
+  if (const int re = epoch_guard(c, c)) return re;
   unsigned epoch = c->epoch;
   c->epoch += 40;  // > max_iter + 2
   void* args[] = {&a, &s, &epoch, &sh, &hp};
@@ -1409,11 +1549,7 @@ int launch_update_multi(lio_ctx* const* cs, int n, double R, int max_iter, int e
     lio_ctx* k = cs[q];
     m.a[q] = make_pass_args(k, ext, -INFINITY, INFINITY);
     m.s[q] = make_solve_args(k, R, max_iter, from_snapshot);
-    if (k->epoch > 0xF0000000u) {
-      LIO_CHECK(c, cudaMemsetAsync(k->d_arrive, 0, sizeof(unsigned) * 1024, c->stream));
-      LIO_CHECK(c, cudaMemsetAsync(k->d_sync, 0, 2 * sizeof(unsigned), c->stream));
-      k->epoch = 0;
-    }
+    if (const int re = epoch_guard(k, c)) return re;
     m.epoch[q] = k->epoch;
     k->epoch += 40;
   }
@@ -1431,7 +1567,8 @@ int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float ow
   PassArgs a = make_pass_args(c, extrinsic_est, own_min, own_max);
   SolveArgs s = make_solve_args(c, 0.0, 0, 0);
   LIO_CHECK(c, cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
-  pass_kernel<<<pass_grid_blocks(c), THREADS, 0, c->stream>>>(a, s, mode);
+  if (const int re = epoch_guard(c, c)) return re;
+  pass_kernel<<<pass_grid_blocks(c), THREADS, 0, c->stream>>>(a, s, mode, ++c->epoch);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());
   return LIO_OK;
@@ -1439,7 +1576,7 @@ int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float ow
 
 int launch_solve(lio_ctx* c, double R, int extrinsic_est) {
   SolveArgs s = make_solve_args(c, R, 0, 0);
-  solve_kernel<<<1, THREADS, 0, c->stream>>>(s, extrinsic_est);
+  solve_kernel<<<1, THREADS, 0, c->stream>>>(s, extrinsic_est, ++c->epoch);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());
   return LIO_OK;

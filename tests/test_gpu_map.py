@@ -146,7 +146,7 @@ def test_map_incremental_large_filter_size(ctx, orc, small_cfg):
     """filter_size_map so large (3 fs^2 > 5) that neighbours beyond sqrt(5) m can decide need_add: the rows are
     completed to the reference's five unbounded neighbours before the classification."""
     cfg = small_cfg
-    mp = cfg["map"][::6]  # thin map: most rows are short after the bounded search
+    mp = cfg["map"][::20]  # thin map: many rows are short after the bounded search
     ctx.map_build(_p4(mp))
     om = orc.Map(1.0)
     om.build(mp)

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 from agi_lidar_slam_b200 import _cabi  # noqa: E402
 
 TAGS = {1: "pass entry", 2: "pass const ready", 3: "search done", 4: "finish done", 5: "tile reduced", 6: "partial written",
-        7: "ticket taken", 8: "released", 10: "solver: start", 11: "solver: partials reduced", 12: "solver: solved", 20: "solve: inputs in smem", 21: "solve: inverse+boxminus done", 22: "solve: K, KH, dx done", 23: "solve: boxplus+ctrl done"}
+        7: "ticket taken", 8: "released", 10: "solver: start", 13: "solver: rows seen (warp 7)", 11: "solver: partials reduced", 12: "solver: solved", 20: "solve: start", 21: "solve: u = S^-1 v done", 22: "solve: dx done", 23: "solve: boxplus + ctrl done, state published"}
 
 
 def show(name, tl):
@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--cols", type=int, default=1024)
     ap.add_argument("--poses", type=int, default=4)
     ap.add_argument("--map-cell", type=float, default=1.5)
+    ap.add_argument("--pose", type=int, default=0)
     a = ap.parse_args()
     a.workload = "os1_128_2m"
     wl = bench.make_workload(a, 0)
@@ -45,7 +46,7 @@ def main():
     ctx = _cabi.Context(0, max_scan_points=max(1 << 18, a.rings * a.cols), max_down_points=100000,
                         max_map_points=max(1 << 21, int(len(mp) * 1.05)), map_cell=a.map_cell)
     ctx.map_build(np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1))
-    s = wl["scans"][0]
+    s = wl["scans"][a.pose]
     body, _, _ = ctx.scan_preprocess(s["scan"], None, None, wl["leaf"])
     print("M =", len(body))
     ctx.scan_upload(body)
