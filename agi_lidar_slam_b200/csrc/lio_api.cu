@@ -153,6 +153,10 @@ static int create_impl(lio_ctx* c) {
     c->no_zero_copy = !(env && atoi(env));
   }
   {
+    const char* env = getenv("LIO_STAGE_SEARCH");
+    c->stage_search = env && atoi(env);
+  }
+  {
     const char* env = getenv("LIO_TIMELINE");
     if (env && atoi(env)) {
       ALLOC(c->d_dbg, 256 * sizeof(long long));

@@ -44,6 +44,141 @@ struct TopK {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory staging of the neighbour cells of a query TILE (north_star (1)).  The scan arrives sorted by voxel, so
+// the queries of a tile are spatial neighbours and share most of the 27 cells each of them has to look at.  Per tile:
+//   1. every (query, neighbour cell) pair is entered into a cell SET in shared memory (open addressing on the packed
+//      cell key); the pair remembers its slot,
+//   2. one thread per distinct cell probes the map's hash table (one dependent round trip for the whole tile),
+//   3. the cell's bucket -- one contiguous run of float4 {x,y,z,id} in the point pool -- is brought into shared memory
+//      by ONE bulk asynchronous copy (cp.async.bulk, completion counted in bytes on an mbarrier): no registers, no
+//      per-point instructions, all copies of the tile in flight together,
+//   4. the searches of the tile then stream their candidates from shared memory.
+// Every distinct bucket crosses L2 -> SM once per tile instead of once per query that needs it.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ST_TILE = 64;     // queries per tile at most
+constexpr int ST_HASH = 2048;   // slots of the cell set (27 * ST_TILE = 1728 distinct cells at most)
+constexpr int ST_PTS = 4096;    // staged map points per tile (64 KB); a tile that needs more searches global memory
+constexpr uint32_t ST_FLAG = 0x80000000u;  // slot values with this bit index StageSmem::pts, the others the point pool
+struct __align__(16) StageSmem {
+  float4 pts[ST_PTS];
+  unsigned long long key[ST_HASH];  // packed cell key or LIO_EMPTY_KEY
+  uint32_t cell[ST_HASH];           // staged offset << 12 | count
+  uint16_t list[ST_HASH];           // the slots in use
+  uint16_t qslot[ST_TILE * 27];     // slot of every (query, neighbour cell) pair
+  unsigned long long mbar;          // mbarrier of the bulk copies: THREADS arrivals + the bytes in flight per tile
+  int n_list, n_pts, overflow, phase;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* mbar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* mbar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(mbar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(mbar)), "r"(parity)
+      : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `mbar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
+
+// Stages the neighbour cells of the tile's `cnt` queries (q[0 .. cnt): their FP32 p_world, filled and the block
+// synchronised by the caller).  Whole block.  On return (block synchronised) st->overflow says whether the tile fits; if not, nothing of
+// the staging may be used.
+template <int NT>
+__device__ __forceinline__ void stage_cells(const MapView& map, StageSmem* st, const float4* q, int cnt,
+                                            long long* dbg = nullptr) {
+  const int tid = threadIdx.x;
+  auto mark = [&](int tag) {  // LIO_TIMELINE instrumentation: last thread of block 0
+    if (dbg != nullptr && blockIdx.x == 0 && tid == NT - 1) {
+      const long long n = dbg[0];
+      if (n < 62) {
+        long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        dbg[1 + 2 * n] = tag;
+        dbg[2 + 2 * n] = t;
+        dbg[0] = n + 1;
+      }
+    }
+  };
+  mark(30);
+  // 1. the cell set
+#pragma unroll 1
+  for (int p = tid; p < cnt * 27; p += NT) {
+    const int qi = p / 27, c = p - qi * 27;
+    const float4 qv = q[qi];
+    const unsigned long long key = pack_cell(cell_coord(qv.x, map.inv_cell) + c % 3 - 1, cell_coord(qv.y, map.inv_cell) + (c / 3) % 3 - 1,
+                                             cell_coord(qv.z, map.inv_cell) + c / 9 - 1);
+    uint32_t h = hash64(key) & (ST_HASH - 1);
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&st->key[h], LIO_EMPTY_KEY, key);
+      if (prev == LIO_EMPTY_KEY) {
+        st->list[atomicAdd(&st->n_list, 1)] = (uint16_t)h;
+        break;
+      }
+      if (prev == key) break;
+      h = (h + 1) & (ST_HASH - 1);
+    }
+    st->qslot[p] = (uint16_t)h;
+  }
+  __syncthreads();
+  mark(31);
+  // 2. + 3. one thread per distinct cell: probe the map, reserve room, start the copy
+  uint32_t bytes = 0;
+  const int n_list = st->n_list;
+#pragma unroll 1
+  for (int e = tid; e < n_list; e += NT) {
+    const uint32_t h = st->list[e];
+    uint32_t start, count;
+    map_find(map, st->key[h], start, count);
+    uint32_t info = 0;
+    if (count > 0) {
+      const uint32_t off = (uint32_t)atomicAdd(&st->n_pts, (int)count);
+      if (off + count <= (uint32_t)ST_PTS && count < 4096u) {
+        info = (off << 12) | count;
+        bulk_g2s(&st->pts[off], map.pool + start, count * 16u, &st->mbar);
+        bytes += count * 16u;
+      } else {
+        st->overflow = 1;
+      }
+    }
+    st->cell[h] = info;
+  }
+  mark(32);
+  if (bytes)
+    mbar_arrive_expect_tx(&st->mbar, bytes);
+  else
+    mbar_arrive(&st->mbar);
+  mbar_wait(&st->mbar, (uint32_t)st->phase & 1u);
+  __syncthreads();
+  mark(33);
+  if (dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+    dbg[220] = st->n_list;
+    dbg[221] = st->n_pts;
+    dbg[222] = st->overflow;
+  }
+}
+
 // A group of G lanes (G = 8, 16 or 32, aligned inside a warp) calls this with the SAME query; `gl` is the lane's index
 // inside the group.  ALL 32 lanes of the warp must be here together (idle groups repeat a query): the shuffles below
 // use the full mask.
@@ -55,10 +190,13 @@ struct TopK {
 // time through the same code, the remaining cells of the (2*rings+1)^3 block whose box distance is within the bound.
 // The group then extracts the global top-5 with five rounds of redux.min on (d2 bits, id).
 // Outputs are group-uniform: out_key[r] (d2 bits << 32 | id; ~0 when fewer than r+1 found), out_slot[r].
+// With st != nullptr round 0 takes the candidates of the query's 27 cells from the tile's staging area (query qi of the
+// tile) instead of global memory; the slots it reports then carry ST_FLAG and index st->pts.
 template <int G>
 __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy, float qz, float max_d2, int rings,
                                           int gl, unsigned long long out_key[LIO_K],
-                                          uint32_t out_slot[LIO_K], long long* dbg = nullptr) {
+                                          uint32_t out_slot[LIO_K], long long* dbg = nullptr,
+                                          StageSmem* st = nullptr, int qi = 0) {
   constexpr int CPL = (27 + G - 1) / G;  // cells per lane and round
   auto mark = [&](int slot) {  // LIO_TIMELINE instrumentation: block 0 / thread 0 only
     if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -77,6 +215,20 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
   int nrounds = 1;
 #pragma unroll 1
   for (int round = 0; round < nrounds; ++round) {
+    if (round == 0 && st != nullptr) {
+      // staged round 0: the lane's cells of the 3x3x3 block, candidates from shared memory
+#pragma unroll 1
+      for (int c = gl; c < 27; c += G) {
+        const uint32_t info = st->cell[st->qslot[qi * 27 + c]];
+        const uint32_t off = info >> 12, n = info & 0xfffu;
+#pragma unroll 1
+        for (uint32_t j = 0; j < n; ++j) {
+          const float4 p = st->pts[off + j];
+          const uint32_t d = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
+          if (__float_as_int(p.w) >= 0 && d <= max_bits) top.insert(((unsigned long long)d << 32) | __float_as_uint(p.w), ST_FLAG | (off + j));
+        }
+      }
+    } else {
     unsigned long long key[CPL];
     uint32_t h[CPL];
     uint4 e[CPL];
@@ -182,6 +334,7 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+    }
     }
     if (round == 0) mark(242);
     if (round == 0 && rings > 1) {

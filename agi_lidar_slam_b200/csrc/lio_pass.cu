@@ -67,6 +67,7 @@ struct PassArgs {
   float max_d2, plane_thr;
   int rings;
   float own_min, own_max;
+  int stage;  // 1: the searches of a tile stage its neighbour cells in shared memory first (stage_cells)
   unsigned long long* partials;  // [workers][ROW_WORDS]: one row of stamped words per worker block (st_stamped)
   long long* dbg;    // optional timeline (LIO_TIMELINE=1): [0] = entries used by block 0, [1..] = (tag, globaltimer ns)
 };
@@ -123,6 +124,8 @@ __device__ __forceinline__ int scan_size(const PassArgs& a) {
 // The per-point arrays (neighbour cache, plane, selected, normvec, ...) are then private to one block for the whole
 // update, so no pass has to wait for another block's writes to become visible -- the only traffic between blocks is the
 // partial rows up and the new state down, both made of self-validating words (st_stamped / ld_stamped): no fences.
+// (Tiles dealt round-robin instead of contiguous chunks were tried for load balance -- tile costs differ by 3x between
+// open ground and cluttered corners -- and lost: 137 us against 124 us per update on the bench workload.)
 __device__ __forceinline__ int chunk_points(int M, int nworkers) {
   int c = (M + nworkers - 1) / nworkers;
   c = (c + 7) & ~7;
@@ -181,26 +184,28 @@ __device__ __forceinline__ void body_to_world(const PassConst& pc, const double 
 
 constexpr int SROWS_MAX = THREADS / 8;  // rows of a search tile at the smallest group size
 
-// Search phase of one tile: THREADS / G queries, one per G-lane group (esekfom.hpp:140).  The 5 neighbours go to
-// the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.
+// Search phase of one tile: its queries (at most THREADS / G), one per G-lane group (esekfom.hpp:140).  The 5 neighbours
+// go to the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.  With staging
+// on the caller has staged the tile's neighbour cells (stage_cells); use_stage says whether the tile fitted.
 template <int G>
 __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int i0, int end, float4* s_nb,
-                                         int* s_cnt, float4* s_body, const float4* body) {
+                                         int* s_cnt, float4* s_body, const float4* body, StageSmem* st, bool use_stage) {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int row = threadIdx.x / G;
   const int i_raw = i0 + row;
   const bool act = i_raw < end;  // group-uniform
-  const int i = act ? i_raw : end - 1;  // idle groups redo the last query: the whole warp stays together for the shuffles
+  const int qi = act ? row : end - 1 - i0;  // idle groups redo the last query: the whole warp stays together for the shuffles
+  const int i = i0 + qi;
   const float4 b = body[i];  // device copy, or the caller's pinned host buffer in pass 0 of the host-direct path
-  if (gl == 0) s_body[row] = b;
+  if (gl == 0 && act) s_body[row] = b;
   const double pb[3] = {b.x, b.y, b.z};
-  float pwx, pwy, pwz;
-  body_to_world(pc, pb, pwx, pwy, pwz);
+  float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+  body_to_world(pc, pb, qv.x, qv.y, qv.z);
   unsigned long long key[LIO_K];
   uint32_t slot[LIO_K];
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[239] = global_ns();
-  const int cnt = group_knn5<G>(a.map, pwx, pwy, pwz, a.max_d2, a.rings, gl, key, slot, a.dbg);
+  const int cnt = group_knn5<G>(a.map, qv.x, qv.y, qv.z, a.max_d2, a.rings, gl, key, slot, a.dbg, use_stage ? st : nullptr, qi);
   if (!act) return;
   // lanes 0..4 of the group fetch and publish one neighbour each
   if (gl < LIO_K) {
@@ -215,7 +220,7 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
     float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     float d = CUDART_INF_F;
     if (gl < cnt) {
-      v = __ldg(a.map.pool + sl);
+      v = (sl & ST_FLAG) ? st->pts[sl & ~ST_FLAG] : __ldg(a.map.pool + sl);
       d = __uint_as_float((uint32_t)(k >> 32));
     }
     s_nb[row * LIO_K + gl] = v;
@@ -228,7 +233,7 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
     const bool sel = (cnt < LIO_K) ? false : (d4 > 5.0f ? false : true);
     s_cnt[row] = sel ? 1 : 0;
     a.near_cnt[i] = cnt;
-    a.near_q[i] = make_float4(pwx, pwy, pwz, 0.f);
+    a.near_q[i] = make_float4(qv.x, qv.y, qv.z, 0.f);
   }
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[245] = global_ns();
 }
@@ -331,8 +336,8 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
 // memory, products accumulated by thread (output o, segment seg) over rows seg, seg + nseg, ... of every tile, then
 // the segments are combined in order and the block's partial blob is written to a.partials[blockIdx.x].
 struct PassSmem;
-__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid, bool first_pass,
-                           unsigned target);
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSmem* st, int nworkers, int wid,
+                           bool first_pass, unsigned target);
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -927,16 +932,23 @@ struct __align__(16) PassSmem {
   PassConst pc;
   int cnt[SROWS_MAX];            // gate 1 of the search phase
   float4 body_row[SROWS_MAX];    // the search tile's scan points, for its finish phase
+  float4 q[SROWS_MAX];           // ... and their FP32 p_world: the queries
   unsigned char valid[ROWS_MAX];
   double xrecv[15];  // worker_receive: the published x[0..13] and, in the low half of [14], the flags
   int flag;
 };
 
+static_assert(SROWS_MAX == ST_TILE, "a search tile is a staging tile");
+// dynamic shared memory of the pass / update kernels: {PassSmem | SolveSmem} then the staging area of the searches
+constexpr size_t SMEM_STAGE_OFF =
+    ((sizeof(PassSmem) > sizeof(SolveSmem) ? sizeof(PassSmem) : sizeof(SolveSmem)) + 127) & ~(size_t)127;
+constexpr size_t SMEM_PASS_BYTES = SMEM_STAGE_OFF + sizeof(StageSmem);  // with staging; SMEM_STAGE_OFF without
+static size_t pass_smem_bytes(const lio_ctx* c) { return c->stage_search ? SMEM_PASS_BYTES : SMEM_STAGE_OFF; }
 // ps->pc holds the per-pass constants (the caller loads or computes them and synchronises the block).
 // Worker `wid` of `nworkers` runs its chunk of the scan (chunk_points) and leaves its partial blob, stamped `target`, in
 // row wid of a.partials; a worker whose chunk is empty writes nothing (the reduction knows: workers_used).
-__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nworkers, int wid, bool first_pass,
-                           unsigned target) {
+__device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSmem* st, int nworkers, int wid,
+                           bool first_pass, unsigned target) {
   const int tid = threadIdx.x;
   const bool from_host = first_pass && a.body_src != nullptr;  // pass 0 always searches
   const float4* body = from_host ? a.body_src : a.body;
@@ -947,7 +959,6 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nwo
   if (beg >= M) return;  // block-uniform
   const int end = min(M, beg + C);
   const int G = pick_group(C);
-  const int rows = search ? THREADS / G : (C < ROWS_MAX ? C : ROWS_MAX);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   const int nseg = THREADS / nout;
   const int o = tid % nout, seg = tid / nout;
@@ -957,16 +968,43 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, int nwo
     cb = a.extrinsic_est ? c_ob_ext[o] : c_ob_no[o];
   }
   double acc = 0.0;
+  const int step = search ? THREADS / G : (C < ROWS_MAX ? C : ROWS_MAX);
 #pragma unroll 1
-  for (int i0 = beg; i0 < end; i0 += rows) {
+  for (int i0 = beg; i0 < end; i0 += step) {
+    const int rows = step;
     if (search) {
+      const int tend = min(end, i0 + step);
+      // the tile's queries (p_world, FP64 -> FP32) and, when staging, an empty cell set; the previous tile is done with
+      // the staging area
+      if (a.stage) {
+        for (int h = tid; h < ST_HASH; h += THREADS) st->key[h] = LIO_EMPTY_KEY;
+        if (tid == 0) {
+          st->n_list = 0;
+          st->n_pts = 0;
+          st->overflow = 0;
+        }
+      }
+      bool use_stage = false;
+      if (a.stage) {
+        if (tid < tend - i0) {  // the staging needs the queries first; search_tile recomputes the same bits
+          const float4 b = body[i0 + tid];
+          const double pb[3] = {b.x, b.y, b.z};
+          float pwx, pwy, pwz;
+          body_to_world(ps->pc, pb, pwx, pwy, pwz);
+          ps->q[tid] = make_float4(pwx, pwy, pwz, 0.f);
+        }
+        __syncthreads();
+        stage_cells<THREADS>(a.map, st, ps->q, tend - i0, a.dbg);
+        use_stage = st->overflow == 0;
+      }
       if (G == 32)
-        search_tile<32>(a, ps->pc, i0, end, ps->nb, ps->cnt, ps->body_row, body);
+        search_tile<32>(a, ps->pc, i0, tend, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       else if (G == 16)
-        search_tile<16>(a, ps->pc, i0, end, ps->nb, ps->cnt, ps->body_row, body);
+        search_tile<16>(a, ps->pc, i0, tend, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       else
-        search_tile<8>(a, ps->pc, i0, end, ps->nb, ps->cnt, ps->body_row, body);
+        search_tile<8>(a, ps->pc, i0, tend, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       __syncthreads();
+      if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
       stamp(a.dbg, 0, 3);
     }
     finish_tile(a, ps->pc, i0, end, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
@@ -1081,8 +1119,7 @@ __device__ __forceinline__ void worker_receive(const SolveArgs& s, PassSmem* ps,
 template <bool HOST>
 __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& s, const unsigned epoch,
                                             const ShardArgs& sh, const HostPath& hp, const int nblk, const int bid) {
-  __shared__ __align__(16) unsigned char smem_raw[sizeof(PassSmem) > sizeof(SolveSmem) ? sizeof(PassSmem)
-                                                                                        : sizeof(SolveSmem)];
+  extern __shared__ __align__(128) unsigned char smem_raw[];  // SMEM_PASS_BYTES
   const int tid = threadIdx.x;
   const int n = a.extrinsic_est ? 12 : 6;
   const int nworkers = nblk - 1;
@@ -1125,7 +1162,12 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
   }
   // ------------------------------------------------------------------ workers
   PassSmem& ps = *reinterpret_cast<PassSmem*>(smem_raw);
+  StageSmem* st = reinterpret_cast<StageSmem*>(smem_raw + SMEM_STAGE_OFF);
   const int wid = bid;
+  if (tid == 0 && a.stage) {  // (without staging the area is not even allocated)
+    mbar_init(&st->mbar, THREADS);
+    st->phase = 0;
+  }
   const StateD* x_first =
       (HOST && hp.use_param_prior) ? reinterpret_cast<const StateD*>(hp.x0) : (s.from_snapshot ? s.x0 : s.x);
   stamp(a.dbg, 0, 1);
@@ -1134,7 +1176,7 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
   bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
     const unsigned target = epoch + (unsigned)pass_no + 1u;
-    block_pass(a, search, &ps, nworkers, wid, pass_no == 0, target);
+    block_pass(a, search, &ps, st, nworkers, wid, pass_no == 0, target);
     stamp(a.dbg, 0, 7);
     worker_receive(s, &ps, target, &ps.flag, wid);
     __syncthreads();
@@ -1215,7 +1257,9 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_mult
 // mode: 0 cached, 1 search, -1 as the loop state says (sharded driver).
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const PassArgs a, const SolveArgs s, int mode,
                                                                           unsigned target) {
-  __shared__ PassSmem ps;
+  extern __shared__ __align__(128) unsigned char smem_raw[];  // SMEM_PASS_BYTES
+  PassSmem& ps = *reinterpret_cast<PassSmem*>(smem_raw);
+  StageSmem* st = reinterpret_cast<StageSmem*>(smem_raw + SMEM_STAGE_OFF);
   // the reduction of the last block runs after its pass: its scratch lies over the row staging area
   static_assert(sizeof(ps.rows) >= sizeof(double) * (THREADS / 32) * LIO_BLOB && THREADS >= LIO_BLOB, "reduce scratch");
   double* s_warp = ps.rows;
@@ -1225,9 +1269,15 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
   if (mode < 0 && s.ctrl->done) return;
   const bool search = mode < 0 ? (s.ctrl->converge != 0) : (mode != 0);
   if ((int)blockIdx.x < nworkers) {
-    if (tid == 0) load_pass_const(s.x, ps.pc);
+    if (tid == 0) {
+      load_pass_const(s.x, ps.pc);
+      if (a.stage) {
+        mbar_init(&st->mbar, THREADS);
+        st->phase = 0;
+      }
+    }
     __syncthreads();
-    block_pass(a, search, &ps, nworkers, (int)blockIdx.x, false, target);
+    block_pass(a, search, &ps, st, nworkers, (int)blockIdx.x, false, target);
   }
   __threadfence();
   __syncthreads();
@@ -1413,6 +1463,11 @@ int ensure_tables(lio_ctx* c) {
     for (int i = 0; i < 21; ++i) is_no[ne[i]] = 1;
     LIO_CHECK(c, cudaMemcpyToSymbol(c_is_no, is_no, 78));
   }
+  // the pass / update kernels carry {pass or solve state | staging area of the searches} in dynamic shared memory
+  const void* big[] = {(const void*)update_kernel, (const void*)update_kernel_host, (const void*)update_kernel_multi,
+                       (const void*)pass_kernel};
+  for (const void* f : big)
+    LIO_CHECK(c, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS_BYTES));
   if (c->device < 64) g_tables_ready[c->device] = true;
   return LIO_OK;
 }
@@ -1421,7 +1476,9 @@ int ensure_tables(lio_ctx* c) {
 int pass_grid_blocks(lio_ctx* c) {
   if (c->pass_grid > 0) return c->pass_grid;
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, update_kernel, THREADS, 0) != cudaSuccess || per_sm < 1)
+  cudaFuncSetAttribute((const void*)update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS_BYTES);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, update_kernel, THREADS, SMEM_PASS_BYTES) != cudaSuccess ||
+      per_sm < 1)
     per_sm = 1;
   if (per_sm > LIO_BLOCKS_PER_SM) per_sm = LIO_BLOCKS_PER_SM;
   c->pass_grid = per_sm * c->sm_count;
@@ -1450,6 +1507,7 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.rings = c->knn_rings;
   a.own_min = own_min;
   a.own_max = own_max;
+  a.stage = c->stage_search ? 1 : 0;
   a.partials = c->d_partials;
   a.dbg = c->d_dbg;
   if (c->d_dbg) cudaMemsetAsync(c->d_dbg, 0, 256 * sizeof(long long), c->stream);
@@ -1533,7 +1591,7 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   c->epoch += 40;  // > max_iter + 2
   void* args[] = {&a, &s, &epoch, &sh, &hp};
   LIO_CHECK(c, cudaLaunchCooperativeKernel(hd != nullptr ? (const void*)update_kernel_host : (const void*)update_kernel,
-                                           dim3(pass_grid_blocks(c)), dim3(THREADS), args, 0, c->stream));
+                                           dim3(pass_grid_blocks(c)), dim3(THREADS), args, pass_smem_bytes(c), c->stream));
   c->launches++;
   return LIO_OK;
 }
@@ -1555,7 +1613,7 @@ int launch_update_multi(lio_ctx* const* cs, int n, double R, int max_iter, int e
   }
   void* args[] = {&m};
   LIO_CHECK(c, cudaLaunchCooperativeKernel((const void*)update_kernel_multi, dim3(pass_grid_blocks(c)), dim3(THREADS),
-                                           args, 0, c->stream));
+                                           args, pass_smem_bytes(c), c->stream));
   c->launches++;
   return LIO_OK;
 }
@@ -1568,7 +1626,7 @@ int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float ow
   SolveArgs s = make_solve_args(c, 0.0, 0, 0);
   LIO_CHECK(c, cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
   if (const int re = epoch_guard(c, c)) return re;
-  pass_kernel<<<pass_grid_blocks(c), THREADS, 0, c->stream>>>(a, s, mode, ++c->epoch);
+  pass_kernel<<<pass_grid_blocks(c), THREADS, pass_smem_bytes(c), c->stream>>>(a, s, mode, ++c->epoch);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());
   return LIO_OK;

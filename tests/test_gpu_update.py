@@ -245,3 +245,24 @@ def test_multi_sequence_rejects_bad_arguments(ctx, orc, small_cfg):
             _cabi.update_enqueue_multi([ctx, other])  # empty map
     finally:
         other.close()
+
+
+def test_staged_search_equals_direct_search(orc, small_cfg, avia_cfg, monkeypatch):
+    """LIO_STAGE_SEARCH=1: the searches of a tile first bring the buckets of its distinct neighbour cells into shared
+    memory (cell set, one hash probe per distinct cell, one cp.async.bulk per bucket on an mbarrier) and search there.
+    Same candidates, same canonical (d2, id) order: the whole update must come out bit-identical, neighbour cache included."""
+    from agi_lidar_slam_b200 import _cabi
+
+    for cfg in (small_cfg, avia_cfg):
+        out = []
+        for stage in ("0", "1"):
+            monkeypatch.setenv("LIO_STAGE_SEARCH", stage)
+            with _cabi.Context(0, max_scan_points=1 << 18, max_down_points=100000, max_map_points=1 << 20) as c:
+                body, _ = _setup(c, cfg, orc)
+                x, P, nv, npass = c.update_scan(cfg["x_prior"], cfg["P"], 0.001, cfg["max_iter"], False)
+                nb = c.get_neighbors(len(body))
+                out.append((x, P, nv, npass, nb))
+        a, b = out
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2:4] == b[2:4]
+        for k in ("idx", "d2", "selected", "normvec", "world"):
+            assert np.array_equal(a[4][k].view(np.uint8), b[4][k].view(np.uint8)), k

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 from agi_lidar_slam_b200 import _cabi  # noqa: E402
 
 TAGS = {1: "pass entry", 2: "pass const ready", 3: "search done", 4: "finish done", 5: "tile reduced", 6: "partial written",
-        7: "ticket taken", 8: "released", 10: "solver: start", 13: "solver: rows seen (warp 7)", 11: "solver: partials reduced", 12: "solver: solved", 20: "solve: start", 21: "solve: u = S^-1 v done", 22: "solve: dx done", 23: "solve: boxplus + ctrl done, state published"}
+        7: "ticket taken", 8: "released", 30: "stage: queries ready", 31: "stage: cell set built", 32: "stage: probes done, copies issued", 33: "stage: copies landed", 10: "solver: start", 13: "solver: rows seen (warp 7)", 11: "solver: partials reduced", 12: "solver: solved", 20: "solve: start", 21: "solve: u = S^-1 v done", 22: "solve: dx done", 23: "solve: boxplus + ctrl done, state published"}
 
 
 def show(name, tl):
@@ -70,6 +70,8 @@ def main():
         tl = ctx.debug_timeline()
         if rep == 2:
             show("whole update (warm)", tl)
+    r = ctx.timeline_raw
+    print("   last staged tile of block 0: %d distinct cells, %d points, overflow %d" % (int(r[220]), int(r[221]), int(r[222])))
     print(ctx.state_download()[2:])
 
 
