@@ -220,6 +220,30 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_cub_tmp, c->cub_tmp_bytes + 16);
   ALLOC(c->d_prep_counters, 4 * 32);
   LIO_CHECK(c, cudaMemset(c->d_prep_counters, 0, 4 * 32));
+  {
+    // surf voxel filter: leaf hash (>= 2 slots per leaf the scan may have), point slots / segments, grid bitmap
+    lio::VoxelFilter& v = c->vf;
+    const uint32_t hs = pow2_at_least((uint64_t)k.max_down_points * 2);
+    v.hash_mask = hs - 1;
+    v.bitmap_bits = 1ull << 28;  // leaves of the scan's bounding grid (1024 x 1024 x 256 at most; PCL's own limit is 2^31)
+    ALLOC(v.key, 8 * (size_t)hs);
+    LIO_CHECK(c, cudaMemset(v.key, 0xFF, 8 * (size_t)hs));
+    uint32_t** z4[] = {&v.cnt, &v.fill, &v.off, &v.rank, &v.lin, &v.list};
+    for (uint32_t** pp : z4) {
+      ALLOC(*pp, 4 * (size_t)hs);
+      LIO_CHECK(c, cudaMemset(*pp, 0, 4 * (size_t)hs));
+    }
+    ALLOC(v.big, 4 * (N / 32 + 2));
+    ALLOC(v.slot, 4 * N);
+    ALLOC(v.seg, 4 * N);
+    ALLOC(v.bitmap, (size_t)(v.bitmap_bits / 8));
+    LIO_CHECK(c, cudaMemset(v.bitmap, 0, (size_t)(v.bitmap_bits / 8)));
+    ALLOC(v.sbcount, 4 * (size_t)(v.bitmap_bits >> 10));
+    LIO_CHECK(c, cudaMemset(v.sbcount, 0, 4 * (size_t)(v.bitmap_bits >> 10)));
+    ALLOC(v.sbprefix, 4 * (size_t)(v.bitmap_bits >> 10));
+    ALLOC(v.ctr, 4 * 8);
+    LIO_CHECK(c, cudaMemset(v.ctr, 0, 4 * 8));
+  }
 
   int rc = ensure_tables(c);
   if (rc) return rc;
@@ -275,7 +299,9 @@ void lio_destroy(lio_ctx* c) {
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_sorted_aux,  c->d_run_heads,   c->d_runs_status, c->d_runs_ticket,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
-                  c->d_prep_counters};
+                  c->d_prep_counters, c->vf.key,    c->vf.cnt,        c->vf.fill,       c->vf.off,        c->vf.rank,
+                  c->vf.lin,      c->vf.list,       c->vf.big,        c->vf.slot,       c->vf.seg,        c->vf.bitmap,
+                  c->vf.sbcount,  c->vf.sbprefix,   c->vf.ctr};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -567,9 +593,15 @@ static int preprocess_decode(lio_ctx* c, const int* h, int64_t* m) {
     c->err = "more occupied voxels than lio_caps.max_down_points";
     return LIO_E_CAPACITY;
   }
-  if (h[7] == 4) {
-    c->err = "voxel filter: a tile of the run scan never reported (internal error)";
-    return LIO_E_CUDA;
+  if (h[7] == 3) {
+    c->err = "VoxelGrid: leaf size too small for the scan extent (index would overflow)";
+    c->scan_m = 0;
+    if (m) *m = 0;
+    return LIO_E_VOXEL_RANGE;
+  }
+  if (h[7] == 5) {
+    c->err = "VoxelGrid: the scan's bounding grid has more than 2^28 leaves (leaf size too small for this extent)";
+    return LIO_E_VOXEL_RANGE;
   }
   c->scan_m = std::min<int64_t>(h[0], c->caps.max_down_points);
   if (m) *m = c->scan_m;

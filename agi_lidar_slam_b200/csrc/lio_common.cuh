@@ -80,6 +80,29 @@ __device__ __forceinline__ int map_find(const MapView& m, unsigned long long key
   }
 }
 
+// ---------------------------------------------------------------- surf voxel filter (pcl::VoxelGrid) working set
+// Hash of the occupied leaves of the current scan (key = packed absolute leaf index) with, per leaf, its point count,
+// its segment in the point-index array and its output rank; the rank comes from a bitmap over the scan's bounding grid
+// (one bit per leaf, a count per 1024-leaf superblock).  Everything is left clean by the last kernel of a scan.
+struct VoxelFilter {
+  unsigned long long* key;  // [hash_mask + 1]
+  uint32_t* cnt;            // points of the leaf
+  uint32_t* fill;           // ... of them placed in the segment so far
+  uint32_t* off;            // first entry of the leaf's segment in `seg`
+  uint32_t* rank;           // output position
+  uint32_t* lin;            // PCL's linear leaf index relative to the scan's minimum
+  uint32_t* list;           // [hash_mask + 1] hash slots of the occupied leaves, in order of creation
+  uint32_t* big;            // hash slots of the leaves a whole block will sum
+  uint32_t* slot;           // [max_scan_points] hash slot of every point's leaf
+  uint32_t* seg;            // [max_scan_points] point indices, leaf by leaf
+  uint32_t* bitmap;         // [bitmap_bits / 32]
+  uint32_t* sbcount;        // [bitmap_bits / 1024] occupied leaves per superblock
+  uint32_t* sbprefix;       // ... exclusive scan
+  int* ctr;                 // [0] leaves  [1] segment cursor  [2] long leaves  [3] block ticket
+  uint32_t hash_mask;
+  unsigned long long bitmap_bits;
+};
+
 // ---------------------------------------------------------------- FP64 rotation helpers (oracle op order)
 struct Quatd {
   double w, x, y, z;

@@ -87,6 +87,7 @@ struct lio_ctx {
   bool no_zero_copy = true;
 
   // ---- preprocess
+  lio::VoxelFilter vf{};            // working set of the surf voxel filter (lio_preprocess.cu)
   unsigned char* d_cloud = nullptr; // PointCloud2 bytes of the scan being decoded (allocated on first use)
   size_t cloud_bytes = 0;
   int64_t n_decoded = 0;

@@ -388,6 +388,7 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
 // the bounding box of the cells the map has ever used (MapView::counters[8..13]).  After shell r every unseen point is
 // farther than r * cell, so the search stops once the `need`-th best is closer than that, or the box is exhausted.
 // `need` = 1 ... 5 neighbours wanted (the stop rule only; the lanes always keep five).  Outputs as group_knn5.
+// To be called by blocks of ONE warp (it synchronises with __syncthreads).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k) {
 #pragma unroll
@@ -461,46 +462,77 @@ __device__ __noinline__ int warp_knn_far(const MapView& map, float qx, float qy,
     const int side = 2 * r + 1;
     const int n_face = side * side;
     const int n_cells = r == 0 ? 1 : 2 * n_face + (side - 2) * 8 * r;
+    // four cells per lane at a time: their first probes are issued together (the hash table is a dependent load each,
+    // and a shell of radius r has ~24 r^2 cells)
 #pragma unroll 1
-    for (int t = lane; t < n_cells; t += 32) {
-      int dx, dy, dz;
-      if (t < 2 * n_face || r == 0) {  // the two full faces dz = -r, +r
-        const int f = t >= n_face ? 1 : 0;
-        const int e = t - f * n_face;
-        dz = f ? r : -r;
-        dy = e / side - r;
-        dx = e % side - r;
-      } else {  // the perimeter of the layers in between: 8r cells each
-        const int e = t - 2 * n_face;
-        const int layer = e / (8 * r), o = e % (8 * r);
-        dz = -r + 1 + layer;
-        const int s = o / (2 * r), u = o % (2 * r);
-        dx = s == 0 ? -r + u : (s == 1 ? r : (s == 2 ? r - u : -r));
-        dy = s == 0 ? -r : (s == 1 ? -r + u : (s == 2 ? r : r - u));
+    for (int t0 = lane; t0 < n_cells; t0 += 4 * 32) {
+      unsigned long long ckey[4];
+      uint32_t hh[4];
+      uint4 ee[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + 32 * u;
+        ckey[u] = LIO_EMPTY_KEY;
+        hh[u] = 0;
+        ee[u] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+        if (t >= n_cells) continue;
+        int dx, dy, dz;
+        if (t < 2 * n_face || r == 0) {  // the two full faces dz = -r, +r
+          const int f = t >= n_face ? 1 : 0;
+          const int e = t - f * n_face;
+          dz = f ? r : -r;
+          dy = e / side - r;
+          dx = e % side - r;
+        } else {  // the perimeter of the layers in between: 8r cells each
+          const int e = t - 2 * n_face;
+          const int layer = e / (8 * r), o = e % (8 * r);
+          dz = -r + 1 + layer;
+          const int sd = o / (2 * r), uu = o % (2 * r);
+          dx = sd == 0 ? -r + uu : (sd == 1 ? r : (sd == 2 ? r - uu : -r));
+          dy = sd == 0 ? -r : (sd == 1 ? -r + uu : (sd == 2 ? r : r - uu));
+        }
+        const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+        if (x < lo[0] || x > hi[0] || y < lo[1] || y > hi[1] || z < lo[2] || z > hi[2]) continue;
+        if (kth != 0xFFFFFFFFu) {  // cell farther than the need-th best already: nothing in it can matter
+          const float lx = (float)x * map.cell, ly = (float)y * map.cell, lz = (float)z * map.cell;
+          const float ex = fmaxf(fmaxf(lx - qx, qx - (lx + map.cell)), 0.f);
+          const float ey = fmaxf(fmaxf(ly - qy, qy - (ly + map.cell)), 0.f);
+          const float ez = fmaxf(fmaxf(lz - qz, qz - (lz + map.cell)), 0.f);
+          if ((ex * ex + ey * ey + ez * ez) * 0.998f > __uint_as_float(kth)) continue;
+        }
+        ckey[u] = pack_cell(x, y, z);
+        hh[u] = hash64(ckey[u]) & map.hash_mask;
+        ee[u] = __ldg(reinterpret_cast<const uint4*>(map.table + hh[u]));
       }
-      const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
-      if (x < lo[0] || x > hi[0] || y < lo[1] || y > hi[1] || z < lo[2] || z > hi[2]) continue;
-      if (kth != 0xFFFFFFFFu) {  // cell farther than the need-th best already: nothing in it can matter
-        const float lx = (float)x * map.cell, ly = (float)y * map.cell, lz = (float)z * map.cell;
-        const float ex = fmaxf(fmaxf(lx - qx, qx - (lx + map.cell)), 0.f);
-        const float ey = fmaxf(fmaxf(ly - qy, qy - (ly + map.cell)), 0.f);
-        const float ez = fmaxf(fmaxf(lz - qz, qz - (lz + map.cell)), 0.f);
-        if ((ex * ex + ey * ey + ez * ez) * 0.998f > __uint_as_float(kth)) continue;
-      }
-      uint32_t start, count;
-      if (map_find(map, pack_cell(x, y, z), start, count) < 0) continue;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ckey[u] == LIO_EMPTY_KEY) continue;
+        uint32_t start = 0, count = 0;
+        for (;;) {
+          const unsigned long long k = ((unsigned long long)ee[u].y << 32) | ee[u].x;
+          if (k == ckey[u]) {
+            start = ee[u].z;
+            count = ee[u].w;
+            break;
+          }
+          if (k == LIO_EMPTY_KEY) break;
+          hh[u] = (hh[u] + 1) & map.hash_mask;
+          ee[u] = __ldg(reinterpret_cast<const uint4*>(map.table + hh[u]));
+        }
 #pragma unroll 1
-      for (uint32_t j = 0; j < count; ++j) {
-        const float4 p = __ldg(map.pool + start + j);
-        if (__float_as_int(p.w) < 0) continue;
-        const uint32_t d = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
-        top.insert(((unsigned long long)d << 32) | __float_as_uint(p.w), start + j);
+        for (uint32_t j = 0; j < count; ++j) {
+          const float4 p = __ldg(map.pool + start + j);
+          if (__float_as_int(p.w) < 0) continue;
+          const uint32_t d = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
+          top.insert(((unsigned long long)d << 32) | __float_as_uint(p.w), start + j);
+        }
       }
     }
-    __syncwarp();
+    __syncthreads();  // the block IS this warp: the barrier brings its lanes back together before the shuffles (a warp
+                      // left split by the loops above pays ~1,000 cycles per shuffle; __syncwarp does not mend that)
     kth = warp_kth_bits(top, need);
   }
-  __syncwarp();
+  __syncthreads();
   int found = 0;
 #pragma unroll
   for (int r = 0; r < LIO_K; ++r) {

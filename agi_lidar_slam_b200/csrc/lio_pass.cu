@@ -1374,14 +1374,12 @@ __global__ void far_list_kernel(const int* near_cnt, const int* scan_m, int m_va
   if (want) list[base + __popc(b & ((1u << lane) - 1u))] = i;
 }
 
-__global__ void __launch_bounds__(256) far_search_kernel(MapView map, const float4* q, const int* list, const int* n_list,
-                                                         int need, float4* near_pts, float* near_d2, int* near_cnt) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+__global__ void __launch_bounds__(32) far_search_kernel(MapView map, const float4* q, const int* list, const int* n_list,
+                                                        int need, float4* near_pts, float* near_d2, int* near_cnt) {
+  const int lane = threadIdx.x;  // one warp per block (warp_knn_far synchronises the block)
   const int n = *n_list;
 #pragma unroll 1
-  for (int w = warp; w < n; w += n_warps) {
+  for (int w = blockIdx.x; w < n; w += gridDim.x) {
     const int i = list[w];
     const float4 p = __ldg(q + i);
     unsigned long long key[LIO_K];
@@ -1407,6 +1405,7 @@ __global__ void __launch_bounds__(256) far_search_kernel(MapView map, const floa
       near_d2[(size_t)i * LIO_K + lane] = d;
     }
     if (lane == 0) near_cnt[i] = found;
+    __syncthreads();
   }
 }
 
@@ -1660,8 +1659,8 @@ int launch_far_complete(lio_ctx* c, const float4* d_q, int64_t m, int min_m, int
   far_list_kernel<<<(int)((bound + 255) / 256), 256, 0, c->stream>>>(c->d_near_cnt, c->d_scan_m, m >= 0 ? (int)m : -1,
                                                                       m >= 0 ? 0 : min_m, need, c->d_far_list,
                                                                       c->d_far_n);
-  const int grid = (int)std::min<int64_t>((bound + 7) / 8, (int64_t)c->sm_count * 8);
-  far_search_kernel<<<grid, 256, 0, c->stream>>>(c->map, d_q, c->d_far_list, c->d_far_n, need, c->d_near, c->d_near_d2,
+  const int grid = (int)std::min<int64_t>(bound, (int64_t)c->sm_count * 16);
+  far_search_kernel<<<grid, 32, 0, c->stream>>>(c->map, d_q, c->d_far_list, c->d_far_n, need, c->d_near, c->d_near_d2,
                                                  c->d_near_cnt);
   c->launches += 2;
   LIO_CHECK(c, cudaGetLastError());

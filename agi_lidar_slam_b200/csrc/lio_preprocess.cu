@@ -2,14 +2,20 @@
 //   ImuProcess::UndistortPcl back half (src/IMU_Processing.hpp:361-401): per-point motion compensation, FP64
 //   pcl::VoxelGrid<PointType>::filter (src/laserMapping.cpp:737-738, leaf :683): centroid per occupied leaf
 // The raw scan is read once: each point is compensated in registers, its voxel index is taken on the compensated
-// coordinates and the index bounds are reduced on the fly (one kernel).  The voxel filter then follows PCL's own
-// algorithm: linear leaf index relative to the cloud minimum, STABLE sort of (index, point)
-// pairs, one centroid per run of equal indices — with the FP32 sums taken in ascending point order, the order the
-// oracle defines (PCL's std::sort is unstable, so PCL itself leaves it open).  Sequential FP32 sums in a defined
-// order make the centroids BIT-EXACT against the oracle, and run-to-run deterministic, which the downstream
-// neighbour sets and validity gates need (the filter loop amplifies 1e-9 input differences to millimetres within
-// ten scans).  The only library call on the scan path is cub::DeviceRadixSort (the sensor decoders also
-// use cub::DeviceSelect / DeviceScan).
+// coordinates, the index bounds are reduced on the fly and the point is entered into a hash of occupied leaves (one
+// kernel).  What PCL gets from sorting all points by their linear leaf index is obtained without
+// a sort of the points:
+//   * the ORDER of the output (ascending leaf index = ascending (kz,ky,kx)) is a rank over the occupied leaves only: one
+//     bit per leaf of the scan's bounding grid, a count per 1024-leaf superblock, an exclusive scan over the superblocks;
+//     rank = superblock prefix + population count of the bits below;
+//   * the SUM ORDER inside a leaf is the oracle's, ascending point index (PCL's std::sort is unstable, so PCL itself
+//     leaves it open): the points of a leaf are scattered into the leaf's segment in whatever order the atomics give,
+//     and the (small) segment is then put in index order -- by its thread for up to 32 points, by a block-wide bitonic
+//     sort in shared memory for more -- before the sequential FP32 sums.
+// Sequential FP32 sums in a defined order make the centroids BIT-EXACT against the oracle and run-to-run deterministic,
+// which the downstream neighbour sets and validity gates need (the filter loop amplifies 1e-9 input differences to
+// millimetres within ten scans).  No library kernel on this path; the sensor decoders further down still use
+// cub::DeviceSelect / DeviceScan / DeviceRadixSort.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
@@ -24,6 +30,11 @@ namespace lio {
 
 #define MAX_POSES 128
 
+// ---- the leaf hash and the rank structures (device buffers of lio_ctx, see VoxelFilter in lio_ctx.cuh)
+constexpr uint32_t VF_SB_BITS = 10;     // leaves per superblock: 1024
+constexpr int VF_SMALL = 32;            // leaves up to this many points are ordered and summed by one thread
+constexpr int VF_BLOCK_SORT = 8192;     // ... up to this many by a block-wide bitonic sort; more: ordered sweep of the scan
+
 struct PrepArgs {
   const float4* raw;      // x,y,z,t_ms
   int n;
@@ -33,9 +44,13 @@ struct PrepArgs {
   float inv_leaf;
   float4* undist;         // n (x,y,z,t_ms)
   int* vkeys;             // n x 3 absolute voxel indices
-  int* counters;          // [0] M  [1..3] key min  [4..6] key max  [7] error
+  int* counters;          // [0] unused  [1..3] key min  [4..6] key max  [7] error
+  VoxelFilter vf;
+  int max_m;
 };
 
+// One thread per raw point: motion compensation, leaf index, index bounds, and the point's leaf in the leaf hash
+// (key = the packed absolute index; the threads of a warp that hit the same leaf send ONE probe and ONE count update).
 __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
   __shared__ lio_pose6d s_pose[MAX_POSES];
   for (int k = threadIdx.x; k < a.n_poses * 22; k += blockDim.x)
@@ -118,11 +133,42 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
   mxx = __reduce_max_sync(FULL, mxx);
   mxy = __reduce_max_sync(FULL, mxy);
   mxz = __reduce_max_sync(FULL, mxz);
-  // Six words of one L2 sector are the target: 4,096 warps sending their own atomics (or even just reading the words to
-  // filter them) queue up on that sector -- 75 % of this kernel's samples at 131 k points.  So the block reduces first
-  // and six of its threads send one atomic each: 3 k requests instead of 25 k.
-  __shared__ int s_red[6][8];
+  // the leaf of this point: the lanes that share a leaf elect one of them to probe the hash and to add their number
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool in_range = kx > -(1 << 20) && kx < (1 << 20) && ky > -(1 << 20) && ky < (1 << 20) && kz > -(1 << 20) &&
+                        kz < (1 << 20);  // 21 bits per axis in the packed key
+  const unsigned long long key = (act && in_range) ? pack_cell(kx, ky, kz) : (LIO_EMPTY_KEY - 1ull - (unsigned)lane);
+  const unsigned peers = __match_any_sync(FULL, key);
+  const int leader = __ffs(peers) - 1;
+  uint32_t h = 0xFFFFFFFFu;
+  if (act && in_range && lane == leader) {
+    h = hash64(key) & a.vf.hash_mask;
+    uint32_t probes = 0;
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&a.vf.key[h], LIO_EMPTY_KEY, key);
+      if (prev == LIO_EMPTY_KEY) {
+        a.vf.list[atomicAdd(&a.vf.ctr[0], 1)] = h;  // a new leaf (the list is as long as the hash)
+        break;
+      }
+      if (prev == key) break;
+      h = (h + 1) & a.vf.hash_mask;
+      if (++probes > a.vf.hash_mask) {
+        h = 0xFFFFFFFFu;
+        break;
+      }
+    }
+    if (h != 0xFFFFFFFFu) atomicAdd(&a.vf.cnt[h], (uint32_t)__popc(peers));
+  }
+  h = __shfl_sync(FULL, h, leader);
+  if (act) {
+    a.vf.slot[i] = h;
+    if (!in_range) atomicMax(&a.counters[7], 3);   // beyond any grid PCL could index: "leaf size too small"
+    else if (h == 0xFFFFFFFFu) atomicMax(&a.counters[7], 2);  // more leaves than the hash holds (> max_down_points)
+  }
+  // Six words of one L2 sector are the target of the bounds: 4,096 warps sending their own atomics (or even just reading
+  // the words to filter them) queue up on that sector -- 75 % of this kernel's samples at 131 k points.  So the block
+  // reduces first and six of its threads send one atomic each: 3 k requests instead of 25 k.
+  __shared__ int s_red[6][8];
   if (lane == 0) {
     s_red[0][warp] = mnx;
     s_red[1][warp] = mny;
@@ -145,284 +191,318 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
   }
 }
 
-// working counters of the first scan; afterwards centroid_kernel leaves them reset
-__global__ void prep_reset_kernel(int* counters) {
+// working counters of the first scan; afterwards the last kernel of the filter leaves them reset
+__global__ void prep_reset_kernel(int* counters, int* vf_ctr) {
   counters[0] = 0;
   counters[1] = counters[2] = counters[3] = 0x7fffffff;
   counters[4] = counters[5] = counters[6] = -0x7fffffff;
   counters[7] = 0;
+  for (int k = 0; k < 8; ++k) vf_ctr[k] = 0;
 }
 
-// PCL's linear leaf index ijk . (1, div_x, div_x div_y) relative to min_b; values = point index
-__global__ void linear_index_kernel(const int* vkeys, int n, int* counters, uint32_t* keys, uint32_t* vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void unpack_cell(unsigned long long key, int& x, int& y, int& z) {
+  x = (int)(key & 0x1FFFFF) - (1 << 20);
+  y = (int)((key >> 21) & 0x1FFFFF) - (1 << 20);
+  z = (int)((key >> 42) & 0x1FFFFF) - (1 << 20);
+}
+
+// One thread per occupied leaf: PCL's linear leaf index ijk . (1, div_x, div_x div_y) relative to min_b, its bit in the
+// grid bitmap and its superblock's count.  The guards: PCL's own ("leaf size too small": the index would overflow an
+// int -> output = input, reported as LIO_E_VOXEL_RANGE) and this implementation's bitmap capacity.
+__global__ void voxel_bits_kernel(VoxelFilter vf, int* counters) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_leaf = vf.ctr[0];
   const long long dx = (long long)counters[4] - counters[1] + 1, dy = (long long)counters[5] - counters[2] + 1,
                   dz = (long long)counters[6] - counters[3] + 1;
-  if (dx * dy * dz > 0x7fffffffLL) {  // "leaf size too small": PCL returns the input unchanged
-    if (i == 0) counters[7] = 3;
-    keys[i] = 0;
-    vals[i] = i;
+  if (counters[7] >= 2) return;
+  if (dx * dy * dz > 0x7fffffffLL) {
+    if (e == 0) counters[7] = 3;
     return;
   }
-  const long long lin = (long long)(vkeys[3 * i] - counters[1]) +
-                        dx * ((long long)(vkeys[3 * i + 1] - counters[2]) + dy * (long long)(vkeys[3 * i + 2] - counters[3]));
-  keys[i] = (uint32_t)lin;
-  vals[i] = (uint32_t)i;
+  if (dx * dy * dz > (long long)vf.bitmap_bits) {
+    if (e == 0) counters[7] = 5;
+    return;
+  }
+  if (e >= n_leaf) return;
+  const uint32_t h = vf.list[e];
+  int kx, ky, kz;
+  unpack_cell(vf.key[h], kx, ky, kz);
+  const uint32_t lin = (uint32_t)((long long)(kx - counters[1]) + dx * ((long long)(ky - counters[2]) + dy * (long long)(kz - counters[3])));
+  vf.lin[h] = lin;
+  atomicOr(&vf.bitmap[lin >> 5], 1u << (lin & 31));
+  atomicAdd(&vf.sbcount[lin >> VF_SB_BITS], 1u);
 }
 
-// Run heads + gather in one pass over the sorted order (what cub::DeviceSelect + a gather kernel did in three launches).
-// A tile of RT sorted positions per block: head flags (leaf index differs from its predecessor's), block scan, then the
-// tile's exclusive prefix by a decoupled look-back over the tiles before it -- each tile publishes {launch tag, state,
-// count} in one 64-bit word as soon as it knows its own count, a warp sums the published counts of up to 32 predecessors
-// per round until it meets one that already carries its inclusive prefix.  Tiles take their number from a ticket, so a
-// tile only ever waits for tiles that have already started.  Nothing is reset by the host between launches: words are
-// recognised by the launch tag, and the tile with the highest ticket puts the ticket counter back to zero.
-constexpr int RT = 2048;
-__global__ void __launch_bounds__(256) runs_gather_kernel(const uint32_t* keys, const uint32_t* vals, int n,
-                                                          const float4* undist, const float* aux, float4* sorted_pts,
-                                                          float* sorted_aux, int* heads, int* n_runs,
-                                                          unsigned long long* status, unsigned* ticket,
-                                                          unsigned tag, int* stalled) {
-  __shared__ int s_tile, s_prefix, s_warp[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
-  __syncthreads();
-  const int tile = s_tile;
-  const int j0 = tile * RT + tid * 8;
-  uint32_t k[8], prev = 0;
-  bool f[8];
-  int cnt = 0;
-  if (j0 < n) {
-    if (j0 + 8 <= n) {
-      const uint4 a = *reinterpret_cast<const uint4*>(keys + j0), b = *reinterpret_cast<const uint4*>(keys + j0 + 4);
-      k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
-    } else {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) k[u] = j0 + u < n ? keys[j0 + u] : 0u;
-    }
-    if (j0 > 0) prev = keys[j0 - 1];
-  }
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int j = j0 + u;
-    f[u] = j < n && (j == 0 || k[u] != (u ? k[u - 1] : prev));
-    cnt += f[u];
-  }
-  // block-exclusive scan of the per-thread counts
-  int inc = cnt;
+// Exclusive scan of the superblock counts (one block; the grid of a scan has a few ten thousand superblocks).
+__global__ void __launch_bounds__(1024) voxel_scan_kernel(VoxelFilter vf, const int* counters) {
+  __shared__ uint32_t s_w[32];
+  if (counters[7] >= 2) return;
+  const long long cells = ((long long)counters[4] - counters[1] + 1) * ((long long)counters[5] - counters[2] + 1) *
+                          ((long long)counters[6] - counters[3] + 1);
+  const int n_sb = vf.ctr[0] > 0 ? (int)((cells + (1 << VF_SB_BITS) - 1) >> VF_SB_BITS) : 0;
+  const int per = (n_sb + 1023) / 1024;  // the same trip count for every thread: the shuffles below want the warp whole
+  const int lo = (int)threadIdx.x * per;
+  uint32_t sum = 0;
+  for (int k = 0; k < per; ++k) sum += (lo + k < n_sb) ? vf.sbcount[lo + k] : 0u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = sum;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, off);
-    if (lane >= off) inc += t;
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+    inc += lane >= off ? t : 0u;
   }
-  if (lane == 31) s_warp[warp] = inc;
+  if (lane == 31) s_w[warp] = inc;
   __syncthreads();
-  int warp_base = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    if (w < warp) warp_base += s_warp[w];
-    total += s_warp[w];
-  }
-  int local = warp_base + inc - cnt;
-  // word = tag << 32 | state << 30 | count, state 1 = the tile's own count, 2 = inclusive prefix.  The own count goes out
-  // first, then the tile does its gather (independent of the prefix) while the other tiles publish theirs.
-  const unsigned long long mine = ((unsigned long long)tag << 32);
-  if (tid == 0)
-    *reinterpret_cast<volatile unsigned long long*>(status + tile) =
-        mine | ((tile == 0 ? 2ull : 1ull) << 30) | (unsigned)total;
-  // gather into sorted order: the runs become contiguous, so the sequential sums of centroid_kernel stream memory
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int j = j0 + u;
-    if (j < n) {
-      const uint32_t i = vals[j];
-      sorted_pts[j] = __ldg(undist + i);
-      if (aux) sorted_aux[j] = __ldg(aux + i);
-    }
-  }
-  // look-back (warp 0)
   if (warp == 0) {
-    int prefix = 0;
-    for (int p = tile - 1;; p -= 32) {
-      const int idx = p - lane;
-      unsigned st = 2, val = 0;  // before tile 0: an inclusive prefix of nothing
-      if (idx >= 0) {
-        unsigned long long w;
-        unsigned spins = 0;
-        do {
-          w = *reinterpret_cast<volatile unsigned long long*>(status + idx);
-        } while (((unsigned)(w >> 32) != tag || (((unsigned)w >> 30) & 3u) == 0) && ++spins < (1u << 20));
-        if (spins >= (1u << 20)) {  // cannot happen with a healthy launch; never hang the device over it
-          *stalled = 1;
-          w = ((unsigned long long)tag << 32) | (2ull << 30);
-        }
-        st = ((unsigned)w >> 30) & 3u;
-        val = (unsigned)w & 0x3fffffffu;
-      }
-      const unsigned pm = __ballot_sync(0xffffffffu, st == 2);
-      const int first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor that already knows its inclusive prefix
-      int v = lane <= first ? (int)val : 0;
+    uint32_t v = s_w[lane];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      prefix += v;
-      if (pm) break;
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, off);
+      v += lane >= off ? t : 0u;
     }
-    if (lane == 0) {
-      if (tile > 0)
-        *reinterpret_cast<volatile unsigned long long*>(status + tile) = mine | (2ull << 30) | (unsigned)(prefix + total);
-      s_prefix = prefix;
-    }
+    s_w[lane] = v;
   }
   __syncthreads();
-  const int base = s_prefix;
-#pragma unroll
-  for (int u = 0; u < 8; ++u)
-    if (f[u]) heads[base + local++] = j0 + u;
-  if (tid == 0 && tile == (n + RT - 1) / RT - 1) {
-    *n_runs = base + total;
-    *ticket = 0;  // every ticket of this launch has been handed out (this is the highest): ready for the next launch
-  }
+  uint32_t run = (warp ? s_w[warp - 1] : 0u) + inc - sum;
+  for (int k = 0; k < per; ++k)
+    if (lo + k < n_sb) {
+      const uint32_t c = vf.sbcount[lo + k];
+      vf.sbprefix[lo + k] = run;
+      run += c;
+    }
 }
 
-// One run of equal leaf indices per thread: FP32 sums in sorted (= ascending point) order, then / count.  The order
-// is sequential by definition (bit parity with the oracle), so a run cannot be split; what can be done is to keep its
-// adds fed and to keep long runs out of each other's way.  Runs are dealt to the threads warp-first (run m -> warp
-// m % n_warps, lane m / n_warps): neighbouring leaves -- a wall next to the sensor puts thousands of points into each of
-// a few dozen consecutive leaves -- land in different warps instead of queueing up in one.  Short runs: the owning
-// thread streams its points eight loads at a time.  Long runs: the WARP takes them one after the other -- all lanes
-// stage 256 points into shared memory with coalesced loads (the next stage's loads are in flight during the sums), then
-// lanes 0-4 run the five component sums (x, y, z, time, intensity) as five independent sequential chains.
-constexpr int LONG_RUN = 96;
-constexpr int STAGE = 256;
-__global__ void __launch_bounds__(128) centroid_kernel(const float4* sorted_pts, const float* sorted_aux,
-                                                       const int* heads, const int* n_runs, int n, int max_m,
-                                                       float4* body, float* body_time, int* scan_m, int* counters) {
-  __shared__ __align__(16) float s_stage[4][5][STAGE];
-  const int Mtot = *n_runs;
-  const int M = Mtot > max_m ? max_m : Mtot;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_warps = gridDim.x * (blockDim.x >> 5);
-  const int m = lane * n_warps + blockIdx.x * (blockDim.x >> 5) + warp;
-  if (m == 0) {
-    // the last kernel of the preprocessing files this scan's counters as the report the host reads (counters[16..23])
-    // and leaves the working set reset for the next scan -- what a one-thread reset kernel used to do before every scan
-    int err = counters[7];
-    if (counters[14]) {  // runs_gather_kernel gave up waiting for a tile: the run heads are not to be trusted
-      err = 4;
-      counters[14] = 0;
-    }
-    *scan_m = err >= 3 ? 0 : M;
-    if (Mtot > max_m && err == 0) err = 2;  // more voxels than lio_caps.max_down_points
-    counters[16] = Mtot;
-#pragma unroll
-    for (int k = 1; k < 7; ++k) counters[16 + k] = counters[k];
-    counters[23] = err;
-    counters[0] = 0;
-    counters[1] = counters[2] = counters[3] = 0x7fffffff;
-    counters[4] = counters[5] = counters[6] = -0x7fffffff;
-    counters[7] = 0;
+// One thread per occupied leaf: its output position (rank among the occupied leaves in index order), its segment in the
+// point-index array, and -- for the long ones -- a place in the list of leaves a whole block will take.
+__global__ void voxel_offsets_kernel(VoxelFilter vf, const int* counters) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (counters[7] >= 2 || e >= vf.ctr[0]) return;
+  const uint32_t h = vf.list[e];
+  const uint32_t lin = vf.lin[h];
+  uint32_t rank = vf.sbprefix[lin >> VF_SB_BITS];
+  for (uint32_t w = (lin >> VF_SB_BITS) << (VF_SB_BITS - 5); w < (lin >> 5); ++w) rank += (uint32_t)__popc(vf.bitmap[w]);
+  rank += (uint32_t)__popc(vf.bitmap[lin >> 5] & ((1u << (lin & 31)) - 1u));
+  const uint32_t c = vf.cnt[h];
+  const bool big = c > (uint32_t)VF_SMALL;
+  vf.rank[h] = rank | (big ? 0x80000000u : 0u);  // the flag says who sums the leaf (its count is cleared by whoever does)
+  vf.off[h] = (uint32_t)atomicAdd(&vf.ctr[1], (int)c);
+  if (big) vf.big[atomicAdd(&vf.ctr[2], 1)] = h;
+}
+
+// One thread per point: its index into its leaf's segment (the lanes of a warp that share a leaf take their places with
+// one atomic; the order inside the segment is whatever comes -- voxel_centroid_kernel puts it right).
+__global__ void __launch_bounds__(256) voxel_scatter_kernel(VoxelFilter vf, const int* counters, int n) {
+  if (counters[7] >= 2) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t h = i < n ? vf.slot[i] : 0xFFFFFFF0u - (uint32_t)lane;
+  const unsigned peers = __match_any_sync(0xffffffffu, h);
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (i < n && lane == leader) base = atomicAdd(&vf.fill[h], (uint32_t)__popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (i < n) vf.seg[vf.off[h] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;
+}
+
+struct CentroidArgs {
+  VoxelFilter vf;
+  const float4* undist;   // x,y,z,t_ms in input order
+  const float* aux;       // intensity in input order, or nullptr
+  int n, max_m;
+  float4* body;           // centroid x,y,z + mean intensity, in leaf-index order
+  float* body_time;       // mean time
+  int* scan_m;
+  int* counters;
+};
+
+// Leaves a leaf's hash entry, bit and counts as the next scan expects to find them.
+__device__ __forceinline__ void leaf_cleanup(const VoxelFilter& vf, uint32_t h, bool has_lin) {
+  if (has_lin) {
+    const uint32_t lin = vf.lin[h];
+    vf.bitmap[lin >> 5] = 0u;
+    vf.sbcount[lin >> VF_SB_BITS] = 0u;
   }
-  int beg = 0, end = 0;
-  if (m < M) {
-    beg = heads[m];
-    end = (m + 1 < Mtot) ? heads[m + 1] : n;
-  }
-  const bool is_long = (end - beg) >= LONG_RUN;
-  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f, st = 0.f;
-  if (m < M && !is_long) {
-    int j = beg;
-    for (; j + 8 <= end; j += 8) {
-      float4 p[8];
-      float q[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        p[u] = __ldg(sorted_pts + j + u);
-        q[u] = sorted_aux ? __ldg(sorted_aux + j + u) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        sx = sx + p[u].x;
-        sy = sy + p[u].y;
-        sz = sz + p[u].z;
-        st = st + p[u].w;
-        si = si + q[u];
-      }
-    }
-    for (; j < end; ++j) {
-      const float4 p = __ldg(sorted_pts + j);
-      sx = sx + p.x;
-      sy = sy + p.y;
-      sz = sz + p.z;
-      st = st + p.w;
-      if (sorted_aux) si = si + __ldg(sorted_aux + j);
-    }
-  }
-  // long runs of this warp, one at a time
-  unsigned todo = __ballot_sync(0xffffffffu, m < M && is_long);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int rb = __shfl_sync(0xffffffffu, beg, src), re = __shfl_sync(0xffffffffu, end, src);
-    float acc = 0.f;  // lane c < 5: running sum of component c
-    float4 pre[STAGE / 32];
-    float preq[STAGE / 32];
-#pragma unroll
-    for (int u = 0; u < STAGE / 32; ++u) {
-      const int j = rb + lane + 32 * u;
-      pre[u] = j < re ? __ldg(sorted_pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      preq[u] = (sorted_aux && j < re) ? __ldg(sorted_aux + j) : 0.f;
-    }
-    for (int base = rb; base < re; base += STAGE) {
-      const int cnt = min(STAGE, re - base);
-      __syncwarp();
-#pragma unroll
-      for (int u = 0; u < STAGE / 32; ++u) {
-        const int t = lane + 32 * u;
-        s_stage[warp][0][t] = pre[u].x;
-        s_stage[warp][1][t] = pre[u].y;
-        s_stage[warp][2][t] = pre[u].z;
-        s_stage[warp][3][t] = pre[u].w;
-        s_stage[warp][4][t] = preq[u];
-      }
-      __syncwarp();
-      if (base + STAGE < re) {
-#pragma unroll
-        for (int u = 0; u < STAGE / 32; ++u) {
-          const int j = base + STAGE + lane + 32 * u;
-          pre[u] = j < re ? __ldg(sorted_pts + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          preq[u] = (sorted_aux && j < re) ? __ldg(sorted_aux + j) : 0.f;
+  vf.key[h] = LIO_EMPTY_KEY;
+  vf.cnt[h] = 0u;
+  vf.fill[h] = 0u;
+}
+
+// Centroids.  The first half of the grid takes the long leaves (one block each: indices into shared memory, bitonic
+// sort, then five lanes run the five component sums as sequential chains over points the other threads stage 256 at a
+// time), the second half the short ones (one thread each, the <= 32 indices in registers).  The last block to finish
+// files the scan's counters for the host and resets the working set.
+constexpr int VF_CENTROID_SMEM = (VF_BLOCK_SORT + 5 * 256) * 4 + 64;  // dynamic: index area + point stage
+__global__ void __launch_bounds__(256) voxel_centroid_kernel(const CentroidArgs a) {
+  extern __shared__ __align__(16) unsigned char vf_smem[];
+  uint32_t* s_idx = reinterpret_cast<uint32_t*>(vf_smem);                       // [VF_BLOCK_SORT]
+  float(*s_stage)[256] = reinterpret_cast<float(*)[256]>(vf_smem + 4 * VF_BLOCK_SORT);  // [5][256]
+  __shared__ int s_flag;
+  __shared__ int s_cnt8[8];
+  const VoxelFilter& vf = a.vf;
+  const int tid = threadIdx.x;
+  const int err = a.counters[7];
+  const bool ok = err < 2;            // 2: too many leaves, 3: PCL's overflow guard, 5: bitmap capacity
+  const int n_leaf_all = vf.ctr[0];  // every leaf is in the list (and has to be cleaned up), at most max_m come out
+  const int n_leaf = min(n_leaf_all, a.max_m);
+  const int half = (int)gridDim.x / 2;
+  if (ok && (int)blockIdx.x < half) {
+    // ---- long leaves
+    const int n_big = vf.ctr[2];
+    for (int e = blockIdx.x; e < n_big; e += half) {
+      const uint32_t h = vf.big[e];
+      const uint32_t c = vf.cnt[h], off = vf.off[h];
+      float acc = 0.f;  // lane k < 5 of warp 0: running sum of component k
+      if (c <= (uint32_t)VF_BLOCK_SORT) {
+        uint32_t np = 64;
+        while (np < c) np <<= 1;
+        for (uint32_t k = tid; k < np; k += 256) s_idx[k] = k < c ? vf.seg[off + k] : 0xFFFFFFFFu;
+        __syncthreads();
+        for (uint32_t size = 2; size <= np; size <<= 1)
+          for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (np >> 1); t += 256) {
+              const uint32_t lo = 2 * t - (t & (stride - 1));  // the t-th pair of this stage
+              const uint32_t hi = lo + stride;
+              const bool up = (lo & size) == 0;
+              const uint32_t x = s_idx[lo], y = s_idx[hi];
+              if ((x > y) == up) {
+                s_idx[lo] = y;
+                s_idx[hi] = x;
+              }
+            }
+            __syncthreads();
+          }
+        for (uint32_t base = 0; base < c; base += 256) {
+          const uint32_t m = min(256u, c - base);
+          if ((uint32_t)tid < m) {
+            const uint32_t i = s_idx[base + tid];
+            const float4 p = __ldg(a.undist + i);
+            s_stage[0][tid] = p.x;
+            s_stage[1][tid] = p.y;
+            s_stage[2][tid] = p.z;
+            s_stage[3][tid] = p.w;
+            s_stage[4][tid] = a.aux ? __ldg(a.aux + i) : 0.f;
+          }
+          __syncthreads();
+          if (tid < 5) {
+            const float* v = s_stage[tid];
+            uint32_t t = 0;
+            for (; t + 4 <= m; t += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(v + t);
+              acc = acc + w.x;
+              acc = acc + w.y;
+              acc = acc + w.z;
+              acc = acc + w.w;
+            }
+            for (; t < m; ++t) acc = acc + v[t];
+          }
+          __syncthreads();
+        }
+      } else {
+        // more points in ONE leaf than the sort area holds: sweep the scan in point order, 256 points at a time, and add
+        // the members as they come (same order, no sort; cost is a pass over the slot array per such leaf)
+        for (int base = 0; base < a.n; base += 256) {
+          const int i = base + tid;
+          const bool mine = i < a.n && vf.slot[i] == h;
+          const unsigned b = __ballot_sync(0xffffffffu, mine);
+          if ((tid & 31) == 0) s_cnt8[tid >> 5] = __popc(b);
+          __syncthreads();
+          int pos = __popc(b & ((1u << (tid & 31)) - 1u)), m = 0;
+          for (int w = 0; w < 8; ++w) {
+            if (w < (tid >> 5)) pos += s_cnt8[w];
+            m += s_cnt8[w];
+          }
+          if (mine) {
+            const float4 p = __ldg(a.undist + i);
+            s_stage[0][pos] = p.x;
+            s_stage[1][pos] = p.y;
+            s_stage[2][pos] = p.z;
+            s_stage[3][pos] = p.w;
+            s_stage[4][pos] = a.aux ? __ldg(a.aux + i) : 0.f;
+          }
+          __syncthreads();
+          if (tid < 5) {
+            const float* v = s_stage[tid];
+            for (int t = 0; t < m; ++t) acc = acc + v[t];
+          }
+          __syncthreads();
         }
       }
-      if (lane < 5) {
-        const float* v = s_stage[warp][lane];
-        int t = 0;
-        for (; t + 16 <= cnt; t += 16) {
-          const float4 w0 = *reinterpret_cast<const float4*>(v + t), w1 = *reinterpret_cast<const float4*>(v + t + 4),
-                       w2 = *reinterpret_cast<const float4*>(v + t + 8), w3 = *reinterpret_cast<const float4*>(v + t + 12);
-          acc = acc + w0.x; acc = acc + w0.y; acc = acc + w0.z; acc = acc + w0.w;
-          acc = acc + w1.x; acc = acc + w1.y; acc = acc + w1.z; acc = acc + w1.w;
-          acc = acc + w2.x; acc = acc + w2.y; acc = acc + w2.z; acc = acc + w2.w;
-          acc = acc + w3.x; acc = acc + w3.y; acc = acc + w3.z; acc = acc + w3.w;
+      if (tid < 5) s_stage[tid][0] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        const float fc = (float)c;
+        const uint32_t r = vf.rank[h] & 0x7fffffffu;
+        if (r < (uint32_t)a.max_m) {
+          a.body[r] = make_float4(s_stage[0][0] / fc, s_stage[1][0] / fc, s_stage[2][0] / fc, s_stage[4][0] / fc);
+          if (a.body_time) a.body_time[r] = s_stage[3][0] / fc;
         }
-        for (; t < cnt; ++t) acc = acc + v[t];
+        leaf_cleanup(vf, h, true);
       }
+      __syncthreads();
     }
-    const float rx = __shfl_sync(0xffffffffu, acc, 0), ry = __shfl_sync(0xffffffffu, acc, 1),
-                rz = __shfl_sync(0xffffffffu, acc, 2), rt = __shfl_sync(0xffffffffu, acc, 3),
-                ri = __shfl_sync(0xffffffffu, acc, 4);
-    if (lane == src) {
-      sx = rx;
-      sy = ry;
-      sz = rz;
-      st = rt;
-      si = ri;
+  } else {
+    // ---- short leaves (and, after an error, the clean-up of every leaf)
+    const int nthr = ((int)gridDim.x - half) * 256;
+    for (int e = ((int)blockIdx.x - half) * 256 + tid; e < n_leaf_all; e += nthr) {
+      const uint32_t h = vf.list[e];
+      if (ok && (vf.rank[h] & 0x80000000u)) continue;  // a block takes it
+      const uint32_t c = vf.cnt[h];
+      if (ok) {
+        const uint32_t off = vf.off[h];
+        float sx = 0.f, sy = 0.f, sz = 0.f, st = 0.f, si = 0.f;
+        // the leaf's indices stay in registers (fully unrolled); the next point in index order is the smallest index above
+        // the last one: 32 compares per step and no memory in that chain, so the point loads of consecutive steps overlap
+        // and only the additions are sequential
+        uint32_t last = 0;
+        uint32_t v[VF_SMALL];
+#pragma unroll
+        for (int j = 0; j < VF_SMALL; ++j) v[j] = (uint32_t)j < c ? vf.seg[off + j] : 0xFFFFFFFFu;
+#pragma unroll 1
+        for (uint32_t k = 0; k < c; ++k) {
+          uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+          for (int j = 0; j < VF_SMALL; ++j) {
+            const bool take = (k == 0 || v[j] > last) && v[j] < best;
+            best = take ? v[j] : best;
+          }
+          last = best;
+          const float4 p = __ldg(a.undist + best);
+          sx = sx + p.x;
+          sy = sy + p.y;
+          sz = sz + p.z;
+          st = st + p.w;
+          if (a.aux) si = si + __ldg(a.aux + best);
+        }
+        const float fc = (float)c;
+        const uint32_t r = vf.rank[h];
+        if (r < (uint32_t)a.max_m) {
+          a.body[r] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+          if (a.body_time) a.body_time[r] = st / fc;
+        }
+      }
+      leaf_cleanup(vf, h, ok);
     }
   }
-  if (m >= M) return;
-  const float cnt = (float)(end - beg);
-  body[m] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
-  if (body_time) body_time[m] = st / cnt;
+  // ---- the last block files the scan's counters as the report the host reads (counters[16..23]) and leaves the working
+  // set reset for the next scan
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(&vf.ctr[3], 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_flag && tid == 0) {
+    int e2 = err;
+    if (n_leaf_all > a.max_m && e2 == 0) e2 = 2;  // more voxels than lio_caps.max_down_points
+    *a.scan_m = err >= 2 ? 0 : n_leaf;
+    a.counters[16] = n_leaf_all;
+#pragma unroll
+    for (int k = 1; k < 7; ++k) a.counters[16 + k] = a.counters[k];
+    a.counters[23] = e2;
+    a.counters[0] = 0;
+    a.counters[1] = a.counters[2] = a.counters[3] = 0x7fffffff;
+    a.counters[4] = a.counters[5] = a.counters[6] = -0x7fffffff;
+    a.counters[7] = 0;
+    vf.ctr[0] = vf.ctr[1] = vf.ctr[2] = vf.ctr[3] = 0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -645,7 +725,7 @@ int decode_cloud2(lio_ctx* c, int64_t n, const lio_cloud_layout& L, bool yaw_tim
 }
 
 int preprocess_init_counters(lio_ctx* c) {
-  prep_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_prep_counters);
+  prep_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_prep_counters, c->vf.ctr);
   LIO_CHECK(c, cudaGetLastError());
   return LIO_OK;
 }
@@ -671,6 +751,7 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
     c->err = "more than 128 IMU poses in one scan";
     return LIO_E_CAPACITY;
   }
+  const int max_m = (int)c->caps.max_down_points;
   PrepArgs a;
   a.raw = c->d_raw;
   a.n = (int)n;
@@ -684,38 +765,41 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
   a.undist = c->d_undist;
   a.vkeys = c->d_vkeys;
   a.counters = c->d_prep_counters;
-  const int grid = (int)((n + 255) / 256);
-  uint32_t* keys_in = c->d_sort_keys_in;
-  uint32_t* keys_out = c->d_sort_keys_out;
-  int* heads = c->d_run_heads;
-  int* n_runs = c->d_prep_counters + 10;
+  a.vf = c->vf;
+  a.max_m = max_m;
   if (n > 0) {
+    const int grid = (int)((n + 255) / 256);
+    // leaves: at most one per point and never more than the hash holds
+    const int lgrid = (int)((std::min<int64_t>(n, (int64_t)c->vf.hash_mask + 1) + 255) / 256);
     undistort_key_kernel<<<grid, 256, 0, c->stream>>>(a);
-    linear_index_kernel<<<grid, 256, 0, c->stream>>>(c->d_vkeys, (int)n, c->d_prep_counters, keys_in,
-                                                      c->d_sort_vals_in);
-    c->launches += 2;
-    size_t bytes = c->cub_tmp_bytes;
-    LIO_CHECK(c, cub::DeviceRadixSort::SortPairs(c->d_cub_tmp, bytes, keys_in, keys_out, c->d_sort_vals_in,
-                                                 c->d_sort_vals_out, (int)n, 0, 31, c->stream));
-  } else {
-    LIO_CHECK(c, cudaMemsetAsync(n_runs, 0, sizeof(int), c->stream));
+    voxel_bits_kernel<<<lgrid, 256, 0, c->stream>>>(c->vf, c->d_prep_counters);
+    voxel_scan_kernel<<<1, 1024, 0, c->stream>>>(c->vf, c->d_prep_counters);
+    voxel_offsets_kernel<<<lgrid, 256, 0, c->stream>>>(c->vf, c->d_prep_counters);
+    voxel_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->vf, c->d_prep_counters, (int)n);
+    c->launches += 5;
   }
-  const int max_m = (int)c->caps.max_down_points;
-  const int cgrid = (int)((std::min<int64_t>(n, max_m) + 127) / 128);
-  float4* sorted_pts = c->d_raw;  // the raw scan has been consumed by now
-  float* sorted_aux = has_aux ? c->d_sorted_aux : nullptr;
-  if (n > 0) {
-    const unsigned ntiles = (unsigned)((n + RT - 1) / RT);
-    runs_gather_kernel<<<ntiles, 256, 0, c->stream>>>(keys_out, c->d_sort_vals_out, (int)n, c->d_undist,
-                                                      has_aux ? c->d_raw_aux : nullptr, sorted_pts, sorted_aux, heads,
-                                                      n_runs, c->d_runs_status, c->d_runs_ticket, ++c->runs_tag,
-                                                      c->d_prep_counters + 14);
-    c->launches++;
-  }
+  CentroidArgs ca;
+  ca.vf = c->vf;
+  ca.undist = c->d_undist;
+  ca.aux = has_aux ? c->d_raw_aux : nullptr;
+  ca.n = (int)n;
+  ca.max_m = max_m;
+  ca.body = c->d_body;
+  ca.body_time = reinterpret_cast<float*>(c->d_normvec);  // scratch: mean time
+  ca.scan_m = c->d_scan_m;
+  ca.counters = c->d_prep_counters;
+  // the one kernel that overwrites d_body / d_scan_m, which a pending map growth still reads
   if (c->centroid_wait) LIO_CHECK(c, cudaStreamWaitEvent(c->stream, c->centroid_wait, 0));
-  centroid_kernel<<<cgrid > 0 ? cgrid : 1, 128, 0, c->stream>>>(
-      sorted_pts, sorted_aux, heads, n_runs, (int)n, max_m, c->d_body,
-      reinterpret_cast<float*>(c->d_normvec) /*scratch: mean time*/, c->d_scan_m, c->d_prep_counters);
+  static bool attr_set[64] = {false};
+  if (c->device >= 64 || !attr_set[c->device]) {
+    LIO_CHECK(c, cudaFuncSetAttribute((const void*)voxel_centroid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      VF_CENTROID_SMEM));
+    if (c->device < 64) attr_set[c->device] = true;
+  }
+  // half the blocks for the long leaves (one leaf per block at a time), half for the short ones (one per thread)
+  const int64_t leaves_max = std::min<int64_t>(n, (int64_t)c->vf.hash_mask + 1);
+  const int cgrid = 2 * std::max(1, std::min((int)((leaves_max + 255) / 256), c->sm_count * 2));
+  voxel_centroid_kernel<<<cgrid, 256, VF_CENTROID_SMEM, c->stream>>>(ca);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());
   c->scan_m = -1;  // known on the device only until someone asks
