@@ -332,7 +332,7 @@ class Context:
 
     # -- scan
     def scan_preprocess(self, raw_pts, poses=None, end_state=None, leaf=0.5, want_undistorted=False, want_keys=False,
-                        resident=False):
+                        resident=False, want_m=True):
         raw, stride = _points(raw_pts)
         n = raw.shape[0]
         if poses is not None:
@@ -344,8 +344,8 @@ class Context:
         m = C.c_int64(0)
         if resident:
             self._check(self._lib.lio_scan_preprocess_resident(self._h, _ptr(raw), n, stride, _ptr(poses), n_poses,
-                                                               _ptr(end), leaf, C.byref(m)))
-            return m.value
+                                                               _ptr(end), leaf, C.byref(m) if want_m else None))
+            return m.value if want_m else None
         out = np.zeros((int(self.caps.max_down_points), raw.shape[1]), np.float32)
         und = np.zeros((n, 4), np.float32) if want_undistorted else None
         keys = np.zeros((n, 3), np.int32) if want_keys else None

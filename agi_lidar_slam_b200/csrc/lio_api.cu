@@ -228,19 +228,23 @@ static int create_impl(lio_ctx* c) {
     v.bitmap_bits = 1ull << 28;  // leaves of the scan's bounding grid (1024 x 1024 x 256 at most; PCL's own limit is 2^31)
     ALLOC(v.key, 8 * (size_t)hs);
     LIO_CHECK(c, cudaMemset(v.key, 0xFF, 8 * (size_t)hs));
-    uint32_t** z4[] = {&v.cnt, &v.fill, &v.off, &v.rank, &v.lin, &v.list};
+    uint32_t** z4[] = {&v.cnt, &v.off, &v.rank, &v.lin, &v.list};
     for (uint32_t** pp : z4) {
       ALLOC(*pp, 4 * (size_t)hs);
       LIO_CHECK(c, cudaMemset(*pp, 0, 4 * (size_t)hs));
     }
-    ALLOC(v.big, 4 * (N / 32 + 2));
+    ALLOC(v.big, 16 * (N / 128 + 2));
+    ALLOC(v.mid, 16 * (N / 16 + 2));
     ALLOC(v.slot, 4 * N);
+    ALLOC(v.pos, 4 * N);
     ALLOC(v.seg, 4 * N);
+    ALLOC(v.seg2, 4 * N);
     ALLOC(v.bitmap, (size_t)(v.bitmap_bits / 8));
     LIO_CHECK(c, cudaMemset(v.bitmap, 0, (size_t)(v.bitmap_bits / 8)));
-    ALLOC(v.sbcount, 4 * (size_t)(v.bitmap_bits >> 10));
-    LIO_CHECK(c, cudaMemset(v.sbcount, 0, 4 * (size_t)(v.bitmap_bits >> 10)));
-    ALLOC(v.sbprefix, 4 * (size_t)(v.bitmap_bits >> 10));
+    const size_t n_sb = (size_t)(v.bitmap_bits >> 10) + 2048;  // padded: the scan reads whole 16-byte groups per thread
+    ALLOC(v.sbcount, 4 * n_sb);
+    LIO_CHECK(c, cudaMemset(v.sbcount, 0, 4 * n_sb));
+    ALLOC(v.sbprefix, 4 * n_sb);
     ALLOC(v.ctr, 4 * 8);
     LIO_CHECK(c, cudaMemset(v.ctr, 0, 4 * 8));
   }
@@ -299,9 +303,9 @@ void lio_destroy(lio_ctx* c) {
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
                   c->d_vkeys,     c->d_poses,       c->d_sorted_aux,  c->d_run_heads,   c->d_runs_status, c->d_runs_ticket,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
-                  c->d_prep_counters, c->vf.key,    c->vf.cnt,        c->vf.fill,       c->vf.off,        c->vf.rank,
+                  c->d_prep_counters, c->vf.key,    c->vf.cnt,        c->vf.mid,        c->vf.off,        c->vf.rank,
                   c->vf.lin,      c->vf.list,       c->vf.big,        c->vf.slot,       c->vf.seg,        c->vf.bitmap,
-                  c->vf.sbcount,  c->vf.sbprefix,   c->vf.ctr};
+                  c->vf.sbcount,  c->vf.sbprefix,   c->vf.ctr,        c->vf.pos,        c->vf.seg2};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -1006,10 +1010,14 @@ int lio_scan_step_end(lio_ctx* c, float leaf_map, int ekf_inited) {
   LIO_CHECK(c, cudaEventRecord(c->ev_post, c->stream));
   // leaf_map == 0: the map is static -- the relocalisation loop, where map_incremental() is commented out
   // (src/laserMapping_re.cpp:676); the counts of the report are then zero
-  rc = map_incremental_enqueue(c, leaf_map, ekf_inited ? 1 : 0, 5, leaf_map > 0.f ? c->scan_m_bound : 0);
-  if (rc) return rc;
-  LIO_CHECK(c, cudaMemcpyAsync(hp + 620, c->d_prep_counters + 8, 4 * 2, cudaMemcpyDeviceToHost, c->stream));
-  LIO_CHECK(c, cudaMemcpyAsync(hp + 622, c->map.counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (leaf_map > 0.f) {
+    rc = map_incremental_enqueue(c, leaf_map, ekf_inited ? 1 : 0, 5, c->scan_m_bound);
+    if (rc) return rc;
+    LIO_CHECK(c, cudaMemcpyAsync(hp + 620, c->d_prep_counters + 8, 4 * 2, cudaMemcpyDeviceToHost, c->stream));
+    LIO_CHECK(c, cudaMemcpyAsync(hp + 622, c->map.counters, 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+  } else {  // nothing is enqueued for a static map: the counts the report reads are zero by definition
+    memset(hp + 620, 0, 8 * 6);
+  }
   LIO_CHECK(c, cudaEventRecord(c->ev_growth, c->stream));
   c->growth_pending = true;
   c->step_phase = 2;

@@ -87,18 +87,21 @@ __device__ __forceinline__ int map_find(const MapView& m, unsigned long long key
 struct VoxelFilter {
   unsigned long long* key;  // [hash_mask + 1]
   uint32_t* cnt;            // points of the leaf
-  uint32_t* fill;           // ... of them placed in the segment so far
   uint32_t* off;            // first entry of the leaf's segment in `seg`
   uint32_t* rank;           // output position
   uint32_t* lin;            // PCL's linear leaf index relative to the scan's minimum
   uint32_t* list;           // [hash_mask + 1] hash slots of the occupied leaves, in order of creation
-  uint32_t* big;            // hash slots of the leaves a whole block will sum
+  uint4* big;               // {hash slot, points, segment offset} of the leaves a whole block sums (more than VF_MID points)
+  uint4* mid;               // ... a warp sums (VF_SMALL < points <= VF_MID)
   uint32_t* slot;           // [max_scan_points] hash slot of every point's leaf
+  uint32_t* pos;            // [max_scan_points] the point's place in its leaf's segment (arrival order)
   uint32_t* seg;            // [max_scan_points] point indices, leaf by leaf
+  uint32_t* seg2;           // [max_scan_points] the segments of the long leaves in ascending point order
   uint32_t* bitmap;         // [bitmap_bits / 32]
   uint32_t* sbcount;        // [bitmap_bits / 1024] occupied leaves per superblock
   uint32_t* sbprefix;       // ... exclusive scan
-  int* ctr;                 // [0] leaves  [1] segment cursor  [2] long leaves  [3] block ticket
+  int* ctr;                 // [0] leaves  [1] segment cursor  [2] long leaves  [3] centroid block ticket  [4] bits block
+                            // ticket  [5] mid leaves  [6] mid ticket  [7] short-leaf ticket
   uint32_t hash_mask;
   unsigned long long bitmap_bits;
 };

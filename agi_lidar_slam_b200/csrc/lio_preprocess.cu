@@ -9,9 +9,11 @@
 //     bit per leaf of the scan's bounding grid, a count per 1024-leaf superblock, an exclusive scan over the superblocks;
 //     rank = superblock prefix + population count of the bits below;
 //   * the SUM ORDER inside a leaf is the oracle's, ascending point index (PCL's std::sort is unstable, so PCL itself
-//     leaves it open): the points of a leaf are scattered into the leaf's segment in whatever order the atomics give,
-//     and the (small) segment is then put in index order -- by its thread for up to 32 points, by a block-wide bitonic
-//     sort in shared memory for more -- before the sequential FP32 sums.
+//     leaves it open): the points of a leaf are placed into the leaf's segment in the order the atomics of the first
+//     kernel gave, and the segment is put in index order right before the sequential FP32 sums -- by a sorting network in the
+//     registers of one thread for up to 16 points, by a rank sort in one warp for up to 128, and for more by a bitmap over
+//     the point indices in the shared memory of one block (sorting distinct integers of a bounded universe is marking
+//     and counting: no comparison network), whose five sequential sums then run under the loads of the next 512 points.
 // Sequential FP32 sums in a defined order make the centroids BIT-EXACT against the oracle and run-to-run deterministic,
 // which the downstream neighbour sets and validity gates need (the filter loop amplifies 1e-9 input differences to
 // millimetres within ten scans).  No library kernel on this path; the sensor decoders further down still use
@@ -32,8 +34,19 @@ namespace lio {
 
 // ---- the leaf hash and the rank structures (device buffers of lio_ctx, see VoxelFilter in lio_ctx.cuh)
 constexpr uint32_t VF_SB_BITS = 10;     // leaves per superblock: 1024
-constexpr int VF_SMALL = 32;            // leaves up to this many points are ordered and summed by one thread
-constexpr int VF_BLOCK_SORT = 8192;     // ... up to this many by a block-wide bitonic sort; more: ordered sweep of the scan
+constexpr int VF_SMALL = 16;            // leaves up to this many points are ordered and summed by one thread,
+constexpr int VF_MID = 128;             // ... up to this many by one warp, longer ones by one block
+constexpr int VF_WIN_WORDS = 4096;      // block path: words of the point-index bitmap (one window = 131,072 indices)
+constexpr int VF_CHUNK = 896;           // block path: points staged per step of the sequential sums (224 loaders x 4)
+
+// Optional timeline (LIO_TIMELINE=1, lio_debug_timeline): slot k of dbg[200..] takes the maximum over the stamping
+// threads of the global timer in ns (the start of a phase is filed negated, so that its maximum is the earliest start).
+__device__ __forceinline__ void vf_stamp(long long* dbg, int k, bool negate = false) {
+  if (!dbg) return;
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  atomicMax(dbg + 200 + k, negate ? -t : t);
+}
 
 struct PrepArgs {
   const float4* raw;      // x,y,z,t_ms
@@ -50,7 +63,8 @@ struct PrepArgs {
 };
 
 // One thread per raw point: motion compensation, leaf index, index bounds, and the point's leaf in the leaf hash
-// (key = the packed absolute index; the threads of a warp that hit the same leaf send ONE probe and ONE count update).
+// (key = the packed absolute index; the threads of a warp that hit the same leaf send ONE probe and ONE count update,
+// whose return value is also their place in the leaf's segment: no second round of atomics when the points are placed).
 __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
   __shared__ lio_pose6d s_pose[MAX_POSES];
   for (int k = threadIdx.x; k < a.n_poses * 22; k += blockDim.x)
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
   const unsigned long long key = (act && in_range) ? pack_cell(kx, ky, kz) : (LIO_EMPTY_KEY - 1ull - (unsigned)lane);
   const unsigned peers = __match_any_sync(FULL, key);
   const int leader = __ffs(peers) - 1;
-  uint32_t h = 0xFFFFFFFFu;
+  uint32_t h = 0xFFFFFFFFu, base = 0;
   if (act && in_range && lane == leader) {
     h = hash64(key) & a.vf.hash_mask;
     uint32_t probes = 0;
@@ -157,11 +171,13 @@ __global__ void __launch_bounds__(256) undistort_key_kernel(const PrepArgs a) {
         break;
       }
     }
-    if (h != 0xFFFFFFFFu) atomicAdd(&a.vf.cnt[h], (uint32_t)__popc(peers));
+    if (h != 0xFFFFFFFFu) base = atomicAdd(&a.vf.cnt[h], (uint32_t)__popc(peers));
   }
   h = __shfl_sync(FULL, h, leader);
+  base = __shfl_sync(FULL, base, leader);
   if (act) {
     a.vf.slot[i] = h;
+    a.vf.pos[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));  // arrival order; the centroid kernel orders it
     if (!in_range) atomicMax(&a.counters[7], 3);   // beyond any grid PCL could index: "leaf size too small"
     else if (h == 0xFFFFFFFFu) atomicMax(&a.counters[7], 2);  // more leaves than the hash holds (> max_down_points)
   }
@@ -207,9 +223,13 @@ __device__ __forceinline__ void unpack_cell(unsigned long long key, int& x, int&
 }
 
 // One thread per occupied leaf: PCL's linear leaf index ijk . (1, div_x, div_x div_y) relative to min_b, its bit in the
-// grid bitmap and its superblock's count.  The guards: PCL's own ("leaf size too small": the index would overflow an
-// int -> output = input, reported as LIO_E_VOXEL_RANGE) and this implementation's bitmap capacity.
-__global__ void voxel_bits_kernel(VoxelFilter vf, int* counters) {
+// grid bitmap, its superblock's count, its segment in the point-index array and -- by its length -- who will sum it.
+// The guards: PCL's own ("leaf size too small": the index would overflow an int -> output = input, reported as
+// LIO_E_VOXEL_RANGE) and this implementation's bitmap capacity.  The last block to finish turns the superblock counts
+// into their exclusive scan (the grid of a scan has a few ten thousand superblocks).
+__global__ void __launch_bounds__(256) voxel_bits_kernel(VoxelFilter vf, int* counters) {
+  __shared__ uint32_t s_w[8];
+  __shared__ int s_last;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_leaf = vf.ctr[0];
   const long long dx = (long long)counters[4] - counters[1] + 1, dy = (long long)counters[5] - counters[2] + 1,
@@ -223,27 +243,40 @@ __global__ void voxel_bits_kernel(VoxelFilter vf, int* counters) {
     if (e == 0) counters[7] = 5;
     return;
   }
-  if (e >= n_leaf) return;
-  const uint32_t h = vf.list[e];
-  int kx, ky, kz;
-  unpack_cell(vf.key[h], kx, ky, kz);
-  const uint32_t lin = (uint32_t)((long long)(kx - counters[1]) + dx * ((long long)(ky - counters[2]) + dy * (long long)(kz - counters[3])));
-  vf.lin[h] = lin;
-  atomicOr(&vf.bitmap[lin >> 5], 1u << (lin & 31));
-  atomicAdd(&vf.sbcount[lin >> VF_SB_BITS], 1u);
-}
-
-// Exclusive scan of the superblock counts (one block; the grid of a scan has a few ten thousand superblocks).
-__global__ void __launch_bounds__(1024) voxel_scan_kernel(VoxelFilter vf, const int* counters) {
-  __shared__ uint32_t s_w[32];
-  if (counters[7] >= 2) return;
-  const long long cells = ((long long)counters[4] - counters[1] + 1) * ((long long)counters[5] - counters[2] + 1) *
-                          ((long long)counters[6] - counters[3] + 1);
-  const int n_sb = vf.ctr[0] > 0 ? (int)((cells + (1 << VF_SB_BITS) - 1) >> VF_SB_BITS) : 0;
-  const int per = (n_sb + 1023) / 1024;  // the same trip count for every thread: the shuffles below want the warp whole
-  const int lo = (int)threadIdx.x * per;
+  if (e < n_leaf) {
+    const uint32_t h = vf.list[e];
+    int kx, ky, kz;
+    unpack_cell(vf.key[h], kx, ky, kz);
+    const uint32_t lin =
+        (uint32_t)((long long)(kx - counters[1]) + dx * ((long long)(ky - counters[2]) + dy * (long long)(kz - counters[3])));
+    vf.lin[h] = lin;
+    atomicOr(&vf.bitmap[lin >> 5], 1u << (lin & 31));
+    atomicAdd(&vf.sbcount[lin >> VF_SB_BITS], 1u);
+    const uint32_t c = vf.cnt[h];
+    const uint32_t off = (uint32_t)atomicAdd(&vf.ctr[1], (int)c);
+    vf.off[h] = off;
+    if (c > (uint32_t)VF_MID)
+      vf.big[atomicAdd(&vf.ctr[2], 1)] = make_uint4(h, c, off, 0u);
+    else if (c > (uint32_t)VF_SMALL)
+      vf.mid[atomicAdd(&vf.ctr[5], 1)] = make_uint4(h, c, off, 0u);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&vf.ctr[4], 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // every thread scans `per` consecutive counts (a multiple of four: 16-byte loads; the counts behind the grid's last
+  // superblock are zero and the array is padded, so nothing is masked)
+  const int n_sb = n_leaf > 0 ? (int)((dx * dy * dz + (1 << VF_SB_BITS) - 1) >> VF_SB_BITS) : 0;
+  const int per = (((n_sb + 255) / 256) + 3) & ~3;
+  const uint4* src = reinterpret_cast<const uint4*>(vf.sbcount + (size_t)threadIdx.x * per);
+  uint4* dst = reinterpret_cast<uint4*>(vf.sbprefix + (size_t)threadIdx.x * per);
   uint32_t sum = 0;
-  for (int k = 0; k < per; ++k) sum += (lo + k < n_sb) ? vf.sbcount[lo + k] : 0u;
+  for (int k = 0; k < per / 4; ++k) {
+    const uint4 v = __ldcg(src + k);
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = sum;
 #pragma unroll
@@ -253,55 +286,75 @@ __global__ void __launch_bounds__(1024) voxel_scan_kernel(VoxelFilter vf, const 
   }
   if (lane == 31) s_w[warp] = inc;
   __syncthreads();
-  if (warp == 0) {
-    uint32_t v = s_w[lane];
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, v, off);
-      v += lane >= off ? t : 0u;
-    }
-    s_w[lane] = v;
+  uint32_t run = inc - sum;
+  for (int w = 0; w < warp; ++w) run += s_w[w];
+  for (int k = 0; k < per / 4; ++k) {
+    const uint4 v = __ldcg(src + k);
+    uint4 o;
+    o.x = run;
+    o.y = o.x + v.x;
+    o.z = o.y + v.y;
+    o.w = o.z + v.z;
+    run = o.w + v.w;
+    dst[k] = o;
   }
-  __syncthreads();
-  uint32_t run = (warp ? s_w[warp - 1] : 0u) + inc - sum;
-  for (int k = 0; k < per; ++k)
-    if (lo + k < n_sb) {
-      const uint32_t c = vf.sbcount[lo + k];
-      vf.sbprefix[lo + k] = run;
-      run += c;
-    }
 }
 
-// One thread per occupied leaf: its output position (rank among the occupied leaves in index order), its segment in the
-// point-index array, and -- for the long ones -- a place in the list of leaves a whole block will take.
-__global__ void voxel_offsets_kernel(VoxelFilter vf, const int* counters) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (counters[7] >= 2 || e >= vf.ctr[0]) return;
-  const uint32_t h = vf.list[e];
-  const uint32_t lin = vf.lin[h];
-  uint32_t rank = vf.sbprefix[lin >> VF_SB_BITS];
-  for (uint32_t w = (lin >> VF_SB_BITS) << (VF_SB_BITS - 5); w < (lin >> 5); ++w) rank += (uint32_t)__popc(vf.bitmap[w]);
-  rank += (uint32_t)__popc(vf.bitmap[lin >> 5] & ((1u << (lin & 31)) - 1u));
-  const uint32_t c = vf.cnt[h];
-  const bool big = c > (uint32_t)VF_SMALL;
-  vf.rank[h] = rank | (big ? 0x80000000u : 0u);  // the flag says who sums the leaf (its count is cleared by whoever does)
-  vf.off[h] = (uint32_t)atomicAdd(&vf.ctr[1], (int)c);
-  if (big) vf.big[atomicAdd(&vf.ctr[2], 1)] = h;
-}
-
-// One thread per point: its index into its leaf's segment (the lanes of a warp that share a leaf take their places with
-// one atomic; the order inside the segment is whatever comes -- voxel_centroid_kernel puts it right).
-__global__ void __launch_bounds__(256) voxel_scatter_kernel(VoxelFilter vf, const int* counters, int n) {
+// One thread per point: its index goes to its place in its leaf's segment.  The first threads also take one occupied
+// leaf each: its output position = rank among the occupied leaves in index order (superblock prefix + bits below).
+__global__ void __launch_bounds__(256) voxel_place_kernel(VoxelFilter vf, const int* counters, int n) {
   if (counters[7] >= 2) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const uint32_t h = i < n ? vf.slot[i] : 0xFFFFFFF0u - (uint32_t)lane;
-  const unsigned peers = __match_any_sync(0xffffffffu, h);
-  const int leader = __ffs(peers) - 1;
-  uint32_t base = 0;
-  if (i < n && lane == leader) base = atomicAdd(&vf.fill[h], (uint32_t)__popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (i < n) vf.seg[vf.off[h] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;
+  if (i < n) vf.seg[vf.off[vf.slot[i]] + vf.pos[i]] = (uint32_t)i;
+  if (i < vf.ctr[0]) {
+    const uint32_t h = vf.list[i];
+    const uint32_t lin = vf.lin[h];
+    uint32_t rank = vf.sbprefix[lin >> VF_SB_BITS];
+    // the superblock's 32 words are one 128-byte line: eight independent loads, the bits at and above `lin` masked off
+    const uint4* row = reinterpret_cast<const uint4*>(vf.bitmap + ((lin >> VF_SB_BITS) << (VF_SB_BITS - 5)));
+    const uint32_t wl = (lin >> 5) & 31u, below = (1u << (lin & 31)) - 1u;
+#pragma unroll
+    for (uint32_t q = 0; q < 8; ++q) {
+      const uint4 v = row[q];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t wi = 4 * q + j;
+        rank += (uint32_t)__popc(w[j] & (wi < wl ? 0xFFFFFFFFu : (wi == wl ? below : 0u)));
+      }
+    }
+    vf.rank[h] = rank | (vf.cnt[h] > (uint32_t)VF_SMALL ? 0x80000000u : 0u);  // the flag: a warp or a block sums it
+  }
+}
+
+// acc + v[0] + v[1] + ... + v[m - 1], strictly in that order (the FP32 chain the oracle defines).  The additions are
+// the critical path (one dependent FADD per point); the shared-memory reads run one block of 16 ahead of them.  v is
+// 16-byte aligned and readable up to the next multiple of 16 behind m.
+__device__ __forceinline__ float chain_sum(float acc, const float* v, uint32_t m) {
+  const float4* p = reinterpret_cast<const float4*>(v);
+  float4 c0 = p[0], c1 = p[1], c2 = p[2], c3 = p[3];
+  uint32_t t = 0;
+  for (; t + 16 <= m; t += 16) {
+    p += 4;
+    const bool more = t + 16 < m;
+    float4 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
+    if (more) {
+      n0 = p[0];
+      n1 = p[1];
+      n2 = p[2];
+      n3 = p[3];
+    }
+    acc = acc + c0.x; acc = acc + c0.y; acc = acc + c0.z; acc = acc + c0.w;
+    acc = acc + c1.x; acc = acc + c1.y; acc = acc + c1.z; acc = acc + c1.w;
+    acc = acc + c2.x; acc = acc + c2.y; acc = acc + c2.z; acc = acc + c2.w;
+    acc = acc + c3.x; acc = acc + c3.y; acc = acc + c3.z; acc = acc + c3.w;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+  }
+  const float r[16] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w};
+#pragma unroll
+  for (uint32_t k = 0; k < 16; ++k)
+    if (t + k < m) acc = acc + r[k];
+  return acc;
 }
 
 struct CentroidArgs {
@@ -313,6 +366,7 @@ struct CentroidArgs {
   float* body_time;       // mean time
   int* scan_m;
   int* counters;
+  long long* dbg;
 };
 
 // Leaves a leaf's hash entry, bit and counts as the next scan expects to find them.
@@ -324,165 +378,317 @@ __device__ __forceinline__ void leaf_cleanup(const VoxelFilter& vf, uint32_t h, 
   }
   vf.key[h] = LIO_EMPTY_KEY;
   vf.cnt[h] = 0u;
-  vf.fill[h] = 0u;
 }
 
-// Centroids.  The first half of the grid takes the long leaves (one block each: indices into shared memory, bitonic
-// sort, then five lanes run the five component sums as sequential chains over points the other threads stage 256 at a
-// time), the second half the short ones (one thread each, the <= 32 indices in registers).  The last block to finish
-// files the scan's counters for the host and resets the working set.
-constexpr int VF_CENTROID_SMEM = (VF_BLOCK_SORT + 5 * 256) * 4 + 64;  // dynamic: index area + point stage
+__device__ __forceinline__ void leaf_write(const CentroidArgs& a, uint32_t h, uint32_t c, float sx, float sy, float sz,
+                                           float st, float si) {
+  const float fc = (float)c;
+  const uint32_t r = a.vf.rank[h] & 0x7fffffffu;
+  if (r < (uint32_t)a.max_m) {
+    a.body[r] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+    if (a.body_time) a.body_time[r] = st / fc;
+  }
+}
+
+// Centroids: every leaf's five sums are sequential FP32 chains in ascending point index.
+//   long leaves (> VF_MID points), one block each, taken first: the leaf's indices are marked in a bitmap over point
+//     indices in shared memory, a count over the bitmap gives every marked index its place, the ordered indices go to
+//     vf.seg2; then five lanes run the five chains over points the block stages 512 at a time, the loads of the next 512
+//     in flight meanwhile;
+//   mid leaves, one warp each (ticket): rank of every index among the leaf's indices, points staged at their rank;
+//   short leaves, one thread each (ticket per 256): the <= 16 indices through a sorting network in registers.
+// Blocks that have a long leaf join the ticketed work when they are through with it.  The last block to finish files
+// the scan's counters for the host and resets the working set.
+constexpr int VF_STAGE_ROW = VF_CHUNK + 4;  // rows 16 bytes askew: the five chain lanes read five different bank groups
+constexpr int VF_ROW = VF_MID + 4;
+constexpr int VF_CENTROID_SMEM = (2 * VF_WIN_WORDS + 2 * 5 * VF_STAGE_ROW) * 4;  // dynamic: bitmap, counts, two point stages
+static_assert(8 * (VF_MID + 5 * VF_ROW) <= 2 * VF_WIN_WORDS, "the warps' areas overlay the bitmap and its counts");
 __global__ void __launch_bounds__(256) voxel_centroid_kernel(const CentroidArgs a) {
   extern __shared__ __align__(16) unsigned char vf_smem[];
-  uint32_t* s_idx = reinterpret_cast<uint32_t*>(vf_smem);                       // [VF_BLOCK_SORT]
-  float(*s_stage)[256] = reinterpret_cast<float(*)[256]>(vf_smem + 4 * VF_BLOCK_SORT);  // [5][256]
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(vf_smem);                                           // [VF_WIN_WORDS]
+  uint32_t* s_pre = s_bits + VF_WIN_WORDS;                                                            // [VF_WIN_WORDS]
+  float(*s_stage)[5][VF_STAGE_ROW] = reinterpret_cast<float(*)[5][VF_STAGE_ROW]>(vf_smem + 8 * VF_WIN_WORDS);  // [2][5][.]
   __shared__ int s_flag;
-  __shared__ int s_cnt8[8];
+  __shared__ uint32_t s_wtot[8];
+  __shared__ uint32_t s_lohi[2];
+  __shared__ float s_sum[5];
   const VoxelFilter& vf = a.vf;
-  const int tid = threadIdx.x;
-  const int err = a.counters[7];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the counters of this launch, fetched together (they sit at the head of three dependent phases otherwise)
+  const int4 ctr_lo = __ldcg(reinterpret_cast<const int4*>(vf.ctr)), ctr_hi = __ldcg(reinterpret_cast<const int4*>(vf.ctr) + 1);
+  const int err = __ldcg(a.counters + 7);
   const bool ok = err < 2;            // 2: too many leaves, 3: PCL's overflow guard, 5: bitmap capacity
-  const int n_leaf_all = vf.ctr[0];  // every leaf is in the list (and has to be cleaned up), at most max_m come out
+  const int n_leaf_all = ctr_lo.x;   // every leaf is in the list (and has to be cleaned up), at most max_m come out
   const int n_leaf = min(n_leaf_all, a.max_m);
-  const int half = (int)gridDim.x / 2;
-  if (ok && (int)blockIdx.x < half) {
+  if (tid == 0) vf_stamp(a.dbg, 0, true);
+  if (ok) {
     // ---- long leaves
-    const int n_big = vf.ctr[2];
-    for (int e = blockIdx.x; e < n_big; e += half) {
-      const uint32_t h = vf.big[e];
-      const uint32_t c = vf.cnt[h], off = vf.off[h];
-      float acc = 0.f;  // lane k < 5 of warp 0: running sum of component k
-      if (c <= (uint32_t)VF_BLOCK_SORT) {
-        uint32_t np = 64;
-        while (np < c) np <<= 1;
-        for (uint32_t k = tid; k < np; k += 256) s_idx[k] = k < c ? vf.seg[off + k] : 0xFFFFFFFFu;
-        __syncthreads();
-        for (uint32_t size = 2; size <= np; size <<= 1)
-          for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = tid; t < (np >> 1); t += 256) {
-              const uint32_t lo = 2 * t - (t & (stride - 1));  // the t-th pair of this stage
-              const uint32_t hi = lo + stride;
-              const bool up = (lo & size) == 0;
-              const uint32_t x = s_idx[lo], y = s_idx[hi];
-              if ((x > y) == up) {
-                s_idx[lo] = y;
-                s_idx[hi] = x;
-              }
-            }
-            __syncthreads();
-          }
-        for (uint32_t base = 0; base < c; base += 256) {
-          const uint32_t m = min(256u, c - base);
-          if ((uint32_t)tid < m) {
-            const uint32_t i = s_idx[base + tid];
-            const float4 p = __ldg(a.undist + i);
-            s_stage[0][tid] = p.x;
-            s_stage[1][tid] = p.y;
-            s_stage[2][tid] = p.z;
-            s_stage[3][tid] = p.w;
-            s_stage[4][tid] = a.aux ? __ldg(a.aux + i) : 0.f;
-          }
-          __syncthreads();
-          if (tid < 5) {
-            const float* v = s_stage[tid];
-            uint32_t t = 0;
-            for (; t + 4 <= m; t += 4) {
-              const float4 w = *reinterpret_cast<const float4*>(v + t);
-              acc = acc + w.x;
-              acc = acc + w.y;
-              acc = acc + w.z;
-              acc = acc + w.w;
-            }
-            for (; t < m; ++t) acc = acc + v[t];
-          }
-          __syncthreads();
-        }
-      } else {
-        // more points in ONE leaf than the sort area holds: sweep the scan in point order, 256 points at a time, and add
-        // the members as they come (same order, no sort; cost is a pass over the slot array per such leaf)
-        for (int base = 0; base < a.n; base += 256) {
-          const int i = base + tid;
-          const bool mine = i < a.n && vf.slot[i] == h;
-          const unsigned b = __ballot_sync(0xffffffffu, mine);
-          if ((tid & 31) == 0) s_cnt8[tid >> 5] = __popc(b);
-          __syncthreads();
-          int pos = __popc(b & ((1u << (tid & 31)) - 1u)), m = 0;
-          for (int w = 0; w < 8; ++w) {
-            if (w < (tid >> 5)) pos += s_cnt8[w];
-            m += s_cnt8[w];
-          }
-          if (mine) {
-            const float4 p = __ldg(a.undist + i);
-            s_stage[0][pos] = p.x;
-            s_stage[1][pos] = p.y;
-            s_stage[2][pos] = p.z;
-            s_stage[3][pos] = p.w;
-            s_stage[4][pos] = a.aux ? __ldg(a.aux + i) : 0.f;
-          }
-          __syncthreads();
-          if (tid < 5) {
-            const float* v = s_stage[tid];
-            for (int t = 0; t < m; ++t) acc = acc + v[t];
-          }
-          __syncthreads();
+    const int n_big = ctr_lo.z;
+    for (int e = blockIdx.x; e < n_big; e += gridDim.x) {
+      const uint4 leaf = __ldcg(vf.big + e);
+      const uint32_t h = leaf.x, c = leaf.y, off = leaf.z;
+      // span of the leaf's point indices
+      uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+      for (uint32_t k0 = tid; k0 < c; k0 += 8 * 256) {
+        uint32_t idx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idx[j] = __ldcg(vf.seg + off + min(k0 + 256u * j, c - 1));  // (clamped: a repeat)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          lo = min(lo, idx[j]);
+          hi = max(hi, idx[j]);
         }
       }
-      if (tid < 5) s_stage[tid][0] = acc;
+      lo = __reduce_min_sync(0xffffffffu, lo);
+      hi = __reduce_max_sync(0xffffffffu, hi);
+      if (tid == 0) {
+        s_lohi[0] = 0xFFFFFFFFu;
+        s_lohi[1] = 0u;
+      }
+      __syncthreads();
+      if (lane == 0) {
+        atomicMin(&s_lohi[0], lo);
+        atomicMax(&s_lohi[1], hi);
+      }
+      __syncthreads();
+      const uint32_t wbase = s_lohi[0] >> 5, nwords = (s_lohi[1] >> 5) - wbase + 1;
+      if (tid == 0) vf_stamp(a.dbg, 5);
+      uint32_t out = 0;
+      for (uint32_t w0 = 0; w0 < nwords; w0 += VF_WIN_WORDS) {
+        const uint32_t nw = min((uint32_t)VF_WIN_WORDS, nwords - w0);
+        for (uint32_t w = tid; w < nw; w += 256) s_bits[w] = 0u;
+        __syncthreads();
+        for (uint32_t k0 = tid; k0 < c; k0 += 8 * 256) {  // eight loads in flight, then their marks
+          uint32_t idx[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) idx[j] = __ldcg(vf.seg + off + min(k0 + 256u * j, c - 1));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t w = (idx[j] >> 5) - wbase - w0;  // wraps to a large number below the window
+            if (k0 + 256u * j < c && w < nw) atomicOr(&s_bits[w], 1u << (idx[j] & 31));
+          }
+        }
+        __syncthreads();
+        // exclusive count of the marks before every word: each thread counts a run of g consecutive words, the runs'
+        // totals go through a block scan
+        const uint32_t g = (nw + 255) / 256;
+        uint32_t sum = 0;
+        for (uint32_t k = 0; k < g; ++k) {
+          const uint32_t w = tid * g + k;
+          sum += w < nw ? (uint32_t)__popc(s_bits[w]) : 0u;
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+          inc += lane >= d ? t : 0u;
+        }
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t run = out + inc - sum;
+        for (int w = 0; w < warp; ++w) run += s_wtot[w];
+        for (uint32_t k = 0; k < g; ++k) {
+          const uint32_t w = tid * g + k;
+          if (w < nw) {
+            s_pre[w] = run;
+            run += (uint32_t)__popc(s_bits[w]);
+          }
+        }
+        for (int w = 0; w < 8; ++w) out += s_wtot[w];
+        __syncthreads();
+        // the marked indices in ascending order (words interleaved over the threads: a dense stretch of the leaf is
+        // spread over a whole warp)
+        for (uint32_t w = tid; w < nw; w += 256) {
+          uint32_t v = s_bits[w];
+          uint32_t q = s_pre[w];
+          const uint32_t first = (wbase + w0 + w) << 5;
+          while (v) {
+            vf.seg2[off + q++] = first + (uint32_t)(__ffs(v) - 1);
+            v &= v - 1u;
+          }
+        }
+        __syncthreads();
+      }
+      if (tid == 0) vf_stamp(a.dbg, 6);
+      // ---- the five chains: warp 0 sums (lane k < 5: component k), warps 1-7 stage VF_CHUNK points per step; the points
+      // run one step ahead of the sums and their indices one step ahead of the points, and every load is unconditional
+      // (indices clamped, not branched around), so none of them makes a warp wait where it is issued
+      float acc = 0.f;
+      {
+        constexpr int NL = 224, PER = VF_CHUNK / NL;
+        static_assert(PER * NL == VF_CHUNK, "chunk = loader threads x points per thread");
+        const int lt = tid - 32;
+        float4 pp[PER];
+        float xx[PER];
+        uint32_t ii[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) xx[j] = 0.f;
+        auto load_idx = [&](uint32_t base) {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) ii[j] = __ldcg(vf.seg2 + off + min(base + (uint32_t)(lt + NL * j), c - 1));
+        };
+        auto load_pts = [&]() {
+#pragma unroll
+          for (int j = 0; j < PER; ++j) {
+            pp[j] = __ldg(a.undist + ii[j]);
+            if (a.aux) xx[j] = __ldg(a.aux + ii[j]);
+          }
+        };
+        auto stash = [&](int buf) {
+          float(*st)[VF_STAGE_ROW] = s_stage[buf];
+#pragma unroll
+          for (int j = 0; j < PER; ++j) {
+            st[0][lt + NL * j] = pp[j].x;
+            st[1][lt + NL * j] = pp[j].y;
+            st[2][lt + NL * j] = pp[j].z;
+            st[3][lt + NL * j] = pp[j].w;
+            st[4][lt + NL * j] = xx[j];
+          }
+        };
+        if (warp > 0) {
+          load_idx(0);
+          load_pts();
+          load_idx(VF_CHUNK);
+          stash(0);
+        }
+        __syncthreads();
+        int buf = 0;
+        for (uint32_t base = 0; base < c; base += VF_CHUNK) {
+          const uint32_t m = min((uint32_t)VF_CHUNK, c - base);
+          const bool next = base + VF_CHUNK < c;
+          if (warp > 0) {
+            if (next) {
+              load_pts();
+              load_idx(base + 2 * VF_CHUNK);
+              stash(buf ^ 1);
+            }
+          } else if (lane < 5) {
+            acc = chain_sum(acc, s_stage[buf][lane], m);
+          }
+          __syncthreads();
+          buf ^= 1;
+        }
+      }
+      if (tid < 5) s_sum[tid] = acc;
       __syncthreads();
       if (tid == 0) {
-        const float fc = (float)c;
-        const uint32_t r = vf.rank[h] & 0x7fffffffu;
-        if (r < (uint32_t)a.max_m) {
-          a.body[r] = make_float4(s_stage[0][0] / fc, s_stage[1][0] / fc, s_stage[2][0] / fc, s_stage[4][0] / fc);
-          if (a.body_time) a.body_time[r] = s_stage[3][0] / fc;
-        }
+        leaf_write(a, h, c, s_sum[0], s_sum[1], s_sum[2], s_sum[3], s_sum[4]);
         leaf_cleanup(vf, h, true);
       }
       __syncthreads();
     }
-  } else {
-    // ---- short leaves (and, after an error, the clean-up of every leaf)
-    const int nthr = ((int)gridDim.x - half) * 256;
-    for (int e = ((int)blockIdx.x - half) * 256 + tid; e < n_leaf_all; e += nthr) {
-      const uint32_t h = vf.list[e];
-      if (ok && (vf.rank[h] & 0x80000000u)) continue;  // a block takes it
-      const uint32_t c = vf.cnt[h];
-      if (ok) {
-        const uint32_t off = vf.off[h];
-        float sx = 0.f, sy = 0.f, sz = 0.f, st = 0.f, si = 0.f;
-        // the leaf's indices stay in registers (fully unrolled); the next point in index order is the smallest index above
-        // the last one: 32 compares per step and no memory in that chain, so the point loads of consecutive steps overlap
-        // and only the additions are sequential
-        uint32_t last = 0;
-        uint32_t v[VF_SMALL];
+    if (tid == 0) vf_stamp(a.dbg, 1);
+    // ---- mid leaves: one warp per leaf
+    {
+      uint32_t* w_idx = reinterpret_cast<uint32_t*>(vf_smem) + warp * (VF_MID + 5 * VF_ROW);  // [VF_MID] indices
+      float* w_pt = reinterpret_cast<float*>(w_idx + VF_MID);                                 // [5][VF_ROW] points at their rank
+      const int n_mid = ctr_hi.y;
+      for (;;) {
+        int e = 0;
+        if (lane == 0) e = atomicAdd(&vf.ctr[6], 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= n_mid) break;
+        const uint4 leaf = __ldcg(vf.mid + e);
+        const uint32_t h = leaf.x, c = leaf.y, off = leaf.z;
+        uint32_t v[VF_MID / 32], r[VF_MID / 32];
 #pragma unroll
-        for (int j = 0; j < VF_SMALL; ++j) v[j] = (uint32_t)j < c ? vf.seg[off + j] : 0xFFFFFFFFu;
-#pragma unroll 1
-        for (uint32_t k = 0; k < c; ++k) {
-          uint32_t best = 0xFFFFFFFFu;
+        for (int q = 0; q < VF_MID / 32; ++q) {
+          const uint32_t k = (uint32_t)(lane + 32 * q);
+          v[q] = k < c ? __ldcg(vf.seg + off + k) : 0xFFFFFFFFu;
+          w_idx[k] = v[q];
+          r[q] = 0;
+        }
+        __syncwarp();
+        for (uint32_t j = 0; j < c; ++j) {
+          const uint32_t x = w_idx[j];
 #pragma unroll
-          for (int j = 0; j < VF_SMALL; ++j) {
-            const bool take = (k == 0 || v[j] > last) && v[j] < best;
-            best = take ? v[j] : best;
+          for (int q = 0; q < VF_MID / 32; ++q) r[q] += x < v[q] ? 1u : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < VF_MID / 32; ++q)
+          if (v[q] != 0xFFFFFFFFu) {
+            const float4 p = __ldg(a.undist + v[q]);
+            w_pt[0 * VF_ROW + r[q]] = p.x;
+            w_pt[1 * VF_ROW + r[q]] = p.y;
+            w_pt[2 * VF_ROW + r[q]] = p.z;
+            w_pt[3 * VF_ROW + r[q]] = p.w;
+            w_pt[4 * VF_ROW + r[q]] = a.aux ? __ldg(a.aux + v[q]) : 0.f;
           }
-          last = best;
-          const float4 p = __ldg(a.undist + best);
-          sx = sx + p.x;
-          sy = sy + p.y;
-          sz = sz + p.z;
-          st = st + p.w;
-          if (a.aux) si = si + __ldg(a.aux + best);
+        __syncwarp();
+        float acc = 0.f;
+        if (lane < 5) acc = chain_sum(0.f, w_pt + lane * VF_ROW, c);
+        const float sx = __shfl_sync(0xffffffffu, acc, 0), sy = __shfl_sync(0xffffffffu, acc, 1),
+                    sz = __shfl_sync(0xffffffffu, acc, 2), st = __shfl_sync(0xffffffffu, acc, 3),
+                    si = __shfl_sync(0xffffffffu, acc, 4);
+        if (lane == 0) {
+          leaf_write(a, h, c, sx, sy, sz, st, si);
+          leaf_cleanup(vf, h, true);
         }
-        const float fc = (float)c;
-        const uint32_t r = vf.rank[h];
-        if (r < (uint32_t)a.max_m) {
-          a.body[r] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
-          if (a.body_time) a.body_time[r] = st / fc;
-        }
+        __syncwarp();
       }
-      leaf_cleanup(vf, h, ok);
     }
   }
+  if (lane == 0) vf_stamp(a.dbg, 2);
+  // ---- short leaves (and, after an error, the clean-up of every leaf): one thread per leaf, 256 leaves per ticket
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_flag = atomicAdd(&vf.ctr[7], 256);
+    __syncthreads();
+    const int e0 = s_flag;
+    if (e0 >= n_leaf_all) break;
+    const int e = e0 + tid;
+    if (e >= n_leaf_all) continue;
+    const uint32_t h = vf.list[e];
+    if (ok && (vf.rank[h] & 0x80000000u)) continue;  // a warp or a block takes it (and may have cleared its count already)
+    const uint32_t c = vf.cnt[h];
+    if (ok) {
+      const uint32_t off = vf.off[h];
+      // The leaf's indices go through a sorting network in registers (fixed sequence of min/max, padding sorts to the
+      // end), then every point load is issued before the first addition: two memory latencies per leaf, whatever its
+      // length, instead of one per point (issue is in order: an addition that waits for its load holds up the rest).
+      uint32_t v[VF_SMALL];
+#pragma unroll
+      for (int j = 0; j < VF_SMALL; ++j) v[j] = (uint32_t)j < c ? __ldcg(vf.seg + off + j) : 0xFFFFFFFFu;
+#pragma unroll
+      for (int size = 2; size <= VF_SMALL; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1)
+#pragma unroll
+          for (int i = 0; i < VF_SMALL; ++i) {
+            const int j = i ^ stride;
+            if (j > i) {
+              const uint32_t lo = min(v[i], v[j]), hi = max(v[i], v[j]);
+              const bool up = (i & size) == 0;
+              v[i] = up ? lo : hi;
+              v[j] = up ? hi : lo;
+            }
+          }
+      float4 p[VF_SMALL];
+      float x[VF_SMALL];
+#pragma unroll
+      for (int j = 0; j < VF_SMALL; ++j) {
+        p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x[j] = 0.f;
+        if ((uint32_t)j < c) {
+          p[j] = __ldg(a.undist + v[j]);
+          if (a.aux) x[j] = __ldg(a.aux + v[j]);
+        }
+      }
+      float sx = 0.f, sy = 0.f, sz = 0.f, st = 0.f, si = 0.f;
+#pragma unroll
+      for (int j = 0; j < VF_SMALL; ++j)
+        if ((uint32_t)j < c) {
+          sx = sx + p[j].x;
+          sy = sy + p[j].y;
+          sz = sz + p[j].z;
+          st = st + p[j].w;
+          si = si + x[j];
+        }
+      leaf_write(a, h, c, sx, sy, sz, st, si);
+    }
+    leaf_cleanup(vf, h, ok);
+  }
+  if (tid == 0) vf_stamp(a.dbg, 3);
   // ---- the last block files the scan's counters as the report the host reads (counters[16..23]) and leaves the working
   // set reset for the next scan
   __threadfence();
@@ -501,7 +707,9 @@ __global__ void __launch_bounds__(256) voxel_centroid_kernel(const CentroidArgs 
     a.counters[1] = a.counters[2] = a.counters[3] = 0x7fffffff;
     a.counters[4] = a.counters[5] = a.counters[6] = -0x7fffffff;
     a.counters[7] = 0;
-    vf.ctr[0] = vf.ctr[1] = vf.ctr[2] = vf.ctr[3] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vf.ctr[k] = 0;
+    vf_stamp(a.dbg, 4);
   }
 }
 
@@ -773,10 +981,8 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
     const int lgrid = (int)((std::min<int64_t>(n, (int64_t)c->vf.hash_mask + 1) + 255) / 256);
     undistort_key_kernel<<<grid, 256, 0, c->stream>>>(a);
     voxel_bits_kernel<<<lgrid, 256, 0, c->stream>>>(c->vf, c->d_prep_counters);
-    voxel_scan_kernel<<<1, 1024, 0, c->stream>>>(c->vf, c->d_prep_counters);
-    voxel_offsets_kernel<<<lgrid, 256, 0, c->stream>>>(c->vf, c->d_prep_counters);
-    voxel_scatter_kernel<<<grid, 256, 0, c->stream>>>(c->vf, c->d_prep_counters, (int)n);
-    c->launches += 5;
+    voxel_place_kernel<<<grid, 256, 0, c->stream>>>(c->vf, c->d_prep_counters, (int)n);
+    c->launches += 3;
   }
   CentroidArgs ca;
   ca.vf = c->vf;
@@ -788,6 +994,8 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
   ca.body_time = reinterpret_cast<float*>(c->d_normvec);  // scratch: mean time
   ca.scan_m = c->d_scan_m;
   ca.counters = c->d_prep_counters;
+  ca.dbg = c->d_dbg;
+  if (c->d_dbg) LIO_CHECK(c, cudaMemsetAsync(c->d_dbg + 200, 0x80, 8 * 8, c->stream));
   // the one kernel that overwrites d_body / d_scan_m, which a pending map growth still reads
   if (c->centroid_wait) LIO_CHECK(c, cudaStreamWaitEvent(c->stream, c->centroid_wait, 0));
   static bool attr_set[64] = {false};
@@ -796,9 +1004,9 @@ int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, f
                                       VF_CENTROID_SMEM));
     if (c->device < 64) attr_set[c->device] = true;
   }
-  // half the blocks for the long leaves (one leaf per block at a time), half for the short ones (one per thread)
+  // long leaves first (one block each, strided), then tickets for the mid and the short ones
   const int64_t leaves_max = std::min<int64_t>(n, (int64_t)c->vf.hash_mask + 1);
-  const int cgrid = 2 * std::max(1, std::min((int)((leaves_max + 255) / 256), c->sm_count * 2));
+  const int cgrid = std::max(1, std::min((int)((leaves_max + 63) / 64), c->sm_count * 2));
   voxel_centroid_kernel<<<cgrid, 256, VF_CENTROID_SMEM, c->stream>>>(ca);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());
