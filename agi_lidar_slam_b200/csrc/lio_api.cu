@@ -61,9 +61,8 @@ static int refresh_scan_m(lio_ctx* c) {
 using namespace lio;
 
 // peer mailbox of the sharded-map exchange: blobs [8 ranks][2 slots][LIO_BLOB] doubles, stamps [8][2] u32, error flag
-static const size_t MAILBOX_STAMPS = 8 * 2 * LIO_BLOB * sizeof(double);
-static const size_t MAILBOX_ERR = MAILBOX_STAMPS + 8 * 2 * sizeof(unsigned);
-static const size_t MAILBOX_BYTES = 12288;
+static const size_t MAILBOX_ERR = 8 * 2 * LIO_BLOB * 2 * sizeof(unsigned long long);  // behind the stamped words
+static const size_t MAILBOX_BYTES = 24576;
 
 extern "C" {
 
@@ -1140,8 +1139,7 @@ int lio_peer_connect(lio_ctx* c, int rank, int world, const unsigned char* handl
       LIO_CHECK(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
       c->peer_base[r] = base;
     }
-    c->peer_mbox[r] = static_cast<double*>(base);
-    c->peer_stamp[r] = reinterpret_cast<unsigned*>(static_cast<char*>(base) + MAILBOX_STAMPS);
+    c->peer_mbox[r] = static_cast<unsigned long long*>(base);
   }
   c->d_peer_err = reinterpret_cast<int*>(static_cast<char*>(c->d_mailbox) + MAILBOX_ERR);
   c->peer_rank = rank;

@@ -55,11 +55,10 @@ struct lio_ctx {
   double* d_prior = nullptr;        // 288: P11^-1 and P21 P11^-1 of the current update
   unsigned* d_sync = nullptr;       // grid barrier words {arrivals, release}
   // sharded map: peer mailboxes (own one allocated here, the peers' mapped through cudaIpc)
-  void* d_mailbox = nullptr;        // {double blob[8][2][LIO_BLOB]; unsigned stamp[8][2]; int err}
+  void* d_mailbox = nullptr;        // {stamped words [8 ranks][2 slots][LIO_BLOB][2]; int err}
   int peer_world = 0, peer_rank = 0;
   unsigned peer_epoch = 0;          // advanced by sharded launches only: stays in lockstep across the ranks
-  double* peer_mbox[8] = {nullptr};
-  unsigned* peer_stamp[8] = {nullptr};
+  unsigned long long* peer_mbox[8] = {nullptr};
   void* peer_base[8] = {nullptr};   // cudaIpcOpenMemHandle results (closed in lio_destroy)
   int* d_peer_err = nullptr;
   unsigned epoch = 0;               // stamp base of the next update_kernel launch

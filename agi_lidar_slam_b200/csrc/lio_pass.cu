@@ -67,6 +67,7 @@ struct PassArgs {
   float max_d2, plane_thr;
   int rings;
   float own_min, own_max;
+  int sharded;  // the window above is finite: rows are shared out over the ranks
   int stage;  // 1: the searches of a tile stage its neighbour cells in shared memory first (stage_cells)
   unsigned long long* partials;  // [workers][ROW_WORDS]: one row of stamped words per worker block (st_stamped)
   long long* dbg;    // optional timeline (LIO_TIMELINE=1): [0] = entries used by block 0, [1..] = (tag, globaltimer ns)
@@ -184,19 +185,26 @@ __device__ __forceinline__ void body_to_world(const PassConst& pc, const double 
 
 constexpr int SROWS_MAX = THREADS / 8;  // rows of a search tile at the smallest group size
 
+// A block works through positions t = 0 .. n-1 of its chunk of the scan: all of its points in order, or -- sharded map --
+// only the ones this rank owns (list = their offsets in the chunk, ascending).
+constexpr int OWN_MAX = 2048;  // longest chunk a list is kept for (beyond: every point is visited and the rows are masked)
+__device__ __forceinline__ int point_index(int beg, const unsigned short* list, int t) {
+  return beg + (list ? (int)list[t] : t);
+}
+
 // Search phase of one tile: its queries (at most THREADS / G), one per G-lane group (esekfom.hpp:140).  The 5 neighbours
 // go to the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.  With staging
 // on the caller has staged the tile's neighbour cells (stage_cells); use_stage says whether the tile fitted.
 template <int G>
-__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int i0, int end, float4* s_nb,
-                                         int* s_cnt, float4* s_body, const float4* body, StageSmem* st, bool use_stage) {
+__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int t0, int n, int beg,
+                                         const unsigned short* list, float4* s_nb, int* s_cnt, float4* s_body,
+                                         const float4* body, StageSmem* st, bool use_stage) {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int row = threadIdx.x / G;
-  const int i_raw = i0 + row;
-  const bool act = i_raw < end;  // group-uniform
-  const int qi = act ? row : end - 1 - i0;  // idle groups redo the last query: the whole warp stays together for the shuffles
-  const int i = i0 + qi;
+  const bool act = t0 + row < n;  // group-uniform
+  const int qi = act ? row : n - 1 - t0;  // idle groups redo the last query: the whole warp stays together for the shuffles
+  const int i = point_index(beg, list, t0 + qi);
   const float4 b = body[i];  // device copy, or the caller's pinned host buffer in pass 0 of the host-direct path
   if (gl == 0 && act) s_body[row] = b;
   const double pb[3] = {b.x, b.y, b.z};
@@ -240,16 +248,17 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
 
 // Finish phase of one tile, one thread per point: steps 1.1-1.2 and 1.5-3 of h_share_model (esekfom.hpp:123-133,
 // 153-226) from the point's 5 neighbours (just found: shared memory; cached: a.near_pts with the sticky mask).
-__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int i0, int end, int rows, bool search,
-                                         const float4* s_nb, const int* s_cnt, double* s_rows,
-                                         unsigned char* s_valid, const float4* s_body, bool copy_body) {
+__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int t0, int n, int beg,
+                                         const unsigned short* list, int rows, bool search, const float4* s_nb,
+                                         const int* s_cnt, double* s_rows, unsigned char* s_valid, const float4* s_body,
+                                         bool copy_body) {
   const int row = threadIdx.x;
   if (row >= rows) return;
-  const int i = i0 + row;
-  if (i >= end) {
+  if (t0 + row >= n) {
     s_valid[row] = 0;
     return;
   }
+  const int i = point_index(beg, list, t0 + row);
   const float4 b = search ? s_body[row] : __ldcg(a.body + i);  // the search phase left it in shared memory
   if (copy_body) const_cast<float4*>(a.body)[i] = b;            // host-direct path, pass 0: keep a device copy
   const double pb[3] = {b.x, b.y, b.z};
@@ -290,7 +299,11 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
   }
   a.selected[i] = sel ? 1 : 0;
   if (sel) a.normvec[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
-  const bool valid = sel && (pwx >= a.own_min) && (pwx < a.own_max);
+  // Ownership (sharded map): by the x of the position the row was SEARCHED at -- the same on every rank and fixed until
+  // the next search pass, so a row and its cached neighbours stay with one rank.  Listed rows are owned by construction.
+  float qx = pwx;
+  if (!list && !search && a.sharded) qx = __ldcg(&a.near_q[i]).x;
+  const bool valid = sel && (list != nullptr || ((qx >= a.own_min) && (qx < a.own_max)));
   s_valid[row] = valid ? 1 : 0;
   if (valid) {
     // step 3 (esekfom.hpp:197-226): Jacobian row and residual
@@ -936,6 +949,9 @@ struct __align__(16) PassSmem {
   unsigned char valid[ROWS_MAX];
   double xrecv[15];  // worker_receive: the published x[0..13] and, in the low half of [14], the flags
   int flag;
+  int n_own;                      // sharded map: length of `own` (-1: not built yet)
+  int wcnt[THREADS / 32];
+  unsigned short own[OWN_MAX];    // offsets (in the chunk) of the points this rank owns, ascending
 };
 
 static_assert(SROWS_MAX == ST_TILE, "a search tile is a staging tile");
@@ -958,7 +974,54 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
   const int beg = wid * C;
   if (beg >= M) return;  // block-uniform
   const int end = min(M, beg + C);
-  const int G = pick_group(C);
+  // ---- sharded map: the points of this chunk the rank owns = whose p_world.x AT THE LAST SEARCH PASS lies in its window.
+  // Every rank computes the same bits for every point, so the ranks' lists partition the scan.  The list is rebuilt in
+  // search passes (when the positions change) and kept across the cached passes that follow (the persistent kernel keeps
+  // it in shared memory; a per-pass launch rebuilds it from a.near_q).
+  const bool compact = a.sharded && (end - beg) <= OWN_MAX;
+  if (compact && (search || ps->n_own < 0)) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int built = 0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < end - beg; k0 += THREADS) {
+      const int k = k0 + tid, i = beg + k;
+      const bool in = k < end - beg;
+      float qx = 0.f;
+      if (in) {
+        if (search) {
+          const float4 b = body[i];
+          const double pb[3] = {b.x, b.y, b.z};
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          body_to_world(ps->pc, pb, q.x, q.y, q.z);
+          a.near_q[i] = q;
+          qx = q.x;
+        } else {
+          qx = __ldcg(&a.near_q[i]).x;
+        }
+      }
+      const bool own = in && (qx >= a.own_min) && (qx < a.own_max);
+      if (in && !own && search) {  // another rank's row: nothing cached here
+        a.selected[i] = 0;
+        a.near_cnt[i] = 0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, own);
+      if (lane == 0) ps->wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int base = built, tot = 0;
+      for (int w = 0; w < THREADS / 32; ++w) {
+        if (w < warp) base += ps->wcnt[w];
+        tot += ps->wcnt[w];
+      }
+      if (own) ps->own[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)k;
+      built += tot;
+      __syncthreads();
+    }
+    if (tid == 0) ps->n_own = built;
+    __syncthreads();
+  }
+  const unsigned short* list = compact ? ps->own : nullptr;
+  const int n = compact ? ps->n_own : end - beg;
+  const int G = pick_group(n);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   const int nseg = THREADS / nout;
   const int o = tid % nout, seg = tid / nout;
@@ -968,12 +1031,12 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
     cb = a.extrinsic_est ? c_ob_ext[o] : c_ob_no[o];
   }
   double acc = 0.0;
-  const int step = search ? THREADS / G : (C < ROWS_MAX ? C : ROWS_MAX);
+  const int step = search ? THREADS / G : (n < ROWS_MAX ? max(n, 1) : ROWS_MAX);
 #pragma unroll 1
-  for (int i0 = beg; i0 < end; i0 += step) {
+  for (int t0 = 0; t0 < n; t0 += step) {
     const int rows = step;
     if (search) {
-      const int tend = min(end, i0 + step);
+      const int tend = min(n, t0 + step);
       // the tile's queries (p_world, FP64 -> FP32) and, when staging, an empty cell set; the previous tile is done with
       // the staging area
       if (a.stage) {
@@ -986,28 +1049,28 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
       }
       bool use_stage = false;
       if (a.stage) {
-        if (tid < tend - i0) {  // the staging needs the queries first; search_tile recomputes the same bits
-          const float4 b = body[i0 + tid];
+        if (tid < tend - t0) {  // the staging needs the queries first; search_tile recomputes the same bits
+          const float4 b = body[point_index(beg, list, t0 + tid)];
           const double pb[3] = {b.x, b.y, b.z};
           float pwx, pwy, pwz;
           body_to_world(ps->pc, pb, pwx, pwy, pwz);
           ps->q[tid] = make_float4(pwx, pwy, pwz, 0.f);
         }
         __syncthreads();
-        stage_cells<THREADS>(a.map, st, ps->q, tend - i0, a.dbg);
+        stage_cells<THREADS>(a.map, st, ps->q, tend - t0, a.dbg);
         use_stage = st->overflow == 0;
       }
       if (G == 32)
-        search_tile<32>(a, ps->pc, i0, tend, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<32>(a, ps->pc, t0, n, beg, list, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       else if (G == 16)
-        search_tile<16>(a, ps->pc, i0, tend, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<16>(a, ps->pc, t0, n, beg, list, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       else
-        search_tile<8>(a, ps->pc, i0, tend, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<8>(a, ps->pc, t0, n, beg, list, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       __syncthreads();
       if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
       stamp(a.dbg, 0, 3);
     }
-    finish_tile(a, ps->pc, i0, end, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
+    finish_tile(a, ps->pc, t0, n, beg, list, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
     __syncthreads();
     stamp(a.dbg, 0, 4);
     if (seg < nseg) {
@@ -1030,61 +1093,74 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
 
 // ---------------------------------------------------------------------------------------------------------
 // Sharded map (SURVEY.md 8e case 2): the ranks' blobs are exchanged INSIDE the persistent kernel over NVLink peer
-// memory.  Every rank owns a mailbox {blob[world][2][LIO_BLOB], stamp[world][2]} that its peers have mapped
-// (cudaIpc); after its local reduction the solver block stores its 92 doubles into slot [rank][pass & 1] of every
-// rank's mailbox (plain peer stores), fences at system scope and stamps the slot; it then waits for the stamps of all
-// ranks in its own mailbox and adds the blobs in RANK ORDER, so that every rank forms the same bits and performs the
-// identical Kalman step.  Two slots suffice: a peer can only write pass p + 2 after it has received this rank's
-// pass p + 1 blob, which is sent after pass p has been read.  No NCCL call, no launch, no host on the path.
+// memory.  Every rank owns a mailbox of stamped words {words[world][2][LIO_BLOB][2]} that its peers have mapped
+// (cudaIpc).  After its local reduction the solver block stores its 92 doubles into slot [rank][pass & 1] of every
+// rank's mailbox as self-validating words (st_stamped at system scope: value and stamp travel in the same 8-byte store),
+// then polls its own mailbox until every word of every rank carries this pass's stamp and adds the blobs in RANK ORDER,
+// so that every rank forms the same bits and performs the identical Kalman step.  No fence, no flag, no second hop: the
+// exchange costs one NVLink store latency plus the skew between the ranks.  Two slots suffice: a peer can only write
+// pass p + 2 after it has received this rank's pass p + 1 blob, which is sent after pass p has been read.  No NCCL
+// call, no launch, no host on the path.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LIO_MAX_RANKS = 8;
 struct ShardArgs {
   int world, rank;
-  double* mbox[LIO_MAX_RANKS];     // mailbox blobs of every rank as mapped in THIS process ([rank] = own)
-  unsigned* stamp[LIO_MAX_RANKS];  // mailbox stamps of every rank
-  int* err;                        // set to 1 when a peer did not show up in time
-  unsigned epoch;                  // stamp base of this sharded launch (advances in lockstep on all ranks)
+  unsigned long long* mbox[LIO_MAX_RANKS];  // mailbox words of every rank as mapped in THIS process ([rank] = own)
+  int* err;                                 // set to 1 when a peer did not show up in time
+  unsigned epoch;                           // stamp base of this sharded launch (advances in lockstep on all ranks)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void st_stamped_sys(unsigned long long* p, double v, unsigned stamp) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long hs = (unsigned long long)stamp << 32;
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(hs | (b & 0xffffffffull)), "l"(hs | (b >> 32))
+               : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ bool ld_stamped_sys(const unsigned long long* p, unsigned stamp, double& v) {
+  unsigned long long lo, hi;
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+  return (unsigned)(lo >> 32) == stamp && (unsigned)(hi >> 32) == stamp;
 }
 
-__device__ __noinline__ void block_exchange(const ShardArgs& sh, unsigned target, int pass_no, double* s_blob) {
+__device__ __noinline__ void block_exchange(const ShardArgs& sh, unsigned target, int pass_no, double* s_blob,
+                                            double* s_in) {
   const int tid = threadIdx.x;
   const int slot = pass_no & 1;
-  // 1. this rank's blob into everybody's mailbox (own included)
+  const int total = sh.world * LIO_BLOB;
+  // 1. this rank's blob into everybody's mailbox (own included), the remote ones first
 #pragma unroll 1
-  for (int k = tid; k < sh.world * LIO_BLOB; k += THREADS) {
-    const int p = k / LIO_BLOB, e = k - p * LIO_BLOB;
-    sh.mbox[p][((size_t)sh.rank * 2 + slot) * LIO_BLOB + e] = s_blob[e];
+  for (int k = tid; k < total; k += THREADS) {
+    const int pp = k / LIO_BLOB, e = k - pp * LIO_BLOB;
+    const int p = (sh.rank + 1 + pp) % sh.world;
+    st_stamped_sys(sh.mbox[p] + (((size_t)sh.rank * 2 + slot) * LIO_BLOB + e) * 2, s_blob[e], target);
   }
-  __threadfence_system();
-  __syncthreads();
-  if (tid < sh.world) st_release_sys(sh.stamp[tid] + sh.rank * 2 + slot, target);
-  // 2. wait for every rank's stamp in the own mailbox (bounded: a missing peer must not hang the GPU)
-  if (tid < sh.world) {
-    const unsigned* f = sh.stamp[sh.rank] + tid * 2 + slot;
+  // 2. every rank's blob out of the own mailbox, each word polled until it carries the stamp (bounded: a missing peer
+  //    must not hang the GPU).  Uniform control flow per warp (see block_step on split warps).
+  const unsigned long long* mine = sh.mbox[sh.rank];
+#pragma unroll 1
+  for (int k0 = 0; k0 < total; k0 += THREADS) {
+    const int k = min(k0 + tid, total - 1);
+    const int r = k / LIO_BLOB, e = k - r * LIO_BLOB;
+    const unsigned long long* w = mine + (((size_t)r * 2 + slot) * LIO_BLOB + e) * 2;
+    double v;
+    bool ok;
     long long spins = 0;
-    while ((ld_acquire_sys(f) - target) >= 0x40000000u) {
-      if (++spins > 400000000LL) {
+    do {
+      ok = ld_stamped_sys(w, target, v);
+      if (!ok && ++spins > 200000000LL) {
         *sh.err = 1;
-        break;
+        ok = true;
       }
-    }
+    } while (!__all_sync(0xffffffffu, ok));
+    if (k0 + tid < total) s_in[k] = v;
   }
   __syncthreads();
   // 3. sum in rank order
   if (tid < LIO_BLOB) {
-    const volatile double* mine = sh.mbox[sh.rank];
     double acc = 0.0;
 #pragma unroll 1
-    for (int r = 0; r < sh.world; ++r) acc += mine[((size_t)r * 2 + slot) * LIO_BLOB + tid];
+    for (int r = 0; r < sh.world; ++r) acc += s_in[r * LIO_BLOB + tid];
     if (tid == 91) acc = s_blob[91];
     s_blob[tid] = acc;
   }
@@ -1137,7 +1213,7 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
       const unsigned target = epoch + (unsigned)pass_no + 1u;
       stamp(a.dbg, 128, 10);
       block_reduce_partials(a, search, nworkers, target, ss.blob, ss.warp_part);
-      if (sh.world > 1) block_exchange(sh, sh.epoch + (unsigned)pass_no + 1u, pass_no, ss.blob);
+      if (sh.world > 1) block_exchange(sh, sh.epoch + (unsigned)pass_no + 1u, pass_no, ss.blob, ss.warp_part);
       stamp(a.dbg, 128, 11);
       block_step(s, n, &ss, target);
       stamp(a.dbg, 128, 12);
@@ -1171,7 +1247,10 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
   const StateD* x_first =
       (HOST && hp.use_param_prior) ? reinterpret_cast<const StateD*>(hp.x0) : (s.from_snapshot ? s.x0 : s.x);
   stamp(a.dbg, 0, 1);
-  if (tid == 0) load_pass_const(x_first, ps.pc);  // pass 0 searches at the prior
+  if (tid == 0) {
+    load_pass_const(x_first, ps.pc);  // pass 0 searches at the prior
+    ps.n_own = -1;
+  }
   __syncthreads();
   bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
@@ -1271,6 +1350,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
   if ((int)blockIdx.x < nworkers) {
     if (tid == 0) {
       load_pass_const(s.x, ps.pc);
+      ps.n_own = -1;  // (a launch per pass: the ownership list is rebuilt from a.near_q)
       if (a.stage) {
         mbar_init(&st->mbar, THREADS);
         st->phase = 0;
@@ -1506,6 +1586,7 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.rings = c->knn_rings;
   a.own_min = own_min;
   a.own_max = own_max;
+  a.sharded = !(own_min == -INFINITY && own_max == INFINITY) ? 1 : 0;
   a.stage = c->stage_search ? 1 : 0;
   a.partials = c->d_partials;
   a.dbg = c->d_dbg;
@@ -1577,7 +1658,6 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
     sh.rank = c->peer_rank;
     for (int r = 0; r < c->peer_world; ++r) {
       sh.mbox[r] = c->peer_mbox[r];
-      sh.stamp[r] = c->peer_stamp[r];
     }
     sh.err = c->d_peer_err;
     sh.epoch = c->peer_epoch;

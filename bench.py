@@ -72,6 +72,11 @@ def parse():
     ap.add_argument("--sync-growth", action="store_true",
                     help="trajectory workloads: wait for each scan's map growth inside its step (default: deferred, the "
                          "step returns with the posterior as the reference publishes before map_incremental)")
+    ap.add_argument("--legs", default="auto", help="extra legs of the default workload's line: 'auto' = sharded + os1_64_seqs "
+                    "when N > 1, knn_hbm + dense_scene when N = 1; 'none'; or a comma list of those names")
+    ap.add_argument("--sharded-map-points", type=int, default=50_000_000, help="map size of the `sharded` extra leg")
+    ap.add_argument("--e2e-steps", type=int, default=200, help="the e2e leg times max(--steps, this) steps and reports the "
+                    "median step (one OS hiccup on one rank does not set an 8-rank number)")
     ap.add_argument("--map-cell", type=float, default=0.0, help="kNN hash cell edge [m] (0: library default); no effect on results")
     return ap.parse_args()
 
@@ -320,6 +325,15 @@ def traj_cpu_arm(seq, warmup, steps, seconds_budget, threads=None):
 
 
 def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
+    line = traj_leg(args, rank, world, local, dev, torch, dist, _cabi, cpu_baseline=not args.no_cpu_baseline)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def traj_leg(args, rank, world, local, dev, torch, dist, _cabi, cpu_baseline=False):
     """Configs 2 and 4: one step = one scan of every sequence through the whole main loop of laserMapping.cpp:702-800.
     The raw scan and the IMU samples come from host memory every step by nature, so `value` is host-timed end to end
     (= `e2e`); max over ranks; the sequences of a GPU share one cooperative update launch per scan."""
@@ -419,26 +433,43 @@ def traj_main(args, rank, world, local, dev, torch, dist, _cabi):
                      "note": "B_scan = 16N + 16M + 116*M*I (SURVEY.md §8d); latency- and host-bound"},
         "clocks": clocks,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and cpu_baseline:
         r = traj_cpu_arm(seqs[0], args.warmup, args.steps, args.cpu_seconds)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                 "kind_detail": r["kind_detail"],
                                 "sample": "%d scans of sequence 0 through the same loop" % r["steps"]}
         r3 = traj_cpu_arm(seqs[0], args.warmup, args.steps, min(8.0, args.cpu_seconds), threads=3)
         line["cpu_baseline_3_threads"] = {"value": r3["value"], "unit": UNIT, "cores": 3}
-    if rank == 0:
-        print(json.dumps(line))
     for r in runs:
         r.close()
     for c in ctxs:
         c.close()
+    return line
+
+
+# ------------------------------------------------------------------------------------------ sharded map (config 5)
+def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
+    line = sharded_leg(args, rank, world, local, dev, torch, dist, _cabi)
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-# ------------------------------------------------------------------------------------------ sharded map (config 5)
-def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
+def _world_x(body, x):
+    """x coordinate of p_world = rot * (R_LI * p + t_LI) + pos for the points of a downsampled scan (host, FP64)."""
+    def rot(q):
+        w, a, b, c = q
+        return np.array([[1 - 2 * (b * b + c * c), 2 * (a * b - w * c), 2 * (a * c + w * b)],
+                         [2 * (a * b + w * c), 1 - 2 * (a * a + c * c), 2 * (b * c - w * a)],
+                         [2 * (a * c - w * b), 2 * (b * c + w * a), 1 - 2 * (a * a + b * b)]])
+    x = np.asarray(x, np.float64)
+    pi = np.asarray(body[:, :3], np.float64) @ rot(x[7:11]).T + x[11:14]
+    return (pi @ rot(x[3:7]).T + x[0:3])[:, 0]
+
+
+def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
     """One map in x-slabs over the ranks; every rank runs every pass on the whole scan against its slab (+ halo) and
     contributes the rows of the queries it owns; one NCCL all-reduce of 92 doubles per pass; identical Kalman step on
     every rank.  Strong scaling: the same scans, whatever the number of GPUs."""
@@ -523,6 +554,31 @@ def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
         same = bool(torch.equal(xs, x0))
     else:
         same = True
+    # how the scan splits over the ranks (points whose p_world.x lies in the rank's window, at the last posterior)
+    j_last = (args.steps - 1) % len(bodies)  # run(steps, 0): step k replays scan k % len(bodies)
+    pw_x = _world_x(bodies[j_last], x_last)
+    owned = int(((pw_x >= own[0]) & (pw_x < own[1])).sum())
+    owned_max = owned
+    vs_single = None
+    if world > 1:
+        t = torch.tensor([owned], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        owned_max = int(t.item())
+        if rank == 0:
+            # the same scan against the WHOLE map in one context on this GPU: what a single GPU would have answered
+            c1 = _cabi.Context(local, max_scan_points=1 << 12, max_down_points=100000,
+                               max_map_points=max(1 << 20, int(len(mp) * 1.02)))
+            c1.set_stream(stream.cuda_stream)
+            c1.map_build(np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1))
+            c1.scan_upload(bodies[j_last])
+            c1.state_upload(wl["scans"][j_last]["x_prior"], wl["P"])
+            c1.update_enqueue(R_COV, wl["max_iter"], wl["ext"], from_snapshot=True)
+            x1, P1, nv1, np1 = c1.state_download()
+            c1.close()
+            vs_single = {"max_abs_state_diff": float(np.abs(np.asarray(x_last) - np.asarray(x1)).max()),
+                         "pos_diff_m": float(np.abs(np.asarray(x_last)[0:3] - np.asarray(x1)[0:3]).max()),
+                         "passes_single": int(np1)}
+        barrier()
     peak, peak_src = measured_peak()
     passes = npass / args.steps
     alg = 116.0 * M * passes
@@ -534,7 +590,8 @@ def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
                    "%s" % (len(mp), world, args.rings, args.cols,
                            "blobs exchanged inside the persistent kernel over NVLink peer memory" if fused else
                            "NCCL all-reduce of 92 doubles per pass between pass and solve kernels"), "M": M,
-                   "passes_per_scan": passes, "local_map_points": int(len(keep)),
+                   "passes_per_scan": passes, "local_map_points": int(len(keep)), "owned_points_max_rank": owned_max,
+                   "vs_single_gpu": vs_single,
                    "l2": "flushed (384 MiB write) before every timed step", "states_identical_across_ranks": same},
         "matched_pts_per_s": nvalid / (ms / 1000.0), "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "update_kernel with in-kernel peer exchange" if fused else
@@ -543,12 +600,100 @@ def sharded_main(args, rank, world, local, dev, torch, dist, _cabi):
                      "frac": alg / (ms / args.steps * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
         "clocks": clocks,
     }
-    if rank == 0:
-        print(json.dumps(line))
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return line
+
+
+
+# ------------------------------------------------------------------------------------------ extra legs at N = 1
+def knn_hbm_leg(args, local, dev, torch, _cabi):
+    """The search kernel against HBM (north_star: achieved bandwidth of the kNN kernel): batched 5-NN on a 50M-point map
+    (800 MB of points + the cell table: far beyond L2), 1M queries per launch, CUDA events.  queries/s is measured here;
+    DRAM bytes per query come from the committed ncu capture of the same kernel on the same map and query order."""
+    from agi_lidar_slam_b200 import synth
+
+    n_map, nq = args.sharded_map_points, 1_000_000
+    _, mp = synth.city_map(n_map, 5005)
+    rng = np.random.default_rng(1)
+    # scan order: a real downsampled scan arrives sorted by voxel (kz, ky, kx); random: no locality at all
+    sel = rng.integers(0, len(mp), nq)
+    q = np.ascontiguousarray(mp[sel] + rng.normal(0, 0.15, (nq, 3)).astype(np.float32), np.float32)
+    cell = np.floor(q / 0.5).astype(np.int64)
+    order = np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))
+    ctx = _cabi.Context(local, max_scan_points=1 << 16, max_down_points=nq, max_map_points=int(len(mp) * 1.02))
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.map_build(np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1))
+    ctx.synchronize()
+    out = {"map_points": int(len(mp)), "queries_per_launch": nq, "unit": "queries/s",
+           "algorithmic_bytes_per_query": 116}
+    cap = {}
+    f = ROOT / "profiles" / "r2_knn_hbm.json"
+    if f.exists():
+        cap = json.loads(f.read_text())
+    peak, peak_src = measured_peak()
+    for name, qq in (("random", q), ("scan_order", q[order])):
+        ctx._check(ctx._lib.lio_knn5(ctx._h, qq.ctypes.data, nq, 5.0, None, None, None))  # queries -> device
+        ts = []
+        for rep in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.knn5_resident(nq)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts[1:]))
+        leg = {"ms_per_launch": ms, "queries_per_s": nq / (ms * 1e-3)}
+        c = cap.get(name)
+        if c:  # DRAM bytes of the ncu capture applied to the duration measured here
+            leg["dram_bytes_per_query"] = c["dram_bytes_per_launch"] / c["queries_per_launch"]
+            leg["dram_GBps"] = leg["dram_bytes_per_query"] * nq / (ms * 1e-3) / 1e9
+            leg["frac_of_hbm_peak"] = leg["dram_GBps"] / peak
+            leg["ncu_ms_per_launch"] = c["ms_per_launch"]
+        out[name] = leg
+    out["traffic_source"] = "profiles/r2_knn_hbm.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of knn_batch_kernel)" if cap else None
+    out["peak"], out["peak_source"] = peak, peak_src
+    ctx.close()
+    return out
+
+
+def dense_leg(args, wl, map4, local, dev, torch, _cabi, stream):
+    """The same update on a dense scan: the OS1-128 scans downsampled at 0.15 m instead of 0.5 m (M ~ 40k, the size
+    SURVEY.md 8d's worked example assumes): multi-tile chunks and 8-lane search groups.  Device-timed, L2 flushed."""
+    n_map = len(map4)
+    ctx = _cabi.Context(local, max_scan_points=max(1 << 18, args.rings * args.cols), max_down_points=150000,
+                        max_map_points=max(1 << 21, int(n_map * 1.05)))
+    ctx.set_stream(stream.cuda_stream)
+    ctx.map_build(map4)
+    bodies = [np.ascontiguousarray(ctx.scan_preprocess(s["scan"], None, None, 0.15)[0]) for s in wl["scans"]]
+    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    evs, npass, nvalid = [], 0, 0
+    steps = min(args.steps, 20)
+    for k in range(3 + steps):
+        j = k % len(bodies)
+        ctx.scan_upload(bodies[j])
+        ctx.state_upload(wl["scans"][j]["x_prior"], wl["P"])
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.update_enqueue(R_COV, wl["max_iter"], wl["ext"], from_snapshot=True)
+        e1.record(stream)
+        x, P, nv, npz = ctx.state_download()
+        if k >= 3:
+            evs.append((e0, e1))
+            npass += npz
+            nvalid += nv
+    torch.cuda.synchronize(dev)
+    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    M = int(np.mean([len(b) for b in bodies]))
+    passes = npass / steps
+    peak, _ = measured_peak()
+    ctx.close()
+    return {"value": 1000.0 / ms, "unit": UNIT, "ms_per_step": ms, "steps": steps, "M": M, "passes_per_scan": passes,
+            "matched_pts_per_s": nvalid / steps / (ms * 1e-3), "surf_leaf": 0.15,
+            "roofline_frac": 116.0 * M * passes / (ms * 1e-3) / 1e9 / peak,
+            "what": "update of the same OS1-128 scans downsampled at 0.15 m (dense scene), device-resident, cold L2"}
 
 
 # ------------------------------------------------------------------------------------------ main
@@ -700,7 +845,7 @@ def main():
 
     # ---------------------------------------------------------------- e2e: host buffers through the C-ABI
     def e2e_run(steps, warmup):
-        t_ms = 0.0
+        ts = []
         for k in range(warmup + steps):
             j = k % len(bodies)
             l2_flush()
@@ -713,16 +858,20 @@ def main():
             ctx.update_scan_host(bodies_np[j], x_io, P_io, R_COV, wl["max_iter"], wl["ext"])
             dt = time.perf_counter() - t0  # returns after the D2H of the posterior (host sync)
             if k >= warmup:
-                t_ms += dt * 1000.0
-        return t_ms
+                ts.append(dt * 1000.0)
+        return np.asarray(ts)
 
     bodies_np = [b.numpy() for b in bodies]  # views of the pinned tensors
     x_io, P_io = np.zeros(26), np.zeros((24, 24))
+    e2e_steps = max(args.steps, args.e2e_steps)
     e2e_run(0, 3)
     barrier()
-    e2e_ms = max_over_ranks(e2e_run(args.steps, 0))
+    e2e_ts = e2e_run(e2e_steps, 0)
     barrier()
-    e2e_value = n_gpus * args.steps / (e2e_ms / 1000.0)
+    # the step a rank typically takes (median over >= 200 steps), max over ranks; the mean over the same window beside it
+    e2e_med_ms = max_over_ranks(float(np.median(e2e_ts)))
+    e2e_mean_ms = max_over_ranks(float(np.mean(e2e_ts)))
+    e2e_value = n_gpus / (e2e_med_ms / 1000.0)
     clocks = sampler.stop()  # sampled over both timed regions (device-resident and end-to-end)
     h2d = M * 16 + 602 * 8  # scan (one copy) + prior {x, P} (kernel parameters)
     d2h = 607 * 8  # posterior {x, P, loop state} + sequence word, written by the kernel into mapped pinned memory
@@ -861,11 +1010,46 @@ def main():
         "full_scan": {"value": full_value, "unit": UNIT,
                       "what": "raw scan H2D + voxel downsample + update + posterior D2H through one lio_scan_step call (static map), host-timed"},
         "preprocess": preprocess,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step_median": e2e_med_ms, "ms_per_step_mean": e2e_mean_ms,
+                "value_from_mean": n_gpus / (e2e_mean_ms / 1000.0),
+                "how": "n_gpus / (max over ranks of the median host-timed step over `steps` steps)"},
         "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
     }
     if multi:
         line["multi_sequence"] = multi
+
+    ctx.close()
+    del flush
+    torch.cuda.empty_cache()
+    legs = args.legs
+    if legs == "auto":
+        legs = "sharded,os1_64_seqs" if world > 1 else "knn_hbm,dense_scene"
+    legs = [] if legs == "none" else [v.strip() for v in legs.split(",") if v.strip()]
+    sub = argparse.Namespace(**vars(args))
+    sub.steps, sub.warmup = min(args.steps, 30), max(3, min(args.warmup, 5))
+    if "sharded" in legs and world > 1:
+        # config 5: ONE map cut into x-slabs over the ranks, the same scans on every rank, strong scaling
+        sub.map_points, sub.workload = args.sharded_map_points, "sharded"
+        r = sharded_leg(sub, rank, world, local, dev, torch, dist, _cabi)
+        line["sharded"] = {"value": r["value"], "unit": UNIT, "scaling": "strong", "ms_per_step": r["ms_per_step"],
+                           "steps": sub.steps, "exchange": args.exchange, "map_points": args.sharded_map_points,
+                           "local_map_points": r["config"]["local_map_points"], "M": r["config"]["M"],
+                           "owned_points_max_rank": r["config"].get("owned_points_max_rank"),
+                           "passes_per_scan": r["config"]["passes_per_scan"],
+                           "states_identical": r["config"]["states_identical_across_ranks"],
+                           "vs_single_gpu": r["config"].get("vs_single_gpu"), "what": r["config"]["workload"]}
+    if "os1_64_seqs" in legs and world > 1:
+        # config 4: 8 independent OS1-64 sequences per GPU through the whole main loop
+        sub.workload, sub.seqs_per_gpu = "os1_64_seqs", 8
+        r = traj_leg(sub, rank, world, local, dev, torch, dist, _cabi)
+        line["os1_64_seqs"] = {"value": r["value"], "unit": UNIT, "scaling": "weak", "ms_per_step": r["ms_per_step"],
+                               "steps": sub.steps, "sequences": 8 * world, "host_threads": r["config"]["host_threads"],
+                               "M": r["config"]["M"], "N_raw": r["config"]["N_raw"], "what": r["config"]["workload"]}
+    if "knn_hbm" in legs and world == 1:
+        line["knn_hbm"] = knn_hbm_leg(args, local, dev, torch, _cabi)
+    if "dense_scene" in legs and world == 1:
+        line["dense_scene"] = dense_leg(args, wl, map4, local, dev, torch, _cabi, stream)
 
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         r = cpu_arm(wl, steps=1000, warmup=1, seconds_budget=args.cpu_seconds)
@@ -879,7 +1063,6 @@ def main():
                                           "note": "MP_PROC_NUM=3, the reference's own setting (CMakeLists.txt:23-26)"}
     if rank == 0:
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

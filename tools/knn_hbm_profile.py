@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""profiles/r2_knn_hbm.json from an ncu launch list of tools/knn_roofline.py:
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,\\
+l1tex__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none \\
+        -k regex:knn_batch_kernel --csv --log-file gpurun_out/r2_knn_hbm.csv python tools/knn_roofline.py --reps 3
+The 1M-query launches split evenly: first half random queries, second half scan-ordered ones (the tool's order)."""
+import csv
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+src = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "gpurun_out" / "r2_knn_hbm.csv"
+rows = list(csv.DictReader([l for l in open(src) if not l.startswith("==")]))
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "%": 1.0}
+launches = {}
+for r in rows:
+    d = launches.setdefault(int(r["ID"]), {"grid": r["Grid Size"]})
+    d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * scale.get(r["Metric Unit"], 1.0)
+big = [v for k, v in sorted(launches.items()) if v.get("dram__bytes_read.sum", 0) > 1e8]
+half = len(big) // 2
+out = {"source": str(src.name), "map_points": 50_000_000}
+for name, ls in (("random", big[:half]), ("scan_order", big[half:])):
+    ls = ls[1:]  # the first launch of an order also pays for first-touch effects
+    n = len(ls)
+    out[name] = {"queries_per_launch": 1_000_000, "launches": n,
+                 "ms_per_launch": sum(l["gpu__time_duration.sum"] for l in ls) / n,
+                 "dram_bytes_per_launch": sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in ls) / n,
+                 "lts_hit_pct": sum(l.get("lts__t_sector_hit_rate.pct", 0) for l in ls) / n,
+                 "l1tex_hit_pct": sum(l.get("l1tex__t_sector_hit_rate.pct", 0) for l in ls) / n,
+                 "warps_active_pct": sum(l.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0) for l in ls) / n}
+    o = out[name]
+    o["dram_bytes_per_query"] = o["dram_bytes_per_launch"] / o["queries_per_launch"]
+    o["dram_GBps"] = o["dram_bytes_per_launch"] / (o["ms_per_launch"] * 1e-3) / 1e9
+(ROOT / "profiles" / "r2_knn_hbm.json").write_text(json.dumps(out, indent=1) + "\n")
+print(json.dumps(out, indent=1))

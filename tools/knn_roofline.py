@@ -33,8 +33,12 @@ def main():
     print(f"map: {len(mp)} points, extent {np.ptp(mp[:, 0]):.0f} x {np.ptp(mp[:, 1]):.0f} m, generated in {time.time() - t0:.1f} s",
           flush=True)
     rng = np.random.default_rng(1)
+    a.queries = min(a.queries, 1_000_000)  # one launch worth: the two query orders below use the same points
     q = mp[rng.integers(0, len(mp), a.queries)] + rng.normal(0, 0.15, (a.queries, 3)).astype(np.float32)
     q = np.ascontiguousarray(q, np.float32)
+    # scan order: a real downsampled scan arrives sorted by voxel (kz, ky, kx) -- neighbouring queries share cells
+    cell = np.floor(q / 0.5).astype(np.int64)
+    q_scan = np.ascontiguousarray(q[np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))])
     chunk = min(a.queries, 1_000_000)  # queries per launch (they go through the scan-sized buffers)
     ctx = _cabi.Context(0, max_scan_points=1 << 16, max_down_points=chunk, max_map_points=int(len(mp) * 1.02))
     t0 = time.time()
@@ -54,11 +58,10 @@ def main():
         ok = dd[o] <= 5.0
         assert np.array_equal(idx[k][ok], o[ok].astype(np.int32)), (idx[k], o)
     found5 = float((idx[:, 4] >= 0).mean())
-    times = []
-    nq = (a.queries // chunk) * chunk
-    for off in range(0, nq, chunk):
-        ctx.knn5(q[off:off + chunk], want_xyz=False) if False else ctx._check(
-            ctx._lib.lio_knn5(ctx._h, q[off:off + chunk].ctypes.data, chunk, 5.0, None, None, None))  # queries -> device
+    # per order: one lio_knn5 call that brings the queries to the device (1 launch) + reps + 1 resident launches
+    for name, qq in (("random", q), ("scan_order", q_scan)):
+        times = []
+        ctx._check(ctx._lib.lio_knn5(ctx._h, qq.ctypes.data, chunk, 5.0, None, None, None))
         for rep in range(a.reps + 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -67,10 +70,9 @@ def main():
             torch.cuda.synchronize(dev)
             if rep:
                 times.append(e0.elapsed_time(e1))
-    ms = float(np.mean(times))
-    print(f"{chunk} queries per launch: {ms:.3f} ms -> {chunk / ms / 1e3:.1f} M queries/s; {found5:.2f} of the queries have 5 "
-          f"neighbours within sqrt(5) m")
-    print("algorithmic bytes (SURVEY.md 8d, 116 B per query): %.1f GB/s" % (116.0 * chunk / (ms * 1e-3) / 1e9))
+        ms = float(np.mean(times))
+        print(f"[{name}] {chunk} queries per launch: {ms:.3f} ms -> {chunk / ms / 1e3:.1f} M queries/s; {found5:.2f} of the "
+              f"queries have 5 neighbours within sqrt(5) m; algorithmic (116 B/query): {116.0 * chunk / (ms * 1e-3) / 1e9:.1f} GB/s")
 
 
 if __name__ == "__main__":
