@@ -102,7 +102,7 @@ EXPORTS = [
     "lio_update_enqueue_multi", "lio_scan_step", "lio_scan_step_begin", "lio_scan_step_end",
     "lio_scan_step_finish", "lio_scan_step_prefetch", "lio_set_deferred_growth", "lio_scan_step_settle", "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_peer_handle", "lio_peer_connect",
-    "lio_update_enqueue_sharded", "lio_peer_status", "lio_pass_only_enqueue", "lio_debug_timeline",
+    "lio_update_enqueue_sharded", "lio_peer_status", "lio_set_shard_stripes", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
     "lio_imu_proc_init", "lio_imu_set_param", "lio_imu_process",
     "lio_seq_default_config", "lio_seq_create", "lio_seq_destroy", "lio_seq_process", "lio_seq_process_many",
@@ -174,6 +174,7 @@ def load_library() -> C.CDLL:
         "lio_update_enqueue_sharded": (C.c_int, [vp, f64, C.c_int, C.c_int, C.c_int, f32, f32]),
         "lio_peer_status": (C.c_int, [vp, P(i32)]),
         "lio_pass_only_enqueue": (C.c_int, [vp, C.c_int, C.c_int]),
+        "lio_set_shard_stripes": (C.c_int, [vp, f32, f32, C.c_int, C.c_int]),
         "lio_debug_timeline": (C.c_int, [vp, vp]),
         "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "lio_map_incremental": (C.c_int, [vp, vp, f32, C.c_int, vp]),
@@ -501,6 +502,9 @@ class Context:
                                x_own_max=np.inf):
         self._check(self._lib.lio_update_enqueue_sharded(self._h, R, max_iter, int(extrinsic_est), int(from_snapshot),
                                                          x_own_min, x_own_max))
+
+    def set_shard_stripes(self, x_origin: float, stripe_width: float, world: int, rank: int):
+        self._check(self._lib.lio_set_shard_stripes(self._h, x_origin, stripe_width, world, rank))
 
     def peer_timed_out(self) -> bool:
         v = C.c_int32(0)

@@ -1148,6 +1148,21 @@ int lio_peer_connect(lio_ctx* c, int rank, int world, const unsigned char* handl
   return LIO_OK;
 }
 
+int lio_set_shard_stripes(lio_ctx* c, float x_origin, float stripe_width, int world, int rank) {
+  if (!c) return LIO_E_INVALID;
+  if (world == 0) {  // back to the x windows of the calls
+    c->stripe_world = 0;
+    return LIO_OK;
+  }
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || !(stripe_width > 0.f) || !(x_origin == x_origin))
+    return LIO_E_INVALID;
+  c->stripe_world = world;
+  c->stripe_rank = rank;
+  c->stripe_origin = x_origin;
+  c->stripe_width = stripe_width;
+  return LIO_OK;
+}
+
 int lio_update_enqueue_sharded(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot, float x_own_min,
                                float x_own_max) {
   if (!c || max_iter < 0 || max_iter > 32) return LIO_E_INVALID;
@@ -1178,7 +1193,7 @@ int lio_update_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snaps
 int lio_update_pass_enqueue(lio_ctx* c, int extrinsic_est, float x_own_min, float x_own_max) {
   if (!c) return LIO_E_INVALID;
   LIO_CHECK(c, cudaSetDevice(c->device));
-  return launch_pass(c, -1, extrinsic_est ? 1 : 0, x_own_min, x_own_max);
+  return launch_pass(c, -1, extrinsic_est ? 1 : 0, x_own_min, x_own_max, true);
 }
 
 int lio_update_step_enqueue(lio_ctx* c, double R, int extrinsic_est) {

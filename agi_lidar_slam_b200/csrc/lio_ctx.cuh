@@ -58,6 +58,9 @@ struct lio_ctx {
   void* d_mailbox = nullptr;        // {stamped words [8 ranks][2 slots][LIO_BLOB][2]; int err}
   int peer_world = 0, peer_rank = 0;
   unsigned peer_epoch = 0;          // advanced by sharded launches only: stays in lockstep across the ranks
+  // striped ownership of the sharded calls (lio_set_shard_stripes); stripe_world == 0: the calls' x windows
+  int stripe_world = 0, stripe_rank = 0;
+  float stripe_origin = 0.f, stripe_width = 0.f;
   unsigned long long* peer_mbox[8] = {nullptr};
   void* peer_base[8] = {nullptr};   // cudaIpcOpenMemHandle results (closed in lio_destroy)
   int* d_peer_err = nullptr;
@@ -159,7 +162,7 @@ int pass_grid_blocks(lio_ctx* c);
 int launch_update(lio_ctx* c, double R, int max_iter, int extrinsic_est, int from_snapshot, float own_min = -INFINITY,
                   float own_max = INFINITY, bool sharded = false, const HostDirect* hd = nullptr);
 int launch_update_multi(lio_ctx* const* cs, int n, double R, int max_iter, int extrinsic_est, int from_snapshot);
-int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float own_max);
+int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float own_max, bool sharded_call = false);
 int launch_solve(lio_ctx* c, double R, int extrinsic_est);
 int launch_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot);
 int launch_knn_batch(lio_ctx* c, const float4* d_q, int64_t m);

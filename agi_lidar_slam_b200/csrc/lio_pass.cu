@@ -67,7 +67,11 @@ struct PassArgs {
   float max_d2, plane_thr;
   int rings;
   float own_min, own_max;
-  int sharded;  // the window above is finite: rows are shared out over the ranks
+  int sharded;  // rows are shared out over the ranks (a finite window, or stripes)
+  // striped ownership (lio_set_shard_stripes): the rank owns the stripes s = floor((x - origin) / width) with
+  // s mod stripe_mod == stripe_rank; stripe_mod == 0: the window above
+  float stripe_origin, stripe_inv_w;
+  int stripe_mod, stripe_rank;
   int stage;  // 1: the searches of a tile stage its neighbour cells in shared memory first (stage_cells)
   unsigned long long* partials;  // [workers][ROW_WORDS]: one row of stamped words per worker block (st_stamped)
   long long* dbg;    // optional timeline (LIO_TIMELINE=1): [0] = entries used by block 0, [1..] = (tag, globaltimer ns)
@@ -185,26 +189,47 @@ __device__ __forceinline__ void body_to_world(const PassConst& pc, const double 
 
 constexpr int SROWS_MAX = THREADS / 8;  // rows of a search tile at the smallest group size
 
+// Does this rank own a row searched at world x = qx?  The same FP32 operations on every rank: the answers partition the rows.
+__device__ __forceinline__ bool owns_row(const PassArgs& a, float qx) {
+  if (a.stripe_mod > 0) {
+    const int st = (int)floorf((qx - a.stripe_origin) * a.stripe_inv_w);
+    int r = st % a.stripe_mod;
+    if (r < 0) r += a.stripe_mod;
+    return r == a.stripe_rank;
+  }
+  return (qx >= a.own_min) && (qx < a.own_max);
+}
+
 // A block works through positions t = 0 .. n-1 of its chunk of the scan: all of its points in order, or -- sharded map --
 // only the ones this rank owns (list = their offsets in the chunk, ascending).
 constexpr int OWN_MAX = 2048;  // longest chunk a list is kept for (beyond: every point is visited and the rows are masked)
-__device__ __forceinline__ int point_index(int beg, const unsigned short* list, int t) {
-  return beg + (list ? (int)list[t] : t);
-}
+// Which points a block visits.  Unsharded: its contiguous chunk [beg, beg + C) (neighbouring queries share cells).
+// Sharded: runs of 8 points dealt round-robin over the blocks (run g = r * nworkers + wid), so that every block holds a
+// uniform sample of the scan and owns ~1/world of it whatever the shape of the ranks' regions -- with contiguous chunks
+// (28 m of scan each) whole blocks fall to one rank and the slowest block of a pass is as slow as on one GPU.
+struct Chunk {
+  int beg, wid, nworkers;
+  const unsigned short* list;  // sharded: offsets k of the owned points, ascending; else nullptr (k = t)
+  __device__ __forceinline__ int point(int k) const {
+    return list ? ((((k >> 3) * nworkers + wid) << 3) + (k & 7)) : beg + k;
+  }
+  __device__ __forceinline__ int at(int t) const { return point(list ? (int)list[t] : t); }
+};
+__device__ __forceinline__ bool sharded_lists(const PassArgs& a, int C) { return a.sharded && C <= OWN_MAX; }
 
 // Search phase of one tile: its queries (at most THREADS / G), one per G-lane group (esekfom.hpp:140).  The 5 neighbours
 // go to the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.  With staging
 // on the caller has staged the tile's neighbour cells (stage_cells); use_stage says whether the tile fitted.
 template <int G>
-__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int t0, int n, int beg,
-                                         const unsigned short* list, float4* s_nb, int* s_cnt, float4* s_body,
+__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk ch,
+                                         float4* s_nb, int* s_cnt, float4* s_body,
                                          const float4* body, StageSmem* st, bool use_stage) {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int row = threadIdx.x / G;
   const bool act = t0 + row < n;  // group-uniform
   const int qi = act ? row : n - 1 - t0;  // idle groups redo the last query: the whole warp stays together for the shuffles
-  const int i = point_index(beg, list, t0 + qi);
+  const int i = ch.at(t0 + qi);
   const float4 b = body[i];  // device copy, or the caller's pinned host buffer in pass 0 of the host-direct path
   if (gl == 0 && act) s_body[row] = b;
   const double pb[3] = {b.x, b.y, b.z};
@@ -248,8 +273,8 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
 
 // Finish phase of one tile, one thread per point: steps 1.1-1.2 and 1.5-3 of h_share_model (esekfom.hpp:123-133,
 // 153-226) from the point's 5 neighbours (just found: shared memory; cached: a.near_pts with the sticky mask).
-__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int t0, int n, int beg,
-                                         const unsigned short* list, int rows, bool search, const float4* s_nb,
+__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk ch,
+                                         int rows, bool search, const float4* s_nb,
                                          const int* s_cnt, double* s_rows, unsigned char* s_valid, const float4* s_body,
                                          bool copy_body) {
   const int row = threadIdx.x;
@@ -258,7 +283,8 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
     s_valid[row] = 0;
     return;
   }
-  const int i = point_index(beg, list, t0 + row);
+  const int i = ch.at(t0 + row);
+  const unsigned short* list = ch.list;
   const float4 b = search ? s_body[row] : __ldcg(a.body + i);  // the search phase left it in shared memory
   if (copy_body) const_cast<float4*>(a.body)[i] = b;            // host-direct path, pass 0: keep a device copy
   const double pb[3] = {b.x, b.y, b.z};
@@ -303,7 +329,7 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
   // the next search pass, so a row and its cached neighbours stay with one rank.  Listed rows are owned by construction.
   float qx = pwx;
   if (!list && !search && a.sharded) qx = __ldcg(&a.near_q[i]).x;
-  const bool valid = sel && (list != nullptr || ((qx >= a.own_min) && (qx < a.own_max)));
+  const bool valid = sel && (list != nullptr || owns_row(a, qx));
   s_valid[row] = valid ? 1 : 0;
   if (valid) {
     // step 3 (esekfom.hpp:197-226): Jacobian row and residual
@@ -440,7 +466,9 @@ __device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout,
 __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool search, int nworkers, unsigned target,
                                                    double* s_blob, double* s_warp) {
   const int tid = threadIdx.x;
-  const int nb = workers_used(scan_size(a), nworkers);
+  const int Ms = scan_size(a);
+  // (sharded lists: the runs of the scan are dealt over ALL the workers, every one of them files a row)
+  const int nb = sharded_lists(a, chunk_points(Ms, nworkers)) ? nworkers : workers_used(Ms, nworkers);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   if (a.extrinsic_est)
     reduce_rows<3, 8>(a, nb, nout, target, s_warp);
@@ -972,20 +1000,21 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
   stamp(a.dbg, 0, 2);
   const int C = chunk_points(M, nworkers);
   const int beg = wid * C;
-  if (beg >= M) return;  // block-uniform
+  const bool compact = sharded_lists(a, C);
+  if (!compact && beg >= M) return;  // block-uniform
   const int end = min(M, beg + C);
-  // ---- sharded map: the points of this chunk the rank owns = whose p_world.x AT THE LAST SEARCH PASS lies in its window.
+  Chunk ch{beg, wid, nworkers, compact ? ps->own : nullptr};
+  // ---- sharded map: the points of this block the rank owns = whose p_world.x AT THE LAST SEARCH PASS lies in its region.
   // Every rank computes the same bits for every point, so the ranks' lists partition the scan.  The list is rebuilt in
   // search passes (when the positions change) and kept across the cached passes that follow (the persistent kernel keeps
   // it in shared memory; a per-pass launch rebuilds it from a.near_q).
-  const bool compact = a.sharded && (end - beg) <= OWN_MAX;
   if (compact && (search || ps->n_own < 0)) {
     const int lane = tid & 31, warp = tid >> 5;
     int built = 0;
 #pragma unroll 1
-    for (int k0 = 0; k0 < end - beg; k0 += THREADS) {
-      const int k = k0 + tid, i = beg + k;
-      const bool in = k < end - beg;
+    for (int k0 = 0; k0 < C; k0 += THREADS) {
+      const int k = k0 + tid, i = ch.point(k);
+      const bool in = k < C && i < M;
       float qx = 0.f;
       if (in) {
         if (search) {
@@ -999,7 +1028,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
           qx = __ldcg(&a.near_q[i]).x;
         }
       }
-      const bool own = in && (qx >= a.own_min) && (qx < a.own_max);
+      const bool own = in && owns_row(a, qx);
       if (in && !own && search) {  // another rank's row: nothing cached here
         a.selected[i] = 0;
         a.near_cnt[i] = 0;
@@ -1019,7 +1048,6 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
     if (tid == 0) ps->n_own = built;
     __syncthreads();
   }
-  const unsigned short* list = compact ? ps->own : nullptr;
   const int n = compact ? ps->n_own : end - beg;
   const int G = pick_group(n);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
@@ -1050,7 +1078,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
       bool use_stage = false;
       if (a.stage) {
         if (tid < tend - t0) {  // the staging needs the queries first; search_tile recomputes the same bits
-          const float4 b = body[point_index(beg, list, t0 + tid)];
+          const float4 b = body[ch.at(t0 + tid)];
           const double pb[3] = {b.x, b.y, b.z};
           float pwx, pwy, pwz;
           body_to_world(ps->pc, pb, pwx, pwy, pwz);
@@ -1061,16 +1089,16 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
         use_stage = st->overflow == 0;
       }
       if (G == 32)
-        search_tile<32>(a, ps->pc, t0, n, beg, list, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<32>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       else if (G == 16)
-        search_tile<16>(a, ps->pc, t0, n, beg, list, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<16>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       else
-        search_tile<8>(a, ps->pc, t0, n, beg, list, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<8>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       __syncthreads();
       if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
       stamp(a.dbg, 0, 3);
     }
-    finish_tile(a, ps->pc, t0, n, beg, list, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
+    finish_tile(a, ps->pc, t0, n, ch, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
     __syncthreads();
     stamp(a.dbg, 0, 4);
     if (seg < nseg) {
@@ -1564,7 +1592,7 @@ int pass_grid_blocks(lio_ctx* c) {
   return c->pass_grid;
 }
 
-static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max) {
+static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max, bool sharded_call = false) {
   PassArgs a;
   a.body = c->d_body;
   a.scan_m = c->d_scan_m;
@@ -1586,7 +1614,11 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.rings = c->knn_rings;
   a.own_min = own_min;
   a.own_max = own_max;
-  a.sharded = !(own_min == -INFINITY && own_max == INFINITY) ? 1 : 0;
+  a.stripe_mod = sharded_call ? c->stripe_world : 0;
+  a.stripe_rank = c->stripe_rank;
+  a.stripe_origin = c->stripe_origin;
+  a.stripe_inv_w = c->stripe_width > 0.f ? 1.0f / c->stripe_width : 0.f;
+  a.sharded = (a.stripe_mod > 0 || !(own_min == -INFINITY && own_max == INFINITY)) ? 1 : 0;
   a.stage = c->stage_search ? 1 : 0;
   a.partials = c->d_partials;
   a.dbg = c->d_dbg;
@@ -1630,7 +1662,7 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
                   bool sharded, const HostDirect* hd) {
   int rc = ensure_tables(c);
   if (rc) return rc;
-  PassArgs a = make_pass_args(c, ext, own_min, own_max);
+  PassArgs a = make_pass_args(c, ext, own_min, own_max, sharded);
   static thread_local HostPath hp;  // 4.9 KB: kept off the stack frame of every call
   hp.use_param_prior = 0;
   hp.host_out = nullptr;
@@ -1698,10 +1730,10 @@ int launch_update_multi(lio_ctx* const* cs, int n, double R, int max_iter, int e
 }
 
 // mode: -1 = as the device loop state says, 0 = cached, 1 = search.  The reduced blob lands in c->d_blob.
-int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float own_max) {
+int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float own_max, bool sharded_call) {
   int rc = ensure_tables(c);
   if (rc) return rc;
-  PassArgs a = make_pass_args(c, extrinsic_est, own_min, own_max);
+  PassArgs a = make_pass_args(c, extrinsic_est, own_min, own_max, sharded_call);
   SolveArgs s = make_solve_args(c, 0.0, 0, 0);
   LIO_CHECK(c, cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
   if (const int re = epoch_guard(c, c)) return re;

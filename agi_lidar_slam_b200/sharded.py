@@ -33,6 +33,25 @@ def shard_indices(x_coords: np.ndarray, bounds: np.ndarray, rank: int, knn_max_d
     return np.nonzero((x >= bounds[rank] - halo) & (x < bounds[rank + 1] + halo))[0]
 
 
+def stripe_of(x_coords, x_origin: float, width: float) -> np.ndarray:
+    """Stripe number floor((x - origin) / width) in FP32, the arithmetic of the kernels (owns_row, csrc/lio_pass.cu)."""
+    x = np.asarray(x_coords, np.float32)
+    return np.floor((x - np.float32(x_origin)) * (np.float32(1.0) / np.float32(width))).astype(np.int64)
+
+
+def stripe_indices(x_coords: np.ndarray, x_origin: float, width: float, world: int, rank: int,
+                   knn_max_d2: float = 5.0) -> np.ndarray:
+    """Indices of the map points rank `rank` keeps under striped ownership (lio_set_shard_stripes): the points of its
+    stripes (stripe mod world == rank) plus the halo on both sides of every one of them.  width must exceed the halo."""
+    halo = np.float32(np.sqrt(knn_max_d2) + HALO_MARGIN)
+    assert width > halo
+    x = np.asarray(x_coords, np.float32)
+    keep = np.zeros(len(x), bool)
+    for dx in (np.float32(0), -halo, halo):  # own stripe, or within the halo of a neighbouring stripe that is ours
+        keep |= np.mod(stripe_of(x + dx, x_origin, width), world) == rank
+    return np.nonzero(keep)[0]
+
+
 class ShardedUpdate:
     """update_iterated_dyn_share_modified (esekfom.hpp:270-346) over a sharded map.
 

@@ -74,6 +74,8 @@ def parse():
                          "step returns with the posterior as the reference publishes before map_incremental)")
     ap.add_argument("--legs", default="auto", help="extra legs of the default workload's line: 'auto' = sharded + os1_64_seqs "
                     "when N > 1, knn_hbm + dense_scene when N = 1; 'none'; or a comma list of those names")
+    ap.add_argument("--shard-stripe", type=float, default=16.0, help="sharded map: width [m] of the x stripes dealt round-robin "
+                    "to the ranks (lio_set_shard_stripes); 0 = one contiguous x slab per rank")
     ap.add_argument("--sharded-map-points", type=int, default=50_000_000, help="map size of the `sharded` extra leg")
     ap.add_argument("--e2e-steps", type=int, default=200, help="the e2e leg times max(--steps, this) steps and reports the "
                     "median step (one OS hiccup on one rank does not set an 8-rank number)")
@@ -478,17 +480,27 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
     wl = make_workload(args, 0)  # the SAME map and scans on every rank
     mp = wl["map"]
     bounds = sharded.slab_bounds(mp[:, 0], world)
-    keep = sharded.shard_indices(mp[:, 0], bounds, rank)
-    ctx = _cabi.Context(local, max_scan_points=max(1 << 18, args.rings * args.cols), max_down_points=100000,
+    stripe = float(args.shard_stripe) if world > 1 else 0.0
+    x_org = float(np.floor(mp[:, 0].min()))
+    if stripe > 0:
+        keep = sharded.stripe_indices(mp[:, 0], x_org, stripe, world, rank)
+    else:
+        keep = sharded.shard_indices(mp[:, 0], bounds, rank)
+    ctx = _cabi.Context(local, max_scan_points=max(1 << 18, args.rings * args.cols), max_down_points=150000,
                         max_map_points=max(1 << 20, int(len(keep) * 1.05)))
+    if stripe > 0:
+        ctx.set_shard_stripes(x_org, stripe, world, rank)
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.map_build(np.concatenate([mp[keep], np.zeros((len(keep), 1), np.float32)], 1))
-    bodies = []
+    bodies, dense_bodies = [], []
     for s in wl["scans"]:
         body, _, _ = ctx.scan_preprocess(s["scan"], None, None, wl["leaf"])
         bodies.append(np.ascontiguousarray(body))
+        body, _, _ = ctx.scan_preprocess(s["scan"], None, None, 0.15)  # the dense-scene variant (M ~ 40k)
+        dense_bodies.append(np.ascontiguousarray(body))
+    sparse_bodies = bodies
     M = int(np.mean([len(b) for b in bodies]))
     fused = world > 1 and args.exchange == "peer"
     if fused:
@@ -501,7 +513,7 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
     own = (float(bounds[rank]), float(bounds[rank + 1]))
     flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def run(steps, warmup):
+    def run(steps, warmup, bodies=sparse_bodies):
         evs, nvalid, npass = [], 0, 0
         for k in range(warmup + steps):
             j = k % len(bodies)
@@ -542,12 +554,18 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
     launches = ctx.launch_count - l0
     barrier()
     clocks = sampler.stop()
+    # the same on the dense variant of the scans: enough rows per block that a rank's share of them matters
+    dsteps = min(args.steps, 20)
+    run(0, 3, dense_bodies)
+    barrier()
+    dms, _, dnpass, _ = run(dsteps, 0, dense_bodies)
+    barrier()
     if fused and ctx.peer_timed_out():
         raise SystemExit("peer exchange timed out")
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, dms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, dms = float(t[0].item()), float(t[1].item())
         xs = torch.tensor(x_last, dtype=torch.float64, device=dev)
         x0 = xs.clone()
         dist.broadcast(x0, 0)
@@ -557,7 +575,10 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
     # how the scan splits over the ranks (points whose p_world.x lies in the rank's window, at the last posterior)
     j_last = (args.steps - 1) % len(bodies)  # run(steps, 0): step k replays scan k % len(bodies)
     pw_x = _world_x(bodies[j_last], x_last)
-    owned = int(((pw_x >= own[0]) & (pw_x < own[1])).sum())
+    if stripe > 0:
+        owned = int((np.mod(sharded.stripe_of(pw_x, x_org, stripe), world) == rank).sum())
+    else:
+        owned = int(((pw_x >= own[0]) & (pw_x < own[1])).sum())
     owned_max = owned
     vs_single = None
     if world > 1:
@@ -586,11 +607,16 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
         "metric": METRIC, "value": args.steps / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": "sharded map: %d-point city map in %d x-slabs (+ sqrt(5)+0.5 m halo), OS1-128 %dx%d scans, "
-                   "%s" % (len(mp), world, args.rings, args.cols,
+        "config": {"workload": "sharded map: %d-point city map in %s (+ sqrt(5)+0.5 m halo), OS1-128 %dx%d scans, "
+                   "%s" % (len(mp), ("%g m x-stripes dealt round-robin to %d ranks" % (stripe, world)) if stripe > 0 else
+                           "%d x-slabs" % world, args.rings, args.cols,
                            "blobs exchanged inside the persistent kernel over NVLink peer memory" if fused else
                            "NCCL all-reduce of 92 doubles per pass between pass and solve kernels"), "M": M,
                    "passes_per_scan": passes, "local_map_points": int(len(keep)), "owned_points_max_rank": owned_max,
+                   "scan_points_last": int(len(bodies[j_last])),
+                   "dense": {"value": dsteps / (dms / 1000.0), "unit": UNIT, "ms_per_step": dms / dsteps, "steps": dsteps,
+                             "M": int(np.mean([len(b) for b in dense_bodies])), "passes_per_scan": dnpass / dsteps,
+                             "what": "the same scans downsampled at 0.15 m"},
                    "vs_single_gpu": vs_single,
                    "l2": "flushed (384 MiB write) before every timed step", "states_identical_across_ranks": same},
         "matched_pts_per_s": nvalid / (ms / 1000.0), "gpu_launches": int(launches),
@@ -1038,7 +1064,8 @@ def main():
                            "owned_points_max_rank": r["config"].get("owned_points_max_rank"),
                            "passes_per_scan": r["config"]["passes_per_scan"],
                            "states_identical": r["config"]["states_identical_across_ranks"],
-                           "vs_single_gpu": r["config"].get("vs_single_gpu"), "what": r["config"]["workload"]}
+                           "vs_single_gpu": r["config"].get("vs_single_gpu"), "dense": r["config"].get("dense"),
+                           "what": r["config"]["workload"]}
     if "os1_64_seqs" in legs and world > 1:
         # config 4: 8 independent OS1-64 sequences per GPU through the whole main loop
         sub.workload, sub.seqs_per_gpu = "os1_64_seqs", 8

@@ -274,6 +274,13 @@ int lio_peer_connect(lio_ctx* ctx, int rank, int world, const unsigned char* han
 int lio_update_enqueue_sharded(lio_ctx* ctx, double R, int max_iter, int extrinsic_est, int from_snapshot,
                                float x_own_min, float x_own_max);
 int lio_peer_status(lio_ctx* ctx, int32_t* timed_out);
+/* Striped ownership for the two sharded calls above (lio_update_pass_enqueue, lio_update_enqueue_sharded): instead of
+ * one x window per rank, rank r owns the rows whose search position falls into the stripes
+ * s = floor((p_world.x - x_origin) / stripe_width) with s mod world == r, and holds the map points of those stripes plus
+ * the halo.  A scan is a few hundred metres wide, so with stripes of a few tens of metres every rank gets ~1/world of
+ * its rows wherever the robot is (one window per rank leaves all of them with the one or two ranks around it).  The
+ * calls' x_own_min / x_own_max are then ignored.  world = 0 switches back to windows.  No reference counterpart. */
+int lio_set_shard_stripes(lio_ctx* ctx, float x_origin, float stripe_width, int world, int rank);
 /* Instrumentation: enqueue ONE h_share_model pass (search or cached) at the device-resident state with no Kalman
  * step behind it, so that bench.py can bracket exactly that kernel with CUDA events. */
 int lio_pass_only_enqueue(lio_ctx* ctx, int do_search, int extrinsic_est);

@@ -66,6 +66,30 @@ def main():
             assert np.abs(ref[0] - f[0]).max() < 1e-9
             print(f"ext={ext}: fused == nccl bitwise on {world} ranks; |x - unsharded| = {np.abs(ref[0] - f[0]).max():.1e}; "
                   f"valid {f[2]}, passes {f[3]}", flush=True)
+    # striped ownership (lio_set_shard_stripes): the same checks with the rows dealt out in 8 m stripes
+    x0, width = float(mp[:, 0].min()), 8.0
+    keep = sharded.stripe_indices(mp[:, 0], x0, width, world, rank)
+    ctx.map_build(p4(mp[keep]))
+    ctx.scan_upload(body)
+    ctx.set_shard_stripes(x0, width, world, rank)
+    for ext in (False, True):
+        red, _t = sharded.nccl_reduce(ctx, dev)
+        a = sharded.ShardedUpdate(ctx, own, reduce=red).update(cfg["x_prior"], cfg["P"], 0.001, 4, ext)
+        ctx.blob_bind(None)
+        f = sharded.PeerShardedUpdate(ctx, own).update(cfg["x_prior"], cfg["P"], 0.001, 4, ext)
+        assert not ctx.peer_timed_out()
+        assert a[2:] == f[2:] and np.array_equal(a[0], f[0]) and np.array_equal(a[1], f[1]), "stripes: fused != NCCL"
+        xs = torch.tensor(f[0], dtype=torch.float64, device=dev)
+        x0t = xs.clone()
+        dist.broadcast(x0t, 0)
+        assert torch.equal(xs, x0t), "stripes: ranks disagree"
+        if rank == 0:
+            with _cabi.Context(local, **kw) as full:
+                full.map_build(p4(mp))
+                full.scan_upload(body)
+                ref = full.update_scan(cfg["x_prior"], cfg["P"], 0.001, 4, ext)
+            assert ref[2:] == f[2:] and np.abs(ref[0] - f[0]).max() < 1e-9
+            print(f"stripes ext={ext}: fused == nccl bitwise; |x - unsharded| = {np.abs(ref[0] - f[0]).max():.1e}", flush=True)
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()

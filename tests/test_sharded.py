@@ -70,8 +70,8 @@ def test_blob_allreduce_two_ranks_gloo():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ext", [False, True])
-def test_two_shards_equal_unsharded_update(orc, small_cfg, ext):
+@pytest.mark.parametrize("ext,stripes", [(False, False), (True, False), (False, True), (True, True)])
+def test_two_shards_equal_unsharded_update(orc, small_cfg, ext, stripes):
     from agi_lidar_slam_b200 import _cabi, sharded
 
     cfg = small_cfg
@@ -88,10 +88,15 @@ def test_two_shards_equal_unsharded_update(orc, small_cfg, ext):
     world = 2
     b = sharded.slab_bounds(mp[:, 0], world)
     ranks = []
+    x0, width = float(mp[:, 0].min()), 8.0  # striped ownership: 8 m stripes dealt round-robin (lio_set_shard_stripes)
     for r in range(world):
         c = _cabi.Context(0, **kw)
-        keep = sharded.shard_indices(mp[:, 0], b, r)
-        assert len(keep) < 0.8 * len(mp)  # a real shard, not a replica
+        if stripes:
+            keep = sharded.stripe_indices(mp[:, 0], x0, width, world, r)
+            c.set_shard_stripes(x0, width, world, r)
+        else:
+            keep = sharded.shard_indices(mp[:, 0], b, r)
+        assert len(keep) < (0.9 if stripes else 0.8) * len(mp)  # a real shard, not a replica
         c.map_build(p4(mp[keep]))
         c.scan_upload(body)
         ranks.append(c)
