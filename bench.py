@@ -74,7 +74,7 @@ def parse():
                          "step returns with the posterior as the reference publishes before map_incremental)")
     ap.add_argument("--legs", default="auto", help="extra legs of the default workload's line: 'auto' = sharded + os1_64_seqs "
                     "when N > 1, knn_hbm + dense_scene when N = 1; 'none'; or a comma list of those names")
-    ap.add_argument("--shard-stripe", type=float, default=16.0, help="sharded map: width [m] of the x stripes dealt round-robin "
+    ap.add_argument("--shard-stripe", type=float, default=8.0, help="sharded map: width [m] of the x stripes dealt round-robin "
                     "to the ranks (lio_set_shard_stripes); 0 = one contiguous x slab per rank")
     ap.add_argument("--sharded-map-points", type=int, default=50_000_000, help="map size of the `sharded` extra leg")
     ap.add_argument("--e2e-steps", type=int, default=200, help="the e2e leg times max(--steps, this) steps and reports the "
@@ -138,7 +138,7 @@ class ClockSampler:
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index, period_s=0.002):
+    def __init__(self, gpu_index, period_s=0.01):
         self.period = period_s
         self.sm, self.bits, self.power = [], [], []
         self.stop_flag = threading.Event()
@@ -513,13 +513,27 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
     own = (float(bounds[rank]), float(bounds[rank + 1]))
     flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def run(steps, warmup, bodies=sparse_bodies):
-        evs, nvalid, npass = [], 0, 0
+    # pinned copies: the uploads of a step are then truly asynchronous and the host runs ahead of the stream
+    pin = lambda b: torch.from_numpy(b).pin_memory()  # noqa: E731
+    keepalive = [[pin(b) for b in sparse_bodies], [pin(b) for b in dense_bodies]]
+    sparse_bodies = bodies = [t.numpy() for t in keepalive[0]]
+    dense_bodies = [t.numpy() for t in keepalive[1]]
+    passes_of = {}
+
+    def run(steps, warmup, bodies=None, aligned=False, queued=True):
+        """Timed steps.  queued: nothing is read back between the steps, so the host runs ahead and every rank's stream
+        holds the next step's kernel when the current one ends -- the ranks stay aligned through the exchange itself
+        instead of paying the host's launch jitter (tens of microseconds at 8 processes) in every step.  The steps of the
+        warm-up are read back one by one (pass counts per scan).  aligned: diagnostic, NCCL barrier before each step."""
+        bodies = sparse_bodies if bodies is None else bodies
+        evs, nvalid, npass, x = [], 0, 0, None
         for k in range(warmup + steps):
             j = k % len(bodies)
             ctx.scan_upload(bodies[j])
             ctx.state_upload(wl["scans"][j]["x_prior"], wl["P"])
             flush.fill_(1)
+            if aligned and world > 1:
+                dist.barrier()  # an NCCL kernel on this stream: the update kernels of all ranks start together
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             if fused:
@@ -531,11 +545,16 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
                     reduce()
                     ctx.update_step_enqueue(R_COV, wl["ext"])
             e1.record(stream)
-            x, P, nv, npz = ctx.state_download()
+            if k < warmup or not queued:
+                x, P, nv, npz = ctx.state_download()
+                passes_of[(id(bodies), j)] = (nv, npz)
             if k >= warmup:
                 evs.append((e0, e1))
+                nv, npz = passes_of.get((id(bodies), j), (0, 0))
                 nvalid += nv
                 npass += npz
+        if queued and steps > 0:
+            x, P, _, _ = ctx.state_download()  # the last step's posterior; synchronises
         torch.cuda.synchronize(dev)
         return sum(a.elapsed_time(b) for a, b in evs), nvalid, npass, x
 
@@ -545,7 +564,7 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    run(0, max(3, args.warmup))
+    run(0, max(len(bodies), 3, args.warmup))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -553,19 +572,27 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
     ms, nvalid, npass, x_last = run(args.steps, 0)
     launches = ctx.launch_count - l0
     barrier()
+    # The sharded update is a collective: its kernels wait for each other in every pass, so a rank that starts late is
+    # paid for by all of them.  `value` times it the way collectives are timed -- the ranks' streams aligned by an NCCL
+    # barrier kernel in front of every step's first event (outside the timed bracket), as when one scan reaches all ranks
+    # at once; the unaligned figure (every rank launches when its own host and its own L2 flush get there: +40 us of start
+    # skew per step at 8 processes) is filed beside it.
+    ums = ms
+    ms, nvalid, npass, x_last = run(args.steps, 0, aligned=True)
+    barrier()
     clocks = sampler.stop()
     # the same on the dense variant of the scans: enough rows per block that a rank's share of them matters
     dsteps = min(args.steps, 20)
-    run(0, 3, dense_bodies)
+    run(0, max(3, len(dense_bodies)), dense_bodies)
     barrier()
-    dms, _, dnpass, _ = run(dsteps, 0, dense_bodies)
+    dms, _, dnpass, _ = run(dsteps, 0, dense_bodies, aligned=True)
     barrier()
     if fused and ctx.peer_timed_out():
         raise SystemExit("peer exchange timed out")
     if world > 1:
-        t = torch.tensor([ms, dms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, dms, ums], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, dms = float(t[0].item()), float(t[1].item())
+        ms, dms, ums = float(t[0].item()), float(t[1].item()), float(t[2].item())
         xs = torch.tensor(x_last, dtype=torch.float64, device=dev)
         x0 = xs.clone()
         dist.broadcast(x0, 0)
@@ -614,6 +641,10 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
                            "NCCL all-reduce of 92 doubles per pass between pass and solve kernels"), "M": M,
                    "passes_per_scan": passes, "local_map_points": int(len(keep)), "owned_points_max_rank": owned_max,
                    "scan_points_last": int(len(bodies[j_last])),
+                   "value_unaligned": args.steps / (ums / 1000.0),
+                   "timing": "CUDA events around every step's update on its stream, max over ranks of their sum; an NCCL barrier "
+                             "kernel on the same stream in front of every step's first event aligns the ranks' starts (the "
+                             "update is a collective); value_unaligned: without it",
                    "dense": {"value": dsteps / (dms / 1000.0), "unit": UNIT, "ms_per_step": dms / dsteps, "steps": dsteps,
                              "M": int(np.mean([len(b) for b in dense_bodies])), "passes_per_scan": dnpass / dsteps,
                              "what": "the same scans downsampled at 0.15 m"},
@@ -1065,6 +1096,8 @@ def main():
                            "passes_per_scan": r["config"]["passes_per_scan"],
                            "states_identical": r["config"]["states_identical_across_ranks"],
                            "vs_single_gpu": r["config"].get("vs_single_gpu"), "dense": r["config"].get("dense"),
+                           "value_unaligned": r["config"].get("value_unaligned"), "timing": r["config"].get("timing"),
+                           "scan_points_last": r["config"].get("scan_points_last"),
                            "what": r["config"]["workload"]}
     if "os1_64_seqs" in legs and world > 1:
         # config 4: 8 independent OS1-64 sequences per GPU through the whole main loop
