@@ -102,7 +102,7 @@ EXPORTS = [
     "lio_update_enqueue_multi", "lio_scan_step", "lio_scan_step_begin", "lio_scan_step_end",
     "lio_scan_step_finish", "lio_scan_step_prefetch", "lio_set_deferred_growth", "lio_scan_step_settle", "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_peer_handle", "lio_peer_connect",
-    "lio_update_enqueue_sharded", "lio_peer_status", "lio_set_shard_stripes", "lio_pass_only_enqueue", "lio_debug_timeline",
+    "lio_update_enqueue_sharded", "lio_peer_status", "lio_set_shard_stripes", "lio_map_removed_points", "lio_pass_only_enqueue", "lio_debug_timeline",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
     "lio_imu_proc_init", "lio_imu_set_param", "lio_imu_process",
     "lio_seq_default_config", "lio_seq_create", "lio_seq_destroy", "lio_seq_process", "lio_seq_process_many",
@@ -175,6 +175,7 @@ def load_library() -> C.CDLL:
         "lio_peer_status": (C.c_int, [vp, P(i32)]),
         "lio_pass_only_enqueue": (C.c_int, [vp, C.c_int, C.c_int]),
         "lio_set_shard_stripes": (C.c_int, [vp, f32, f32, C.c_int, C.c_int]),
+        "lio_map_removed_points": (C.c_int, [vp, vp, C.c_int64, vp]),
         "lio_debug_timeline": (C.c_int, [vp, vp]),
         "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "lio_map_incremental": (C.c_int, [vp, vp, f32, C.c_int, vp]),
@@ -314,6 +315,14 @@ class Context:
         if n.value:
             self._check(self._lib.lio_map_dump(self._h, _ptr(xyz), _ptr(ids), n.value, C.byref(n)))
         return xyz, ids
+
+    def map_removed_points(self) -> np.ndarray:
+        """The points deleted since the last call (fetch and clear), (n, 3) float32, order unspecified."""
+        n = C.c_int64(0)
+        self._check(self._lib.lio_map_removed_points(self._h, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 3), np.float32)
+        self._check(self._lib.lio_map_removed_points(self._h, _ptr(out), n.value, C.byref(n)))
+        return out[: n.value].copy()
 
     def map_set_downsample(self, downsample_size: float):
         self._check(self._lib.lio_map_set_downsample(self._h, float(downsample_size)))

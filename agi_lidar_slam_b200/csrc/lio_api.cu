@@ -114,6 +114,8 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->map.cell_base, 4 * (size_t)c->hash_cap);
   ALLOC(c->map.pool, sizeof(float4) * (size_t)c->map.pool_cap);
   ALLOC(c->map.counters, 4 * 16);
+  c->map.removed_cap = (uint32_t)std::min<uint64_t>((uint64_t)k.max_map_points, 1ull << 22);
+  ALLOC(c->map.removed, sizeof(float4) * (size_t)c->map.removed_cap);
   c->map_downsample = k.map_downsample;
   c->batch_cap = std::max<int64_t>(k.max_map_points, k.max_down_points);
   ALLOC(c->d_batch_pts, sizeof(float4) * (size_t)c->batch_cap);
@@ -291,7 +293,7 @@ void lio_destroy(lio_ctx* c) {
   if (c->prep_stream) cudaStreamSynchronize(c->prep_stream);  // a prefetched scan may still be on its way
   for (int r = 0; r < 8; ++r)
     if (c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
-  void* ptrs[] = {c->map.table,   c->map.cell_cap,  c->map.cell_pend, c->map.cell_base, c->map.pool,
+  void* ptrs[] = {c->map.removed, c->map.table,   c->map.cell_cap,  c->map.cell_pend, c->map.cell_base, c->map.pool,
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
                   c->d_vox_best,  c->d_vox_key,     c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
@@ -463,6 +465,13 @@ int lio_map_size(lio_ctx* c, int64_t* total, int64_t* valid) {
   if (total) *total = c->next_id;
   if (valid) *valid = h[2];
   return LIO_OK;
+}
+
+int lio_map_removed_points(lio_ctx* c, float* xyz, int64_t cap, int64_t* n) {
+  if (!c || cap < 0 || !n) return LIO_E_INVALID;
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  if (const int rs = settle_growth(c)) return rs;
+  return map_removed_points(c, xyz, cap, n);
 }
 
 int lio_map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n) {

@@ -32,12 +32,24 @@ struct MapView {
   float4* pool;         // [pool_cap] x,y,z, id bits (id < 0: dead slot)
   uint32_t hash_mask;
   uint32_t pool_cap;
+  float4* removed;      // [removed_cap] log of the points taken out of the map (box deletes, downsample replacements)
+  uint32_t removed_cap;
   uint32_t* counters;  // [0] pool_top  [1] n_cells  [2] n_live  [3] error flag  [4] scratch count  [5] slots used
+                       // [6] removed points logged  [7] ... that did not fit the log
                        // [8..10] / [11..13] smallest / largest cell index (as int) that ever held a point: the box an
                        // unbounded search has to cover (warp_knn_far)
   float inv_cell;
   float cell;
 };
+
+// Files a point that leaves the map (≙ KD_TREE::Points_deleted, ikd_Tree.cpp:582-594: what acquire_removed_points hands out).
+__device__ __forceinline__ void log_removed(const MapView& m, const float4& q) {
+  const uint32_t k = atomicAdd(&m.counters[6], 1u);
+  if (k < m.removed_cap)
+    m.removed[k] = q;
+  else
+    atomicAdd(&m.counters[7], 1u);
+}
 
 __host__ __device__ __forceinline__ unsigned long long pack_cell(int x, int y, int z) {
   const unsigned long long B = 1u << 20;

@@ -173,6 +173,7 @@ int map_append_batch(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base
 int map_add_downsample(lio_ctx* c, const float4* d_pts, int64_t n, int32_t id_base, int32_t* n_added);
 int map_delete_boxes(lio_ctx* c, const float* h_boxes6, int nb, int32_t* n_deleted);
 int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
+int map_removed_points(lio_ctx* c, float* xyz, int64_t cap, int64_t* n);
 int map_incremental(lio_ctx* c, const lio_state* x, float fsm, int ekf_inited, int32_t counts[3]);
 int map_incremental_enqueue(lio_ctx* c, float fsm, int ekf_inited, int min_m, int64_t bound);
 int map_build_scan(lio_ctx* c, const lio_state* x);

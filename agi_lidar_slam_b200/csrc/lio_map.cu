@@ -284,6 +284,7 @@ __global__ void vox_apply_kernel(MapView m, const float4* pts, int n, BatchDev b
           if (__float_as_int(q.w) < 0) continue;
           if (g.bmin[0] <= q.x && g.bmax[0] > q.x && g.bmin[1] <= q.y && g.bmax[1] > q.y && g.bmin[2] <= q.z &&
               g.bmax[2] > q.z && (best_id < 0 || start + t != best_slot)) {
+            log_removed(m, q);
             q.w = __int_as_float(-1);
             m.pool[start + t] = q;
           }
@@ -310,6 +311,7 @@ __global__ void map_delete_kernel(MapView m, const float* boxes6, int nb, uint32
       hit = mn[0] <= q.x && mn[3] > q.x && mn[1] <= q.y && mn[4] > q.y && mn[2] <= q.z && mn[5] > q.z;
     }
     if (hit) {
+      log_removed(m, q);
       q.w = __int_as_float(-1);
       m.pool[s] = q;
       atomicAdd(n_deleted, 1u);
@@ -591,6 +593,32 @@ int map_delete_boxes(lio_ctx* c, const float* h_boxes6, int nb, int32_t* n_delet
 #include <vector>
 
 namespace lio {
+
+// ≙ KD_TREE::acquire_removed_points: the points deleted since the last call that took them (fetch and clear).
+int map_removed_points(lio_ctx* c, float* xyz, int64_t cap, int64_t* n) {
+  uint32_t h[8];
+  LIO_CHECK(c, cudaMemcpyAsync(h, c->map.counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  const int64_t logged = std::min<int64_t>(h[6], c->map.removed_cap);
+  if (n) *n = logged;
+  if (!xyz) return LIO_OK;  // a question about the size only
+  const int64_t take = std::min<int64_t>(logged, cap);
+  std::vector<float4> buf((size_t)take);
+  if (take > 0)
+    LIO_CHECK(c, cudaMemcpyAsync(buf.data(), c->map.removed, sizeof(float4) * (size_t)take, cudaMemcpyDeviceToHost, c->stream));
+  LIO_CHECK(c, cudaMemsetAsync(c->map.counters + 6, 0, 2 * sizeof(uint32_t), c->stream));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  for (int64_t i = 0; i < take; ++i) {
+    xyz[3 * i] = buf[(size_t)i].x;
+    xyz[3 * i + 1] = buf[(size_t)i].y;
+    xyz[3 * i + 2] = buf[(size_t)i].z;
+  }
+  if (h[7] != 0) {
+    c->err = "removed-point log overflowed: the oldest entries were kept, later deletions of this period are missing";
+    return LIO_E_CAPACITY;
+  }
+  return LIO_OK;
+}
 
 int map_dump(lio_ctx* c, float* xyz, int32_t* ids, int64_t cap, int64_t* n) {
   uint32_t h[8];

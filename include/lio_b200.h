@@ -115,6 +115,13 @@ int lio_map_size(lio_ctx* ctx, int64_t* total, int64_t* valid);
 /* ≙ KD_TREE::flatten(Root_Node, PCL_Storage, NOT_RECORD) (ikd_Tree.cpp:1490-1516): live points, ascending id.
  * xyz (cap x 3) and ids (cap) may be NULL; *n = live count. */
 int lio_map_dump(lio_ctx* ctx, float* xyz, int32_t* ids, int64_t cap, int64_t* n);
+/* ≙ KD_TREE::acquire_removed_points (ikd_Tree.h:294, ikd_Tree.cpp:582-594; laserMapping.cpp:361-362): the points that
+ * left the map since the last call that took them -- box deletes (Delete_Point_Boxes) and the points a downsampling
+ * Add_Points replaced -- x,y,z each, order unspecified.  *n = points logged; with xyz != NULL the first min(*n, cap) are
+ * copied and the log is cleared, with xyz == NULL only the count is returned.  (The reference files a deleted point
+ * when the subtree holding it is next rebuilt; here it is filed when it is deleted.)  The log holds
+ * min(max_map_points, 2^22) points: LIO_E_CAPACITY if more were deleted between two calls. */
+int lio_map_removed_points(lio_ctx* ctx, float* xyz, int64_t cap, int64_t* n);
 /* ≙ a batch of KD_TREE::Nearest_Search(point, 5, Nearest_Points, Point_Distance, max_dist) (ikd_Tree.cpp:370-402;
  * esekfom.hpp:140).  max_d2 = max_dist * max_dist, as the tree squares it (ikd_Tree.cpp:965) and tests `dist <= max_d2`
  * (:980); INFINITY is the reference's default (ikd_Tree.h:285) and what esekfom.hpp:140-141 gets.  Up to

@@ -130,7 +130,21 @@ class KD_TREE {
       Storage.push_back(p);
     }
   }
-  void acquire_removed_points(PointVector& removed_points) { removed_points.clear(); }  // deletions are not logged
+  // ikd_Tree.cpp:582-594: APPENDS the points deleted since the last call (box deletes, downsample replacements) and
+  // clears the log.  Order unspecified, as in the reference (it files them rebuild by rebuild).
+  void acquire_removed_points(PointVector& removed_points) {
+    int64_t n = 0;
+    last_error = lio_map_removed_points(ctx_->get(), nullptr, 0, &n);
+    if (last_error != LIO_OK || n == 0) return;
+    std::vector<float> xyz((size_t)n * 3);
+    last_error = lio_map_removed_points(ctx_->get(), xyz.data(), n, &n);
+    for (int64_t i = 0; i < n; ++i) {
+      PointType p;
+      std::memset(&p, 0, sizeof(p));
+      std::memcpy(&p, &xyz[3 * i], 12);
+      removed_points.push_back(p);
+    }
+  }
 
   PointVector PCL_Storage;
   KD_TREE_NODE* Root_Node = nullptr;
@@ -149,6 +163,14 @@ class KD_TREE {
 struct input_ikfom {  // use-ikfom.hpp:29-33
   double acc[3];
   double gyro[3];
+};
+
+// esekfom.hpp:15-22 without Eigen: h is effct_feat_num long, h_x is effct_feat_num x 12, row-major.
+struct dyn_share_datastruct {
+  bool valid = true;
+  bool converge = true;
+  std::vector<double> h;
+  std::vector<double> h_x;
 };
 
 class esekf {
@@ -214,13 +236,128 @@ class esekf {
       }
     }
   }
+  // esekfom.hpp:106-227: ONE measurement-model pass at the filter's current state x_.  ekfom_data.converge says whether
+  // the neighbours are searched again (:136-141); on return valid / h / h_x are the reference's: one row per matched
+  // point, in scan order (laserCloudOri is filled in index order, :176-187), h_x = [n^T, A^T, B^T, C^T] (:197-226) with
+  // B = C = 0 unless extrinsic_est, h = -pd2.  The pass itself runs on the device (lio_update_pass); the rows are formed
+  // here from its per-point outputs (normal, residual) and the state, in the reference's FP64 arithmetic.
+  template <typename CloudPtr, typename PointType, typename Alloc>
+  void h_share_model(dyn_share_datastruct& ekfom_data, CloudPtr& feats_down_body, KD_TREE<PointType, Alloc>& ikdtree,
+                     std::vector<std::vector<PointType, Alloc>>& Nearest_Points, bool extrinsic_est) {
+    lio_ctx* c = ikdtree.context()->get();
+    const auto& pts = feats_down_body->points;
+    const size_t m = pts.size();
+    last_error = lio_scan_upload(c, pts.data(), (int64_t)m, (int)sizeof(PointType));
+    if (last_error != LIO_OK) return;
+    double blob[90];
+    last_error = lio_update_pass(c, &x_, ekfom_data.converge ? 1 : 0, extrinsic_est ? 1 : 0, blob, &effct_feat_num);
+    if (last_error != LIO_OK) return;
+    if (ekfom_data.converge) fetch_neighbors(ikdtree, m, Nearest_Points);
+    std::vector<uint8_t> sel(m);
+    std::vector<float> nv(4 * m);
+    last_error = lio_get_neighbors(c, nullptr, nullptr, nullptr, nullptr, sel.data(), nv.data());
+    if (last_error != LIO_OK) return;
+    ekfom_data.h.clear();
+    ekfom_data.h_x.clear();
+    if (effct_feat_num < 1) {  // :189-194
+      ekfom_data.valid = false;
+      return;
+    }
+    double R[9], Rli[9];
+    quat_to_mat(x_.rot, R);
+    quat_to_mat(x_.offset_R_L_I, Rli);
+    for (size_t i = 0; i < m; ++i) {
+      if (!sel[i]) continue;
+      const float* pf = reinterpret_cast<const float*>(&pts[i]);
+      const double pb[3] = {pf[0], pf[1], pf[2]};
+      double pI[3], C[3], A[3], B[3] = {0.0, 0.0, 0.0};
+      for (int r = 0; r < 3; ++r)
+        pI[r] = (Rli[3 * r] * pb[0] + Rli[3 * r + 1] * pb[1]) + Rli[3 * r + 2] * pb[2] + x_.offset_T_L_I[r];  // :206
+      const double n[3] = {nv[4 * i], nv[4 * i + 1], nv[4 * i + 2]};
+      for (int r = 0; r < 3; ++r) C[r] = (R[r] * n[0] + R[3 + r] * n[1]) + R[6 + r] * n[2];  // rot^T * norm_vec (:214)
+      A[0] = pI[1] * C[2] - pI[2] * C[1];                                                       // [pI]x * C (:215)
+      A[1] = pI[2] * C[0] - pI[0] * C[2];
+      A[2] = pI[0] * C[1] - pI[1] * C[0];
+      double row[12] = {n[0], n[1], n[2], A[0], A[1], A[2], 0, 0, 0, 0, 0, 0};
+      if (extrinsic_est) {  // :216-221
+        double D[3];  // offset_R_L_I^T * C
+        for (int r = 0; r < 3; ++r) D[r] = (Rli[r] * C[0] + Rli[3 + r] * C[1]) + Rli[6 + r] * C[2];
+        B[0] = pb[1] * D[2] - pb[2] * D[1];
+        B[1] = pb[2] * D[0] - pb[0] * D[2];
+        B[2] = pb[0] * D[1] - pb[1] * D[0];
+        for (int r = 0; r < 3; ++r) {
+          row[6 + r] = B[r];
+          row[9 + r] = C[r];
+        }
+      }
+      ekfom_data.h_x.insert(ekfom_data.h_x.end(), row, row + 12);
+      ekfom_data.h.push_back(-(double)nv[4 * i + 3]);  // :225
+    }
+  }
   int32_t effct_feat_num = 0;  // esekfom.hpp:26
   int32_t n_passes = 0;
   int last_error = LIO_OK;
 
  private:
+  static void quat_to_mat(const double q[4], double m[9]) {  // w, x, y, z -> row-major rotation matrix
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    m[0] = 1 - 2 * (y * y + z * z);
+    m[1] = 2 * (x * y - w * z);
+    m[2] = 2 * (x * z + w * y);
+    m[3] = 2 * (x * y + w * z);
+    m[4] = 1 - 2 * (x * x + z * z);
+    m[5] = 2 * (y * z - w * x);
+    m[6] = 2 * (x * z - w * y);
+    m[7] = 2 * (y * z + w * x);
+    m[8] = 1 - 2 * (x * x + y * y);
+  }
   lio_state x_;
   double P_[576];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// pcl::VoxelGrid<PointType> as laserMapping.cpp uses it (:66-67 declaration, :683-686 setLeafSize, :737-738
+// setInputCloud + filter): the centroid of every occupied leaf, in ascending leaf-index order (PCL's own order).
+// Cloud types: anything with a `points` vector (and optionally width / height / is_dense, which are not touched).
+// ---------------------------------------------------------------------------------------------------------
+template <typename PointType>
+class VoxelGrid {
+  static_assert(sizeof(PointType) == 16 || sizeof(PointType) == 48, "PointType must be 16 or 48 bytes (x,y,z first)");
+
+ public:
+  explicit VoxelGrid(std::shared_ptr<Context> ctx) : ctx_(std::move(ctx)) {}
+  void setLeafSize(float lx, float ly, float lz) {
+    leaf_ = lx;
+    cubic_ = (lx == ly && ly == lz);  // the path only ever sets cubic leaves; anything else is refused in filter()
+  }
+  template <typename CloudPtr>
+  void setInputCloud(const CloudPtr& cloud) {
+    in_ = cloud->points.data();
+    n_ = (int64_t)cloud->points.size();
+  }
+  template <typename Cloud>
+  void filter(Cloud& output) {
+    output.points.clear();
+    if (!cubic_ || !(leaf_ > 0.f) || in_ == nullptr) {
+      last_error = LIO_E_INVALID;
+      return;
+    }
+    std::vector<PointType> out((size_t)(n_ < 1 ? 1 : n_));  // at most one centroid per input point
+    int64_t m = 0;
+    last_error = lio_scan_preprocess(ctx_->get(), in_, n_, (int)sizeof(PointType), nullptr, 0, nullptr, leaf_, out.data(),
+                                     &m, nullptr, nullptr);
+    if (last_error != LIO_OK) return;
+    out.resize((size_t)m);
+    output.points.assign(out.begin(), out.end());
+  }
+  int last_error = LIO_OK;
+
+ private:
+  std::shared_ptr<Context> ctx_;
+  const PointType* in_ = nullptr;
+  int64_t n_ = 0;
+  float leaf_ = 0.f;
+  bool cubic_ = false;
 };
 
 // ---------------------------------------------------------------------------------------------------------

@@ -83,3 +83,45 @@ def test_os1_128_scan_against_2m_map(big, big_ctx, orc):
     x3, _, _, _ = ctx.update_scan(x, big["P"], 0.001, 4, False)
     d3 = orc.boxminus(x3, x)
     assert np.abs(d3[0:3]).max() < 2e-3 and np.abs(d3[3:6]).max() < 2e-3
+
+
+def test_full_size_update_with_extrinsic_estimation(big, big_ctx, orc):
+    """The same scan with extrinsic_est = true (12 x 12 normal equations, 91 outputs per row): whole update against the
+    oracle at full size."""
+    ctx = big_ctx
+    body, _, _ = ctx.scan_preprocess(big["scan"], None, None, 0.5)
+    om = orc.Map(1.0)
+    om.build(big["map"])
+    x, P, nv, npass = ctx.update_scan(big["x_prior"], big["P"], 0.001, 4, True)
+    xr, Pr, trace, nvr = orc.Scan(body[:, :3]).update(big["x_prior"], big["P"], om.knn_backend(), 0.001, 4, True)
+    assert npass == len(trace) and nv == nvr and nv > 1000
+    dx = orc.boxminus(x, xr)
+    assert np.abs(dx[0:3]).max() < 1e-4 and np.abs(dx[3:6]).max() < 1e-4  # north_star
+    assert np.abs(dx).max() < 1e-7 and np.abs(P - Pr).max() < 1e-9
+    assert np.abs(dx[6:12]).max() > 0 or np.array_equal(x[7:14], xr[7:14])  # the extrinsic block took part
+    x2, P2, nv2, np2 = ctx.update_scan(big["x_prior"], big["P"], 0.001, 4, True)
+    assert np.array_equal(x, x2) and np.array_equal(P, P2) and (nv, npass) == (nv2, np2)
+
+
+def test_dense_scan_many_tiles_per_block(big, orc):
+    """The scan downsampled at 0.15 m: M ~ 40k points (the size SURVEY.md 8d's worked example assumes), i.e. several
+    search tiles per block and 8-lane search groups.  Voxel filter bit-exact, update against the oracle."""
+    from agi_lidar_slam_b200 import _cabi
+
+    scan, mp = big["scan"], big["map"]
+    with _cabi.Context(0, max_scan_points=1 << 17, max_down_points=150000, max_map_points=1 << 21) as ctx:
+        ctx.map_build(np.concatenate([mp, np.zeros((len(mp), 1), np.float32)], 1))
+        body, _, _ = ctx.scan_preprocess(scan, None, None, 0.15)
+        cen, _, _ = orc.voxel_grid(np.concatenate([scan[:, :3], np.zeros((len(scan), 1), np.float32), scan[:, 3:4]], 1),
+                                   0.15)
+        assert len(body) == len(cen) and len(body) > 30000
+        assert np.array_equal(body[:, :3].view(np.uint32), cen[:, :3].view(np.uint32))
+        om = orc.Map(1.0)
+        om.build(mp)
+        for ext in (False, True):
+            x, P, nv, npass = ctx.update_scan(big["x_prior"], big["P"], 0.001, 4, ext)
+            xr, Pr, trace, nvr = orc.Scan(body[:, :3]).update(big["x_prior"], big["P"], om.knn_backend(), 0.001, 4, ext)
+            assert npass == len(trace) and nv == nvr and nv > 10000
+            dx = orc.boxminus(x, xr)
+            assert np.abs(dx[0:3]).max() < 1e-4 and np.abs(dx[3:6]).max() < 1e-4
+            assert np.abs(dx).max() < 1e-7 and np.abs(P - Pr).max() < 1e-9

@@ -167,3 +167,34 @@ def test_map_incremental_large_filter_size(ctx, orc, small_cfg):
         counts = ctx.map_incremental(xr, fs, True)
         assert counts.tolist() == [int((cls == 1).sum()), int((cls == 2).sum()), na], fs
         _same_map(ctx, om)
+
+
+def test_removed_points_log(orc, small_cfg):
+    """lio_map_removed_points ≙ KD_TREE::acquire_removed_points: box deletes and downsample replacements are handed out
+    once, then the log is empty; Build starts a new one."""
+    from agi_lidar_slam_b200 import _cabi
+
+    mp = small_cfg["map"]
+    p4 = lambda a: np.concatenate([a, np.zeros((len(a), 1), np.float32)], 1)  # noqa: E731
+    with _cabi.Context(0, max_scan_points=1 << 12, max_down_points=1 << 15, max_map_points=1 << 17) as ctx:
+        ctx.map_build(p4(mp))
+        assert len(ctx.map_removed_points()) == 0
+        box = np.array([[-5, -5, -10, 5, 5, 10]], np.float32)
+        inside = (mp[:, 0] >= -5) & (mp[:, 0] < 5) & (mp[:, 1] >= -5) & (mp[:, 1] < 5)
+        n_del = ctx.map_delete_boxes(box)
+        assert n_del == int(inside.sum()) > 0
+        got = ctx.map_removed_points()
+        key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]  # noqa: E731
+        assert np.array_equal(key(got).view(np.uint32), key(mp[inside]).view(np.uint32))
+        assert len(ctx.map_removed_points()) == 0  # taken
+        # a downsampling Add_Points whose new point beats the old one of its box retires the old one
+        live_xyz, _ = ctx.map_dump()
+        victim = live_xyz[len(live_xyz) // 2]
+        centre = (np.floor(victim / 0.5) + 0.5) * 0.5
+        ctx.map_set_downsample(0.5)
+        added = ctx.map_add(p4(centre[None].astype(np.float32)), True)
+        got = ctx.map_removed_points()
+        if added == 1:  # the box centre itself is closer than any sampled point unless one sits exactly there
+            assert len(got) >= 1 and (np.abs(got - victim).max(1) < 1e-6).any()
+        ctx.map_build(p4(mp))
+        assert len(ctx.map_removed_points()) == 0
