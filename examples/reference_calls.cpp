@@ -77,12 +77,12 @@ int main() {
   normal_distribution<float> g(0.f, 0.005f);
   for (int i = -40; i < 40; ++i)
     for (int j = -40; j < 40; ++j)
-      for (int r = 0; r < 3; ++r) feats_undistort->points.push_back(pt(0.5f * (i + u(rng)), 0.5f * (j + u(rng)), -1.5f + g(rng)));
+      for (int r = 0; r < 3; ++r) feats_undistort->points.push_back(pt(0.5f * (i + u(rng)), 0.5f * (j + u(rng)), -1.3f + g(rng)));
   for (int j = -40; j < 40; ++j)
     for (int k = 0; k < 10; ++k)
       for (int r = 0; r < 3; ++r) {
-        feats_undistort->points.push_back(pt(15.f + g(rng), 0.5f * (j + u(rng)), -1.5f + 0.5f * (k + u(rng))));
-        feats_undistort->points.push_back(pt(0.5f * (j + u(rng)), -12.f + g(rng), -1.5f + 0.5f * (k + u(rng))));
+        feats_undistort->points.push_back(pt(15.2f + g(rng), 0.5f * (j + u(rng)), -1.5f + 0.5f * (k + u(rng))));
+        feats_undistort->points.push_back(pt(0.5f * (j + u(rng)), -12.2f + g(rng), -1.5f + 0.5f * (k + u(rng))));
       }
 
   // ---- laserMapping.cpp:683
@@ -158,7 +158,7 @@ int main() {
   // ---- :430-431 (map_incremental's two calls): a strip of new ground beyond the old one, and a few loose points
   PointVector PointToAdd, PointNoNeedDownsample;
   for (int i = 40; i < 50; ++i)
-    for (int j = -40; j < 40; ++j) PointToAdd.push_back(pt(0.5f * (i + u(rng)), 0.5f * (j + u(rng)), -1.5f));
+    for (int j = -40; j < 40; ++j) PointToAdd.push_back(pt(0.5f * (i + u(rng)), 0.5f * (j + u(rng)), -1.3f));
   for (int j = 0; j < 7; ++j) PointNoNeedDownsample.push_back(pt(40.f + j, 40.f, 3.f));
   const int before = ikdtree.validnum();
   add_point_size = ikdtree.Add_Points(PointToAdd, true);
