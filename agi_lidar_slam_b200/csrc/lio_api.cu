@@ -156,6 +156,8 @@ static int create_impl(lio_ctx* c) {
   {
     const char* env = getenv("LIO_STAGE_SEARCH");
     c->stage_search = env && atoi(env);
+    const char* il = getenv("LIO_INTERLEAVE");
+    c->interleave = il && atoi(il);
   }
   {
     const char* env = getenv("LIO_TIMELINE");

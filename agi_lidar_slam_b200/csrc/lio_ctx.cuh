@@ -22,6 +22,7 @@ struct lio_ctx {
   int32_t next_id = 0;     // id given to the next inserted point (host mirror)
   bool map_built = false;  // ≙ ikdtree.Root_Node != nullptr
   int knn_rings = 3;
+  bool interleave = false;      // LIO_INTERLEAVE=1: scan points dealt to the update's blocks in runs of 8 (load balance)
   bool stage_search = false;    // LIO_STAGE_SEARCH=1: the update's searches stage their cells in shared memory
   float map_downsample = 0.5f;  // ≙ KD_TREE::downsample_size (set_downsample_param, laserMapping.cpp:748)
   // batch scratch (sized for max(max_down_points, build chunk))

@@ -68,6 +68,7 @@ struct PassArgs {
   int rings;
   float own_min, own_max;
   int sharded;  // rows are shared out over the ranks (a finite window, or stripes)
+  int interleave;  // LIO_INTERLEAVE=1: runs of 8 points dealt round-robin over the blocks also on one GPU (load balance)
   // striped ownership (lio_set_shard_stripes): the rank owns the stripes s = floor((x - origin) / width) with
   // s mod stripe_mod == stripe_rank; stripe_mod == 0: the window above
   float stripe_origin, stripe_inv_w;
@@ -210,12 +211,21 @@ constexpr int OWN_MAX = 2048;  // longest chunk a list is kept for (beyond: ever
 struct Chunk {
   int beg, wid, nworkers;
   const unsigned short* list;  // sharded: offsets k of the owned points, ascending; else nullptr (k = t)
+  bool dealt;                  // runs of 8 dealt round-robin (always with a list)
   __device__ __forceinline__ int point(int k) const {
-    return list ? ((((k >> 3) * nworkers + wid) << 3) + (k & 7)) : beg + k;
+    return dealt ? ((((k >> 3) * nworkers + wid) << 3) + (k & 7)) : beg + k;
   }
   __device__ __forceinline__ int at(int t) const { return point(list ? (int)list[t] : t); }
 };
 __device__ __forceinline__ bool sharded_lists(const PassArgs& a, int C) { return a.sharded && C <= OWN_MAX; }
+// runs dealt round-robin: every worker files a row (the reduction waits for all of them)
+__device__ __forceinline__ bool dealt_runs(const PassArgs& a, int C) { return sharded_lists(a, C) || a.interleave; }
+// number of points of worker `wid` under the dealing: its runs r = 0 .. C/8-1 clipped to the scan (a prefix of k)
+__device__ __forceinline__ int dealt_count(int M, int C, int nworkers, int wid) {
+  int n = 0;
+  for (int r = 0; r < (C >> 3); ++r) n += max(0, min(8, M - (((r * nworkers) + wid) << 3)));
+  return n;
+}
 
 // Search phase of one tile: its queries (at most THREADS / G), one per G-lane group (esekfom.hpp:140).  The 5 neighbours
 // go to the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.  With staging
@@ -468,7 +478,7 @@ __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool searc
   const int tid = threadIdx.x;
   const int Ms = scan_size(a);
   // (sharded lists: the runs of the scan are dealt over ALL the workers, every one of them files a row)
-  const int nb = sharded_lists(a, chunk_points(Ms, nworkers)) ? nworkers : workers_used(Ms, nworkers);
+  const int nb = dealt_runs(a, chunk_points(Ms, nworkers)) ? nworkers : workers_used(Ms, nworkers);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   if (a.extrinsic_est)
     reduce_rows<3, 8>(a, nb, nout, target, s_warp);
@@ -1001,9 +1011,10 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
   const int C = chunk_points(M, nworkers);
   const int beg = wid * C;
   const bool compact = sharded_lists(a, C);
-  if (!compact && beg >= M) return;  // block-uniform
+  const bool dealt = dealt_runs(a, C);
+  if (!dealt && beg >= M) return;  // block-uniform
   const int end = min(M, beg + C);
-  Chunk ch{beg, wid, nworkers, compact ? ps->own : nullptr};
+  Chunk ch{beg, wid, nworkers, compact ? ps->own : nullptr, dealt};
   // ---- sharded map: the points of this block the rank owns = whose p_world.x AT THE LAST SEARCH PASS lies in its region.
   // Every rank computes the same bits for every point, so the ranks' lists partition the scan.  The list is rebuilt in
   // search passes (when the positions change) and kept across the cached passes that follow (the persistent kernel keeps
@@ -1048,7 +1059,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
     if (tid == 0) ps->n_own = built;
     __syncthreads();
   }
-  const int n = compact ? ps->n_own : end - beg;
+  const int n = compact ? ps->n_own : (dealt ? dealt_count(M, C, nworkers, wid) : end - beg);
   const int G = pick_group(n);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   const int nseg = THREADS / nout;
@@ -1620,6 +1631,7 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.stripe_inv_w = c->stripe_width > 0.f ? 1.0f / c->stripe_width : 0.f;
   a.sharded = (a.stripe_mod > 0 || !(own_min == -INFINITY && own_max == INFINITY)) ? 1 : 0;
   a.stage = c->stage_search ? 1 : 0;
+  a.interleave = c->interleave ? 1 : 0;
   a.partials = c->d_partials;
   a.dbg = c->d_dbg;
   if (c->d_dbg) cudaMemsetAsync(c->d_dbg, 0, 256 * sizeof(long long), c->stream);

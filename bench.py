@@ -59,7 +59,9 @@ def parse():
     ap.add_argument("--map-points", type=int, default=2_000_000)
     ap.add_argument("--rings", type=int, default=128)
     ap.add_argument("--cols", type=int, default=1024)
-    ap.add_argument("--poses", type=int, default=4, help="distinct scan poses cycled through the steps")
+    ap.add_argument("--poses", type=int, default=4, help="distinct scan poses cycled through the steps (SURVEY.md 8d suggests "
+                    "100: builder lines with --poses 32 are under profiles/; the default stays at round 1's 4 so that the "
+                    "lines of the rounds compare)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sequences", default="2,4,8",
                     help="extra leg: independent sequences per cooperative launch (lio_update_enqueue_multi); '' = skip")
@@ -241,6 +243,16 @@ def cpu_arm(wl, steps, warmup, seconds_budget, threads=None):
     return r
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return "%s x %d" % (line.split(":", 1)[1].strip(), os.cpu_count() or 1)
+    except OSError:
+        pass
+    return "unknown x %d" % (os.cpu_count() or 1)
+
+
 def cpu_arm_inner(wl, steps, warmup, seconds_budget, threads=None):
     from oracle import pyoracle as orc
 
@@ -257,10 +269,22 @@ def cpu_arm_inner(wl, steps, warmup, seconds_budget, threads=None):
     build_s = time.perf_counter() - t0
     backend = tree.knn_backend()
     bodies = []
+    t_vox = []
     for s in wl["scans"]:
         raw = s["scan"]
         pts5 = np.concatenate([raw[:, :3], np.zeros((len(raw), 1), np.float32), raw[:, 3:4]], 1)
-        bodies.append(np.ascontiguousarray(orc.voxel_grid(pts5, wl["leaf"])[0][:, :3]))
+        t0 = time.perf_counter()
+        cen = orc.voxel_grid(pts5, wl["leaf"])[0]
+        t_vox.append(time.perf_counter() - t0)
+        bodies.append(np.ascontiguousarray(cen[:, :3]))
+    # one search pass alone (Nearest_Search of every downsampled point at the prior, all threads): SURVEY.md 8d asks for
+    # the stages of the CPU path, not only their sum
+    t_knn = []
+    for j in range(min(len(bodies), 4)):
+        q = orc.body_to_world(wl["scans"][j]["x_prior"], bodies[j])
+        t0 = time.perf_counter()
+        tree.knn(q, 5, threads=threads) if use_ikd else tree.knn(q, 5, 5.0, threads=threads)
+        t_knn.append(time.perf_counter() - t0)
     times, nvalid, npass = [], [], []
     k = 0
     t_start = time.perf_counter()
@@ -284,7 +308,13 @@ def cpu_arm_inner(wl, steps, warmup, seconds_budget, threads=None):
                              "h_share_model/update loop (Eigen/PCL/Sophus absent)") if use_ikd else
                 "oracle port (hashed-grid kNN + restated update loop)", build_s=build_s,
                 matched_pts_per_s=float(np.sum(nvalid)) / tot, m=int(np.mean([len(b) for b in bodies])),
-                passes=float(np.mean(npass)))
+                passes=float(np.mean(npass)), cpu_model=cpu_model(),
+                stages_ms={"voxel_grid_1_thread": 1000 * float(np.mean(t_vox)),
+                           "nearest_search_one_pass": 1000 * float(np.mean(t_knn)),
+                           "update_all_passes": 1000 * tot / len(times),
+                           "note": "update_all_passes = searches (about half of the passes search again) + plane fits + "
+                                   "Jacobian rows + HtH/Hth products + 24x24 steps; voxel_grid is the oracle's restated "
+                                   "pcl::VoxelGrid (single-threaded, as PCL's)"})
 
 
 # ------------------------------------------------------------------------------------------ trajectories (configs 2, 4)
@@ -785,7 +815,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": workload_name(args, len(wl["map"])), "M": r["m"], "passes_per_scan": r["passes"]},
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                             "kind_detail": r["kind_detail"],
+                             "kind_detail": r["kind_detail"], "cpu_model": r["cpu_model"], "stages_ms": r["stages_ms"],
                              "sample": "%d whole updates of the bench scans (tree build %.1f s untimed)" %
                              (r["steps"], r["build_s"])},
             "matched_pts_per_s": r["matched_pts_per_s"],
@@ -1117,7 +1147,8 @@ def main():
                                 "kind_detail": r["kind_detail"],
                                 "sample": "%d whole updates of the same scans in %.1f s (tree build %.1f s untimed)" %
                                 (r["steps"], r["steps"] / r["value"], r["build_s"]),
-                                "matched_pts_per_s": r["matched_pts_per_s"]}
+                                "matched_pts_per_s": r["matched_pts_per_s"], "cpu_model": r["cpu_model"],
+                                "stages_ms": r["stages_ms"]}
         r3 = cpu_arm(wl, steps=1000, warmup=1, seconds_budget=min(8.0, args.cpu_seconds), threads=3)
         line["cpu_baseline_3_threads"] = {"value": r3["value"], "unit": UNIT, "cores": 3,
                                           "note": "MP_PROC_NUM=3, the reference's own setting (CMakeLists.txt:23-26)"}
