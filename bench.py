@@ -700,14 +700,12 @@ def knn_hbm_leg(args, local, dev, torch, _cabi):
     from agi_lidar_slam_b200 import synth
 
     n_map, nq = args.sharded_map_points, 1_000_000
-    _, mp = synth.city_map(n_map, 5005)
+    scene, mp = synth.city_map(n_map, 5005)
     rng = np.random.default_rng(1)
-    # scan order: a real downsampled scan arrives sorted by voxel (kz, ky, kx); random: no locality at all
+    # random: map points + noise in random order, no locality at all (the worst case)
     sel = rng.integers(0, len(mp), nq)
     q = np.ascontiguousarray(mp[sel] + rng.normal(0, 0.15, (nq, 3)).astype(np.float32), np.float32)
-    cell = np.floor(q / 0.5).astype(np.int64)
-    order = np.lexsort((cell[:, 0], cell[:, 1], cell[:, 2]))
-    ctx = _cabi.Context(local, max_scan_points=1 << 16, max_down_points=nq, max_map_points=int(len(mp) * 1.02))
+    ctx = _cabi.Context(local, max_scan_points=1 << 18, max_down_points=nq, max_map_points=int(len(mp) * 1.02))
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -720,24 +718,42 @@ def knn_hbm_leg(args, local, dev, torch, _cabi):
     if f.exists():
         cap = json.loads(f.read_text())
     peak, peak_src = measured_peak()
-    for name, qq in (("random", q), ("scan_order", q[order])):
-        ctx._check(ctx._lib.lio_knn5(ctx._h, qq.ctypes.data, nq, 5.0, None, None, None))  # queries -> device
+    # scans: what the update's searches look like -- OS1-128 scans at random poses in the same city, downsampled at 0.5 m
+    # by the product's own voxel filter (voxel order), in the world frame, back to back until the launch is full
+    d, col = synth.spinning_dirs(128, 1024, -22.5, 22.5)
+    ext = float(np.ptp(mp[:, 0])) / 2 - 150.0
+    parts, k = [], 0
+    nqs = 1 << 18  # queries of the `scans` launches (a raycast scan costs the host half a second)
+    while sum(len(p) for p in parts) < nqs:
+        r2 = np.random.default_rng(100 + k)
+        pos = np.array([r2.uniform(-ext, ext), r2.uniform(-ext, ext), 2.0])
+        R = synth.rot_zyx(r2.uniform(-np.pi, np.pi), r2.normal(0, 0.02), r2.normal(0, 0.02))
+        scan = synth.static_scan(scene, d, col / 1024 * 100.0, pos, R, 120.0, 200 + k)
+        body, _, _ = ctx.scan_preprocess(scan, None, None, 0.5)
+        parts.append((body[:, :3].astype(np.float64) @ R.T + pos).astype(np.float32))
+        k += 1
+    q_scans = np.ascontiguousarray(np.concatenate(parts)[:nqs])
+    out["scans_in_launch"] = k
+    for name, qq in (("random", q), ("scans", q_scans)):
+        n = len(qq)
+        ctx._check(ctx._lib.lio_knn5(ctx._h, qq.ctypes.data, n, 5.0, None, None, None))  # queries -> device
         ts = []
         for rep in range(6):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            ctx.knn5_resident(nq)
+            ctx.knn5_resident(n)
             e1.record(stream)
             torch.cuda.synchronize(dev)
             ts.append(e0.elapsed_time(e1))
         ms = float(np.median(ts[1:]))
-        leg = {"ms_per_launch": ms, "queries_per_s": nq / (ms * 1e-3)}
+        leg = {"queries_per_launch": n, "ms_per_launch": ms, "queries_per_s": n / (ms * 1e-3)}
         c = cap.get(name)
         if c:  # DRAM bytes of the ncu capture applied to the duration measured here
             leg["dram_bytes_per_query"] = c["dram_bytes_per_launch"] / c["queries_per_launch"]
-            leg["dram_GBps"] = leg["dram_bytes_per_query"] * nq / (ms * 1e-3) / 1e9
+            leg["dram_GBps"] = leg["dram_bytes_per_query"] * n / (ms * 1e-3) / 1e9
             leg["frac_of_hbm_peak"] = leg["dram_GBps"] / peak
             leg["ncu_ms_per_launch"] = c["ms_per_launch"]
+            leg["lts_hit_pct"], leg["l1tex_hit_pct"] = c.get("lts_hit_pct"), c.get("l1tex_hit_pct")
         out[name] = leg
     out["traffic_source"] = "profiles/r2_knn_hbm.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of knn_batch_kernel)" if cap else None
     out["peak"], out["peak_source"] = peak, peak_src
