@@ -197,7 +197,9 @@ class ClockSampler:
 
 def ncu_traffic():
     """DRAM bytes per update_kernel launch from the committed ncu capture of this same workload (profiles/)."""
-    p = ROOT / "profiles" / "r1_update_kernel_traffic.json"
+    p = ROOT / "profiles" / "r2_update_kernel_traffic.json"
+    if not p.exists():
+        p = ROOT / "profiles" / "r1_update_kernel_traffic.json"
     try:
         return float(json.loads(p.read_text())["dram_bytes_per_launch"])
     except Exception:  # noqa: BLE001
@@ -1095,7 +1097,7 @@ def main():
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "update_kernel (persistent: all h_share_model passes + Kalman steps of one scan)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                "traffic_source": "profiles/r1_update_kernel_traffic.json (ncu --set full, dram__bytes_read+write.sum)",
+                "traffic_source": "profiles/r2_update_kernel_traffic.json (ncu --set full, dram__bytes_read+write.sum)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms_cold_l2": launch_ms,
                 "note": "latency-bound by construction: 116 B x M x passes is ~4 MB per scan (SURVEY.md §8d)",
                 "single_pass_kernel": {"search_ms_cold_l2": t_search_cold, "search_ms_warm_l2": t_search_warm,
