@@ -106,7 +106,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // synchronised by the caller).  Whole block.  On return (block synchronised) st->overflow says whether the tile fits; if not, nothing of
 // the staging may be used.
 template <int NT>
-__device__ __forceinline__ void stage_cells(const MapView& map, StageSmem* st, const float4* q, int cnt,
+__device__ __noinline__ void stage_cells(const MapView& map, StageSmem* st, const float4* q, int cnt,
                                             long long* dbg = nullptr) {
   const int tid = threadIdx.x;
   auto mark = [&](int tag) {  // LIO_TIMELINE instrumentation: last thread of block 0

@@ -208,20 +208,23 @@ constexpr int OWN_MAX = 2048;  // longest chunk a list is kept for (beyond: ever
 // Sharded: runs of 8 points dealt round-robin over the blocks (run g = r * nworkers + wid), so that every block holds a
 // uniform sample of the scan and owns ~1/world of it whatever the shape of the ranks' regions -- with contiguous chunks
 // (28 m of scan each) whole blocks fall to one rank and the slowest block of a pass is as slow as on one GPU.
+template <bool SH>
 struct Chunk {
   int beg, wid, nworkers;
   const unsigned short* list;  // sharded: offsets k of the owned points, ascending; else nullptr (k = t)
   bool dealt;                  // runs of 8 dealt round-robin (always with a list)
   __device__ __forceinline__ int point(int k) const {
-    return dealt ? ((((k >> 3) * nworkers + wid) << 3) + (k & 7)) : beg + k;
+    return (SH && dealt) ? ((((k >> 3) * nworkers + wid) << 3) + (k & 7)) : beg + k;
   }
-  __device__ __forceinline__ int at(int t) const { return point(list ? (int)list[t] : t); }
+  __device__ __forceinline__ int at(int t) const { return point((SH && list) ? (int)list[t] : t); }
 };
+// SH = false is the instantiation every unsharded update runs: lists, dealing and ownership are compiled out of it (a
+// pass runs from a cold instruction cache and registers are at the limit: the feature must cost nothing where it is off)
 __device__ __forceinline__ bool sharded_lists(const PassArgs& a, int C) { return a.sharded && C <= OWN_MAX; }
 // runs dealt round-robin: every worker files a row (the reduction waits for all of them)
 __device__ __forceinline__ bool dealt_runs(const PassArgs& a, int C) { return sharded_lists(a, C) || a.interleave; }
 // number of points of worker `wid` under the dealing: its runs r = 0 .. C/8-1 clipped to the scan (a prefix of k)
-__device__ __forceinline__ int dealt_count(int M, int C, int nworkers, int wid) {
+__device__ __noinline__ int dealt_count(int M, int C, int nworkers, int wid) {
   int n = 0;
   for (int r = 0; r < (C >> 3); ++r) n += max(0, min(8, M - (((r * nworkers) + wid) << 3)));
   return n;
@@ -230,8 +233,8 @@ __device__ __forceinline__ int dealt_count(int M, int C, int nworkers, int wid) 
 // Search phase of one tile: its queries (at most THREADS / G), one per G-lane group (esekfom.hpp:140).  The 5 neighbours
 // go to the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.  With staging
 // on the caller has staged the tile's neighbour cells (stage_cells); use_stage says whether the tile fitted.
-template <int G>
-__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk ch,
+template <int G, bool SH>
+__device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk<SH> ch,
                                          float4* s_nb, int* s_cnt, float4* s_body,
                                          const float4* body, StageSmem* st, bool use_stage) {
   const int lane = threadIdx.x & 31;
@@ -283,7 +286,8 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
 
 // Finish phase of one tile, one thread per point: steps 1.1-1.2 and 1.5-3 of h_share_model (esekfom.hpp:123-133,
 // 153-226) from the point's 5 neighbours (just found: shared memory; cached: a.near_pts with the sticky mask).
-__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk ch,
+template <bool SH>
+__device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk<SH> ch,
                                          int rows, bool search, const float4* s_nb,
                                          const int* s_cnt, double* s_rows, unsigned char* s_valid, const float4* s_body,
                                          bool copy_body) {
@@ -294,7 +298,7 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
     return;
   }
   const int i = ch.at(t0 + row);
-  const unsigned short* list = ch.list;
+  const unsigned short* list = SH ? ch.list : nullptr;
   const float4 b = search ? s_body[row] : __ldcg(a.body + i);  // the search phase left it in shared memory
   if (copy_body) const_cast<float4*>(a.body)[i] = b;            // host-direct path, pass 0: keep a device copy
   const double pb[3] = {b.x, b.y, b.z};
@@ -337,9 +341,14 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
   if (sel) a.normvec[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pd2);
   // Ownership (sharded map): by the x of the position the row was SEARCHED at -- the same on every rank and fixed until
   // the next search pass, so a row and its cached neighbours stay with one rank.  Listed rows are owned by construction.
-  float qx = pwx;
-  if (!list && !search && a.sharded) qx = __ldcg(&a.near_q[i]).x;
-  const bool valid = sel && (list != nullptr || owns_row(a, qx));
+  bool valid = sel;
+  if (SH) {
+    float qx = pwx;
+    if (!list && !search && a.sharded) qx = __ldcg(&a.near_q[i]).x;
+    valid = sel && (list != nullptr || owns_row(a, qx));
+  } else {
+    valid = sel && !(pwx != pwx);  // (an unsharded update owns every row; a NaN position contributes nothing, as before)
+  }
   s_valid[row] = valid ? 1 : 0;
   if (valid) {
     // step 3 (esekfom.hpp:197-226): Jacobian row and residual
@@ -385,6 +394,7 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
 // memory, products accumulated by thread (output o, segment seg) over rows seg, seg + nseg, ... of every tile, then
 // the segments are combined in order and the block's partial blob is written to a.partials[blockIdx.x].
 struct PassSmem;
+template <bool SH>
 __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSmem* st, int nworkers, int wid,
                            bool first_pass, unsigned target);
 
@@ -998,9 +1008,57 @@ constexpr size_t SMEM_STAGE_OFF =
     ((sizeof(PassSmem) > sizeof(SolveSmem) ? sizeof(PassSmem) : sizeof(SolveSmem)) + 127) & ~(size_t)127;
 constexpr size_t SMEM_PASS_BYTES = SMEM_STAGE_OFF + sizeof(StageSmem);  // with staging; SMEM_STAGE_OFF without
 static size_t pass_smem_bytes(const lio_ctx* c) { return c->stage_search ? SMEM_PASS_BYTES : SMEM_STAGE_OFF; }
+// Sharded map: the points of this block the rank owns = whose p_world.x AT THE LAST SEARCH PASS lies in its region.
+// Every rank computes the same bits for every point, so the ranks' lists partition the scan.  The list is rebuilt in
+// search passes (when the positions change) and kept across the cached passes that follow (the persistent kernel keeps
+// it in shared memory; a per-pass launch rebuilds it from a.near_q).  Out of line: the unsharded update never fetches
+// this code (a pass runs from a cold instruction cache, its cost is its code size).
+__device__ __noinline__ void build_own_list(const PassArgs& a, PassSmem* ps, const Chunk<true> ch, const float4* body, int C,
+                                            int M, bool search) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int built = 0;
+#pragma unroll 1
+  for (int k0 = 0; k0 < C; k0 += THREADS) {
+    const int k = k0 + tid, i = ch.point(k);
+    const bool in = k < C && i < M;
+    float qx = 0.f;
+    if (in) {
+      if (search) {
+        const float4 b = body[i];
+        const double pb[3] = {b.x, b.y, b.z};
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        body_to_world(ps->pc, pb, q.x, q.y, q.z);
+        a.near_q[i] = q;
+        qx = q.x;
+      } else {
+        qx = __ldcg(&a.near_q[i]).x;
+      }
+    }
+    const bool own = in && owns_row(a, qx);
+    if (in && !own && search) {  // another rank's row: nothing cached here
+      a.selected[i] = 0;
+      a.near_cnt[i] = 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, own);
+    if (lane == 0) ps->wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int base = built, tot = 0;
+    for (int w = 0; w < THREADS / 32; ++w) {
+      if (w < warp) base += ps->wcnt[w];
+      tot += ps->wcnt[w];
+    }
+    if (own) ps->own[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)k;
+    built += tot;
+    __syncthreads();
+  }
+  if (tid == 0) ps->n_own = built;
+  __syncthreads();
+}
+
 // ps->pc holds the per-pass constants (the caller loads or computes them and synchronises the block).
 // Worker `wid` of `nworkers` runs its chunk of the scan (chunk_points) and leaves its partial blob, stamped `target`, in
 // row wid of a.partials; a worker whose chunk is empty writes nothing (the reduction knows: workers_used).
+template <bool SH>
 __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSmem* st, int nworkers, int wid,
                            bool first_pass, unsigned target) {
   const int tid = threadIdx.x;
@@ -1010,54 +1068,14 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
   stamp(a.dbg, 0, 2);
   const int C = chunk_points(M, nworkers);
   const int beg = wid * C;
-  const bool compact = sharded_lists(a, C);
-  const bool dealt = dealt_runs(a, C);
+  const bool compact = SH && sharded_lists(a, C);
+  const bool dealt = SH && dealt_runs(a, C);
   if (!dealt && beg >= M) return;  // block-uniform
   const int end = min(M, beg + C);
-  Chunk ch{beg, wid, nworkers, compact ? ps->own : nullptr, dealt};
-  // ---- sharded map: the points of this block the rank owns = whose p_world.x AT THE LAST SEARCH PASS lies in its region.
-  // Every rank computes the same bits for every point, so the ranks' lists partition the scan.  The list is rebuilt in
-  // search passes (when the positions change) and kept across the cached passes that follow (the persistent kernel keeps
-  // it in shared memory; a per-pass launch rebuilds it from a.near_q).
-  if (compact && (search || ps->n_own < 0)) {
-    const int lane = tid & 31, warp = tid >> 5;
-    int built = 0;
-#pragma unroll 1
-    for (int k0 = 0; k0 < C; k0 += THREADS) {
-      const int k = k0 + tid, i = ch.point(k);
-      const bool in = k < C && i < M;
-      float qx = 0.f;
-      if (in) {
-        if (search) {
-          const float4 b = body[i];
-          const double pb[3] = {b.x, b.y, b.z};
-          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-          body_to_world(ps->pc, pb, q.x, q.y, q.z);
-          a.near_q[i] = q;
-          qx = q.x;
-        } else {
-          qx = __ldcg(&a.near_q[i]).x;
-        }
-      }
-      const bool own = in && owns_row(a, qx);
-      if (in && !own && search) {  // another rank's row: nothing cached here
-        a.selected[i] = 0;
-        a.near_cnt[i] = 0;
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, own);
-      if (lane == 0) ps->wcnt[warp] = __popc(bal);
-      __syncthreads();
-      int base = built, tot = 0;
-      for (int w = 0; w < THREADS / 32; ++w) {
-        if (w < warp) base += ps->wcnt[w];
-        tot += ps->wcnt[w];
-      }
-      if (own) ps->own[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)k;
-      built += tot;
-      __syncthreads();
-    }
-    if (tid == 0) ps->n_own = built;
-    __syncthreads();
+  Chunk<SH> ch{beg, wid, nworkers, compact ? ps->own : nullptr, dealt};
+  if (SH) {
+    if (compact && (search || ps->n_own < 0))
+      build_own_list(a, ps, Chunk<true>{beg, wid, nworkers, ps->own, dealt}, body, C, M, search);
   }
   const int n = compact ? ps->n_own : (dealt ? dealt_count(M, C, nworkers, wid) : end - beg);
   const int G = pick_group(n);
@@ -1100,16 +1118,16 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
         use_stage = st->overflow == 0;
       }
       if (G == 32)
-        search_tile<32>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<32, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       else if (G == 16)
-        search_tile<16>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<16, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       else
-        search_tile<8>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+        search_tile<8, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
       __syncthreads();
       if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
       stamp(a.dbg, 0, 3);
     }
-    finish_tile(a, ps->pc, t0, n, ch, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
+    finish_tile<SH>(a, ps->pc, t0, n, ch, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
     __syncthreads();
     stamp(a.dbg, 0, 4);
     if (seg < nseg) {
@@ -1231,7 +1249,7 @@ __device__ __forceinline__ void worker_receive(const SolveArgs& s, PassSmem* ps,
 // (target = epoch + pass + 1): nothing is zeroed between launches and there is no fence on the per-pass path.
 // nblk / bid: size of the (sub-)grid that works on this update and this block's index in it -- the whole grid for a
 // single update, a slice of it when several independent sequences share one launch (update_kernel_multi).
-template <bool HOST>
+template <bool HOST, bool SH>
 __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& s, const unsigned epoch,
                                             const ShardArgs& sh, const HostPath& hp, const int nblk, const int bid) {
   extern __shared__ __align__(128) unsigned char smem_raw[];  // SMEM_PASS_BYTES
@@ -1294,7 +1312,7 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
   bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
     const unsigned target = epoch + (unsigned)pass_no + 1u;
-    block_pass(a, search, &ps, st, nworkers, wid, pass_no == 0, target);
+    block_pass<SH>(a, search, &ps, st, nworkers, wid, pass_no == 0, target);
     stamp(a.dbg, 0, 7);
     worker_receive(s, &ps, target, &ps.flag, wid);
     __syncthreads();
@@ -1340,14 +1358,19 @@ __device__ __forceinline__ void worker_receive(const SolveArgs& s, PassSmem* ps,
 
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const PassArgs a, const SolveArgs s,
                                                                             const unsigned epoch, const ShardArgs sh) {
-  update_body<false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x,
-                     (int)blockIdx.x);  // the host path is compiled out
+  update_body<false, false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x,
+                            (int)blockIdx.x);  // the host path is compiled out
+}
+// the instantiation with ownership lists and dealt runs: sharded map (windows or stripes), or LIO_INTERLEAVE=1
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_sh(const PassArgs a, const SolveArgs s,
+                                                                               const unsigned epoch, const ShardArgs sh) {
+  update_body<false, true>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x, (int)blockIdx.x);
 }
 // the same loop with the host-direct prologue / epilogue; its 4.9 KB of extra parameters are only paid by that path
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host(const PassArgs a, const SolveArgs s,
                                                                                  const unsigned epoch, const ShardArgs sh,
                                                                                  const __grid_constant__ HostPath hp) {
-  update_body<true>(a, s, epoch, sh, hp, (int)gridDim.x, (int)blockIdx.x);
+  update_body<true, false>(a, s, epoch, sh, hp, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // Several INDEPENDENT updates (different sequences, each with its own map, scan and filter: BASELINE.json config 4) in
@@ -1366,13 +1389,14 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_mult
   if (q >= m.n) return;  // left-over blocks when the grid does not divide evenly
   ShardArgs sh;
   sh.world = 1;
-  update_body<false>(m.a[q], m.s[q], m.epoch[q], sh, *reinterpret_cast<const HostPath*>(&m), per,
+  update_body<false, false>(m.a[q], m.s[q], m.epoch[q], sh, *reinterpret_cast<const HostPath*>(&m), per,
                      (int)blockIdx.x - q * per);
 }
 
 // One pass at the state in s.x; the last block to finish reduces the partials into s.blob (same worker split and
 // the same summation order as update_kernel, so the stepwise driver reproduces its bits).
 // mode: 0 cached, 1 search, -1 as the loop state says (sharded driver).
+template <bool SH>
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const PassArgs a, const SolveArgs s, int mode,
                                                                           unsigned target) {
   extern __shared__ __align__(128) unsigned char smem_raw[];  // SMEM_PASS_BYTES
@@ -1396,7 +1420,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
       }
     }
     __syncthreads();
-    block_pass(a, search, &ps, st, nworkers, (int)blockIdx.x, false, target);
+    block_pass<SH>(a, search, &ps, st, nworkers, (int)blockIdx.x, false, target);
   }
   __threadfence();
   __syncthreads();
@@ -1582,8 +1606,8 @@ int ensure_tables(lio_ctx* c) {
     LIO_CHECK(c, cudaMemcpyToSymbol(c_is_no, is_no, 78));
   }
   // the pass / update kernels carry {pass or solve state | staging area of the searches} in dynamic shared memory
-  const void* big[] = {(const void*)update_kernel, (const void*)update_kernel_host, (const void*)update_kernel_multi,
-                       (const void*)pass_kernel};
+  const void* big[] = {(const void*)update_kernel,       (const void*)update_kernel_sh,   (const void*)update_kernel_host,
+                       (const void*)update_kernel_multi, (const void*)pass_kernel<false>, (const void*)pass_kernel<true>};
   for (const void* f : big)
     LIO_CHECK(c, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS_BYTES));
   if (c->device < 64) g_tables_ready[c->device] = true;
@@ -1675,6 +1699,7 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   int rc = ensure_tables(c);
   if (rc) return rc;
   PassArgs a = make_pass_args(c, ext, own_min, own_max, sharded);
+  if (hd != nullptr) a.interleave = 0;  // the host-direct kernel is the plain instantiation
   static thread_local HostPath hp;  // 4.9 KB: kept off the stack frame of every call
   hp.use_param_prior = 0;
   hp.host_out = nullptr;
@@ -1713,7 +1738,9 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   unsigned epoch = c->epoch;
   c->epoch += 40;  // > max_iter + 2
   void* args[] = {&a, &s, &epoch, &sh, &hp};
-  LIO_CHECK(c, cudaLaunchCooperativeKernel(hd != nullptr ? (const void*)update_kernel_host : (const void*)update_kernel,
+  const bool sh_code = a.sharded || a.interleave;  // (never with the host-direct path: launch_update's callers)
+  LIO_CHECK(c, cudaLaunchCooperativeKernel(hd != nullptr ? (const void*)update_kernel_host
+                                                         : (sh_code ? (const void*)update_kernel_sh : (const void*)update_kernel),
                                            dim3(pass_grid_blocks(c)), dim3(THREADS), args, pass_smem_bytes(c), c->stream));
   c->launches++;
   return LIO_OK;
@@ -1729,6 +1756,7 @@ int launch_update_multi(lio_ctx* const* cs, int n, double R, int max_iter, int e
   for (int q = 0; q < n; ++q) {
     lio_ctx* k = cs[q];
     m.a[q] = make_pass_args(k, ext, -INFINITY, INFINITY);
+    m.a[q].interleave = 0;  // (the multi-sequence kernel is the plain instantiation)
     m.s[q] = make_solve_args(k, R, max_iter, from_snapshot);
     if (const int re = epoch_guard(k, c)) return re;
     m.epoch[q] = k->epoch;
@@ -1749,7 +1777,10 @@ int launch_pass(lio_ctx* c, int mode, int extrinsic_est, float own_min, float ow
   SolveArgs s = make_solve_args(c, 0.0, 0, 0);
   LIO_CHECK(c, cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
   if (const int re = epoch_guard(c, c)) return re;
-  pass_kernel<<<pass_grid_blocks(c), THREADS, pass_smem_bytes(c), c->stream>>>(a, s, mode, ++c->epoch);
+  if (a.sharded || a.interleave)
+    pass_kernel<true><<<pass_grid_blocks(c), THREADS, pass_smem_bytes(c), c->stream>>>(a, s, mode, ++c->epoch);
+  else
+    pass_kernel<false><<<pass_grid_blocks(c), THREADS, pass_smem_bytes(c), c->stream>>>(a, s, mode, ++c->epoch);
   c->launches++;
   LIO_CHECK(c, cudaGetLastError());
   return LIO_OK;
