@@ -11,7 +11,6 @@
 namespace lio {
 size_t preprocess_sort_bytes(int64_t n);
 int preprocess_init_counters(lio_ctx* c);
-int preprocess_init_tables(lio_ctx* c);
 
 __global__ void set_w_kernel(float4* dst, const float* w, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,12 +208,6 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_undist, sizeof(float4) * N);
   ALLOC(c->d_vkeys, 12 * N);
   ALLOC(c->d_poses, sizeof(lio_pose6d) * 128);
-  ALLOC(c->d_sorted_aux, 4 * N);
-  ALLOC(c->d_run_heads, 4 * N);
-  ALLOC(c->d_runs_status, 8 * (N / 2048 + 2));
-  ALLOC(c->d_runs_ticket, 4);
-  LIO_CHECK(c, cudaMemset(c->d_runs_status, 0, 8 * (N / 2048 + 2)));
-  LIO_CHECK(c, cudaMemset(c->d_runs_ticket, 0, 4));
   ALLOC(c->d_sort_keys_in, 4 * N);
   ALLOC(c->d_sort_keys_out, 4 * N);
   ALLOC(c->d_sort_vals_in, 4 * N);
@@ -255,8 +248,6 @@ static int create_impl(lio_ctx* c) {
   int rc = ensure_tables(c);
   if (rc) return rc;
   rc = map_reset(c);
-  if (rc) return rc;
-  rc = preprocess_init_tables(c);
   if (rc) return rc;
   rc = preprocess_init_counters(c);
   if (rc) return rc;
@@ -304,7 +295,7 @@ void lio_destroy(lio_ctx* c) {
                   c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_mailbox,
                   c->d_cloud,
                   c->d_raw,       c->d_raw_aux,     c->d_undist,
-                  c->d_vkeys,     c->d_poses,       c->d_sorted_aux,  c->d_run_heads,   c->d_runs_status, c->d_runs_ticket,
+                  c->d_vkeys,     c->d_poses,
                   c->d_sort_keys_in, c->d_sort_keys_out, c->d_sort_vals_in, c->d_sort_vals_out, c->d_cub_tmp,
                   c->d_prep_counters, c->vf.key,    c->vf.cnt,        c->vf.mid,        c->vf.off,        c->vf.rank,
                   c->vf.lin,      c->vf.list,       c->vf.big,        c->vf.slot,       c->vf.seg,        c->vf.bitmap,

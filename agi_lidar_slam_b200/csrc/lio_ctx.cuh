@@ -99,12 +99,7 @@ struct lio_ctx {
   float4* d_undist = nullptr;       // N undistorted
   int* d_vkeys = nullptr;           // N x 3
   lio_pose6d* d_poses = nullptr;    // up to 256
-  float* d_sorted_aux = nullptr;    // N intensities in leaf-sorted order
-  int* d_run_heads = nullptr;       // first sorted position of every occupied leaf
-  unsigned long long* d_runs_status = nullptr;  // runs_gather_kernel: one look-back word per tile
-  unsigned* d_runs_ticket = nullptr;            // ... tile tickets (the last tile of a launch puts it back to zero)
-  unsigned runs_tag = 0;
-  uint32_t* d_sort_keys_in = nullptr;  // N linear leaf indices (and ring keys while decoding)
+  uint32_t* d_sort_keys_in = nullptr;  // ring keys of the sensor decoders (the scan's voxel filter sorts nothing)
   uint32_t* d_sort_keys_out = nullptr;
   uint32_t* d_sort_vals_in = nullptr;
   uint32_t* d_sort_vals_out = nullptr;

@@ -951,8 +951,6 @@ size_t preprocess_sort_bytes(int64_t n) {
   return a > b ? a : b;
 }
 
-int preprocess_init_tables(lio_ctx*) { return LIO_OK; }
-
 // raw points already staged in c->d_raw (and c->d_raw_aux when has_aux), poses in c->d_poses
 int preprocess(lio_ctx* c, int64_t n, int n_poses, const lio_state* end_state, float leaf, bool has_aux) {
   if (n_poses > MAX_POSES) {

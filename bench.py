@@ -928,7 +928,9 @@ def main():
                 nvalid += nv
                 npass += npz
         torch.cuda.synchronize(dev)
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        resident_run.median_ms = float(np.median(per_step)) if per_step else None
+        total_ms = sum(per_step)
         return total_ms, nvalid, npass
 
     resident_run(0, max(3, args.warmup), True)
@@ -937,6 +939,7 @@ def main():
     sampler.start()
     launches0 = ctx.launch_count
     ms_cold, nvalid, npass = resident_run(args.steps, 0, True)
+    med_cold = max_over_ranks(resident_run.median_ms)
     launches = ctx.launch_count - launches0
     barrier()
     ms_cold = max_over_ranks(ms_cold)
@@ -1111,7 +1114,7 @@ def main():
         "config": {"workload": workload_name(args, n_map), "N_raw": int(np.mean([len(r) for r in raws])), "M": M,
                    "passes_per_scan": passes_per_scan, "l2": "flushed (384 MiB write) before every timed step",
                    "map_build_s": map_build_s},
-        "value_l2_warm": value_warm, "matched_pts_per_s": matched,
+        "value_l2_warm": value_warm, "ms_per_step_median": med_cold, "matched_pts_per_s": matched,
         "full_scan": {"value": full_value, "unit": UNIT,
                       "what": "raw scan H2D + voxel downsample + update + posterior D2H through one lio_scan_step call (static map), host-timed"},
         "preprocess": preprocess,
