@@ -6,9 +6,11 @@
 //            boxplus, convergence state machine, covariance update.
 // update_kernel runs the WHOLE update_iterated_dyn_share_modified loop as one persistent cooperative launch.  Blocks
 // 0 .. grid-2 are workers (one h_share_model pass after the other: search tile -> finish tile -> block reduction ->
-// one partial row); the last block is the solver: it keeps the filter in shared memory, adds the workers' rows as
-// their arrival stamps come in, performs the Kalman step and publishes the constants of the next pass.  There is no
-// host round trip and no launch between passes.  pass_kernel / solve_kernel / begin_kernel run the same device code
+// one partial row of self-validating stamped words); the last block is the solver: it keeps the filter in shared
+// memory, adds the workers' rows once their stamps show up, performs the Kalman step and publishes the new pose the
+// same way.  There is no host round trip, no launch and no fence between passes.  The sharded-map variant (ownership
+// lists, runs dealt over the blocks, peer exchange) lives in its own instantiation (block_pass<true>, update_kernel_sh)
+// so that the plain update does not carry its code or its registers.  pass_kernel / solve_kernel / begin_kernel run the same device code
 // as single steps (host-driven passes, and the NCCL variant of the sharded-map driver); update_kernel_host adds the
 // host-direct prologue / epilogue; block_exchange moves the sharded-map blobs through NVLink peer mailboxes.
 // No floating-point atomics anywhere: every sum has a fixed order.

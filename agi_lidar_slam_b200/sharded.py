@@ -1,12 +1,15 @@
 """Spatially sharded map (BASELINE.json config 5, SURVEY.md §8e case 2): host side.
 
-The map is cut into `world` equal-count slabs along x.  Rank r holds the points of its slab plus a halo of
-sqrt(knn_max_d2) + margin metres on both sides, so every neighbour set that can pass the validity gate
-(d2[4] <= 5, esekfom.hpp:147) of a query inside the slab is complete in the rank's local map.  During an update every
-rank runs the pass on the whole scan against its local map, but only the queries whose p_world.x falls inside its CORE
-slab contribute Jacobian rows (lio_update_pass_enqueue's ownership window); the 92-double blob {HtH 78, Hth 12, n_valid,
-searched} is summed over the ranks (NCCL all-reduce on the device buffer, or any `reduce` callable) and every rank
-performs the identical Kalman step, so the states stay bit-identical across ranks.  Nothing else crosses NVLink.
+The map is cut over `world` ranks along x -- one equal-count slab per rank (`slab_bounds` / `shard_indices`), or stripes
+of a few metres dealt round-robin (`stripe_indices` + `Context.set_shard_stripes`: every rank then gets a share of a
+scan wherever the robot is).  Rank r holds the points of its region plus a halo of sqrt(knn_max_d2) + margin metres on
+both sides, so every neighbour set that can pass the validity gate (d2[4] <= 5, esekfom.hpp:147) of a query inside
+the region is complete in the rank's local map.  During an update a rank searches and contributes only the rows it
+OWNS: those whose p_world.x at their last search pass falls into its region (the same bits on every rank; the
+ownership arguments of lio_update_pass_enqueue / lio_update_enqueue_sharded).  The 92-double blob {HtH 78, Hth 12,
+n_valid, searched} is summed over the ranks in rank order (inside the kernel over NVLink peer mailboxes, or by an
+NCCL all-reduce / any `reduce` callable between the pass and the step) and every rank performs the identical Kalman
+step, so the states stay bit-identical across ranks.  Nothing else crosses NVLink.
 """
 from __future__ import annotations
 

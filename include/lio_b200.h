@@ -265,14 +265,18 @@ int lio_scan_step_settle(lio_ctx*, int32_t counts[3]);
  * context (stream order between the contexts' streams and the launch is taken care of). */
 int lio_update_enqueue_multi(lio_ctx* const* ctxs, int n, double R, int max_iter, int extrinsic_est, int from_snapshot);
 /* Sharded-map driver: begin, then per pass {pass_enqueue -> all-reduce 92 doubles at
- * lio_blob_device_ptr -> step_enqueue}.  x_own_min/max restrict the queries this rank owns to
- * x_own_min <= p_world.x < x_own_max (use -inf/+inf for a single GPU).  begin resets the loop state
- * (x_propagated = x, converge = true, ...) and forms the per-update constants of the Kalman step. */
+ * lio_blob_device_ptr -> step_enqueue}.  x_own_min/max say which rows this rank owns: those whose p_world.x AT THEIR
+ * LAST SEARCH PASS lies in [x_own_min, x_own_max) -- the same FP32 bits on every rank, fixed until the next search pass,
+ * so a row and its cached neighbours stay with one rank (use -inf/+inf for a single GPU; lio_set_shard_stripes replaces
+ * the window by stripes).  A rank searches only the rows it owns; after a sharded update the per-point outputs
+ * (lio_get_neighbors) are meaningful for owned rows only.  begin resets the loop state (x_propagated = x,
+ * converge = true, ...) and forms the per-update constants of the Kalman step. */
 int lio_update_begin(lio_ctx* ctx, int max_iter, int extrinsic_est, int from_snapshot);
 int lio_update_pass_enqueue(lio_ctx* ctx, int extrinsic_est, float x_own_min, float x_own_max);
 int lio_update_step_enqueue(lio_ctx* ctx, double R, int extrinsic_est);
 /* The same exchange INSIDE the persistent kernel, over NVLink peer memory instead of NCCL + launches: every rank's
- * solver block stores its blob into a mailbox of every peer (mapped with cudaIpc), waits for the peers' stamps and adds
+ * solver block stores its blob as self-validating stamped words into a mailbox of every peer (mapped with cudaIpc; no
+ * fence, no flag), polls its own mailbox until every rank's words carry the pass's stamp and adds
  * the blobs in rank order; the whole sharded update is one launch per rank.  Setup once: lio_peer_handle on every rank,
  * all-gather the 64-byte handles, lio_peer_connect.  All ranks must then enqueue the same sequence of sharded updates.
  * lio_peer_status reports whether a peer failed to show up (the wait is bounded; the update is then garbage). */
