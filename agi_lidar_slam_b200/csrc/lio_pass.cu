@@ -238,7 +238,7 @@ __device__ __noinline__ int dealt_count(int M, int C, int nworkers, int wid) {
 template <int G, bool SH>
 __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk<SH> ch,
                                          float4* s_nb, int* s_cnt, float4* s_body,
-                                         const float4* body, StageSmem* st, bool use_stage) {
+                                         const float4* body, StageSmem* st, bool use_stage, bool copy_body) {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int row = threadIdx.x / G;
@@ -246,7 +246,10 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
   const int qi = act ? row : n - 1 - t0;  // idle groups redo the last query: the whole warp stays together for the shuffles
   const int i = ch.at(t0 + qi);
   const float4 b = body[i];  // device copy, or the caller's pinned host buffer in pass 0 of the host-direct path
-  if (gl == 0 && act) s_body[row] = b;
+  if (gl == 0 && act) {
+    s_body[row] = b;
+    if (copy_body) const_cast<float4*>(a.body)[i] = b;  // host-direct pass 0: the finish phase reads the device copy
+  }
   const double pb[3] = {b.x, b.y, b.z};
   float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
   body_to_world(pc, pb, qv.x, qv.y, qv.z);
@@ -290,9 +293,13 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
 // 153-226) from the point's 5 neighbours (just found: shared memory; cached: a.near_pts with the sticky mask).
 template <bool SH>
 __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk<SH> ch,
-                                         int rows, bool search, const float4* s_nb,
+                                         int rows, int mode, const float4* s_nb,
                                          const int* s_cnt, double* s_rows, unsigned char* s_valid, const float4* s_body,
                                          bool copy_body) {
+  // mode 0: cached pass (plane of the last search pass); 1: the search tile just done (neighbours, gate and points in
+  // shared memory); 2: search pass of a block with several tiles, all searched before (neighbours and gate from the cache
+  // they were filed in, one thread per row for ROWS_MAX rows at a time instead of a quarter of that per search tile)
+  const bool search = mode != 0;
   const int row = threadIdx.x;
   if (row >= rows) return;
   if (t0 + row >= n) {
@@ -301,8 +308,8 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
   }
   const int i = ch.at(t0 + row);
   const unsigned short* list = SH ? ch.list : nullptr;
-  const float4 b = search ? s_body[row] : __ldcg(a.body + i);  // the search phase left it in shared memory
-  if (copy_body) const_cast<float4*>(a.body)[i] = b;            // host-direct path, pass 0: keep a device copy
+  const float4 b = mode == 1 ? s_body[row] : __ldcg(a.body + i);  // the search phase left it in shared memory
+  if (copy_body) const_cast<float4*>(a.body)[i] = b;               // host-direct path, pass 0: keep a device copy
   const double pb[3] = {b.x, b.y, b.z};
   float pwx, pwy, pwz;
   body_to_world(pc, pb, pwx, pwy, pwz);
@@ -315,9 +322,16 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
   bool sel;
   if (search) {
     float4 nb[LIO_K];
+    if (mode == 1) {
 #pragma unroll
-    for (int r = 0; r < LIO_K; ++r) nb[r] = s_nb[row * LIO_K + r];
-    sel = s_cnt[row] != 0;
+      for (int r = 0; r < LIO_K; ++r) nb[r] = s_nb[row * LIO_K + r];
+      sel = s_cnt[row] != 0;
+    } else {
+#pragma unroll
+      for (int r = 0; r < LIO_K; ++r) nb[r] = __ldcg(a.near_pts + (size_t)i * LIO_K + r);
+      // gate 1 as search_tile takes it (esekfom.hpp:144-147): five neighbours, the fifth within sqrt(5) m
+      sel = __ldcg(a.near_cnt + i) >= LIO_K && !(__ldcg(a.near_d2 + (size_t)i * LIO_K + (LIO_K - 1)) > 5.0f);
+    }
     if (sel) {
       sel = esti_plane(nb, a.plane_thr, pabcd);
       a.plane[i] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
@@ -1090,55 +1104,68 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
     cb = a.extrinsic_est ? c_ob_ext[o] : c_ob_no[o];
   }
   double acc = 0.0;
-  const int step = search ? THREADS / G : (n < ROWS_MAX ? max(n, 1) : ROWS_MAX);
+  // A block whose share is one search tile (the latency-bound bench case) searches and finishes it out of shared memory.
+  // With several tiles (dense scans, many sequences per launch) all of them are searched first and the rows are then
+  // finished ROWS_MAX at a time from the neighbour cache: one thread per row keeps 256 threads busy with the plane fits
+  // instead of THREADS / G (64) between every two searches.
+  const int sstep = THREADS / G;
+  const int mode = !search ? 0 : (n > sstep ? 2 : 1);
+  const int step = mode == 1 ? sstep : (n < ROWS_MAX ? max(n, 1) : ROWS_MAX);
 #pragma unroll 1
-  for (int t0 = 0; t0 < n; t0 += step) {
-    const int rows = step;
-    if (search) {
-      const int tend = min(n, t0 + step);
-      // the tile's queries (p_world, FP64 -> FP32) and, when staging, an empty cell set; the previous tile is done with
-      // the staging area
-      if (a.stage) {
-        for (int h = tid; h < ST_HASH; h += THREADS) st->key[h] = LIO_EMPTY_KEY;
-        if (tid == 0) {
-          st->n_list = 0;
-          st->n_pts = 0;
-          st->overflow = 0;
+  for (int phase = (mode == 2 ? 0 : 1); phase < 2; ++phase) {
+    const int pstep = phase == 0 ? sstep : step;
+#pragma unroll 1
+    for (int t0 = 0; t0 < n; t0 += pstep) {
+      const int rows = pstep;
+      if (phase == 0 || mode == 1) {
+        const int tend = min(n, t0 + sstep);
+        // the tile's queries (p_world, FP64 -> FP32) and, when staging, an empty cell set; the previous tile is done with
+        // the staging area
+        if (a.stage) {
+          for (int h = tid; h < ST_HASH; h += THREADS) st->key[h] = LIO_EMPTY_KEY;
+          if (tid == 0) {
+            st->n_list = 0;
+            st->n_pts = 0;
+            st->overflow = 0;
+          }
         }
-      }
-      bool use_stage = false;
-      if (a.stage) {
-        if (tid < tend - t0) {  // the staging needs the queries first; search_tile recomputes the same bits
-          const float4 b = body[ch.at(t0 + tid)];
-          const double pb[3] = {b.x, b.y, b.z};
-          float pwx, pwy, pwz;
-          body_to_world(ps->pc, pb, pwx, pwy, pwz);
-          ps->q[tid] = make_float4(pwx, pwy, pwz, 0.f);
+        bool use_stage = false;
+        if (a.stage) {
+          if (tid < tend - t0) {  // the staging needs the queries first; search_tile recomputes the same bits
+            const float4 b = body[ch.at(t0 + tid)];
+            const double pb[3] = {b.x, b.y, b.z};
+            float pwx, pwy, pwz;
+            body_to_world(ps->pc, pb, pwx, pwy, pwz);
+            ps->q[tid] = make_float4(pwx, pwy, pwz, 0.f);
+          }
+          __syncthreads();
+          stage_cells<THREADS>(a.map, st, ps->q, tend - t0, a.dbg);
+          use_stage = st->overflow == 0;
         }
+        const bool cp = from_host && mode == 2;
+        if (G == 32)
+          search_tile<32, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage, cp);
+        else if (G == 16)
+          search_tile<16, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage, cp);
+        else
+          search_tile<8, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage, cp);
         __syncthreads();
-        stage_cells<THREADS>(a.map, st, ps->q, tend - t0, a.dbg);
-        use_stage = st->overflow == 0;
+        if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
+        stamp(a.dbg, 0, 3);
       }
-      if (G == 32)
-        search_tile<32, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
-      else if (G == 16)
-        search_tile<16, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
-      else
-        search_tile<8, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage);
+      if (phase == 0) continue;
+      finish_tile<SH>(a, ps->pc, t0, n, ch, rows, mode, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row,
+                      from_host && mode == 1);
       __syncthreads();
-      if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
-      stamp(a.dbg, 0, 3);
-    }
-    finish_tile<SH>(a, ps->pc, t0, n, ch, rows, search, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row, from_host);
-    __syncthreads();
-    stamp(a.dbg, 0, 4);
-    if (seg < nseg) {
+      stamp(a.dbg, 0, 4);
+      if (seg < nseg) {
 #pragma unroll 1
-      for (int r = seg; r < rows; r += nseg)
-        if (ps->valid[r]) acc = fma(ps->rows[r * RS + ca], ps->rows[r * RS + cb], acc);
+        for (int r = seg; r < rows; r += nseg)
+          if (ps->valid[r]) acc = fma(ps->rows[r * RS + ca], ps->rows[r * RS + cb], acc);
+      }
+      __syncthreads();
+      stamp(a.dbg, 0, 5);
     }
-    __syncthreads();
-    stamp(a.dbg, 0, 5);
   }
   if (seg < nseg) ps->acc[seg * nout + o] = acc;
   __syncthreads();
