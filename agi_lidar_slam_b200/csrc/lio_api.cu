@@ -133,8 +133,6 @@ static int create_impl(lio_ctx* c) {
   ALLOC(c->d_near_d2, 4 * M * LIO_K);
   ALLOC(c->d_near_cnt, 4 * M);
   ALLOC(c->d_near_q, sizeof(float4) * M);
-  ALLOC(c->d_far_list, 4 * M);
-  ALLOC(c->d_far_n, 4);
   ALLOC(c->d_selected, M);
   ALLOC(c->d_normvec, sizeof(float4) * M);
   ALLOC(c->d_plane, sizeof(float4) * M);
@@ -157,6 +155,8 @@ static int create_impl(lio_ctx* c) {
     c->stage_search = env && atoi(env);
     const char* il = getenv("LIO_INTERLEAVE");
     c->interleave = il && atoi(il);
+    const char* bf = getenv("LIO_FINISH_BATCHED");
+    c->batched_finish = !(bf && !atoi(bf));
   }
   {
     const char* env = getenv("LIO_TIMELINE");
@@ -290,7 +290,7 @@ void lio_destroy(lio_ctx* c) {
                   c->map.counters, c->d_batch_pts,  c->d_batch_slot,  c->d_batch_rank,  c->d_batch_flag,
                   c->d_vox_best,  c->d_vox_key,     c->d_body,        c->d_world,
                   c->d_near,      c->d_near_d2,     c->d_near_cnt,    c->d_selected,    c->d_normvec,     c->d_plane,
-                  c->d_near_q,    c->d_far_list,    c->d_far_n,
+                  c->d_near_q,
                   c->d_partials,  c->d_blob_own,    c->d_cls,         c->d_add_a,
                   c->d_state_blk, c->d_prior,       c->d_dbg,         c->d_pub,         c->d_mailbox,
                   c->d_cloud,

@@ -22,6 +22,7 @@ struct lio_ctx {
   int32_t next_id = 0;     // id given to the next inserted point (host mirror)
   bool map_built = false;  // ≙ ikdtree.Root_Node != nullptr
   int knn_rings = 3;
+  bool batched_finish = true;   // LIO_FINISH_BATCHED=0: finish every search tile right behind its search
   bool interleave = false;      // LIO_INTERLEAVE=1: scan points dealt to the update's blocks in runs of 8 (load balance)
   bool stage_search = false;    // LIO_STAGE_SEARCH=1: the update's searches stage their cells in shared memory
   float map_downsample = 0.5f;  // ≙ KD_TREE::downsample_size (set_downsample_param, laserMapping.cpp:748)
@@ -44,8 +45,6 @@ struct lio_ctx {
   float* d_near_d2 = nullptr;       // M x 5
   int* d_near_cnt = nullptr;        // M: length of the row's known prefix of the unbounded neighbour list
   float4* d_near_q = nullptr;       // M: FP32 p_world the row was searched at
-  int* d_far_list = nullptr;        // M: rows handed to far_search_kernel
-  int* d_far_n = nullptr;           // their number
   uint8_t* d_selected = nullptr;    // M point_selected_surf
   float4* d_normvec = nullptr;      // M x (a,b,c,pd2)
   float4* d_plane = nullptr;        // M x pabcd fitted by the last search pass

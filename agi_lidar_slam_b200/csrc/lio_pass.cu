@@ -70,6 +70,7 @@ struct PassArgs {
   int rings;
   float own_min, own_max;
   int sharded;  // rows are shared out over the ranks (a finite window, or stripes)
+  int batched_finish;  // 0 (LIO_FINISH_BATCHED=0): blocks with several tiles finish each tile right after its search
   int interleave;  // LIO_INTERLEAVE=1: runs of 8 points dealt round-robin over the blocks also on one GPU (load balance)
   // striped ownership (lio_set_shard_stripes): the rank owns the stripes s = floor((x - origin) / width) with
   // s mod stripe_mod == stripe_rank; stripe_mod == 0: the window above
@@ -1109,7 +1110,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
   // finished ROWS_MAX at a time from the neighbour cache: one thread per row keeps 256 threads busy with the plane fits
   // instead of THREADS / G (64) between every two searches.
   const int sstep = THREADS / G;
-  const int mode = !search ? 0 : (n > sstep ? 2 : 1);
+  const int mode = !search ? 0 : ((n > sstep && a.batched_finish) ? 2 : 1);
   const int step = mode == 1 ? sstep : (n < ROWS_MAX ? max(n, 1) : ROWS_MAX);
 #pragma unroll 1
   for (int phase = (mode == 2 ? 0 : 1); phase < 2; ++phase) {
@@ -1529,30 +1530,20 @@ __global__ void __launch_bounds__(256) knn_batch_kernel(MapView map, const float
 // Unbounded completion of neighbour rows (esekfom.hpp:140-141: Nearest_Search gets no max_dist, so the reference's
 // Nearest_Points[i] holds min(5, #live points) neighbours however far away).  near_cnt[i] is the length of the row's
 // KNOWN PREFIX of that list: the bounded search of the update leaves the neighbours within d2 <= 5 (all of them when
-// it found five), far_search_kernel extends the rows listed by far_list_kernel to `need` entries.
+// it found five), far_search_kernel extends the short rows to `need` entries.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void far_list_kernel(const int* near_cnt, const int* scan_m, int m_value, int min_m, int need, int* list,
-                                int* n_list) {
+// One warp per block, rows dealt to the warps with the grid's stride: a warp looks at the count of each of its rows and
+// completes the short ones (they cluster in index -- a frontier is contiguous in voxel order -- and the stride spreads them
+// over the warps; no list, no second launch).
+__global__ void __launch_bounds__(32) far_search_kernel(MapView map, const float4* q, const int* scan_m, int m_value,
+                                                        int min_m, int need, float4* near_pts, float* near_d2,
+                                                        int* near_cnt) {
+  const int lane = threadIdx.x;  // (warp_knn_far synchronises the block)
   int M = m_value >= 0 ? m_value : *scan_m;
   if (M < min_m) M = 0;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool want = i < M && near_cnt[i] < need;
-  const unsigned b = __ballot_sync(0xffffffffu, want);
-  if (b == 0) return;
-  const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == 0) base = atomicAdd(n_list, __popc(b));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (want) list[base + __popc(b & ((1u << lane) - 1u))] = i;
-}
-
-__global__ void __launch_bounds__(32) far_search_kernel(MapView map, const float4* q, const int* list, const int* n_list,
-                                                        int need, float4* near_pts, float* near_d2, int* near_cnt) {
-  const int lane = threadIdx.x;  // one warp per block (warp_knn_far synchronises the block)
-  const int n = *n_list;
 #pragma unroll 1
-  for (int w = blockIdx.x; w < n; w += gridDim.x) {
-    const int i = list[w];
+  for (int i = blockIdx.x; i < M; i += gridDim.x) {
+    if (__ldcg(near_cnt + i) >= need) continue;  // block-uniform
     const float4 p = __ldg(q + i);
     unsigned long long key[LIO_K];
     uint32_t slot[LIO_K];
@@ -1685,6 +1676,7 @@ static PassArgs make_pass_args(lio_ctx* c, int ext, float own_min, float own_max
   a.sharded = (a.stripe_mod > 0 || !(own_min == -INFINITY && own_max == INFINITY)) ? 1 : 0;
   a.stage = c->stage_search ? 1 : 0;
   a.interleave = c->interleave ? 1 : 0;
+  a.batched_finish = c->batched_finish ? 1 : 0;
   a.partials = c->d_partials;
   a.dbg = c->d_dbg;
   if (c->d_dbg) cudaMemsetAsync(c->d_dbg, 0, 256 * sizeof(long long), c->stream);
@@ -1839,14 +1831,10 @@ int launch_begin(lio_ctx* c, int max_iter, int extrinsic_est, int from_snapshot)
 // scan size (a scan of fewer than min_m points counts as empty), `bound` rows at most.  Enqueue only.
 int launch_far_complete(lio_ctx* c, const float4* d_q, int64_t m, int min_m, int64_t bound, int need) {
   if (bound <= 0) return LIO_OK;
-  LIO_CHECK(c, cudaMemsetAsync(c->d_far_n, 0, sizeof(int), c->stream));
-  far_list_kernel<<<(int)((bound + 255) / 256), 256, 0, c->stream>>>(c->d_near_cnt, c->d_scan_m, m >= 0 ? (int)m : -1,
-                                                                      m >= 0 ? 0 : min_m, need, c->d_far_list,
-                                                                      c->d_far_n);
   const int grid = (int)std::min<int64_t>(bound, (int64_t)c->sm_count * 16);
-  far_search_kernel<<<grid, 32, 0, c->stream>>>(c->map, d_q, c->d_far_list, c->d_far_n, need, c->d_near, c->d_near_d2,
-                                                 c->d_near_cnt);
-  c->launches += 2;
+  far_search_kernel<<<grid, 32, 0, c->stream>>>(c->map, d_q, c->d_scan_m, m >= 0 ? (int)m : -1, m >= 0 ? 0 : min_m, need,
+                                                 c->d_near, c->d_near_d2, c->d_near_cnt);
+  c->launches += 1;
   LIO_CHECK(c, cudaGetLastError());
   return LIO_OK;
 }
