@@ -332,18 +332,16 @@ __global__ void __launch_bounds__(256) voxel_place_kernel(VoxelFilter vf, const 
 // 16-byte aligned and readable up to the next multiple of 16 behind m.
 __device__ __forceinline__ float chain_sum(float acc, const float* v, uint32_t m) {
   const float4* p = reinterpret_cast<const float4*>(v);
+  // the buffer is readable up to the next multiple of 16 behind m and the loads run a block ahead WITHOUT a condition (a
+  // predicated load waits for its predicate, i.e. for the loop counter): stale lanes are loaded and never added
   float4 c0 = p[0], c1 = p[1], c2 = p[2], c3 = p[3];
   uint32_t t = 0;
+  const uint32_t last = (m + 15u) / 16u * 4u;  // float4s that may be read
   for (; t + 16 <= m; t += 16) {
     p += 4;
-    const bool more = t + 16 < m;
-    float4 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
-    if (more) {
-      n0 = p[0];
-      n1 = p[1];
-      n2 = p[2];
-      n3 = p[3];
-    }
+    const uint32_t q = min((uint32_t)(t / 4 + 4), last - 4);  // clamped: re-reads the last block instead of running over
+    const float4* pn = reinterpret_cast<const float4*>(v) + q;
+    const float4 n0 = pn[0], n1 = pn[1], n2 = pn[2], n3 = pn[3];
     acc = acc + c0.x; acc = acc + c0.y; acc = acc + c0.z; acc = acc + c0.w;
     acc = acc + c1.x; acc = acc + c1.y; acc = acc + c1.z; acc = acc + c1.w;
     acc = acc + c2.x; acc = acc + c2.y; acc = acc + c2.z; acc = acc + c2.w;
@@ -429,10 +427,21 @@ __global__ void __launch_bounds__(256) voxel_centroid_kernel(const CentroidArgs 
       const uint32_t h = leaf.x, c = leaf.y, off = leaf.z;
       // span of the leaf's point indices
       uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-      for (uint32_t k0 = tid; k0 < c; k0 += 8 * 256) {
+      // the first VF_KEEP x 256 indices stay in registers for the marking below: one round trip for all of them (the
+      // longest leaf of an OS1-128 scan next to a wall has ~4,600 points), no reload
+      constexpr int VF_KEEP = 24;
+      uint32_t keep[VF_KEEP];
+#pragma unroll
+      for (int j = 0; j < VF_KEEP; ++j) keep[j] = __ldcg(vf.seg + off + min((uint32_t)tid + 256u * j, c - 1));  // (clamped: a repeat)
+#pragma unroll
+      for (int j = 0; j < VF_KEEP; ++j) {
+        lo = min(lo, keep[j]);
+        hi = max(hi, keep[j]);
+      }
+      for (uint32_t k0 = tid + 256u * VF_KEEP; k0 < c; k0 += 8 * 256) {
         uint32_t idx[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) idx[j] = __ldcg(vf.seg + off + min(k0 + 256u * j, c - 1));  // (clamped: a repeat)
+        for (int j = 0; j < 8; ++j) idx[j] = __ldcg(vf.seg + off + min(k0 + 256u * j, c - 1));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           lo = min(lo, idx[j]);
@@ -458,7 +467,12 @@ __global__ void __launch_bounds__(256) voxel_centroid_kernel(const CentroidArgs 
         const uint32_t nw = min((uint32_t)VF_WIN_WORDS, nwords - w0);
         for (uint32_t w = tid; w < nw; w += 256) s_bits[w] = 0u;
         __syncthreads();
-        for (uint32_t k0 = tid; k0 < c; k0 += 8 * 256) {  // eight loads in flight, then their marks
+#pragma unroll
+        for (int j = 0; j < VF_KEEP; ++j) {
+          const uint32_t w = (keep[j] >> 5) - wbase - w0;  // wraps to a large number below the window
+          if ((uint32_t)tid + 256u * j < c && w < nw) atomicOr(&s_bits[w], 1u << (keep[j] & 31));
+        }
+        for (uint32_t k0 = tid + 256u * VF_KEEP; k0 < c; k0 += 8 * 256) {  // eight loads in flight, then their marks
           uint32_t idx[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) idx[j] = __ldcg(vf.seg + off + min(k0 + 256u * j, c - 1));
