@@ -102,7 +102,7 @@ EXPORTS = [
     "lio_update_enqueue_multi", "lio_scan_step", "lio_scan_step_begin", "lio_scan_step_end",
     "lio_scan_step_finish", "lio_scan_step_prefetch", "lio_set_deferred_growth", "lio_scan_step_settle", "lio_update_begin", "lio_update_pass_enqueue", "lio_update_step_enqueue", "lio_blob_device_ptr",
     "lio_blob_download", "lio_blob_upload", "lio_blob_bind", "lio_peer_handle", "lio_peer_connect",
-    "lio_update_enqueue_sharded", "lio_peer_status", "lio_set_shard_stripes", "lio_map_removed_points", "lio_pass_only_enqueue", "lio_debug_timeline",
+    "lio_update_enqueue_sharded", "lio_peer_status", "lio_set_shard_stripes", "lio_map_removed_points", "lio_pass_only_enqueue", "lio_debug_timeline", "lio_debug_blocks",
     "lio_get_neighbors", "lio_map_incremental", "lio_map_build_scan", "lio_predict", "lio_boxplus", "lio_boxminus",
     "lio_imu_proc_init", "lio_imu_set_param", "lio_imu_process",
     "lio_seq_default_config", "lio_seq_create", "lio_seq_destroy", "lio_seq_process", "lio_seq_process_many",
@@ -177,6 +177,7 @@ def load_library() -> C.CDLL:
         "lio_set_shard_stripes": (C.c_int, [vp, f32, f32, C.c_int, C.c_int]),
         "lio_map_removed_points": (C.c_int, [vp, vp, C.c_int64, vp]),
         "lio_debug_timeline": (C.c_int, [vp, vp]),
+        "lio_debug_blocks": (C.c_int, [vp, vp]),
         "lio_get_neighbors": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "lio_map_incremental": (C.c_int, [vp, vp, f32, C.c_int, vp]),
         "lio_map_build_scan": (C.c_int, [vp, vp]),
@@ -528,6 +529,12 @@ class Context:
         b = [(int(t[129 + 2 * k]), int(t[130 + 2 * k])) for k in range(int(t[128]))]
         self.timeline_raw = t
         return a, b
+
+    def debug_blocks(self):
+        """Per-block times of the last pass (lio_debug_blocks): workers' rows filed, searches left, solver warps."""
+        t = np.zeros(768, np.int64)
+        self._check(self._lib.lio_debug_blocks(self._h, _ptr(t)))
+        return t
 
     def blob_download(self):
         b = np.zeros(BLOB, np.float64)

@@ -161,8 +161,8 @@ static int create_impl(lio_ctx* c) {
   {
     const char* env = getenv("LIO_TIMELINE");
     if (env && atoi(env)) {
-      ALLOC(c->d_dbg, 256 * sizeof(long long));
-      LIO_CHECK(c, cudaMemset(c->d_dbg, 0, 256 * sizeof(long long)));
+      ALLOC(c->d_dbg, 1024 * sizeof(long long));
+      LIO_CHECK(c, cudaMemset(c->d_dbg, 0, 1024 * sizeof(long long)));
     }
   }
   ALLOC(c->d_cls, M);
@@ -1220,6 +1220,18 @@ int lio_debug_timeline(lio_ctx* c, int64_t out[256]) {
   LIO_CHECK(c, cudaSetDevice(c->device));
   LIO_CHECK(c, cudaStreamSynchronize(c->stream));
   LIO_CHECK(c, cudaMemcpy(out, c->d_dbg, 256 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return LIO_OK;
+}
+
+int lio_debug_blocks(lio_ctx* c, int64_t out[768]) {
+  if (!c || !out) return LIO_E_INVALID;
+  if (!c->d_dbg) {
+    c->err = "timeline not enabled (set LIO_TIMELINE=1 before lio_create)";
+    return LIO_E_INVALID;
+  }
+  LIO_CHECK(c, cudaSetDevice(c->device));
+  LIO_CHECK(c, cudaStreamSynchronize(c->stream));
+  LIO_CHECK(c, cudaMemcpy(out, c->d_dbg + 256, 768 * sizeof(long long), cudaMemcpyDeviceToHost));
   return LIO_OK;
 }
 

@@ -100,6 +100,11 @@ __device__ __forceinline__ void stamp(long long* dbg, int base, int tag) {
   }
 }
 
+// per-block / per-warp times of the last pass (lio_debug_blocks): slot 256 + k of the timeline buffer
+__device__ __forceinline__ void stamp_slot(long long* dbg, int k) {
+  if (dbg != nullptr) dbg[256 + k] = global_ns();
+}
+
 struct SolveArgs {
   StateD* x;
   StateD* xprop;
@@ -449,6 +454,7 @@ __device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout,
     e[k] = a.extrinsic_est ? c_oe_ext[o[k]] : c_oe_no[o[k]];
     acc[k] = 0.0;
   }
+  const unsigned long long* a_partials = a.partials;  // (read once: the asm statements below clobber nothing)
 #pragma unroll 1
   for (int base = warp; base < nb; base += NW * CH) {
     // 1. wait: lane j watches ONE word of row j of the chunk until all of them have shown up.  Cheap (a few dozen
@@ -466,34 +472,45 @@ __device__ __forceinline__ void reduce_rows(const PassArgs& a, int nb, int nout,
       } while (!__all_sync(0xffffffffu, seen));
     }
     stamp(a.dbg, 128, 13);
-    // 2. load: one coalesced 16-byte load per output and row, all CH rows in flight; every word validates itself (the
-    //    other words of a row may lag a little behind the watched one: then simply once more)
-    double v[CH][KPL];
+    if (lane == 0) stamp_slot(a.dbg, 512 + warp);
+    // 2. load: one coalesced 16-byte load per output and row.  ALL the loads of the chunk are issued before the first
+    //    stamp is looked at (rows beyond the last one are clamped to it and dropped, so no load is conditional): with
+    //    the check behind every load the compiler waited for each pair of them, and the ten rows of a warp cost five
+    //    L2 round trips instead of one (2.3 us of every pass between "rows seen" and "rows loaded").  Every word
+    //    validates itself (the other words of a row may lag a little behind the watched one: then simply once more).
+    unsigned long long lo[CH][KPL], hi[CH][KPL];
     bool ready;
     do {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int b = base + NW * j;
+        const unsigned long long* rowp = a_partials + (size_t)(b < nb ? b : nb - 1) * ROW_WORDS;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k)
+          asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
+                       : "=l"(lo[j][k]), "=l"(hi[j][k])
+                       : "l"(rowp + 2 * o[k]));
+      }
       ready = true;
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
-        const int b = base + NW * j;  // the same for the whole warp: this branch does not split it
-        if (b < nb) {
+        const bool in = base + NW * j < nb;  // the same for the whole warp
 #pragma unroll
-          for (int k = 0; k < KPL; ++k) {
-            double x;
-            const bool ok = ld_stamped(a.partials + (size_t)b * ROW_WORDS + 2 * o[k], target, x);
-            v[j][k] = use[k] ? x : 0.0;
-            ready = ready && ok;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < KPL; ++k) v[j][k] = 0.0;
-        }
+        for (int k = 0; k < KPL; ++k)
+          ready = ready && (!in || ((unsigned)(lo[j][k] >> 32) == target && (unsigned)(hi[j][k] >> 32) == target));
       }
     } while (!__all_sync(0xffffffffu, ready));
+    if (lane == 0) stamp_slot(a.dbg, 544 + warp);
     // 3. add, in row order
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
+    for (int j = 0; j < CH; ++j) {
+      const bool in = base + NW * j < nb;
 #pragma unroll
-      for (int k = 0; k < KPL; ++k) acc[k] += v[j][k];
+      for (int k = 0; k < KPL; ++k) {
+        const double x = __longlong_as_double((long long)((hi[j][k] << 32) | (lo[j][k] & 0xffffffffull)));
+        acc[k] += (in && use[k]) ? x : 0.0;
+      }
+    }
   }
 #pragma unroll
   for (int k = 0; k < KPL; ++k)
@@ -508,9 +525,9 @@ __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool searc
   const int nb = dealt_runs(a, chunk_points(Ms, nworkers)) ? nworkers : workers_used(Ms, nworkers);
   const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
   if (a.extrinsic_est)
-    reduce_rows<3, 8>(a, nb, nout, target, s_warp);
+    reduce_rows<3, 5>(a, nb, nout, target, s_warp);
   else
-    reduce_rows<1, 32>(a, nb, nout, target, s_warp);  // 8 warps x 32 rows: (nearly) every worker row in one chunk
+    reduce_rows<1, 10>(a, nb, nout, target, s_warp);  // 16 warps x 10 rows: every worker row of a 148-SM grid in one chunk
   __syncthreads();
   if (tid < LIO_BLOB) {
     double sum = 0.0;
@@ -1153,6 +1170,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
         __syncthreads();
         if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
         stamp(a.dbg, 0, 3);
+        if (tid == THREADS - 1 && wid < 256) stamp_slot(a.dbg, 256 + wid);
       }
       if (phase == 0) continue;
       finish_tile<SH>(a, ps->pc, t0, n, ch, rows, mode, ps->nb, ps->cnt, ps->rows, ps->valid, ps->body_row,
@@ -1175,6 +1193,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
     for (int g = 0; g < nseg; ++g) sum += ps->acc[g * nout + tid];
     st_stamped(a.partials + (size_t)wid * ROW_WORDS + 2 * tid, sum, target);  // outputs back to back
   }
+  if (tid == THREADS - 1 && wid < 256) stamp_slot(a.dbg, wid);
   stamp(a.dbg, 0, 6);
 }
 

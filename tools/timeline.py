@@ -31,6 +31,22 @@ def show(name, tl):
         prev = t
 
 
+def spread(name, ctx, t_ref=None):
+    """Spread of the worker blocks and of the solver's warps in the last pass (lio_debug_blocks)."""
+    t = ctx.debug_blocks()
+    filed, left, seen, loaded = t[0:256], t[256:512], t[512:528], t[544:560]
+    f = filed[filed > 0]
+    t0 = f.min()
+    q = lambda v: "min %+.2f  p50 %+.2f  p90 %+.2f  max %+.2f us" % tuple((np.percentile(v, p) - t0) / 1000.0 for p in (0, 50, 90, 100))
+    print(f"   {name}: {len(f)} rows filed: {q(f)} (relative to the first row)")
+    l = left[left > 0]
+    if len(l):
+        print(f"      searches left: {q(l)}")
+    print("      ten last workers:", ", ".join("%d:%+.2f" % (b, (filed[b] - t0) / 1000.0) for b in np.argsort(filed)[-10:]))
+    print(f"      solver warps, rows seen:   {q(seen[seen > 0])}")
+    print(f"      solver warps, rows loaded: {q(loaded[loaded > 0])}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--map-points", type=int, default=2_000_000)
@@ -61,10 +77,12 @@ def main():
                      "top-5 merged", "neighbours published"]
             print("   query 0 of block 0: " + ", ".join("%s +%.2f us" % (nm, (r[240 + k] - r[239 + k]) / 1000.0)
                                                          for k, nm in enumerate(names)))
+            spread("search pass", ctx)
         ctx.pass_only_enqueue(False, False)
         tl = ctx.debug_timeline()
         if rep == 2:
             show("single cached pass (warm)", tl)
+            spread("cached pass", ctx)
     for rep in range(3):
         ctx.update_enqueue(0.001, 4, False, from_snapshot=True)
         tl = ctx.debug_timeline()
