@@ -56,6 +56,7 @@ struct TopK {
 //   4. the searches of the tile then stream their candidates from shared memory.
 // Every distinct bucket crosses L2 -> SM once per tile instead of once per query that needs it.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int KNN_CELLS = 32;   // cells of one round of a group's search (G lanes x ceil(27 / G) cells: 32 for G = 8, 16, 32)
 constexpr int ST_TILE = 64;     // queries per tile at most
 constexpr int ST_HASH = 2048;   // slots of the cell set (27 * ST_TILE = 1728 distinct cells at most)
 constexpr int ST_PTS = 4096;    // staged map points per tile (64 KB); a tile that needs more searches global memory
@@ -194,7 +195,7 @@ __device__ __noinline__ void stage_cells(const MapView& map, StageSmem* st, cons
 // tile) instead of global memory; the slots it reports then carry ST_FLAG and index st->pts.
 template <int G>
 __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy, float qz, float max_d2, int rings,
-                                          int gl, unsigned long long out_key[LIO_K],
+                                          int gl, uint2* cells, unsigned long long out_key[LIO_K],
                                           uint32_t out_slot[LIO_K], long long* dbg = nullptr,
                                           StageSmem* st = nullptr, int qi = 0) {
   constexpr int CPL = (27 + G - 1) / G;  // cells per lane and round
@@ -213,6 +214,8 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
   const int side = 2 * rings + 1;
   const int ncell = side * side * side;
   int nrounds = 1;
+  bool more = false;  // group-uniform: this query needs the rings beyond the 3x3x3 block
+  uint32_t total = 0;
 #pragma unroll 1
   for (int round = 0; round < nrounds; ++round) {
     if (round == 0 && st != nullptr) {
@@ -250,7 +253,7 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
         dx = c % side - rings;
         dy = (c / side) % side - rings;
         dz = c / (side * side) - rings;
-        take = c < ncell && !(dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1);
+        take = more && c < ncell && !(dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1);
         if (take) {
           const float lx = (float)(cx + dx) * map.cell, ly = (float)(cy + dy) * map.cell,
                       lz = (float)(cz + dz) * map.cell;
@@ -267,10 +270,9 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
         e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
       }
     }
-    // resolve the probes; the lane's buckets then form ONE virtual list [0, total): list index idx lives in pool slot
-    // base[u] + idx for the first u with idx < end[u]
-    uint32_t base[CPL], end[CPL];
-    uint32_t total = 0;
+    // resolve the probes
+    uint32_t bst[CPL], bcn[CPL];
+    uint32_t lsum = 0, lne = 0;  // the lane's candidates and non-empty cells
 #pragma unroll
     for (int u = 0; u < CPL; ++u) {
       uint32_t st = 0, cn = 0;
@@ -287,33 +289,72 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
           e[u] = __ldg(reinterpret_cast<const uint4*>(map.table + h[u]));
         }
       }
-      base[u] = st - total;
-      total += cn;
-      end[u] = total;
+      bst[u] = st;
+      bcn[u] = cn;
+      lsum += cn;
+      lne += cn > 0 ? 1u : 0u;
     }
     if (round == 0) mark(241);
-    // stream the list four points at a time, the next four already in flight while the current four are inserted
-    float4 cur[4], nxt[4];
-    auto slot_of = [&](uint32_t idx) -> uint32_t {
-      uint32_t b = base[CPL - 1];
+    // The buckets of the GROUP form one virtual list [0, total) (lane-major, then the lane's cells): a scan over the
+    // lanes gives every non-empty bucket its {end, base} (list index idx lives in pool slot base + idx of the first
+    // bucket with idx < end), filed in shared memory.  Lane gl then takes the indices gl, gl + G, ...: every lane gets
+    // the same number of candidates (+-1) whatever the cells hold -- dealt by CELLS, the lane that drew the full cells
+    // of a wall set the pace of the whole tile with twice the mean (measured on the bench scans: 4.7 rounds of four
+    // loads against 2.2) -- and the lanes of a group read consecutive points of a bucket in one request.
+    {
+      uint32_t isum = lsum, ine = lne;
 #pragma unroll
-      for (int u = CPL - 2; u >= 0; --u)
-        if (idx < end[u]) b = base[u];
-      return b + idx;
+      for (int off = 1; off < G; off <<= 1) {
+        const uint32_t ts = __shfl_up_sync(0xffffffffu, isum, off, G);
+        const uint32_t tn = __shfl_up_sync(0xffffffffu, ine, off, G);
+        if (gl >= off) {
+          isum += ts;
+          ine += tn;
+        }
+      }
+      total = __shfl_sync(0xffffffffu, isum, G - 1, G);
+      uint32_t ex = isum - lsum, pos = ine - lne;
+      if (round > 0) __syncwarp();  // the last round's list has been read
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) {
+        if (bcn[u] > 0) {
+          cells[pos] = make_uint2(ex + bcn[u], bst[u] - ex);
+          ++pos;
+          ex += bcn[u];
+        }
+      }
+      __syncwarp();
+    }
+    // stream the lane's share four points at a time, the next four already in flight while the current four are inserted
+    const uint32_t nl = total > (uint32_t)gl ? (total - (uint32_t)gl + G - 1) / G : 0u;
+    uint32_t cpos = 0;
+    uint2 ce = cells[0];  // (unused when total == 0)
+    auto slot_of = [&](uint32_t j) -> uint32_t {  // j-th candidate of the lane, j ascending over the calls
+      const uint32_t idx = (uint32_t)gl + j * G;
+      while (idx >= ce.x) ce = cells[++cpos];
+      return ce.y + idx;
     };
-    if (total > 0) {
+    float4 cur[4], nxt[4];
+    uint32_t cs[4], ns[4];
+    if (nl > 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = __ldg(map.pool + slot_of(min((uint32_t)j, total - 1)));
+      for (int j = 0; j < 4; ++j) {
+        cs[j] = slot_of(min((uint32_t)j, nl - 1));
+        cur[j] = __ldg(map.pool + cs[j]);
+      }
     }
 #pragma unroll 1
-    for (uint32_t t = 0; t < total; t += 4) {
-      if (t + 4 < total) {
+    for (uint32_t t = 0; t < nl; t += 4) {
+      if (t + 4 < nl) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) nxt[j] = __ldg(map.pool + slot_of(min(t + 4 + j, total - 1)));
+        for (int j = 0; j < 4; ++j) {
+          ns[j] = slot_of(min(t + 4 + j, nl - 1));
+          nxt[j] = __ldg(map.pool + ns[j]);
+        }
       }
       // distance of the four points first (no selects), against the lane's current 5th best: most candidates are
       // farther and never reach the insertion code, of which there is ONE copy
-      const uint32_t nj = min(4u, total - t);
+      const uint32_t nj = min(4u, nl - t);
       const uint32_t thr = min(max_bits, (uint32_t)(top.k4 >> 32));
       uint32_t db[4];
       unsigned pass = 0;
@@ -326,14 +367,17 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
       while (pass) {
         const int j = __ffs(pass) - 1;
         pass &= pass - 1;
-        uint32_t d = db[0], id = __float_as_uint(cur[0].w);
-        if (j == 1) { d = db[1]; id = __float_as_uint(cur[1].w); }
-        if (j == 2) { d = db[2]; id = __float_as_uint(cur[2].w); }
-        if (j == 3) { d = db[3]; id = __float_as_uint(cur[3].w); }
-        top.insert(((unsigned long long)d << 32) | id, slot_of(t + (uint32_t)j));
+        uint32_t d = db[0], id = __float_as_uint(cur[0].w), sl = cs[0];
+        if (j == 1) { d = db[1]; id = __float_as_uint(cur[1].w); sl = cs[1]; }
+        if (j == 2) { d = db[2]; id = __float_as_uint(cur[2].w); sl = cs[2]; }
+        if (j == 3) { d = db[3]; id = __float_as_uint(cur[3].w); sl = cs[3]; }
+        top.insert(((unsigned long long)d << 32) | id, sl);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      for (int j = 0; j < 4; ++j) {
+        cur[j] = nxt[j];
+        cs[j] = ns[j];
+      }
     }
     }
     if (round == 0) mark(242);
@@ -346,7 +390,9 @@ __device__ __forceinline__ int group_knn5(const MapView& map, float qx, float qy
       int seen = mine;
 #pragma unroll
       for (int off = G / 2; off > 0; off >>= 1) seen += __shfl_xor_sync(0xffffffffu, seen, off);
-      if (seen < LIO_K) nrounds = 1 + (ncell + G * CPL - 1) / (G * CPL);
+      // (the rounds hold warp-wide shuffles: the whole warp walks through them, the groups that are done with no cell)
+      more = seen < LIO_K;
+      if (__any_sync(0xffffffffu, more)) nrounds = 1 + (ncell + G * CPL - 1) / (G * CPL);
     }
   }
   mark(243);

@@ -243,7 +243,7 @@ __device__ __noinline__ int dealt_count(int M, int C, int nworkers, int wid) {
 // on the caller has staged the tile's neighbour cells (stage_cells); use_stage says whether the tile fitted.
 template <int G, bool SH>
 __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk<SH> ch,
-                                         float4* s_nb, int* s_cnt, float4* s_body,
+                                         float4* s_nb, int* s_cnt, float4* s_body, uint2* s_cells,
                                          const float4* body, StageSmem* st, bool use_stage, bool copy_body) {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
@@ -262,7 +262,8 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
   unsigned long long key[LIO_K];
   uint32_t slot[LIO_K];
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[239] = global_ns();
-  const int cnt = group_knn5<G>(a.map, qv.x, qv.y, qv.z, a.max_d2, a.rings, gl, key, slot, a.dbg, use_stage ? st : nullptr, qi);
+  const int cnt = group_knn5<G>(a.map, qv.x, qv.y, qv.z, a.max_d2, a.rings, gl, s_cells + row * KNN_CELLS, key, slot, a.dbg,
+                                use_stage ? st : nullptr, qi);
   if (!act) return;
   // lanes 0..4 of the group fetch and publish one neighbour each
   if (gl < LIO_K) {
@@ -1028,6 +1029,7 @@ struct __align__(16) PassSmem {
   int cnt[SROWS_MAX];            // gate 1 of the search phase
   float4 body_row[SROWS_MAX];    // the search tile's scan points, for its finish phase
   float4 q[SROWS_MAX];           // ... and their FP32 p_world: the queries
+  uint2 cells[SROWS_MAX * KNN_CELLS];  // group_knn5: {end, base} of the non-empty buckets of every group's round
   unsigned char valid[ROWS_MAX];
   double xrecv[15];  // worker_receive: the published x[0..13] and, in the low half of [14], the flags
   int flag;
@@ -1162,11 +1164,11 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
         }
         const bool cp = from_host && mode == 2;
         if (G == 32)
-          search_tile<32, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage, cp);
+          search_tile<32, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
         else if (G == 16)
-          search_tile<16, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage, cp);
+          search_tile<16, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
         else
-          search_tile<8, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, body, st, use_stage, cp);
+          search_tile<8, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
         __syncthreads();
         if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
         stamp(a.dbg, 0, 3);
@@ -1509,6 +1511,7 @@ __global__ void __launch_bounds__(THREADS) begin_kernel(const SolveArgs s, int e
 __global__ void __launch_bounds__(256) knn_batch_kernel(MapView map, const float4* q, int m, float max_d2, int rings,
                                                         float4* near_pts, float* near_d2, int* near_cnt) {
   constexpr int G = 8;
+  __shared__ uint2 s_cells[(256 / G) * KNN_CELLS];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
   const int gglobal = (blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -1521,7 +1524,7 @@ __global__ void __launch_bounds__(256) knn_batch_kernel(MapView map, const float
     const float4 p = __ldg(q + i);
     unsigned long long ok[LIO_K];
     uint32_t os[LIO_K];
-    const int f = group_knn5<G>(map, p.x, p.y, p.z, max_d2, rings, gl, ok, os);
+    const int f = group_knn5<G>(map, p.x, p.y, p.z, max_d2, rings, gl, s_cells + (threadIdx.x / G) * KNN_CELLS, ok, os);
     if (!act) continue;
     if (gl < LIO_K) {
       unsigned long long k = ok[0];
