@@ -34,6 +34,8 @@ def show(name, tl):
 def spread(name, ctx, t_ref=None):
     """Spread of the worker blocks and of the solver's warps in the last pass (lio_debug_blocks)."""
     t = ctx.debug_blocks()
+    if os.environ.get("LIO_TIMELINE_DUMP"):
+        np.save(os.environ["LIO_TIMELINE_DUMP"] + "_" + name.replace(" ", "_") + ".npy", t)
     filed, left, seen, loaded = t[0:256], t[256:512], t[512:528], t[544:560]
     f = filed[filed > 0]
     t0 = f.min()
@@ -42,6 +44,19 @@ def spread(name, ctx, t_ref=None):
     l = left[left > 0]
     if len(l):
         print(f"      searches left: {q(l)}")
+    if len(l):
+        dur = (filed - left)[filed > 0] / 1000.0
+        print("      by worker index (octiles), row filed after the first [us]:",
+              " ".join("%.1f" % ((filed[filed > 0][k::8].mean() - t0) / 1000.0) for k in range(1)),
+              "| mean over index ranges:", " ".join("%.1f" % ((c.mean() - t0) / 1000.0) for c in np.array_split(f, 8)))
+    first = t[576:768]
+    if len(l) and (first > 0).any():
+        order = np.argsort(filed)[-10:]
+        print("      first tile searched / all tiles searched / row filed of the ten last:",
+              ", ".join("%d: %+.1f %+.1f %+.1f" % (b, (first[b] - t0) / 1000.0, (left[b] - t0) / 1000.0, (filed[b] - t0) / 1000.0) for b in order))
+        order = np.argsort(filed)[:5]
+        print("      ... of the five first:",
+              ", ".join("%d: %+.1f %+.1f %+.1f" % (b, (first[b] - t0) / 1000.0, (left[b] - t0) / 1000.0, (filed[b] - t0) / 1000.0) for b in order if filed[b] > 0))
     print("      ten last workers:", ", ".join("%d:%+.2f" % (b, (filed[b] - t0) / 1000.0) for b in np.argsort(filed)[-10:]))
     print(f"      solver warps, rows seen:   {q(seen[seen > 0])}")
     print(f"      solver warps, rows loaded: {q(loaded[loaded > 0])}")
