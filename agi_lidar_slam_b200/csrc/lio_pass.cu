@@ -241,7 +241,7 @@ __device__ __noinline__ int dealt_count(int M, int C, int nworkers, int wid) {
 // Search phase of one tile: its queries (at most THREADS / G), one per G-lane group (esekfom.hpp:140).  The 5 neighbours
 // go to the cache the later passes read (a.near_*) and to shared memory for the finish phase of this tile.  With staging
 // on the caller has staged the tile's neighbour cells (stage_cells); use_stage says whether the tile fitted.
-template <int G, bool SH>
+template <int G, bool SH, bool STG>
 __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc, int t0, int n, const Chunk<SH> ch,
                                          float4* s_nb, int* s_cnt, float4* s_body, uint2* s_cells,
                                          const float4* body, StageSmem* st, bool use_stage, bool copy_body) {
@@ -263,7 +263,7 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
   uint32_t slot[LIO_K];
   if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[239] = global_ns();
   const int cnt = group_knn5<G>(a.map, qv.x, qv.y, qv.z, a.max_d2, a.rings, gl, s_cells + row * KNN_CELLS, key, slot, a.dbg,
-                                use_stage ? st : nullptr, qi);
+                                (STG && use_stage) ? st : nullptr, qi);
   if (!act) return;
   // lanes 0..4 of the group fetch and publish one neighbour each
   if (gl < LIO_K) {
@@ -278,7 +278,7 @@ __device__ __noinline__ void search_tile(const PassArgs& a, const PassConst& pc,
     float4 v = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
     float d = CUDART_INF_F;
     if (gl < cnt) {
-      v = (sl & ST_FLAG) ? st->pts[sl & ~ST_FLAG] : __ldg(a.map.pool + sl);
+      v = (STG && (sl & ST_FLAG)) ? st->pts[sl & ~ST_FLAG] : __ldg(a.map.pool + sl);
       d = __uint_as_float((uint32_t)(k >> 32));
     }
     s_nb[row * LIO_K + gl] = v;
@@ -417,7 +417,7 @@ __device__ __noinline__ void finish_tile(const PassArgs& a, const PassConst& pc,
 // memory, products accumulated by thread (output o, segment seg) over rows seg, seg + nseg, ... of every tile, then
 // the segments are combined in order and the block's partial blob is written to a.partials[blockIdx.x].
 struct PassSmem;
-template <bool SH>
+template <bool SH, bool STG>
 __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSmem* st, int nworkers, int wid,
                            bool first_pass, unsigned target);
 
@@ -1094,7 +1094,7 @@ __device__ __noinline__ void build_own_list(const PassArgs& a, PassSmem* ps, con
 // ps->pc holds the per-pass constants (the caller loads or computes them and synchronises the block).
 // Worker `wid` of `nworkers` runs its chunk of the scan (chunk_points) and leaves its partial blob, stamped `target`, in
 // row wid of a.partials; a worker whose chunk is empty writes nothing (the reduction knows: workers_used).
-template <bool SH>
+template <bool SH, bool STG>
 __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSmem* st, int nworkers, int wid,
                            bool first_pass, unsigned target) {
   const int tid = threadIdx.x;
@@ -1141,7 +1141,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
         const int tend = min(n, t0 + sstep);
         // the tile's queries (p_world, FP64 -> FP32) and, when staging, an empty cell set; the previous tile is done with
         // the staging area
-        if (a.stage) {
+        if (STG && a.stage) {
           for (int h = tid; h < ST_HASH; h += THREADS) st->key[h] = LIO_EMPTY_KEY;
           if (tid == 0) {
             st->n_list = 0;
@@ -1150,7 +1150,7 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
           }
         }
         bool use_stage = false;
-        if (a.stage) {
+        if (STG && a.stage) {
           if (tid < tend - t0) {  // the staging needs the queries first; search_tile recomputes the same bits
             const float4 b = body[ch.at(t0 + tid)];
             const double pb[3] = {b.x, b.y, b.z};
@@ -1164,13 +1164,13 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
         }
         const bool cp = from_host && mode == 2;
         if (G == 32)
-          search_tile<32, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
+          search_tile<32, SH, STG>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
         else if (G == 16)
-          search_tile<16, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
+          search_tile<16, SH, STG>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
         else
-          search_tile<8, SH>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
+          search_tile<8, SH, STG>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
         __syncthreads();
-        if (tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
+        if (STG && tid == 0 && a.stage) st->phase ^= 1;  // the mbarrier's next phase (read again only behind the next tile's barriers)
         stamp(a.dbg, 0, 3);
         if (tid == THREADS - 1 && wid < 256) stamp_slot(a.dbg, 256 + wid);
       }
@@ -1300,7 +1300,7 @@ __device__ __forceinline__ void worker_receive(const SolveArgs& s, PassSmem* ps,
 // (target = epoch + pass + 1): nothing is zeroed between launches and there is no fence on the per-pass path.
 // nblk / bid: size of the (sub-)grid that works on this update and this block's index in it -- the whole grid for a
 // single update, a slice of it when several independent sequences share one launch (update_kernel_multi).
-template <bool HOST, bool SH>
+template <bool HOST, bool SH, bool STG>
 __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& s, const unsigned epoch,
                                             const ShardArgs& sh, const HostPath& hp, const int nblk, const int bid) {
   extern __shared__ __align__(128) unsigned char smem_raw[];  // SMEM_PASS_BYTES
@@ -1348,7 +1348,7 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
   PassSmem& ps = *reinterpret_cast<PassSmem*>(smem_raw);
   StageSmem* st = reinterpret_cast<StageSmem*>(smem_raw + SMEM_STAGE_OFF);
   const int wid = bid;
-  if (tid == 0 && a.stage) {  // (without staging the area is not even allocated)
+  if (STG && tid == 0 && a.stage) {  // (without staging the area is not even allocated)
     mbar_init(&st->mbar, THREADS);
     st->phase = 0;
   }
@@ -1363,7 +1363,7 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
   bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
     const unsigned target = epoch + (unsigned)pass_no + 1u;
-    block_pass<SH>(a, search, &ps, st, nworkers, wid, pass_no == 0, target);
+    block_pass<SH, STG>(a, search, &ps, st, nworkers, wid, pass_no == 0, target);
     stamp(a.dbg, 0, 7);
     worker_receive(s, &ps, target, &ps.flag, wid);
     __syncthreads();
@@ -1409,19 +1409,32 @@ __device__ __forceinline__ void worker_receive(const SolveArgs& s, PassSmem* ps,
 
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const PassArgs a, const SolveArgs s,
                                                                             const unsigned epoch, const ShardArgs sh) {
-  update_body<false, false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x,
-                            (int)blockIdx.x);  // the host path is compiled out
+  update_body<false, false, false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x,
+                                   (int)blockIdx.x);  // the host path is compiled out
 }
 // the instantiation with ownership lists and dealt runs: sharded map (windows or stripes), or LIO_INTERLEAVE=1
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_sh(const PassArgs a, const SolveArgs s,
                                                                                const unsigned epoch, const ShardArgs sh) {
-  update_body<false, true>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x, (int)blockIdx.x);
+  update_body<false, true, false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x, (int)blockIdx.x);
 }
 // the same loop with the host-direct prologue / epilogue; its 4.9 KB of extra parameters are only paid by that path
 __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host(const PassArgs a, const SolveArgs s,
                                                                                  const unsigned epoch, const ShardArgs sh,
                                                                                  const __grid_constant__ HostPath hp) {
-  update_body<true, false>(a, s, epoch, sh, hp, (int)gridDim.x, (int)blockIdx.x);
+  update_body<true, false, false>(a, s, epoch, sh, hp, (int)gridDim.x, (int)blockIdx.x);
+}
+// LIO_STAGE_SEARCH=1: the same two kernels with the shared-memory staging of a search tile's neighbour cells compiled in
+// (stage_cells; measured slower than the direct search, DESIGN.md 4.1, so the default instantiations do not carry its
+// code: a pass runs straight-line code from a cold instruction cache and its registers are the kernel's)
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_stage(const PassArgs a, const SolveArgs s,
+                                                                                  const unsigned epoch, const ShardArgs sh) {
+  update_body<false, false, true>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x, (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host_stage(const PassArgs a, const SolveArgs s,
+                                                                                       const unsigned epoch,
+                                                                                       const ShardArgs sh,
+                                                                                       const __grid_constant__ HostPath hp) {
+  update_body<true, false, true>(a, s, epoch, sh, hp, (int)gridDim.x, (int)blockIdx.x);
 }
 
 // Several INDEPENDENT updates (different sequences, each with its own map, scan and filter: BASELINE.json config 4) in
@@ -1440,8 +1453,8 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_mult
   if (q >= m.n) return;  // left-over blocks when the grid does not divide evenly
   ShardArgs sh;
   sh.world = 1;
-  update_body<false, false>(m.a[q], m.s[q], m.epoch[q], sh, *reinterpret_cast<const HostPath*>(&m), per,
-                     (int)blockIdx.x - q * per);
+  update_body<false, false, false>(m.a[q], m.s[q], m.epoch[q], sh, *reinterpret_cast<const HostPath*>(&m), per,
+                                   (int)blockIdx.x - q * per);
 }
 
 // One pass at the state in s.x; the last block to finish reduces the partials into s.blob (same worker split and
@@ -1465,13 +1478,9 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
     if (tid == 0) {
       load_pass_const(s.x, ps.pc);
       ps.n_own = -1;  // (a launch per pass: the ownership list is rebuilt from a.near_q)
-      if (a.stage) {
-        mbar_init(&st->mbar, THREADS);
-        st->phase = 0;
-      }
     }
     __syncthreads();
-    block_pass<SH>(a, search, &ps, st, nworkers, (int)blockIdx.x, false, target);
+    block_pass<SH, false>(a, search, &ps, st, nworkers, (int)blockIdx.x, false, target);
   }
   __threadfence();
   __syncthreads();
@@ -1649,7 +1658,8 @@ int ensure_tables(lio_ctx* c) {
   }
   // the pass / update kernels carry {pass or solve state | staging area of the searches} in dynamic shared memory
   const void* big[] = {(const void*)update_kernel,       (const void*)update_kernel_sh,   (const void*)update_kernel_host,
-                       (const void*)update_kernel_multi, (const void*)pass_kernel<false>, (const void*)pass_kernel<true>};
+                       (const void*)update_kernel_multi, (const void*)pass_kernel<false>, (const void*)pass_kernel<true>,
+                       (const void*)update_kernel_stage, (const void*)update_kernel_host_stage};
   for (const void* f : big)
     LIO_CHECK(c, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PASS_BYTES));
   if (c->device < 64) g_tables_ready[c->device] = true;
@@ -1782,9 +1792,13 @@ int launch_update(lio_ctx* c, double R, int max_iter, int ext, int from_snapshot
   c->epoch += 40;  // > max_iter + 2
   void* args[] = {&a, &s, &epoch, &sh, &hp};
   const bool sh_code = a.sharded || a.interleave;  // (never with the host-direct path: launch_update's callers)
-  LIO_CHECK(c, cudaLaunchCooperativeKernel(hd != nullptr ? (const void*)update_kernel_host
-                                                         : (sh_code ? (const void*)update_kernel_sh : (const void*)update_kernel),
-                                           dim3(pass_grid_blocks(c)), dim3(THREADS), args, pass_smem_bytes(c), c->stream));
+  // staging (LIO_STAGE_SEARCH=1) exists for the unsharded single-sequence update only
+  const bool stg = a.stage && !sh_code;
+  a.stage = stg ? 1 : 0;
+  const void* fn = hd != nullptr ? (stg ? (const void*)update_kernel_host_stage : (const void*)update_kernel_host)
+                                 : (sh_code ? (const void*)update_kernel_sh
+                                            : (stg ? (const void*)update_kernel_stage : (const void*)update_kernel));
+  LIO_CHECK(c, cudaLaunchCooperativeKernel(fn, dim3(pass_grid_blocks(c)), dim3(THREADS), args, pass_smem_bytes(c), c->stream));
   c->launches++;
   return LIO_OK;
 }
