@@ -1030,6 +1030,7 @@ struct __align__(16) PassSmem {
   float4 body_row[SROWS_MAX];    // the search tile's scan points, for its finish phase
   float4 q[SROWS_MAX];           // ... and their FP32 p_world: the queries
   uint2 cells[SROWS_MAX * KNN_CELLS];  // group_knn5: {end, base} of the non-empty buckets of every group's round
+  unsigned short oab[THREADS];         // thread (output o, segment): row columns (a | b << 8) of its product (fill_oab)
   unsigned char valid[ROWS_MAX];
   double xrecv[15];  // worker_receive: the published x[0..13] and, in the low half of [14], the flags
   int flag;
@@ -1094,6 +1095,14 @@ __device__ __noinline__ void build_own_list(const PassArgs& a, PassSmem* ps, con
 // ps->pc holds the per-pass constants (the caller loads or computes them and synchronises the block).
 // Worker `wid` of `nworkers` runs its chunk of the scan (chunk_points) and leaves its partial blob, stamped `target`, in
 // row wid of a.partials; a worker whose chunk is empty writes nothing (the reduction knows: workers_used).
+// once per kernel, before the first pass (the caller synchronises the block)
+__device__ __forceinline__ void fill_oab(const PassArgs& a, PassSmem* ps) {
+  const int nout = a.extrinsic_est ? NOUT_EXT : NOUT_NOEXT;
+  const int o = threadIdx.x % nout;
+  ps->oab[threadIdx.x] = a.extrinsic_est ? (unsigned short)(c_oa_ext[o] | (c_ob_ext[o] << 8))
+                                          : (unsigned short)(c_oa_no[o] | (c_ob_no[o] << 8));
+}
+
 template <bool SH, bool STG>
 __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSmem* st, int nworkers, int wid,
                            bool first_pass, unsigned target) {
@@ -1120,8 +1129,10 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
   const int o = tid % nout, seg = tid / nout;
   int ca = 0, cb = 0;
   if (seg < nseg) {
-    ca = a.extrinsic_est ? c_oa_ext[o] : c_oa_no[o];
-    cb = a.extrinsic_est ? c_ob_ext[o] : c_ob_no[o];
+    // (from shared memory, filed once per kernel: indexed by thread, the constant bank serves a warp's 28 addresses one
+    // after the other -- 5 % of a pass's stall samples sat on these two loads)
+    ca = ps->oab[tid] & 0xff;
+    cb = ps->oab[tid] >> 8;
   }
   double acc = 0.0;
   // A block whose share is one search tile (the latency-bound bench case) searches and finishes it out of shared memory.
@@ -1359,6 +1370,7 @@ __device__ __forceinline__ void update_body(const PassArgs& a, const SolveArgs& 
     load_pass_const(x_first, ps.pc);  // pass 0 searches at the prior
     ps.n_own = -1;
   }
+  fill_oab(a, &ps);
   __syncthreads();
   bool search = true;
   for (int pass_no = 0; pass_no <= s.max_iter; ++pass_no) {
@@ -1479,6 +1491,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
       load_pass_const(s.x, ps.pc);
       ps.n_own = -1;  // (a launch per pass: the ownership list is rebuilt from a.near_q)
     }
+    fill_oab(a, &ps);
     __syncthreads();
     block_pass<SH, false>(a, search, &ps, st, nworkers, (int)blockIdx.x, false, target);
   }
