@@ -1419,32 +1419,32 @@ __device__ __forceinline__ void worker_receive(const SolveArgs& s, PassSmem* ps,
   }
 }
 
-__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const PassArgs a, const SolveArgs s,
-                                                                            const unsigned epoch, const ShardArgs sh) {
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel(const __grid_constant__ PassArgs a, const __grid_constant__ SolveArgs s,
+                                                                            const unsigned epoch, const __grid_constant__ ShardArgs sh) {
   update_body<false, false, false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x,
                                    (int)blockIdx.x);  // the host path is compiled out
 }
 // the instantiation with ownership lists and dealt runs: sharded map (windows or stripes), or LIO_INTERLEAVE=1
-__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_sh(const PassArgs a, const SolveArgs s,
-                                                                               const unsigned epoch, const ShardArgs sh) {
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_sh(const __grid_constant__ PassArgs a, const __grid_constant__ SolveArgs s,
+                                                                               const unsigned epoch, const __grid_constant__ ShardArgs sh) {
   update_body<false, true, false>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x, (int)blockIdx.x);
 }
 // the same loop with the host-direct prologue / epilogue; its 4.9 KB of extra parameters are only paid by that path
-__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host(const PassArgs a, const SolveArgs s,
-                                                                                 const unsigned epoch, const ShardArgs sh,
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host(const __grid_constant__ PassArgs a, const __grid_constant__ SolveArgs s,
+                                                                                 const unsigned epoch, const __grid_constant__ ShardArgs sh,
                                                                                  const __grid_constant__ HostPath hp) {
   update_body<true, false, false>(a, s, epoch, sh, hp, (int)gridDim.x, (int)blockIdx.x);
 }
 // LIO_STAGE_SEARCH=1: the same two kernels with the shared-memory staging of a search tile's neighbour cells compiled in
 // (stage_cells; measured slower than the direct search, DESIGN.md 4.1, so the default instantiations do not carry its
 // code: a pass runs straight-line code from a cold instruction cache and its registers are the kernel's)
-__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_stage(const PassArgs a, const SolveArgs s,
-                                                                                  const unsigned epoch, const ShardArgs sh) {
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_stage(const __grid_constant__ PassArgs a, const __grid_constant__ SolveArgs s,
+                                                                                  const unsigned epoch, const __grid_constant__ ShardArgs sh) {
   update_body<false, false, true>(a, s, epoch, sh, *reinterpret_cast<const HostPath*>(&a), (int)gridDim.x, (int)blockIdx.x);
 }
-__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host_stage(const PassArgs a, const SolveArgs s,
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_host_stage(const __grid_constant__ PassArgs a, const __grid_constant__ SolveArgs s,
                                                                                        const unsigned epoch,
-                                                                                       const ShardArgs sh,
+                                                                                       const __grid_constant__ ShardArgs sh,
                                                                                        const __grid_constant__ HostPath hp) {
   update_body<true, false, true>(a, s, epoch, sh, hp, (int)gridDim.x, (int)blockIdx.x);
 }
@@ -1473,7 +1473,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) update_kernel_mult
 // the same summation order as update_kernel, so the stepwise driver reproduces its bits).
 // mode: 0 cached, 1 search, -1 as the loop state says (sharded driver).
 template <bool SH>
-__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const PassArgs a, const SolveArgs s, int mode,
+__global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const __grid_constant__ PassArgs a, const __grid_constant__ SolveArgs s, int mode,
                                                                           unsigned target) {
   extern __shared__ __align__(128) unsigned char smem_raw[];  // SMEM_PASS_BYTES
   PassSmem& ps = *reinterpret_cast<PassSmem*>(smem_raw);
