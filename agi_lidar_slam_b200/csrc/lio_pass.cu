@@ -1514,7 +1514,7 @@ __global__ void __launch_bounds__(THREADS, LIO_BLOCKS_PER_SM) pass_kernel(const 
 }
 
 // Kalman step from the blob in s.blob (already summed over ranks by the sharded driver).
-__global__ void __launch_bounds__(THREADS) solve_kernel(const SolveArgs s, int extrinsic_est, unsigned target) {
+__global__ void __launch_bounds__(THREADS) solve_kernel(const __grid_constant__ SolveArgs s, int extrinsic_est, unsigned target) {
   __shared__ SolveSmem ss;
   if (s.ctrl->done) return;
   solve_load_inputs(s, &ss);
@@ -1523,7 +1523,7 @@ __global__ void __launch_bounds__(THREADS) solve_kernel(const SolveArgs s, int e
   block_step(s, extrinsic_est ? 12 : 6, &ss, target);
 }
 
-__global__ void __launch_bounds__(THREADS) begin_kernel(const SolveArgs s, int extrinsic_est) {
+__global__ void __launch_bounds__(THREADS) begin_kernel(const __grid_constant__ SolveArgs s, int extrinsic_est) {
   __shared__ SolveSmem ss;
   block_prior(s, extrinsic_est ? 12 : 6, &ss, reinterpret_cast<const double*>(s.from_snapshot ? s.x0 : s.x),
               s.from_snapshot ? s.P0 : s.P, s.from_snapshot != 0);
@@ -1579,7 +1579,7 @@ __global__ void __launch_bounds__(256) knn_batch_kernel(MapView map, const float
 // One warp per block, rows dealt to the warps with the grid's stride: a warp looks at the count of each of its rows and
 // completes the short ones (they cluster in index -- a frontier is contiguous in voxel order -- and the stride spreads them
 // over the warps; no list, no second launch).
-__global__ void __launch_bounds__(32) far_search_kernel(MapView map, const float4* q, const int* scan_m, int m_value,
+__global__ void __launch_bounds__(32) far_search_kernel(const __grid_constant__ MapView map, const float4* q, const int* scan_m, int m_value,
                                                         int min_m, int need, float4* near_pts, float* near_d2,
                                                         int* near_cnt) {
   const int lane = threadIdx.x;  // (warp_knn_far synchronises the block)
