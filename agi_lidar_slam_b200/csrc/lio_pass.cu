@@ -47,7 +47,8 @@ constexpr int NOUT_NOEXT = 28;   // 21 HtH (6x6 upper) + 6 Hth + count
 // compact output o -> (row column a, row column b): the accumulated quantity is sum_rows row[a] * row[b]
 __constant__ unsigned char c_oa_ext[NOUT_EXT], c_ob_ext[NOUT_EXT], c_oe_ext[NOUT_EXT];
 __constant__ unsigned char c_oa_no[NOUT_NOEXT], c_ob_no[NOUT_NOEXT], c_oe_no[NOUT_NOEXT];
-__constant__ unsigned char c_is_no[78];  // 1 where the HtH entry is one of the 21 kept without extrinsic estimation
+__constant__ unsigned long long c_is_no[2];  // bit e set where HtH entry e (< 78) is one of the 21 kept without extrinsic estimation
+                                             // (a mask, not a table: read with a uniform address, the constant bank serves it in one go)
 
 struct PassArgs {
   const float4* body;
@@ -532,7 +533,7 @@ __device__ __noinline__ void block_reduce_partials(const PassArgs& a, bool searc
   __syncthreads();
   if (tid < LIO_BLOB) {
     double sum = 0.0;
-    const int o_valid = a.extrinsic_est ? 1 : ((tid < 78 && c_is_no[tid]) || (tid >= 78 && tid < 84) || tid == 90);
+    const int o_valid = a.extrinsic_est ? 1 : ((tid < 78 && ((c_is_no[tid >> 6] >> (tid & 63)) & 1ull)) || (tid >= 78 && tid < 84) || tid == 90);
     if (tid < 91 && o_valid) {
 #pragma unroll
       for (int w = 0; w < THREADS / 32; ++w) sum += s_warp[w * LIO_BLOB + tid];
@@ -1664,10 +1665,9 @@ int ensure_tables(lio_ctx* c) {
   LIO_CHECK(c, cudaMemcpyToSymbol(c_ob_no, nb, NOUT_NOEXT));
   LIO_CHECK(c, cudaMemcpyToSymbol(c_oe_no, ne, NOUT_NOEXT));
   {
-    unsigned char is_no[78];
-    memset(is_no, 0, sizeof(is_no));
-    for (int i = 0; i < 21; ++i) is_no[ne[i]] = 1;
-    LIO_CHECK(c, cudaMemcpyToSymbol(c_is_no, is_no, 78));
+    unsigned long long is_no[2] = {0ull, 0ull};
+    for (int i = 0; i < 21; ++i) is_no[ne[i] >> 6] |= 1ull << (ne[i] & 63);
+    LIO_CHECK(c, cudaMemcpyToSymbol(c_is_no, is_no, sizeof(is_no)));
   }
   // the pass / update kernels carry {pass or solve state | staging area of the searches} in dynamic shared memory
   const void* big[] = {(const void*)update_kernel,       (const void*)update_kernel_sh,   (const void*)update_kernel_host,
