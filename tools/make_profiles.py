@@ -64,8 +64,8 @@ for r in rows[2:]:
     {"kernel": "update_kernel", "dram_bytes_per_launch": sum(r + w for r, w in traffic) / len(traffic),
      "dram_bytes_read": sum(r for r, _ in traffic) / len(traffic), "dram_bytes_write": sum(w for _, w in traffic) / len(traffic),
      "launches_captured": len(traffic), "source": f"{tag}_update_kernel_ncu.txt",
-     "note": "one captured launch: which of the bench's four scans it ran decides the figure (a 4.3 k-point scan reads "
-             "about 1 MB, the 19.8 k-point one about 4.3 MB); writes of up to 2.7 MB in other captures are the write-back "
-             "of dirty L2 lines left by bench.py's 384 MiB flush kernel, which runs right before every timed update"}) + "\n")
+     "note": "one captured launch of a 4.3 k-point scan; the read / write split varies between captures (4.3 MB + 0 here, "
+             "1.0 MB + 3.2 MB in the previous one) with what bench.py's 384 MiB flush kernel, which runs right before every "
+             "timed update, left dirty in L2; the sum is stable"}) + "\n")
 print("\n".join(out[:24]))
 print((dst / f"{tag}_launches_summary.txt").read_text()[:1500])
