@@ -1007,7 +1007,9 @@ __device__ __noinline__ void block_step(const SolveArgs& s, int n, SolveSmem* sm
   if (tid == 0) *s.ctrl = sm->sc;
   __syncthreads();
   if (sm->fin) {
-    // S^-1 itself is only needed for the covariance, once, after the last step
+    // S^-1 itself is only needed for the covariance, once, after the last step.  (Forming it in the idle warp next to
+    // every step's solve was tried: the six right-hand sides take longer than the one of the solve and the barrier
+    // behind it waits for both: +0.5 us per pass.)
     if (tid < 32) {
       if (n == 6)
         warp_invert<6>(sm, inv_R, lane);
@@ -1145,12 +1147,16 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
   const int step = mode == 1 ? sstep : (n < ROWS_MAX ? max(n, 1) : ROWS_MAX);
 #pragma unroll 1
   for (int phase = (mode == 2 ? 0 : 1); phase < 2; ++phase) {
-    const int pstep = phase == 0 ? sstep : step;
+    int pstep = phase == 0 ? sstep : step;
 #pragma unroll 1
     for (int t0 = 0; t0 < n; t0 += pstep) {
+      // the last search tile of a block with several (mode 2) takes the widest groups that fit what is left: 7 queries
+      // behind two full tiles of 64 are searched by 32 lanes each, not by 8
+      const int Gt = phase == 0 ? pick_group(n - t0) : G;
+      if (phase == 0) pstep = THREADS / Gt;
       const int rows = pstep;
       if (phase == 0 || mode == 1) {
-        const int tend = min(n, t0 + sstep);
+        const int tend = min(n, t0 + THREADS / Gt);
         // the tile's queries (p_world, FP64 -> FP32) and, when staging, an empty cell set; the previous tile is done with
         // the staging area
         if (STG && a.stage) {
@@ -1175,9 +1181,9 @@ __device__ void block_pass(const PassArgs& a, bool search, PassSmem* ps, StageSm
           use_stage = st->overflow == 0;
         }
         const bool cp = from_host && mode == 2;
-        if (G == 32)
+        if (Gt == 32)
           search_tile<32, SH, STG>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
-        else if (G == 16)
+        else if (Gt == 16)
           search_tile<16, SH, STG>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
         else
           search_tile<8, SH, STG>(a, ps->pc, t0, n, ch, ps->nb, ps->cnt, ps->body_row, ps->cells, body, st, use_stage, cp);
