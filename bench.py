@@ -695,6 +695,53 @@ def sharded_leg(args, rank, world, local, dev, torch, dist, _cabi):
 
 
 # ------------------------------------------------------------------------------------------ extra legs at N = 1
+def cell_count_grid(mp, cell=1.5):
+    """Points per kNN cell of a map as a dense array over its bounding grid (None when that would not fit)."""
+    try:
+        inv = np.float32(1.0 / cell)
+        ck = np.floor(mp[:, :3] * inv).astype(np.int32)
+        lo = ck.min(0) - 1
+        dim = (ck.max(0) + 2 - lo).astype(np.int64)
+        ncell = int(dim[0] * dim[1] * dim[2])
+        if ncell > 400_000_000:
+            return None
+        lin = (ck[:, 0] - lo[0]).astype(np.int64) + dim[0] * ((ck[:, 1] - lo[1]).astype(np.int64) + dim[1] * (ck[:, 2] - lo[2]).astype(np.int64))
+        return {"counts": np.bincount(lin, minlength=ncell).astype(np.int32), "lo": lo, "dim": dim, "inv": inv, "cell": cell}
+    except (MemoryError, ValueError):
+        return None
+
+
+def knn_stream_model(grid, queries, sample=20000):
+    """SURVEY.md 8(d)'s candidate-streaming model next to the measured bytes: B_knn_stream = 16 + 16 C + 20 bytes per query,
+    C = mean number of candidates a query examines = the points in the 27 cells of its 3x3x3 block (host arithmetic on the
+    same map and a sample of the same queries)."""
+    if grid is None:
+        return None
+    counts, lo, dim = grid["counts"], grid["lo"], grid["dim"]
+    qs = queries[:: max(1, len(queries) // sample)]
+    qc = np.floor(qs[:, :3] * grid["inv"]).astype(np.int64) - lo
+    qc = qc[np.all((qc >= 1) & (qc < dim - 1), axis=1)]
+    if len(qc) == 0:
+        return None
+    cand = np.zeros(len(qc), np.int64)
+    occ = np.zeros(len(qc), np.int64)
+    sect = np.zeros(len(qc), np.int64)
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                c = counts[(qc[:, 0] + dx) + dim[0] * ((qc[:, 1] + dy) + dim[1] * (qc[:, 2] + dz))].astype(np.int64)
+                cand += c
+                occ += c > 0
+                sect += np.where(c > 0, (c * 16 + 63) // 64 + 1, 0)  # 64-byte DRAM bursts a bucket touches (unaligned: one more)
+    C = float(cand.mean())
+    return {"cell_m": grid["cell"], "queries_sampled": int(len(qc)), "candidates_per_query_mean": C,
+            "occupied_cells_of_27_mean": float(occ.mean()), "B_knn_stream_bytes_per_query": 16 + 16 * C + 20,
+            "B_bursts_bytes_per_query": float(27 * 64 + 64 * sect.mean()),
+            "what": "B_knn_stream = 16 (query) + 16 C (candidates streamed) + 20 (ids out), C = points in the query's 27 cells; "
+                    "B_bursts = what a query without any sharing must move at the 64-byte granularity of a DRAM burst: 27 hash "
+                    "probes (16 bytes used of each) + the bursts its occupied buckets touch"}
+
+
 def knn_hbm_leg(args, local, dev, torch, _cabi):
     """The search kernel against HBM (north_star: achieved bandwidth of the kNN kernel): batched 5-NN on a 50M-point map
     (800 MB of points + the cell table: far beyond L2), 1M queries per launch, CUDA events.  queries/s is measured here;
@@ -736,6 +783,7 @@ def knn_hbm_leg(args, local, dev, torch, _cabi):
         k += 1
     q_scans = np.ascontiguousarray(np.concatenate(parts)[:nqs])
     out["scans_in_launch"] = k
+    grid = cell_count_grid(mp)
     for name, qq in (("random", q), ("scans", q_scans)):
         n = len(qq)
         ctx._check(ctx._lib.lio_knn5(ctx._h, qq.ctypes.data, n, 5.0, None, None, None))  # queries -> device
@@ -756,6 +804,11 @@ def knn_hbm_leg(args, local, dev, torch, _cabi):
             leg["frac_of_hbm_peak"] = leg["dram_GBps"] / peak
             leg["ncu_ms_per_launch"] = c["ms_per_launch"]
             leg["lts_hit_pct"], leg["l1tex_hit_pct"] = c.get("lts_hit_pct"), c.get("l1tex_hit_pct")
+        m = knn_stream_model(grid, qq)
+        if m:
+            leg["stream_model"] = m
+            if "dram_bytes_per_query" in leg:
+                leg["dram_bytes_over_model"] = leg["dram_bytes_per_query"] / m["B_knn_stream_bytes_per_query"]
         out[name] = leg
     out["traffic_source"] = "profiles/r2_knn_hbm.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of knn_batch_kernel)" if cap else None
     out["peak"], out["peak_source"] = peak, peak_src
