@@ -23,3 +23,26 @@ def test_reference_arm_line_has_the_contract_keys():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None
+
+
+def test_knn_stream_model_counts_the_candidates_of_a_3x3x3_block():
+    """bench.py's candidate-streaming model (B_knn_stream = 16 + 16 C + 20) against a brute-force count."""
+    import numpy as np
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    rng = np.random.default_rng(7)
+    mp = rng.uniform(-20, 20, (40000, 3)).astype(np.float32)
+    q = rng.uniform(-10, 10, (500, 3)).astype(np.float32)
+    grid = bench.cell_count_grid(mp, cell=1.5)
+    m = bench.knn_stream_model(grid, q, sample=len(q))
+    inv = np.float32(1.0 / 1.5)
+    ck = np.floor(mp * inv).astype(np.int64)
+    qc = np.floor(q * inv).astype(np.int64)
+    cand = np.array([np.count_nonzero(np.all(np.abs(ck - c) <= 1, axis=1)) for c in qc])
+    assert m["queries_sampled"] == len(q)
+    assert abs(m["candidates_per_query_mean"] - cand.mean()) < 1e-9
+    assert abs(m["B_knn_stream_bytes_per_query"] - (36 + 16 * cand.mean())) < 1e-6
+    assert m["B_bursts_bytes_per_query"] >= 27 * 64
+    assert bench.knn_stream_model(None, q) is None
