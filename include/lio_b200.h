@@ -300,7 +300,8 @@ int lio_pass_only_enqueue(lio_ctx* ctx, int do_search, int extrinsic_est);
  * the block that ran the Kalman step from out[129] on.  Tags are listed in csrc/lio_pass.cu. */
 int lio_debug_timeline(lio_ctx* ctx, int64_t out[256]);
 /* Instrumentation (LIO_TIMELINE=1), the spread over the blocks in the last pass that ran: out[b] = ns at which worker
- * block b filed its partial row (b < 256), out[256 + b] = ns at which it left its search tiles (0 in a cached pass),
+ * block b filed its partial row (b < 256), out[256 + b] = ns at which it left its search tiles (a cached pass leaves the
+ * last search pass's value),
  * out[512 + w] = ns at which warp w of the solving block had seen its rows, out[544 + w] = had loaded them. */
 int lio_debug_blocks(lio_ctx* ctx, int64_t out[768]);
 /* Device pointer of the 92-double reduction blob {HtH 78, Hth 12, n_valid, n_searched} written by pass_enqueue. */
